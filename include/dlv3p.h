@@ -1,0 +1,205 @@
+/*
+ * dlv3p.h — C ABI of libdlv3p.so: the DeepLabV3+ encoder head (ASPP / ASPP-Lite /
+ * Decoder / prediction tail) as hand-written sm_100a CUDA kernels.
+ *
+ * The reference (david8862/tf-keras-deeplabv3p-model-set) has NO native / FFI
+ * interface for this path: it is three Python graph-builder functions plus six
+ * lines of tail code executed by TensorFlow.  Each entry point below therefore
+ * cites the reference *Python* site it stands in for:
+ *
+ *   ASPP_block(x, OS)                deeplabv3p/models/layers.py:114-163
+ *   ASPP_Lite_block(x)               deeplabv3p/models/layers.py:166-196
+ *   Decoder_block(x, skip)           deeplabv3p/models/layers.py:199-219
+ *   SepConv_BN(...)                  deeplabv3p/models/layers.py:74-111
+ *   tail: conv_upsample/pred_resize/Softmax   deeplabv3p/model.py:75-86
+ *   host argmax                      deeplab.py:99, eval.py:35,
+ *                                    inference/MNN/deeplabSegment.cpp:160-169
+ *   weight loading                   deeplabv3p/model.py:102-103 (Keras layer names,
+ *                                    SURVEY.md §8(b) table)
+ *
+ * Conventions: every function returns 0 (DLV3P_OK) or a negative dlv3p_status;
+ * nothing throws, nothing aborts.  A context is bound to one CUDA device and is
+ * NOT thread-safe.  All tensors are NHWC.  Device pointers are owned by the
+ * caller; kernels are enqueued asynchronously on the stream given.
+ * There is no CPU fallback: without a sm_100 device dlv3p_create fails with
+ * DLV3P_ERR_CUDA / DLV3P_ERR_UNSUPPORTED.
+ */
+#ifndef DLV3P_H_
+#define DLV3P_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DLV3P_ABI_VERSION 1
+
+typedef enum dlv3p_status {
+  DLV3P_OK = 0,
+  DLV3P_ERR_INVALID = -1,     /* bad argument / config (reference: ValueError, layers.py:126) */
+  DLV3P_ERR_CUDA = -2,        /* CUDA runtime / driver error, see dlv3p_last_error */
+  DLV3P_ERR_UNSUPPORTED = -3, /* valid request this build does not implement */
+  DLV3P_ERR_STATE = -4,       /* call order (forward before finalize, ...) */
+  DLV3P_ERR_NOMEM = -5,
+  DLV3P_ERR_NAME = -6         /* unknown layer / variable name, or shape mismatch */
+} dlv3p_status;
+
+/* which blocks of the head run (bitmask). Mirrors the reference call sites:
+ * constructors call ASPP_block then Decoder_block (deeplabv3p_xception.py:212-215),
+ * model.py:75-86 appends the tail. */
+enum {
+  DLV3P_STAGE_ASPP = 1,    /* ASPP_block or ASPP_Lite_block (variant) */
+  DLV3P_STAGE_DECODER = 2, /* Decoder_block */
+  DLV3P_STAGE_TAIL = 4     /* conv_upsample + pred_resize (+Softmax / argmax) */
+};
+
+enum { /* variant */
+  DLV3P_VARIANT_ASPP = 0,     /* full ASPP (layers.py:114) */
+  DLV3P_VARIANT_ASPP_LITE = 1 /* ASPP Lite (layers.py:166) */
+};
+
+enum { /* in_dtype of the feature / skip tensors handed to forward */
+  DLV3P_DTYPE_BF16 = 0,
+  DLV3P_DTYPE_FP32 = 2 /* converted to bf16 on device by a cast kernel */
+};
+
+enum { /* out_mode: what forward writes to d_out */
+  DLV3P_OUT_LABELS_U8 = 0,      /* uint8 [B,H,W]: argmax(resize(logits)), first-max ties  (model.py:76 + deeplab.py:99) */
+  DLV3P_OUT_LOGITS_LOWRES = 1,  /* fp32 [B,NC,ho,wo] PLANAR, classifier output before pred_resize (model.py:75) */
+  DLV3P_OUT_SOFTMAX = 2,        /* fp32 [B,H,W,NC]: the reference model output 'pred_mask' (model.py:86) */
+  DLV3P_OUT_LOGITS_FULL = 3,    /* fp32 [B,H,W,NC]: pred_resize output (model.py:76) */
+  DLV3P_OUT_FEATURES_BF16 = 4,  /* bf16 NHWC feature map of the last enabled block (no TAIL stage) */
+  DLV3P_OUT_FEATURES_FP32 = 5   /* fp32 NHWC feature map of the last enabled block (no TAIL stage) */
+};
+
+enum { /* flags */
+  DLV3P_FLAG_UNFUSED_DECODER = 1, /* run the decoder depthwise convs as standalone kernels (A/B + debugging) */
+  DLV3P_FLAG_NO_GRAPH = 2         /* reserved */
+};
+
+typedef struct dlv3p_config {
+  int32_t B;            /* batch */
+  int32_t H, W;         /* model input size (pred_resize target; model.py:76) */
+  int32_t OS;           /* output stride 8/16/32 -> atrous rates (layers.py:118-126) */
+  int32_t h, w;         /* backbone feature size; 0 -> ceil(H/OS), ceil(W/OS) */
+  int32_t hs, ws;       /* skip feature size;     0 -> ceil(H/4),  ceil(W/4)  */
+  int32_t Cin;          /* backbone feature channels (multiple of 8) */
+  int32_t Cskip;        /* skip channels (multiple of 8; ignored without DECODER) */
+  int32_t NC;           /* classes (1..256) */
+  int32_t variant;      /* DLV3P_VARIANT_* */
+  int32_t stages;       /* DLV3P_STAGE_* bitmask; 0 -> ASPP|DECODER|TAIL (ASPP|TAIL for Lite) */
+  int32_t in_dtype;     /* DLV3P_DTYPE_* */
+  int32_t out_mode;     /* DLV3P_OUT_* */
+  float   bn_eps;       /* head BatchNorm epsilon; 0 -> 1e-5 (layers.py:136 etc.) */
+  int32_t flags;        /* DLV3P_FLAG_* */
+} dlv3p_config;
+
+typedef struct dlv3p_ctx dlv3p_ctx; /* opaque */
+
+/* --- life cycle -------------------------------------------------------------------- */
+int dlv3p_abi_version(void);
+
+/* Builds a context on CUDA device `device`; allocates the workspace.  Replaces the graph
+ * construction done by ASPP_block/Decoder_block (layers.py:114-219) + model.py:75-86.
+ * device == -1 builds a PLAN-ONLY context: config validation, the weight inventory and the size queries
+ * work (host-side tests), finalize / forward / read_tap return DLV3P_ERR_STATE — there is no CPU path. */
+int dlv3p_create(const dlv3p_config* cfg, int device, dlv3p_ctx** out);
+void dlv3p_destroy(dlv3p_ctx* ctx);
+
+/* Thread-local message for ctx==NULL, else the context's last error. Never NULL. */
+const char* dlv3p_last_error(const dlv3p_ctx* ctx);
+
+/* --- weights (Keras layout, reference layer names; model.py:102-103) ------------------
+ * layer: e.g. "aspp1_depthwise", "aspp1_depthwise_BN", "concat_projection", "conv_upsample"
+ *        ("logits_semantic" is accepted as an alias, deeplabv3p_xception.py:218).
+ * var:   "kernel" (1,1,K,N) | "depthwise_kernel" (3,3,C,1) | "bias" (N) |
+ *        "gamma" | "beta" | "moving_mean" | "moving_variance" (C).
+ * host_fp32 is copied; shape is checked against the config. */
+int dlv3p_set_weight(dlv3p_ctx* ctx, const char* layer, const char* var,
+                     const float* host_fp32, const int64_t* shape, int rank);
+
+/* Number of weight tensors the configured stages expect, and the i-th (layer,var,shape) in
+ * Keras creation order — the order load_weights(by_name=False) relies on (model.py:103). */
+int dlv3p_num_weights(const dlv3p_ctx* ctx);
+int dlv3p_weight_info(const dlv3p_ctx* ctx, int index, const char** layer, const char** var,
+                      int64_t shape_out[4], int* rank_out);
+
+/* Folds BatchNorm (inference form), packs weights (bf16, K-major, zero padded), uploads.
+ * Fails with DLV3P_ERR_STATE if a weight is missing. */
+int dlv3p_finalize_weights(dlv3p_ctx* ctx);
+
+/* --- forward ------------------------------------------------------------------------
+ * d_feat: [B,h,w,Cin] (ASPP stage on) or [B,h,w,256] (DECODER first) or [B,hs,ws,256] (TAIL only)
+ * d_skip: [B,hs,ws,Cskip] or NULL when the DECODER stage is off
+ * d_out : per out_mode; size from dlv3p_output_bytes.
+ * Asynchronous on `cuda_stream` (a cudaStream_t; NULL = default stream). */
+int dlv3p_forward(dlv3p_ctx* ctx, const void* d_feat, const void* d_skip, void* d_out,
+                  void* cuda_stream);
+
+/* Same call with HOST buffers (pageable or pinned): H2D copies, forward, D2H copy, and a
+ * stream synchronize — the end-to-end path model.predict()+np.argmax takes (deeplab.py:96-99). */
+int dlv3p_forward_host(dlv3p_ctx* ctx, const void* h_feat, const void* h_skip, void* h_out);
+
+int dlv3p_input_bytes(const dlv3p_ctx* ctx, size_t* feat_bytes, size_t* skip_bytes);
+int dlv3p_output_bytes(const dlv3p_ctx* ctx, size_t* out_bytes);
+int dlv3p_workspace_bytes(const dlv3p_ctx* ctx, size_t* bytes);
+
+/* Debug / parity taps: copy an internal activation to the host as fp32 NHWC after a forward.
+ * name: "aspp_out" [B,h,w,256], "decoder_in" [B,hs,ws,Cd], "decoder_conv0" / "decoder_out"
+ * [B,hs,ws,256], "logits" [B,NC,ho,wo] planar, "image_pooling" [B,256].
+ * Layer names follow layers.py; returns DLV3P_ERR_NAME if the tap does not exist. */
+int dlv3p_read_tap(dlv3p_ctx* ctx, const char* name, float* host_out, size_t host_elems);
+
+/* Counters for bench.py: kernels launched by the last forward, and cumulative. */
+int dlv3p_launch_count(const dlv3p_ctx* ctx, int64_t* last_forward, int64_t* total);
+
+/* Per-kernel device timing of one forward (CUDA events on `cuda_stream`, synchronises).
+ * names_out[i] points into static storage; ms_out[i] milliseconds.  Returns the number of
+ * kernels (<= max) or a negative status. */
+int dlv3p_profile_forward(dlv3p_ctx* ctx, const void* d_feat, const void* d_skip, void* d_out,
+                          void* cuda_stream, const char** names_out, float* ms_out, int max);
+
+/* --- device-memory helpers so hosts need neither PyTorch nor cuda-python ------------ */
+int dlv3p_device_count(int* n);
+int dlv3p_device_info(int device, int* sm_major, int* sm_minor, int* sm_count, size_t* total_mem);
+int dlv3p_dev_alloc(int device, size_t bytes, void** d_ptr);
+int dlv3p_dev_free(int device, void* d_ptr);
+int dlv3p_host_alloc_pinned(size_t bytes, void** h_ptr);
+int dlv3p_host_free_pinned(void* h_ptr);
+int dlv3p_memcpy_h2d(int device, void* d_dst, const void* h_src, size_t bytes);
+int dlv3p_memcpy_d2h(int device, void* h_dst, const void* d_src, size_t bytes);
+int dlv3p_dev_memset(int device, void* d_ptr, int value, size_t bytes);
+int dlv3p_dev_synchronize(int device);
+
+/* --- standalone operators (unit parity tests; same kernels the forward uses) --------- */
+/* D[M,N] = epilogue(A[M,K] * W[K,N]):  y = acc*scale[n] + shift[n], optional ReLU.
+ * a_bf16: device bf16 [M,K] row-major (K%8==0). w_kn_fp32: HOST fp32 [K,N] (Keras HWIO 1x1 kernel).
+ * out_bf16: device bf16 [M,N].  tcgen05 / TMEM / TMA path (conv 1x1: layers.py:14-21). */
+int dlv3p_op_pointwise(int device, const void* a_bf16, int64_t M, int K, int N,
+                       const float* w_kn_fp32, const float* scale, const float* shift, int relu,
+                       void* out_bf16, void* cuda_stream);
+/* Depthwise 3x3, dilation `rate`, 'same' zero padding, + per-channel scale/shift + ReLU
+ * (layers.py:100-104).  x,out: device bf16 [B,H,W,C]; w_hwc_fp32: HOST fp32 [3,3,C]. */
+int dlv3p_op_depthwise(int device, const void* x_bf16, int B, int H, int W, int C, int rate,
+                       const float* w_hwc_fp32, const float* scale, const float* shift, int relu,
+                       void* out_bf16, void* cuda_stream);
+/* Fused SepConv_BN (depth_activation=True, layers.py:74-111): depthwise 3x3 (rate) + BN + ReLU
+ * computed on chip as the A-operand of the tcgen05 pointwise GEMM + BN + ReLU. */
+int dlv3p_op_sepconv(int device, const void* x_bf16, int B, int H, int W, int C, int rate,
+                     const float* dw_hwc_fp32, const float* dw_scale, const float* dw_shift,
+                     int N, const float* pw_kn_fp32, const float* pw_scale, const float* pw_shift,
+                     void* out_bf16, void* cuda_stream);
+/* tf.image.resize(bilinear, half-pixel centres) (layers.py:48-50). bf16 NHWC in/out. */
+int dlv3p_op_resize_bilinear(int device, const void* x_bf16, int B, int hi, int wi, int C,
+                             int ho, int wo, void* out_bf16, void* cuda_stream);
+/* pred_resize + argmax (model.py:76 + deeplab.py:99): logits fp32 PLANAR [B,NC,hi,wi] ->
+ * uint8 labels [B,ho,wo]; first-max tie-break (deeplabSegment.cpp:160-167). */
+int dlv3p_op_resize_argmax(int device, const float* logits_planar, int B, int NC, int hi, int wi,
+                           int ho, int wo, uint8_t* labels, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DLV3P_H_ */

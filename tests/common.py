@@ -1,0 +1,39 @@
+"""Shared helpers for the parity tests (test infrastructure: may import oracle/)."""
+import ast
+import os
+
+import numpy as np
+
+from oracle import head_ref as R
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+HEAD_CASES = ['head_small_full', 'head_small_os8', 'head_small_os32', 'head_small_lite', 'head_small_lite_dec', 'head_odd_size']
+
+
+def load_case(name):
+    z = np.load(os.path.join(GOLDEN, name + '.npz'))
+    kw = ast.literal_eval(str(z['cfg'][0]))
+    cfg = R.HeadConfig(**kw)
+    W = R.make_weights(cfg, int(z['wseed']))
+    feat, skip = R.make_inputs(cfg, int(z['iseed']))
+    return cfg, W, feat, skip, z
+
+
+def rel_err(a, ref):
+    """max|a-ref| / max|ref| per tensor (element-wise relative error is meaningless near zero)."""
+    ref = np.asarray(ref, np.float64)
+    return float(np.abs(np.asarray(a, np.float64) - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def make_head(cfg, W, out_mode=0, in_dtype=0, flags=0, device=0):
+    """CUDA head for an oracle HeadConfig."""
+    import dlv3p_b200
+    hd = dlv3p_b200.DeepLabHead(cfg.B, cfg.H, cfg.W, cfg.OS, cfg.Cin, cfg.Cskip, cfg.NC, lite=cfg.lite, decoder=cfg.decoder,
+                                out_mode=out_mode, in_dtype=in_dtype, device=device, h=cfg.h, w=cfg.w, hs=cfg.hs, ws=cfg.ws,
+                                flags=flags)
+    hd.set_weights(W)
+    return hd
+
+
+def planar_to_nhwc(a):
+    return np.ascontiguousarray(np.transpose(a, (0, 2, 3, 1)))

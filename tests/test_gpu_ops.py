@@ -1,0 +1,112 @@
+"""GPU parity tests, operator level: each CUDA kernel through the C ABI vs the oracle on the same seeded
+inputs.  Integer outputs (labels) must be bit exact; bf16 outputs within one bf16 rounding of the fp32 result."""
+import numpy as np
+import pytest
+
+from dlv3p_b200 import ffi
+from oracle import head_ref as R
+from tests.common import rel_err
+
+pytestmark = pytest.mark.gpu
+
+BF16_EPS = 2.0 ** -8     # half ulp of bf16 relative to the value (8 bit mantissa incl. hidden bit)
+
+
+def _assert_bf16_close(got_bits, ref_f32, extra_abs=0.0, what=''):
+    got = ffi.bf16_bits_to_f32(got_bits)
+    tol = np.abs(ref_f32) * (2 * BF16_EPS) + extra_abs
+    bad = np.abs(got - ref_f32) > tol
+    assert not bad.any(), '%s: %d / %d elements out of tolerance, max abs err %.4g (rel-to-max %.3g)' % (
+        what, bad.sum(), bad.size, np.abs(got - ref_f32).max(), rel_err(got, ref_f32))
+
+
+@pytest.mark.parametrize('M,K,N', [(128, 64, 256), (256, 2048, 256), (1000, 304, 256), (4096, 256, 48), (777, 320, 256),
+                                    (512, 256, 24), (300, 1024, 256), (130, 160, 256), (64, 96, 16), (20000, 256, 256)])
+def test_pointwise_gemm(gpu, M, K, N):
+    """tcgen05 1x1 conv + BN + ReLU (layers.py:14-21, :141-143) incl. ragged M, K % 64 != 0, narrow N."""
+    rng = np.random.default_rng(M + K + N)
+    a = R.bf16_round(rng.standard_normal((M, K)).astype(np.float32))
+    w = rng.standard_normal((K, N)).astype(np.float32) * np.float32(np.sqrt(2.0 / K))
+    s = rng.uniform(0.5, 1.5, N).astype(np.float32)
+    t = rng.standard_normal(N).astype(np.float32) * 0.1
+    got = ffi.op_pointwise(R.to_bf16_bits(a), w, s, t, relu=True)
+    ref = np.maximum((a.astype(np.float64) @ R.bf16_round(w).astype(np.float64)) * s + t, 0).astype(np.float32)
+    _assert_bf16_close(got, ref, extra_abs=2e-3, what='pointwise M=%d K=%d N=%d' % (M, K, N))
+    # no-ReLU / no-BN variant: pure GEMM
+    got2 = ffi.op_pointwise(R.to_bf16_bits(a), w, None, None, relu=False)
+    ref2 = (a.astype(np.float64) @ R.bf16_round(w).astype(np.float64)).astype(np.float32)
+    _assert_bf16_close(got2, ref2, extra_abs=2e-3, what='gemm M=%d K=%d N=%d' % (M, K, N))
+
+
+@pytest.mark.parametrize('B,H,W,C,rate', [(2, 32, 32, 64, 6), (1, 32, 32, 128, 18), (1, 20, 17, 24, 1), (1, 40, 33, 8, 12),
+                                           (2, 16, 16, 304, 1), (1, 64, 48, 16, 36)])
+def test_depthwise(gpu, B, H, W, C, rate):
+    """dilated depthwise 3x3 'same' + BN + ReLU (layers.py:100-104)."""
+    rng = np.random.default_rng(B * 1000 + H + C + rate)
+    x = R.bf16_round(rng.standard_normal((B, H, W, C)).astype(np.float32))
+    k = rng.standard_normal((3, 3, C, 1)).astype(np.float32) * 0.3
+    s = rng.uniform(0.5, 1.5, C).astype(np.float32)
+    t = rng.standard_normal(C).astype(np.float32) * 0.1
+    got = ffi.op_depthwise(R.to_bf16_bits(x), k[..., 0], rate, s, t, relu=True)
+    ref = np.maximum(R.depthwise3x3(x, k, rate) * s + t, 0)
+    _assert_bf16_close(got, ref, extra_abs=1e-5, what='depthwise')
+
+
+@pytest.mark.parametrize('B,H,W,C', [(1, 8, 16, 64), (2, 16, 32, 256), (1, 24, 40, 304), (1, 13, 21, 128), (3, 9, 7, 192),
+                                      (1, 64, 64, 304), (2, 32, 32, 320), (1, 5, 3, 8)])
+def test_fused_sepconv(gpu, B, H, W, C):
+    """SepConv_BN(depth_activation=True) fused: depthwise stencil as the on-chip A operand of the tcgen05 GEMM
+    (layers.py:74-111; decoder_conv0 C=304, decoder_conv1 C=256)."""
+    rng = np.random.default_rng(B + H * 7 + W * 13 + C)
+    x = R.bf16_round(rng.standard_normal((B, H, W, C)).astype(np.float32))
+    dk = rng.standard_normal((3, 3, C, 1)).astype(np.float32) * 0.3
+    ds = rng.uniform(0.5, 1.5, C).astype(np.float32)
+    dt = rng.standard_normal(C).astype(np.float32) * 0.1
+    pk = rng.standard_normal((C, 256)).astype(np.float32) * np.float32(np.sqrt(2.0 / C))
+    ps = rng.uniform(0.5, 1.5, 256).astype(np.float32)
+    pt = rng.standard_normal(256).astype(np.float32) * 0.1
+    got = ffi.op_sepconv(R.to_bf16_bits(x), dk[..., 0], ds, dt, pk, ps, pt)
+    mid = R.bf16_round(np.maximum(R.depthwise3x3(x, dk, 1) * ds + dt, 0))
+    ref = np.maximum((mid.reshape(-1, C).astype(np.float64) @ R.bf16_round(pk).astype(np.float64)) * ps + pt, 0)
+    ref = ref.reshape(B, H, W, 256).astype(np.float32)
+    # the intermediate is rounded to bf16 on both sides; a 1-ulp flip there moves the output by ~|w|*ulp
+    got_f = ffi.bf16_bits_to_f32(got)
+    assert rel_err(got_f, ref) < 6e-3, 'fused sepconv rel err %.3g' % rel_err(got_f, ref)
+    frac_bad = (np.abs(got_f - ref) > np.abs(ref) * (4 * BF16_EPS) + 2e-2).mean()
+    assert frac_bad < 1e-3, 'fused sepconv: %.4f of elements off' % frac_bad
+
+
+@pytest.mark.parametrize('B,hi,wi,C,ho,wo', [(2, 32, 32, 256, 128, 128), (1, 7, 5, 16, 25, 19), (1, 1, 1, 8, 9, 4), (1, 16, 16, 24, 7, 9),
+                                              (1, 33, 33, 8, 129, 129)])
+def test_resize_bilinear(gpu, B, hi, wi, C, ho, wo):
+    """tf.image.resize bilinear, half-pixel centres (layers.py:48-50): same op order as the oracle -> bit exact."""
+    rng = np.random.default_rng(hi * wi + C)
+    x = R.bf16_round(rng.standard_normal((B, hi, wi, C)).astype(np.float32))
+    got = ffi.op_resize_bilinear(R.to_bf16_bits(x), ho, wo)
+    ref = R.to_bf16_bits(R.resize_bilinear(x, (ho, wo)))
+    assert np.array_equal(got, ref), 'resize mismatch on %d elements' % (got != ref).sum()
+
+
+@pytest.mark.parametrize('B,NC,hi,wi,ho,wo', [(2, 21, 128, 128, 512, 512), (1, 19, 25, 19, 100, 76), (1, 21, 32, 32, 512, 512),
+                                               (1, 5, 9, 7, 36, 28), (1, 150, 16, 16, 64, 64), (1, 3, 10, 10, 33, 47), (1, 21, 1, 1, 4, 4)])
+def test_resize_argmax_bit_exact(gpu, B, NC, hi, wi, ho, wo):
+    """pred_resize + np.argmax (model.py:76, deeplab.py:99): integer output, bit exact incl. first-max ties."""
+    rng = np.random.default_rng(NC * hi + wo)
+    logits = rng.standard_normal((B, hi, wi, NC)).astype(np.float32)
+    # plant exact ties: duplicate a class plane into a later class
+    if NC >= 4:
+        logits[..., NC - 1] = logits[..., 1]
+        logits[..., 2] = np.maximum(logits[..., 2], logits[..., 1])
+    ref = R.argmax_labels(R.resize_bilinear(logits, (ho, wo))).astype(np.uint8)
+    got = ffi.op_resize_argmax(np.ascontiguousarray(np.transpose(logits, (0, 3, 1, 2))), ho, wo)
+    assert np.array_equal(got, ref), 'labels differ on %d of %d pixels' % ((got != ref).sum(), ref.size)
+
+
+def test_ops_reject_bad_arguments(gpu):
+    import dlv3p_b200
+    with pytest.raises(dlv3p_b200.Dlv3pError):
+        ffi.op_pointwise(np.zeros((128, 60), np.uint16), np.zeros((60, 256), np.float32))      # K % 8
+    with pytest.raises(dlv3p_b200.Dlv3pError) as e:
+        ffi.op_sepconv(np.zeros((1, 8, 8, 64), np.uint16), np.zeros((3, 3, 64)), np.ones(64), np.zeros(64),
+                       np.zeros((64, 256)), np.ones(256), np.zeros(256), rate=2)                # fused kernel: rate 1 only
+    assert e.value.status == -3

@@ -1,0 +1,1253 @@
+// dlv3p_api.cu — C ABI (include/dlv3p.h) over the sm_100a kernels: context, weight folding/packing,
+// TMA descriptors, the forward launch sequence, and the standalone operators used by the parity tests.
+//
+// Reference sites this file stands in for (paths relative to the reference repo):
+//   graph construction  deeplabv3p/models/layers.py:114-219, deeplabv3p/model.py:75-86
+//   weight loading      deeplabv3p/model.py:102-103 (Keras layer names / shapes)
+//   predict + argmax    deeplab.py:96-99
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/dlv3p.h"
+#include "dwpw_gemm.cuh"
+#include "mem_kernels.cuh"
+#include "pw_gemm.cuh"
+
+using namespace dlv3p;
+
+// =====================================================================================================
+// small host utilities
+// =====================================================================================================
+namespace {
+
+thread_local std::string g_tls_error;
+
+uint16_t f32_to_bf16_rne(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u && (u & 0x007FFFFFu)) return static_cast<uint16_t>((u >> 16) | 0x40);  // NaN
+  const uint32_t lsb = (u >> 16) & 1u;
+  u += 0x7FFFu + lsb;
+  return static_cast<uint16_t>(u >> 16);
+}
+float bf16_to_f32(uint16_t b) {
+  uint32_t u = static_cast<uint32_t>(b) << 16;
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+
+std::string fmt(const char* f, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, f);
+  vsnprintf(buf, sizeof(buf), f, ap);
+  va_end(ap);
+  return std::string(buf);
+}
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point: no link-time dependency on libcuda
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn(std::string* err) {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+    if (err) *err = fmt("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s", cudaGetErrorString(e));
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 2D bf16 [rows, cols] row-major (ld elements), box {64, box_rows}, 128B swizzle
+bool encode_2d_sw128(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                     std::string* err) {
+  EncodeTiledFn fn = get_encode_fn(err);
+  if (!fn) return false;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) *err = fmt("cuTensorMapEncodeTiled(2d rows=%llu cols=%llu ld=%llu box=%u) -> %d", (unsigned long long)rows,
+                        (unsigned long long)cols, (unsigned long long)ld, box_rows, (int)r);
+    return false;
+  }
+  return true;
+}
+// 4D bf16 NHWC {C, W, H, B} (channel stride ldc elements), box {64, bw, bh, 1}, no swizzle, OOB -> 0
+bool encode_4d_halo(CUtensorMap* tm, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint64_t ldc,
+                    uint32_t bw, uint32_t bh, std::string* err) {
+  EncodeTiledFn fn = get_encode_fn(err);
+  if (!fn) return false;
+  cuuint64_t gdim[4] = {C, W, H, B};
+  cuuint64_t gstride[3] = {ldc * 2, W * ldc * 2, H * W * ldc * 2};
+  cuuint32_t box[4] = {64, bw, bh, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) *err = fmt("cuTensorMapEncodeTiled(4d B=%llu H=%llu W=%llu C=%llu) -> %d", (unsigned long long)B,
+                        (unsigned long long)H, (unsigned long long)W, (unsigned long long)C, (int)r);
+    return false;
+  }
+  return true;
+}
+
+struct BnFold {
+  std::vector<float> scale, shift;
+};
+BnFold fold_bn(const float* gamma, const float* beta, const float* mean, const float* var, int n, float eps) {
+  BnFold f;
+  f.scale.resize(n);
+  f.shift.resize(n);
+  for (int i = 0; i < n; ++i) {
+    const float inv = gamma[i] / sqrtf(var[i] + eps);
+    f.scale[i] = inv;
+    f.shift[i] = beta[i] - mean[i] * inv;
+  }
+  return f;
+}
+
+// Keras 1x1 kernel [K][N] fp32 -> bf16 [Npad][Kpad], K-major rows, zero padded
+std::vector<uint16_t> pack_pw(const float* w_kn, int K, int N, int k_begin, int k_count, int Npad, int Kpad) {
+  std::vector<uint16_t> out(static_cast<size_t>(Npad) * Kpad, 0);
+  for (int k = 0; k < k_count; ++k)
+    for (int n = 0; n < N; ++n) out[static_cast<size_t>(n) * Kpad + k] = f32_to_bf16_rne(w_kn[static_cast<size_t>(k_begin + k) * N + n]);
+  (void)K;
+  return out;
+}
+// Keras depthwise kernel [3][3][C] (x BN scale) -> [9][Cpad]
+std::vector<float> pack_dw(const float* w_hwc, const float* scale, int C, int Cpad) {
+  std::vector<float> out(static_cast<size_t>(9) * Cpad, 0.0f);
+  for (int t = 0; t < 9; ++t)
+    for (int c = 0; c < C; ++c) out[static_cast<size_t>(t) * Cpad + c] = w_hwc[static_cast<size_t>(t) * C + c] * (scale ? scale[c] : 1.0f);
+  return out;
+}
+
+int pick_bn(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : 256); }
+
+}  // namespace
+
+// =====================================================================================================
+// kernel launch helpers (shared by the context and the standalone operators)
+// =====================================================================================================
+namespace {
+
+template <int BN>
+cudaError_t launch_pw_t(const PwLaunch& L, int num_sms, cudaStream_t st) {
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(pw_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, PwCfg<BN>::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_done[dev & 63] = true;
+  }
+  const int items = L.num_tiles * L.num_problems;
+  const int grid = items < num_sms ? items : num_sms;
+  pw_gemm_kernel<BN><<<grid, kPwThreads, PwCfg<BN>::kSmemBytes, st>>>(L);
+  return cudaGetLastError();
+}
+cudaError_t launch_pw(int BN, const PwLaunch& L, int num_sms, cudaStream_t st) {
+  switch (BN) {
+    case 32: return launch_pw_t<32>(L, num_sms, st);
+    case 64: return launch_pw_t<64>(L, num_sms, st);
+    case 256: return launch_pw_t<256>(L, num_sms, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+template <int KB, int AS>
+cudaError_t launch_dwpw_t(const DwPwParams& P, int num_sms, cudaStream_t st) {
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(dwpw_gemm_kernel<KB, AS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         DwPwCfg<KB, AS>::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_done[dev & 63] = true;
+  }
+  const int grid = P.num_tiles < num_sms ? P.num_tiles : num_sms;
+  dwpw_gemm_kernel<KB, AS><<<grid, kDwThreads, DwPwCfg<KB, AS>::kSmemBytes, st>>>(P);
+  return cudaGetLastError();
+}
+cudaError_t launch_dwpw(int KB, const DwPwParams& P, int num_sms, cudaStream_t st) {
+  switch (KB) {
+    case 1: return launch_dwpw_t<1, 2>(P, num_sms, st);
+    case 2: return launch_dwpw_t<2, 2>(P, num_sms, st);
+    case 3: return launch_dwpw_t<3, 2>(P, num_sms, st);
+    case 4: return launch_dwpw_t<4, 2>(P, num_sms, st);
+    case 5: return launch_dwpw_t<5, 1>(P, num_sms, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+int grid_for(size_t items, int num_sms) {
+  size_t g = (items + 255) / 256;
+  const size_t cap = static_cast<size_t>(num_sms) * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace
+
+// =====================================================================================================
+// context
+// =====================================================================================================
+struct WeightSlot {
+  std::string layer, var;
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+  bool set = false;
+};
+
+enum TmSlot {
+  TM_FEAT = 0, TM_DW1, TM_DW2, TM_DW3, TM_CONCAT, TM_SKIP, TM_DECIN, TM_DEC0, TM_CLS_IN,
+  TM_W_ASPP0, TM_W_ASPP1, TM_W_ASPP2, TM_W_ASPP3, TM_W_PROJ, TM_W_FP0, TM_W_DEC0, TM_W_DEC1, TM_W_CLS,
+  TM_COUNT
+};
+
+struct PwWeights {      // device-side packed 1x1 conv
+  uint16_t* w = nullptr;  // bf16 [Npad][Kpad]
+  float* scale = nullptr;
+  float* shift = nullptr;
+  int K = 0, N = 0, Npad = 0, Kpad = 0;
+};
+struct DwWeights {      // device-side packed depthwise conv (fused kernel / standalone)
+  float* w = nullptr;      // [9][Cpad]
+  float* shift = nullptr;  // [Cpad]
+  int C = 0, Cpad = 0;
+};
+
+struct dlv3p_ctx {
+  dlv3p_config cfg{};
+  int device = 0;
+  bool plan_only = false;  // device == -1: validation, weight inventory and sizes only (host-side tests)
+  int num_sms = 148;
+  std::string err;
+  // derived
+  int h = 0, w = 0, hs = 0, ws = 0, ho = 0, wo = 0;  // ho,wo = classifier resolution
+  int M1 = 0, M2 = 0, Mc = 0;                        // pixels at ASPP / decoder / classifier resolution
+  int Ccat = 0;                                      // channels of the GEMM part of the concat (1024 / 256)
+  int rates[3] = {0, 0, 0};
+  bool st_aspp = false, st_dec = false, st_tail = false, lite = false;
+  float eps = 1e-5f;
+
+  std::vector<WeightSlot> weights;
+  std::map<std::string, int> windex;
+  bool finalized = false;
+
+  // device memory
+  std::vector<void*> allocs;
+  size_t ws_bytes = 0;
+  __nv_bfloat16 *feat_bf16 = nullptr, *skip_bf16 = nullptr;  // cast targets / forward_host staging
+  void *in_feat_stage = nullptr, *in_skip_stage = nullptr;   // forward_host raw staging (in_dtype)
+  void* out_stage = nullptr;
+  __nv_bfloat16* dw_out = nullptr;     // [3][M1][Cin]
+  float* pool_partial = nullptr;       // [B][nbands][Cin]
+  float* img_shift = nullptr;          // [B][256]
+  float* b4 = nullptr;                 // [B][256]
+  __nv_bfloat16* concat = nullptr;     // [M1][Ccat]
+  __nv_bfloat16* aspp_out = nullptr;   // [M1][256]
+  __nv_bfloat16* dec_in = nullptr;     // [M2][304]
+  __nv_bfloat16* dec_tmp = nullptr;    // [M2][304]  (unfused path: depthwise output)
+  __nv_bfloat16* dec0 = nullptr;       // [M2][256]
+  __nv_bfloat16* dec1 = nullptr;       // [M2][256]
+  float* logits = nullptr;             // [B][NC][ho*wo] planar
+  int nbands = 1, rows_per_band = 1;
+
+  // packed weights
+  PwWeights pw_aspp[4], pw_proj, pw_fp0, pw_dec0, pw_dec1, pw_cls;
+  DwWeights dw_dec0, dw_dec1;
+  float *aspp_dw_w = nullptr, *aspp_dw_shift = nullptr;    // [3][9][Cin], [3][Cin]
+  uint16_t *w_ip = nullptr, *w_proj4 = nullptr;            // [Cin][256], [256][256] bf16
+  float *ip_scale = nullptr, *ip_shift = nullptr;
+
+  // tensor maps
+  CUtensorMap h_tm[TM_COUNT];
+  CUtensorMap* d_tm = nullptr;
+  const void* tm_feat_ptr = nullptr;
+  const void* tm_skip_ptr = nullptr;
+
+  cudaStream_t own_stream = nullptr;
+  int64_t launches_last = 0, launches_total = 0;
+
+  // profiling
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;
+  std::vector<const char*> prof_names;
+};
+
+namespace {
+
+int fail(dlv3p_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  g_tls_error = msg;
+  return code;
+}
+#define CU_TRY(c, expr)                                                                              \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess) return fail((c), DLV3P_ERR_CUDA, fmt("%s: %s", #expr, cudaGetErrorString(_e))); \
+  } while (0)
+
+template <class T>
+int dev_alloc(dlv3p_ctx* c, T** p, size_t count) {
+  void* q = nullptr;
+  size_t bytes = align_up(count * sizeof(T) + 256, 256);
+  if (c->plan_only) {
+    c->ws_bytes += bytes;
+    *p = nullptr;
+    return 0;
+  }
+  cudaError_t e = cudaMalloc(&q, bytes);
+  if (e != cudaSuccess) return fail(c, DLV3P_ERR_NOMEM, fmt("cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)));
+  c->allocs.push_back(q);
+  c->ws_bytes += bytes;
+  *p = reinterpret_cast<T*>(q);
+  return 0;
+}
+template <class T>
+int upload(dlv3p_ctx* c, T** p, const std::vector<T>& h) {
+  int r = dev_alloc(c, p, h.size());
+  if (r) return r;
+  CU_TRY(c, cudaMemcpy(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+void add_w(dlv3p_ctx* c, const std::string& layer, const std::string& var, std::vector<int64_t> shape) {
+  WeightSlot s;
+  s.layer = layer;
+  s.var = var;
+  s.shape = std::move(shape);
+  c->windex[layer + "/" + var] = static_cast<int>(c->weights.size());
+  c->weights.push_back(std::move(s));
+}
+void add_conv(dlv3p_ctx* c, const std::string& n, int k, int nn, bool bias = false) {
+  add_w(c, n, "kernel", {1, 1, k, nn});
+  if (bias) add_w(c, n, "bias", {nn});
+}
+void add_bn(dlv3p_ctx* c, const std::string& n, int ch) {
+  for (const char* v : {"gamma", "beta", "moving_mean", "moving_variance"}) add_w(c, n, v, {ch});
+}
+void add_sep(dlv3p_ctx* c, const std::string& p, int ch, int nn) {
+  add_w(c, p + "_depthwise", "depthwise_kernel", {3, 3, ch, 1});
+  add_bn(c, p + "_depthwise_BN", ch);
+  add_conv(c, p + "_pointwise", ch, nn);
+  add_bn(c, p + "_pointwise_BN", nn);
+}
+
+const float* W(const dlv3p_ctx* c, const std::string& layer, const std::string& var) {
+  auto it = c->windex.find(layer + "/" + var);
+  return it == c->windex.end() ? nullptr : c->weights[it->second].data.data();
+}
+BnFold fold(const dlv3p_ctx* c, const std::string& bn, int n) {
+  return fold_bn(W(c, bn, "gamma"), W(c, bn, "beta"), W(c, bn, "moving_mean"), W(c, bn, "moving_variance"), n, c->eps);
+}
+
+int make_pw(dlv3p_ctx* c, PwWeights* pw, const float* w_kn, int Ktot, int N, int k_begin, int k_count,
+            const std::vector<float>& scale, const std::vector<float>& shift) {
+  pw->K = k_count;
+  pw->N = N;
+  pw->Npad = pick_bn(N);
+  pw->Kpad = ceil_div(k_count, 64) * 64;
+  std::vector<uint16_t> packed = pack_pw(w_kn, Ktot, N, k_begin, k_count, pw->Npad, pw->Kpad);
+  int r = upload(c, &pw->w, packed);
+  if (r) return r;
+  std::vector<float> s(pw->Npad, 0.0f), t(pw->Npad, 0.0f);
+  for (int i = 0; i < N; ++i) {
+    s[i] = scale[i];
+    t[i] = shift[i];
+  }
+  if ((r = upload(c, &pw->scale, s))) return r;
+  return upload(c, &pw->shift, t);
+}
+
+}  // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+int dlv3p_abi_version(void) { return DLV3P_ABI_VERSION; }
+
+const char* dlv3p_last_error(const dlv3p_ctx* ctx) { return ctx ? ctx->err.c_str() : g_tls_error.c_str(); }
+
+int dlv3p_device_count(int* n) {
+  if (!n) return fail(nullptr, DLV3P_ERR_INVALID, "null argument");
+  cudaError_t e = cudaGetDeviceCount(n);
+  if (e != cudaSuccess) {
+    *n = 0;
+    return fail(nullptr, DLV3P_ERR_CUDA, fmt("cudaGetDeviceCount: %s", cudaGetErrorString(e)));
+  }
+  return DLV3P_OK;
+}
+int dlv3p_device_info(int device, int* sm_major, int* sm_minor, int* sm_count, size_t* total_mem) {
+  cudaDeviceProp p;
+  CU_TRY(nullptr, cudaGetDeviceProperties(&p, device));
+  if (sm_major) *sm_major = p.major;
+  if (sm_minor) *sm_minor = p.minor;
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (total_mem) *total_mem = p.totalGlobalMem;
+  return DLV3P_OK;
+}
+int dlv3p_dev_alloc(int device, size_t bytes, void** d_ptr) {
+  if (!d_ptr) return fail(nullptr, DLV3P_ERR_INVALID, "null argument");
+  CU_TRY(nullptr, cudaSetDevice(device));
+  cudaError_t e = cudaMalloc(d_ptr, bytes ? bytes : 1);
+  if (e != cudaSuccess) return fail(nullptr, DLV3P_ERR_NOMEM, fmt("cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)));
+  return DLV3P_OK;
+}
+int dlv3p_dev_free(int device, void* d_ptr) {
+  CU_TRY(nullptr, cudaSetDevice(device));
+  CU_TRY(nullptr, cudaFree(d_ptr));
+  return DLV3P_OK;
+}
+int dlv3p_host_alloc_pinned(size_t bytes, void** h_ptr) {
+  if (!h_ptr) return fail(nullptr, DLV3P_ERR_INVALID, "null argument");
+  cudaError_t e = cudaMallocHost(h_ptr, bytes ? bytes : 1);
+  if (e != cudaSuccess) return fail(nullptr, DLV3P_ERR_NOMEM, fmt("cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(e)));
+  return DLV3P_OK;
+}
+int dlv3p_host_free_pinned(void* h_ptr) {
+  CU_TRY(nullptr, cudaFreeHost(h_ptr));
+  return DLV3P_OK;
+}
+int dlv3p_memcpy_h2d(int device, void* d_dst, const void* h_src, size_t bytes) {
+  CU_TRY(nullptr, cudaSetDevice(device));
+  CU_TRY(nullptr, cudaMemcpy(d_dst, h_src, bytes, cudaMemcpyHostToDevice));
+  return DLV3P_OK;
+}
+int dlv3p_memcpy_d2h(int device, void* h_dst, const void* d_src, size_t bytes) {
+  CU_TRY(nullptr, cudaSetDevice(device));
+  CU_TRY(nullptr, cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
+  return DLV3P_OK;
+}
+int dlv3p_dev_memset(int device, void* d_ptr, int value, size_t bytes) {
+  CU_TRY(nullptr, cudaSetDevice(device));
+  CU_TRY(nullptr, cudaMemset(d_ptr, value, bytes));
+  return DLV3P_OK;
+}
+int dlv3p_dev_synchronize(int device) {
+  CU_TRY(nullptr, cudaSetDevice(device));
+  CU_TRY(nullptr, cudaDeviceSynchronize());
+  return DLV3P_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- create
+int dlv3p_create(const dlv3p_config* cfg, int device, dlv3p_ctx** out) {
+  if (!cfg || !out) return fail(nullptr, DLV3P_ERR_INVALID, "null argument");
+  *out = nullptr;
+  dlv3p_ctx* c = new dlv3p_ctx();
+  c->cfg = *cfg;
+  c->device = device;
+  auto bail = [&](int code, const std::string& m) {
+    fail(nullptr, code, m);
+    dlv3p_destroy(c);
+    return code;
+  };
+
+  // ---- validate (reference raises ValueError for a bad OS, layers.py:126)
+  const dlv3p_config& g = c->cfg;
+  c->lite = g.variant == DLV3P_VARIANT_ASPP_LITE;
+  if (g.variant != DLV3P_VARIANT_ASPP && g.variant != DLV3P_VARIANT_ASPP_LITE) return bail(DLV3P_ERR_INVALID, "invalid variant");
+  int stages = g.stages;
+  if (stages == 0) stages = c->lite ? (DLV3P_STAGE_ASPP | DLV3P_STAGE_TAIL) : (DLV3P_STAGE_ASPP | DLV3P_STAGE_DECODER | DLV3P_STAGE_TAIL);
+  c->cfg.stages = stages;
+  c->st_aspp = stages & DLV3P_STAGE_ASPP;
+  c->st_dec = stages & DLV3P_STAGE_DECODER;
+  c->st_tail = stages & DLV3P_STAGE_TAIL;
+  if (!(c->st_aspp || c->st_dec || c->st_tail)) return bail(DLV3P_ERR_INVALID, "no stage enabled");
+  if (g.B < 1 || g.H < 1 || g.W < 1) return bail(DLV3P_ERR_INVALID, "B, H, W must be positive");
+  if (c->st_aspp) {
+    if (g.OS == 8) { c->rates[0] = 12; c->rates[1] = 24; c->rates[2] = 36; }
+    else if (g.OS == 16) { c->rates[0] = 6; c->rates[1] = 12; c->rates[2] = 18; }
+    else if (g.OS == 32) { c->rates[0] = 3; c->rates[1] = 6; c->rates[2] = 9; }
+    else return bail(DLV3P_ERR_INVALID, fmt("invalid output stride %d", g.OS));
+    if (g.Cin < 8 || g.Cin % 8) return bail(DLV3P_ERR_INVALID, "Cin must be a positive multiple of 8");
+  } else if (g.OS < 1) {
+    c->cfg.OS = 16;
+  }
+  if (c->st_dec && (g.Cskip < 8 || g.Cskip % 8)) return bail(DLV3P_ERR_INVALID, "Cskip must be a positive multiple of 8");
+  if (c->st_tail && (g.NC < 1 || g.NC > 256)) return bail(DLV3P_ERR_INVALID, "NC must be in 1..256");
+  if (g.in_dtype != DLV3P_DTYPE_BF16 && g.in_dtype != DLV3P_DTYPE_FP32)
+    return bail(DLV3P_ERR_UNSUPPORTED, "in_dtype: only bf16 (0) and fp32 (2) are implemented");
+  if (c->st_tail) {
+    if (g.out_mode < DLV3P_OUT_LABELS_U8 || g.out_mode > DLV3P_OUT_LOGITS_FULL) return bail(DLV3P_ERR_INVALID, "out_mode does not match a TAIL stage");
+  } else if (g.out_mode != DLV3P_OUT_FEATURES_BF16 && g.out_mode != DLV3P_OUT_FEATURES_FP32) {
+    return bail(DLV3P_ERR_INVALID, "without the TAIL stage out_mode must be FEATURES_BF16/FP32");
+  }
+  c->eps = g.bn_eps > 0 ? g.bn_eps : 1e-5f;
+  c->h = g.h > 0 ? g.h : ceil_div(g.H, c->cfg.OS);
+  c->w = g.w > 0 ? g.w : ceil_div(g.W, c->cfg.OS);
+  c->hs = g.hs > 0 ? g.hs : ceil_div(g.H, 4);
+  c->ws = g.ws > 0 ? g.ws : ceil_div(g.W, 4);
+  c->ho = c->st_dec ? c->hs : c->h;
+  c->wo = c->st_dec ? c->ws : c->w;
+  if (!c->st_aspp && !c->st_dec) { c->ho = c->hs; c->wo = c->ws; }  // TAIL only: input is [B,hs,ws,256]
+  c->M1 = g.B * c->h * c->w;
+  c->M2 = g.B * c->hs * c->ws;
+  c->Mc = g.B * c->ho * c->wo;
+  c->Ccat = c->lite ? 256 : 1024;
+
+  // ---- device (device == -1: plan-only context, nothing is allocated and nothing can run)
+  c->plan_only = device == -1;
+  if (!c->plan_only) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return bail(DLV3P_ERR_CUDA, "no CUDA device: libdlv3p has no CPU fallback");
+    if (device < 0 || device >= ndev) return bail(DLV3P_ERR_INVALID, fmt("device %d out of range (%d devices)", device, ndev));
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(DLV3P_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10) return bail(DLV3P_ERR_UNSUPPORTED, fmt("device sm_%d%d: kernels are sm_100a only", prop.major, prop.minor));
+    c->num_sms = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess) return bail(DLV3P_ERR_CUDA, "cudaSetDevice failed");
+  }
+
+  // ---- weight inventory in Keras creation order
+  if (c->st_aspp) {
+    add_conv(c, "image_pooling", g.Cin, 256);
+    add_bn(c, "image_pooling_BN", 256);
+    add_conv(c, "aspp0", g.Cin, 256);
+    add_bn(c, "aspp0_BN", 256);
+    if (!c->lite)
+      for (int i = 1; i <= 3; ++i) add_sep(c, fmt("aspp%d", i), g.Cin, 256);
+    add_conv(c, "concat_projection", c->lite ? 512 : 1280, 256);
+    add_bn(c, "concat_projection_BN", 256);
+  }
+  if (c->st_dec) {
+    add_conv(c, "feature_projection0", g.Cskip, 48);
+    add_bn(c, "feature_projection0_BN", 48);
+    add_sep(c, "decoder_conv0", 304, 256);
+    add_sep(c, "decoder_conv1", 256, 256);
+  }
+  if (c->st_tail) add_conv(c, "conv_upsample", 256, g.NC, true);
+
+  // ---- workspace
+  int r = 0;
+  const size_t B = g.B;
+  if (c->st_aspp) {
+    const int px = c->h * c->w;
+    c->rows_per_band = px <= 1024 ? c->h : (1024 / c->w > 0 ? 1024 / c->w : 1);
+    c->nbands = ceil_div(c->h, c->rows_per_band);
+    if (!c->lite && (r = dev_alloc(c, &c->dw_out, 3 * static_cast<size_t>(c->M1) * g.Cin))) return bail(r, c->err);
+    if ((r = dev_alloc(c, &c->pool_partial, B * c->nbands * g.Cin))) return bail(r, c->err);
+    if ((r = dev_alloc(c, &c->img_shift, B * 256))) return bail(r, c->err);
+    if ((r = dev_alloc(c, &c->b4, B * 256))) return bail(r, c->err);
+    if ((r = dev_alloc(c, &c->concat, static_cast<size_t>(c->M1) * c->Ccat))) return bail(r, c->err);
+    if ((r = dev_alloc(c, &c->aspp_out, static_cast<size_t>(c->M1) * 256))) return bail(r, c->err);
+    if (g.in_dtype == DLV3P_DTYPE_FP32 && (r = dev_alloc(c, &c->feat_bf16, static_cast<size_t>(c->M1) * g.Cin))) return bail(r, c->err);
+  }
+  if (c->st_dec) {
+    if ((r = dev_alloc(c, &c->dec_in, static_cast<size_t>(c->M2) * 304))) return bail(r, c->err);
+    if ((g.flags & DLV3P_FLAG_UNFUSED_DECODER) && (r = dev_alloc(c, &c->dec_tmp, static_cast<size_t>(c->M2) * 304))) return bail(r, c->err);
+    if ((r = dev_alloc(c, &c->dec0, static_cast<size_t>(c->M2) * 256))) return bail(r, c->err);
+    if ((r = dev_alloc(c, &c->dec1, static_cast<size_t>(c->M2) * 256))) return bail(r, c->err);
+    if (g.in_dtype == DLV3P_DTYPE_FP32 && (r = dev_alloc(c, &c->skip_bf16, static_cast<size_t>(c->M2) * g.Cskip))) return bail(r, c->err);
+    if (!c->st_aspp && g.in_dtype == DLV3P_DTYPE_FP32 && (r = dev_alloc(c, &c->feat_bf16, static_cast<size_t>(c->M1) * 256))) return bail(r, c->err);
+  }
+  if (c->st_tail) {
+    if ((r = dev_alloc(c, &c->logits, B * g.NC * c->ho * c->wo))) return bail(r, c->err);
+    if (!c->st_aspp && !c->st_dec && g.in_dtype == DLV3P_DTYPE_FP32 && (r = dev_alloc(c, &c->feat_bf16, static_cast<size_t>(c->Mc) * 256))) return bail(r, c->err);
+  }
+  if ((r = dev_alloc(c, &c->d_tm, TM_COUNT))) return bail(r, c->err);
+  std::memset(c->h_tm, 0, sizeof(c->h_tm));
+  if (!c->plan_only && cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(DLV3P_ERR_CUDA, "cudaStreamCreate failed");
+  *out = c;
+  return DLV3P_OK;
+}
+
+void dlv3p_destroy(dlv3p_ctx* c) {
+  if (!c) return;
+  if (c->plan_only) {
+    delete c;
+    return;
+  }
+  cudaSetDevice(c->device);
+  for (void* p : c->allocs) cudaFree(p);
+  if (c->in_feat_stage) cudaFree(c->in_feat_stage);
+  if (c->in_skip_stage) cudaFree(c->in_skip_stage);
+  if (c->out_stage) cudaFree(c->out_stage);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
+  delete c;
+}
+
+// ---------------------------------------------------------------------------------------------- weights
+int dlv3p_num_weights(const dlv3p_ctx* c) { return c ? static_cast<int>(c->weights.size()) : DLV3P_ERR_INVALID; }
+
+int dlv3p_weight_info(const dlv3p_ctx* c, int index, const char** layer, const char** var, int64_t shape_out[4], int* rank_out) {
+  if (!c || index < 0 || index >= static_cast<int>(c->weights.size())) return fail(nullptr, DLV3P_ERR_INVALID, "bad weight index");
+  const WeightSlot& s = c->weights[index];
+  if (layer) *layer = s.layer.c_str();
+  if (var) *var = s.var.c_str();
+  if (rank_out) *rank_out = static_cast<int>(s.shape.size());
+  if (shape_out)
+    for (size_t i = 0; i < s.shape.size() && i < 4; ++i) shape_out[i] = s.shape[i];
+  return DLV3P_OK;
+}
+
+int dlv3p_set_weight(dlv3p_ctx* c, const char* layer, const char* var, const float* host, const int64_t* shape, int rank) {
+  if (!c || !layer || !var || !host || !shape) return fail(c, DLV3P_ERR_INVALID, "null argument");
+  std::string ln(layer);
+  if (ln == "logits_semantic") ln = "conv_upsample";  // raw-constructor name of the classifier (deeplabv3p_xception.py:218)
+  auto it = c->windex.find(ln + "/" + var);
+  if (it == c->windex.end()) return fail(c, DLV3P_ERR_NAME, fmt("unknown weight %s/%s for this configuration", layer, var));
+  WeightSlot& s = c->weights[it->second];
+  if (rank != static_cast<int>(s.shape.size())) return fail(c, DLV3P_ERR_NAME, fmt("%s/%s: rank %d, expected %zu", layer, var, rank, s.shape.size()));
+  size_t n = 1;
+  for (int i = 0; i < rank; ++i) {
+    if (shape[i] != s.shape[i]) return fail(c, DLV3P_ERR_NAME, fmt("%s/%s: dim %d is %lld, expected %lld", layer, var, i, (long long)shape[i], (long long)s.shape[i]));
+    n *= static_cast<size_t>(shape[i]);
+  }
+  s.data.assign(host, host + n);
+  s.set = true;
+  c->finalized = false;
+  return DLV3P_OK;
+}
+
+int dlv3p_finalize_weights(dlv3p_ctx* c) {
+  if (!c) return fail(nullptr, DLV3P_ERR_INVALID, "null context");
+  for (const WeightSlot& s : c->weights)
+    if (!s.set) return fail(c, DLV3P_ERR_STATE, fmt("weight %s/%s was never set", s.layer.c_str(), s.var.c_str()));
+  if (c->plan_only) return fail(c, DLV3P_ERR_STATE, "plan-only context (device -1): nothing can be uploaded or run; there is no CPU path");
+  if (c->finalized) return DLV3P_OK;
+  CU_TRY(c, cudaSetDevice(c->device));
+  const dlv3p_config& g = c->cfg;
+  int r = 0;
+  std::string terr;
+  if (c->st_aspp) {
+    const int Cin = g.Cin;
+    // image pooling branch: GEMV weights [Cin][256] bf16 + folded BN
+    {
+      const float* k = W(c, "image_pooling", "kernel");
+      std::vector<uint16_t> wip(static_cast<size_t>(Cin) * 256);
+      for (size_t i = 0; i < wip.size(); ++i) wip[i] = f32_to_bf16_rne(k[i]);
+      if ((r = upload(c, &c->w_ip, wip))) return r;
+      BnFold f = fold(c, "image_pooling_BN", 256);
+      if ((r = upload(c, &c->ip_scale, f.scale))) return r;
+      if ((r = upload(c, &c->ip_shift, f.shift))) return r;
+    }
+    {
+      BnFold f = fold(c, "aspp0_BN", 256);
+      if ((r = make_pw(c, &c->pw_aspp[0], W(c, "aspp0", "kernel"), Cin, 256, 0, Cin, f.scale, f.shift))) return r;
+    }
+    if (!c->lite) {
+      std::vector<float> dw(static_cast<size_t>(3) * 9 * Cin), dsh(static_cast<size_t>(3) * Cin);
+      for (int i = 1; i <= 3; ++i) {
+        const std::string p = fmt("aspp%d", i);
+        BnFold fd = fold(c, p + "_depthwise_BN", Cin);
+        std::vector<float> one = pack_dw(W(c, p + "_depthwise", "depthwise_kernel"), fd.scale.data(), Cin, Cin);
+        std::memcpy(&dw[static_cast<size_t>(i - 1) * 9 * Cin], one.data(), one.size() * sizeof(float));
+        std::memcpy(&dsh[static_cast<size_t>(i - 1) * Cin], fd.shift.data(), Cin * sizeof(float));
+        BnFold fp = fold(c, p + "_pointwise_BN", 256);
+        if ((r = make_pw(c, &c->pw_aspp[i], W(c, p + "_pointwise", "kernel"), Cin, 256, 0, Cin, fp.scale, fp.shift))) return r;
+      }
+      if ((r = upload(c, &c->aspp_dw_w, dw))) return r;
+      if ((r = upload(c, &c->aspp_dw_shift, dsh))) return r;
+    }
+    {
+      // concat_projection: rows 0..255 multiply b4 (image pooling) -> per-image shift; the rest is the GEMM (F9)
+      const float* k = W(c, "concat_projection", "kernel");
+      std::vector<uint16_t> w4(256 * 256);
+      for (size_t i = 0; i < w4.size(); ++i) w4[i] = f32_to_bf16_rne(k[i]);
+      if ((r = upload(c, &c->w_proj4, w4))) return r;
+      BnFold f = fold(c, "concat_projection_BN", 256);
+      if ((r = make_pw(c, &c->pw_proj, k, c->Ccat + 256, 256, 256, c->Ccat, f.scale, f.shift))) return r;
+    }
+  }
+  if (c->st_dec) {
+    {
+      BnFold f = fold(c, "feature_projection0_BN", 48);
+      if ((r = make_pw(c, &c->pw_fp0, W(c, "feature_projection0", "kernel"), g.Cskip, 48, 0, g.Cskip, f.scale, f.shift))) return r;
+    }
+    struct Sep { const char* p; int C; PwWeights* pw; DwWeights* dw; };
+    Sep seps[2] = {{"decoder_conv0", 304, &c->pw_dec0, &c->dw_dec0}, {"decoder_conv1", 256, &c->pw_dec1, &c->dw_dec1}};
+    for (const Sep& s : seps) {
+      const std::string p(s.p);
+      BnFold fd = fold(c, p + "_depthwise_BN", s.C);
+      s.dw->C = s.C;
+      s.dw->Cpad = ceil_div(s.C, 64) * 64;
+      std::vector<float> dw = pack_dw(W(c, p + "_depthwise", "depthwise_kernel"), fd.scale.data(), s.C, s.dw->Cpad);
+      std::vector<float> sh(s.dw->Cpad, 0.0f);
+      std::memcpy(sh.data(), fd.shift.data(), s.C * sizeof(float));
+      if ((r = upload(c, &s.dw->w, dw))) return r;
+      if ((r = upload(c, &s.dw->shift, sh))) return r;
+      BnFold fp = fold(c, p + "_pointwise_BN", 256);
+      if ((r = make_pw(c, s.pw, W(c, p + "_pointwise", "kernel"), s.C, 256, 0, s.C, fp.scale, fp.shift))) return r;
+    }
+  }
+  if (c->st_tail) {
+    std::vector<float> ones(g.NC, 1.0f), bias(W(c, "conv_upsample", "bias"), W(c, "conv_upsample", "bias") + g.NC);
+    if ((r = make_pw(c, &c->pw_cls, W(c, "conv_upsample", "kernel"), 256, g.NC, 0, 256, ones, bias))) return r;
+  }
+
+  // ---- tensor maps over weights and workspace buffers
+  auto enc2 = [&](int slot, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    return encode_2d_sw128(&c->h_tm[slot], base, rows, cols, ld, box_rows, &terr);
+  };
+  bool ok = true;
+  if (c->st_aspp) {
+    for (int i = 0; i < (c->lite ? 1 : 4); ++i)
+      ok = ok && enc2(TM_W_ASPP0 + i, c->pw_aspp[i].w, c->pw_aspp[i].Npad, c->pw_aspp[i].Kpad, c->pw_aspp[i].Kpad, c->pw_aspp[i].Npad);
+    ok = ok && enc2(TM_W_PROJ, c->pw_proj.w, 256, c->pw_proj.Kpad, c->pw_proj.Kpad, 256);
+    if (!c->lite)
+      for (int i = 0; i < 3; ++i)
+        ok = ok && enc2(TM_DW1 + i, c->dw_out + static_cast<size_t>(i) * c->M1 * g.Cin, c->M1, g.Cin, g.Cin, 128);
+    ok = ok && enc2(TM_CONCAT, c->concat, c->M1, c->Ccat, c->Ccat, 128);
+    if (c->feat_bf16) {
+      ok = ok && enc2(TM_FEAT, c->feat_bf16, c->M1, g.Cin, g.Cin, 128);
+      c->tm_feat_ptr = c->feat_bf16;
+    }
+  }
+  if (c->st_dec) {
+    ok = ok && enc2(TM_W_FP0, c->pw_fp0.w, c->pw_fp0.Npad, c->pw_fp0.Kpad, c->pw_fp0.Kpad, c->pw_fp0.Npad);
+    ok = ok && enc2(TM_W_DEC0, c->pw_dec0.w, 256, c->pw_dec0.Kpad, c->pw_dec0.Kpad, 256);
+    ok = ok && enc2(TM_W_DEC1, c->pw_dec1.w, 256, c->pw_dec1.Kpad, c->pw_dec1.Kpad, 256);
+    if (g.flags & DLV3P_FLAG_UNFUSED_DECODER) {
+      ok = ok && enc2(TM_DECIN, c->dec_tmp, c->M2, 304, 304, 128);
+      ok = ok && enc2(TM_DEC0, c->dec_tmp, c->M2, 256, 256, 128);
+    } else {
+      ok = ok && encode_4d_halo(&c->h_tm[TM_DECIN], c->dec_in, g.B, c->hs, c->ws, 304, 304, kDwHaloW, kDwHaloH, &terr);
+      ok = ok && encode_4d_halo(&c->h_tm[TM_DEC0], c->dec0, g.B, c->hs, c->ws, 256, 256, kDwHaloW, kDwHaloH, &terr);
+    }
+    if (c->skip_bf16) {
+      ok = ok && enc2(TM_SKIP, c->skip_bf16, c->M2, g.Cskip, g.Cskip, 128);
+      c->tm_skip_ptr = c->skip_bf16;
+    }
+  }
+  if (c->st_tail) {
+    ok = ok && enc2(TM_W_CLS, c->pw_cls.w, c->pw_cls.Npad, c->pw_cls.Kpad, c->pw_cls.Kpad, c->pw_cls.Npad);
+    const __nv_bfloat16* cls_in = c->st_dec ? c->dec1 : (c->st_aspp ? c->aspp_out : c->feat_bf16);
+    if (cls_in) ok = ok && enc2(TM_CLS_IN, cls_in, c->Mc, 256, 256, 128);
+  }
+  if (!ok) return fail(c, DLV3P_ERR_CUDA, terr);
+  CU_TRY(c, cudaMemcpy(c->d_tm, c->h_tm, sizeof(c->h_tm), cudaMemcpyHostToDevice));
+  c->finalized = true;
+  return DLV3P_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- sizes
+int dlv3p_input_bytes(const dlv3p_ctx* c, size_t* feat_bytes, size_t* skip_bytes) {
+  if (!c) return fail(nullptr, DLV3P_ERR_INVALID, "null context");
+  const size_t es = c->cfg.in_dtype == DLV3P_DTYPE_FP32 ? 4 : 2;
+  size_t f = 0;
+  if (c->st_aspp) f = static_cast<size_t>(c->M1) * c->cfg.Cin * es;
+  else if (c->st_dec) f = static_cast<size_t>(c->M1) * 256 * es;
+  else f = static_cast<size_t>(c->Mc) * 256 * es;
+  if (feat_bytes) *feat_bytes = f;
+  if (skip_bytes) *skip_bytes = c->st_dec ? static_cast<size_t>(c->M2) * c->cfg.Cskip * es : 0;
+  return DLV3P_OK;
+}
+int dlv3p_output_bytes(const dlv3p_ctx* c, size_t* out_bytes) {
+  if (!c || !out_bytes) return fail(nullptr, DLV3P_ERR_INVALID, "null argument");
+  const dlv3p_config& g = c->cfg;
+  const size_t B = g.B;
+  switch (g.out_mode) {
+    case DLV3P_OUT_LABELS_U8: *out_bytes = B * g.H * g.W; break;
+    case DLV3P_OUT_LOGITS_LOWRES: *out_bytes = B * g.NC * c->ho * c->wo * 4; break;
+    case DLV3P_OUT_SOFTMAX:
+    case DLV3P_OUT_LOGITS_FULL: *out_bytes = B * g.H * g.W * g.NC * 4; break;
+    case DLV3P_OUT_FEATURES_BF16: *out_bytes = static_cast<size_t>(c->st_dec ? c->M2 : c->M1) * 256 * 2; break;
+    case DLV3P_OUT_FEATURES_FP32: *out_bytes = static_cast<size_t>(c->st_dec ? c->M2 : c->M1) * 256 * 4; break;
+    default: return fail(nullptr, DLV3P_ERR_INVALID, "bad out_mode");
+  }
+  return DLV3P_OK;
+}
+int dlv3p_workspace_bytes(const dlv3p_ctx* c, size_t* bytes) {
+  if (!c || !bytes) return fail(nullptr, DLV3P_ERR_INVALID, "null argument");
+  *bytes = c->ws_bytes;
+  return DLV3P_OK;
+}
+int dlv3p_launch_count(const dlv3p_ctx* c, int64_t* last_forward, int64_t* total) {
+  if (!c) return fail(nullptr, DLV3P_ERR_INVALID, "null context");
+  if (last_forward) *last_forward = c->launches_last;
+  if (total) *total = c->launches_total;
+  return DLV3P_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------- forward
+namespace {
+struct Launcher {
+  dlv3p_ctx* c;
+  cudaStream_t st;
+  int rc = 0;
+  bool begin(const char* name) {
+    if (rc) return false;
+    if (c->profiling) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      cudaEventRecord(e, st);
+      c->prof_events.push_back(e);
+      c->prof_names.push_back(name);
+    }
+    return true;
+  }
+  void end(const char* name, cudaError_t e) {
+    if (e != cudaSuccess) rc = fail(c, DLV3P_ERR_CUDA, fmt("launch %s: %s", name, cudaGetErrorString(e)));
+    else ++c->launches_last;
+  }
+};
+}  // namespace
+
+static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, void* d_out, cudaStream_t st) {
+  if (!c) return fail(nullptr, DLV3P_ERR_INVALID, "null context");
+  if (c->plan_only) return fail(c, DLV3P_ERR_STATE, "plan-only context (device -1): there is no CPU path");
+  if (!c->finalized) return fail(c, DLV3P_ERR_STATE, "dlv3p_finalize_weights has not been called");
+  if (!d_feat || !d_out) return fail(c, DLV3P_ERR_INVALID, "null feature / output pointer");
+  if (c->st_dec && !d_skip) return fail(c, DLV3P_ERR_INVALID, "decoder stage needs the skip feature");
+  CU_TRY(c, cudaSetDevice(c->device));
+  const dlv3p_config& g = c->cfg;
+  c->launches_last = 0;
+  Launcher L{c, st};
+  std::string terr;
+
+  // ---- inputs: cast fp32 -> bf16, or (re)encode the TMA descriptors over the caller's bf16 buffers
+  const __nv_bfloat16* feat = nullptr;
+  const __nv_bfloat16* skip = nullptr;
+  const size_t feat_elems = c->st_aspp ? static_cast<size_t>(c->M1) * g.Cin : (c->st_dec ? static_cast<size_t>(c->M1) * 256 : static_cast<size_t>(c->Mc) * 256);
+  if (g.in_dtype == DLV3P_DTYPE_FP32) {
+    if (L.begin("cast_f32_bf16")) {
+      cast_f32_bf16_kernel<<<grid_for(feat_elems / 8, c->num_sms), 256, 0, st>>>(static_cast<const float*>(d_feat), c->feat_bf16, feat_elems / 8);
+      L.end("cast_f32_bf16", cudaGetLastError());
+    }
+    feat = c->feat_bf16;
+    if (c->st_dec) {
+      const size_t n = static_cast<size_t>(c->M2) * g.Cskip;
+      if (L.begin("cast_f32_bf16")) {
+        cast_f32_bf16_kernel<<<grid_for(n / 8, c->num_sms), 256, 0, st>>>(static_cast<const float*>(d_skip), c->skip_bf16, n / 8);
+        L.end("cast_f32_bf16", cudaGetLastError());
+      }
+      skip = c->skip_bf16;
+    }
+  } else {
+    feat = static_cast<const __nv_bfloat16*>(d_feat);
+    skip = static_cast<const __nv_bfloat16*>(d_skip);
+    if (c->st_aspp && c->tm_feat_ptr != d_feat) {
+      if (!encode_2d_sw128(&c->h_tm[TM_FEAT], feat, c->M1, g.Cin, g.Cin, 128, &terr)) return fail(c, DLV3P_ERR_CUDA, terr);
+      CU_TRY(c, cudaMemcpyAsync(&c->d_tm[TM_FEAT], &c->h_tm[TM_FEAT], sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
+      c->tm_feat_ptr = d_feat;
+    }
+    if (c->st_dec && c->tm_skip_ptr != d_skip) {
+      if (!encode_2d_sw128(&c->h_tm[TM_SKIP], skip, c->M2, g.Cskip, g.Cskip, 128, &terr)) return fail(c, DLV3P_ERR_CUDA, terr);
+      CU_TRY(c, cudaMemcpyAsync(&c->d_tm[TM_SKIP], &c->h_tm[TM_SKIP], sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
+      c->tm_skip_ptr = d_skip;
+    }
+    if (!c->st_aspp && !c->st_dec && c->tm_feat_ptr != d_feat) {  // TAIL only
+      if (!encode_2d_sw128(&c->h_tm[TM_CLS_IN], feat, c->Mc, 256, 256, 128, &terr)) return fail(c, DLV3P_ERR_CUDA, terr);
+      CU_TRY(c, cudaMemcpyAsync(&c->d_tm[TM_CLS_IN], &c->h_tm[TM_CLS_IN], sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
+      c->tm_feat_ptr = d_feat;
+    }
+  }
+
+  const __nv_bfloat16* x256 = feat;  // running 256-channel feature map
+  // ------------------------------------------------------------------ ASPP (layers.py:114-196)
+  if (c->st_aspp) {
+    if (L.begin("aspp_dw_pool")) {
+      AsppDwParams P{};
+      P.x = feat; P.w = c->aspp_dw_w; P.shift = c->aspp_dw_shift; P.out = c->dw_out; P.pool_partial = c->pool_partial;
+      P.B = g.B; P.h = c->h; P.w_ = c->w; P.C = g.Cin; P.nrates = c->lite ? 0 : 3;
+      for (int i = 0; i < 3; ++i) P.rates[i] = c->rates[i];
+      P.rows_per_band = c->rows_per_band; P.nbands = c->nbands;
+      dim3 grid(ceil_div(g.Cin, 64), c->nbands, g.B);
+      aspp_dw_pool_kernel<<<grid, 256, 0, st>>>(P);
+      L.end("aspp_dw_pool", cudaGetLastError());
+    }
+    if (L.begin("pool_proj")) {
+      PoolProjParams P{};
+      P.pool_partial = c->pool_partial; P.w_ip = reinterpret_cast<const __nv_bfloat16*>(c->w_ip);
+      P.ip_scale = c->ip_scale; P.ip_shift = c->ip_shift; P.w_proj4 = reinterpret_cast<const __nv_bfloat16*>(c->w_proj4);
+      P.proj_scale = c->pw_proj.scale; P.proj_shift = c->pw_proj.shift; P.img_shift = c->img_shift; P.b4_out = c->b4;
+      P.C = g.Cin; P.nbands = c->nbands; P.inv_count = 1.0f / static_cast<float>(c->h * c->w);
+      pool_proj_kernel<<<g.B, 256, (g.Cin + 256) * sizeof(float), st>>>(P);
+      L.end("pool_proj", cudaGetLastError());
+    }
+    if (L.begin("aspp_branches_gemm")) {
+      PwLaunch PL{};
+      PL.num_problems = c->lite ? 1 : 4;
+      PL.M = c->M1; PL.num_tiles = ceil_div(c->M1, kPwBM); PL.rows_per_img = c->h * c->w;
+      for (int i = 0; i < PL.num_problems; ++i) {
+        PwProblem& p = PL.prob[i];
+        p.tmap_a = &c->d_tm[i == 0 ? TM_FEAT : TM_DW1 + (i - 1)];
+        p.tmap_w = &c->d_tm[TM_W_ASPP0 + i];
+        p.scale = c->pw_aspp[i].scale; p.shift = c->pw_aspp[i].shift; p.img_shift = nullptr;
+        p.out = c->concat; p.K = g.Cin; p.N = 256; p.ldo = c->Ccat; p.col_off = 256 * i; p.relu = 1; p.epi = kEpiBf16;
+      }
+      L.end("aspp_branches_gemm", launch_pw(256, PL, c->num_sms, st));
+    }
+    if (L.begin("concat_projection_gemm")) {
+      PwLaunch PL{};
+      PL.num_problems = 1; PL.M = c->M1; PL.num_tiles = ceil_div(c->M1, kPwBM); PL.rows_per_img = c->h * c->w;
+      PwProblem& p = PL.prob[0];
+      p.tmap_a = &c->d_tm[TM_CONCAT]; p.tmap_w = &c->d_tm[TM_W_PROJ];
+      p.scale = c->pw_proj.scale; p.shift = c->pw_proj.shift; p.img_shift = c->img_shift;
+      p.out = c->aspp_out; p.K = c->Ccat; p.N = 256; p.ldo = 256; p.col_off = 0; p.relu = 1; p.epi = kEpiBf16ImgShift;
+      L.end("concat_projection_gemm", launch_pw(256, PL, c->num_sms, st));
+    }
+    x256 = c->aspp_out;
+  }
+  // ------------------------------------------------------------------ Decoder (layers.py:199-219)
+  if (c->st_dec) {
+    if (L.begin("decoder_resize")) {
+      ResizeParams P{};
+      P.x = x256; P.out = c->dec_in; P.B = g.B; P.hi = c->h; P.wi = c->w; P.C = 256; P.ho = c->hs; P.wo = c->ws;
+      P.ldo = 304; P.col_off = 0;
+      P.sy = static_cast<float>(c->h) / static_cast<float>(c->hs); P.sx = static_cast<float>(c->w) / static_cast<float>(c->ws);
+      resize_bilinear_kernel<<<grid_for(static_cast<size_t>(c->M2) * 32, c->num_sms), 256, 0, st>>>(P);
+      L.end("decoder_resize", cudaGetLastError());
+    }
+    if (L.begin("feature_projection0_gemm")) {
+      PwLaunch PL{};
+      PL.num_problems = 1; PL.M = c->M2; PL.num_tiles = ceil_div(c->M2, kPwBM); PL.rows_per_img = c->hs * c->ws;
+      PwProblem& p = PL.prob[0];
+      p.tmap_a = &c->d_tm[TM_SKIP]; p.tmap_w = &c->d_tm[TM_W_FP0];
+      p.scale = c->pw_fp0.scale; p.shift = c->pw_fp0.shift; p.img_shift = nullptr;
+      p.out = c->dec_in; p.K = g.Cskip; p.N = 48; p.ldo = 304; p.col_off = 256; p.relu = 1; p.epi = kEpiBf16;
+      L.end("feature_projection0_gemm", launch_pw(64, PL, c->num_sms, st));
+    }
+    const int tiles_x = ceil_div(c->ws, kDwTW), tiles_y = ceil_div(c->hs, kDwTH);
+    struct SepRun { const char* name; const __nv_bfloat16* in; int C; int tm_x; int tm_w; DwWeights* dw; PwWeights* pw; __nv_bfloat16* out; };
+    SepRun runs[2] = {{"decoder_conv0_sepconv", c->dec_in, 304, TM_DECIN, TM_W_DEC0, &c->dw_dec0, &c->pw_dec0, c->dec0},
+                      {"decoder_conv1_sepconv", c->dec0, 256, TM_DEC0, TM_W_DEC1, &c->dw_dec1, &c->pw_dec1, c->dec1}};
+    for (const SepRun& s : runs) {
+      if (g.flags & DLV3P_FLAG_UNFUSED_DECODER) {
+        if (L.begin("decoder_depthwise")) {
+          DwParams P{};
+          P.x = s.in; P.w = s.dw->w; P.shift = s.dw->shift; P.out = c->dec_tmp; P.B = g.B; P.H = c->hs; P.W = c->ws; P.C = s.C;
+          P.rate = 1; P.relu = 1; P.wstride = s.dw->Cpad;
+          depthwise3x3_kernel<<<grid_for(static_cast<size_t>(c->M2) * (s.C / 8), c->num_sms), 256, 0, st>>>(P);
+          L.end("decoder_depthwise", cudaGetLastError());
+        }
+        if (L.begin("decoder_pointwise_gemm")) {
+          PwLaunch PL{};
+          PL.num_problems = 1; PL.M = c->M2; PL.num_tiles = ceil_div(c->M2, kPwBM); PL.rows_per_img = c->hs * c->ws;
+          PwProblem& p = PL.prob[0];
+          p.tmap_a = &c->d_tm[s.tm_x]; p.tmap_w = &c->d_tm[s.tm_w];
+          p.scale = s.pw->scale; p.shift = s.pw->shift; p.img_shift = nullptr;
+          p.out = s.out; p.K = s.C; p.N = 256; p.ldo = 256; p.col_off = 0; p.relu = 1; p.epi = kEpiBf16;
+          L.end("decoder_pointwise_gemm", launch_pw(256, PL, c->num_sms, st));
+        }
+      } else if (L.begin(s.name)) {
+        DwPwParams P{};
+        P.tmap_x = &c->d_tm[s.tm_x]; P.tmap_w = &c->d_tm[s.tm_w];
+        P.dw_w = s.dw->w; P.dw_shift = s.dw->shift; P.scale = s.pw->scale; P.shift = s.pw->shift; P.out = s.out;
+        P.B = g.B; P.H = c->hs; P.W = c->ws; P.tiles_x = tiles_x; P.tiles_y = tiles_y; P.num_tiles = g.B * tiles_x * tiles_y;
+        L.end(s.name, launch_dwpw(s.dw->Cpad / 64, P, c->num_sms, st));
+      }
+    }
+    x256 = c->dec1;
+  }
+  // ------------------------------------------------------------------ tail (model.py:75-86, deeplab.py:99)
+  if (c->st_tail) {
+    if (L.begin("classifier_gemm")) {
+      PwLaunch PL{};
+      PL.num_problems = 1; PL.M = c->Mc; PL.num_tiles = ceil_div(c->Mc, kPwBM); PL.rows_per_img = c->ho * c->wo;
+      PwProblem& p = PL.prob[0];
+      p.tmap_a = &c->d_tm[TM_CLS_IN]; p.tmap_w = &c->d_tm[TM_W_CLS];
+      p.scale = c->pw_cls.scale; p.shift = c->pw_cls.shift; p.img_shift = nullptr;
+      p.out = g.out_mode == DLV3P_OUT_LOGITS_LOWRES ? d_out : c->logits;
+      p.K = 256; p.N = g.NC; p.ldo = 0; p.col_off = 0; p.relu = 0; p.epi = kEpiPlanarF32;
+      L.end("classifier_gemm", launch_pw(c->pw_cls.Npad, PL, c->num_sms, st));
+    }
+    const float sy = static_cast<float>(c->ho) / static_cast<float>(g.H), sx = static_cast<float>(c->wo) / static_cast<float>(g.W);
+    if (g.out_mode == DLV3P_OUT_LABELS_U8) {
+      if (L.begin("resize_argmax")) {
+        ArgmaxParams P{};
+        P.logits = c->logits; P.labels = static_cast<uint8_t*>(d_out); P.B = g.B; P.NC = g.NC; P.hi = c->ho; P.wi = c->wo;
+        P.ho = g.H; P.wo = g.W; P.sy = sy; P.sx = sx;
+        if (g.H == 4 * c->ho && g.W == 4 * c->wo)
+          resize_argmax_x4_kernel<<<grid_for(static_cast<size_t>(g.B) * (c->ho + 1) * (c->wo + 1), c->num_sms), 256, 0, st>>>(P);
+        else
+          resize_argmax_generic_kernel<<<grid_for(static_cast<size_t>(g.B) * g.H * g.W, c->num_sms), 256, 0, st>>>(P);
+        L.end("resize_argmax", cudaGetLastError());
+      }
+    } else if (g.out_mode == DLV3P_OUT_SOFTMAX || g.out_mode == DLV3P_OUT_LOGITS_FULL) {
+      if (L.begin("resize_dense")) {
+        DenseResizeParams P{};
+        P.logits = c->logits; P.out = static_cast<float*>(d_out); P.B = g.B; P.NC = g.NC; P.hi = c->ho; P.wi = c->wo;
+        P.ho = g.H; P.wo = g.W; P.softmax = g.out_mode == DLV3P_OUT_SOFTMAX; P.sy = sy; P.sx = sx;
+        resize_dense_kernel<<<grid_for(static_cast<size_t>(g.B) * g.H * g.W, c->num_sms), 256, 0, st>>>(P);
+        L.end("resize_dense", cudaGetLastError());
+      }
+    }
+  } else {
+    const size_t n = static_cast<size_t>(c->st_dec ? c->M2 : c->M1) * 256;
+    if (g.out_mode == DLV3P_OUT_FEATURES_BF16) {
+      if (!L.rc) CU_TRY(c, cudaMemcpyAsync(d_out, x256, n * 2, cudaMemcpyDeviceToDevice, st));
+    } else if (L.begin("cast_bf16_f32")) {
+      cast_bf16_f32_kernel<<<grid_for(n / 8, c->num_sms), 256, 0, st>>>(x256, static_cast<float*>(d_out), n / 8);
+      L.end("cast_bf16_f32", cudaGetLastError());
+    }
+  }
+  if (c->profiling) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    c->prof_events.push_back(e);
+  }
+  c->launches_total += c->launches_last;
+  return L.rc;
+}
+
+extern "C" {
+
+int dlv3p_forward(dlv3p_ctx* c, const void* d_feat, const void* d_skip, void* d_out, void* cuda_stream) {
+  return forward_impl(c, d_feat, d_skip, d_out, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int dlv3p_forward_host(dlv3p_ctx* c, const void* h_feat, const void* h_skip, void* h_out) {
+  if (!c || !h_feat || !h_out) return fail(c, DLV3P_ERR_INVALID, "null argument");
+  if (c->plan_only) return fail(c, DLV3P_ERR_STATE, "plan-only context (device -1): there is no CPU path");
+  CU_TRY(c, cudaSetDevice(c->device));
+  size_t fb = 0, sb = 0, ob = 0;
+  dlv3p_input_bytes(c, &fb, &sb);
+  int r = dlv3p_output_bytes(c, &ob);
+  if (r) return r;
+  if (!c->in_feat_stage) CU_TRY(c, cudaMalloc(&c->in_feat_stage, fb));
+  if (sb && !c->in_skip_stage) CU_TRY(c, cudaMalloc(&c->in_skip_stage, sb));
+  if (!c->out_stage) CU_TRY(c, cudaMalloc(&c->out_stage, ob));
+  if (sb && !h_skip) return fail(c, DLV3P_ERR_INVALID, "decoder stage needs the skip feature");
+  cudaStream_t st = c->own_stream;
+  CU_TRY(c, cudaMemcpyAsync(c->in_feat_stage, h_feat, fb, cudaMemcpyHostToDevice, st));
+  if (sb) CU_TRY(c, cudaMemcpyAsync(c->in_skip_stage, h_skip, sb, cudaMemcpyHostToDevice, st));
+  r = forward_impl(c, c->in_feat_stage, sb ? c->in_skip_stage : nullptr, c->out_stage, st);
+  if (r) return r;
+  CU_TRY(c, cudaMemcpyAsync(h_out, c->out_stage, ob, cudaMemcpyDeviceToHost, st));
+  CU_TRY(c, cudaStreamSynchronize(st));
+  return DLV3P_OK;
+}
+
+int dlv3p_profile_forward(dlv3p_ctx* c, const void* d_feat, const void* d_skip, void* d_out, void* cuda_stream,
+                          const char** names_out, float* ms_out, int max) {
+  if (!c) return fail(nullptr, DLV3P_ERR_INVALID, "null context");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
+  c->prof_events.clear();
+  c->prof_names.clear();
+  c->profiling = true;
+  int r = forward_impl(c, d_feat, d_skip, d_out, st);
+  c->profiling = false;
+  if (r) return r;
+  CU_TRY(c, cudaStreamSynchronize(st));
+  const int n = static_cast<int>(c->prof_names.size());
+  for (int i = 0; i < n && i < max; ++i) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->prof_events[i], c->prof_events[i + 1]);
+    if (names_out) names_out[i] = c->prof_names[i];
+    if (ms_out) ms_out[i] = ms;
+  }
+  return n < max ? n : max;
+}
+
+int dlv3p_read_tap(dlv3p_ctx* c, const char* name, float* host_out, size_t host_elems) {
+  if (!c || !name || !host_out) return fail(c, DLV3P_ERR_INVALID, "null argument");
+  if (c->plan_only) return fail(c, DLV3P_ERR_STATE, "plan-only context (device -1): there is no CPU path");
+  CU_TRY(c, cudaSetDevice(c->device));
+  CU_TRY(c, cudaDeviceSynchronize());
+  const std::string n(name);
+  const void* src = nullptr;
+  size_t elems = 0;
+  bool is_f32 = false;
+  if (n == "aspp_out" && c->aspp_out) { src = c->aspp_out; elems = static_cast<size_t>(c->M1) * 256; }
+  else if (n == "concat" && c->concat) { src = c->concat; elems = static_cast<size_t>(c->M1) * c->Ccat; }
+  else if (n == "aspp_depthwise" && c->dw_out) { src = c->dw_out; elems = static_cast<size_t>(3) * c->M1 * c->cfg.Cin; }
+  else if (n == "decoder_in" && c->dec_in) { src = c->dec_in; elems = static_cast<size_t>(c->M2) * 304; }
+  else if (n == "decoder_conv0" && c->dec0) { src = c->dec0; elems = static_cast<size_t>(c->M2) * 256; }
+  else if (n == "decoder_out" && c->dec1) { src = c->dec1; elems = static_cast<size_t>(c->M2) * 256; }
+  else if (n == "logits" && c->logits) { src = c->logits; elems = static_cast<size_t>(c->cfg.B) * c->cfg.NC * c->ho * c->wo; is_f32 = true; }
+  else if (n == "image_pooling" && c->b4) { src = c->b4; elems = static_cast<size_t>(c->cfg.B) * 256; is_f32 = true; }
+  else return fail(c, DLV3P_ERR_NAME, fmt("no tap named %s in this configuration", name));
+  if (host_elems < elems) return fail(c, DLV3P_ERR_INVALID, fmt("tap %s needs %zu elements, buffer has %zu", name, elems, host_elems));
+  if (is_f32) {
+    CU_TRY(c, cudaMemcpy(host_out, src, elems * 4, cudaMemcpyDeviceToHost));
+  } else {
+    std::vector<uint16_t> tmp(elems);
+    CU_TRY(c, cudaMemcpy(tmp.data(), src, elems * 2, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < elems; ++i) host_out[i] = bf16_to_f32(tmp[i]);
+  }
+  return DLV3P_OK;
+}
+
+}  // extern "C"
+
+// =====================================================================================================
+// standalone operators (parity tests drive the same kernels one at a time)
+// =====================================================================================================
+namespace {
+struct TmpDev {
+  std::vector<void*> ptrs;
+  ~TmpDev() {
+    for (void* p : ptrs) cudaFree(p);
+  }
+  template <class T>
+  T* put(const std::vector<T>& h) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, h.size() * sizeof(T) + 256) != cudaSuccess) return nullptr;
+    ptrs.push_back(p);
+    cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return static_cast<T*>(p);
+  }
+  template <class T>
+  T* alloc(size_t n) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, n * sizeof(T) + 256) != cudaSuccess) return nullptr;
+    ptrs.push_back(p);
+    return static_cast<T*>(p);
+  }
+};
+int op_prolog(int device, int* num_sms) {
+  CU_TRY(nullptr, cudaSetDevice(device));
+  cudaDeviceProp p;
+  CU_TRY(nullptr, cudaGetDeviceProperties(&p, device));
+  if (p.major != 10) return fail(nullptr, DLV3P_ERR_UNSUPPORTED, fmt("device sm_%d%d: kernels are sm_100a only", p.major, p.minor));
+  *num_sms = p.multiProcessorCount;
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int dlv3p_op_pointwise(int device, const void* a_bf16, int64_t M, int K, int N, const float* w_kn, const float* scale,
+                       const float* shift, int relu, void* out_bf16, void* cuda_stream) {
+  int sms = 0, r = op_prolog(device, &sms);
+  if (r) return r;
+  if (!a_bf16 || !w_kn || !out_bf16 || M < 1 || K < 8 || K % 8 || N < 8 || N % 8 || N > 256) return fail(nullptr, DLV3P_ERR_INVALID, "op_pointwise: bad arguments (K%8, N%8, N<=256)");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const int BN = pick_bn(N), Kpad = ceil_div(K, 64) * 64;
+  TmpDev tmp;
+  uint16_t* dw = tmp.put(pack_pw(w_kn, K, N, 0, K, BN, Kpad));
+  std::vector<float> s(BN, 0.0f), t(BN, 0.0f);
+  for (int i = 0; i < N; ++i) { s[i] = scale ? scale[i] : 1.0f; t[i] = shift ? shift[i] : 0.0f; }
+  float* ds = tmp.put(s);
+  float* dt = tmp.put(t);
+  std::string terr;
+  std::vector<CUtensorMap> tm(2);
+  if (!encode_2d_sw128(&tm[0], a_bf16, M, K, K, 128, &terr) || !encode_2d_sw128(&tm[1], dw, BN, Kpad, Kpad, BN, &terr)) return fail(nullptr, DLV3P_ERR_CUDA, terr);
+  CUtensorMap* dtm = tmp.put(tm);
+  if (!dw || !ds || !dt || !dtm) return fail(nullptr, DLV3P_ERR_NOMEM, "op_pointwise: cudaMalloc failed");
+  PwLaunch PL{};
+  PL.num_problems = 1; PL.M = static_cast<int>(M); PL.num_tiles = ceil_div(static_cast<int>(M), kPwBM); PL.rows_per_img = static_cast<int>(M);
+  PwProblem& p = PL.prob[0];
+  p.tmap_a = &dtm[0]; p.tmap_w = &dtm[1]; p.scale = ds; p.shift = dt; p.img_shift = nullptr; p.out = out_bf16;
+  p.K = K; p.N = N; p.ldo = N; p.col_off = 0; p.relu = relu; p.epi = kEpiBf16;
+  CU_TRY(nullptr, launch_pw(BN, PL, sms, st));
+  CU_TRY(nullptr, cudaStreamSynchronize(st));
+  return DLV3P_OK;
+}
+
+int dlv3p_op_depthwise(int device, const void* x_bf16, int B, int H, int W_, int C, int rate, const float* w_hwc,
+                       const float* scale, const float* shift, int relu, void* out_bf16, void* cuda_stream) {
+  int sms = 0, r = op_prolog(device, &sms);
+  if (r) return r;
+  if (!x_bf16 || !w_hwc || !out_bf16 || B < 1 || H < 1 || W_ < 1 || C < 8 || C % 8 || rate < 1) return fail(nullptr, DLV3P_ERR_INVALID, "op_depthwise: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  TmpDev tmp;
+  float* dw = tmp.put(pack_dw(w_hwc, scale, C, C));
+  std::vector<float> sh(C, 0.0f);
+  if (shift) sh.assign(shift, shift + C);
+  float* dsh = tmp.put(sh);
+  if (!dw || !dsh) return fail(nullptr, DLV3P_ERR_NOMEM, "op_depthwise: cudaMalloc failed");
+  DwParams P{};
+  P.x = static_cast<const __nv_bfloat16*>(x_bf16); P.w = dw; P.shift = dsh; P.out = static_cast<__nv_bfloat16*>(out_bf16);
+  P.B = B; P.H = H; P.W = W_; P.C = C; P.rate = rate; P.relu = relu; P.wstride = C;
+  depthwise3x3_kernel<<<grid_for(static_cast<size_t>(B) * H * W_ * (C / 8), sms), 256, 0, st>>>(P);
+  CU_TRY(nullptr, cudaGetLastError());
+  CU_TRY(nullptr, cudaStreamSynchronize(st));
+  return DLV3P_OK;
+}
+
+int dlv3p_op_sepconv(int device, const void* x_bf16, int B, int H, int W_, int C, int rate, const float* dw_hwc,
+                     const float* dw_scale, const float* dw_shift, int N, const float* pw_kn, const float* pw_scale,
+                     const float* pw_shift, void* out_bf16, void* cuda_stream) {
+  int sms = 0, r = op_prolog(device, &sms);
+  if (r) return r;
+  if (!x_bf16 || !dw_hwc || !pw_kn || !out_bf16 || C < 8 || C % 8) return fail(nullptr, DLV3P_ERR_INVALID, "op_sepconv: bad arguments");
+  if (rate != 1 || N != 256 || C > 320) return fail(nullptr, DLV3P_ERR_UNSUPPORTED, "op_sepconv: fused kernel covers rate 1, N = 256, C <= 320");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const int KB = ceil_div(C, 64), Cpad = KB * 64;
+  TmpDev tmp;
+  float* ddw = tmp.put(pack_dw(dw_hwc, dw_scale, C, Cpad));
+  std::vector<float> sh(Cpad, 0.0f);
+  if (dw_shift) std::memcpy(sh.data(), dw_shift, C * sizeof(float));
+  float* dsh = tmp.put(sh);
+  uint16_t* dpw = tmp.put(pack_pw(pw_kn, C, N, 0, C, 256, Cpad));
+  std::vector<float> s(256, 1.0f), t(256, 0.0f);
+  if (pw_scale) s.assign(pw_scale, pw_scale + 256);
+  if (pw_shift) t.assign(pw_shift, pw_shift + 256);
+  float* ds = tmp.put(s);
+  float* dt = tmp.put(t);
+  std::string terr;
+  std::vector<CUtensorMap> tm(2);
+  if (!encode_4d_halo(&tm[0], x_bf16, B, H, W_, C, C, kDwHaloW, kDwHaloH, &terr) || !encode_2d_sw128(&tm[1], dpw, 256, Cpad, Cpad, 256, &terr))
+    return fail(nullptr, DLV3P_ERR_CUDA, terr);
+  CUtensorMap* dtm = tmp.put(tm);
+  if (!ddw || !dsh || !dpw || !ds || !dt || !dtm) return fail(nullptr, DLV3P_ERR_NOMEM, "op_sepconv: cudaMalloc failed");
+  DwPwParams P{};
+  P.tmap_x = &dtm[0]; P.tmap_w = &dtm[1]; P.dw_w = ddw; P.dw_shift = dsh; P.scale = ds; P.shift = dt;
+  P.out = static_cast<__nv_bfloat16*>(out_bf16); P.B = B; P.H = H; P.W = W_;
+  P.tiles_x = ceil_div(W_, kDwTW); P.tiles_y = ceil_div(H, kDwTH); P.num_tiles = B * P.tiles_x * P.tiles_y;
+  CU_TRY(nullptr, launch_dwpw(KB, P, sms, st));
+  CU_TRY(nullptr, cudaStreamSynchronize(st));
+  return DLV3P_OK;
+}
+
+int dlv3p_op_resize_bilinear(int device, const void* x_bf16, int B, int hi, int wi, int C, int ho, int wo, void* out_bf16,
+                             void* cuda_stream) {
+  int sms = 0, r = op_prolog(device, &sms);
+  if (r) return r;
+  if (!x_bf16 || !out_bf16 || C < 8 || C % 8 || hi < 1 || wi < 1 || ho < 1 || wo < 1) return fail(nullptr, DLV3P_ERR_INVALID, "op_resize_bilinear: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  ResizeParams P{};
+  P.x = static_cast<const __nv_bfloat16*>(x_bf16); P.out = static_cast<__nv_bfloat16*>(out_bf16);
+  P.B = B; P.hi = hi; P.wi = wi; P.C = C; P.ho = ho; P.wo = wo; P.ldo = C; P.col_off = 0;
+  P.sy = static_cast<float>(hi) / static_cast<float>(ho); P.sx = static_cast<float>(wi) / static_cast<float>(wo);
+  resize_bilinear_kernel<<<grid_for(static_cast<size_t>(B) * ho * wo * (C / 8), sms), 256, 0, st>>>(P);
+  CU_TRY(nullptr, cudaGetLastError());
+  CU_TRY(nullptr, cudaStreamSynchronize(st));
+  return DLV3P_OK;
+}
+
+int dlv3p_op_resize_argmax(int device, const float* logits_planar, int B, int NC, int hi, int wi, int ho, int wo,
+                           uint8_t* labels, void* cuda_stream) {
+  int sms = 0, r = op_prolog(device, &sms);
+  if (r) return r;
+  if (!logits_planar || !labels || NC < 1 || NC > 256) return fail(nullptr, DLV3P_ERR_INVALID, "op_resize_argmax: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  ArgmaxParams P{};
+  P.logits = logits_planar; P.labels = labels; P.B = B; P.NC = NC; P.hi = hi; P.wi = wi; P.ho = ho; P.wo = wo;
+  P.sy = static_cast<float>(hi) / static_cast<float>(ho); P.sx = static_cast<float>(wi) / static_cast<float>(wo);
+  if (ho == 4 * hi && wo == 4 * wi)
+    resize_argmax_x4_kernel<<<grid_for(static_cast<size_t>(B) * (hi + 1) * (wi + 1), sms), 256, 0, st>>>(P);
+  else
+    resize_argmax_generic_kernel<<<grid_for(static_cast<size_t>(B) * ho * wo, sms), 256, 0, st>>>(P);
+  CU_TRY(nullptr, cudaGetLastError());
+  CU_TRY(nullptr, cudaStreamSynchronize(st));
+  return DLV3P_OK;
+}
+
+}  // extern "C"

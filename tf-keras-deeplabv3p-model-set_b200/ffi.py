@@ -1,0 +1,350 @@
+"""ctypes binding of libdlv3p.so (include/dlv3p.h) — no PyTorch, no cuda-python.
+
+This is the reference-side binding a maintainer of tf-keras-deeplabv3p-model-set would add (see
+INTEGRATION.md): plain pointers and sizes over the C ABI.  There is deliberately NO fallback: if the
+shared library is missing, or the machine has no sm_100 GPU, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libdlv3p.so')
+
+# ---- enums (mirror include/dlv3p.h) ----------------------------------------------------------
+STAGE_ASPP, STAGE_DECODER, STAGE_TAIL = 1, 2, 4
+VARIANT_ASPP, VARIANT_ASPP_LITE = 0, 1
+DTYPE_BF16, DTYPE_FP32 = 0, 2
+OUT_LABELS_U8, OUT_LOGITS_LOWRES, OUT_SOFTMAX, OUT_LOGITS_FULL, OUT_FEATURES_BF16, OUT_FEATURES_FP32 = range(6)
+FLAG_UNFUSED_DECODER = 1
+
+STATUS = {0: 'OK', -1: 'ERR_INVALID', -2: 'ERR_CUDA', -3: 'ERR_UNSUPPORTED', -4: 'ERR_STATE', -5: 'ERR_NOMEM', -6: 'ERR_NAME'}
+
+
+class Dlv3pError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__('dlv3p %s (%d): %s' % (STATUS.get(status, '?'), status, message))
+        self.status = status
+
+
+class Config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ('B', 'H', 'W', 'OS', 'h', 'w', 'hs', 'ws', 'Cin', 'Cskip', 'NC', 'variant', 'stages', 'in_dtype', 'out_mode')] + \
+               [('bn_eps', C.c_float), ('flags', C.c_int32)]
+
+
+# every symbol include/dlv3p.h declares: (name, restype, argtypes)
+_vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
+_fp = C.POINTER(C.c_float)
+SYMBOLS = [
+    ('dlv3p_abi_version', _i, []),
+    ('dlv3p_create', _i, [C.POINTER(Config), _i, C.POINTER(_vp)]),
+    ('dlv3p_destroy', None, [_vp]),
+    ('dlv3p_last_error', C.c_char_p, [_vp]),
+    ('dlv3p_set_weight', _i, [_vp, C.c_char_p, C.c_char_p, _fp, C.POINTER(C.c_int64), _i]),
+    ('dlv3p_num_weights', _i, [_vp]),
+    ('dlv3p_weight_info', _i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.POINTER(_i)]),
+    ('dlv3p_finalize_weights', _i, [_vp]),
+    ('dlv3p_forward', _i, [_vp, _vp, _vp, _vp, _vp]),
+    ('dlv3p_forward_host', _i, [_vp, _vp, _vp, _vp]),
+    ('dlv3p_input_bytes', _i, [_vp, C.POINTER(_sz), C.POINTER(_sz)]),
+    ('dlv3p_output_bytes', _i, [_vp, C.POINTER(_sz)]),
+    ('dlv3p_workspace_bytes', _i, [_vp, C.POINTER(_sz)]),
+    ('dlv3p_read_tap', _i, [_vp, C.c_char_p, _fp, _sz]),
+    ('dlv3p_launch_count', _i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    ('dlv3p_profile_forward', _i, [_vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_char_p), _fp, _i]),
+    ('dlv3p_device_count', _i, [C.POINTER(_i)]),
+    ('dlv3p_device_info', _i, [_i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_sz)]),
+    ('dlv3p_dev_alloc', _i, [_i, _sz, C.POINTER(_vp)]),
+    ('dlv3p_dev_free', _i, [_i, _vp]),
+    ('dlv3p_host_alloc_pinned', _i, [_sz, C.POINTER(_vp)]),
+    ('dlv3p_host_free_pinned', _i, [_vp]),
+    ('dlv3p_memcpy_h2d', _i, [_i, _vp, _vp, _sz]),
+    ('dlv3p_memcpy_d2h', _i, [_i, _vp, _vp, _sz]),
+    ('dlv3p_dev_memset', _i, [_i, _vp, _i, _sz]),
+    ('dlv3p_dev_synchronize', _i, [_i]),
+    ('dlv3p_op_pointwise', _i, [_i, _vp, C.c_int64, _i, _i, _fp, _fp, _fp, _i, _vp, _vp]),
+    ('dlv3p_op_depthwise', _i, [_i, _vp, _i, _i, _i, _i, _i, _fp, _fp, _fp, _i, _vp, _vp]),
+    ('dlv3p_op_sepconv', _i, [_i, _vp, _i, _i, _i, _i, _i, _fp, _fp, _fp, _i, _fp, _fp, _fp, _vp, _vp]),
+    ('dlv3p_op_resize_bilinear', _i, [_i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    ('dlv3p_op_resize_argmax', _i, [_i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+]
+
+_lib = None
+
+
+def load_library(path: Optional[str] = None) -> C.CDLL:
+    """dlopen libdlv3p.so and type every entry point. Raises if the extension has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise ImportError('libdlv3p.so not found at %s — build it first: python -c "import __graft_entry__ as g; g.build()" '
+                          '(there is no CPU / PyTorch fallback for this path)' % p)
+    lib = C.CDLL(p)
+    for name, res, args in SYMBOLS:
+        fn = getattr(lib, name)          # AttributeError here == header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    if lib.dlv3p_abi_version() != 1:
+        raise ImportError('libdlv3p.so ABI version %d, binding expects 1' % lib.dlv3p_abi_version())
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _check(status: int, ctx=None):
+    if status < 0:
+        msg = load_library().dlv3p_last_error(ctx)
+        raise Dlv3pError(status, msg.decode() if msg else '')
+    return status
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    st = load_library().dlv3p_device_count(C.byref(n))
+    return n.value if st == 0 else 0
+
+
+def device_info(device: int = 0) -> dict:
+    ma, mi, sms, mem = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+    _check(load_library().dlv3p_device_info(device, C.byref(ma), C.byref(mi), C.byref(sms), C.byref(mem)))
+    return {'sm': (ma.value, mi.value), 'sm_count': sms.value, 'total_mem': mem.value}
+
+
+# ---- bf16 <-> numpy (uint16 bit patterns; round to nearest even) ------------------------------
+def f32_to_bf16_bits(x: np.ndarray) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    u = x.view(np.uint32).astype(np.uint64)
+    r = (u + 0x7FFF + ((u >> 16) & 1)) >> 16
+    return (r & 0xFFFF).astype(np.uint16).reshape(x.shape)
+
+
+def bf16_bits_to_f32(b: np.ndarray) -> np.ndarray:
+    return (np.ascontiguousarray(b, dtype=np.uint16).astype(np.uint32) << 16).view(np.float32).reshape(b.shape)
+
+
+class DeviceBuffer:
+    """A cudaMalloc'ed buffer owned by Python (freed on GC)."""
+
+    def __init__(self, nbytes: int, device: int = 0):
+        self.device, self.nbytes = device, int(nbytes)
+        p = C.c_void_p()
+        _check(load_library().dlv3p_dev_alloc(device, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    @classmethod
+    def from_numpy(cls, a: np.ndarray, device: int = 0) -> 'DeviceBuffer':
+        a = np.ascontiguousarray(a)
+        buf = cls(a.nbytes, device)
+        buf.upload(a)
+        return buf
+
+    def upload(self, a: np.ndarray):
+        a = np.ascontiguousarray(a)
+        assert a.nbytes <= self.nbytes
+        _check(load_library().dlv3p_memcpy_h2d(self.device, self.ptr, a.ctypes.data, a.nbytes))
+
+    def download(self, shape: Sequence[int], dtype) -> np.ndarray:
+        out = np.empty(shape, dtype=dtype)
+        assert out.nbytes <= self.nbytes
+        _check(load_library().dlv3p_memcpy_d2h(self.device, out.ctypes.data, self.ptr, out.nbytes))
+        return out
+
+    def memset(self, value: int = 0):
+        _check(load_library().dlv3p_dev_memset(self.device, self.ptr, value, self.nbytes))
+
+    def free(self):
+        if getattr(self, 'ptr', None):
+            load_library().dlv3p_dev_free(self.device, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PinnedBuffer:
+    """cudaMallocHost'ed host memory exposed as a numpy array."""
+
+    def __init__(self, nbytes: int):
+        p = C.c_void_p()
+        _check(load_library().dlv3p_host_alloc_pinned(int(nbytes), C.byref(p)))
+        self.ptr, self.nbytes = p.value, int(nbytes)
+        self.array = np.ctypeslib.as_array((C.c_uint8 * self.nbytes).from_address(self.ptr))
+
+    def view(self, dtype, shape):
+        return self.array[:int(np.prod(shape)) * np.dtype(dtype).itemsize].view(dtype).reshape(shape)
+
+    def free(self):
+        if getattr(self, 'ptr', None):
+            self.array = None
+            load_library().dlv3p_host_free_pinned(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def synchronize(device: int = 0):
+    _check(load_library().dlv3p_dev_synchronize(device))
+
+
+class Context:
+    """One dlv3p_ctx: a head instance with static shapes on one device."""
+
+    def __init__(self, device: int = 0, **cfg):
+        self.lib = load_library()
+        self.cfg = Config()
+        for k, v in cfg.items():
+            if not hasattr(self.cfg, k):
+                raise TypeError('unknown config field %r' % k)
+            setattr(self.cfg, k, v)
+        self.device = device
+        h = C.c_void_p()
+        _check(self.lib.dlv3p_create(C.byref(self.cfg), device, C.byref(h)))
+        self.handle = h
+
+    # -- weights --------------------------------------------------------------------------
+    def weight_specs(self) -> List[Tuple[str, str, Tuple[int, ...]]]:
+        out = []
+        for i in range(self.lib.dlv3p_num_weights(self.handle)):
+            layer, var = C.c_char_p(), C.c_char_p()
+            shape = (C.c_int64 * 4)()
+            rank = C.c_int()
+            _check(self.lib.dlv3p_weight_info(self.handle, i, C.byref(layer), C.byref(var), shape, C.byref(rank)), self.handle)
+            out.append((layer.value.decode(), var.value.decode(), tuple(int(shape[j]) for j in range(rank.value))))
+        return out
+
+    def set_weight(self, layer: str, var: str, value: np.ndarray):
+        a = np.ascontiguousarray(value, dtype=np.float32)
+        shape = (C.c_int64 * a.ndim)(*a.shape)
+        _check(self.lib.dlv3p_set_weight(self.handle, layer.encode(), var.encode(),
+                                         a.ctypes.data_as(_fp), shape, a.ndim), self.handle)
+
+    def set_weights(self, weights: Dict[Tuple[str, str], np.ndarray], finalize: bool = True):
+        for (layer, var), v in weights.items():
+            self.set_weight(layer, var, v)
+        if finalize:
+            self.finalize()
+
+    def finalize(self):
+        _check(self.lib.dlv3p_finalize_weights(self.handle), self.handle)
+
+    # -- sizes ----------------------------------------------------------------------------
+    def input_bytes(self) -> Tuple[int, int]:
+        f, s = C.c_size_t(), C.c_size_t()
+        _check(self.lib.dlv3p_input_bytes(self.handle, C.byref(f), C.byref(s)), self.handle)
+        return f.value, s.value
+
+    def output_bytes(self) -> int:
+        o = C.c_size_t()
+        _check(self.lib.dlv3p_output_bytes(self.handle, C.byref(o)), self.handle)
+        return o.value
+
+    def workspace_bytes(self) -> int:
+        o = C.c_size_t()
+        _check(self.lib.dlv3p_workspace_bytes(self.handle, C.byref(o)), self.handle)
+        return o.value
+
+    # -- execution ------------------------------------------------------------------------
+    def forward(self, d_feat: int, d_skip: Optional[int], d_out: int, stream: int = 0):
+        _check(self.lib.dlv3p_forward(self.handle, d_feat, d_skip, d_out, stream), self.handle)
+
+    def forward_host(self, h_feat: np.ndarray, h_skip: Optional[np.ndarray], h_out: np.ndarray):
+        _check(self.lib.dlv3p_forward_host(self.handle, h_feat.ctypes.data, None if h_skip is None else h_skip.ctypes.data,
+                                           h_out.ctypes.data), self.handle)
+
+    def profile(self, d_feat: int, d_skip: Optional[int], d_out: int, stream: int = 0) -> List[Tuple[str, float]]:
+        names = (C.c_char_p * 64)()
+        ms = (C.c_float * 64)()
+        n = _check(self.lib.dlv3p_profile_forward(self.handle, d_feat, d_skip, d_out, stream, names, ms, 64), self.handle)
+        return [(names[i].decode(), float(ms[i])) for i in range(n)]
+
+    def read_tap(self, name: str, shape: Sequence[int]) -> np.ndarray:
+        out = np.empty(shape, dtype=np.float32)
+        _check(self.lib.dlv3p_read_tap(self.handle, name.encode(), out.ctypes.data_as(_fp), out.size), self.handle)
+        return out
+
+    def launch_count(self) -> Tuple[int, int]:
+        a, b = C.c_int64(), C.c_int64()
+        _check(self.lib.dlv3p_launch_count(self.handle, C.byref(a), C.byref(b)), self.handle)
+        return a.value, b.value
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            self.lib.dlv3p_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- standalone operators (unit parity tests) -------------------------------------------------
+def _f(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32).ctypes.data_as(_fp)
+
+
+def op_pointwise(a_bits: np.ndarray, w_kn: np.ndarray, scale=None, shift=None, relu=True, device=0) -> np.ndarray:
+    """a_bits: uint16 bf16 [M,K]; w_kn fp32 [K,N] -> uint16 bf16 [M,N]."""
+    M, K = a_bits.shape
+    N = w_kn.shape[1]
+    da = DeviceBuffer.from_numpy(a_bits, device)
+    do = DeviceBuffer(M * N * 2, device)
+    w = np.ascontiguousarray(w_kn, np.float32)
+    s = None if scale is None else np.ascontiguousarray(scale, np.float32)
+    t = None if shift is None else np.ascontiguousarray(shift, np.float32)
+    _check(load_library().dlv3p_op_pointwise(device, da.ptr, M, K, N, _f(w), _f(s), _f(t), int(relu), do.ptr, None))
+    return do.download((M, N), np.uint16)
+
+
+def op_depthwise(x_bits: np.ndarray, w_hwc: np.ndarray, rate: int, scale=None, shift=None, relu=True, device=0) -> np.ndarray:
+    B, H, W, Cc = x_bits.shape
+    dx = DeviceBuffer.from_numpy(x_bits, device)
+    do = DeviceBuffer(x_bits.nbytes, device)
+    w = np.ascontiguousarray(w_hwc, np.float32)
+    s = None if scale is None else np.ascontiguousarray(scale, np.float32)
+    t = None if shift is None else np.ascontiguousarray(shift, np.float32)
+    _check(load_library().dlv3p_op_depthwise(device, dx.ptr, B, H, W, Cc, rate, _f(w), _f(s), _f(t), int(relu), do.ptr, None))
+    return do.download(x_bits.shape, np.uint16)
+
+
+def op_sepconv(x_bits: np.ndarray, dw_hwc, dw_scale, dw_shift, pw_kn, pw_scale, pw_shift, rate: int = 1, device=0) -> np.ndarray:
+    B, H, W, Cc = x_bits.shape
+    N = pw_kn.shape[1]
+    dx = DeviceBuffer.from_numpy(x_bits, device)
+    do = DeviceBuffer(B * H * W * N * 2, device)
+    arrs = [np.ascontiguousarray(a, np.float32) for a in (dw_hwc, dw_scale, dw_shift, pw_kn, pw_scale, pw_shift)]
+    _check(load_library().dlv3p_op_sepconv(device, dx.ptr, B, H, W, Cc, rate, _f(arrs[0]), _f(arrs[1]), _f(arrs[2]), N,
+                                           _f(arrs[3]), _f(arrs[4]), _f(arrs[5]), do.ptr, None))
+    return do.download((B, H, W, N), np.uint16)
+
+
+def op_resize_bilinear(x_bits: np.ndarray, ho: int, wo: int, device=0) -> np.ndarray:
+    B, hi, wi, Cc = x_bits.shape
+    dx = DeviceBuffer.from_numpy(x_bits, device)
+    do = DeviceBuffer(B * ho * wo * Cc * 2, device)
+    _check(load_library().dlv3p_op_resize_bilinear(device, dx.ptr, B, hi, wi, Cc, ho, wo, do.ptr, None))
+    return do.download((B, ho, wo, Cc), np.uint16)
+
+
+def op_resize_argmax(logits_planar: np.ndarray, ho: int, wo: int, device=0) -> np.ndarray:
+    """logits fp32 [B,NC,hi,wi] planar -> uint8 [B,ho,wo]."""
+    B, NC, hi, wi = logits_planar.shape
+    dl = DeviceBuffer.from_numpy(np.ascontiguousarray(logits_planar, np.float32), device)
+    do = DeviceBuffer(B * ho * wo, device)
+    _check(load_library().dlv3p_op_resize_argmax(device, dl.ptr, B, NC, hi, wi, ho, wo, do.ptr, None))
+    return do.download((B, ho, wo), np.uint8)
