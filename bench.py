@@ -1,0 +1,321 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the DeepLabV3+ head hot path (BASELINE.json: images/sec, DeepLabV3+ Xception
+OS16 512x512 forward at 1/2/4/8 B200; ASPP %roofline).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (libdlv3p.so via ctypes)
+  python bench.py --impl reference --gpus N --steps K ...   # the reference path's CPU restatement (oracle), host cores
+  torchrun --nproc-per-node N ... bench.py --gpus N ...     # one rank per GPU; batch-sharded, no data-path collective
+
+One "step" = one forward of the head over one batch of synthetic backbone features (configs[1]: Xception OS16
+512x512, VOC 21 classes, batch 32 per GPU, bf16): ASPP -> Decoder -> classifier -> pred_resize -> argmax, uint8
+labels out.  The backbone is outside the hot path: the number is HEAD-ONLY images/s.
+
+PyTorch is used here only as plumbing: CUDA events on the launch stream, device buffers for the synthetic inputs and
+torch.distributed (NCCL) for the barrier / max-over-ranks.  The measured path is the C ABI.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# ---- workload: BASELINE.json configs[1] ---------------------------------------------------------------------------
+CFG = dict(B=32, H=512, W=512, OS=16, Cin=2048, Cskip=256, NC=21)
+WORKLOAD = 'DeepLabV3+ Xception OS16 512x512 VOC head (ASPP+decoder+classifier+resize+argmax), batch 32/GPU, bf16 forward'
+METRIC = 'images/sec DeepLabV3+ Xception OS16 512^2 fwd (head only)'
+
+# algorithmic work per image at this config (SURVEY.md §8(d), 2 FLOP per MAC; DESIGN.md "Measurement")
+GEMM_FLOP_PER_IMG = {
+    'aspp_branches_gemm': 4 * 2 * 1024 * 2048 * 256,          # aspp0 + three atrous pointwise convs
+    'concat_projection_gemm': 2 * 1024 * 1024 * 256,           # K = 1024: the b4 slice is a per-image bias
+    'feature_projection0_gemm': 2 * 16384 * 256 * 48,
+    'decoder_conv0_sepconv': 2 * 16384 * 304 * 256,
+    'decoder_conv1_sepconv': 2 * 16384 * 256 * 256,
+    'decoder_pointwise_gemm': 2 * 16384 * 280 * 256,           # unfused path only (mean of K=304 and K=256)
+    'classifier_gemm': 2 * 16384 * 256 * 21,
+}
+# algorithmic HBM bytes per image for the memory-bound kernels (read inputs once + write outputs once)
+HBM_BYTES_PER_IMG = {
+    'aspp_dw_pool': 1024 * 2048 * 2 * (1 + 3),                  # read x once, write three depthwise maps
+    'decoder_resize': 1024 * 256 * 2 + 16384 * 256 * 2,
+    'feature_projection0_gemm': 16384 * 256 * 2 + 16384 * 48 * 2,
+    'classifier_gemm': 16384 * 256 * 2 + 16384 * 21 * 4,
+    'resize_argmax': 16384 * 21 * 4 + 512 * 512,
+    'pool_proj': 2048 * 4 + 256 * 4,
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {'hbm_gbs': d['hbm_gbs'], 'tflops': d.get('bf16_tflops_sustained', d['bf16_tflops']),
+                'tflops_burst': d['bf16_tflops'], 'src': 'measured'}
+    return {'hbm_gbs': 6650.0, 'tflops': 1400.0, 'tflops_burst': 1590.0, 'src': 'fallback'}
+
+
+def random_weights(specs, seed=1234):
+    """Seeded random-init weights in Keras layout for ctx.weight_specs() (same recipe as SURVEY §8(c))."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for layer, var, shape in specs:
+        if var == 'kernel':
+            a = rng.normal(0.0, np.sqrt(2.0 / shape[2]), size=shape)
+        elif var == 'depthwise_kernel':
+            a = rng.normal(0.0, 0.3, size=shape)
+        elif var in ('gamma', 'moving_variance'):
+            a = rng.uniform(0.5, 1.5, size=shape)
+        else:
+            a = rng.normal(0.0, 0.1, size=shape)
+        out[(layer, var)] = a.astype(np.float32)
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu_index):
+        self.idx, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'power_w_max': max(pw) if pw else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def cpu_reference_throughput(budget_s=20.0, batch=2, max_iters=20):
+    """The reference path restated with torch-CPU ops (oracle/head_ref.py), fp32, all host threads — TensorFlow is
+    not installable here: 'restatement, not TensorFlow'. Bounded sample of the same workload."""
+    import torch
+    from oracle import head_ref as R
+    cfg = R.HeadConfig(B=batch, H=CFG['H'], W=CFG['W'], OS=CFG['OS'], Cin=CFG['Cin'], Cskip=CFG['Cskip'], NC=CFG['NC'])
+    W = R.make_weights(cfg, 1234)
+    feat, skip = R.make_inputs(cfg, 1236)
+    tf, ts = torch.from_numpy(feat), torch.from_numpy(skip)
+    R.head_forward_torch(tf, ts, W, cfg, 'fp32')              # warm-up (thread pool, allocator)
+    t0 = time.perf_counter()
+    it = 0
+    while it < max_iters and (it < 2 or time.perf_counter() - t0 < budget_s):
+        R.head_forward_torch(tf, ts, W, cfg, 'fp32')
+        it += 1
+    dt = time.perf_counter() - t0
+    return {'value': batch * it / dt, 'unit': 'images/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': '%d iterations of batch %d of the same workload, fp32 torch-CPU restatement incl. softmax+argmax (%.1f s)' % (it, batch, dt),
+            'host_cpus': os.cpu_count()}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    res = cpu_reference_throughput(budget_s=min(120.0, 6.0 * steps), batch=2, max_iters=max(2, steps))
+    line = {'impl': 'reference', 'metric': METRIC, 'value': res['value'], 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': steps,
+            'warmup': args.warmup, 'ms_per_step': 1000.0 * 2 / res['value'], 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD + ' [reference arm: batch 2 per step on host cores]'},
+            'cpu_baseline': res,
+            'e2e': {'value': res['value'], 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='dlv3p', choices=['dlv3p', 'reference'])
+    ap.add_argument('--batch', type=int, default=CFG['B'], help='per-GPU batch (default: the BASELINE config)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--unfused', action='store_true', help='A/B: standalone decoder depthwise kernels')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import dlv3p_b200
+    from dlv3p_b200 import ffi
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device — the hot path has no CPU fallback (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B = args.batch
+    flags = ffi.FLAG_UNFUSED_DECODER if args.unfused else 0
+    head = dlv3p_b200.DeepLabHead(B, CFG['H'], CFG['W'], CFG['OS'], CFG['Cin'], CFG['Cskip'], CFG['NC'], device=local_rank, flags=flags)
+    head.set_weights(random_weights(head.weight_specs()))
+    ctx = head.ctx
+
+    # synthetic backbone features, resident in HBM before the timed region (feat ~ relu(N(0,1)), skip ~ N(0,1))
+    g = torch.Generator(device='cuda').manual_seed(1236 + rank)
+    feat = torch.randn((B, 32, 32, CFG['Cin']), generator=g, device='cuda', dtype=torch.float32).clamp_(min=0).to(torch.bfloat16)
+    skip = torch.randn((B, 128, 128, CFG['Cskip']), generator=g, device='cuda', dtype=torch.float32).to(torch.bfloat16)
+    out = torch.empty((B, CFG['H'], CFG['W']), device='cuda', dtype=torch.uint8)
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+
+    def step():
+        ctx.forward(feat.data_ptr(), skip.data_ptr(), out.data_ptr(), sp)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # ---- timed region: exactly K steps, CUDA events on the launch stream, barrier + synchronize on both sides
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches_per_step = ctx.launch_count()[0]
+
+    # ---- per-kernel device times (CUDA events between launches, same stream): the roofline line
+    prof = {}
+    nprof = max(3, min(10, args.steps))
+    for _ in range(nprof):
+        for name, t in ctx.profile(feat.data_ptr(), skip.data_ptr(), out.data_ptr(), sp):
+            prof.setdefault(name, []).append(t)
+    prof = {k: float(np.mean(v)) for k, v in prof.items()}
+
+    # ---- end to end through the public host API: pinned host inputs -> H2D -> forward -> D2H labels, every step
+    fb, sb = ctx.input_bytes()
+    ob = ctx.output_bytes()
+    pin_f, pin_s, pin_o = ffi.PinnedBuffer(fb), ffi.PinnedBuffer(sb), ffi.PinnedBuffer(ob)
+    pin_f.view(np.uint16, (fb // 2,))[:] = feat.view(torch.int16).cpu().numpy().view(np.uint16).reshape(-1)
+    pin_s.view(np.uint16, (sb // 2,))[:] = skip.view(torch.int16).cpu().numpy().view(np.uint16).reshape(-1)
+    hf, hs, ho = pin_f.view(np.uint16, (fb // 2,)), pin_s.view(np.uint16, (sb // 2,)), pin_o.view(np.uint8, (ob,))
+    e2e_steps = max(3, min(args.steps, 10))
+    ctx.forward_host(hf, hs, ho)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.forward_host(hf, hs, ho)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1000.0
+    labels_ok = bool(np.array_equal(ho.reshape(B, CFG['H'], CFG['W']), out.cpu().numpy()))
+
+    # ---- max over ranks
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks = load_peaks()
+        total_imgs = B * world * args.steps
+        value = total_imgs / (ms / 1000.0)
+        # dominant kernel and its roofline
+        dom = max(prof, key=prof.get)
+        step_ms_prof = sum(prof.values())
+        if dom in GEMM_FLOP_PER_IMG and dom not in ('feature_projection0_gemm', 'classifier_gemm'):
+            ach = GEMM_FLOP_PER_IMG[dom] * B / (prof[dom] / 1000.0) / 1e12
+            roof = {'kernel': dom, 'bound': 'tensor', 'achieved': ach, 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
+                    'frac': ach / peaks['tflops'], 'frac_of_burst': ach / peaks['tflops_burst'], 'traffic': None,
+                    'peak_source': peaks['src'] + ' (sustained bf16; kernel timed inside a long step)'}
+        else:
+            byt = HBM_BYTES_PER_IMG.get(dom, 0) * B
+            ach = byt / (prof[dom] / 1000.0) / 1e9
+            roof = {'kernel': dom, 'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / peaks['hbm_gbs'],
+                    'traffic': None, 'peak_source': peaks['src']}
+        roof['kernel_ms'] = prof[dom]
+        roof['share_of_step'] = prof[dom] / step_ms_prof
+        gemm_flop = sum(GEMM_FLOP_PER_IMG[k] for k in prof if k in GEMM_FLOP_PER_IMG) * B
+        kernels = {}
+        for k, t in sorted(prof.items(), key=lambda kv: -kv[1]):
+            d = {'ms': round(t, 4)}
+            if k in GEMM_FLOP_PER_IMG:
+                d['tflops'] = round(GEMM_FLOP_PER_IMG[k] * B / (t / 1000.0) / 1e12, 1)
+            if k in HBM_BYTES_PER_IMG:
+                d['gbs'] = round(HBM_BYTES_PER_IMG[k] * B / (t / 1000.0) / 1e9, 1)
+            kernels[k] = d
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+            'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'batch_per_gpu': B, 'global_batch': B * world, 'sharding': 'batch (independent images, no collective)',
+                       'l2': 'inputs 402 MB/step per GPU > 126 MB L2 (no flush needed)', 'decoder': 'unfused' if args.unfused else 'fused'},
+            'e2e': {'value': B * world * e2e_steps / (e2e_ms / 1000.0), 'unit': 'images/s', 'h2d_bytes_per_step': fb + sb,
+                    'd2h_bytes_per_step': ob, 'steps': e2e_steps, 'labels_equal_device_path': labels_ok},
+            'gpu_launches': int(launches_per_step * args.steps),
+            'clocks': clocks,
+            'roofline': roof,
+            'whole_step': {'gemm_tflops': gemm_flop / (ms / args.steps / 1000.0) / 1e12, 'frac_of_tensor_peak': gemm_flop / (ms / args.steps / 1000.0) / 1e12 / peaks['tflops'],
+                           'sum_kernel_ms': step_ms_prof},
+            'kernels': kernels,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line['cpu_baseline'] = cpu_reference_throughput()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,4 +1,5 @@
-"""GPU parity tests, operator level: each CUDA kernel through the C ABI vs the oracle on the same seeded
+"""GPU parity tests, operator level (several cases exceed 148 tiles so that every persistent CTA loops over more
+than one tile — barrier phase wrap-around, both TMEM accumulator stages): each CUDA kernel through the C ABI vs the oracle on the same seeded
 inputs.  Integer outputs (labels) must be bit exact; bf16 outputs within one bf16 rounding of the fp32 result."""
 import numpy as np
 import pytest
@@ -21,7 +22,8 @@ def _assert_bf16_close(got_bits, ref_f32, extra_abs=0.0, what=''):
 
 
 @pytest.mark.parametrize('M,K,N', [(128, 64, 256), (256, 2048, 256), (1000, 304, 256), (4096, 256, 48), (777, 320, 256),
-                                    (512, 256, 24), (300, 1024, 256), (130, 160, 256), (64, 96, 16), (20000, 256, 256)])
+                                    (512, 256, 24), (300, 1024, 256), (130, 160, 256), (64, 96, 16), (20000, 256, 256),
+                                    (128 * 148 * 3 + 5, 64, 256), (128 * 148 * 5 + 77, 128, 48), (128 * 148 * 2 + 1, 320, 256)])
 def test_pointwise_gemm(gpu, M, K, N):
     """tcgen05 1x1 conv + BN + ReLU (layers.py:14-21, :141-143) incl. ragged M, K % 64 != 0, narrow N."""
     rng = np.random.default_rng(M + K + N)
@@ -53,7 +55,8 @@ def test_depthwise(gpu, B, H, W, C, rate):
 
 
 @pytest.mark.parametrize('B,H,W,C', [(1, 8, 16, 64), (2, 16, 32, 256), (1, 24, 40, 304), (1, 13, 21, 128), (3, 9, 7, 192),
-                                      (1, 64, 64, 304), (2, 32, 32, 320), (1, 5, 3, 8)])
+                                      (1, 64, 64, 304), (2, 32, 32, 320), (1, 5, 3, 8),
+                                      (4, 64, 128, 304), (8, 128, 128, 256), (6, 100, 76, 304), (5, 72, 88, 64)])
 def test_fused_sepconv(gpu, B, H, W, C):
     """SepConv_BN(depth_activation=True) fused: depthwise stencil as the on-chip A operand of the tcgen05 GEMM
     (layers.py:74-111; decoder_conv0 C=304, decoder_conv1 C=256)."""

@@ -23,7 +23,7 @@ def test_head_matches_golden(gpu, name):
     labels = hd(feat, skip)
     logits = planar_to_nhwc(hd.tap('logits'))
     assert rel_err(logits, z['logits_fp32']) < LOGIT_TOL, 'logits vs fp32 oracle: %.3g' % rel_err(logits, z['logits_fp32'])
-    assert rel_err(logits, z['logits_bf16']) < 4e-3, 'logits vs bf16-sim oracle: %.3g' % rel_err(logits, z['logits_bf16'])
+    assert rel_err(logits, z['logits_bf16']) < 8e-3, 'logits vs bf16-sim oracle: %.3g' % rel_err(logits, z['logits_bf16'])
     agree = (labels == z['labels_bf16']).mean()
     assert agree >= LABEL_AGREE, 'label agreement vs bf16-sim oracle %.5f' % agree
     assert (labels == z['labels_fp32']).mean() >= 0.98
@@ -170,7 +170,10 @@ def test_cfg3_cityscapes_os8_shapes(gpu):
     hd = make_head(cfg, W)
     labels = hd(feat, skip)
     o16 = R.head_forward_torch(feat, skip, W, cfg, 'bf16')
-    assert rel_err(planar_to_nhwc(hd.tap('logits')), o16['logits'].numpy()) < 4e-3
+    o32 = R.head_forward_torch(feat, skip, W, cfg, 'fp32')
+    logits = planar_to_nhwc(hd.tap('logits'))
+    assert rel_err(logits, o32['logits'].numpy()) < LOGIT_TOL
+    assert rel_err(logits, o16['logits'].numpy()) < 8e-3        # 1-ulp bf16 flips of intermediates on either side
     assert (labels == o16['labels'].numpy()).mean() >= LABEL_AGREE
     hd.close()
 
@@ -185,7 +188,10 @@ def test_cfg4_mobilenetv3_lite(gpu):
         hd = make_head(cfg, W)
         labels = hd(feat, skip)
         o16 = R.head_forward_torch(feat, skip, W, cfg, 'bf16')
-        assert rel_err(planar_to_nhwc(hd.tap('logits')), o16['logits'].numpy()) < 4e-3
+        o32 = R.head_forward_torch(feat, skip, W, cfg, 'fp32')
+        logits = planar_to_nhwc(hd.tap('logits'))
+        assert rel_err(logits, o32['logits'].numpy()) < LOGIT_TOL
+        assert rel_err(logits, o16['logits'].numpy()) < 8e-3
         assert (labels == o16['labels'].numpy()).mean() >= LABEL_AGREE
         hd.close()
 

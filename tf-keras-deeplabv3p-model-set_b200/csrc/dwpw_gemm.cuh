@@ -269,7 +269,13 @@ __global__ void __launch_bounds__(kDwThreads, 1) dwpw_gemm_kernel(const __grid_c
           }
           if (r >= 2) {  // output row r-2 is complete
             const int orow = r - 2;
-            if (orow == 0) mbar_wait(&a_empty[sa], ((c / AS) & 1) ^ 1);  // MMA finished with this A stage
+            if (orow == 0) {
+              // With a single A stage the two stencil groups alternate on the same barrier pair, so a group can be
+              // two phases away from a_empty's current phase and a bare parity wait could alias.  Order the groups:
+              // first see the other group's tile (c-1) published, then wait for the MMA that consumes it.
+              if (AS == 1 && c > 0) mbar_wait(&a_full[0], (c - 1) & 1);
+              mbar_wait(&a_empty[sa], ((c / AS) & 1) ^ 1);  // MMA finished with this A stage
+            }
 #pragma unroll
             for (int oc = 0; oc < 2; ++oc) {
               const unsigned long long lo = acc_lo[orow % 3][oc], hi = acc_hi[orow % 3][oc];
