@@ -199,6 +199,11 @@ int dlv3p_op_resize_bilinear(int device, const void* x_bf16, int B, int hi, int 
 int dlv3p_op_resize_argmax(int device, const float* logits_planar, int B, int NC, int hi, int wi,
                            int ho, int wo, uint8_t* labels, void* cuda_stream);
 
+/* Benchmark aid (tools/kbench.py): average ms per launch of ONE operator on synthetic device data (CUDA events).
+ * op 0 pointwise {M,K,N}; 1 fused sepconv {B,H,W,C}; 2 resize {B,hi,wi,C,ho,wo}; 3 resize_argmax {B,NC,hi,wi,ho,wo}.
+ * flags: per-kernel debug bits (skip stores / stencil / MMA) to attribute time; results are then meaningless. */
+int dlv3p_op_time(int device, int op, const int64_t* dims, int ndims, int iters, int flags, float* ms_out);
+
 #ifdef __cplusplus
 }
 #endif

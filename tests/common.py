@@ -37,3 +37,21 @@ def make_head(cfg, W, out_mode=0, in_dtype=0, flags=0, device=0):
 
 def planar_to_nhwc(a):
     return np.ascontiguousarray(np.transpose(a, (0, 2, 3, 1)))
+
+
+def label_agreement(labels, ref_labels, ref_logits_full, logit_tol=1e-2):
+    """Label parity that is honest about near-ties (with random-init weights ~1 % of pixels have a
+    top1-top2 margin below the logits tolerance itself).  Returns
+      overall    fraction of identical labels,
+      decided    fraction of identical labels among pixels whose oracle margin exceeds the logits tolerance
+                 (logit_tol * max|logit|) — a mismatch there would be a real error,
+      worst      largest oracle margin (relative to max|logit|) at a mismatching pixel."""
+    ref_logits_full = np.asarray(ref_logits_full, np.float32)
+    srt = np.sort(ref_logits_full, axis=-1)
+    margin = (srt[..., -1] - srt[..., -2]) / max(float(np.abs(ref_logits_full).max()), 1e-30)
+    same = np.asarray(labels) == np.asarray(ref_labels)
+    decided = margin > logit_tol
+    overall = float(same.mean())
+    dec = float(same[decided].mean()) if decided.any() else 1.0
+    worst = float(margin[~same].max()) if (~same).any() else 0.0
+    return overall, dec, worst

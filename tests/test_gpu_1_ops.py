@@ -113,3 +113,20 @@ def test_ops_reject_bad_arguments(gpu):
         ffi.op_sepconv(np.zeros((1, 8, 8, 64), np.uint16), np.zeros((3, 3, 64)), np.ones(64), np.zeros(64),
                        np.zeros((64, 256)), np.ones(256), np.zeros(256), rate=2)                # fused kernel: rate 1 only
     assert e.value.status == -3
+
+
+def test_fused_sepconv_is_deterministic_and_batch_independent(gpu):
+    """Many tiles per persistent CTA, identical images in every batch slot: any barrier-phase race between the
+    stencil warps shows up as slot-to-slot or run-to-run differences (integer comparison of the bf16 bit patterns)."""
+    rng = np.random.default_rng(2)
+    for C in (256, 304):
+        x1 = R.to_bf16_bits(rng.standard_normal((2, 128, 128, C)).astype(np.float32))
+        x = np.tile(x1, (12, 1, 1, 1))
+        dk = rng.standard_normal((3, 3, C)).astype(np.float32) * 0.3
+        pk = rng.standard_normal((C, 256)).astype(np.float32) * np.float32(np.sqrt(2.0 / C))
+        args = (dk, np.ones(C, np.float32), np.zeros(C, np.float32), pk, np.ones(256, np.float32), np.zeros(256, np.float32))
+        a = ffi.op_sepconv(x, *args)
+        b = ffi.op_sepconv(x, *args)
+        assert np.array_equal(a, b), 'C=%d: run-to-run difference on %d elements' % (C, (a != b).sum())
+        for rep in range(1, 12):
+            assert np.array_equal(a[:2], a[2 * rep:2 * rep + 2]), 'C=%d: batch slot %d differs from slot 0' % (C, rep)

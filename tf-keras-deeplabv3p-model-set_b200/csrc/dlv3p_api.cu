@@ -94,6 +94,10 @@ bool encode_2d_sw128(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t 
   }
   return true;
 }
+// 2D bf16 output view [rows, cols] (row stride ld elements), box {64, 32}, 128B swizzle: the epilogue's TMA store
+bool encode_2d_out(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, std::string* err) {
+  return encode_2d_sw128(tm, base, rows, cols, ld, 32, err);
+}
 // 4D bf16 NHWC {C, W, H, B} (channel stride ldc elements), box {64, bw, bh, 1}, no swizzle, OOB -> 0
 bool encode_4d_halo(CUtensorMap* tm, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint64_t ldc,
                     uint32_t bw, uint32_t bh, std::string* err) {
@@ -178,28 +182,28 @@ cudaError_t launch_pw(int BN, const PwLaunch& L, int num_sms, cudaStream_t st) {
   }
 }
 
-template <int KB, int AS>
+template <int KB, int AS, int IS>
 cudaError_t launch_dwpw_t(const DwPwParams& P, int num_sms, cudaStream_t st) {
   static bool attr_done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(dwpw_gemm_kernel<KB, AS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         DwPwCfg<KB, AS>::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(dwpw_gemm_kernel<KB, AS, IS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         DwPwCfg<KB, AS, IS>::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_done[dev & 63] = true;
   }
   const int grid = P.num_tiles < num_sms ? P.num_tiles : num_sms;
-  dwpw_gemm_kernel<KB, AS><<<grid, kDwThreads, DwPwCfg<KB, AS>::kSmemBytes, st>>>(P);
+  dwpw_gemm_kernel<KB, AS, IS><<<grid, kDwThreads, DwPwCfg<KB, AS, IS>::kSmemBytes, st>>>(P);
   return cudaGetLastError();
 }
 cudaError_t launch_dwpw(int KB, const DwPwParams& P, int num_sms, cudaStream_t st) {
   switch (KB) {
-    case 1: return launch_dwpw_t<1, 2>(P, num_sms, st);
-    case 2: return launch_dwpw_t<2, 2>(P, num_sms, st);
-    case 3: return launch_dwpw_t<3, 2>(P, num_sms, st);
-    case 4: return launch_dwpw_t<4, 2>(P, num_sms, st);
-    case 5: return launch_dwpw_t<5, 1>(P, num_sms, st);
+    case 1: return launch_dwpw_t<1, 2, 4>(P, num_sms, st);
+    case 2: return launch_dwpw_t<2, 2, 4>(P, num_sms, st);
+    case 3: return launch_dwpw_t<3, 2, 4>(P, num_sms, st);
+    case 4: return (P.debug & 8) ? launch_dwpw_t<4, 1, 3>(P, num_sms, st) : launch_dwpw_t<4, 2, 2>(P, num_sms, st);
+    case 5: return launch_dwpw_t<5, 1, 2>(P, num_sms, st);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -227,6 +231,7 @@ struct WeightSlot {
 enum TmSlot {
   TM_FEAT = 0, TM_DW1, TM_DW2, TM_DW3, TM_CONCAT, TM_SKIP, TM_DECIN, TM_DEC0, TM_CLS_IN,
   TM_W_ASPP0, TM_W_ASPP1, TM_W_ASPP2, TM_W_ASPP3, TM_W_PROJ, TM_W_FP0, TM_W_DEC0, TM_W_DEC1, TM_W_CLS,
+  TM_O_ASPP0, TM_O_ASPP1, TM_O_ASPP2, TM_O_ASPP3, TM_O_PROJ, TM_O_FP0, TM_O_DEC0, TM_O_DEC1,
   TM_COUNT
 };
 
@@ -277,7 +282,10 @@ struct dlv3p_ctx {
   __nv_bfloat16* dec0 = nullptr;       // [M2][256]
   __nv_bfloat16* dec1 = nullptr;       // [M2][256]
   float* logits = nullptr;             // [B][NC][ho*wo] planar
-  int nbands = 1, rows_per_band = 1;
+  int nbands = 1, pix_per_band = 256;   // pooling partials: ASPP Lite bands, or rate-0 phase items of the ASPP kernel
+  AsppDwParams aspp_plan{};
+  bool aspp_slab = false;               // small maps: shared-memory slab kernel
+  size_t aspp_slab_smem = 0;
 
   // packed weights
   PwWeights pw_aspp[4], pw_proj, pw_fp0, pw_dec0, pw_dec1, pw_cls;
@@ -551,8 +559,31 @@ int dlv3p_create(const dlv3p_config* cfg, int device, dlv3p_ctx** out) {
   const size_t B = g.B;
   if (c->st_aspp) {
     const int px = c->h * c->w;
-    c->rows_per_band = px <= 1024 ? c->h : (1024 / c->w > 0 ? 1024 / c->w : 1);
-    c->nbands = ceil_div(c->h, c->rows_per_band);
+    if (c->lite) {
+      c->pix_per_band = 256;
+      c->nbands = ceil_div(px, c->pix_per_band);
+    } else {
+      AsppDwParams& A = c->aspp_plan;
+      A.B = g.B; A.h = c->h; A.w_ = c->w; A.C = g.Cin; A.nrates = 3; A.nchunks = ceil_div(g.Cin, 64);
+      A.item_off[0] = 0;
+      for (int i = 0; i < 3; ++i) {
+        const int rr = c->rates[i];
+        A.rates[i] = rr;
+        const int nt = ceil_div(c->w, rr);
+        static const int kTs[5] = {2, 3, 4, 6, 8};
+        int sel = 4;
+        for (int k = 4; k >= 0; --k)
+          if (kTs[k] >= (nt < 8 ? nt : 8)) sel = k;
+        A.ts_sel[i] = sel;
+        A.nseg[i] = ceil_div(nt, kTs[sel]);
+        A.item_off[i + 1] = A.item_off[i] + rr * rr * A.nseg[i];
+      }
+      c->aspp_slab_smem = static_cast<size_t>(px) * 128 + (27 * 64 + 3 * 64 + 16 * 64) * sizeof(float);
+      c->aspp_slab = c->aspp_slab_smem <= 220 * 1024;
+      A.pool_items = c->aspp_slab ? 1 : A.item_off[1];
+      A.total_warps = static_cast<long long>(g.B) * A.item_off[3] * A.nchunks;
+      c->nbands = A.pool_items;
+    }
     if (!c->lite && (r = dev_alloc(c, &c->dw_out, 3 * static_cast<size_t>(c->M1) * g.Cin))) return bail(r, c->err);
     if ((r = dev_alloc(c, &c->pool_partial, B * c->nbands * g.Cin))) return bail(r, c->err);
     if ((r = dev_alloc(c, &c->img_shift, B * 256))) return bail(r, c->err);
@@ -718,6 +749,9 @@ int dlv3p_finalize_weights(dlv3p_ctx* c) {
       for (int i = 0; i < 3; ++i)
         ok = ok && enc2(TM_DW1 + i, c->dw_out + static_cast<size_t>(i) * c->M1 * g.Cin, c->M1, g.Cin, g.Cin, 128);
     ok = ok && enc2(TM_CONCAT, c->concat, c->M1, c->Ccat, c->Ccat, 128);
+    for (int i = 0; i < (c->lite ? 1 : 4); ++i)
+      ok = ok && encode_2d_out(&c->h_tm[TM_O_ASPP0 + i], c->concat + 256 * i, c->M1, 256, c->Ccat, &terr);
+    ok = ok && encode_2d_out(&c->h_tm[TM_O_PROJ], c->aspp_out, c->M1, 256, 256, &terr);
     if (c->feat_bf16) {
       ok = ok && enc2(TM_FEAT, c->feat_bf16, c->M1, g.Cin, g.Cin, 128);
       c->tm_feat_ptr = c->feat_bf16;
@@ -727,6 +761,9 @@ int dlv3p_finalize_weights(dlv3p_ctx* c) {
     ok = ok && enc2(TM_W_FP0, c->pw_fp0.w, c->pw_fp0.Npad, c->pw_fp0.Kpad, c->pw_fp0.Kpad, c->pw_fp0.Npad);
     ok = ok && enc2(TM_W_DEC0, c->pw_dec0.w, 256, c->pw_dec0.Kpad, c->pw_dec0.Kpad, 256);
     ok = ok && enc2(TM_W_DEC1, c->pw_dec1.w, 256, c->pw_dec1.Kpad, c->pw_dec1.Kpad, 256);
+    ok = ok && encode_2d_out(&c->h_tm[TM_O_FP0], c->dec_in + 256, c->M2, 48, 304, &terr);
+    ok = ok && encode_2d_out(&c->h_tm[TM_O_DEC0], c->dec0, c->M2, 256, 256, &terr);
+    ok = ok && encode_2d_out(&c->h_tm[TM_O_DEC1], c->dec1, c->M2, 256, 256, &terr);
     if (g.flags & DLV3P_FLAG_UNFUSED_DECODER) {
       ok = ok && enc2(TM_DECIN, c->dec_tmp, c->M2, 304, 304, 128);
       ok = ok && enc2(TM_DEC0, c->dec_tmp, c->M2, 256, 256, 128);
@@ -868,14 +905,25 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
   const __nv_bfloat16* x256 = feat;  // running 256-channel feature map
   // ------------------------------------------------------------------ ASPP (layers.py:114-196)
   if (c->st_aspp) {
-    if (L.begin("aspp_dw_pool")) {
-      AsppDwParams P{};
+    if (c->lite) {
+      if (L.begin("global_pool")) {
+        PoolParams P{};
+        P.x = feat; P.pool_partial = c->pool_partial; P.npix = c->h * c->w; P.C = g.Cin; P.nbands = c->nbands; P.pix_per_band = c->pix_per_band;
+        dim3 grid(ceil_div(g.Cin, 64), c->nbands, g.B);
+        global_pool_kernel<<<grid, 256, 0, st>>>(P);
+        L.end("global_pool", cudaGetLastError());
+      }
+    } else if (L.begin("aspp_dw_pool")) {
+      AsppDwParams P = c->aspp_plan;
       P.x = feat; P.w = c->aspp_dw_w; P.shift = c->aspp_dw_shift; P.out = c->dw_out; P.pool_partial = c->pool_partial;
-      P.B = g.B; P.h = c->h; P.w_ = c->w; P.C = g.Cin; P.nrates = c->lite ? 0 : 3;
-      for (int i = 0; i < 3; ++i) P.rates[i] = c->rates[i];
-      P.rows_per_band = c->rows_per_band; P.nbands = c->nbands;
-      dim3 grid(ceil_div(g.Cin, 64), c->nbands, g.B);
-      aspp_dw_pool_kernel<<<grid, 256, 0, st>>>(P);
+      if (c->aspp_slab) {
+        cudaError_t e = cudaFuncSetAttribute(aspp_dw_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->aspp_slab_smem));
+        const int slabs = g.B * P.nchunks;
+        if (e == cudaSuccess) aspp_dw_slab_kernel<<<slabs < c->num_sms ? slabs : c->num_sms, kSlabThreads, c->aspp_slab_smem, st>>>(P);
+      } else {
+        const long long blocks = (P.total_warps + 3) / 4;
+        aspp_dw_phase_kernel<<<static_cast<unsigned>(blocks), 128, 0, st>>>(P);
+      }
       L.end("aspp_dw_pool", cudaGetLastError());
     }
     if (L.begin("pool_proj")) {
@@ -884,7 +932,7 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
       P.ip_scale = c->ip_scale; P.ip_shift = c->ip_shift; P.w_proj4 = reinterpret_cast<const __nv_bfloat16*>(c->w_proj4);
       P.proj_scale = c->pw_proj.scale; P.proj_shift = c->pw_proj.shift; P.img_shift = c->img_shift; P.b4_out = c->b4;
       P.C = g.Cin; P.nbands = c->nbands; P.inv_count = 1.0f / static_cast<float>(c->h * c->w);
-      pool_proj_kernel<<<g.B, 256, (g.Cin + 256) * sizeof(float), st>>>(P);
+      pool_proj_kernel<<<g.B, 1024, (g.Cin + 256 + 1024) * sizeof(float), st>>>(P);
       L.end("pool_proj", cudaGetLastError());
     }
     if (L.begin("aspp_branches_gemm")) {
@@ -895,6 +943,7 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
         PwProblem& p = PL.prob[i];
         p.tmap_a = &c->d_tm[i == 0 ? TM_FEAT : TM_DW1 + (i - 1)];
         p.tmap_w = &c->d_tm[TM_W_ASPP0 + i];
+        p.tmap_out = &c->d_tm[TM_O_ASPP0 + i];
         p.scale = c->pw_aspp[i].scale; p.shift = c->pw_aspp[i].shift; p.img_shift = nullptr;
         p.out = c->concat; p.K = g.Cin; p.N = 256; p.ldo = c->Ccat; p.col_off = 256 * i; p.relu = 1; p.epi = kEpiBf16;
       }
@@ -904,7 +953,7 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
       PwLaunch PL{};
       PL.num_problems = 1; PL.M = c->M1; PL.num_tiles = ceil_div(c->M1, kPwBM); PL.rows_per_img = c->h * c->w;
       PwProblem& p = PL.prob[0];
-      p.tmap_a = &c->d_tm[TM_CONCAT]; p.tmap_w = &c->d_tm[TM_W_PROJ];
+      p.tmap_a = &c->d_tm[TM_CONCAT]; p.tmap_w = &c->d_tm[TM_W_PROJ]; p.tmap_out = &c->d_tm[TM_O_PROJ];
       p.scale = c->pw_proj.scale; p.shift = c->pw_proj.shift; p.img_shift = c->img_shift;
       p.out = c->aspp_out; p.K = c->Ccat; p.N = 256; p.ldo = 256; p.col_off = 0; p.relu = 1; p.epi = kEpiBf16ImgShift;
       L.end("concat_projection_gemm", launch_pw(256, PL, c->num_sms, st));
@@ -918,22 +967,22 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
       P.x = x256; P.out = c->dec_in; P.B = g.B; P.hi = c->h; P.wi = c->w; P.C = 256; P.ho = c->hs; P.wo = c->ws;
       P.ldo = 304; P.col_off = 0;
       P.sy = static_cast<float>(c->h) / static_cast<float>(c->hs); P.sx = static_cast<float>(c->w) / static_cast<float>(c->ws);
-      resize_bilinear_kernel<<<grid_for(static_cast<size_t>(c->M2) * 32, c->num_sms), 256, 0, st>>>(P);
+      resize_bilinear_kernel<<<dim3(c->hs, g.B), 256, 0, st>>>(P);
       L.end("decoder_resize", cudaGetLastError());
     }
     if (L.begin("feature_projection0_gemm")) {
       PwLaunch PL{};
       PL.num_problems = 1; PL.M = c->M2; PL.num_tiles = ceil_div(c->M2, kPwBM); PL.rows_per_img = c->hs * c->ws;
       PwProblem& p = PL.prob[0];
-      p.tmap_a = &c->d_tm[TM_SKIP]; p.tmap_w = &c->d_tm[TM_W_FP0];
+      p.tmap_a = &c->d_tm[TM_SKIP]; p.tmap_w = &c->d_tm[TM_W_FP0]; p.tmap_out = &c->d_tm[TM_O_FP0];
       p.scale = c->pw_fp0.scale; p.shift = c->pw_fp0.shift; p.img_shift = nullptr;
       p.out = c->dec_in; p.K = g.Cskip; p.N = 48; p.ldo = 304; p.col_off = 256; p.relu = 1; p.epi = kEpiBf16;
       L.end("feature_projection0_gemm", launch_pw(64, PL, c->num_sms, st));
     }
     const int tiles_x = ceil_div(c->ws, kDwTW), tiles_y = ceil_div(c->hs, kDwTH);
-    struct SepRun { const char* name; const __nv_bfloat16* in; int C; int tm_x; int tm_w; DwWeights* dw; PwWeights* pw; __nv_bfloat16* out; };
-    SepRun runs[2] = {{"decoder_conv0_sepconv", c->dec_in, 304, TM_DECIN, TM_W_DEC0, &c->dw_dec0, &c->pw_dec0, c->dec0},
-                      {"decoder_conv1_sepconv", c->dec0, 256, TM_DEC0, TM_W_DEC1, &c->dw_dec1, &c->pw_dec1, c->dec1}};
+    struct SepRun { const char* name; const __nv_bfloat16* in; int C; int tm_x; int tm_w; int tm_o; DwWeights* dw; PwWeights* pw; __nv_bfloat16* out; };
+    SepRun runs[2] = {{"decoder_conv0_sepconv", c->dec_in, 304, TM_DECIN, TM_W_DEC0, TM_O_DEC0, &c->dw_dec0, &c->pw_dec0, c->dec0},
+                      {"decoder_conv1_sepconv", c->dec0, 256, TM_DEC0, TM_W_DEC1, TM_O_DEC1, &c->dw_dec1, &c->pw_dec1, c->dec1}};
     for (const SepRun& s : runs) {
       if (g.flags & DLV3P_FLAG_UNFUSED_DECODER) {
         if (L.begin("decoder_depthwise")) {
@@ -947,7 +996,7 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
           PwLaunch PL{};
           PL.num_problems = 1; PL.M = c->M2; PL.num_tiles = ceil_div(c->M2, kPwBM); PL.rows_per_img = c->hs * c->ws;
           PwProblem& p = PL.prob[0];
-          p.tmap_a = &c->d_tm[s.tm_x]; p.tmap_w = &c->d_tm[s.tm_w];
+          p.tmap_a = &c->d_tm[s.tm_x]; p.tmap_w = &c->d_tm[s.tm_w]; p.tmap_out = &c->d_tm[s.tm_o];
           p.scale = s.pw->scale; p.shift = s.pw->shift; p.img_shift = nullptr;
           p.out = s.out; p.K = s.C; p.N = 256; p.ldo = 256; p.col_off = 0; p.relu = 1; p.epi = kEpiBf16;
           L.end("decoder_pointwise_gemm", launch_pw(256, PL, c->num_sms, st));
@@ -1146,14 +1195,15 @@ int dlv3p_op_pointwise(int device, const void* a_bf16, int64_t M, int K, int N, 
   float* ds = tmp.put(s);
   float* dt = tmp.put(t);
   std::string terr;
-  std::vector<CUtensorMap> tm(2);
-  if (!encode_2d_sw128(&tm[0], a_bf16, M, K, K, 128, &terr) || !encode_2d_sw128(&tm[1], dw, BN, Kpad, Kpad, BN, &terr)) return fail(nullptr, DLV3P_ERR_CUDA, terr);
+  std::vector<CUtensorMap> tm(3);
+  if (!encode_2d_sw128(&tm[0], a_bf16, M, K, K, 128, &terr) || !encode_2d_sw128(&tm[1], dw, BN, Kpad, Kpad, BN, &terr) ||
+      !encode_2d_out(&tm[2], out_bf16, M, N, N, &terr)) return fail(nullptr, DLV3P_ERR_CUDA, terr);
   CUtensorMap* dtm = tmp.put(tm);
   if (!dw || !ds || !dt || !dtm) return fail(nullptr, DLV3P_ERR_NOMEM, "op_pointwise: cudaMalloc failed");
   PwLaunch PL{};
   PL.num_problems = 1; PL.M = static_cast<int>(M); PL.num_tiles = ceil_div(static_cast<int>(M), kPwBM); PL.rows_per_img = static_cast<int>(M);
   PwProblem& p = PL.prob[0];
-  p.tmap_a = &dtm[0]; p.tmap_w = &dtm[1]; p.scale = ds; p.shift = dt; p.img_shift = nullptr; p.out = out_bf16;
+  p.tmap_a = &dtm[0]; p.tmap_w = &dtm[1]; p.tmap_out = &dtm[2]; p.scale = ds; p.shift = dt; p.img_shift = nullptr; p.out = out_bf16;
   p.K = K; p.N = N; p.ldo = N; p.col_off = 0; p.relu = relu; p.epi = kEpiBf16;
   CU_TRY(nullptr, launch_pw(BN, PL, sms, st));
   CU_TRY(nullptr, cudaStreamSynchronize(st));
@@ -1226,7 +1276,7 @@ int dlv3p_op_resize_bilinear(int device, const void* x_bf16, int B, int hi, int 
   P.x = static_cast<const __nv_bfloat16*>(x_bf16); P.out = static_cast<__nv_bfloat16*>(out_bf16);
   P.B = B; P.hi = hi; P.wi = wi; P.C = C; P.ho = ho; P.wo = wo; P.ldo = C; P.col_off = 0;
   P.sy = static_cast<float>(hi) / static_cast<float>(ho); P.sx = static_cast<float>(wi) / static_cast<float>(wo);
-  resize_bilinear_kernel<<<grid_for(static_cast<size_t>(B) * ho * wo * (C / 8), sms), 256, 0, st>>>(P);
+  resize_bilinear_kernel<<<dim3(ho, B), 256, 0, st>>>(P);
   CU_TRY(nullptr, cudaGetLastError());
   CU_TRY(nullptr, cudaStreamSynchronize(st));
   return DLV3P_OK;
@@ -1248,6 +1298,122 @@ int dlv3p_op_resize_argmax(int device, const float* logits_planar, int B, int NC
   CU_TRY(nullptr, cudaGetLastError());
   CU_TRY(nullptr, cudaStreamSynchronize(st));
   return DLV3P_OK;
+}
+
+
+// Benchmark aid (tools/kbench.py): ms per launch of one operator on synthetic device data, CUDA events, `iters` launches.
+int dlv3p_op_time(int device, int op, const int64_t* d, int ndims, int iters, int flags, float* ms_out) {
+  int sms = 0, r = op_prolog(device, &sms);
+  if (r) return r;
+  if (!d || !ms_out || iters < 1) return fail(nullptr, DLV3P_ERR_INVALID, "op_time: bad arguments");
+  TmpDev tmp;
+  cudaStream_t st = nullptr;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  std::string terr;
+  auto fill = [&](size_t n) -> uint16_t* {   // bf16 pattern data (small finite values)
+    std::vector<uint16_t> h(n);
+    uint32_t sd = 12345u;
+    for (size_t i = 0; i < n; ++i) { sd = sd * 1664525u + 1013904223u; h[i] = f32_to_bf16_rne(static_cast<float>((sd >> 16) & 0xFF) / 128.0f - 1.0f); }
+    return tmp.put(h);
+  };
+  auto run = [&](auto&& launch) -> int {
+    for (int i = 0; i < 2; ++i) launch();
+    if (cudaStreamSynchronize(st) != cudaSuccess) return fail(nullptr, DLV3P_ERR_CUDA, fmt("op_time warmup: %s", cudaGetErrorString(cudaGetLastError())));
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < iters; ++i) launch();
+    cudaEventRecord(e1, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(nullptr, DLV3P_ERR_CUDA, fmt("op_time: %s", cudaGetErrorString(e)));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *ms_out = ms / iters;
+    return DLV3P_OK;
+  };
+  int rc = DLV3P_ERR_INVALID;
+  if (op == 0 && ndims >= 3) {   // pointwise {M,K,N}
+    const int M = static_cast<int>(d[0]), K = static_cast<int>(d[1]), N = static_cast<int>(d[2]);
+    const int BN = pick_bn(N), Kpad = ceil_div(K, 64) * 64;
+    uint16_t* a = fill(static_cast<size_t>(M) * K);
+    uint16_t* w = fill(static_cast<size_t>(BN) * Kpad);
+    uint16_t* o = tmp.alloc<uint16_t>(static_cast<size_t>(M) * N);
+    float* s = tmp.put(std::vector<float>(BN, 1.0f));
+    float* t = tmp.put(std::vector<float>(BN, 0.0f));
+    if (N % 8) return fail(nullptr, DLV3P_ERR_INVALID, "op_time pointwise: N % 8");
+    std::vector<CUtensorMap> tm(3);
+    if (!encode_2d_sw128(&tm[0], a, M, K, K, 128, &terr) || !encode_2d_sw128(&tm[1], w, BN, Kpad, Kpad, BN, &terr) ||
+        !encode_2d_out(&tm[2], o, M, N, N, &terr)) return fail(nullptr, DLV3P_ERR_CUDA, terr);
+    CUtensorMap* dtm = tmp.put(tm);
+    PwLaunch PL{};
+    PL.num_problems = 1; PL.M = M; PL.num_tiles = ceil_div(M, kPwBM); PL.rows_per_img = M; PL.debug = flags;
+    PwProblem& p = PL.prob[0];
+    p.tmap_a = &dtm[0]; p.tmap_w = &dtm[1]; p.tmap_out = &dtm[2]; p.scale = s; p.shift = t; p.out = o; p.K = K; p.N = N; p.ldo = N; p.relu = 1; p.epi = kEpiBf16;
+    rc = run([&] { launch_pw(BN, PL, sms, st); });
+  } else if (op == 1 && ndims >= 4) {   // fused sepconv {B,H,W,C}
+    const int B = static_cast<int>(d[0]), H = static_cast<int>(d[1]), W_ = static_cast<int>(d[2]), C = static_cast<int>(d[3]);
+    const int KB = ceil_div(C, 64), Cpad = KB * 64;
+    if (KB > 5) return fail(nullptr, DLV3P_ERR_UNSUPPORTED, "op_time sepconv: C <= 320");
+    uint16_t* x = fill(static_cast<size_t>(B) * H * W_ * C);
+    uint16_t* w = fill(static_cast<size_t>(256) * Cpad);
+    uint16_t* o = tmp.alloc<uint16_t>(static_cast<size_t>(B) * H * W_ * 256);
+    float* dw = tmp.put(std::vector<float>(static_cast<size_t>(9) * Cpad, 0.1f));
+    float* dsh = tmp.put(std::vector<float>(Cpad, 0.0f));
+    float* s = tmp.put(std::vector<float>(256, 1.0f));
+    float* t = tmp.put(std::vector<float>(256, 0.0f));
+    std::vector<CUtensorMap> tm(2);
+    if (!encode_4d_halo(&tm[0], x, B, H, W_, C, C, kDwHaloW, kDwHaloH, &terr) || !encode_2d_sw128(&tm[1], w, 256, Cpad, Cpad, 256, &terr)) return fail(nullptr, DLV3P_ERR_CUDA, terr);
+    CUtensorMap* dtm = tmp.put(tm);
+    DwPwParams P{};
+    P.tmap_x = &dtm[0]; P.tmap_w = &dtm[1]; P.dw_w = dw; P.dw_shift = dsh; P.scale = s; P.shift = t;
+    P.out = reinterpret_cast<__nv_bfloat16*>(o); P.B = B; P.H = H; P.W = W_;
+    P.tiles_x = ceil_div(W_, kDwTW); P.tiles_y = ceil_div(H, kDwTH); P.num_tiles = B * P.tiles_x * P.tiles_y; P.debug = flags;
+    rc = run([&] { launch_dwpw(KB, P, sms, st); });
+  } else if (op == 2 && ndims >= 6) {   // resize {B,hi,wi,C,ho,wo}
+    ResizeParams P{};
+    P.B = static_cast<int>(d[0]); P.hi = static_cast<int>(d[1]); P.wi = static_cast<int>(d[2]); P.C = static_cast<int>(d[3]);
+    P.ho = static_cast<int>(d[4]); P.wo = static_cast<int>(d[5]); P.ldo = P.C; P.col_off = 0;
+    P.sy = static_cast<float>(P.hi) / P.ho; P.sx = static_cast<float>(P.wi) / P.wo;
+    P.x = reinterpret_cast<__nv_bfloat16*>(fill(static_cast<size_t>(P.B) * P.hi * P.wi * P.C));
+    P.out = reinterpret_cast<__nv_bfloat16*>(tmp.alloc<uint16_t>(static_cast<size_t>(P.B) * P.ho * P.wo * P.C));
+    rc = run([&] { resize_bilinear_kernel<<<dim3(P.ho, P.B), 256, 0, st>>>(P); });
+  } else if (op == 3 && ndims >= 6) {   // resize_argmax {B,NC,hi,wi,ho,wo}
+    ArgmaxParams P{};
+    P.B = static_cast<int>(d[0]); P.NC = static_cast<int>(d[1]); P.hi = static_cast<int>(d[2]); P.wi = static_cast<int>(d[3]);
+    P.ho = static_cast<int>(d[4]); P.wo = static_cast<int>(d[5]);
+    P.sy = static_cast<float>(P.hi) / P.ho; P.sx = static_cast<float>(P.wi) / P.wo;
+    const size_t n = static_cast<size_t>(P.B) * P.NC * P.hi * P.wi;
+    std::vector<float> h(n);
+    uint32_t sd = 777u;
+    for (size_t i = 0; i < n; ++i) { sd = sd * 1664525u + 1013904223u; h[i] = static_cast<float>(sd >> 8) / 8388608.0f - 1.0f; }
+    P.logits = tmp.put(h);
+    P.labels = tmp.alloc<uint8_t>(static_cast<size_t>(P.B) * P.ho * P.wo);
+    const bool x4 = P.ho == 4 * P.hi && P.wo == 4 * P.wi && !(flags & 1);
+    rc = run([&] {
+      if (x4) resize_argmax_x4_kernel<<<grid_for(static_cast<size_t>(P.B) * (P.hi + 1) * (P.wi + 1), sms), 256, 0, st>>>(P);
+      else resize_argmax_generic_kernel<<<grid_for(static_cast<size_t>(P.B) * P.ho * P.wo, sms), 256, 0, st>>>(P);
+    });
+  } else if (op == 4 && ndims >= 4) {   // ASPP depthwise slab kernel {B,h,w,C} at OS16 rates
+    AsppDwParams P{};
+    P.B = static_cast<int>(d[0]); P.h = static_cast<int>(d[1]); P.w_ = static_cast<int>(d[2]); P.C = static_cast<int>(d[3]);
+    P.nrates = 3; P.rates[0] = 6; P.rates[1] = 12; P.rates[2] = 18; P.nchunks = ceil_div(P.C, 64); P.pool_items = 1; P.debug = flags;
+    const size_t n = static_cast<size_t>(P.B) * P.h * P.w_ * P.C;
+    P.x = reinterpret_cast<__nv_bfloat16*>(fill(n));
+    P.out = reinterpret_cast<__nv_bfloat16*>(tmp.alloc<uint16_t>(3 * n));
+    P.w = tmp.put(std::vector<float>(static_cast<size_t>(27) * P.C, 0.1f));
+    P.shift = tmp.put(std::vector<float>(static_cast<size_t>(3) * P.C, 0.0f));
+    P.pool_partial = tmp.alloc<float>(static_cast<size_t>(P.B) * P.C);
+    const size_t smem = static_cast<size_t>(P.h) * P.w_ * 128 + (27 * 64 + 3 * 64 + 16 * 64) * sizeof(float);
+    if (smem > 220 * 1024) return fail(nullptr, DLV3P_ERR_UNSUPPORTED, "op_time aspp_dw: map too large for the slab kernel");
+    cudaFuncSetAttribute(aspp_dw_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    const int slabs = P.B * P.nchunks;
+    rc = run([&] { aspp_dw_slab_kernel<<<slabs < sms ? slabs : sms, kSlabThreads, smem, st>>>(P); });
+  } else {
+    rc = fail(nullptr, DLV3P_ERR_INVALID, "op_time: unknown op / too few dims");
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return rc;
 }
 
 }  // extern "C"

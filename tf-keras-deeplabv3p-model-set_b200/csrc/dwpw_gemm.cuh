@@ -27,7 +27,6 @@ constexpr int kDwHaloW = kDwTW + 2;
 constexpr int kDwInStageBytes = kDwHaloH * kDwHaloW * 128;  // 64 bf16 channels per pixel
 constexpr int kDwAStageBytes = 128 * 128;
 constexpr int kDwWBlockBytes = 256 * 128;
-constexpr int kDwInStages = 2;
 constexpr int kDwThreads = 14 * 32;
 constexpr int kDwBN = 256;
 
@@ -41,14 +40,15 @@ struct DwPwParams {
   __nv_bfloat16* out;         // [B, H, W, 256]
   int B, H, W;
   int tiles_x, tiles_y, num_tiles;
+  int debug;  // benchmark aid: bit0 skip epilogue stores, bit1 skip the stencil math (A tiles left stale), bit2 skip the MMAs
 };
 
-template <int KB, int AS>
+template <int KB, int AS, int kDwInStages>
 struct DwPwCfg {
   static constexpr int kWBytes = KB * kDwWBlockBytes;
   static constexpr int kABytes = AS * kDwAStageBytes;
   static constexpr int kInBytes = kDwInStages * kDwInStageBytes;
-  static constexpr int kSmemBytes = kWBytes + kABytes + kInBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kWBytes + kABytes + kInBytes + 2048 /*BN scale+shift*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
@@ -65,15 +65,18 @@ __device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long 
   asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
 }
 
-template <int KB, int AS>
+template <int KB, int AS, int kDwInStages>
 __global__ void __launch_bounds__(kDwThreads, 1) dwpw_gemm_kernel(const __grid_constant__ DwPwParams P) {
-  using Cfg = DwPwCfg<KB, AS>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using Cfg = DwPwCfg<KB, AS, kDwInStages>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;   // dynamic smem is the only shared memory of this kernel: 1024-byte aligned (checked below)
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
   uint8_t* smem_w = smem;                      // KB x [256 rows x 128 B], swizzled
   uint8_t* smem_a = smem_w + Cfg::kWBytes;     // AS x [128 rows x 128 B], swizzled
   uint8_t* smem_in = smem_a + Cfg::kABytes;    // kDwInStages x [10][18][64] bf16
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_in + Cfg::kInBytes);
+  float* s_scale = reinterpret_cast<float*>(smem_in + Cfg::kInBytes);   // [256] pointwise BN scale (L1 is ~0 KB here)
+  float* s_shift = s_scale + 256;                                        // [256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
   uint64_t* w_full = bars;                     // [1]
   uint64_t* in_full = bars + 1;                // [kDwInStages]
   uint64_t* in_empty = in_full + kDwInStages;  // [kDwInStages]
@@ -105,6 +108,10 @@ __global__ void __launch_bounds__(kDwThreads, 1) dwpw_gemm_kernel(const __grid_c
   if (warp == 1) {
     tmem_alloc(tmem_base_ptr, 512);
     tmem_relinquish();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 256) {
+    s_scale[threadIdx.x - 64] = P.scale[threadIdx.x - 64];
+    s_shift[threadIdx.x - 64] = P.shift[threadIdx.x - 64];
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -151,12 +158,14 @@ __global__ void __launch_bounds__(kDwThreads, 1) dwpw_gemm_kernel(const __grid_c
         mbar_wait(&a_full[sa], ph);
         tcgen05_fence_after();
         if (elect_one()) {
+          if (!(P.debug & 4)) {
           const uint64_t da = make_smem_desc_sw128(smem_u32(smem_a + sa * kDwAStageBytes));
           const uint64_t db = make_smem_desc_sw128(smem_u32(smem_w + kb * kDwWBlockBytes));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_bf16_ss(tmem_d, smem_desc_advance(da, k * 32), smem_desc_advance(db, k * 32), idesc,
                          (kb > 0 || k > 0) ? 1u : 0u);
+          }
           umma_commit(&a_empty[sa]);
           if (kb == KB - 1) umma_commit(&tmem_full[acc]);
         }
@@ -190,8 +199,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) dwpw_gemm_kernel(const __grid_c
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 s = __ldg(reinterpret_cast<const float4*>(P.scale + c0 + j));
-          const float4 t = __ldg(reinterpret_cast<const float4*>(P.shift + c0 + j));
+          const float4 s = *reinterpret_cast<const float4*>(s_scale + c0 + j);
+          const float4 t = *reinterpret_cast<const float4*>(s_shift + c0 + j);
           const float y0 = fmaxf(fmaf(__uint_as_float(v[j + 0]), s.x, t.x), 0.0f);
           const float y1 = fmaxf(fmaf(__uint_as_float(v[j + 1]), s.y, t.y), 0.0f);
           const float y2 = fmaxf(fmaf(__uint_as_float(v[j + 2]), s.z, t.z), 0.0f);
@@ -199,9 +208,11 @@ __global__ void __launch_bounds__(kDwThreads, 1) dwpw_gemm_kernel(const __grid_c
           pk[j / 2 + 0] = pack_bf16x2(y0, y1);
           pk[j / 2 + 1] = pack_bf16x2(y2, y3);
         }
-        if (ok) {
+        if (ok && !(P.debug & 1)) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) stg_v4(o + c0 + j * 8, make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
+          for (int j = 0; j < 2; ++j)
+            stg_v8(o + c0 + j * 16, make_uint4(pk[8 * j], pk[8 * j + 1], pk[8 * j + 2], pk[8 * j + 3]),
+                   make_uint4(pk[8 * j + 4], pk[8 * j + 5], pk[8 * j + 6], pk[8 * j + 7]));
         }
       }
       tcgen05_fence_before();
@@ -215,23 +226,34 @@ __global__ void __launch_bounds__(kDwThreads, 1) dwpw_gemm_kernel(const __grid_c
     const int cp = wg * 2 + (lane >> 4);    // column pair: output cols 2cp, 2cp+1
     const uint32_t in_base = smem_u32(smem_in);
     const uint32_t a_base = smem_u32(smem_a);
-    uint32_t c = 0;
-    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
-      for (int kb = 0; kb < KB; ++kb, ++c) {
-        if ((c & 1u) != static_cast<uint32_t>(g)) continue;
-        // taps + shift for this thread's 4 channels (L1-resident, 40 floats)
-        const int ch = kb * 64 + v4 * 4;
-        unsigned long long wlo[9], whi[9];
+    // this CTA's K blocks are numbered c = 0, 1, 2, ... over (tile, kb); group g owns the blocks with c % 2 == g
+    int my_tiles = 0;
+    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) ++my_tiles;
+    const uint32_t total_c = static_cast<uint32_t>(my_tiles) * KB;
+    unsigned long long wlo[9], whi[9], sh_lo, sh_hi;
+    auto load_taps = [&](uint32_t cn) {   // taps + shift of this thread's 4 channels; L1 is ~0 KB here -> L2 latency, so issue early
+      const int ch = static_cast<int>(cn % KB) * 64 + v4 * 4;
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const float4 w = __ldg(reinterpret_cast<const float4*>(P.dw_w + t * (KB * 64) + ch));
-          wlo[t] = pack_f32x2(w.x, w.y);
-          whi[t] = pack_f32x2(w.z, w.w);
-        }
-        const float4 sh = __ldg(reinterpret_cast<const float4*>(P.dw_shift + ch));
-        const unsigned long long sh_lo = pack_f32x2(sh.x, sh.y), sh_hi = pack_f32x2(sh.z, sh.w);
-
+      for (int t = 0; t < 9; ++t) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(P.dw_w + t * (KB * 64) + ch));
+        wlo[t] = pack_f32x2(w.x, w.y);
+        whi[t] = pack_f32x2(w.z, w.w);
+      }
+      const float4 sh = __ldg(reinterpret_cast<const float4*>(P.dw_shift + ch));
+      sh_lo = pack_f32x2(sh.x, sh.y);
+      sh_hi = pack_f32x2(sh.z, sh.w);
+    };
+    if (static_cast<uint32_t>(g) < total_c) load_taps(g);
+    {
+      for (uint32_t c = g; c < total_c; c += 2) {
+        // AS == 1: the parity arguments below are per GROUP, so keep the four warps of a group inside the same K block
+        // (a warp that ran a block ahead of a slow sibling could otherwise see a stale barrier phase and pass early)
+        if (AS == 1) asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
         const uint32_t si = c % kDwInStages;
+        // Parity waits are only sound while the waiter is at most one phase behind the barrier.  With an even stage
+        // count every input stage belongs to one group; with an odd count the groups alternate on a stage, which is
+        // safe only because a single A stage (AS == 1) keeps the two groups in lock step (see the a_full wait below).
+        static_assert((kDwInStages % 2 == 0) || AS == 1, "odd input stage counts need the AS == 1 lock step");
         mbar_wait(&in_full[si], (c / kDwInStages) & 1);
         const uint32_t sa = c % AS;
         const uint32_t in_addr = in_base + si * kDwInStageBytes + (2 * cp) * 128 + v4 * 8;
@@ -239,8 +261,10 @@ __global__ void __launch_bounds__(kDwThreads, 1) dwpw_gemm_kernel(const __grid_c
 
         // rolling window over the 10 halo rows; 3 output rows in flight, 2 output columns, 2 channel pairs
         unsigned long long acc_lo[3][2], acc_hi[3][2];
+        if (P.debug & 2) mbar_wait(&a_empty[sa], ((c / AS) & 1) ^ 1);
 #pragma unroll
         for (int r = 0; r < kDwHaloH; ++r) {
+          if (P.debug & 2) break;
           unsigned long long x_lo[4], x_hi[4];
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
@@ -290,6 +314,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dwpw_gemm_kernel(const __grid_c
         mbar_arrive(&in_empty[si]);      // halo tile fully consumed
         fence_proxy_async_smem();        // make the A tile visible to the tensor-core (async) proxy
         mbar_arrive(&a_full[sa]);
+        if (c + 2 < total_c) load_taps(c + 2);   // next block's taps: latency hides behind the barrier waits
       }
     }
   }

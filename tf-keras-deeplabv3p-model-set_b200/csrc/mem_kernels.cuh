@@ -44,95 +44,270 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, float
 }
 
 // ------------------------------------------------------------------------------------------------
-// ASPP: three dilated depthwise convs + pooling partial sums in one pass.
-// grid (ceil(C/64), nbands, B), block 256 = 8 channel-vectors x 32 pixel lanes.
+// ASPP: the three dilated depthwise 3x3 convs (+BN+ReLU) and the image-pooling partial sums.
+//
+// A 3x3 convolution with dilation r only couples pixels of the same phase (i mod r, j mod r): it is r*r independent
+// dense 3x3 convolutions on the phase-subsampled images.  One warp owns one (image, 64-channel chunk, rate, phase,
+// column segment) and walks down the phase image with a three-row register window, so every input element is
+// loaded once per rate (instead of nine times) and all loads/stores are 128-byte coalesced (32 lanes x bf16x2).
+// Packed fp32x2 FMAs; taps that fall outside the map are zeros held in registers ('same' padding).
 struct AsppDwParams {
   const __nv_bfloat16* x;   // [B,h,w,C]
   const float* w;           // [nrates][9][C]  BN scale folded
   const float* shift;       // [nrates][C]
   __nv_bfloat16* out;       // [nrates][B*h*w][C]
-  float* pool_partial;      // [B][nbands][C]
+  float* pool_partial;      // [B][pool_items][C]  (rate 0 items also reduce their pixels for the pooling branch)
   int B, h, w_, C;
-  int nrates;               // 3 (ASPP) or 0 (ASPP Lite: pooling only)
+  int nrates;
   int rates[3];
-  int rows_per_band, nbands;
+  int nchunks;              // ceil(C / 64)
+  int nseg[3];              // column segments per phase image
+  int ts_sel[3];            // segment width selector: 0,1,2,3,4 -> 2,3,4,6,8 outputs per segment
+  int item_off[4];          // prefix sums of items per rate (items = r*r*nseg)
+  int pool_items;           // item_off[1]
+  long long total_warps;    // B * item_off[nrates] * nchunks
+  int debug;                // benchmark aid: bit0 skip output stores, bit1 skip the tap math
 };
 
-__global__ void __launch_bounds__(256) aspp_dw_pool_kernel(const AsppDwParams P) {
-  __shared__ float s_w[3 * 9 * 64];
-  __shared__ float s_shift[3 * 64];
-  __shared__ float s_red[32 * 64];
-  const int chunk = blockIdx.x, band = blockIdx.y, b = blockIdx.z;
-  const int vec = threadIdx.x & 7, pl = threadIdx.x >> 3;
-  const int c0 = chunk * 64 + vec * 8;
-  const bool active = c0 < P.C;
-  for (int i = threadIdx.x; i < P.nrates * 9 * 64; i += 256) {
-    const int rt = i / 64, cc = chunk * 64 + (i & 63);
-    s_w[i] = cc < P.C ? P.w[static_cast<size_t>(rt) * P.C + cc] : 0.0f;
-  }
-  for (int i = threadIdx.x; i < P.nrates * 64; i += 256) {
-    const int r = i / 64, cc = chunk * 64 + (i & 63);
-    s_shift[i] = cc < P.C ? P.shift[static_cast<size_t>(r) * P.C + cc] : 0.0f;
-  }
-  __syncthreads();
+__device__ __forceinline__ unsigned long long f32x2_from_bf16x2(uint32_t v) {
+  return (static_cast<unsigned long long>(v & 0xFFFF0000u) << 32) | (v << 16);
+}
+__device__ __forceinline__ void ffma2_acc(unsigned long long& d, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 
-  const int r0 = band * P.rows_per_band;
-  const int r1 = min(P.h, r0 + P.rows_per_band);
-  const int npix = (r1 - r0) * P.w_;
+// kSmem = false: inputs straight from global memory (large maps; every load is a coalesced 128-byte line)
+// kSmem = true : inputs from a shared-memory slab [h*w pixels][64 channels] staged once per (image, chunk)
+template <int TS, bool kSmem>
+__device__ __forceinline__ void aspp_dw_phase_item(const AsppDwParams& P, int b, int chunk, int ri, int pi, int pj, int seg,
+                                                   int item_in_rate, int lane, uint32_t slab, const float* s_w, const float* s_shift) {
+  const int r = P.rates[ri];
+  const int c0 = chunk * 64 + lane * 2;
+  const bool ch_ok = c0 < P.C;
+  const int cc = ch_ok ? c0 : 0;
+  // taps / shift for this lane's two channels
+  unsigned long long wt[9];
+  unsigned long long sh;
+  if (kSmem) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float2 v = *reinterpret_cast<const float2*>(s_w + (ri * 9 + t) * 64 + lane * 2);
+      wt[t] = (static_cast<unsigned long long>(__float_as_uint(v.y)) << 32) | __float_as_uint(v.x);
+    }
+    const float2 shv = *reinterpret_cast<const float2*>(s_shift + ri * 64 + lane * 2);
+    sh = (static_cast<unsigned long long>(__float_as_uint(shv.y)) << 32) | __float_as_uint(shv.x);
+  } else {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(P.w + (static_cast<size_t>(ri) * 9 + t) * P.C + cc));
+      wt[t] = (static_cast<unsigned long long>(__float_as_uint(v.y)) << 32) | __float_as_uint(v.x);
+    }
+    const float2 shv = __ldg(reinterpret_cast<const float2*>(P.shift + static_cast<size_t>(ri) * P.C + cc));
+    sh = (static_cast<unsigned long long>(__float_as_uint(shv.y)) << 32) | __float_as_uint(shv.x);
+  }
+
   const size_t img_px = static_cast<size_t>(P.h) * P.w_;
-  const __nv_bfloat16* xb = P.x + static_cast<size_t>(b) * img_px * P.C + c0;
-  float psum[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) psum[k] = 0.0f;
+  const __nv_bfloat16* xb = P.x + static_cast<size_t>(b) * img_px * P.C + cc;
+  __nv_bfloat16* ob = P.out + (static_cast<size_t>(ri) * P.B + b) * img_px * P.C + cc;
+  const uint32_t slab_lane = slab + lane * 4;
+  const int na = pi < P.h ? (P.h - pi + r - 1) / r : 0;   // rows of this phase image
+  const int t0 = seg * TS;                                 // first output column (phase coordinates)
+  unsigned long long psum = 0ull;                          // packed (0.f, 0.f)
 
-  if (active) {
-    for (int p = pl; p < npix; p += 32) {
-      const int i = r0 + p / P.w_;
-      const int j = p % P.w_;
-      float ctr[8];
-      unpack8(ldg_nc_v4(xb + (static_cast<size_t>(i) * P.w_ + j) * P.C), ctr);
+  auto load_row = [&](int q, unsigned long long (&row)[TS + 2]) {
+    const int i = pi + r * q;
+    const bool row_ok = ch_ok && q >= 0 && i < P.h;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) psum[k] += ctr[k];
-      for (int r = 0; r < P.nrates; ++r) {
-        const int d = P.rates[r];
-        float acc[8];
+    for (int t = 0; t < TS + 2; ++t) {
+      const int tt = t0 + t - 1;
+      const int j = pj + r * tt;
+      uint32_t v = 0u;
+      if (row_ok && tt >= 0 && j < P.w_) {
+        if (kSmem) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(slab_lane + (i * P.w_ + j) * 128));
+        else v = __ldg(reinterpret_cast<const unsigned int*>(xb + (static_cast<size_t>(i) * P.w_ + j) * P.C));
+      }
+      row[t] = f32x2_from_bf16x2(v);
+    }
+  };
+  auto emit = [&](int a, const unsigned long long (&top)[TS + 2], const unsigned long long (&mid)[TS + 2],
+                  const unsigned long long (&bot)[TS + 2]) {
+    const int i = pi + r * a;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = s_shift[r * 64 + vec * 8 + k];
-#pragma unroll
-        for (int u = 0; u < 3; ++u) {
-          const int ii = i + (u - 1) * d;
-          if (ii < 0 || ii >= P.h) continue;
-#pragma unroll
-          for (int v = 0; v < 3; ++v) {
-            const int jj = j + (v - 1) * d;
-            if (jj < 0 || jj >= P.w_) continue;
-            float xv[8];
-            if (u == 1 && v == 1) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) xv[k] = ctr[k];
-            } else {
-              unpack8(ldg_nc_v4(xb + (static_cast<size_t>(ii) * P.w_ + jj) * P.C), xv);
-            }
-            const float* wt = &s_w[(r * 9 + u * 3 + v) * 64 + vec * 8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] = fmaf(xv[k], wt[k], acc[k]);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = fmaxf(acc[k], 0.0f);
-        __nv_bfloat16* o = P.out + (static_cast<size_t>(r) * P.B * img_px + static_cast<size_t>(b) * img_px +
-                                    static_cast<size_t>(i) * P.w_ + j) * P.C + c0;
-        stg_v4(o, pack8(acc));
+    for (int t = 0; t < TS; ++t) {
+      const int j = pj + r * (t0 + t);
+      unsigned long long acc = sh;
+      ffma2_acc(acc, wt[0], top[t]); ffma2_acc(acc, wt[1], top[t + 1]); ffma2_acc(acc, wt[2], top[t + 2]);
+      ffma2_acc(acc, wt[3], mid[t]); ffma2_acc(acc, wt[4], mid[t + 1]); ffma2_acc(acc, wt[5], mid[t + 2]);
+      ffma2_acc(acc, wt[6], bot[t]); ffma2_acc(acc, wt[7], bot[t + 1]); ffma2_acc(acc, wt[8], bot[t + 2]);
+      if (ch_ok && j < P.w_ && !(P.debug & 1)) {
+        const float lo = fmaxf(__uint_as_float(static_cast<uint32_t>(acc)), 0.0f);
+        const float hi = fmaxf(__uint_as_float(static_cast<uint32_t>(acc >> 32)), 0.0f);
+        *reinterpret_cast<uint32_t*>(ob + (static_cast<size_t>(i) * P.w_ + j) * P.C) = pack_bf16x2(lo, hi);
+        if (!kSmem) psum = fadd2(psum, mid[t + 1]);
+      }
+    }
+  };
+
+  unsigned long long ra[TS + 2], rb[TS + 2], rc[TS + 2];
+  if (na > 0) {
+    load_row(-1, ra);
+    load_row(0, rb);
+    for (int a = 0; a < na; a += 3) {
+      load_row(a + 1, rc);
+      emit(a, ra, rb, rc);
+      if (a + 1 < na) {
+        load_row(a + 2, ra);
+        emit(a + 1, rb, rc, ra);
+      }
+      if (a + 2 < na) {
+        load_row(a + 3, rb);
+        emit(a + 2, rc, ra, rb);
       }
     }
   }
-  // deterministic block reduction of the pooling partial sums over the 32 pixel lanes
+  if (!kSmem && ri == 0 && ch_ok) {
+    float2 pv;
+    pv.x = __uint_as_float(static_cast<uint32_t>(psum));
+    pv.y = __uint_as_float(static_cast<uint32_t>(psum >> 32));
+    *reinterpret_cast<float2*>(P.pool_partial + (static_cast<size_t>(b) * P.pool_items + item_in_rate) * P.C + c0) = pv;
+  }
+}
+
+template <bool kSmem>
+__device__ __forceinline__ void aspp_dw_dispatch(const AsppDwParams& P, int b, int chunk, int it, int lane, uint32_t slab,
+                                                 const float* s_w, const float* s_shift) {
+  int ri = 0;
+  if (P.nrates > 1 && it >= P.item_off[1]) ri = 1;
+  if (P.nrates > 2 && it >= P.item_off[2]) ri = 2;
+  const int local = it - P.item_off[ri];
+  const int nseg = P.nseg[ri];
+  const int seg = local % nseg;
+  const int ph = local / nseg;
+  const int r = P.rates[ri];
+  const int pj = ph % r;
+  const int pi = ph / r;
+  switch (P.ts_sel[ri]) {
+    case 0: aspp_dw_phase_item<2, kSmem>(P, b, chunk, ri, pi, pj, seg, local, lane, slab, s_w, s_shift); break;
+    case 1: aspp_dw_phase_item<3, kSmem>(P, b, chunk, ri, pi, pj, seg, local, lane, slab, s_w, s_shift); break;
+    case 2: aspp_dw_phase_item<4, kSmem>(P, b, chunk, ri, pi, pj, seg, local, lane, slab, s_w, s_shift); break;
+    case 3: aspp_dw_phase_item<6, kSmem>(P, b, chunk, ri, pi, pj, seg, local, lane, slab, s_w, s_shift); break;
+    default: aspp_dw_phase_item<8, kSmem>(P, b, chunk, ri, pi, pj, seg, local, lane, slab, s_w, s_shift); break;
+  }
+}
+
+// large maps: one warp per work item, inputs from global memory
+__global__ void __launch_bounds__(128, 4) aspp_dw_phase_kernel(const __grid_constant__ AsppDwParams P) {
+  const long long gw = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (gw >= P.total_warps) return;
+  const int lane = threadIdx.x & 31;
+  const int chunk = static_cast<int>(gw % P.nchunks);
+  const long long rest = gw / P.nchunks;
+  const int items_per_img = P.item_off[P.nrates];
+  const int it = static_cast<int>(rest % items_per_img);
+  const int b = static_cast<int>(rest / items_per_img);
+  aspp_dw_dispatch<false>(P, b, chunk, it, lane, 0u, nullptr, nullptr);
+}
+
+// small maps (h*w*128 B fits in shared memory): persistent CTAs, one (image, 64-channel chunk) slab at a time.
+// The slab is staged with 16-byte cp.async; all three rates and the pooling partial sums are then computed from
+// shared memory (deterministic order), so x is read from HBM exactly once.
+constexpr int kSlabThreads = 512;
+__global__ void __launch_bounds__(kSlabThreads, 1) aspp_dw_slab_kernel(const __grid_constant__ AsppDwParams P) {
+  extern __shared__ __align__(128) uint8_t slab_smem[];
+  const int npix = P.h * P.w_;
+  uint8_t* s_slab = slab_smem;
+  float* s_w = reinterpret_cast<float*>(s_slab + static_cast<size_t>(npix) * 128);   // [27][64]
+  float* s_shift = s_w + 27 * 64;                                                     // [3][64]
+  float* s_red = s_shift + 3 * 64;                                                    // [16][64]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t slab = smem_u32(s_slab);
+  const int nitems = P.item_off[P.nrates];
+  const int num_slabs = P.B * P.nchunks;
+  for (int sid = blockIdx.x; sid < num_slabs; sid += gridDim.x) {
+    const int b = sid / P.nchunks, chunk = sid - b * P.nchunks;
+    const __nv_bfloat16* xs = P.x + static_cast<size_t>(b) * npix * P.C + chunk * 64;
+    for (int idx = tid; idx < npix * 8; idx += kSlabThreads) {
+      const int p = idx >> 3, part = idx & 7;
+      const uint32_t dst = slab + p * 128 + part * 16;
+      if (chunk * 64 + part * 8 < P.C) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(xs + static_cast<size_t>(p) * P.C + part * 8) : "memory");
+      } else {
+        sts_v4(dst, make_uint4(0u, 0u, 0u, 0u));
+      }
+    }
+    for (int i = tid; i < P.nrates * 9 * 64; i += kSlabThreads) {
+      const int cc = chunk * 64 + (i & 63);
+      s_w[i] = cc < P.C ? __ldg(P.w + static_cast<size_t>(i >> 6) * P.C + cc) : 0.0f;
+    }
+    for (int i = tid; i < P.nrates * 64; i += kSlabThreads) {
+      const int cc = chunk * 64 + (i & 63);
+      s_shift[i] = cc < P.C ? __ldg(P.shift + static_cast<size_t>(i >> 6) * P.C + cc) : 0.0f;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    // the 16 warps share the (rate, phase, segment) items of the slab, heaviest rate first
+    for (int it = warp; it < nitems; it += kSlabThreads / 32) aspp_dw_dispatch<true>(P, b, chunk, it, lane, slab, s_w, s_shift);
+
+    // image-pooling partial sums over the slab: lane = 2 channels, 16 warps stride over the pixels
+    {
+      float sx = 0.0f, sy = 0.0f;
+      for (int p = warp; p < npix; p += kSlabThreads / 32) {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(slab + p * 128 + lane * 4));
+        sx += bf16_lo(v);
+        sy += bf16_hi(v);
+      }
+      s_red[warp * 64 + lane * 2] = sx;
+      s_red[warp * 64 + lane * 2 + 1] = sy;
+    }
+    __syncthreads();
+    if (tid < 64) {
+      float s0 = 0.0f;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) s_red[pl * 64 + vec * 8 + k] = psum[k];
+      for (int q = 0; q < kSlabThreads / 32; ++q) s0 += s_red[q * 64 + tid];
+      const int cc = chunk * 64 + tid;
+      if (cc < P.C) P.pool_partial[static_cast<size_t>(b) * P.C + cc] = s0;   // pool_items == 1 on this path
+    }
+    __syncthreads();   // slab / s_red are rewritten by the next iteration
+  }
+}
+
+// ASPP Lite has no atrous branches: plain per-channel partial sums for the image-pooling branch.
+// grid (ceil(C/64), nbands, B), block 256 = 8 warps striding over the band's pixels; lane = 2 channels.
+struct PoolParams {
+  const __nv_bfloat16* x;   // [B,h*w,C]
+  float* pool_partial;      // [B][nbands][C]
+  int npix, C, nbands, pix_per_band;
+};
+__global__ void __launch_bounds__(256) global_pool_kernel(const PoolParams P) {
+  __shared__ float s_red[8][64];
+  const int chunk = blockIdx.x, band = blockIdx.y, b = blockIdx.z;
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int c0 = chunk * 64 + lane * 2;
+  const int p0 = band * P.pix_per_band, p1 = min(P.npix, p0 + P.pix_per_band);
+  float sx = 0.0f, sy = 0.0f;
+  if (c0 < P.C) {
+    const __nv_bfloat16* xb = P.x + static_cast<size_t>(b) * P.npix * P.C + c0;
+    for (int p = p0 + wp; p < p1; p += 8) {
+      const uint32_t v = __ldg(reinterpret_cast<const unsigned int*>(xb + static_cast<size_t>(p) * P.C));
+      sx += bf16_lo(v);
+      sy += bf16_hi(v);
+    }
+  }
+  s_red[wp][lane * 2] = sx;
+  s_red[wp][lane * 2 + 1] = sy;
   __syncthreads();
   if (threadIdx.x < 64) {
     float s = 0.0f;
-    for (int q = 0; q < 32; ++q) s += s_red[q * 64 + threadIdx.x];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += s_red[q][threadIdx.x];
     const int cc = chunk * 64 + threadIdx.x;
     if (cc < P.C) P.pool_partial[(static_cast<size_t>(b) * P.nbands + band) * P.C + cc] = s;
   }
@@ -140,7 +315,7 @@ __global__ void __launch_bounds__(256) aspp_dw_pool_kernel(const AsppDwParams P)
 
 // ------------------------------------------------------------------------------------------------
 // image-pooling branch folded into a per-image shift of the concat_projection epilogue.
-// grid B, block 256 (one thread per output channel).
+// grid B, block 1024.
 struct PoolProjParams {
   const float* pool_partial;     // [B][nbands][C]
   const __nv_bfloat16* w_ip;     // [C][256]  image_pooling kernel, bf16, k-major rows
@@ -155,26 +330,58 @@ struct PoolProjParams {
   float inv_count;               // 1 / (h*w)
 };
 
-__global__ void __launch_bounds__(256) pool_proj_kernel(const PoolProjParams P) {
-  extern __shared__ float s_mean[];  // [C] + [256]
+// block 1024 = 256 output channels x 4 K-slices; each thread keeps 4 independent accumulators
+__global__ void __launch_bounds__(1024) pool_proj_kernel(const PoolProjParams P) {
+  extern __shared__ float s_mean[];  // [C] + [256] + [4][256]
   float* s_b4 = s_mean + P.C;
-  const int b = blockIdx.x, n = threadIdx.x;
-  for (int c = n; c < P.C; c += 256) {
+  float* s_part = s_b4 + 256;
+  const int b = blockIdx.x, n = threadIdx.x & 255, ks = threadIdx.x >> 8;
+  for (int c = threadIdx.x; c < P.C; c += 1024) {
     float s = 0.0f;
     for (int q = 0; q < P.nbands; ++q) s += P.pool_partial[(static_cast<size_t>(b) * P.nbands + q) * P.C + c];
     s_mean[c] = s * P.inv_count;
   }
   __syncthreads();
-  float acc = 0.0f;
-  for (int k = 0; k < P.C; ++k) acc = fmaf(s_mean[k], __bfloat162float(P.w_ip[static_cast<size_t>(k) * 256 + n]), acc);
-  float v = fmaxf(fmaf(acc, P.ip_scale[n], P.ip_shift[n]), 0.0f);
-  v = __bfloat162float(__float2bfloat16_rn(v));  // activation rounding point, as every other branch
-  s_b4[n] = v;
-  P.b4_out[static_cast<size_t>(b) * 256 + n] = v;
+  {
+    const int kq = (P.C + 3) / 4, k0 = ks * kq, k1 = min(P.C, k0 + kq);
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    int k = k0;
+    for (; k + 3 < k1; k += 4) {
+      a0 = fmaf(s_mean[k + 0], __bfloat162float(P.w_ip[static_cast<size_t>(k + 0) * 256 + n]), a0);
+      a1 = fmaf(s_mean[k + 1], __bfloat162float(P.w_ip[static_cast<size_t>(k + 1) * 256 + n]), a1);
+      a2 = fmaf(s_mean[k + 2], __bfloat162float(P.w_ip[static_cast<size_t>(k + 2) * 256 + n]), a2);
+      a3 = fmaf(s_mean[k + 3], __bfloat162float(P.w_ip[static_cast<size_t>(k + 3) * 256 + n]), a3);
+    }
+    for (; k < k1; ++k) a0 = fmaf(s_mean[k], __bfloat162float(P.w_ip[static_cast<size_t>(k) * 256 + n]), a0);
+    s_part[ks * 256 + n] = (a0 + a1) + (a2 + a3);
+  }
   __syncthreads();
-  float acc2 = 0.0f;
-  for (int k = 0; k < 256; ++k) acc2 = fmaf(s_b4[k], __bfloat162float(P.w_proj4[static_cast<size_t>(k) * 256 + n]), acc2);
-  P.img_shift[static_cast<size_t>(b) * 256 + n] = fmaf(acc2, P.proj_scale[n], P.proj_shift[n]);
+  if (ks == 0) {
+    const float acc = (s_part[n] + s_part[256 + n]) + (s_part[512 + n] + s_part[768 + n]);
+    float v = fmaxf(fmaf(acc, P.ip_scale[n], P.ip_shift[n]), 0.0f);
+    v = __bfloat162float(__float2bfloat16_rn(v));  // activation rounding point, as every other branch
+    s_b4[n] = v;
+    P.b4_out[static_cast<size_t>(b) * 256 + n] = v;
+  }
+  __syncthreads();
+  {
+    const int k0 = ks * 64;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll 4
+    for (int k = k0; k < k0 + 64; k += 4) {
+      a0 = fmaf(s_b4[k + 0], __bfloat162float(P.w_proj4[static_cast<size_t>(k + 0) * 256 + n]), a0);
+      a1 = fmaf(s_b4[k + 1], __bfloat162float(P.w_proj4[static_cast<size_t>(k + 1) * 256 + n]), a1);
+      a2 = fmaf(s_b4[k + 2], __bfloat162float(P.w_proj4[static_cast<size_t>(k + 2) * 256 + n]), a2);
+      a3 = fmaf(s_b4[k + 3], __bfloat162float(P.w_proj4[static_cast<size_t>(k + 3) * 256 + n]), a3);
+    }
+    __syncthreads();   // s_part reuse
+    s_part[ks * 256 + n] = (a0 + a1) + (a2 + a3);
+  }
+  __syncthreads();
+  if (ks == 0) {
+    const float acc2 = (s_part[n] + s_part[256 + n]) + (s_part[512 + n] + s_part[768 + n]);
+    P.img_shift[static_cast<size_t>(b) * 256 + n] = fmaf(acc2, P.proj_scale[n], P.proj_shift[n]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -252,34 +459,35 @@ struct ResizeParams {
   int B, hi, wi, C, ho, wo, ldo, col_off;
   float sy, sx;            // hi/ho, wi/wo computed in fp32 on the host exactly like the oracle
 };
+// grid (ho, B): one output row per block; threads stride over (X, 8-channel vector) with 32-bit index math
 __global__ void __launch_bounds__(256) resize_bilinear_kernel(const ResizeParams P) {
   const int vecs = P.C >> 3;
-  const size_t total = static_cast<size_t>(P.B) * P.ho * P.wo * vecs;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int vec = static_cast<int>(idx % vecs);
-    size_t pix = idx / vecs;
-    const int X = static_cast<int>(pix % P.wo);
-    pix /= P.wo;
-    const int Y = static_cast<int>(pix % P.ho);
-    const int b = static_cast<int>(pix / P.ho);
-    int y0, y1, x0, x1;
-    float ty, tx;
-    resize_coord(Y, P.sy, P.hi, y0, y1, ty);
+  const int Y = blockIdx.x, b = blockIdx.y;
+  int y0, y1;
+  float ty;
+  resize_coord(Y, P.sy, P.hi, y0, y1, ty);
+  const __nv_bfloat16* row0 = P.x + (static_cast<size_t>(b) * P.hi + y0) * P.wi * P.C;
+  const __nv_bfloat16* row1 = P.x + (static_cast<size_t>(b) * P.hi + y1) * P.wi * P.C;
+  __nv_bfloat16* orow = P.out + (static_cast<size_t>(b) * P.ho + Y) * P.wo * P.ldo + P.col_off;
+  const int total = P.wo * vecs;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int X = idx / vecs;
+    const int vec = idx - X * vecs;
+    int x0, x1;
+    float tx;
     resize_coord(X, P.sx, P.wi, x0, x1, tx);
-    const __nv_bfloat16* xb = P.x + static_cast<size_t>(b) * P.hi * P.wi * P.C + vec * 8;
     float tl[8], tr[8], bl[8], br[8], o[8];
-    unpack8(ldg_nc_v4(xb + (static_cast<size_t>(y0) * P.wi + x0) * P.C), tl);
-    unpack8(ldg_nc_v4(xb + (static_cast<size_t>(y0) * P.wi + x1) * P.C), tr);
-    unpack8(ldg_nc_v4(xb + (static_cast<size_t>(y1) * P.wi + x0) * P.C), bl);
-    unpack8(ldg_nc_v4(xb + (static_cast<size_t>(y1) * P.wi + x1) * P.C), br);
+    unpack8(ldg_nc_v4(row0 + x0 * P.C + vec * 8), tl);
+    unpack8(ldg_nc_v4(row0 + x1 * P.C + vec * 8), tr);
+    unpack8(ldg_nc_v4(row1 + x0 * P.C + vec * 8), bl);
+    unpack8(ldg_nc_v4(row1 + x1 * P.C + vec * 8), br);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float top = lerp_nofma(tl[k], tr[k], tx);
       const float bot = lerp_nofma(bl[k], br[k], tx);
       o[k] = lerp_nofma(top, bot, ty);
     }
-    stg_v4(P.out + ((static_cast<size_t>(b) * P.ho + Y) * P.wo + X) * P.ldo + P.col_off + vec * 8, pack8(o));
+    stg_v4(orow + static_cast<size_t>(X) * P.ldo + vec * 8, pack8(o));
   }
 }
 

@@ -9,7 +9,9 @@
 //   warp 0      TMA producer   (cp.async.bulk.tensor, 128B swizzle, kStages-deep mbarrier ring)
 //   warp 1      MMA issuer     (one elected lane issues tcgen05.mma, fp32 accumulators in TMEM,
 //                               two accumulator stages so the epilogue overlaps the next tile)
-//   warps 2..5  epilogue       (tcgen05.ld -> scale/shift/ReLU -> bf16 / fp32 -> global)
+//   warps 2..5  epilogue       (tcgen05.ld -> scale/shift/ReLU -> bf16 -> 128B-swizzled smem -> TMA store, one
+//                               32-row x 64-column box per warp, double buffered; fp32 planar logits are stored
+//                               directly: consecutive lanes = consecutive pixels of one class plane)
 // Persistent over (tile, problem) work items; a launch can carry up to kMaxProblems GEMMs that
 // share M (the four ASPP branches: aspp0 + three atrous pointwise convs).
 #pragma once
@@ -34,6 +36,7 @@ enum PwEpilogue : int {
 struct PwProblem {
   const CUtensorMap* tmap_a;  // [M, K] bf16, box {64, 128}, SWIZZLE_128B   (device memory)
   const CUtensorMap* tmap_w;  // [Npad, Kpad] bf16, box {64, BN}, SWIZZLE_128B
+  const CUtensorMap* tmap_out;  // bf16 modes, BN >= 64: [M, N] view of the output (row stride ldo), box {64, 32}, SWIZZLE_128B
   const float* scale;         // [BN]
   const float* shift;         // [BN]
   const float* img_shift;     // [B, BN] (kEpiBf16ImgShift)
@@ -52,6 +55,7 @@ struct PwLaunch {
   int M;
   int num_tiles;      // ceil(M / 128)
   int rows_per_img;   // pixels per image (per-image shift, planar output)
+  int debug;          // benchmark aid: bit0 = skip the global stores of the epilogue
 };
 
 template <int BN>
@@ -59,19 +63,24 @@ struct PwCfg {
   static constexpr int kStageBytes = kPwBM * 128 + BN * 128;
   static constexpr int kStages = (BN >= 256) ? 4 : 6;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kStoreBytes = (BN >= 64) ? 4 * 2 * 4096 : 0;  // 4 epilogue warps x 2 buffers x [32 rows x 128 B]
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + 2 * BN * 4 /*scale+shift*/ + 256 /*barriers*/;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(kPwThreads, 1) pw_gemm_kernel(const __grid_constant__ PwLaunch L) {
   using Cfg = PwCfg<BN>;
   constexpr int kStages = Cfg::kStages;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment required by the 128B swizzle atoms
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw;   // dynamic smem is the only shared memory of this kernel: 1024-byte aligned (checked below)
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
   uint8_t* smem_a = smem;                                  // kStages x [128 rows x 128 B]
   uint8_t* smem_b = smem + kStages * (kPwBM * 128);        // kStages x [BN rows x 128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* smem_c = smem + kStages * Cfg::kStageBytes;     // epilogue staging (1024-byte aligned)
+  float* s_scale = reinterpret_cast<float*>(smem_c + Cfg::kStoreBytes);  // [BN] current problem's BN scale (L1 is ~0 KB here)
+  float* s_shift = s_scale + BN;                                          // [BN] shift (per image in kEpiBf16ImgShift)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + BN);
   uint64_t* full_bar = bars;                    // [kStages]  TMA -> MMA
   uint64_t* empty_bar = bars + kStages;         // [kStages]  MMA -> TMA
   uint64_t* tmem_full = bars + 2 * kStages;     // [2]        MMA -> epilogue
@@ -155,6 +164,8 @@ __global__ void __launch_bounds__(kPwThreads, 1) pw_gemm_kernel(const __grid_con
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     uint32_t it = 0;
+    uint32_t store_buf = 0;
+    int ss_key = -1;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
       const int p = item % L.num_problems;
       const int tile = item / L.num_problems;
@@ -166,24 +177,89 @@ __global__ void __launch_bounds__(kPwThreads, 1) pw_gemm_kernel(const __grid_con
       const int row = tile * kPwBM + q * 32 + lane;
       const bool row_ok = row < L.M;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-      const float* shift = P.shift;
       int img = 0, pix = 0;
       if (P.epi != kEpiBf16) {
         img = row_ok ? row / L.rows_per_img : 0;
         pix = row - img * L.rows_per_img;
-        if (P.epi == kEpiBf16ImgShift) shift = P.img_shift + static_cast<size_t>(img) * BN;
       }
+      // scale / shift of the current problem (and image, for the per-image shift) live in shared memory: with ~224 KB
+      // of dynamic smem there is no L1 left and every __ldg would pay L2 latency inside the epilogue's critical path
+      {
+        const int row_first = tile * kPwBM, row_last = min(tile * kPwBM + kPwBM, L.M) - 1;
+        const int img_first = P.epi == kEpiBf16ImgShift ? row_first / L.rows_per_img : 0;
+        const int img_last = P.epi == kEpiBf16ImgShift ? row_last / L.rows_per_img : 0;
+        const int key = (p << 24) | (img_first == img_last ? img_first : 0xFFFFFF);
+        if (key != ss_key) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");   // everyone is done with the previous values
+          const float* gshift = (P.epi == kEpiBf16ImgShift && img_first == img_last) ? P.img_shift + static_cast<size_t>(img_first) * BN : P.shift;
+          for (int i = (warp - 2) * 32 + lane; i < BN; i += 128) {
+            s_scale[i] = __ldg(P.scale + i);
+            s_shift[i] = __ldg(gshift + i);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          ss_key = key;
+        }
+      }
+      // a tile that straddles two images (per-image shift only) reads its shift from global memory instead
+      const bool shift_global = P.epi == kEpiBf16ImgShift && (ss_key & 0xFFFFFF) == 0xFFFFFF;
+      const float* shift = shift_global ? P.img_shift + static_cast<size_t>(img) * BN : s_shift;
+      bool staged = false;
+      if constexpr (BN >= 64) staged = P.epi != kEpiPlanarF32;
+      if (staged) {
+        if constexpr (BN >= 64) {
+          // ---- bf16 output through swizzled smem + TMA store (full 128-byte lines, asynchronous)
+          uint8_t* my_c = smem_c + (warp - 2) * 2 * 4096;
+#pragma unroll 1
+          for (int cb = 0; cb < BN / 64; ++cb) {
+            if (cb * 64 >= P.N) break;
+            if (lane == 0) tma_store_wait_read<1>();   // the buffer written two blocks ago has been read out
+            __syncwarp();
+            const uint32_t cbuf = smem_u32(my_c + store_buf * 4096) + lane * 128;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int c0 = cb * 64 + half * 32;
+              uint32_t v[32];
+              tmem_ld_32x32b_x32(taddr + c0, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const float4 s0 = *reinterpret_cast<const float4*>(s_scale + c0 + j);
+                const float4 s1 = *reinterpret_cast<const float4*>(s_scale + c0 + j + 4);
+                const float4 t0 = *reinterpret_cast<const float4*>(shift + c0 + j);       // generic load: smem, or global when straddling
+                const float4 t1 = *reinterpret_cast<const float4*>(shift + c0 + j + 4);
+                float y0 = fmaf(__uint_as_float(v[j + 0]), s0.x, t0.x), y1 = fmaf(__uint_as_float(v[j + 1]), s0.y, t0.y);
+                float y2 = fmaf(__uint_as_float(v[j + 2]), s0.z, t0.z), y3 = fmaf(__uint_as_float(v[j + 3]), s0.w, t0.w);
+                float y4 = fmaf(__uint_as_float(v[j + 4]), s1.x, t1.x), y5 = fmaf(__uint_as_float(v[j + 5]), s1.y, t1.y);
+                float y6 = fmaf(__uint_as_float(v[j + 6]), s1.z, t1.z), y7 = fmaf(__uint_as_float(v[j + 7]), s1.w, t1.w);
+                if (P.relu) {
+                  y0 = fmaxf(y0, 0.0f); y1 = fmaxf(y1, 0.0f); y2 = fmaxf(y2, 0.0f); y3 = fmaxf(y3, 0.0f);
+                  y4 = fmaxf(y4, 0.0f); y5 = fmaxf(y5, 0.0f); y6 = fmaxf(y6, 0.0f); y7 = fmaxf(y7, 0.0f);
+                }
+                const uint32_t chunk = static_cast<uint32_t>(half * 4 + (j >> 3)) ^ static_cast<uint32_t>(lane & 7);
+                sts_v4(cbuf + chunk * 16, make_uint4(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3), pack_bf16x2(y4, y5), pack_bf16x2(y6, y7)));
+              }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && !(L.debug & 1)) {
+              tma_store_2d(P.tmap_out, my_c + store_buf * 4096, cb * 64, tile * kPwBM + q * 32);
+              tma_store_commit();
+            }
+            store_buf ^= 1;
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (c0 >= P.N) break;  // padded columns: nothing to store (uniform branch)
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + c0, v);
         tmem_ld_wait();
-        if (c0 >= P.N) continue;  // padded columns: nothing to store (uniform branch)
         float y[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 s = __ldg(reinterpret_cast<const float4*>(P.scale + c0 + j));
-          const float4 t = __ldg(reinterpret_cast<const float4*>(shift + c0 + j));
+          const float4 s = *reinterpret_cast<const float4*>(s_scale + c0 + j);
+          const float4 t = *reinterpret_cast<const float4*>(shift + c0 + j);
           y[j + 0] = fmaf(__uint_as_float(v[j + 0]), s.x, t.x);
           y[j + 1] = fmaf(__uint_as_float(v[j + 1]), s.y, t.y);
           y[j + 2] = fmaf(__uint_as_float(v[j + 2]), s.z, t.z);
@@ -200,7 +276,7 @@ __global__ void __launch_bounds__(kPwThreads, 1) pw_gemm_kernel(const __grid_con
             for (int j = 0; j < 32; ++j)
               if (c0 + j < P.N) o[static_cast<size_t>(j) * L.rows_per_img] = y[j];
           }
-        } else if (row_ok) {
+        } else if (row_ok && !(L.debug & 1)) {
           __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + static_cast<size_t>(row) * P.ldo + P.col_off + c0;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
@@ -215,9 +291,11 @@ __global__ void __launch_bounds__(kPwThreads, 1) pw_gemm_kernel(const __grid_con
           }
         }
       }
+      }
       tcgen05_fence_before();
       mbar_arrive(&tmem_empty[acc]);
     }
+    if (lane == 0) tma_store_wait_all<0>();   // all bulk stores of this warp have completed before smem goes away
   }
 
   tcgen05_fence_before();

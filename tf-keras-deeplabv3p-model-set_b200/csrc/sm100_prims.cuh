@@ -228,6 +228,12 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
 __device__ __forceinline__ void stg_v4(void* p, const uint4& v) {
   asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// 256-bit global store (sm_100): one full 32-byte sector per thread
+__device__ __forceinline__ void stg_v8(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+               "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
 __device__ __forceinline__ void sts_v4(uint32_t smem_addr, const uint4& v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(smem_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");

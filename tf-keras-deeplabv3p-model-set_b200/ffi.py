@@ -72,6 +72,7 @@ SYMBOLS = [
     ('dlv3p_op_sepconv', _i, [_i, _vp, _i, _i, _i, _i, _i, _fp, _fp, _fp, _i, _fp, _fp, _fp, _vp, _vp]),
     ('dlv3p_op_resize_bilinear', _i, [_i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     ('dlv3p_op_resize_argmax', _i, [_i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    ('dlv3p_op_time', _i, [_i, _i, C.POINTER(C.c_int64), _i, _i, _i, _fp]),
 ]
 
 _lib = None
@@ -348,3 +349,11 @@ def op_resize_argmax(logits_planar: np.ndarray, ho: int, wo: int, device=0) -> n
     do = DeviceBuffer(B * ho * wo, device)
     _check(load_library().dlv3p_op_resize_argmax(device, dl.ptr, B, NC, hi, wi, ho, wo, do.ptr, None))
     return do.download((B, ho, wo), np.uint8)
+
+
+def op_time(op: int, dims: Sequence[int], iters: int = 20, flags: int = 0, device: int = 0) -> float:
+    """ms per launch of one operator on synthetic data (benchmark aid, see include/dlv3p.h)."""
+    arr = (C.c_int64 * len(dims))(*dims)
+    ms = C.c_float()
+    _check(load_library().dlv3p_op_time(device, op, arr, len(dims), iters, flags, C.byref(ms)))
+    return ms.value
