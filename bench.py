@@ -261,16 +261,12 @@ def main():
     e2e_ms = (time.perf_counter() - t0) * 1000.0
     labels_ok = bool(np.array_equal(ho.reshape(B, CFG['H'], CFG['W']), out.cpu().numpy()))
 
-    # ---- max over ranks
-    if world > 1:
-        t = torch.tensor([ms, e2e_ms], device='cuda', dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = float(t[0]), float(t[1])
+    # ---- max over ranks (device-side timings; no data-path collective exists in this path)
+    ms, e2e_ms = dlv3p_b200.sharding.max_over_ranks([ms, e2e_ms], device='cuda')
 
     if rank == 0:
         peaks = load_peaks()
-        total_imgs = B * world * args.steps
-        value = total_imgs / (ms / 1000.0)
+        value = dlv3p_b200.sharding.aggregate_throughput(B, args.steps, world, ms)
         # dominant kernel and its roofline
         dom = max(prof, key=prof.get)
         step_ms_prof = sum(prof.values())
