@@ -94,6 +94,23 @@ bool encode_2d_sw128(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t 
   }
   return true;
 }
+// 2D bf16 [rows, cols] row-major, box {64, 256}, NO swizzle: pixel-major slabs [256 px][64 ch] for the ASPP depthwise kernel
+bool encode_2d_slab(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, std::string* err) {
+  EncodeTiledFn fn = get_encode_fn(err);
+  if (!fn) return false;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {64, 256};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) *err = fmt("cuTensorMapEncodeTiled(slab rows=%llu cols=%llu) -> %d", (unsigned long long)rows, (unsigned long long)cols, (int)r);
+    return false;
+  }
+  return true;
+}
 // 2D bf16 output view [rows, cols] (row stride ld elements), box {64, 32}, 128B swizzle: the epilogue's TMA store
 bool encode_2d_out(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, std::string* err) {
   return encode_2d_sw128(tm, base, rows, cols, ld, 32, err);
@@ -231,7 +248,7 @@ struct WeightSlot {
 enum TmSlot {
   TM_FEAT = 0, TM_DW1, TM_DW2, TM_DW3, TM_CONCAT, TM_SKIP, TM_DECIN, TM_DEC0, TM_CLS_IN,
   TM_W_ASPP0, TM_W_ASPP1, TM_W_ASPP2, TM_W_ASPP3, TM_W_PROJ, TM_W_FP0, TM_W_DEC0, TM_W_DEC1, TM_W_CLS,
-  TM_O_ASPP0, TM_O_ASPP1, TM_O_ASPP2, TM_O_ASPP3, TM_O_PROJ, TM_O_FP0, TM_O_DEC0, TM_O_DEC1,
+  TM_O_ASPP0, TM_O_ASPP1, TM_O_ASPP2, TM_O_ASPP3, TM_O_PROJ, TM_O_FP0, TM_O_DEC0, TM_O_DEC1, TM_FEAT_SLAB,
   TM_COUNT
 };
 
@@ -271,7 +288,7 @@ struct dlv3p_ctx {
   __nv_bfloat16 *feat_bf16 = nullptr, *skip_bf16 = nullptr;  // cast targets / forward_host staging
   void *in_feat_stage = nullptr, *in_skip_stage = nullptr;   // forward_host raw staging (in_dtype)
   void* out_stage = nullptr;
-  __nv_bfloat16* dw_out = nullptr;     // [3][M1][Cin]
+  __nv_bfloat16* dw_out = nullptr;     // [3][Cin/64][M1][64]  K-block-major
   float* pool_partial = nullptr;       // [B][nbands][Cin]
   float* img_shift = nullptr;          // [B][256]
   float* b4 = nullptr;                 // [B][256]
@@ -578,13 +595,17 @@ int dlv3p_create(const dlv3p_config* cfg, int device, dlv3p_ctx** out) {
         A.nseg[i] = ceil_div(nt, kTs[sel]);
         A.item_off[i + 1] = A.item_off[i] + rr * rr * A.nseg[i];
       }
-      c->aspp_slab_smem = static_cast<size_t>(px) * 128 + (27 * 64 + 3 * 64 + 16 * 64) * sizeof(float);
+      c->aspp_slab_smem = static_cast<size_t>(ceil_div(px, 256)) * 32768 + (27 * 64 + 3 * 64 + 16 * 64) * sizeof(float) + 16;
       c->aspp_slab = c->aspp_slab_smem <= 220 * 1024;
       A.pool_items = c->aspp_slab ? 1 : A.item_off[1];
       A.total_warps = static_cast<long long>(g.B) * A.item_off[3] * A.nchunks;
       c->nbands = A.pool_items;
     }
-    if (!c->lite && (r = dev_alloc(c, &c->dw_out, 3 * static_cast<size_t>(c->M1) * g.Cin))) return bail(r, c->err);
+    if (!c->lite) {
+      const size_t n = 3 * static_cast<size_t>(ceil_div(g.Cin, 64)) * c->M1 * 64;
+      if ((r = dev_alloc(c, &c->dw_out, n))) return bail(r, c->err);
+      if (!c->plan_only && cudaMemset(c->dw_out, 0, n * 2) != cudaSuccess) return bail(DLV3P_ERR_CUDA, "cudaMemset failed");   // padded channels stay 0
+    }
     if ((r = dev_alloc(c, &c->pool_partial, B * c->nbands * g.Cin))) return bail(r, c->err);
     if ((r = dev_alloc(c, &c->img_shift, B * 256))) return bail(r, c->err);
     if ((r = dev_alloc(c, &c->b4, B * 256))) return bail(r, c->err);
@@ -747,13 +768,14 @@ int dlv3p_finalize_weights(dlv3p_ctx* c) {
     ok = ok && enc2(TM_W_PROJ, c->pw_proj.w, 256, c->pw_proj.Kpad, c->pw_proj.Kpad, 256);
     if (!c->lite)
       for (int i = 0; i < 3; ++i)
-        ok = ok && enc2(TM_DW1 + i, c->dw_out + static_cast<size_t>(i) * c->M1 * g.Cin, c->M1, g.Cin, g.Cin, 128);
+        ok = ok && enc2(TM_DW1 + i, c->dw_out + static_cast<size_t>(i) * ceil_div(g.Cin, 64) * c->M1 * 64, static_cast<uint64_t>(ceil_div(g.Cin, 64)) * c->M1, 64, 64, 128);
     ok = ok && enc2(TM_CONCAT, c->concat, c->M1, c->Ccat, c->Ccat, 128);
     for (int i = 0; i < (c->lite ? 1 : 4); ++i)
       ok = ok && encode_2d_out(&c->h_tm[TM_O_ASPP0 + i], c->concat + 256 * i, c->M1, 256, c->Ccat, &terr);
     ok = ok && encode_2d_out(&c->h_tm[TM_O_PROJ], c->aspp_out, c->M1, 256, 256, &terr);
     if (c->feat_bf16) {
       ok = ok && enc2(TM_FEAT, c->feat_bf16, c->M1, g.Cin, g.Cin, 128);
+      ok = ok && encode_2d_slab(&c->h_tm[TM_FEAT_SLAB], c->feat_bf16, c->M1, g.Cin, g.Cin, &terr);
       c->tm_feat_ptr = c->feat_bf16;
     }
   }
@@ -887,7 +909,9 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
     skip = static_cast<const __nv_bfloat16*>(d_skip);
     if (c->st_aspp && c->tm_feat_ptr != d_feat) {
       if (!encode_2d_sw128(&c->h_tm[TM_FEAT], feat, c->M1, g.Cin, g.Cin, 128, &terr)) return fail(c, DLV3P_ERR_CUDA, terr);
+      if (!encode_2d_slab(&c->h_tm[TM_FEAT_SLAB], feat, c->M1, g.Cin, g.Cin, &terr)) return fail(c, DLV3P_ERR_CUDA, terr);
       CU_TRY(c, cudaMemcpyAsync(&c->d_tm[TM_FEAT], &c->h_tm[TM_FEAT], sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
+      CU_TRY(c, cudaMemcpyAsync(&c->d_tm[TM_FEAT_SLAB], &c->h_tm[TM_FEAT_SLAB], sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
       c->tm_feat_ptr = d_feat;
     }
     if (c->st_dec && c->tm_skip_ptr != d_skip) {
@@ -916,6 +940,7 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
     } else if (L.begin("aspp_dw_pool")) {
       AsppDwParams P = c->aspp_plan;
       P.x = feat; P.w = c->aspp_dw_w; P.shift = c->aspp_dw_shift; P.out = c->dw_out; P.pool_partial = c->pool_partial;
+      P.tmap_slab = &c->d_tm[TM_FEAT_SLAB];
       if (c->aspp_slab) {
         cudaError_t e = cudaFuncSetAttribute(aspp_dw_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->aspp_slab_smem));
         const int slabs = g.B * P.nchunks;
@@ -946,6 +971,7 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
         p.tmap_out = &c->d_tm[TM_O_ASPP0 + i];
         p.scale = c->pw_aspp[i].scale; p.shift = c->pw_aspp[i].shift; p.img_shift = nullptr;
         p.out = c->concat; p.K = g.Cin; p.N = 256; p.ldo = c->Ccat; p.col_off = 256 * i; p.relu = 1; p.epi = kEpiBf16;
+        p.a_kblock_rows = i == 0 ? 0 : c->M1;
       }
       L.end("aspp_branches_gemm", launch_pw(256, PL, c->num_sms, st));
     }
@@ -967,7 +993,10 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
       P.x = x256; P.out = c->dec_in; P.B = g.B; P.hi = c->h; P.wi = c->w; P.C = 256; P.ho = c->hs; P.wo = c->ws;
       P.ldo = 304; P.col_off = 0;
       P.sy = static_cast<float>(c->h) / static_cast<float>(c->hs); P.sx = static_cast<float>(c->w) / static_cast<float>(c->ws);
-      resize_bilinear_kernel<<<dim3(c->hs, g.B), 256, 0, st>>>(P);
+      if (c->hs == 4 * c->h && c->ws == 4 * c->w)
+        resize_bilinear_x4_kernel<<<grid_for(static_cast<size_t>(g.B) * (c->h + 1) * (c->w + 1) * 32, c->num_sms), 256, 0, st>>>(P);
+      else
+        resize_bilinear_kernel<<<dim3(c->hs, g.B), 256, 0, st>>>(P);
       L.end("decoder_resize", cudaGetLastError());
     }
     if (L.begin("feature_projection0_gemm")) {
@@ -1124,7 +1153,20 @@ int dlv3p_read_tap(dlv3p_ctx* c, const char* name, float* host_out, size_t host_
   bool is_f32 = false;
   if (n == "aspp_out" && c->aspp_out) { src = c->aspp_out; elems = static_cast<size_t>(c->M1) * 256; }
   else if (n == "concat" && c->concat) { src = c->concat; elems = static_cast<size_t>(c->M1) * c->Ccat; }
-  else if (n == "aspp_depthwise" && c->dw_out) { src = c->dw_out; elems = static_cast<size_t>(3) * c->M1 * c->cfg.Cin; }
+  else if (n == "aspp_depthwise" && c->dw_out) {
+    // device layout is K-block-major [3][Cin/64][M1][64]; hand back [3][M1][Cin]
+    const int nch = ceil_div(c->cfg.Cin, 64), Cin = c->cfg.Cin;
+    const size_t total = static_cast<size_t>(3) * nch * c->M1 * 64;
+    if (host_elems < static_cast<size_t>(3) * c->M1 * Cin) return fail(c, DLV3P_ERR_INVALID, "tap buffer too small");
+    std::vector<uint16_t> tmp(total);
+    CU_TRY(c, cudaMemcpy(tmp.data(), c->dw_out, total * 2, cudaMemcpyDeviceToHost));
+    for (int r3 = 0; r3 < 3; ++r3)
+      for (int k = 0; k < nch; ++k)
+        for (int m = 0; m < c->M1; ++m)
+          for (int j = 0; j < 64 && k * 64 + j < Cin; ++j)
+            host_out[(static_cast<size_t>(r3) * c->M1 + m) * Cin + k * 64 + j] = bf16_to_f32(tmp[((static_cast<size_t>(r3) * nch + k) * c->M1 + m) * 64 + j]);
+    return DLV3P_OK;
+  }
   else if (n == "decoder_in" && c->dec_in) { src = c->dec_in; elems = static_cast<size_t>(c->M2) * 304; }
   else if (n == "decoder_conv0" && c->dec0) { src = c->dec0; elems = static_cast<size_t>(c->M2) * 256; }
   else if (n == "decoder_out" && c->dec1) { src = c->dec1; elems = static_cast<size_t>(c->M2) * 256; }
@@ -1276,7 +1318,10 @@ int dlv3p_op_resize_bilinear(int device, const void* x_bf16, int B, int hi, int 
   P.x = static_cast<const __nv_bfloat16*>(x_bf16); P.out = static_cast<__nv_bfloat16*>(out_bf16);
   P.B = B; P.hi = hi; P.wi = wi; P.C = C; P.ho = ho; P.wo = wo; P.ldo = C; P.col_off = 0;
   P.sy = static_cast<float>(hi) / static_cast<float>(ho); P.sx = static_cast<float>(wi) / static_cast<float>(wo);
-  resize_bilinear_kernel<<<dim3(ho, B), 256, 0, st>>>(P);
+  if (ho == 4 * hi && wo == 4 * wi)
+    resize_bilinear_x4_kernel<<<grid_for(static_cast<size_t>(B) * (hi + 1) * (wi + 1) * 32, sms), 256, 0, st>>>(P);
+  else
+    resize_bilinear_kernel<<<dim3(ho, B), 256, 0, st>>>(P);
   CU_TRY(nullptr, cudaGetLastError());
   CU_TRY(nullptr, cudaStreamSynchronize(st));
   return DLV3P_OK;
@@ -1376,7 +1421,11 @@ int dlv3p_op_time(int device, int op, const int64_t* d, int ndims, int iters, in
     P.sy = static_cast<float>(P.hi) / P.ho; P.sx = static_cast<float>(P.wi) / P.wo;
     P.x = reinterpret_cast<__nv_bfloat16*>(fill(static_cast<size_t>(P.B) * P.hi * P.wi * P.C));
     P.out = reinterpret_cast<__nv_bfloat16*>(tmp.alloc<uint16_t>(static_cast<size_t>(P.B) * P.ho * P.wo * P.C));
-    rc = run([&] { resize_bilinear_kernel<<<dim3(P.ho, P.B), 256, 0, st>>>(P); });
+    const bool x4 = P.ho == 4 * P.hi && P.wo == 4 * P.wi && !(flags & 1);
+    rc = run([&] {
+      if (x4) resize_bilinear_x4_kernel<<<grid_for(static_cast<size_t>(P.B) * (P.hi + 1) * (P.wi + 1) * 32, sms), 256, 0, st>>>(P);
+      else resize_bilinear_kernel<<<dim3(P.ho, P.B), 256, 0, st>>>(P);
+    });
   } else if (op == 3 && ndims >= 6) {   // resize_argmax {B,NC,hi,wi,ho,wo}
     ArgmaxParams P{};
     P.B = static_cast<int>(d[0]); P.NC = static_cast<int>(d[1]); P.hi = static_cast<int>(d[2]); P.wi = static_cast<int>(d[3]);
@@ -1396,14 +1445,27 @@ int dlv3p_op_time(int device, int op, const int64_t* d, int ndims, int iters, in
   } else if (op == 4 && ndims >= 4) {   // ASPP depthwise slab kernel {B,h,w,C} at OS16 rates
     AsppDwParams P{};
     P.B = static_cast<int>(d[0]); P.h = static_cast<int>(d[1]); P.w_ = static_cast<int>(d[2]); P.C = static_cast<int>(d[3]);
-    P.nrates = 3; P.rates[0] = 6; P.rates[1] = 12; P.rates[2] = 18; P.nchunks = ceil_div(P.C, 64); P.pool_items = 1; P.debug = flags;
+    P.nrates = 3; P.nchunks = ceil_div(P.C, 64); P.pool_items = 1; P.debug = flags;
+    static const int kTs[5] = {2, 3, 4, 6, 8};
+    const int rr[3] = {6, 12, 18};
+    for (int i = 0; i < 3; ++i) {
+      P.rates[i] = rr[i];
+      const int nt = ceil_div(P.w_, rr[i]);
+      int sel = 4;
+      for (int k = 4; k >= 0; --k)
+        if (kTs[k] >= (nt < 8 ? nt : 8)) sel = k;
+      P.ts_sel[i] = sel; P.nseg[i] = ceil_div(nt, kTs[sel]); P.item_off[i + 1] = P.item_off[i] + rr[i] * rr[i] * P.nseg[i];
+    }
     const size_t n = static_cast<size_t>(P.B) * P.h * P.w_ * P.C;
     P.x = reinterpret_cast<__nv_bfloat16*>(fill(n));
-    P.out = reinterpret_cast<__nv_bfloat16*>(tmp.alloc<uint16_t>(3 * n));
+    P.out = reinterpret_cast<__nv_bfloat16*>(tmp.alloc<uint16_t>(3 * static_cast<size_t>(P.nchunks) * P.B * P.h * P.w_ * 64));
     P.w = tmp.put(std::vector<float>(static_cast<size_t>(27) * P.C, 0.1f));
     P.shift = tmp.put(std::vector<float>(static_cast<size_t>(3) * P.C, 0.0f));
     P.pool_partial = tmp.alloc<float>(static_cast<size_t>(P.B) * P.C);
-    const size_t smem = static_cast<size_t>(P.h) * P.w_ * 128 + (27 * 64 + 3 * 64 + 16 * 64) * sizeof(float);
+    std::vector<CUtensorMap> tm(1);
+    if (!encode_2d_slab(&tm[0], P.x, static_cast<uint64_t>(P.B) * P.h * P.w_, P.C, P.C, &terr)) return fail(nullptr, DLV3P_ERR_CUDA, terr);
+    P.tmap_slab = tmp.put(tm);
+    const size_t smem = static_cast<size_t>(ceil_div(P.h * P.w_, 256)) * 32768 + (27 * 64 + 3 * 64 + 16 * 64) * sizeof(float) + 16;
     if (smem > 220 * 1024) return fail(nullptr, DLV3P_ERR_UNSUPPORTED, "op_time aspp_dw: map too large for the slab kernel");
     cudaFuncSetAttribute(aspp_dw_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     const int slabs = P.B * P.nchunks;

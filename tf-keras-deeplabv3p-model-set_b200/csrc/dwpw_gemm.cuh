@@ -11,7 +11,7 @@
 //   warp 0          TMA producer: halo tiles [10][18][64ch] per 64-channel K block (OOB zero fill = 'same' padding)
 //   warp 1          MMA issuer  : tcgen05.mma 128 x 256 x 16, fp32 accumulators in TMEM (2 stages)
 //   warps 2..5      epilogue    : tcgen05.ld -> BN scale/shift -> ReLU -> bf16 -> NHWC global
-//   warps 6..13     stencil     : two groups of 4 warps, alternating K blocks; packed fp32x2 FMAs
+//   warps 6..13     stencil     : 8 warps on the same K block (two row halves); packed fp32x2 FMAs
 #pragma once
 
 #include <cuda.h>
@@ -93,10 +93,10 @@ __global__ void __launch_bounds__(kDwThreads, 1) dwpw_gemm_kernel(const __grid_c
     mbar_init(w_full, 1);
     for (int i = 0; i < kDwInStages; ++i) {
       mbar_init(&in_full[i], 1);
-      mbar_init(&in_empty[i], 128);
+      mbar_init(&in_empty[i], 256);
     }
     for (int i = 0; i < AS; ++i) {
-      mbar_init(&a_full[i], 128);
+      mbar_init(&a_full[i], 256);
       mbar_init(&a_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -119,7 +119,10 @@ __global__ void __launch_bounds__(kDwThreads, 1) dwpw_gemm_kernel(const __grid_c
   const uint32_t tmem_base = *tmem_base_ptr;
   const int tiles_per_img = P.tiles_x * P.tiles_y;
 
-  if (warp == 0) {
+  const bool free_run = P.debug & 16;   // benchmark aid: stencil warps alone, no synchronisation at all
+  if (free_run && warp < 6) {
+    // nothing
+  } else if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       mbar_arrive_expect_tx(w_full, Cfg::kWBytes);
@@ -199,14 +202,12 @@ __global__ void __launch_bounds__(kDwThreads, 1) dwpw_gemm_kernel(const __grid_c
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 s = *reinterpret_cast<const float4*>(s_scale + c0 + j);
-          const float4 t = *reinterpret_cast<const float4*>(s_shift + c0 + j);
-          const float y0 = fmaxf(fmaf(__uint_as_float(v[j + 0]), s.x, t.x), 0.0f);
-          const float y1 = fmaxf(fmaf(__uint_as_float(v[j + 1]), s.y, t.y), 0.0f);
-          const float y2 = fmaxf(fmaf(__uint_as_float(v[j + 2]), s.z, t.z), 0.0f);
-          const float y3 = fmaxf(fmaf(__uint_as_float(v[j + 3]), s.w, t.w), 0.0f);
-          pk[j / 2 + 0] = pack_bf16x2(y0, y1);
-          pk[j / 2 + 1] = pack_bf16x2(y2, y3);
+          const ulonglong2 s = *reinterpret_cast<const ulonglong2*>(s_scale + c0 + j);   // two packed fp32 pairs
+          const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(s_shift + c0 + j);
+          const unsigned long long y01 = f32x2_fma(f32x2_make(v[j + 0], v[j + 1]), s.x, t.x);
+          const unsigned long long y23 = f32x2_fma(f32x2_make(v[j + 2], v[j + 3]), s.y, t.y);
+          pk[j / 2 + 0] = relu_bf16x2(f32x2_to_bf16x2(y01));
+          pk[j / 2 + 1] = relu_bf16x2(f32x2_to_bf16x2(y23));
         }
         if (ok && !(P.debug & 1)) {
 #pragma unroll
@@ -220,16 +221,20 @@ __global__ void __launch_bounds__(kDwThreads, 1) dwpw_gemm_kernel(const __grid_c
     }
   } else {
     // ------------------------------------------------------------------ depthwise stencil warps
-    const int g = (warp - 6) >> 2;          // group 0/1
-    const int wg = (warp - 6) & 3;          // warp within group
+    // All eight stencil warps work on the SAME K block: warps 6..9 produce output rows 0..3 of the tile, warps 10..13
+    // rows 4..7 (each half reads 6 halo rows).  The halo stages are therefore a true ring: the TMA of block c+1 is in
+    // flight while block c is being computed.  Every barrier has one producer set and one consumer set that advance
+    // together, so each parity wait is at most one phase behind.
+    const int g = (warp - 6) >> 2;          // row half 0/1
+    const int wg = (warp - 6) & 3;          // warp within the half
     const int v4 = lane & 15;               // which 4-channel slice of the 64-channel K block
     const int cp = wg * 2 + (lane >> 4);    // column pair: output cols 2cp, 2cp+1
+    constexpr int kRows = kDwTH / 2;        // output rows per half
     const uint32_t in_base = smem_u32(smem_in);
     const uint32_t a_base = smem_u32(smem_a);
-    // this CTA's K blocks are numbered c = 0, 1, 2, ... over (tile, kb); group g owns the blocks with c % 2 == g
     int my_tiles = 0;
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) ++my_tiles;
-    const uint32_t total_c = static_cast<uint32_t>(my_tiles) * KB;
+    const uint32_t total_c = static_cast<uint32_t>(my_tiles) * KB;   // this CTA's K blocks, numbered over (tile, kb)
     unsigned long long wlo[9], whi[9], sh_lo, sh_hi;
     auto load_taps = [&](uint32_t cn) {   // taps + shift of this thread's 4 channels; L1 is ~0 KB here -> L2 latency, so issue early
       const int ch = static_cast<int>(cn % KB) * 64 + v4 * 4;
@@ -243,79 +248,69 @@ __global__ void __launch_bounds__(kDwThreads, 1) dwpw_gemm_kernel(const __grid_c
       sh_lo = pack_f32x2(sh.x, sh.y);
       sh_hi = pack_f32x2(sh.z, sh.w);
     };
-    if (static_cast<uint32_t>(g) < total_c) load_taps(g);
-    {
-      for (uint32_t c = g; c < total_c; c += 2) {
-        // AS == 1: the parity arguments below are per GROUP, so keep the four warps of a group inside the same K block
-        // (a warp that ran a block ahead of a slow sibling could otherwise see a stale barrier phase and pass early)
-        if (AS == 1) asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
-        const uint32_t si = c % kDwInStages;
-        // Parity waits are only sound while the waiter is at most one phase behind the barrier.  With an even stage
-        // count every input stage belongs to one group; with an odd count the groups alternate on a stage, which is
-        // safe only because a single A stage (AS == 1) keeps the two groups in lock step (see the a_full wait below).
-        static_assert((kDwInStages % 2 == 0) || AS == 1, "odd input stage counts need the AS == 1 lock step");
-        mbar_wait(&in_full[si], (c / kDwInStages) & 1);
-        const uint32_t sa = c % AS;
-        const uint32_t in_addr = in_base + si * kDwInStageBytes + (2 * cp) * 128 + v4 * 8;
-        const uint32_t a_addr = a_base + sa * kDwAStageBytes;
+    if (total_c > 0) load_taps(0);
+    for (uint32_t c = 0; c < total_c; ++c) {
+      const uint32_t si = c % kDwInStages;
+      const uint32_t sa = c % AS;
+      if (!free_run) mbar_wait(&in_full[si], (c / kDwInStages) & 1);
+      const uint32_t in_addr = in_base + si * kDwInStageBytes + ((g * kRows) * kDwHaloW + 2 * cp) * 128 + v4 * 8;
+      const uint32_t a_addr = a_base + sa * kDwAStageBytes;
 
-        // rolling window over the 10 halo rows; 3 output rows in flight, 2 output columns, 2 channel pairs
-        unsigned long long acc_lo[3][2], acc_hi[3][2];
-        if (P.debug & 2) mbar_wait(&a_empty[sa], ((c / AS) & 1) ^ 1);
+      // rolling window over this half's 6 halo rows; 3 output rows in flight, 2 output columns, 2 channel pairs.
+      // The raw loads of halo row r+1 are issued before the math of row r (software pipelining of the LDS latency).
+      unsigned long long acc_lo[3][2], acc_hi[3][2];
+      uint2 raw_next[4];
 #pragma unroll
-        for (int r = 0; r < kDwHaloH; ++r) {
-          if (P.debug & 2) break;
-          unsigned long long x_lo[4], x_hi[4];
+      for (int cc = 0; cc < 4; ++cc) raw_next[cc] = lds_v2(in_addr + cc * 128);
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            const uint2 raw = lds_v2(in_addr + (r * kDwHaloW + cc) * 128);
-            x_lo[cc] = bf16x2_to_f32x2(raw.x);
-            x_hi[cc] = bf16x2_to_f32x2(raw.y);
-          }
-          if (r < kDwTH) {  // output row r starts with halo row r (dy = 0)
+      for (int r = 0; r < kRows + 2; ++r) {
+        unsigned long long x_lo[4], x_hi[4];
 #pragma unroll
-            for (int oc = 0; oc < 2; ++oc) {
-              acc_lo[r % 3][oc] = sh_lo;
-              acc_hi[r % 3][oc] = sh_hi;
-            }
-          }
+        for (int cc = 0; cc < 4; ++cc) {
+          x_lo[cc] = bf16x2_to_f32x2(raw_next[cc].x);
+          x_hi[cc] = bf16x2_to_f32x2(raw_next[cc].y);
+        }
+        if (r + 1 < kRows + 2) {
 #pragma unroll
-          for (int dy = 0; dy < 3; ++dy) {
-            const int orow = r - dy;
-            if (orow < 0 || orow >= kDwTH) continue;
+          for (int cc = 0; cc < 4; ++cc) raw_next[cc] = lds_v2(in_addr + ((r + 1) * kDwHaloW + cc) * 128);
+        }
+        if (r < kRows) {  // output row r starts with halo row r (dy = 0)
 #pragma unroll
-            for (int oc = 0; oc < 2; ++oc)
-#pragma unroll
-              for (int dx = 0; dx < 3; ++dx) {
-                ffma2(acc_lo[orow % 3][oc], wlo[dy * 3 + dx], x_lo[oc + dx]);
-                ffma2(acc_hi[orow % 3][oc], whi[dy * 3 + dx], x_hi[oc + dx]);
-              }
-          }
-          if (r >= 2) {  // output row r-2 is complete
-            const int orow = r - 2;
-            if (orow == 0) {
-              // With a single A stage the two stencil groups alternate on the same barrier pair, so a group can be
-              // two phases away from a_empty's current phase and a bare parity wait could alias.  Order the groups:
-              // first see the other group's tile (c-1) published, then wait for the MMA that consumes it.
-              if (AS == 1 && c > 0) mbar_wait(&a_full[0], (c - 1) & 1);
-              mbar_wait(&a_empty[sa], ((c / AS) & 1) ^ 1);  // MMA finished with this A stage
-            }
-#pragma unroll
-            for (int oc = 0; oc < 2; ++oc) {
-              const unsigned long long lo = acc_lo[orow % 3][oc], hi = acc_hi[orow % 3][oc];
-              const uint32_t p0 = pack_bf16x2(fmaxf(f32x2_lo(lo), 0.0f), fmaxf(f32x2_hi(lo), 0.0f));
-              const uint32_t p1 = pack_bf16x2(fmaxf(f32x2_lo(hi), 0.0f), fmaxf(f32x2_hi(hi), 0.0f));
-              const int m = orow * kDwTW + 2 * cp + oc;
-              const uint32_t chunk = static_cast<uint32_t>(v4 >> 1) ^ static_cast<uint32_t>(m & 7);
-              sts_v2(a_addr + m * 128 + chunk * 16 + (v4 & 1) * 8, p0, p1);
-            }
+          for (int oc = 0; oc < 2; ++oc) {
+            acc_lo[r % 3][oc] = sh_lo;
+            acc_hi[r % 3][oc] = sh_hi;
           }
         }
-        mbar_arrive(&in_empty[si]);      // halo tile fully consumed
-        fence_proxy_async_smem();        // make the A tile visible to the tensor-core (async) proxy
-        mbar_arrive(&a_full[sa]);
-        if (c + 2 < total_c) load_taps(c + 2);   // next block's taps: latency hides behind the barrier waits
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+          const int orow = r - dy;
+          if (orow < 0 || orow >= kRows) continue;
+#pragma unroll
+          for (int oc = 0; oc < 2; ++oc)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              ffma2(acc_lo[orow % 3][oc], wlo[dy * 3 + dx], x_lo[oc + dx]);
+              ffma2(acc_hi[orow % 3][oc], whi[dy * 3 + dx], x_hi[oc + dx]);
+            }
+        }
+        if (r >= 2) {  // output row r-2 of this half is complete
+          const int orow = r - 2;
+          if (orow == 0 && !free_run) mbar_wait(&a_empty[sa], ((c / AS) & 1) ^ 1);  // the MMA is done with this A stage
+#pragma unroll
+          for (int oc = 0; oc < 2; ++oc) {
+            const unsigned long long lo = acc_lo[orow % 3][oc], hi = acc_hi[orow % 3][oc];
+            const uint32_t p0 = relu_bf16x2(f32x2_to_bf16x2(lo));
+            const uint32_t p1 = relu_bf16x2(f32x2_to_bf16x2(hi));
+            const int m = (g * kRows + orow) * kDwTW + 2 * cp + oc;
+            const uint32_t chunk = static_cast<uint32_t>(v4 >> 1) ^ static_cast<uint32_t>(m & 7);
+            if (!(P.debug & 2)) sts_v2(a_addr + m * 128 + chunk * 16 + (v4 & 1) * 8, p0, p1);
+          }
+        }
       }
+      if (!free_run) mbar_arrive(&in_empty[si]);   // halo tile fully consumed by this thread
+      fence_proxy_async_smem();                    // make the A tile visible to the tensor-core (async) proxy
+      if (!free_run) mbar_arrive(&a_full[sa]);
+      if (c + 1 < total_c) load_taps(c + 1);       // next block's taps: the L2 latency hides behind the barrier waits
     }
   }
 

@@ -55,7 +55,8 @@ struct AsppDwParams {
   const __nv_bfloat16* x;   // [B,h,w,C]
   const float* w;           // [nrates][9][C]  BN scale folded
   const float* shift;       // [nrates][C]
-  __nv_bfloat16* out;       // [nrates][B*h*w][C]
+  __nv_bfloat16* out;       // [nrates][C/64 chunks][B*h*w][64]: K-block-major, every 64-channel slab of a rate is contiguous
+                            // (sequential HBM writes here, contiguous 16 KB TMA boxes for the pointwise GEMM's A operand)
   float* pool_partial;      // [B][pool_items][C]  (rate 0 items also reduce their pixels for the pooling branch)
   int B, h, w_, C;
   int nrates;
@@ -67,6 +68,7 @@ struct AsppDwParams {
   int pool_items;           // item_off[1]
   long long total_warps;    // B * item_off[nrates] * nchunks
   int debug;                // benchmark aid: bit0 skip output stores, bit1 skip the tap math
+  const void* tmap_slab;    // slab kernel: 2D [B*h*w, C] bf16 view of x, box {64, 256}, no swizzle (device memory)
 };
 
 __device__ __forceinline__ unsigned long long f32x2_from_bf16x2(uint32_t v) {
@@ -113,7 +115,7 @@ __device__ __forceinline__ void aspp_dw_phase_item(const AsppDwParams& P, int b,
 
   const size_t img_px = static_cast<size_t>(P.h) * P.w_;
   const __nv_bfloat16* xb = P.x + static_cast<size_t>(b) * img_px * P.C + cc;
-  __nv_bfloat16* ob = P.out + (static_cast<size_t>(ri) * P.B + b) * img_px * P.C + cc;
+  __nv_bfloat16* ob = P.out + ((static_cast<size_t>(ri) * P.nchunks + chunk) * P.B + b) * img_px * 64 + lane * 2;
   const uint32_t slab_lane = slab + lane * 4;
   const int na = pi < P.h ? (P.h - pi + r - 1) / r : 0;   // rows of this phase image
   const int t0 = seg * TS;                                 // first output column (phase coordinates)
@@ -147,7 +149,7 @@ __device__ __forceinline__ void aspp_dw_phase_item(const AsppDwParams& P, int b,
       if (ch_ok && j < P.w_ && !(P.debug & 1)) {
         const float lo = fmaxf(__uint_as_float(static_cast<uint32_t>(acc)), 0.0f);
         const float hi = fmaxf(__uint_as_float(static_cast<uint32_t>(acc >> 32)), 0.0f);
-        *reinterpret_cast<uint32_t*>(ob + (static_cast<size_t>(i) * P.w_ + j) * P.C) = pack_bf16x2(lo, hi);
+        *reinterpret_cast<uint32_t*>(ob + (static_cast<size_t>(i) * P.w_ + j) * 64) = pack_bf16x2(lo, hi);
         if (!kSmem) psum = fadd2(psum, mid[t + 1]);
       }
     }
@@ -220,25 +222,28 @@ constexpr int kSlabThreads = 512;
 __global__ void __launch_bounds__(kSlabThreads, 1) aspp_dw_slab_kernel(const __grid_constant__ AsppDwParams P) {
   extern __shared__ __align__(128) uint8_t slab_smem[];
   const int npix = P.h * P.w_;
+  const int nbox = (npix + 255) / 256;                 // TMA boxes of 256 pixels x 64 channels (32 KB each)
   uint8_t* s_slab = slab_smem;
-  float* s_w = reinterpret_cast<float*>(s_slab + static_cast<size_t>(npix) * 128);   // [27][64]
+  float* s_w = reinterpret_cast<float*>(s_slab + static_cast<size_t>(nbox) * 256 * 128);   // [27][64]
   float* s_shift = s_w + 27 * 64;                                                     // [3][64]
   float* s_red = s_shift + 3 * 64;                                                    // [16][64]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_red + 16 * 64);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t slab = smem_u32(s_slab);
   const int nitems = P.item_off[P.nrates];
   const int num_slabs = P.B * P.nchunks;
+  if (tid == 0) {
+    mbar_init(s_bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  uint32_t slab_phase = 0;
   for (int sid = blockIdx.x; sid < num_slabs; sid += gridDim.x) {
     const int b = sid / P.nchunks, chunk = sid - b * P.nchunks;
-    const __nv_bfloat16* xs = P.x + static_cast<size_t>(b) * npix * P.C + chunk * 64;
-    for (int idx = tid; idx < npix * 8; idx += kSlabThreads) {
-      const int p = idx >> 3, part = idx & 7;
-      const uint32_t dst = slab + p * 128 + part * 16;
-      if (chunk * 64 + part * 8 < P.C) {
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(xs + static_cast<size_t>(p) * P.C + part * 8) : "memory");
-      } else {
-        sts_v4(dst, make_uint4(0u, 0u, 0u, 0u));
-      }
+    if (tid == 0) {   // the whole slab arrives through TMA (OOB channels / rows are zero filled); x is read from HBM once
+      mbar_arrive_expect_tx(s_bar, static_cast<uint32_t>(nbox) * 32768u);
+      for (int q = 0; q < nbox; ++q)
+        tma_load_2d(s_slab + static_cast<size_t>(q) * 32768, P.tmap_slab, s_bar, chunk * 64, b * npix + q * 256, kEvictFirst);
     }
     for (int i = tid; i < P.nrates * 9 * 64; i += kSlabThreads) {
       const int cc = chunk * 64 + (i & 63);
@@ -248,9 +253,9 @@ __global__ void __launch_bounds__(kSlabThreads, 1) aspp_dw_slab_kernel(const __g
       const int cc = chunk * 64 + (i & 63);
       s_shift[i] = cc < P.C ? __ldg(P.shift + static_cast<size_t>(i >> 6) * P.C + cc) : 0.0f;
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
+    __syncthreads();                  // taps / shifts staged
+    mbar_wait(s_bar, slab_phase);     // slab landed
+    slab_phase ^= 1;
 
     // the 16 warps share the (rate, phase, segment) items of the slab, heaviest rate first
     for (int it = warp; it < nitems; it += kSlabThreads / 32) aspp_dw_dispatch<true>(P, b, chunk, it, lane, slab, s_w, s_shift);
@@ -488,6 +493,60 @@ __global__ void __launch_bounds__(256) resize_bilinear_kernel(const ResizeParams
       o[k] = lerp_nofma(top, bot, ty);
     }
     stg_v4(orow + static_cast<size_t>(X) * P.ldo + vec * 8, pack8(o));
+  }
+}
+
+// x4 upsampling (decoder_resize at OS16: 32x32 -> 128x128): one warp per low-res cell, lane = 8-channel vector.
+// The 4x4 outputs Y in [4m+2, 4m+6), X in [4k+2, 4k+6) share the four corner pixels (m, m+1) x (k, k+1): corners are
+// loaded and unpacked once, the horizontal lerps once per column.  Same operations in the same order as the generic
+// kernel / the oracle (top/bottom lerp, then vertical), so the result is bit identical.
+__global__ void __launch_bounds__(256) resize_bilinear_x4_kernel(const ResizeParams P) {
+  const int cells_x = P.wi + 1, cells_y = P.hi + 1;
+  const int total = P.B * cells_y * cells_x;
+  const int lane = threadIdx.x & 31;
+  const int vecs = P.C >> 3;
+  for (int cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); cell < total; cell += gridDim.x * (blockDim.x >> 5)) {
+    const int k = cell % cells_x - 1;
+    const int r = cell / cells_x;
+    const int m = r % cells_y - 1;
+    const int b = r / cells_y;
+    const int X0 = 4 * k + 2, Y0 = 4 * m + 2;
+    float ty[4], tx[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      int lo, hi;
+      resize_coord(min(max(Y0 + d, 0), P.ho - 1), P.sy, P.hi, lo, hi, ty[d]);
+      resize_coord(min(max(X0 + d, 0), P.wo - 1), P.sx, P.wi, lo, hi, tx[d]);
+    }
+    const int y0 = max(m, 0), y1 = min(m + 1, P.hi - 1), x0 = max(k, 0), x1 = min(k + 1, P.wi - 1);
+    const __nv_bfloat16* xb = P.x + static_cast<size_t>(b) * P.hi * P.wi * P.C;
+    for (int vec = lane; vec < vecs; vec += 32) {
+      float tl[8], tr[8], bl[8], br[8];
+      unpack8(ldg_nc_v4(xb + (static_cast<size_t>(y0) * P.wi + x0) * P.C + vec * 8), tl);
+      unpack8(ldg_nc_v4(xb + (static_cast<size_t>(y0) * P.wi + x1) * P.C + vec * 8), tr);
+      unpack8(ldg_nc_v4(xb + (static_cast<size_t>(y1) * P.wi + x0) * P.C + vec * 8), bl);
+      unpack8(ldg_nc_v4(xb + (static_cast<size_t>(y1) * P.wi + x1) * P.C + vec * 8), br);
+#pragma unroll
+      for (int dx = 0; dx < 4; ++dx) {
+        const int X = X0 + dx;
+        if (X < 0 || X >= P.wo) continue;
+        float top[8], bot[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          top[c] = lerp_nofma(tl[c], tr[c], tx[dx]);
+          bot[c] = lerp_nofma(bl[c], br[c], tx[dx]);
+        }
+#pragma unroll
+        for (int dy = 0; dy < 4; ++dy) {
+          const int Y = Y0 + dy;
+          if (Y < 0 || Y >= P.ho) continue;
+          float o[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) o[c] = lerp_nofma(top[c], bot[c], ty[dy]);
+          stg_v4(P.out + ((static_cast<size_t>(b) * P.ho + Y) * P.wo + X) * P.ldo + P.col_off + vec * 8, pack8(o));
+        }
+      }
+    }
   }
 }
 

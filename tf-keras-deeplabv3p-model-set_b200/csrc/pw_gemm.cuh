@@ -47,6 +47,7 @@ struct PwProblem {
   int col_off;     // bf16 modes: first output column
   int relu;
   int epi;
+  int a_kblock_rows;  // 0: A is [M, K] row-major.  > 0: A is K-block-major [K/64][a_kblock_rows][64] (ASPP depthwise outputs)
 };
 
 struct PwLaunch {
@@ -123,8 +124,10 @@ __global__ void __launch_bounds__(kPwThreads, 1) pw_gemm_kernel(const __grid_con
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(smem_a + stage * (kPwBM * 128), P.tmap_a, &full_bar[stage], kb * kPwBK, tile * kPwBM,
-                      kEvictFirst);
+          if (P.a_kblock_rows > 0)
+            tma_load_2d(smem_a + stage * (kPwBM * 128), P.tmap_a, &full_bar[stage], 0, kb * P.a_kblock_rows + tile * kPwBM, kEvictFirst);
+          else
+            tma_load_2d(smem_a + stage * (kPwBM * 128), P.tmap_a, &full_bar[stage], kb * kPwBK, tile * kPwBM, kEvictFirst);
           tma_load_2d(smem_b + stage * (BN * 128), P.tmap_w, &full_bar[stage], kb * kPwBK, 0, kEvictLast);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -223,20 +226,17 @@ __global__ void __launch_bounds__(kPwThreads, 1) pw_gemm_kernel(const __grid_con
               tmem_ld_wait();
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
-                const float4 s0 = *reinterpret_cast<const float4*>(s_scale + c0 + j);
-                const float4 s1 = *reinterpret_cast<const float4*>(s_scale + c0 + j + 4);
-                const float4 t0 = *reinterpret_cast<const float4*>(shift + c0 + j);       // generic load: smem, or global when straddling
-                const float4 t1 = *reinterpret_cast<const float4*>(shift + c0 + j + 4);
-                float y0 = fmaf(__uint_as_float(v[j + 0]), s0.x, t0.x), y1 = fmaf(__uint_as_float(v[j + 1]), s0.y, t0.y);
-                float y2 = fmaf(__uint_as_float(v[j + 2]), s0.z, t0.z), y3 = fmaf(__uint_as_float(v[j + 3]), s0.w, t0.w);
-                float y4 = fmaf(__uint_as_float(v[j + 4]), s1.x, t1.x), y5 = fmaf(__uint_as_float(v[j + 5]), s1.y, t1.y);
-                float y6 = fmaf(__uint_as_float(v[j + 6]), s1.z, t1.z), y7 = fmaf(__uint_as_float(v[j + 7]), s1.w, t1.w);
-                if (P.relu) {
-                  y0 = fmaxf(y0, 0.0f); y1 = fmaxf(y1, 0.0f); y2 = fmaxf(y2, 0.0f); y3 = fmaxf(y3, 0.0f);
-                  y4 = fmaxf(y4, 0.0f); y5 = fmaxf(y5, 0.0f); y6 = fmaxf(y6, 0.0f); y7 = fmaxf(y7, 0.0f);
-                }
+                const ulonglong2 s0 = *reinterpret_cast<const ulonglong2*>(s_scale + c0 + j);       // packed fp32 pairs
+                const ulonglong2 s1 = *reinterpret_cast<const ulonglong2*>(s_scale + c0 + j + 4);
+                const ulonglong2 t0 = *reinterpret_cast<const ulonglong2*>(shift + c0 + j);          // generic: smem, or global when straddling
+                const ulonglong2 t1 = *reinterpret_cast<const ulonglong2*>(shift + c0 + j + 4);
+                uint32_t q0 = f32x2_to_bf16x2(f32x2_fma(f32x2_make(v[j + 0], v[j + 1]), s0.x, t0.x));
+                uint32_t q1 = f32x2_to_bf16x2(f32x2_fma(f32x2_make(v[j + 2], v[j + 3]), s0.y, t0.y));
+                uint32_t q2 = f32x2_to_bf16x2(f32x2_fma(f32x2_make(v[j + 4], v[j + 5]), s1.x, t1.x));
+                uint32_t q3 = f32x2_to_bf16x2(f32x2_fma(f32x2_make(v[j + 6], v[j + 7]), s1.y, t1.y));
+                if (P.relu) { q0 = relu_bf16x2(q0); q1 = relu_bf16x2(q1); q2 = relu_bf16x2(q2); q3 = relu_bf16x2(q3); }
                 const uint32_t chunk = static_cast<uint32_t>(half * 4 + (j >> 3)) ^ static_cast<uint32_t>(lane & 7);
-                sts_v4(cbuf + chunk * 16, make_uint4(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3), pack_bf16x2(y4, y5), pack_bf16x2(y6, y7)));
+                sts_v4(cbuf + chunk * 16, make_uint4(q0, q1, q2, q3));
               }
             }
             fence_proxy_async_smem();

@@ -38,14 +38,15 @@ def main():
     if 'sep' in sel:
         for C in (256, 304):
             M = 32 * 128 * 128
-            for fl in ((0, 8, 1, 4, 5) if C == 256 else (0, 1, 4, 5)):
+            for fl in ((0, 1, 4, 5, 16) if C == 256 else (0, 16)):
                 rec('sepconv B=32 128x128 C=%d' % C, 1, [32, 128, 128, C], fl, flop=2.0 * M * C * 256, byts=2.0 * M * (C + 256))
     if 'aspp' in sel:
         n = 32 * 32 * 32 * 2048 * 2.0
         for fl in (0, 1, 2, 3):
             rec('aspp_dw slab B=32 32x32 C=2048', 4, [32, 32, 32, 2048], fl, byts=4 * n)
     if 'mem' in sel:
-        rec('resize 32x32x256 -> 128x128 (B=32)', 2, [32, 32, 32, 256, 128, 128], 0, byts=32 * (1024 * 512 + 16384 * 512.0))
+        rec('resize x4 32x32x256 -> 128x128 (B=32)', 2, [32, 32, 32, 256, 128, 128], 0, byts=32 * (1024 * 512 + 16384 * 512.0))
+        rec('resize generic (same shape)', 2, [32, 32, 32, 256, 128, 128], 1, byts=32 * (1024 * 512 + 16384 * 512.0))
         rec('resize_argmax x4 21cls 128->512 (B=32)', 3, [32, 21, 128, 128, 512, 512], 0, byts=32 * (16384 * 84 + 262144.0))
         rec('resize_argmax generic (same shape)', 3, [32, 21, 128, 128, 512, 512], 1, byts=32 * (16384 * 84 + 262144.0))
     with open(os.path.join(OUT, 'kbench.txt'), 'a') as f:
