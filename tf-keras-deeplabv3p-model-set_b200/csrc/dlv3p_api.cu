@@ -115,6 +115,23 @@ bool encode_2d_slab(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t c
 bool encode_2d_out(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, std::string* err) {
   return encode_2d_sw128(tm, base, rows, cols, ld, 32, err);
 }
+// 4D bf16 NHWC output {C, W, H, B}, box {64, 16, 2, 1}, 128B swizzle: the fused kernel's TMA-store epilogue
+bool encode_4d_out(CUtensorMap* tm, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C, std::string* err) {
+  EncodeTiledFn fn = get_encode_fn(err);
+  if (!fn) return false;
+  cuuint64_t gdim[4] = {C, W, H, B};
+  cuuint64_t gstride[3] = {C * 2, W * C * 2, H * W * C * 2};
+  cuuint32_t box[4] = {64, 16, 2, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) *err = fmt("cuTensorMapEncodeTiled(4d out) -> %d", (int)r);
+    return false;
+  }
+  return true;
+}
 // 4D bf16 NHWC {C, W, H, B} (channel stride ldc elements), box {64, bw, bh, 1}, no swizzle, OOB -> 0
 bool encode_4d_halo(CUtensorMap* tm, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint64_t ldc,
                     uint32_t bw, uint32_t bh, std::string* err) {
@@ -218,7 +235,7 @@ cudaError_t launch_dwpw(int KB, const DwPwParams& P, int num_sms, cudaStream_t s
   switch (KB) {
     case 1: return launch_dwpw_t<1, 2, 4>(P, num_sms, st);
     case 2: return launch_dwpw_t<2, 2, 4>(P, num_sms, st);
-    case 3: return launch_dwpw_t<3, 2, 4>(P, num_sms, st);
+    case 3: return launch_dwpw_t<3, 2, 2>(P, num_sms, st);
     case 4: return (P.debug & 8) ? launch_dwpw_t<4, 1, 3>(P, num_sms, st) : launch_dwpw_t<4, 2, 2>(P, num_sms, st);
     case 5: return launch_dwpw_t<5, 1, 2>(P, num_sms, st);
     default: return cudaErrorInvalidValue;
@@ -248,7 +265,7 @@ struct WeightSlot {
 enum TmSlot {
   TM_FEAT = 0, TM_DW1, TM_DW2, TM_DW3, TM_CONCAT, TM_SKIP, TM_DECIN, TM_DEC0, TM_CLS_IN,
   TM_W_ASPP0, TM_W_ASPP1, TM_W_ASPP2, TM_W_ASPP3, TM_W_PROJ, TM_W_FP0, TM_W_DEC0, TM_W_DEC1, TM_W_CLS,
-  TM_O_ASPP0, TM_O_ASPP1, TM_O_ASPP2, TM_O_ASPP3, TM_O_PROJ, TM_O_FP0, TM_O_DEC0, TM_O_DEC1, TM_FEAT_SLAB,
+  TM_O_ASPP0, TM_O_ASPP1, TM_O_ASPP2, TM_O_ASPP3, TM_O_PROJ, TM_O_FP0, TM_O_DEC0, TM_O_DEC1, TM_FEAT_SLAB, TM_O4_DEC0, TM_O4_DEC1,
   TM_COUNT
 };
 
@@ -591,8 +608,11 @@ int dlv3p_create(const dlv3p_config* cfg, int device, dlv3p_ctx** out) {
         int sel = 4;
         for (int k = 4; k >= 0; --k)
           if (kTs[k] >= (nt < 8 ? nt : 8)) sel = k;
+        const int na_max = ceil_div(c->h, rr);
+        if (na_max <= 2 && nt <= 2) sel = 5;
+        else if (na_max <= 3 && nt <= 3) sel = 6;
         A.ts_sel[i] = sel;
-        A.nseg[i] = ceil_div(nt, kTs[sel]);
+        A.nseg[i] = sel >= 5 ? 1 : ceil_div(nt, kTs[sel]);
         A.item_off[i + 1] = A.item_off[i] + rr * rr * A.nseg[i];
       }
       c->aspp_slab_smem = static_cast<size_t>(ceil_div(px, 256)) * 32768 + (27 * 64 + 3 * 64 + 16 * 64) * sizeof(float) + 16;
@@ -786,6 +806,8 @@ int dlv3p_finalize_weights(dlv3p_ctx* c) {
     ok = ok && encode_2d_out(&c->h_tm[TM_O_FP0], c->dec_in + 256, c->M2, 48, 304, &terr);
     ok = ok && encode_2d_out(&c->h_tm[TM_O_DEC0], c->dec0, c->M2, 256, 256, &terr);
     ok = ok && encode_2d_out(&c->h_tm[TM_O_DEC1], c->dec1, c->M2, 256, 256, &terr);
+    ok = ok && encode_4d_out(&c->h_tm[TM_O4_DEC0], c->dec0, g.B, c->hs, c->ws, 256, &terr);
+    ok = ok && encode_4d_out(&c->h_tm[TM_O4_DEC1], c->dec1, g.B, c->hs, c->ws, 256, &terr);
     if (g.flags & DLV3P_FLAG_UNFUSED_DECODER) {
       ok = ok && enc2(TM_DECIN, c->dec_tmp, c->M2, 304, 304, 128);
       ok = ok && enc2(TM_DEC0, c->dec_tmp, c->M2, 256, 256, 128);
@@ -957,7 +979,7 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
       P.ip_scale = c->ip_scale; P.ip_shift = c->ip_shift; P.w_proj4 = reinterpret_cast<const __nv_bfloat16*>(c->w_proj4);
       P.proj_scale = c->pw_proj.scale; P.proj_shift = c->pw_proj.shift; P.img_shift = c->img_shift; P.b4_out = c->b4;
       P.C = g.Cin; P.nbands = c->nbands; P.inv_count = 1.0f / static_cast<float>(c->h * c->w);
-      pool_proj_kernel<<<g.B, 1024, (g.Cin + 256 + 1024) * sizeof(float), st>>>(P);
+      pool_proj_kernel<<<g.B, 1024, (g.Cin + 256 + 2048) * sizeof(float), st>>>(P);
       L.end("pool_proj", cudaGetLastError());
     }
     if (L.begin("aspp_branches_gemm")) {
@@ -1034,6 +1056,7 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
         DwPwParams P{};
         P.tmap_x = &c->d_tm[s.tm_x]; P.tmap_w = &c->d_tm[s.tm_w];
         P.dw_w = s.dw->w; P.dw_shift = s.dw->shift; P.scale = s.pw->scale; P.shift = s.pw->shift; P.out = s.out;
+        P.tmap_out = &c->d_tm[s.tm_o == TM_O_DEC0 ? TM_O4_DEC0 : TM_O4_DEC1];
         P.B = g.B; P.H = c->hs; P.W = c->ws; P.tiles_x = tiles_x; P.tiles_y = tiles_y; P.num_tiles = g.B * tiles_x * tiles_y;
         L.end(s.name, launch_dwpw(s.dw->Cpad / 64, P, c->num_sms, st));
       }
@@ -1294,13 +1317,14 @@ int dlv3p_op_sepconv(int device, const void* x_bf16, int B, int H, int W_, int C
   float* ds = tmp.put(s);
   float* dt = tmp.put(t);
   std::string terr;
-  std::vector<CUtensorMap> tm(2);
-  if (!encode_4d_halo(&tm[0], x_bf16, B, H, W_, C, C, kDwHaloW, kDwHaloH, &terr) || !encode_2d_sw128(&tm[1], dpw, 256, Cpad, Cpad, 256, &terr))
+  std::vector<CUtensorMap> tm(3);
+  if (!encode_4d_halo(&tm[0], x_bf16, B, H, W_, C, C, kDwHaloW, kDwHaloH, &terr) || !encode_2d_sw128(&tm[1], dpw, 256, Cpad, Cpad, 256, &terr) ||
+      !encode_4d_out(&tm[2], out_bf16, B, H, W_, 256, &terr))
     return fail(nullptr, DLV3P_ERR_CUDA, terr);
   CUtensorMap* dtm = tmp.put(tm);
   if (!ddw || !dsh || !dpw || !ds || !dt || !dtm) return fail(nullptr, DLV3P_ERR_NOMEM, "op_sepconv: cudaMalloc failed");
   DwPwParams P{};
-  P.tmap_x = &dtm[0]; P.tmap_w = &dtm[1]; P.dw_w = ddw; P.dw_shift = dsh; P.scale = ds; P.shift = dt;
+  P.tmap_x = &dtm[0]; P.tmap_w = &dtm[1]; P.tmap_out = &dtm[2]; P.dw_w = ddw; P.dw_shift = dsh; P.scale = ds; P.shift = dt;
   P.out = static_cast<__nv_bfloat16*>(out_bf16); P.B = B; P.H = H; P.W = W_;
   P.tiles_x = ceil_div(W_, kDwTW); P.tiles_y = ceil_div(H, kDwTH); P.num_tiles = B * P.tiles_x * P.tiles_y;
   CU_TRY(nullptr, launch_dwpw(KB, P, sms, st));
@@ -1406,11 +1430,12 @@ int dlv3p_op_time(int device, int op, const int64_t* d, int ndims, int iters, in
     float* dsh = tmp.put(std::vector<float>(Cpad, 0.0f));
     float* s = tmp.put(std::vector<float>(256, 1.0f));
     float* t = tmp.put(std::vector<float>(256, 0.0f));
-    std::vector<CUtensorMap> tm(2);
-    if (!encode_4d_halo(&tm[0], x, B, H, W_, C, C, kDwHaloW, kDwHaloH, &terr) || !encode_2d_sw128(&tm[1], w, 256, Cpad, Cpad, 256, &terr)) return fail(nullptr, DLV3P_ERR_CUDA, terr);
+    std::vector<CUtensorMap> tm(3);
+    if (!encode_4d_halo(&tm[0], x, B, H, W_, C, C, kDwHaloW, kDwHaloH, &terr) || !encode_2d_sw128(&tm[1], w, 256, Cpad, Cpad, 256, &terr) ||
+        !encode_4d_out(&tm[2], o, B, H, W_, 256, &terr)) return fail(nullptr, DLV3P_ERR_CUDA, terr);
     CUtensorMap* dtm = tmp.put(tm);
     DwPwParams P{};
-    P.tmap_x = &dtm[0]; P.tmap_w = &dtm[1]; P.dw_w = dw; P.dw_shift = dsh; P.scale = s; P.shift = t;
+    P.tmap_x = &dtm[0]; P.tmap_w = &dtm[1]; P.tmap_out = &dtm[2]; P.dw_w = dw; P.dw_shift = dsh; P.scale = s; P.shift = t;
     P.out = reinterpret_cast<__nv_bfloat16*>(o); P.B = B; P.H = H; P.W = W_;
     P.tiles_x = ceil_div(W_, kDwTW); P.tiles_y = ceil_div(H, kDwTH); P.num_tiles = B * P.tiles_x * P.tiles_y; P.debug = flags;
     rc = run([&] { launch_dwpw(KB, P, sms, st); });
@@ -1454,7 +1479,10 @@ int dlv3p_op_time(int device, int op, const int64_t* d, int ndims, int iters, in
       int sel = 4;
       for (int k = 4; k >= 0; --k)
         if (kTs[k] >= (nt < 8 ? nt : 8)) sel = k;
-      P.ts_sel[i] = sel; P.nseg[i] = ceil_div(nt, kTs[sel]); P.item_off[i + 1] = P.item_off[i] + rr[i] * rr[i] * P.nseg[i];
+      const int na_max = ceil_div(P.h, rr[i]);
+      if (na_max <= 2 && nt <= 2) sel = 5;
+      else if (na_max <= 3 && nt <= 3) sel = 6;
+      P.ts_sel[i] = sel; P.nseg[i] = sel >= 5 ? 1 : ceil_div(nt, kTs[sel]); P.item_off[i + 1] = P.item_off[i] + rr[i] * rr[i] * P.nseg[i];
     }
     const size_t n = static_cast<size_t>(P.B) * P.h * P.w_ * P.C;
     P.x = reinterpret_cast<__nv_bfloat16*>(fill(n));

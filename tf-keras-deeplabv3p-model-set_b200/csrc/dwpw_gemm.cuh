@@ -38,6 +38,7 @@ struct DwPwParams {
   const float* scale;         // [256] pointwise BN scale
   const float* shift;         // [256] pointwise BN shift
   __nv_bfloat16* out;         // [B, H, W, 256]
+  const CUtensorMap* tmap_out;  // 4D {256, W, H, B} bf16, box {64, 16, 2, 1}, SWIZZLE_128B (TMA-store epilogue, KB <= 4)
   int B, H, W;
   int tiles_x, tiles_y, num_tiles;
   int debug;  // benchmark aid: bit0 skip epilogue stores, bit1 skip the stencil math (A tiles left stale), bit2 skip the MMAs
@@ -45,10 +46,12 @@ struct DwPwParams {
 
 template <int KB, int AS, int kDwInStages>
 struct DwPwCfg {
+  static constexpr bool kTmaStore = KB <= 4;                    // room for the epilogue's store staging (4 warps x 4 KB)
+  static constexpr int kStoreBytes = kTmaStore ? 4 * 4096 : 0;   // (+1 KB alignment slack, added below)
   static constexpr int kWBytes = KB * kDwWBlockBytes;
   static constexpr int kABytes = AS * kDwAStageBytes;
   static constexpr int kInBytes = kDwInStages * kDwInStageBytes;
-  static constexpr int kSmemBytes = kWBytes + kABytes + kInBytes + 2048 /*BN scale+shift*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kWBytes + kABytes + kInBytes + kStoreBytes + (kTmaStore ? 1024 : 0) + 2048 /*BN scale+shift*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
@@ -74,7 +77,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) dwpw_gemm_kernel(const __grid_c
   uint8_t* smem_w = smem;                      // KB x [256 rows x 128 B], swizzled
   uint8_t* smem_a = smem_w + Cfg::kWBytes;     // AS x [128 rows x 128 B], swizzled
   uint8_t* smem_in = smem_a + Cfg::kABytes;    // kDwInStages x [10][18][64] bf16
-  float* s_scale = reinterpret_cast<float*>(smem_in + Cfg::kInBytes);   // [256] pointwise BN scale (L1 is ~0 KB here)
+  uint8_t* smem_c = smem_in + Cfg::kInBytes;   // epilogue store staging (1024-byte aligned: all sizes above are multiples of 1024... the halo stages are 22.5 KB, so align up)
+  float* s_scale = reinterpret_cast<float*>(smem_c + Cfg::kStoreBytes + (Cfg::kTmaStore ? 1024 : 0));   // [256] pointwise BN scale (L1 is ~0 KB here)
   float* s_shift = s_scale + 256;                                        // [256]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
   uint64_t* w_full = bars;                     // [1]
@@ -194,6 +198,46 @@ __global__ void __launch_bounds__(kDwThreads, 1) dwpw_gemm_kernel(const __grid_c
       const bool ok = gy < P.H && gx < P.W;
       __nv_bfloat16* o = P.out + ((static_cast<size_t>(b) * P.H + gy) * P.W + gx) * kDwBN;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kDwBN;
+      if constexpr (Cfg::kTmaStore) {
+        // bf16 output through 128B-swizzled smem + TMA store: box = this warp's 2 tile rows x 16 pixels x 64 channels;
+        // partial tiles are clipped by the TMA unit
+        uint8_t* my_c = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_c) + 1023) & ~uintptr_t(1023)) + (warp - 2) * 4096;
+        const uint32_t cbuf = smem_u32(my_c) + lane * 128;
+#pragma unroll 1
+        for (int cb = 0; cb < kDwBN / 64; ++cb) {
+          uint32_t pk[32];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int c0 = cb * 64 + half * 32;
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(taddr + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const ulonglong2 s = *reinterpret_cast<const ulonglong2*>(s_scale + c0 + j);   // two packed fp32 pairs
+              const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(s_shift + c0 + j);
+              pk[half * 16 + j / 2 + 0] = relu_bf16x2(f32x2_to_bf16x2(f32x2_fma(f32x2_make(v[j + 0], v[j + 1]), s.x, t.x)));
+              pk[half * 16 + j / 2 + 1] = relu_bf16x2(f32x2_to_bf16x2(f32x2_fma(f32x2_make(v[j + 2], v[j + 3]), s.y, t.y)));
+            }
+          }
+          if (lane == 0) tma_store_wait_read<0>();   // the previous block has been read out of the staging buffer
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t chunk = static_cast<uint32_t>(j) ^ static_cast<uint32_t>(lane & 7);
+            sts_v4(cbuf + chunk * 16, make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && !(P.debug & 1)) {
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(P.tmap_out)),
+                         "r"(smem_u32(my_c)), "r"(cb * 64), "r"(tx * kDwTW), "r"(ty * kDwTH + 2 * q), "r"(b)
+                         : "memory");
+            tma_store_commit();
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int c0 = 0; c0 < kDwBN; c0 += 32) {
         uint32_t v[32];
@@ -216,9 +260,11 @@ __global__ void __launch_bounds__(kDwThreads, 1) dwpw_gemm_kernel(const __grid_c
                    make_uint4(pk[8 * j + 4], pk[8 * j + 5], pk[8 * j + 6], pk[8 * j + 7]));
         }
       }
+      }
       tcgen05_fence_before();
       mbar_arrive(&tmem_empty[acc]);
     }
+    if (Cfg::kTmaStore && lane == 0) tma_store_wait_all<0>();
   } else {
     // ------------------------------------------------------------------ depthwise stencil warps
     // All eight stencil warps work on the SAME K block: warps 6..9 produce output rows 0..3 of the tile, warps 10..13

@@ -63,7 +63,7 @@ struct AsppDwParams {
   int rates[3];
   int nchunks;              // ceil(C / 64)
   int nseg[3];              // column segments per phase image
-  int ts_sel[3];            // segment width selector: 0,1,2,3,4 -> 2,3,4,6,8 outputs per segment
+  int ts_sel[3];            // 0,1,2,3,4 -> 2,3,4,6,8 outputs per segment; 5 / 6 -> whole phase image (<= 2x2 / 3x3) in registers
   int item_off[4];          // prefix sums of items per rate (items = r*r*nseg)
   int pool_items;           // item_off[1]
   long long total_warps;    // B * item_off[nrates] * nchunks
@@ -180,6 +180,80 @@ __device__ __forceinline__ void aspp_dw_phase_item(const AsppDwParams& P, int b,
   }
 }
 
+// Small phase images (at most NA x NT pixels, e.g. rate 18 or 12 on a 32x32 map): the whole phase image lives in
+// registers, every output is a fully unrolled sum over the taps that exist at compile time.
+template <int NA, int NT, bool kSmem>
+__device__ __forceinline__ void aspp_dw_small_item(const AsppDwParams& P, int b, int chunk, int ri, int pi, int pj, int item_in_rate,
+                                                   int lane, uint32_t slab, const float* s_w, const float* s_shift) {
+  const int r = P.rates[ri];
+  const int c0 = chunk * 64 + lane * 2;
+  const bool ch_ok = c0 < P.C;
+  const int cc = ch_ok ? c0 : 0;
+  unsigned long long wt[9], sh;
+  if (kSmem) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float2 v = *reinterpret_cast<const float2*>(s_w + (ri * 9 + t) * 64 + lane * 2);
+      wt[t] = (static_cast<unsigned long long>(__float_as_uint(v.y)) << 32) | __float_as_uint(v.x);
+    }
+    const float2 shv = *reinterpret_cast<const float2*>(s_shift + ri * 64 + lane * 2);
+    sh = (static_cast<unsigned long long>(__float_as_uint(shv.y)) << 32) | __float_as_uint(shv.x);
+  } else {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(P.w + (static_cast<size_t>(ri) * 9 + t) * P.C + cc));
+      wt[t] = (static_cast<unsigned long long>(__float_as_uint(v.y)) << 32) | __float_as_uint(v.x);
+    }
+    const float2 shv = __ldg(reinterpret_cast<const float2*>(P.shift + static_cast<size_t>(ri) * P.C + cc));
+    sh = (static_cast<unsigned long long>(__float_as_uint(shv.y)) << 32) | __float_as_uint(shv.x);
+  }
+  const size_t img_px = static_cast<size_t>(P.h) * P.w_;
+  const __nv_bfloat16* xb = P.x + static_cast<size_t>(b) * img_px * P.C + cc;
+  __nv_bfloat16* ob = P.out + ((static_cast<size_t>(ri) * P.nchunks + chunk) * P.B + b) * img_px * 64 + lane * 2;
+  const uint32_t slab_lane = slab + lane * 4;
+  unsigned long long x[NA][NT];
+  unsigned long long psum = 0ull;
+#pragma unroll
+  for (int a = 0; a < NA; ++a)
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const int i = pi + r * a, j = pj + r * t;
+      uint32_t v = 0u;
+      if (ch_ok && i < P.h && j < P.w_) {
+        if (kSmem) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(slab_lane + (i * P.w_ + j) * 128));
+        else v = __ldg(reinterpret_cast<const unsigned int*>(xb + (static_cast<size_t>(i) * P.w_ + j) * P.C));
+      }
+      x[a][t] = f32x2_from_bf16x2(v);
+      if (!kSmem) psum = fadd2(psum, x[a][t]);
+    }
+#pragma unroll
+  for (int a = 0; a < NA; ++a)
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const int i = pi + r * a, j = pj + r * t;
+      if (i >= P.h || j >= P.w_) continue;       // warp-uniform
+      unsigned long long acc = sh;
+#pragma unroll
+      for (int u = 0; u < 3; ++u)
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+          const int aa = a + u - 1, tt = t + v - 1;
+          if (aa >= 0 && aa < NA && tt >= 0 && tt < NT) ffma2_acc(acc, wt[u * 3 + v], x[aa][tt]);   // resolved at compile time
+        }
+      if (ch_ok && !(P.debug & 1)) {
+        const float lo = fmaxf(__uint_as_float(static_cast<uint32_t>(acc)), 0.0f);
+        const float hi = fmaxf(__uint_as_float(static_cast<uint32_t>(acc >> 32)), 0.0f);
+        *reinterpret_cast<uint32_t*>(ob + (static_cast<size_t>(i) * P.w_ + j) * 64) = pack_bf16x2(lo, hi);
+      }
+    }
+  if (!kSmem && ri == 0 && ch_ok) {
+    float2 pv;
+    pv.x = __uint_as_float(static_cast<uint32_t>(psum));
+    pv.y = __uint_as_float(static_cast<uint32_t>(psum >> 32));
+    *reinterpret_cast<float2*>(P.pool_partial + (static_cast<size_t>(b) * P.pool_items + item_in_rate) * P.C + c0) = pv;
+  }
+}
+
 template <bool kSmem>
 __device__ __forceinline__ void aspp_dw_dispatch(const AsppDwParams& P, int b, int chunk, int it, int lane, uint32_t slab,
                                                  const float* s_w, const float* s_shift) {
@@ -198,6 +272,8 @@ __device__ __forceinline__ void aspp_dw_dispatch(const AsppDwParams& P, int b, i
     case 1: aspp_dw_phase_item<3, kSmem>(P, b, chunk, ri, pi, pj, seg, local, lane, slab, s_w, s_shift); break;
     case 2: aspp_dw_phase_item<4, kSmem>(P, b, chunk, ri, pi, pj, seg, local, lane, slab, s_w, s_shift); break;
     case 3: aspp_dw_phase_item<6, kSmem>(P, b, chunk, ri, pi, pj, seg, local, lane, slab, s_w, s_shift); break;
+    case 5: aspp_dw_small_item<2, 2, kSmem>(P, b, chunk, ri, pi, pj, local, lane, slab, s_w, s_shift); break;
+    case 6: aspp_dw_small_item<3, 3, kSmem>(P, b, chunk, ri, pi, pj, local, lane, slab, s_w, s_shift); break;
     default: aspp_dw_phase_item<8, kSmem>(P, b, chunk, ri, pi, pj, seg, local, lane, slab, s_w, s_shift); break;
   }
 }
@@ -335,56 +411,64 @@ struct PoolProjParams {
   float inv_count;               // 1 / (h*w)
 };
 
-// block 1024 = 256 output channels x 4 K-slices; each thread keeps 4 independent accumulators
+// block 1024 = 128 output-channel pairs x 8 K-slices.  There is no L1 to speak of next to the big GEMM CTAs and the
+// weights come from L2, so every thread keeps 16 independent 32-bit loads in flight (two adjacent output channels each).
 __global__ void __launch_bounds__(1024) pool_proj_kernel(const PoolProjParams P) {
-  extern __shared__ float s_mean[];  // [C] + [256] + [4][256]
+  extern __shared__ float s_mean[];  // [C] + [256] + [8][256]
   float* s_b4 = s_mean + P.C;
   float* s_part = s_b4 + 256;
-  const int b = blockIdx.x, n = threadIdx.x & 255, ks = threadIdx.x >> 8;
+  const int b = blockIdx.x, np = threadIdx.x & 127, ks = threadIdx.x >> 7;   // np: channel pair, ks: K slice 0..7
   for (int c = threadIdx.x; c < P.C; c += 1024) {
     float s = 0.0f;
     for (int q = 0; q < P.nbands; ++q) s += P.pool_partial[(static_cast<size_t>(b) * P.nbands + q) * P.C + c];
     s_mean[c] = s * P.inv_count;
   }
   __syncthreads();
-  {
-    const int kq = (P.C + 3) / 4, k0 = ks * kq, k1 = min(P.C, k0 + kq);
-    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+  auto gemv = [&](const float* vec, const __nv_bfloat16* w, int K) {   // partial dot products of this K slice -> s_part[ks][2np..]
+    const int kq = (K + 7) / 8, k0 = ks * kq, k1 = min(K, k0 + kq);
+    const unsigned int* wp = reinterpret_cast<const unsigned int*>(w) + np;   // row k: 128 pairs
+    float a0 = 0.0f, a1 = 0.0f, c0 = 0.0f, c1 = 0.0f;
     int k = k0;
-    for (; k + 3 < k1; k += 4) {
-      a0 = fmaf(s_mean[k + 0], __bfloat162float(P.w_ip[static_cast<size_t>(k + 0) * 256 + n]), a0);
-      a1 = fmaf(s_mean[k + 1], __bfloat162float(P.w_ip[static_cast<size_t>(k + 1) * 256 + n]), a1);
-      a2 = fmaf(s_mean[k + 2], __bfloat162float(P.w_ip[static_cast<size_t>(k + 2) * 256 + n]), a2);
-      a3 = fmaf(s_mean[k + 3], __bfloat162float(P.w_ip[static_cast<size_t>(k + 3) * 256 + n]), a3);
+    for (; k + 15 < k1; k += 16) {
+      uint32_t v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] = __ldg(wp + static_cast<size_t>(k + u) * 128);
+#pragma unroll
+      for (int u = 0; u < 16; u += 2) {
+        a0 = fmaf(vec[k + u], bf16_lo(v[u]), a0);
+        a1 = fmaf(vec[k + u], bf16_hi(v[u]), a1);
+        c0 = fmaf(vec[k + u + 1], bf16_lo(v[u + 1]), c0);
+        c1 = fmaf(vec[k + u + 1], bf16_hi(v[u + 1]), c1);
+      }
     }
-    for (; k < k1; ++k) a0 = fmaf(s_mean[k], __bfloat162float(P.w_ip[static_cast<size_t>(k) * 256 + n]), a0);
-    s_part[ks * 256 + n] = (a0 + a1) + (a2 + a3);
-  }
+    for (; k < k1; ++k) {
+      const uint32_t v = __ldg(wp + static_cast<size_t>(k) * 128);
+      a0 = fmaf(vec[k], bf16_lo(v), a0);
+      a1 = fmaf(vec[k], bf16_hi(v), a1);
+    }
+    s_part[ks * 256 + 2 * np] = a0 + c0;
+    s_part[ks * 256 + 2 * np + 1] = a1 + c1;
+  };
+  gemv(s_mean, P.w_ip, P.C);
   __syncthreads();
-  if (ks == 0) {
-    const float acc = (s_part[n] + s_part[256 + n]) + (s_part[512 + n] + s_part[768 + n]);
+  if (threadIdx.x < 256) {
+    const int n = threadIdx.x;
+    float acc = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc += s_part[q * 256 + n];
     float v = fmaxf(fmaf(acc, P.ip_scale[n], P.ip_shift[n]), 0.0f);
     v = __bfloat162float(__float2bfloat16_rn(v));  // activation rounding point, as every other branch
     s_b4[n] = v;
     P.b4_out[static_cast<size_t>(b) * 256 + n] = v;
   }
   __syncthreads();
-  {
-    const int k0 = ks * 64;
-    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-#pragma unroll 4
-    for (int k = k0; k < k0 + 64; k += 4) {
-      a0 = fmaf(s_b4[k + 0], __bfloat162float(P.w_proj4[static_cast<size_t>(k + 0) * 256 + n]), a0);
-      a1 = fmaf(s_b4[k + 1], __bfloat162float(P.w_proj4[static_cast<size_t>(k + 1) * 256 + n]), a1);
-      a2 = fmaf(s_b4[k + 2], __bfloat162float(P.w_proj4[static_cast<size_t>(k + 2) * 256 + n]), a2);
-      a3 = fmaf(s_b4[k + 3], __bfloat162float(P.w_proj4[static_cast<size_t>(k + 3) * 256 + n]), a3);
-    }
-    __syncthreads();   // s_part reuse
-    s_part[ks * 256 + n] = (a0 + a1) + (a2 + a3);
-  }
+  gemv(s_b4, P.w_proj4, 256);
   __syncthreads();
-  if (ks == 0) {
-    const float acc2 = (s_part[n] + s_part[256 + n]) + (s_part[512 + n] + s_part[768 + n]);
+  if (threadIdx.x < 256) {
+    const int n = threadIdx.x;
+    float acc2 = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc2 += s_part[q * 256 + n];
     P.img_shift[static_cast<size_t>(b) * 256 + n] = fmaf(acc2, P.proj_scale[n], P.proj_shift[n]);
   }
 }
