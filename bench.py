@@ -133,6 +133,7 @@ def cpu_reference_throughput(budget_s=20.0, batch=2, max_iters=20):
     not installable here: 'restatement, not TensorFlow'. Bounded sample of the same workload."""
     import torch
     from oracle import head_ref as R
+    torch.set_num_threads(max(1, os.cpu_count() or 1))      # torchrun pins OMP_NUM_THREADS=1: the CPU arm uses all host cores
     cfg = R.HeadConfig(B=batch, H=CFG['H'], W=CFG['W'], OS=CFG['OS'], Cin=CFG['Cin'], Cskip=CFG['Cskip'], NC=CFG['NC'])
     W = R.make_weights(cfg, 1234)
     feat, skip = R.make_inputs(cfg, 1236)

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -20,6 +21,7 @@
 #include "dwpw_gemm.cuh"
 #include "mem_kernels.cuh"
 #include "pw_gemm.cuh"
+#include "pw_gemm2.cuh"
 
 using namespace dlv3p;
 
@@ -184,6 +186,20 @@ std::vector<float> pack_dw(const float* w_hwc, const float* scale, int C, int Cp
 }
 
 int pick_bn(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : 256); }
+// weight tiles travel in TMA boxes of at most 128 rows (a CTA pair loads one box each, a single CTA two)
+uint32_t w_box_rows(int npad) { return static_cast<uint32_t>(npad > 128 ? 128 : npad); }
+
+// (rate, phase, segment) work items of the ASPP depthwise kernels, heaviest rate first, packed for the device
+std::vector<uint32_t> build_aspp_items(const AsppDwParams& A) {
+  std::vector<uint32_t> t;
+  for (int ri = 0; ri < A.nrates; ++ri) {
+    const int r = A.rates[ri];
+    for (int ph = 0; ph < r * r; ++ph)
+      for (int seg = 0; seg < A.nseg[ri]; ++seg)
+        t.push_back((static_cast<uint32_t>(ri) << 28) | (static_cast<uint32_t>(seg) << 20) | (static_cast<uint32_t>(ph / r) << 10) | static_cast<uint32_t>(ph % r));
+  }
+  return t;
+}
 
 }  // namespace
 
@@ -207,7 +223,37 @@ cudaError_t launch_pw_t(const PwLaunch& L, int num_sms, cudaStream_t st) {
   pw_gemm_kernel<BN><<<grid, kPwThreads, PwCfg<BN>::kSmemBytes, st>>>(L);
   return cudaGetLastError();
 }
+// CTA-pair (cta_group::2) variant for the 256-wide bf16 GEMMs; DLV3P_NO_CTA2=1 selects the 1-CTA kernel (A/B runs)
+cudaError_t launch_pw2(const PwLaunch& L, int num_sms, cudaStream_t st) {
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(pw_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPw2SmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_done[dev & 63] = true;
+  }
+  const int pairs = (L.num_tiles + 1) / 2 * L.num_problems;
+  int grid = 2 * pairs < num_sms ? 2 * pairs : (num_sms & ~1);
+  pw_gemm2_kernel<<<grid, kPwThreads, kPw2SmemBytes, st>>>(L);
+  return cudaGetLastError();
+}
+bool use_cta2() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DLV3P_NO_CTA2");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 cudaError_t launch_pw(int BN, const PwLaunch& L, int num_sms, cudaStream_t st) {
+  if (BN == 256 && use_cta2() && !(L.debug & 8)) {
+    bool all_bf16 = true;
+    for (int i = 0; i < L.num_problems; ++i)   // short-K problems are store bound: the pair brings nothing there (measured)
+      all_bf16 = all_bf16 && L.prob[i].epi != kEpiPlanarF32 && L.prob[i].N == 256 && L.prob[i].K >= 512;
+    if (all_bf16) return launch_pw2(L, num_sms, st);
+  }
   switch (BN) {
     case 32: return launch_pw_t<32>(L, num_sms, st);
     case 64: return launch_pw_t<64>(L, num_sms, st);
@@ -325,6 +371,7 @@ struct dlv3p_ctx {
   PwWeights pw_aspp[4], pw_proj, pw_fp0, pw_dec0, pw_dec1, pw_cls;
   DwWeights dw_dec0, dw_dec1;
   float *aspp_dw_w = nullptr, *aspp_dw_shift = nullptr;    // [3][9][Cin], [3][Cin]
+  uint32_t* aspp_items = nullptr;                          // packed work-item table of the ASPP depthwise kernels
   uint16_t *w_ip = nullptr, *w_proj4 = nullptr;            // [Cin][256], [256][256] bf16
   float *ip_scale = nullptr, *ip_shift = nullptr;
 
@@ -739,6 +786,7 @@ int dlv3p_finalize_weights(dlv3p_ctx* c) {
         if ((r = make_pw(c, &c->pw_aspp[i], W(c, p + "_pointwise", "kernel"), Cin, 256, 0, Cin, fp.scale, fp.shift))) return r;
       }
       if ((r = upload(c, &c->aspp_dw_w, dw))) return r;
+      if ((r = upload(c, &c->aspp_items, build_aspp_items(c->aspp_plan)))) return r;
       if ((r = upload(c, &c->aspp_dw_shift, dsh))) return r;
     }
     {
@@ -784,8 +832,8 @@ int dlv3p_finalize_weights(dlv3p_ctx* c) {
   bool ok = true;
   if (c->st_aspp) {
     for (int i = 0; i < (c->lite ? 1 : 4); ++i)
-      ok = ok && enc2(TM_W_ASPP0 + i, c->pw_aspp[i].w, c->pw_aspp[i].Npad, c->pw_aspp[i].Kpad, c->pw_aspp[i].Kpad, c->pw_aspp[i].Npad);
-    ok = ok && enc2(TM_W_PROJ, c->pw_proj.w, 256, c->pw_proj.Kpad, c->pw_proj.Kpad, 256);
+      ok = ok && enc2(TM_W_ASPP0 + i, c->pw_aspp[i].w, c->pw_aspp[i].Npad, c->pw_aspp[i].Kpad, c->pw_aspp[i].Kpad, w_box_rows(c->pw_aspp[i].Npad));
+    ok = ok && enc2(TM_W_PROJ, c->pw_proj.w, 256, c->pw_proj.Kpad, c->pw_proj.Kpad, w_box_rows(256));
     if (!c->lite)
       for (int i = 0; i < 3; ++i)
         ok = ok && enc2(TM_DW1 + i, c->dw_out + static_cast<size_t>(i) * ceil_div(g.Cin, 64) * c->M1 * 64, static_cast<uint64_t>(ceil_div(g.Cin, 64)) * c->M1, 64, 64, 128);
@@ -800,9 +848,9 @@ int dlv3p_finalize_weights(dlv3p_ctx* c) {
     }
   }
   if (c->st_dec) {
-    ok = ok && enc2(TM_W_FP0, c->pw_fp0.w, c->pw_fp0.Npad, c->pw_fp0.Kpad, c->pw_fp0.Kpad, c->pw_fp0.Npad);
-    ok = ok && enc2(TM_W_DEC0, c->pw_dec0.w, 256, c->pw_dec0.Kpad, c->pw_dec0.Kpad, 256);
-    ok = ok && enc2(TM_W_DEC1, c->pw_dec1.w, 256, c->pw_dec1.Kpad, c->pw_dec1.Kpad, 256);
+    ok = ok && enc2(TM_W_FP0, c->pw_fp0.w, c->pw_fp0.Npad, c->pw_fp0.Kpad, c->pw_fp0.Kpad, w_box_rows(c->pw_fp0.Npad));
+    ok = ok && enc2(TM_W_DEC0, c->pw_dec0.w, 256, c->pw_dec0.Kpad, c->pw_dec0.Kpad, w_box_rows(256));
+    ok = ok && enc2(TM_W_DEC1, c->pw_dec1.w, 256, c->pw_dec1.Kpad, c->pw_dec1.Kpad, w_box_rows(256));
     ok = ok && encode_2d_out(&c->h_tm[TM_O_FP0], c->dec_in + 256, c->M2, 48, 304, &terr);
     ok = ok && encode_2d_out(&c->h_tm[TM_O_DEC0], c->dec0, c->M2, 256, 256, &terr);
     ok = ok && encode_2d_out(&c->h_tm[TM_O_DEC1], c->dec1, c->M2, 256, 256, &terr);
@@ -821,7 +869,7 @@ int dlv3p_finalize_weights(dlv3p_ctx* c) {
     }
   }
   if (c->st_tail) {
-    ok = ok && enc2(TM_W_CLS, c->pw_cls.w, c->pw_cls.Npad, c->pw_cls.Kpad, c->pw_cls.Kpad, c->pw_cls.Npad);
+    ok = ok && enc2(TM_W_CLS, c->pw_cls.w, c->pw_cls.Npad, c->pw_cls.Kpad, c->pw_cls.Kpad, w_box_rows(c->pw_cls.Npad));
     const __nv_bfloat16* cls_in = c->st_dec ? c->dec1 : (c->st_aspp ? c->aspp_out : c->feat_bf16);
     if (cls_in) ok = ok && enc2(TM_CLS_IN, cls_in, c->Mc, 256, 256, 128);
   }
@@ -962,7 +1010,7 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
     } else if (L.begin("aspp_dw_pool")) {
       AsppDwParams P = c->aspp_plan;
       P.x = feat; P.w = c->aspp_dw_w; P.shift = c->aspp_dw_shift; P.out = c->dw_out; P.pool_partial = c->pool_partial;
-      P.tmap_slab = &c->d_tm[TM_FEAT_SLAB];
+      P.tmap_slab = &c->d_tm[TM_FEAT_SLAB]; P.item_table = c->aspp_items;
       if (c->aspp_slab) {
         cudaError_t e = cudaFuncSetAttribute(aspp_dw_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->aspp_slab_smem));
         const int slabs = g.B * P.nchunks;
@@ -1261,7 +1309,7 @@ int dlv3p_op_pointwise(int device, const void* a_bf16, int64_t M, int K, int N, 
   float* dt = tmp.put(t);
   std::string terr;
   std::vector<CUtensorMap> tm(3);
-  if (!encode_2d_sw128(&tm[0], a_bf16, M, K, K, 128, &terr) || !encode_2d_sw128(&tm[1], dw, BN, Kpad, Kpad, BN, &terr) ||
+  if (!encode_2d_sw128(&tm[0], a_bf16, M, K, K, 128, &terr) || !encode_2d_sw128(&tm[1], dw, BN, Kpad, Kpad, w_box_rows(BN), &terr) ||
       !encode_2d_out(&tm[2], out_bf16, M, N, N, &terr)) return fail(nullptr, DLV3P_ERR_CUDA, terr);
   CUtensorMap* dtm = tmp.put(tm);
   if (!dw || !ds || !dt || !dtm) return fail(nullptr, DLV3P_ERR_NOMEM, "op_pointwise: cudaMalloc failed");
@@ -1318,7 +1366,7 @@ int dlv3p_op_sepconv(int device, const void* x_bf16, int B, int H, int W_, int C
   float* dt = tmp.put(t);
   std::string terr;
   std::vector<CUtensorMap> tm(3);
-  if (!encode_4d_halo(&tm[0], x_bf16, B, H, W_, C, C, kDwHaloW, kDwHaloH, &terr) || !encode_2d_sw128(&tm[1], dpw, 256, Cpad, Cpad, 256, &terr) ||
+  if (!encode_4d_halo(&tm[0], x_bf16, B, H, W_, C, C, kDwHaloW, kDwHaloH, &terr) || !encode_2d_sw128(&tm[1], dpw, 256, Cpad, Cpad, w_box_rows(256), &terr) ||
       !encode_4d_out(&tm[2], out_bf16, B, H, W_, 256, &terr))
     return fail(nullptr, DLV3P_ERR_CUDA, terr);
   CUtensorMap* dtm = tmp.put(tm);
@@ -1411,7 +1459,7 @@ int dlv3p_op_time(int device, int op, const int64_t* d, int ndims, int iters, in
     float* t = tmp.put(std::vector<float>(BN, 0.0f));
     if (N % 8) return fail(nullptr, DLV3P_ERR_INVALID, "op_time pointwise: N % 8");
     std::vector<CUtensorMap> tm(3);
-    if (!encode_2d_sw128(&tm[0], a, M, K, K, 128, &terr) || !encode_2d_sw128(&tm[1], w, BN, Kpad, Kpad, BN, &terr) ||
+    if (!encode_2d_sw128(&tm[0], a, M, K, K, 128, &terr) || !encode_2d_sw128(&tm[1], w, BN, Kpad, Kpad, w_box_rows(BN), &terr) ||
         !encode_2d_out(&tm[2], o, M, N, N, &terr)) return fail(nullptr, DLV3P_ERR_CUDA, terr);
     CUtensorMap* dtm = tmp.put(tm);
     PwLaunch PL{};
@@ -1431,7 +1479,7 @@ int dlv3p_op_time(int device, int op, const int64_t* d, int ndims, int iters, in
     float* s = tmp.put(std::vector<float>(256, 1.0f));
     float* t = tmp.put(std::vector<float>(256, 0.0f));
     std::vector<CUtensorMap> tm(3);
-    if (!encode_4d_halo(&tm[0], x, B, H, W_, C, C, kDwHaloW, kDwHaloH, &terr) || !encode_2d_sw128(&tm[1], w, 256, Cpad, Cpad, 256, &terr) ||
+    if (!encode_4d_halo(&tm[0], x, B, H, W_, C, C, kDwHaloW, kDwHaloH, &terr) || !encode_2d_sw128(&tm[1], w, 256, Cpad, Cpad, w_box_rows(256), &terr) ||
         !encode_4d_out(&tm[2], o, B, H, W_, 256, &terr)) return fail(nullptr, DLV3P_ERR_CUDA, terr);
     CUtensorMap* dtm = tmp.put(tm);
     DwPwParams P{};
@@ -1493,6 +1541,7 @@ int dlv3p_op_time(int device, int op, const int64_t* d, int ndims, int iters, in
     std::vector<CUtensorMap> tm(1);
     if (!encode_2d_slab(&tm[0], P.x, static_cast<uint64_t>(P.B) * P.h * P.w_, P.C, P.C, &terr)) return fail(nullptr, DLV3P_ERR_CUDA, terr);
     P.tmap_slab = tmp.put(tm);
+    P.item_table = tmp.put(build_aspp_items(P));
     const size_t smem = static_cast<size_t>(ceil_div(P.h * P.w_, 256)) * 32768 + (27 * 64 + 3 * 64 + 16 * 64) * sizeof(float) + 16;
     if (smem > 220 * 1024) return fail(nullptr, DLV3P_ERR_UNSUPPORTED, "op_time aspp_dw: map too large for the slab kernel");
     cudaFuncSetAttribute(aspp_dw_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

@@ -32,7 +32,7 @@ constexpr int kDwBN = 256;
 
 struct DwPwParams {
   const CUtensorMap* tmap_x;  // 4D {C, W, H, B} bf16, box {64, 18, 10, 1}, no swizzle
-  const CUtensorMap* tmap_w;  // 2D [256, KB*64] bf16 K-major, box {64, 256}, SWIZZLE_128B
+  const CUtensorMap* tmap_w;  // 2D [256, KB*64] bf16 K-major, box {64, 128}, SWIZZLE_128B
   const float* dw_w;          // [9][KB*64] fp32 depthwise taps with the BN scale folded in, zero padded
   const float* dw_shift;      // [KB*64]    fp32 depthwise BN shift, zero padded
   const float* scale;         // [256] pointwise BN scale
@@ -131,7 +131,10 @@ __global__ void __launch_bounds__(kDwThreads, 1) dwpw_gemm_kernel(const __grid_c
     if (elect_one()) {
       mbar_arrive_expect_tx(w_full, Cfg::kWBytes);
       for (int kb = 0; kb < KB; ++kb)
+{
         tma_load_2d(smem_w + kb * kDwWBlockBytes, P.tmap_w, w_full, kb * 64, 0, kEvictLast);
+        tma_load_2d(smem_w + kb * kDwWBlockBytes + 128 * 128, P.tmap_w, w_full, kb * 64, 128, kEvictLast);
+      }
       uint32_t c = 0;
       for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
         const int b = tile / tiles_per_img;

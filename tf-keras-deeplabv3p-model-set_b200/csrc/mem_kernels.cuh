@@ -69,6 +69,7 @@ struct AsppDwParams {
   long long total_warps;    // B * item_off[nrates] * nchunks
   int debug;                // benchmark aid: bit0 skip output stores, bit1 skip the tap math
   const void* tmap_slab;    // slab kernel: 2D [B*h*w, C] bf16 view of x, box {64, 256}, no swizzle (device memory)
+  const uint32_t* item_table;  // [items per image] packed (ri << 28 | seg << 20 | pi << 10 | pj): no div/mod per item (device memory)
 };
 
 __device__ __forceinline__ unsigned long long f32x2_from_bf16x2(uint32_t v) {
@@ -257,16 +258,10 @@ __device__ __forceinline__ void aspp_dw_small_item(const AsppDwParams& P, int b,
 template <bool kSmem>
 __device__ __forceinline__ void aspp_dw_dispatch(const AsppDwParams& P, int b, int chunk, int it, int lane, uint32_t slab,
                                                  const float* s_w, const float* s_shift) {
-  int ri = 0;
-  if (P.nrates > 1 && it >= P.item_off[1]) ri = 1;
-  if (P.nrates > 2 && it >= P.item_off[2]) ri = 2;
+  const uint32_t e = __ldg(P.item_table + it);
+  const int ri = static_cast<int>(e >> 28), seg = static_cast<int>((e >> 20) & 0xFF);
+  const int pi = static_cast<int>((e >> 10) & 0x3FF), pj = static_cast<int>(e & 0x3FF);
   const int local = it - P.item_off[ri];
-  const int nseg = P.nseg[ri];
-  const int seg = local % nseg;
-  const int ph = local / nseg;
-  const int r = P.rates[ri];
-  const int pj = ph % r;
-  const int pi = ph / r;
   switch (P.ts_sel[ri]) {
     case 0: aspp_dw_phase_item<2, kSmem>(P, b, chunk, ri, pi, pj, seg, local, lane, slab, s_w, s_shift); break;
     case 1: aspp_dw_phase_item<3, kSmem>(P, b, chunk, ri, pi, pj, seg, local, lane, slab, s_w, s_shift); break;
@@ -679,19 +674,19 @@ __global__ void __launch_bounds__(256) resize_argmax_x4_kernel(const ArgmaxParam
       const float tr = __ldg(lp + static_cast<size_t>(y0) * P.wi + x1);
       const float bl = __ldg(lp + static_cast<size_t>(y1) * P.wi + x0);
       const float br = __ldg(lp + static_cast<size_t>(y1) * P.wi + x1);
-      float top[4], bot[4];
+      // a + (b - a) * t with the differences hoisted: the very same rounded operations as lerp_nofma, fewer of them
+      const float dtop = __fsub_rn(tr, tl), dbot = __fsub_rn(br, bl);
 #pragma unroll
       for (int dx = 0; dx < 4; ++dx) {
-        top[dx] = lerp_nofma(tl, tr, tx[dx]);
-        bot[dx] = lerp_nofma(bl, br, tx[dx]);
-      }
+        const float top = __fadd_rn(tl, __fmul_rn(dtop, tx[dx]));
+        const float bot = __fadd_rn(bl, __fmul_rn(dbot, tx[dx]));
+        const float dv = __fsub_rn(bot, top);
 #pragma unroll
-      for (int dy = 0; dy < 4; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 4; ++dx) {
-          const float v = lerp_nofma(top[dx], bot[dx], ty[dy]);
+        for (int dy = 0; dy < 4; ++dy) {
+          const float v = __fadd_rn(top, __fmul_rn(dv, ty[dy]));
           if (v > best[dy * 4 + dx]) { best[dy * 4 + dx] = v; arg[dy * 4 + dx] = c; }
         }
+      }
     }
     uint8_t* ob = P.labels + static_cast<size_t>(b) * P.ho * P.wo;
 #pragma unroll

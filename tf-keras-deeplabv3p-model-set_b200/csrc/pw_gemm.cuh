@@ -35,7 +35,7 @@ enum PwEpilogue : int {
 
 struct PwProblem {
   const CUtensorMap* tmap_a;  // [M, K] bf16, box {64, 128}, SWIZZLE_128B   (device memory)
-  const CUtensorMap* tmap_w;  // [Npad, Kpad] bf16, box {64, BN}, SWIZZLE_128B
+  const CUtensorMap* tmap_w;  // [Npad, Kpad] bf16, box {64, min(BN, 128)}, SWIZZLE_128B
   const CUtensorMap* tmap_out;  // bf16 modes, BN >= 64: [M, N] view of the output (row stride ldo), box {64, 32}, SWIZZLE_128B
   const float* scale;         // [BN]
   const float* shift;         // [BN]
@@ -129,6 +129,8 @@ __global__ void __launch_bounds__(kPwThreads, 1) pw_gemm_kernel(const __grid_con
           else
             tma_load_2d(smem_a + stage * (kPwBM * 128), P.tmap_a, &full_bar[stage], kb * kPwBK, tile * kPwBM, kEvictFirst);
           tma_load_2d(smem_b + stage * (BN * 128), P.tmap_w, &full_bar[stage], kb * kPwBK, 0, kEvictLast);
+          if constexpr (BN > 128)   // weight boxes hold 128 rows (shared with the CTA-pair kernel)
+            tma_load_2d(smem_b + stage * (BN * 128) + 128 * 128, P.tmap_w, &full_bar[stage], kb * kPwBK, 128, kEvictLast);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }

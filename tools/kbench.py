@@ -33,7 +33,7 @@ def main():
     sel = sys.argv[1:] or ['pw', 'sep', 'mem', 'aspp']
     if 'pw' in sel:
         for (M, K, N) in [(32768, 2048, 256), (32768, 1024, 256), (524288, 256, 256), (524288, 304, 256), (524288, 256, 48)]:
-            for fl in (0, 1):
+            for fl in (0, 8):
                 rec('pointwise M=%d K=%d N=%d' % (M, K, N), 0, [M, K, N], fl, flop=2.0 * M * K * N, byts=2.0 * M * (K + N))
     if 'sep' in sel:
         for C in (256, 304):
