@@ -1,0 +1,177 @@
+// aspp_dw_fast.cuh — geometry-specialised ASPP depthwise kernel for small feature maps (the whole h x w map of a
+// 32-channel group fits in shared memory twice per SM).
+//
+// Replaces, in ONE pass over x: the three `aspp{1,2,3}_depthwise` dilated 3x3 convs + `_depthwise_BN` + ReLU
+// (reference deeplabv3p/models/layers.py:146-153 -> :100-104) and the AveragePooling2D of the image-pooling branch (:132).
+//
+// A 3x3 conv with dilation R only couples pixels of equal phase (i mod R, j mod R): it is R*R independent dense 3x3 convs
+// on phase images of at most ceil(H/R) x ceil(W/R) pixels.  With H, W and the rates known at compile time a phase image
+// lives entirely in registers: every input is read from shared memory ONCE per rate, every address is an immediate
+// offset from one base register, border taps are resolved at compile time (zero padding = absent FMAs).
+//
+//   CTA            one (image, 32-channel group) slab [H*W][32] bf16 = 64 B per pixel, staged by TMA; 2-3 CTAs per SM so
+//                  one CTA's HBM load overlaps the others' arithmetic
+//   half-warp      one phase image: 16 lanes x bf16x2 = the 32 channels; the two halves of a warp take phases whose
+//                  column parity differs, so their 64-byte rows never share a shared-memory bank
+//   warp           fetches work units (heaviest rate first) from a shared-memory counter
+#pragma once
+
+#include "mem_kernels.cuh"
+
+namespace dlv3p {
+
+constexpr int kAsppFastThreads = 256;
+
+__device__ __forceinline__ uint32_t f32x2_to_bf16x2_relu(unsigned long long v) {
+  uint32_t lo, hi, r;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return r;
+}
+
+template <int H, int W, int R>
+__device__ __forceinline__ void aspp_fast_item(const uint8_t* slab_lane, uint8_t* out_lane, int pi, int pj,
+                                               const unsigned long long (&wt)[9], unsigned long long sh, bool store) {
+  constexpr int NA = (H + R - 1) / R, NT = (W + R - 1) / R;
+  const bool last_row = pi + (NA - 1) * R < H;   // does the last row / column of the phase image exist?
+  const bool last_col = pj + (NT - 1) * R < W;
+  const uint8_t* src = slab_lane + (pi * W + pj) * 64;
+  uint8_t* dst = out_lane + (pi * W + pj) * 128;
+  unsigned long long x[NA][NT];
+#pragma unroll
+  for (int a = 0; a < NA; ++a)
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const bool ok = (a < NA - 1 || last_row) && (t < NT - 1 || last_col);
+      uint32_t v = 0u;
+      if (ok) v = *reinterpret_cast<const uint32_t*>(src + (a * R * W + t * R) * 64);
+      x[a][t] = f32x2_from_bf16x2(v);
+    }
+#pragma unroll
+  for (int a = 0; a < NA; ++a)
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      unsigned long long acc = sh;
+#pragma unroll
+      for (int u = 0; u < 3; ++u)
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+          const int aa = a + u - 1, tt = t + v - 1;
+          if (aa >= 0 && aa < NA && tt >= 0 && tt < NT) ffma2_acc(acc, wt[u * 3 + v], x[aa][tt]);   // compile-time
+        }
+      const bool ok = (a < NA - 1 || last_row) && (t < NT - 1 || last_col);
+      if (ok && store) *reinterpret_cast<uint32_t*>(dst + (a * R * W + t * R) * 128) = f32x2_to_bf16x2_relu(acc);
+    }
+}
+
+template <int H, int W, int R0, int R1, int R2>
+struct AsppFastCfg {
+  static_assert(R0 % 2 == 0 && R1 % 2 == 0 && R2 % 2 == 0 && W % 2 == 0, "phase pairing needs even rates and width");
+  static constexpr int kPix = H * W;
+  static constexpr int kBoxes = (kPix + 255) / 256;                 // TMA boxes of 256 pixels x 32 channels (16 KB)
+  static constexpr int kItems0 = R0 * (R0 / 2), kItems1 = R1 * (R1 / 2), kItems2 = R2 * (R2 / 2);   // warp items (phase pairs)
+  static constexpr int kBatch1 = 2, kBatch2 = 4;                    // light items are fetched in batches
+  static constexpr int kUnits0 = kItems0, kUnits1 = (kItems1 + kBatch1 - 1) / kBatch1, kUnits2 = (kItems2 + kBatch2 - 1) / kBatch2;
+  static constexpr int kUnits = kUnits0 + kUnits1 + kUnits2;
+  static constexpr int kSmemBytes = kBoxes * 16384 + (27 * 32 + 3 * 32 + 8 * 32) * 4 + 32;
+};
+
+// grid = B * (C / 32) CTAs, block 256.  P.tmap_slab: 2D [B*H*W, C] bf16 view of x, box {32, 256}, no swizzle.
+template <int H, int W, int R0, int R1, int R2>
+__global__ void __launch_bounds__(kAsppFastThreads, 3) aspp_dw_fast_kernel(const __grid_constant__ AsppDwParams P) {
+  using Cfg = AsppFastCfg<H, W, R0, R1, R2>;
+  extern __shared__ __align__(128) uint8_t fast_smem[];
+  uint8_t* s_slab = fast_smem;
+  float* s_w = reinterpret_cast<float*>(s_slab + Cfg::kBoxes * 16384);   // [3][9][32]
+  float* s_shift = s_w + 27 * 32;                                         // [3][32]
+  float* s_red = s_shift + 3 * 32;                                        // [8][32]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_red + 8 * 32);
+  int* s_next = reinterpret_cast<int*>(s_bar + 1);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int hw = lane >> 4, l16 = lane & 15;
+  const int ngroups = P.C >> 5;
+  const int b = blockIdx.x / ngroups, grp = blockIdx.x - b * ngroups;   // 32-channel group
+  if (tid == 0) {
+    mbar_init(s_bar, 1);
+    fence_barrier_init();
+    *s_next = 0;
+    mbar_arrive_expect_tx(s_bar, static_cast<uint32_t>(Cfg::kBoxes) * 16384u);
+    for (int q = 0; q < Cfg::kBoxes; ++q)
+      tma_load_2d(s_slab + q * 16384, P.tmap_slab, s_bar, grp * 32, b * Cfg::kPix + q * 256, kEvictFirst);
+  }
+  for (int i = tid; i < 27 * 32; i += kAsppFastThreads) s_w[i] = __ldg(P.w + static_cast<size_t>(i >> 5) * P.C + grp * 32 + (i & 31));
+  if (tid < 3 * 32) s_shift[tid] = __ldg(P.shift + static_cast<size_t>(tid >> 5) * P.C + grp * 32 + (tid & 31));
+  __syncthreads();
+  mbar_wait(s_bar, 0);
+
+  const uint8_t* slab_lane = s_slab + l16 * 4;
+  // image-pooling partial sums: warp = 1/8 of the pixels, half-warp = every other pixel
+  {
+    float sx = 0.0f, sy = 0.0f;
+    constexpr int kPer = (Cfg::kPix + 7) / 8;
+#pragma unroll 8
+    for (int k = hw; k < kPer; k += 2) {
+      const int p = warp * kPer + k;
+      if (p < Cfg::kPix) {
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(slab_lane + p * 64);
+        sx += bf16_lo(v);
+        sy += bf16_hi(v);
+      }
+    }
+    sx += __shfl_xor_sync(0xFFFFFFFFu, sx, 16);
+    sy += __shfl_xor_sync(0xFFFFFFFFu, sy, 16);
+    if (hw == 0) {
+      s_red[warp * 32 + l16 * 2] = sx;
+      s_red[warp * 32 + l16 * 2 + 1] = sy;
+    }
+  }
+
+  const bool store = !(P.debug & 1);
+  const size_t rate_stride = static_cast<size_t>(P.nchunks) * P.B * Cfg::kPix * 128;   // bytes per rate
+  uint8_t* out0 = reinterpret_cast<uint8_t*>(P.out) + (static_cast<size_t>(grp >> 1) * P.B + b) * Cfg::kPix * 128 + (grp & 1) * 64 + l16 * 4;
+  unsigned long long wt[9], sh = 0ull;
+  int cur = -1;
+  auto load_taps = [&](int ri) {
+    if (ri == cur) return;
+    cur = ri;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float2 v = *reinterpret_cast<const float2*>(s_w + (ri * 9 + t) * 32 + l16 * 2);
+      wt[t] = (static_cast<unsigned long long>(__float_as_uint(v.y)) << 32) | __float_as_uint(v.x);
+    }
+    const float2 s = *reinterpret_cast<const float2*>(s_shift + ri * 32 + l16 * 2);
+    sh = (static_cast<unsigned long long>(__float_as_uint(s.y)) << 32) | __float_as_uint(s.x);
+  };
+  for (;;) {
+    int u = 0;
+    if (lane == 0) u = atomicAdd(s_next, 1);
+    u = __shfl_sync(0xFFFFFFFFu, u, 0);
+    if (u >= Cfg::kUnits) break;
+    if (u < Cfg::kUnits0) {
+      load_taps(0);
+      aspp_fast_item<H, W, R0>(slab_lane, out0, u / (R0 / 2), 2 * (u % (R0 / 2)) + hw, wt, sh, store);
+    } else if (u < Cfg::kUnits0 + Cfg::kUnits1) {
+      load_taps(1);
+      const int first = (u - Cfg::kUnits0) * Cfg::kBatch1;
+#pragma unroll 1
+      for (int it = first; it < first + Cfg::kBatch1 && it < Cfg::kItems1; ++it)
+        aspp_fast_item<H, W, R1>(slab_lane, out0 + rate_stride, it / (R1 / 2), 2 * (it % (R1 / 2)) + hw, wt, sh, store);
+    } else {
+      load_taps(2);
+      const int first = (u - Cfg::kUnits0 - Cfg::kUnits1) * Cfg::kBatch2;
+#pragma unroll 1
+      for (int it = first; it < first + Cfg::kBatch2 && it < Cfg::kItems2; ++it)
+        aspp_fast_item<H, W, R2>(slab_lane, out0 + 2 * rate_stride, it / (R2 / 2), 2 * (it % (R2 / 2)) + hw, wt, sh, store);
+    }
+  }
+  __syncthreads();
+  if (tid < 32) {
+    float s = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += s_red[q * 32 + tid];
+    P.pool_partial[static_cast<size_t>(b) * P.C + grp * 32 + tid] = s;   // pool_items == 1 on this path
+  }
+}
+
+}  // namespace dlv3p

@@ -22,6 +22,7 @@
 #include "mem_kernels.cuh"
 #include "pw_gemm.cuh"
 #include "pw_gemm2.cuh"
+#include "aspp_dw_fast.cuh"
 
 using namespace dlv3p;
 
@@ -97,12 +98,12 @@ bool encode_2d_sw128(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t 
   return true;
 }
 // 2D bf16 [rows, cols] row-major, box {64, 256}, NO swizzle: pixel-major slabs [256 px][64 ch] for the ASPP depthwise kernel
-bool encode_2d_slab(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, std::string* err) {
+bool encode_2d_slab(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, std::string* err, uint32_t box_cols = 64) {
   EncodeTiledFn fn = get_encode_fn(err);
   if (!fn) return false;
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {ld * 2};
-  cuuint32_t box[2] = {64, 256};
+  cuuint32_t box[2] = {box_cols, 256};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -247,6 +248,27 @@ bool use_cta2() {
   return v == 1;
 }
 
+
+// geometry-specialised ASPP depthwise kernel (aspp_dw_fast.cuh): instantiated for the feature maps the reference's
+// 512x512 configurations produce; every other geometry runs the generic slab / phase kernels
+template <int H, int W, int R0, int R1, int R2>
+cudaError_t launch_aspp_fast_t(const AsppDwParams& P, cudaStream_t st) {
+  using Cfg = AsppFastCfg<H, W, R0, R1, R2>;
+  cudaError_t e = cudaFuncSetAttribute(aspp_dw_fast_kernel<H, W, R0, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  aspp_dw_fast_kernel<H, W, R0, R1, R2><<<P.B * (P.C / 32), kAsppFastThreads, Cfg::kSmemBytes, st>>>(P);
+  return cudaGetLastError();
+}
+bool aspp_fast_supported(const AsppDwParams& P) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("DLV3P_NO_ASPP_FAST"); off = (e && e[0] == '1') ? 1 : 0; }
+  if (off || P.nrates != 3 || P.C % 32 != 0) return false;
+  return P.h == 32 && P.w_ == 32 && P.rates[0] == 6 && P.rates[1] == 12 && P.rates[2] == 18;
+}
+cudaError_t launch_aspp_fast(const AsppDwParams& P, cudaStream_t st) {
+  return launch_aspp_fast_t<32, 32, 6, 12, 18>(P, st);
+}
+
 cudaError_t launch_pw(int BN, const PwLaunch& L, int num_sms, cudaStream_t st) {
   if (BN == 256 && use_cta2() && !(L.debug & 8)) {
     bool all_bf16 = true;
@@ -365,6 +387,7 @@ struct dlv3p_ctx {
   int nbands = 1, pix_per_band = 256;   // pooling partials: ASPP Lite bands, or rate-0 phase items of the ASPP kernel
   AsppDwParams aspp_plan{};
   bool aspp_slab = false;               // small maps: shared-memory slab kernel
+  bool aspp_fast = false;               // geometry-specialised kernel (aspp_dw_fast.cuh)
   size_t aspp_slab_smem = 0;
 
   // packed weights
@@ -664,6 +687,7 @@ int dlv3p_create(const dlv3p_config* cfg, int device, dlv3p_ctx** out) {
       }
       c->aspp_slab_smem = static_cast<size_t>(ceil_div(px, 256)) * 32768 + (27 * 64 + 3 * 64 + 16 * 64) * sizeof(float) + 16;
       c->aspp_slab = c->aspp_slab_smem <= 220 * 1024;
+      c->aspp_fast = aspp_fast_supported(A);
       A.pool_items = c->aspp_slab ? 1 : A.item_off[1];
       A.total_warps = static_cast<long long>(g.B) * A.item_off[3] * A.nchunks;
       c->nbands = A.pool_items;
@@ -843,7 +867,7 @@ int dlv3p_finalize_weights(dlv3p_ctx* c) {
     ok = ok && encode_2d_out(&c->h_tm[TM_O_PROJ], c->aspp_out, c->M1, 256, 256, &terr);
     if (c->feat_bf16) {
       ok = ok && enc2(TM_FEAT, c->feat_bf16, c->M1, g.Cin, g.Cin, 128);
-      ok = ok && encode_2d_slab(&c->h_tm[TM_FEAT_SLAB], c->feat_bf16, c->M1, g.Cin, g.Cin, &terr);
+      ok = ok && encode_2d_slab(&c->h_tm[TM_FEAT_SLAB], c->feat_bf16, c->M1, g.Cin, g.Cin, &terr, c->aspp_fast ? 32 : 64);
       c->tm_feat_ptr = c->feat_bf16;
     }
   }
@@ -979,7 +1003,7 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
     skip = static_cast<const __nv_bfloat16*>(d_skip);
     if (c->st_aspp && c->tm_feat_ptr != d_feat) {
       if (!encode_2d_sw128(&c->h_tm[TM_FEAT], feat, c->M1, g.Cin, g.Cin, 128, &terr)) return fail(c, DLV3P_ERR_CUDA, terr);
-      if (!encode_2d_slab(&c->h_tm[TM_FEAT_SLAB], feat, c->M1, g.Cin, g.Cin, &terr)) return fail(c, DLV3P_ERR_CUDA, terr);
+      if (!encode_2d_slab(&c->h_tm[TM_FEAT_SLAB], feat, c->M1, g.Cin, g.Cin, &terr, c->aspp_fast ? 32 : 64)) return fail(c, DLV3P_ERR_CUDA, terr);
       CU_TRY(c, cudaMemcpyAsync(&c->d_tm[TM_FEAT], &c->h_tm[TM_FEAT], sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
       CU_TRY(c, cudaMemcpyAsync(&c->d_tm[TM_FEAT_SLAB], &c->h_tm[TM_FEAT_SLAB], sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
       c->tm_feat_ptr = d_feat;
@@ -1011,7 +1035,10 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
       AsppDwParams P = c->aspp_plan;
       P.x = feat; P.w = c->aspp_dw_w; P.shift = c->aspp_dw_shift; P.out = c->dw_out; P.pool_partial = c->pool_partial;
       P.tmap_slab = &c->d_tm[TM_FEAT_SLAB]; P.item_table = c->aspp_items;
-      if (c->aspp_slab) {
+      if (c->aspp_fast) {
+        cudaError_t e = launch_aspp_fast(P, st);
+        (void)e;
+      } else if (c->aspp_slab) {
         cudaError_t e = cudaFuncSetAttribute(aspp_dw_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->aspp_slab_smem));
         const int slabs = g.B * P.nchunks;
         if (e == cudaSuccess) aspp_dw_slab_kernel<<<slabs < c->num_sms ? slabs : c->num_sms, kSlabThreads, c->aspp_slab_smem, st>>>(P);
@@ -1538,15 +1565,17 @@ int dlv3p_op_time(int device, int op, const int64_t* d, int ndims, int iters, in
     P.w = tmp.put(std::vector<float>(static_cast<size_t>(27) * P.C, 0.1f));
     P.shift = tmp.put(std::vector<float>(static_cast<size_t>(3) * P.C, 0.0f));
     P.pool_partial = tmp.alloc<float>(static_cast<size_t>(P.B) * P.C);
+    const bool fast = aspp_fast_supported(P) && !(flags & 8);
     std::vector<CUtensorMap> tm(1);
-    if (!encode_2d_slab(&tm[0], P.x, static_cast<uint64_t>(P.B) * P.h * P.w_, P.C, P.C, &terr)) return fail(nullptr, DLV3P_ERR_CUDA, terr);
+    if (!encode_2d_slab(&tm[0], P.x, static_cast<uint64_t>(P.B) * P.h * P.w_, P.C, P.C, &terr, fast ? 32 : 64)) return fail(nullptr, DLV3P_ERR_CUDA, terr);
     P.tmap_slab = tmp.put(tm);
     P.item_table = tmp.put(build_aspp_items(P));
     const size_t smem = static_cast<size_t>(ceil_div(P.h * P.w_, 256)) * 32768 + (27 * 64 + 3 * 64 + 16 * 64) * sizeof(float) + 16;
     if (smem > 220 * 1024) return fail(nullptr, DLV3P_ERR_UNSUPPORTED, "op_time aspp_dw: map too large for the slab kernel");
     cudaFuncSetAttribute(aspp_dw_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     const int slabs = P.B * P.nchunks;
-    rc = run([&] { aspp_dw_slab_kernel<<<slabs < sms ? slabs : sms, kSlabThreads, smem, st>>>(P); });
+    if (fast) rc = run([&] { launch_aspp_fast(P, st); });
+    else rc = run([&] { aspp_dw_slab_kernel<<<slabs < sms ? slabs : sms, kSlabThreads, smem, st>>>(P); });
   } else {
     rc = fail(nullptr, DLV3P_ERR_INVALID, "op_time: unknown op / too few dims");
   }

@@ -42,7 +42,7 @@ def main():
                 rec('sepconv B=32 128x128 C=%d' % C, 1, [32, 128, 128, C], fl, flop=2.0 * M * C * 256, byts=2.0 * M * (C + 256))
     if 'aspp' in sel:
         n = 32 * 32 * 32 * 2048 * 2.0
-        for fl in (0, 1, 2, 3):
+        for fl in (0, 1, 8, 9):
             rec('aspp_dw slab B=32 32x32 C=2048', 4, [32, 32, 32, 2048], fl, byts=4 * n)
     if 'mem' in sel:
         rec('resize x4 32x32x256 -> 128x128 (B=32)', 2, [32, 32, 32, 256, 128, 128], 0, byts=32 * (1024 * 512 + 16384 * 512.0))
