@@ -19,6 +19,7 @@
 
 #include "../../include/dlv3p.h"
 #include "dwpw_gemm.cuh"
+#include "dwpw_gemm2.cuh"
 #include "mem_kernels.cuh"
 #include "pw_gemm.cuh"
 #include "pw_gemm2.cuh"
@@ -299,12 +300,38 @@ cudaError_t launch_dwpw_t(const DwPwParams& P, int num_sms, cudaStream_t st) {
   dwpw_gemm_kernel<KB, AS, IS><<<grid, kDwThreads, DwPwCfg<KB, AS, IS>::kSmemBytes, st>>>(P);
   return cudaGetLastError();
 }
+template <int KB>
+cudaError_t launch_dwpw2_t(const DwPwParams& P, int num_sms, cudaStream_t st) {
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(dwpw_gemm2_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwPw2Cfg<KB>::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_done[dev & 63] = true;
+  }
+  const int items = (P.num_tiles + 1) / 2;
+  const int grid = 2 * items < num_sms ? 2 * items : (num_sms & ~1);
+  dwpw_gemm2_kernel<KB><<<grid, kDwThreads, DwPw2Cfg<KB>::kSmemBytes, st>>>(P);
+  return cudaGetLastError();
+}
+// CTA-pair kernel by default; debug bit 3 (or DLV3P_NO_CTA2=1) selects the 1-CTA kernel for A/B runs
 cudaError_t launch_dwpw(int KB, const DwPwParams& P, int num_sms, cudaStream_t st) {
+  if (use_cta2() && !(P.debug & 8)) {
+    switch (KB) {
+      case 1: return launch_dwpw2_t<1>(P, num_sms, st);
+      case 2: return launch_dwpw2_t<2>(P, num_sms, st);
+      case 3: return launch_dwpw2_t<3>(P, num_sms, st);
+      case 4: return launch_dwpw2_t<4>(P, num_sms, st);
+      case 5: return launch_dwpw2_t<5>(P, num_sms, st);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   switch (KB) {
     case 1: return launch_dwpw_t<1, 2, 4>(P, num_sms, st);
     case 2: return launch_dwpw_t<2, 2, 4>(P, num_sms, st);
     case 3: return launch_dwpw_t<3, 2, 2>(P, num_sms, st);
-    case 4: return (P.debug & 8) ? launch_dwpw_t<4, 1, 3>(P, num_sms, st) : launch_dwpw_t<4, 2, 2>(P, num_sms, st);
+    case 4: return launch_dwpw_t<4, 2, 2>(P, num_sms, st);
     case 5: return launch_dwpw_t<5, 1, 2>(P, num_sms, st);
     default: return cudaErrorInvalidValue;
   }
