@@ -301,7 +301,8 @@ cudaError_t launch_dwpw_t(const DwPwParams& P, int num_sms, cudaStream_t st) {
   return cudaGetLastError();
 }
 template <int KB>
-cudaError_t launch_dwpw2_t(const DwPwParams& P, int num_sms, cudaStream_t st) {
+cudaError_t launch_dwpw2_t(const DwPw2Params& P2, int num_sms, cudaStream_t st) {
+  const DwPwParams& P = P2.base;
   static bool attr_done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -312,18 +313,23 @@ cudaError_t launch_dwpw2_t(const DwPwParams& P, int num_sms, cudaStream_t st) {
   }
   const int items = (P.num_tiles + 1) / 2;
   const int grid = 2 * items < num_sms ? 2 * items : (num_sms & ~1);
-  dwpw_gemm2_kernel<KB><<<grid, kDwThreads, DwPw2Cfg<KB>::kSmemBytes, st>>>(P);
+  dwpw_gemm2_kernel<KB><<<grid, kDwThreads, DwPw2Cfg<KB>::kSmemBytes, st>>>(P2);
   return cudaGetLastError();
 }
 // CTA-pair kernel by default; debug bit 3 (or DLV3P_NO_CTA2=1) selects the 1-CTA kernel for A/B runs
-cudaError_t launch_dwpw(int KB, const DwPwParams& P, int num_sms, cudaStream_t st) {
-  if (use_cta2() && !(P.debug & 8)) {
+// h_scale / h_shift: HOST copies of the pointwise BN scale / shift (256 each) for the pair kernel's constant-bank epilogue
+cudaError_t launch_dwpw(int KB, const DwPwParams& P, const float* h_scale, const float* h_shift, int num_sms, cudaStream_t st) {
+  if (use_cta2() && !(P.debug & 8) && h_scale && h_shift) {
+    DwPw2Params P2;
+    P2.base = P;
+    std::memcpy(P2.scale_c, h_scale, sizeof(P2.scale_c));
+    std::memcpy(P2.shift_c, h_shift, sizeof(P2.shift_c));
     switch (KB) {
-      case 1: return launch_dwpw2_t<1>(P, num_sms, st);
-      case 2: return launch_dwpw2_t<2>(P, num_sms, st);
-      case 3: return launch_dwpw2_t<3>(P, num_sms, st);
-      case 4: return launch_dwpw2_t<4>(P, num_sms, st);
-      case 5: return launch_dwpw2_t<5>(P, num_sms, st);
+      case 1: return launch_dwpw2_t<1>(P2, num_sms, st);
+      case 2: return launch_dwpw2_t<2>(P2, num_sms, st);
+      case 3: return launch_dwpw2_t<3>(P2, num_sms, st);
+      case 4: return launch_dwpw2_t<4>(P2, num_sms, st);
+      case 5: return launch_dwpw2_t<5>(P2, num_sms, st);
       default: return cudaErrorInvalidValue;
     }
   }
@@ -369,6 +375,7 @@ struct PwWeights {      // device-side packed 1x1 conv
   float* scale = nullptr;
   float* shift = nullptr;
   int K = 0, N = 0, Npad = 0, Kpad = 0;
+  std::vector<float> h_scale, h_shift;   // host copies, padded to Npad (kernels that take them as parameters)
 };
 struct DwWeights {      // device-side packed depthwise conv (fused kernel / standalone)
   float* w = nullptr;      // [9][Cpad]
@@ -521,6 +528,8 @@ int make_pw(dlv3p_ctx* c, PwWeights* pw, const float* w_kn, int Ktot, int N, int
     s[i] = scale[i];
     t[i] = shift[i];
   }
+  pw->h_scale = s;
+  pw->h_shift = t;
   if ((r = upload(c, &pw->scale, s))) return r;
   return upload(c, &pw->shift, t);
 }
@@ -1160,7 +1169,7 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
         P.dw_w = s.dw->w; P.dw_shift = s.dw->shift; P.scale = s.pw->scale; P.shift = s.pw->shift; P.out = s.out;
         P.tmap_out = &c->d_tm[s.tm_o == TM_O_DEC0 ? TM_O4_DEC0 : TM_O4_DEC1];
         P.B = g.B; P.H = c->hs; P.W = c->ws; P.tiles_x = tiles_x; P.tiles_y = tiles_y; P.num_tiles = g.B * tiles_x * tiles_y;
-        L.end(s.name, launch_dwpw(s.dw->Cpad / 64, P, c->num_sms, st));
+        L.end(s.name, launch_dwpw(s.dw->Cpad / 64, P, s.pw->h_scale.data(), s.pw->h_shift.data(), c->num_sms, st));
       }
     }
     x256 = c->dec1;
@@ -1429,7 +1438,7 @@ int dlv3p_op_sepconv(int device, const void* x_bf16, int B, int H, int W_, int C
   P.tmap_x = &dtm[0]; P.tmap_w = &dtm[1]; P.tmap_out = &dtm[2]; P.dw_w = ddw; P.dw_shift = dsh; P.scale = ds; P.shift = dt;
   P.out = static_cast<__nv_bfloat16*>(out_bf16); P.B = B; P.H = H; P.W = W_;
   P.tiles_x = ceil_div(W_, kDwTW); P.tiles_y = ceil_div(H, kDwTH); P.num_tiles = B * P.tiles_x * P.tiles_y;
-  CU_TRY(nullptr, launch_dwpw(KB, P, sms, st));
+  CU_TRY(nullptr, launch_dwpw(KB, P, s.data(), t.data(), sms, st));
   CU_TRY(nullptr, cudaStreamSynchronize(st));
   return DLV3P_OK;
 }
@@ -1530,8 +1539,9 @@ int dlv3p_op_time(int device, int op, const int64_t* d, int ndims, int iters, in
     uint16_t* o = tmp.alloc<uint16_t>(static_cast<size_t>(B) * H * W_ * 256);
     float* dw = tmp.put(std::vector<float>(static_cast<size_t>(9) * Cpad, 0.1f));
     float* dsh = tmp.put(std::vector<float>(Cpad, 0.0f));
-    float* s = tmp.put(std::vector<float>(256, 1.0f));
-    float* t = tmp.put(std::vector<float>(256, 0.0f));
+    const std::vector<float> hs(256, 1.0f), ht(256, 0.0f);
+    float* s = tmp.put(hs);
+    float* t = tmp.put(ht);
     std::vector<CUtensorMap> tm(3);
     if (!encode_4d_halo(&tm[0], x, B, H, W_, C, C, kDwHaloW, kDwHaloH, &terr) || !encode_2d_sw128(&tm[1], w, 256, Cpad, Cpad, w_box_rows(256), &terr) ||
         !encode_4d_out(&tm[2], o, B, H, W_, 256, &terr)) return fail(nullptr, DLV3P_ERR_CUDA, terr);
@@ -1540,7 +1550,7 @@ int dlv3p_op_time(int device, int op, const int64_t* d, int ndims, int iters, in
     P.tmap_x = &dtm[0]; P.tmap_w = &dtm[1]; P.tmap_out = &dtm[2]; P.dw_w = dw; P.dw_shift = dsh; P.scale = s; P.shift = t;
     P.out = reinterpret_cast<__nv_bfloat16*>(o); P.B = B; P.H = H; P.W = W_;
     P.tiles_x = ceil_div(W_, kDwTW); P.tiles_y = ceil_div(H, kDwTH); P.num_tiles = B * P.tiles_x * P.tiles_y; P.debug = flags;
-    rc = run([&] { launch_dwpw(KB, P, sms, st); });
+    rc = run([&] { launch_dwpw(KB, P, hs.data(), ht.data(), sms, st); });
   } else if (op == 2 && ndims >= 6) {   // resize {B,hi,wi,C,ho,wo}
     ResizeParams P{};
     P.B = static_cast<int>(d[0]); P.hi = static_cast<int>(d[1]); P.wi = static_cast<int>(d[2]); P.C = static_cast<int>(d[3]);

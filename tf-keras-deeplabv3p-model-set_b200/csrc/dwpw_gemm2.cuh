@@ -23,25 +23,36 @@
 
 #include "dwpw_gemm.cuh"
 #include "pw_gemm2.cuh"
+#include "aspp_dw_fast.cuh"   // f32x2_to_bf16x2_relu
 
 namespace dlv3p {
 
 template <int KB>
 struct DwPw2Cfg {
   static constexpr int kAS = 3;
-  static constexpr int kIS = KB <= 4 ? 4 : 3;
+  static constexpr int kIS = 3;
+  static constexpr int kTapBytes = KB * 10 * 64 * 4;                  // [KB][9 taps + shift][64 channels] fp32
   static constexpr int kWHalfBlockBytes = 128 * 128;               // this CTA's 128 output channels x 64 input channels
   static constexpr int kWBytes = KB * kWHalfBlockBytes;
   static constexpr int kABytes = kAS * kDwAStageBytes;
   static constexpr int kInBytes = kIS * kDwInStageBytes;
   static constexpr int kInBytesPad = (kInBytes + 1023) / 1024 * 1024;   // the store staging wants 1024-byte alignment
   static constexpr int kStoreBytes = 4 * 4096;
-  static constexpr int kSmemBytes = kWBytes + kABytes + kInBytesPad + kStoreBytes + 2048 /*BN scale+shift*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kWBytes + kABytes + kInBytesPad + kStoreBytes + kTapBytes + 256 /*barriers*/;
+};
+
+// The pointwise BN scale / shift travel in the kernel parameters (constant bank): the epilogue reads them as immediate
+// constant operands instead of 128 shared-memory loads per thread and tile.
+struct DwPw2Params {
+  DwPwParams base;
+  float scale_c[256];
+  float shift_c[256];
 };
 
 template <int KB>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDwThreads, 1) dwpw_gemm2_kernel(const __grid_constant__ DwPwParams P) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDwThreads, 1) dwpw_gemm2_kernel(const __grid_constant__ DwPw2Params Q) {
   using Cfg = DwPw2Cfg<KB>;
+  const DwPwParams& P = Q.base;
   constexpr int AS = Cfg::kAS, IS = Cfg::kIS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -50,9 +61,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDwThreads, 1) dwpw_
   uint8_t* smem_a = smem_w + Cfg::kWBytes;         // AS x [128 rows x 128 B], swizzled
   uint8_t* smem_in = smem_a + Cfg::kABytes;        // IS x [10][18][64] bf16
   uint8_t* smem_c = smem_in + Cfg::kInBytesPad;    // epilogue store staging, 4 warps x 4 KB
-  float* s_scale = reinterpret_cast<float*>(smem_c + Cfg::kStoreBytes);
-  float* s_shift = s_scale + 256;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
+  float* s_taps = reinterpret_cast<float*>(smem_c + Cfg::kStoreBytes);   // depthwise taps + shift of every K block (no L1 here: L2 latency otherwise)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_taps + KB * 10 * 64);
   uint64_t* w_full = bars;                   // [1]
   uint64_t* in_full = bars + 1;              // [IS]
   uint64_t* in_empty = in_full + IS;         // [IS]
@@ -86,9 +96,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDwThreads, 1) dwpw_
     }
     fence_barrier_init();
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + 256) {
-    s_scale[threadIdx.x - 64] = P.scale[threadIdx.x - 64];
-    s_shift[threadIdx.x - 64] = P.shift[threadIdx.x - 64];
+  for (int i = threadIdx.x; i < KB * 10 * 64; i += kDwThreads) {
+    const int kb = i / 640, t = (i - kb * 640) >> 6, ch = kb * 64 + (i & 63);
+    s_taps[i] = t < 9 ? __ldg(P.dw_w + t * (KB * 64) + ch) : __ldg(P.dw_shift + ch);
   }
   cluster_sync_all();                       // barriers of both CTAs exist before anyone signals across the pair
   if (warp == 1) {
@@ -173,7 +183,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDwThreads, 1) dwpw_
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kDwBN;
       // bf16 output through 128B-swizzled smem + TMA store: box = this warp's 2 tile rows x 16 pixels x 64 channels;
       // partial (and phantom) tiles are clipped by the TMA unit
-#pragma unroll 1
+#pragma unroll
       for (int cb = 0; cb < kDwBN / 64; ++cb) {
         uint32_t pk[32];
 #pragma unroll
@@ -184,10 +194,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDwThreads, 1) dwpw_
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const ulonglong2 s = *reinterpret_cast<const ulonglong2*>(s_scale + c0 + j);
-            const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(s_shift + c0 + j);
-            pk[half * 16 + j / 2 + 0] = relu_bf16x2(f32x2_to_bf16x2(f32x2_fma(f32x2_make(v[j + 0], v[j + 1]), s.x, t.x)));
-            pk[half * 16 + j / 2 + 1] = relu_bf16x2(f32x2_to_bf16x2(f32x2_fma(f32x2_make(v[j + 2], v[j + 3]), s.y, t.y)));
+            const unsigned long long s01 = pack_f32x2(Q.scale_c[c0 + j], Q.scale_c[c0 + j + 1]), s23 = pack_f32x2(Q.scale_c[c0 + j + 2], Q.scale_c[c0 + j + 3]);
+            const unsigned long long t01 = pack_f32x2(Q.shift_c[c0 + j], Q.shift_c[c0 + j + 1]), t23 = pack_f32x2(Q.shift_c[c0 + j + 2], Q.shift_c[c0 + j + 3]);
+            pk[half * 16 + j / 2 + 0] = f32x2_to_bf16x2_relu(f32x2_fma(f32x2_make(v[j + 0], v[j + 1]), s01, t01));
+            pk[half * 16 + j / 2 + 1] = f32x2_to_bf16x2_relu(f32x2_fma(f32x2_make(v[j + 2], v[j + 3]), s23, t23));
           }
         }
         if (cb == kDwBN / 64 - 1) {   // every column of this accumulator stage is in registers: hand it back early
@@ -216,84 +226,73 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDwThreads, 1) dwpw_
     if (lane == 0) tma_store_wait_all<0>();
   } else {
     // ------------------------------------------------------------------ depthwise stencil warps (both CTAs, own tile)
-    // All eight stencil warps work on the SAME K block: warps 6..9 produce output rows 0..3 of the tile, warps 10..13
-    // rows 4..7 (each half reads 6 halo rows).
-    const int g = (warp - 6) >> 2;          // row half 0/1
-    const int wg = (warp - 6) & 3;          // warp within the half
-    const int v4 = lane & 15;               // which 4-channel slice of the 64-channel K block
-    const int cp = wg * 2 + (lane >> 4);    // column pair: output cols 2cp, 2cp+1
-    constexpr int kRows = kDwTH / 2;        // output rows per half
-    const uint32_t in_base = smem_u32(smem_in);
-    const uint32_t a_base = smem_u32(smem_a);
+    // warp = a 4 x 4 block of output pixels (row half g, column block cbk), lane = one channel PAIR of the 64-channel K
+    // block.  Every warp-wide load / store is one 128-byte pixel row: a single conflict-free shared-memory wavefront
+    // (the 4-channel / 2-pixel mapping of the 1-CTA kernel needs two, and its tap loads four).  Per K block a thread
+    // reads its 6 x 6 halo window once (rolling over the rows, next row's loads in flight during this row's FMAs).
+    const int sw = warp - 6;
+    const int g = sw >> 2;                  // output rows 4g .. 4g+3
+    const int cbk = sw & 3;                 // output cols 4cbk .. 4cbk+3
+    const uint32_t in_base = smem_u32(smem_in) + ((4 * g) * kDwHaloW + 4 * cbk) * 128 + lane * 4;
+    const uint32_t a_base = smem_u32(smem_a) + (lane & 3) * 4;
+    const uint32_t jchunk = static_cast<uint32_t>(lane >> 2);
     int my_items = 0;
     for (int item = cluster_id; item < num_items; item += num_clusters) ++my_items;
     const uint32_t total_c = static_cast<uint32_t>(my_items) * KB;
-    unsigned long long wlo[9], whi[9], sh_lo, sh_hi;
-    auto load_taps = [&](uint32_t cn) {   // taps + shift of this thread's 4 channels (L2 latency: issued one K block early)
-      const int ch = static_cast<int>(cn % KB) * 64 + v4 * 4;
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const float4 w = __ldg(reinterpret_cast<const float4*>(P.dw_w + t * (KB * 64) + ch));
-        wlo[t] = pack_f32x2(w.x, w.y);
-        whi[t] = pack_f32x2(w.z, w.w);
-      }
-      const float4 sh = __ldg(reinterpret_cast<const float4*>(P.dw_shift + ch));
-      sh_lo = pack_f32x2(sh.x, sh.y);
-      sh_hi = pack_f32x2(sh.z, sh.w);
-    };
-    if (total_c > 0) load_taps(0);
+    uint32_t kb = 0;
     for (uint32_t c = 0; c < total_c; ++c) {
       const uint32_t si = c % IS;
       const uint32_t sa = c % AS;
+      // taps + shift of this lane's channel pair: 10 x LDS.64, 256 contiguous bytes per warp
+      unsigned long long wt[9], sh;
+      {
+        const float* tp = s_taps + kb * 640 + lane * 2;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const float2 w = *reinterpret_cast<const float2*>(tp + t * 64);
+          wt[t] = pack_f32x2(w.x, w.y);
+        }
+        const float2 w = *reinterpret_cast<const float2*>(tp + 9 * 64);
+        sh = pack_f32x2(w.x, w.y);
+      }
+      if (++kb == KB) kb = 0;
       mbar_wait(&in_full[si], (c / IS) & 1);
-      const uint32_t in_addr = in_base + si * kDwInStageBytes + ((g * kRows) * kDwHaloW + 2 * cp) * 128 + v4 * 8;
+      const uint32_t in_addr = in_base + si * kDwInStageBytes;
       const uint32_t a_addr = a_base + sa * kDwAStageBytes;
 
-      unsigned long long acc_lo[3][2], acc_hi[3][2];
-      uint2 raw_next[4];
+      unsigned long long acc[3][4];
+      uint32_t raw_next[6];
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) raw_next[cc] = lds_v2(in_addr + cc * 128);
+      for (int cc = 0; cc < 6; ++cc) raw_next[cc] = lds_u32(in_addr + cc * 128);
 #pragma unroll
-      for (int r = 0; r < kRows + 2; ++r) {
-        unsigned long long x_lo[4], x_hi[4];
+      for (int r = 0; r < 6; ++r) {
+        unsigned long long x[6];
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          x_lo[cc] = bf16x2_to_f32x2(raw_next[cc].x);
-          x_hi[cc] = bf16x2_to_f32x2(raw_next[cc].y);
+        for (int cc = 0; cc < 6; ++cc) x[cc] = bf16x2_to_f32x2(raw_next[cc]);
+        if (r + 1 < 6) {
+#pragma unroll
+          for (int cc = 0; cc < 6; ++cc) raw_next[cc] = lds_u32(in_addr + ((r + 1) * kDwHaloW + cc) * 128);
         }
-        if (r + 1 < kRows + 2) {
+        if (r < 4) {
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) raw_next[cc] = lds_v2(in_addr + ((r + 1) * kDwHaloW + cc) * 128);
-        }
-        if (r < kRows) {
-#pragma unroll
-          for (int oc = 0; oc < 2; ++oc) {
-            acc_lo[r % 3][oc] = sh_lo;
-            acc_hi[r % 3][oc] = sh_hi;
-          }
+          for (int oc = 0; oc < 4; ++oc) acc[r % 3][oc] = sh;
         }
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
           const int orow = r - dy;
-          if (orow < 0 || orow >= kRows) continue;
+          if (orow < 0 || orow >= 4) continue;
 #pragma unroll
-          for (int oc = 0; oc < 2; ++oc)
+          for (int oc = 0; oc < 4; ++oc)
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-              ffma2(acc_lo[orow % 3][oc], wlo[dy * 3 + dx], x_lo[oc + dx]);
-              ffma2(acc_hi[orow % 3][oc], whi[dy * 3 + dx], x_hi[oc + dx]);
-            }
+            for (int dx = 0; dx < 3; ++dx) ffma2(acc[orow % 3][oc], wt[dy * 3 + dx], x[oc + dx]);
         }
-        if (r >= 2) {
+        if (r >= 2) {  // output row r-2 of this block is complete
           const int orow = r - 2;
           if (orow == 0) mbar_wait(&a_empty[sa], ((c / AS) & 1) ^ 1);  // the MMA is done with this A stage
 #pragma unroll
-          for (int oc = 0; oc < 2; ++oc) {
-            const uint32_t p0 = relu_bf16x2(f32x2_to_bf16x2(acc_lo[orow % 3][oc]));
-            const uint32_t p1 = relu_bf16x2(f32x2_to_bf16x2(acc_hi[orow % 3][oc]));
-            const int m = (g * kRows + orow) * kDwTW + 2 * cp + oc;
-            const uint32_t chunk = static_cast<uint32_t>(v4 >> 1) ^ static_cast<uint32_t>(m & 7);
-            if (!(P.debug & 2)) sts_v2(a_addr + m * 128 + chunk * 16 + (v4 & 1) * 8, p0, p1);
+          for (int oc = 0; oc < 4; ++oc) {
+            const uint32_t m = static_cast<uint32_t>((4 * g + orow) * kDwTW + 4 * cbk + oc);
+            if (!(P.debug & 2)) sts_u32(a_addr + m * 128 + ((jchunk ^ (m & 7u)) << 4), f32x2_to_bf16x2_relu(acc[orow % 3][oc]));
           }
         }
       }
@@ -304,7 +303,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDwThreads, 1) dwpw_
         if (leader) mbar_arrive(&a_full[sa]);
         else mbar_arrive_cluster(&a_full[sa], 0);
       }
-      if (c + 1 < total_c) load_taps(c + 1);
     }
   }
 

@@ -270,6 +270,14 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t smem_addr) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_addr));
   return r;
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t smem_addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t smem_addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(smem_addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint2 lds_v2(uint32_t smem_addr) {
   uint2 r;
   asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(smem_addr));
