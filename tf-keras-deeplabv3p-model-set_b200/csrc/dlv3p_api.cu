@@ -120,15 +120,15 @@ bool encode_2d_out(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t co
   return encode_2d_sw128(tm, base, rows, cols, ld, 32, err);
 }
 // 4D bf16 NHWC output {C, W, H, B}, box {64, 16, 2, 1}, 128B swizzle: the fused kernel's TMA-store epilogue
-bool encode_4d_out(CUtensorMap* tm, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C, std::string* err) {
+bool encode_4d_out(CUtensorMap* tm, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C, std::string* err, uint32_t box_c = 64) {
   EncodeTiledFn fn = get_encode_fn(err);
   if (!fn) return false;
   cuuint64_t gdim[4] = {C, W, H, B};
   cuuint64_t gstride[3] = {C * 2, W * C * 2, H * W * C * 2};
-  cuuint32_t box[4] = {64, 16, 2, 1};
+  cuuint32_t box[4] = {box_c, 16, 2, 1};   // 64 channels: 128B swizzle; 32 channels: 64B swizzle
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     if (err) *err = fmt("cuTensorMapEncodeTiled(4d out) -> %d", (int)r);
@@ -313,15 +313,16 @@ cudaError_t launch_dwpw2_t(const DwPw2Params& P2, int num_sms, cudaStream_t st) 
   }
   const int items = (P.num_tiles + 1) / 2;
   const int grid = 2 * items < num_sms ? 2 * items : (num_sms & ~1);
-  dwpw_gemm2_kernel<KB><<<grid, kDwThreads, DwPw2Cfg<KB>::kSmemBytes, st>>>(P2);
+  dwpw_gemm2_kernel<KB><<<grid, kDw2Threads, DwPw2Cfg<KB>::kSmemBytes, st>>>(P2);
   return cudaGetLastError();
 }
 // CTA-pair kernel by default; debug bit 3 (or DLV3P_NO_CTA2=1) selects the 1-CTA kernel for A/B runs
 // h_scale / h_shift: HOST copies of the pointwise BN scale / shift (256 each) for the pair kernel's constant-bank epilogue
-cudaError_t launch_dwpw(int KB, const DwPwParams& P, const float* h_scale, const float* h_shift, int num_sms, cudaStream_t st) {
-  if (use_cta2() && !(P.debug & 8) && h_scale && h_shift) {
+cudaError_t launch_dwpw(int KB, const DwPwParams& P, const CUtensorMap* tmap_out32, const float* h_scale, const float* h_shift, int num_sms, cudaStream_t st) {
+  if (use_cta2() && !(P.debug & 8) && h_scale && h_shift && tmap_out32) {
     DwPw2Params P2;
     P2.base = P;
+    P2.tmap_out32 = tmap_out32;
     std::memcpy(P2.scale_c, h_scale, sizeof(P2.scale_c));
     std::memcpy(P2.shift_c, h_shift, sizeof(P2.shift_c));
     switch (KB) {
@@ -366,7 +367,7 @@ struct WeightSlot {
 enum TmSlot {
   TM_FEAT = 0, TM_DW1, TM_DW2, TM_DW3, TM_CONCAT, TM_SKIP, TM_DECIN, TM_DEC0, TM_CLS_IN,
   TM_W_ASPP0, TM_W_ASPP1, TM_W_ASPP2, TM_W_ASPP3, TM_W_PROJ, TM_W_FP0, TM_W_DEC0, TM_W_DEC1, TM_W_CLS,
-  TM_O_ASPP0, TM_O_ASPP1, TM_O_ASPP2, TM_O_ASPP3, TM_O_PROJ, TM_O_FP0, TM_O_DEC0, TM_O_DEC1, TM_FEAT_SLAB, TM_O4_DEC0, TM_O4_DEC1,
+  TM_O_ASPP0, TM_O_ASPP1, TM_O_ASPP2, TM_O_ASPP3, TM_O_PROJ, TM_O_FP0, TM_O_DEC0, TM_O_DEC1, TM_FEAT_SLAB, TM_O4_DEC0, TM_O4_DEC1, TM_O4S_DEC0, TM_O4S_DEC1,
   TM_COUNT
 };
 
@@ -916,6 +917,8 @@ int dlv3p_finalize_weights(dlv3p_ctx* c) {
     ok = ok && encode_2d_out(&c->h_tm[TM_O_DEC1], c->dec1, c->M2, 256, 256, &terr);
     ok = ok && encode_4d_out(&c->h_tm[TM_O4_DEC0], c->dec0, g.B, c->hs, c->ws, 256, &terr);
     ok = ok && encode_4d_out(&c->h_tm[TM_O4_DEC1], c->dec1, g.B, c->hs, c->ws, 256, &terr);
+    ok = ok && encode_4d_out(&c->h_tm[TM_O4S_DEC0], c->dec0, g.B, c->hs, c->ws, 256, &terr, 32);
+    ok = ok && encode_4d_out(&c->h_tm[TM_O4S_DEC1], c->dec1, g.B, c->hs, c->ws, 256, &terr, 32);
     if (g.flags & DLV3P_FLAG_UNFUSED_DECODER) {
       ok = ok && enc2(TM_DECIN, c->dec_tmp, c->M2, 304, 304, 128);
       ok = ok && enc2(TM_DEC0, c->dec_tmp, c->M2, 256, 256, 128);
@@ -1169,7 +1172,7 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
         P.dw_w = s.dw->w; P.dw_shift = s.dw->shift; P.scale = s.pw->scale; P.shift = s.pw->shift; P.out = s.out;
         P.tmap_out = &c->d_tm[s.tm_o == TM_O_DEC0 ? TM_O4_DEC0 : TM_O4_DEC1];
         P.B = g.B; P.H = c->hs; P.W = c->ws; P.tiles_x = tiles_x; P.tiles_y = tiles_y; P.num_tiles = g.B * tiles_x * tiles_y;
-        L.end(s.name, launch_dwpw(s.dw->Cpad / 64, P, s.pw->h_scale.data(), s.pw->h_shift.data(), c->num_sms, st));
+        L.end(s.name, launch_dwpw(s.dw->Cpad / 64, P, &c->d_tm[s.tm_o == TM_O_DEC0 ? TM_O4S_DEC0 : TM_O4S_DEC1], s.pw->h_scale.data(), s.pw->h_shift.data(), c->num_sms, st));
       }
     }
     x256 = c->dec1;
@@ -1428,9 +1431,9 @@ int dlv3p_op_sepconv(int device, const void* x_bf16, int B, int H, int W_, int C
   float* ds = tmp.put(s);
   float* dt = tmp.put(t);
   std::string terr;
-  std::vector<CUtensorMap> tm(3);
+  std::vector<CUtensorMap> tm(4);
   if (!encode_4d_halo(&tm[0], x_bf16, B, H, W_, C, C, kDwHaloW, kDwHaloH, &terr) || !encode_2d_sw128(&tm[1], dpw, 256, Cpad, Cpad, w_box_rows(256), &terr) ||
-      !encode_4d_out(&tm[2], out_bf16, B, H, W_, 256, &terr))
+      !encode_4d_out(&tm[2], out_bf16, B, H, W_, 256, &terr) || !encode_4d_out(&tm[3], out_bf16, B, H, W_, 256, &terr, 32))
     return fail(nullptr, DLV3P_ERR_CUDA, terr);
   CUtensorMap* dtm = tmp.put(tm);
   if (!ddw || !dsh || !dpw || !ds || !dt || !dtm) return fail(nullptr, DLV3P_ERR_NOMEM, "op_sepconv: cudaMalloc failed");
@@ -1438,7 +1441,7 @@ int dlv3p_op_sepconv(int device, const void* x_bf16, int B, int H, int W_, int C
   P.tmap_x = &dtm[0]; P.tmap_w = &dtm[1]; P.tmap_out = &dtm[2]; P.dw_w = ddw; P.dw_shift = dsh; P.scale = ds; P.shift = dt;
   P.out = static_cast<__nv_bfloat16*>(out_bf16); P.B = B; P.H = H; P.W = W_;
   P.tiles_x = ceil_div(W_, kDwTW); P.tiles_y = ceil_div(H, kDwTH); P.num_tiles = B * P.tiles_x * P.tiles_y;
-  CU_TRY(nullptr, launch_dwpw(KB, P, s.data(), t.data(), sms, st));
+  CU_TRY(nullptr, launch_dwpw(KB, P, &dtm[3], s.data(), t.data(), sms, st));
   CU_TRY(nullptr, cudaStreamSynchronize(st));
   return DLV3P_OK;
 }
@@ -1542,15 +1545,15 @@ int dlv3p_op_time(int device, int op, const int64_t* d, int ndims, int iters, in
     const std::vector<float> hs(256, 1.0f), ht(256, 0.0f);
     float* s = tmp.put(hs);
     float* t = tmp.put(ht);
-    std::vector<CUtensorMap> tm(3);
+    std::vector<CUtensorMap> tm(4);
     if (!encode_4d_halo(&tm[0], x, B, H, W_, C, C, kDwHaloW, kDwHaloH, &terr) || !encode_2d_sw128(&tm[1], w, 256, Cpad, Cpad, w_box_rows(256), &terr) ||
-        !encode_4d_out(&tm[2], o, B, H, W_, 256, &terr)) return fail(nullptr, DLV3P_ERR_CUDA, terr);
+        !encode_4d_out(&tm[2], o, B, H, W_, 256, &terr) || !encode_4d_out(&tm[3], o, B, H, W_, 256, &terr, 32)) return fail(nullptr, DLV3P_ERR_CUDA, terr);
     CUtensorMap* dtm = tmp.put(tm);
     DwPwParams P{};
     P.tmap_x = &dtm[0]; P.tmap_w = &dtm[1]; P.tmap_out = &dtm[2]; P.dw_w = dw; P.dw_shift = dsh; P.scale = s; P.shift = t;
     P.out = reinterpret_cast<__nv_bfloat16*>(o); P.B = B; P.H = H; P.W = W_;
     P.tiles_x = ceil_div(W_, kDwTW); P.tiles_y = ceil_div(H, kDwTH); P.num_tiles = B * P.tiles_x * P.tiles_y; P.debug = flags;
-    rc = run([&] { launch_dwpw(KB, P, hs.data(), ht.data(), sms, st); });
+    rc = run([&] { launch_dwpw(KB, P, &dtm[3], hs.data(), ht.data(), sms, st); });
   } else if (op == 2 && ndims >= 6) {   // resize {B,hi,wi,C,ho,wo}
     ResizeParams P{};
     P.B = static_cast<int>(d[0]); P.hi = static_cast<int>(d[1]); P.wi = static_cast<int>(d[2]); P.C = static_cast<int>(d[3]);

@@ -5,18 +5,20 @@
 // Two CTAs of a cluster (two SMs of a TPC) each own one 8 x 16-pixel tile: each CTA stages its own halo tiles, runs its
 // own depthwise stencil into its own A stages, and keeps only HALF of the pointwise weights (128 of the 256 output
 // channels) resident.  One thread of the leader CTA issues tcgen05.mma.cta_group::2 (M = 256): the tensor cores of
-// both SMs read both weight halves.  Against the 1-CTA kernel this
-//   * halves the shared-memory read traffic of the B operand (the MMA of the 1-CTA kernel alone uses 75 % of the
-//     128 B/clk shared-memory bandwidth, leaving too little for the stencil's loads and stores),
-//   * frees 64-80 KB of shared memory: three A stages and three to four halo stages, so the stencil warps, the TMA and the
-//     tensor cores run decoupled instead of in lock step, and every K (<= 320) gets the TMA-store epilogue.
+// both SMs read both weight halves.  Against the 1-CTA kernel this halves the shared-memory traffic of the B operand
+// (the MMA of the 1-CTA kernel alone uses 75 % of the 128 B/clk shared-memory port) and frees 64-80 KB of shared memory.
 //
-//   in_full[s]    (own CTA)   1 arrival + tx bytes : halo tile landed
-//   in_empty[s]   (own CTA)   8 arrivals           : one per stencil warp
-//   a_full[s]     (leader's)  16 arrivals          : the 8 stencil warps of both CTAs
-//   a_empty[s]    (each CTA)  1 arrival            : tcgen05.commit multicast from the leader's MMA thread
-//   tmem_full[a]  (each CTA)  1 arrival            : tcgen05.commit multicast
-//   tmem_empty[a] (leader's)  256 arrivals         : the 4 epilogue warps of both CTAs
+// The stencil is the critical resource (FP32 pipe: 128 px x 64 ch x 9 FMA per K block = 576 clk of the 128-lane pipe;
+// two warps per scheduler only reach ~0.5 IPC), so SIXTEEN stencil warps run as two groups of eight; group p takes the
+// K blocks c with c mod 2 == p (c counts K blocks across tiles).  Each group has its OWN rings (two halo stages, one A
+// stage), so every mbarrier has one producer set and one consumer set advancing in lock step — parity waits stay sound.
+//
+//   in_full[p][s]  (own CTA)   1 arrival + tx bytes : halo tile landed
+//   in_empty[p][s] (own CTA)   8 arrivals           : one per stencil warp of group p
+//   a_full[p]      (leader's)  16 arrivals          : the 8 stencil warps of group p in both CTAs
+//   a_empty[p]     (each CTA)  1 arrival            : tcgen05.commit multicast from the leader's MMA thread
+//   tmem_full[a]   (each CTA)  1 arrival            : tcgen05.commit multicast
+//   tmem_empty[a]  (leader's)  256 arrivals         : the 4 epilogue warps of both CTAs
 #pragma once
 
 #include <cuda.h>
@@ -27,17 +29,17 @@
 
 namespace dlv3p {
 
+constexpr int kDw2Threads = 22 * 32;   // producer, MMA, 4 epilogue, 16 stencil warps
+
 template <int KB>
 struct DwPw2Cfg {
-  static constexpr int kAS = 3;
-  static constexpr int kIS = 3;
   static constexpr int kTapBytes = KB * 10 * 64 * 4;                  // [KB][9 taps + shift][64 channels] fp32
-  static constexpr int kWHalfBlockBytes = 128 * 128;               // this CTA's 128 output channels x 64 input channels
+  static constexpr int kWHalfBlockBytes = 128 * 128;                  // this CTA's 128 output channels x 64 input channels
   static constexpr int kWBytes = KB * kWHalfBlockBytes;
-  static constexpr int kABytes = kAS * kDwAStageBytes;
-  static constexpr int kInBytes = kIS * kDwInStageBytes;
-  static constexpr int kInBytesPad = (kInBytes + 1023) / 1024 * 1024;   // the store staging wants 1024-byte alignment
-  static constexpr int kStoreBytes = 4 * 4096;
+  static constexpr int kABytes = 2 * kDwAStageBytes;                  // one A stage per stencil group
+  static constexpr int kInBytes = 4 * kDwInStageBytes;                // two halo stages per stencil group
+  static constexpr int kInBytesPad = (kInBytes + 1023) / 1024 * 1024;
+  static constexpr int kStoreBytes = 4 * 2048;                        // 4 epilogue warps x [32 rows x 64 B], 64B swizzle
   static constexpr int kSmemBytes = kWBytes + kABytes + kInBytesPad + kStoreBytes + kTapBytes + 256 /*barriers*/;
 };
 
@@ -45,30 +47,30 @@ struct DwPw2Cfg {
 // constant operands instead of 128 shared-memory loads per thread and tile.
 struct DwPw2Params {
   DwPwParams base;
+  const CUtensorMap* tmap_out32;   // 4D {256, W, H, B} bf16, box {32, 16, 2, 1}, SWIZZLE_64B
   float scale_c[256];
   float shift_c[256];
 };
 
 template <int KB>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDwThreads, 1) dwpw_gemm2_kernel(const __grid_constant__ DwPw2Params Q) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDw2Threads, 1) dwpw_gemm2_kernel(const __grid_constant__ DwPw2Params Q) {
   using Cfg = DwPw2Cfg<KB>;
   const DwPwParams& P = Q.base;
-  constexpr int AS = Cfg::kAS, IS = Cfg::kIS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   uint8_t* smem_w = smem;                          // KB x [128 rows x 128 B], swizzled: this CTA's half of the weights
-  uint8_t* smem_a = smem_w + Cfg::kWBytes;         // AS x [128 rows x 128 B], swizzled
-  uint8_t* smem_in = smem_a + Cfg::kABytes;        // IS x [10][18][64] bf16
-  uint8_t* smem_c = smem_in + Cfg::kInBytesPad;    // epilogue store staging, 4 warps x 4 KB
-  float* s_taps = reinterpret_cast<float*>(smem_c + Cfg::kStoreBytes);   // depthwise taps + shift of every K block (no L1 here: L2 latency otherwise)
+  uint8_t* smem_a = smem_w + Cfg::kWBytes;         // 2 x [128 rows x 128 B], swizzled (stage p = stencil group p)
+  uint8_t* smem_in = smem_a + Cfg::kABytes;        // 4 x [10][18][64] bf16 (stages 2p, 2p+1 = stencil group p)
+  uint8_t* smem_c = smem_in + Cfg::kInBytesPad;    // epilogue store staging, 4 warps x 2 KB
+  float* s_taps = reinterpret_cast<float*>(smem_c + Cfg::kStoreBytes);   // depthwise taps + shift of every K block
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_taps + KB * 10 * 64);
   uint64_t* w_full = bars;                   // [1]
-  uint64_t* in_full = bars + 1;              // [IS]
-  uint64_t* in_empty = in_full + IS;         // [IS]
-  uint64_t* a_full = in_empty + IS;          // [AS]
-  uint64_t* a_empty = a_full + AS;           // [AS]
-  uint64_t* tmem_full = a_empty + AS;        // [2]
+  uint64_t* in_full = bars + 1;              // [4]
+  uint64_t* in_empty = in_full + 4;          // [4]
+  uint64_t* a_full = in_empty + 4;           // [2]
+  uint64_t* a_empty = a_full + 2;            // [2]
+  uint64_t* tmem_full = a_empty + 2;         // [2]
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
   uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -82,21 +84,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDwThreads, 1) dwpw_
 
   if (warp == 0 && lane == 0) {
     mbar_init(w_full, 1);
-    for (int i = 0; i < IS; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&in_full[i], 1);
       mbar_init(&in_empty[i], 8);
     }
-    for (int i = 0; i < AS; ++i) {
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&a_full[i], 16);
       mbar_init(&a_empty[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 256);
     }
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < KB * 10 * 64; i += kDwThreads) {
+  for (int i = threadIdx.x; i < KB * 10 * 64; i += kDw2Threads) {
     const int kb = i / 640, t = (i - kb * 640) >> 6, ch = kb * 64 + (i & 63);
     s_taps[i] = t < 9 ? __ldg(P.dw_w + t * (KB * 64) + ch) : __ldg(P.dw_shift + ch);
   }
@@ -124,9 +124,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDwThreads, 1) dwpw_
         const int ty = t2 / P.tiles_x;
         const int tx = t2 - ty * P.tiles_x;
         for (int kb = 0; kb < KB; ++kb, ++c) {
-          const uint32_t si = c % IS;
-          const uint32_t ph = (c / IS) & 1;
+          const uint32_t si = (c & 1) * 2 + ((c >> 1) & 1);   // group c&1, its stage (c>>1)&1
+          const uint32_t ph = (c >> 2) & 1;
           mbar_wait(&in_empty[si], ph ^ 1);
+          if (P.debug & 64) {   // benchmark aid: no halo loads (the stencil runs on stale shared memory)
+            mbar_arrive(&in_full[si]);
+            continue;
+          }
           mbar_arrive_expect_tx(&in_full[si], kDwInStageBytes);
           tma_load_4d(smem_in + si * kDwInStageBytes, P.tmap_x, &in_full[si], kb * 64, tx * kDwTW - 1, ty * kDwTH - 1, b, kEvictNormal);
         }
@@ -145,8 +149,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDwThreads, 1) dwpw_
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kDwBN;
         for (int kb = 0; kb < KB; ++kb, ++c) {
-          const uint32_t sa = c % AS;
-          const uint32_t ph = (c / AS) & 1;
+          const uint32_t sa = c & 1;
+          const uint32_t ph = (c >> 1) & 1;
           mbar_wait(&a_full[sa], ph);
           tcgen05_fence_after();
           if (elect_one()) {
@@ -168,8 +172,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDwThreads, 1) dwpw_
     // ------------------------------------------------------------------ epilogue (both CTAs, own tile)
     const int q = warp & 3;
     uint32_t it = 0;
-    uint8_t* my_c = smem_c + (warp - 2) * 4096;
-    const uint32_t cbuf = smem_u32(my_c) + lane * 128;
+    uint8_t* my_c = smem_c + (warp - 2) * 2048;
+    const uint32_t cbuf = smem_u32(my_c) + lane * 64;
+    const uint32_t rsw = static_cast<uint32_t>(lane >> 1) & 3u;   // 64B swizzle: 16-byte chunk index ^= (row / 2) % 4
     for (int item = cluster_id; item < num_items; item += num_clusters, ++it) {
       const int tile = item * 2 + static_cast<int>(rank);
       const int b = tile / tiles_per_img;
@@ -181,43 +186,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDwThreads, 1) dwpw_
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kDwBN;
-      // bf16 output through 128B-swizzled smem + TMA store: box = this warp's 2 tile rows x 16 pixels x 64 channels;
+      // bf16 output through 64B-swizzled smem + TMA store: box = this warp's 2 tile rows x 16 pixels x 32 channels;
       // partial (and phantom) tiles are clipped by the TMA unit
 #pragma unroll
-      for (int cb = 0; cb < kDwBN / 64; ++cb) {
-        uint32_t pk[32];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int c0 = cb * 64 + half * 32;
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(taddr + c0, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const unsigned long long s01 = pack_f32x2(Q.scale_c[c0 + j], Q.scale_c[c0 + j + 1]), s23 = pack_f32x2(Q.scale_c[c0 + j + 2], Q.scale_c[c0 + j + 3]);
-            const unsigned long long t01 = pack_f32x2(Q.shift_c[c0 + j], Q.shift_c[c0 + j + 1]), t23 = pack_f32x2(Q.shift_c[c0 + j + 2], Q.shift_c[c0 + j + 3]);
-            pk[half * 16 + j / 2 + 0] = f32x2_to_bf16x2_relu(f32x2_fma(f32x2_make(v[j + 0], v[j + 1]), s01, t01));
-            pk[half * 16 + j / 2 + 1] = f32x2_to_bf16x2_relu(f32x2_fma(f32x2_make(v[j + 2], v[j + 3]), s23, t23));
-          }
-        }
-        if (cb == kDwBN / 64 - 1) {   // every column of this accumulator stage is in registers: hand it back early
+      for (int cb = 0; cb < kDwBN / 32; ++cb) {
+        const int c0 = cb * 32;
+        uint32_t v[32], pk[16];
+        tmem_ld_32x32b_x32(taddr + c0, v);
+        tmem_ld_wait();
+        if (cb == kDwBN / 32 - 1) {   // every column of this accumulator stage has been read: hand it back early
           tcgen05_fence_before();
           if (leader) mbar_arrive(&tmem_empty[acc]);
           else mbar_arrive_cluster(&tmem_empty[acc], 0);
         }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const unsigned long long s01 = pack_f32x2(Q.scale_c[c0 + j], Q.scale_c[c0 + j + 1]), s23 = pack_f32x2(Q.scale_c[c0 + j + 2], Q.scale_c[c0 + j + 3]);
+          const unsigned long long t01 = pack_f32x2(Q.shift_c[c0 + j], Q.shift_c[c0 + j + 1]), t23 = pack_f32x2(Q.shift_c[c0 + j + 2], Q.shift_c[c0 + j + 3]);
+          pk[j / 2 + 0] = f32x2_to_bf16x2_relu(f32x2_fma(f32x2_make(v[j + 0], v[j + 1]), s01, t01));
+          pk[j / 2 + 1] = f32x2_to_bf16x2_relu(f32x2_fma(f32x2_make(v[j + 2], v[j + 3]), s23, t23));
+        }
         if (lane == 0) tma_store_wait_read<0>();   // the previous block has been read out of the staging buffer
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t chunk = static_cast<uint32_t>(j) ^ static_cast<uint32_t>(lane & 7);
-          sts_v4(cbuf + chunk * 16, make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
-        }
+        for (int j = 0; j < 4; ++j)
+          sts_v4(cbuf + ((static_cast<uint32_t>(j) ^ rsw) << 4), make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0 && !(P.debug & 1)) {
           asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
-                           reinterpret_cast<uint64_t>(P.tmap_out)),
-                       "r"(smem_u32(my_c)), "r"(cb * 64), "r"(tx * kDwTW), "r"(ty * kDwTH + 2 * q), "r"(b)
+                           reinterpret_cast<uint64_t>(Q.tmap_out32)),
+                       "r"(smem_u32(my_c)), "r"(c0), "r"(tx * kDwTW), "r"(ty * kDwTH + 2 * q), "r"(b)
                        : "memory");
           tma_store_commit();
         }
@@ -227,26 +226,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDwThreads, 1) dwpw_
   } else {
     // ------------------------------------------------------------------ depthwise stencil warps (both CTAs, own tile)
     // warp = a 4 x 4 block of output pixels (row half g, column block cbk), lane = one channel PAIR of the 64-channel K
-    // block.  Every warp-wide load / store is one 128-byte pixel row: a single conflict-free shared-memory wavefront
-    // (the 4-channel / 2-pixel mapping of the 1-CTA kernel needs two, and its tap loads four).  Per K block a thread
-    // reads its 6 x 6 halo window once (rolling over the rows, next row's loads in flight during this row's FMAs).
-    const int sw = warp - 6;
+    // block.  Every warp-wide load / store is one 128-byte pixel row: a single conflict-free shared-memory wavefront.
+    // Per K block a thread reads its 6 x 6 halo window once (rolling over the rows, next row's loads in flight during
+    // this row's FMAs).
+    const int grp = (warp - 6) >> 3;        // stencil group: K blocks c with (c & 1) == grp
+    const int sw = (warp - 6) & 7;
     const int g = sw >> 2;                  // output rows 4g .. 4g+3
     const int cbk = sw & 3;                 // output cols 4cbk .. 4cbk+3
     const uint32_t in_base = smem_u32(smem_in) + ((4 * g) * kDwHaloW + 4 * cbk) * 128 + lane * 4;
-    const uint32_t a_base = smem_u32(smem_a) + (lane & 3) * 4;
+    const uint32_t a_addr = smem_u32(smem_a) + grp * kDwAStageBytes + (lane & 3) * 4;
     const uint32_t jchunk = static_cast<uint32_t>(lane >> 2);
     int my_items = 0;
     for (int item = cluster_id; item < num_items; item += num_clusters) ++my_items;
     const uint32_t total_c = static_cast<uint32_t>(my_items) * KB;
-    uint32_t kb = 0;
-    for (uint32_t c = 0; c < total_c; ++c) {
-      const uint32_t si = c % IS;
-      const uint32_t sa = c % AS;
+    for (uint32_t c = grp; c < total_c; c += 2) {
+      const uint32_t si = grp * 2 + ((c >> 1) & 1);
       // taps + shift of this lane's channel pair: 10 x LDS.64, 256 contiguous bytes per warp
       unsigned long long wt[9], sh;
       {
-        const float* tp = s_taps + kb * 640 + lane * 2;
+        const float* tp = s_taps + (c % KB) * 640 + lane * 2;
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
           const float2 w = *reinterpret_cast<const float2*>(tp + t * 64);
@@ -255,10 +253,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDwThreads, 1) dwpw_
         const float2 w = *reinterpret_cast<const float2*>(tp + 9 * 64);
         sh = pack_f32x2(w.x, w.y);
       }
-      if (++kb == KB) kb = 0;
-      mbar_wait(&in_full[si], (c / IS) & 1);
+      mbar_wait(&in_full[si], (c >> 2) & 1);
       const uint32_t in_addr = in_base + si * kDwInStageBytes;
-      const uint32_t a_addr = a_base + sa * kDwAStageBytes;
+      if (P.debug & 32) {   // benchmark aid: barrier protocol only (times the TMA supply alone)
+        mbar_wait(&a_empty[grp], ((c >> 1) & 1) ^ 1);
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&in_empty[si]);
+          if (leader) mbar_arrive(&a_full[grp]);
+          else mbar_arrive_cluster(&a_full[grp], 0);
+        }
+        continue;
+      }
 
       unsigned long long acc[3][4];
       uint32_t raw_next[6];
@@ -288,7 +294,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDwThreads, 1) dwpw_
         }
         if (r >= 2) {  // output row r-2 of this block is complete
           const int orow = r - 2;
-          if (orow == 0) mbar_wait(&a_empty[sa], ((c / AS) & 1) ^ 1);  // the MMA is done with this A stage
+          if (orow == 0) mbar_wait(&a_empty[grp], ((c >> 1) & 1) ^ 1);  // the MMA is done with this group's A stage
 #pragma unroll
           for (int oc = 0; oc < 4; ++oc) {
             const uint32_t m = static_cast<uint32_t>((4 * g + orow) * kDwTW + 4 * cbk + oc);
@@ -300,8 +306,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDwThreads, 1) dwpw_
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&in_empty[si]);                // the warp is done reading the halo tile
-        if (leader) mbar_arrive(&a_full[sa]);
-        else mbar_arrive_cluster(&a_full[sa], 0);
+        if (leader) mbar_arrive(&a_full[grp]);
+        else mbar_arrive_cluster(&a_full[grp], 0);
       }
     }
   }

@@ -38,7 +38,7 @@ def main():
     if 'sep' in sel:
         for C in (256, 304):
             M = 32 * 128 * 128
-            for fl in ((0, 1, 4, 5, 8) if C == 256 else (0, 8)):
+            for fl in ((0, 1, 4, 5, 5 + 32, 5 + 64, 8) if C == 256 else (0, 8)):
                 rec('sepconv B=32 128x128 C=%d' % C, 1, [32, 128, 128, C], fl, flop=2.0 * M * C * 256, byts=2.0 * M * (C + 256))
     if 'aspp' in sel:
         n = 32 * 32 * 32 * 2048 * 2.0
