@@ -440,6 +440,8 @@ struct dlv3p_ctx {
   const void* tm_skip_ptr = nullptr;
 
   cudaStream_t own_stream = nullptr;
+  cudaStream_t side_stream = nullptr;   // independent branches of the graph (feature_projection0, pool_proj) run beside the main chain
+  cudaEvent_t ev_fork = nullptr, ev_dw = nullptr, ev_pool = nullptr, ev_fp0 = nullptr;
   int64_t launches_last = 0, launches_total = 0;
 
   // profiling
@@ -756,6 +758,14 @@ int dlv3p_create(const dlv3p_config* cfg, int device, dlv3p_ctx** out) {
   if ((r = dev_alloc(c, &c->d_tm, TM_COUNT))) return bail(r, c->err);
   std::memset(c->h_tm, 0, sizeof(c->h_tm));
   if (!c->plan_only && cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(DLV3P_ERR_CUDA, "cudaStreamCreate failed");
+  if (!c->plan_only) {
+    const char* e = getenv("DLV3P_NO_SIDE_STREAM");
+    if (!(e && e[0] == '1')) {
+      if (cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(DLV3P_ERR_CUDA, "cudaStreamCreate failed");
+      for (cudaEvent_t* ev : {&c->ev_fork, &c->ev_dw, &c->ev_pool, &c->ev_fp0})
+        if (cudaEventCreateWithFlags(ev, cudaEventDisableTiming) != cudaSuccess) return bail(DLV3P_ERR_CUDA, "cudaEventCreate failed");
+    }
+  }
   *out = c;
   return DLV3P_OK;
 }
@@ -772,6 +782,9 @@ void dlv3p_destroy(dlv3p_ctx* c) {
   if (c->in_skip_stage) cudaFree(c->in_skip_stage);
   if (c->out_stage) cudaFree(c->out_stage);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->side_stream) cudaStreamDestroy(c->side_stream);
+  for (cudaEvent_t ev : {c->ev_fork, c->ev_dw, c->ev_pool, c->ev_fp0})
+    if (ev) cudaEventDestroy(ev);
   for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
   delete c;
 }
@@ -1059,6 +1072,26 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
     }
   }
 
+  // independent branches on the side stream (not while profiling kernel by kernel): feature_projection0 only needs the
+  // skip feature, pool_proj only the pooling partial sums
+  const bool side = c->side_stream && !c->profiling && c->st_aspp && c->st_dec && !c->lite;
+  auto launch_fp0 = [&](cudaStream_t s_) {
+    if (L.begin("feature_projection0_gemm")) {
+      PwLaunch PL{};
+      PL.num_problems = 1; PL.M = c->M2; PL.num_tiles = ceil_div(c->M2, kPwBM); PL.rows_per_img = c->hs * c->ws;
+      PwProblem& p = PL.prob[0];
+      p.tmap_a = &c->d_tm[TM_SKIP]; p.tmap_w = &c->d_tm[TM_W_FP0]; p.tmap_out = &c->d_tm[TM_O_FP0];
+      p.scale = c->pw_fp0.scale; p.shift = c->pw_fp0.shift; p.img_shift = nullptr;
+      p.out = c->dec_in; p.K = g.Cskip; p.N = 48; p.ldo = 304; p.col_off = 256; p.relu = 1; p.epi = kEpiBf16;
+      L.end("feature_projection0_gemm", launch_pw(64, PL, c->num_sms, s_));
+    }
+  };
+  if (side) {
+    if (cudaEventRecord(c->ev_fork, st) != cudaSuccess || cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0) != cudaSuccess)
+      return fail(c, DLV3P_ERR_CUDA, "side stream fork failed");
+    launch_fp0(c->side_stream);
+    if (cudaEventRecord(c->ev_fp0, c->side_stream) != cudaSuccess) return fail(c, DLV3P_ERR_CUDA, "cudaEventRecord failed");
+  }
   const __nv_bfloat16* x256 = feat;  // running 256-channel feature map
   // ------------------------------------------------------------------ ASPP (layers.py:114-196)
   if (c->st_aspp) {
@@ -1087,14 +1120,19 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
       }
       L.end("aspp_dw_pool", cudaGetLastError());
     }
+    bool pool_on_side = false;
     if (L.begin("pool_proj")) {
       PoolProjParams P{};
       P.pool_partial = c->pool_partial; P.w_ip = reinterpret_cast<const __nv_bfloat16*>(c->w_ip);
       P.ip_scale = c->ip_scale; P.ip_shift = c->ip_shift; P.w_proj4 = reinterpret_cast<const __nv_bfloat16*>(c->w_proj4);
       P.proj_scale = c->pw_proj.scale; P.proj_shift = c->pw_proj.shift; P.img_shift = c->img_shift; P.b4_out = c->b4;
       P.C = g.Cin; P.nbands = c->nbands; P.inv_count = 1.0f / static_cast<float>(c->h * c->w);
-      pool_proj_kernel<<<g.B, 1024, (g.Cin + 256 + 2048) * sizeof(float), st>>>(P);
+      cudaStream_t ps = st;
+      if (side && cudaEventRecord(c->ev_dw, st) == cudaSuccess && cudaStreamWaitEvent(c->side_stream, c->ev_dw, 0) == cudaSuccess) ps = c->side_stream;
+      pool_proj_kernel<<<g.B, 1024, (g.Cin + 256 + 2048) * sizeof(float), ps>>>(P);
       L.end("pool_proj", cudaGetLastError());
+      pool_on_side = ps != st;
+      if (pool_on_side && cudaEventRecord(c->ev_pool, ps) != cudaSuccess) L.rc = fail(c, DLV3P_ERR_CUDA, "cudaEventRecord failed");
     }
     if (L.begin("aspp_branches_gemm")) {
       PwLaunch PL{};
@@ -1111,6 +1149,7 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
       }
       L.end("aspp_branches_gemm", launch_pw(256, PL, c->num_sms, st));
     }
+    if (pool_on_side && !L.rc && cudaStreamWaitEvent(st, c->ev_pool, 0) != cudaSuccess) L.rc = fail(c, DLV3P_ERR_CUDA, "side stream join failed");
     if (L.begin("concat_projection_gemm")) {
       PwLaunch PL{};
       PL.num_problems = 1; PL.M = c->M1; PL.num_tiles = ceil_div(c->M1, kPwBM); PL.rows_per_img = c->h * c->w;
@@ -1135,15 +1174,8 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
         resize_bilinear_kernel<<<dim3(c->hs, g.B), 256, 0, st>>>(P);
       L.end("decoder_resize", cudaGetLastError());
     }
-    if (L.begin("feature_projection0_gemm")) {
-      PwLaunch PL{};
-      PL.num_problems = 1; PL.M = c->M2; PL.num_tiles = ceil_div(c->M2, kPwBM); PL.rows_per_img = c->hs * c->ws;
-      PwProblem& p = PL.prob[0];
-      p.tmap_a = &c->d_tm[TM_SKIP]; p.tmap_w = &c->d_tm[TM_W_FP0]; p.tmap_out = &c->d_tm[TM_O_FP0];
-      p.scale = c->pw_fp0.scale; p.shift = c->pw_fp0.shift; p.img_shift = nullptr;
-      p.out = c->dec_in; p.K = g.Cskip; p.N = 48; p.ldo = 304; p.col_off = 256; p.relu = 1; p.epi = kEpiBf16;
-      L.end("feature_projection0_gemm", launch_pw(64, PL, c->num_sms, st));
-    }
+    if (!side) launch_fp0(st);
+    else if (!L.rc && cudaStreamWaitEvent(st, c->ev_fp0, 0) != cudaSuccess) L.rc = fail(c, DLV3P_ERR_CUDA, "cudaStreamWaitEvent failed");
     const int tiles_x = ceil_div(c->ws, kDwTW), tiles_y = ceil_div(c->hs, kDwTH);
     struct SepRun { const char* name; const __nv_bfloat16* in; int C; int tm_x; int tm_w; int tm_o; DwWeights* dw; PwWeights* pw; __nv_bfloat16* out; };
     SepRun runs[2] = {{"decoder_conv0_sepconv", c->dec_in, 304, TM_DECIN, TM_W_DEC0, TM_O_DEC0, &c->dw_dec0, &c->pw_dec0, c->dec0},
@@ -1196,7 +1228,7 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
         P.logits = c->logits; P.labels = static_cast<uint8_t*>(d_out); P.B = g.B; P.NC = g.NC; P.hi = c->ho; P.wi = c->wo;
         P.ho = g.H; P.wo = g.W; P.sy = sy; P.sx = sx;
         if (g.H == 4 * c->ho && g.W == 4 * c->wo)
-          resize_argmax_x4_kernel<<<grid_for(static_cast<size_t>(g.B) * (c->ho + 1) * (c->wo + 1), c->num_sms), 256, 0, st>>>(P);
+          resize_argmax_x4_kernel<<<static_cast<unsigned>((static_cast<size_t>(g.B) * (c->ho + 1) * (c->wo + 1) + 127) / 128), 128, 0, st>>>(P);
         else
           resize_argmax_generic_kernel<<<grid_for(static_cast<size_t>(g.B) * g.H * g.W, c->num_sms), 256, 0, st>>>(P);
         L.end("resize_argmax", cudaGetLastError());
@@ -1475,7 +1507,7 @@ int dlv3p_op_resize_argmax(int device, const float* logits_planar, int B, int NC
   P.logits = logits_planar; P.labels = labels; P.B = B; P.NC = NC; P.hi = hi; P.wi = wi; P.ho = ho; P.wo = wo;
   P.sy = static_cast<float>(hi) / static_cast<float>(ho); P.sx = static_cast<float>(wi) / static_cast<float>(wo);
   if (ho == 4 * hi && wo == 4 * wi)
-    resize_argmax_x4_kernel<<<grid_for(static_cast<size_t>(B) * (hi + 1) * (wi + 1), sms), 256, 0, st>>>(P);
+    resize_argmax_x4_kernel<<<static_cast<unsigned>((static_cast<size_t>(B) * (hi + 1) * (wi + 1) + 127) / 128), 128, 0, st>>>(P);
   else
     resize_argmax_generic_kernel<<<grid_for(static_cast<size_t>(B) * ho * wo, sms), 256, 0, st>>>(P);
   CU_TRY(nullptr, cudaGetLastError());
@@ -1579,7 +1611,7 @@ int dlv3p_op_time(int device, int op, const int64_t* d, int ndims, int iters, in
     P.labels = tmp.alloc<uint8_t>(static_cast<size_t>(P.B) * P.ho * P.wo);
     const bool x4 = P.ho == 4 * P.hi && P.wo == 4 * P.wi && !(flags & 1);
     rc = run([&] {
-      if (x4) resize_argmax_x4_kernel<<<grid_for(static_cast<size_t>(P.B) * (P.hi + 1) * (P.wi + 1), sms), 256, 0, st>>>(P);
+      if (x4) resize_argmax_x4_kernel<<<static_cast<unsigned>((static_cast<size_t>(P.B) * (P.hi + 1) * (P.wi + 1) + 127) / 128), 128, 0, st>>>(P);
       else resize_argmax_generic_kernel<<<grid_for(static_cast<size_t>(P.B) * P.ho * P.wo, sms), 256, 0, st>>>(P);
     });
   } else if (op == 4 && ndims >= 4) {   // ASPP depthwise slab kernel {B,h,w,C} at OS16 rates

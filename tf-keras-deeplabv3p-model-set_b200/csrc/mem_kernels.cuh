@@ -641,7 +641,7 @@ struct ArgmaxParams {
 
 // integer scale S (even): thread = one low-res cell -> an S x 4 strip handled as (S/4) x ... ; specialised S = 4:
 // outputs Y in [4m+2, 4m+6), X in [4k+2, 4k+6) share the corners (m, m+1) x (k, k+1); m, k start at -1.
-__global__ void __launch_bounds__(256) resize_argmax_x4_kernel(const ArgmaxParams P) {
+__global__ void __launch_bounds__(128) resize_argmax_x4_kernel(const ArgmaxParams P) {
   const int cells_x = P.wi + 1, cells_y = P.hi + 1;
   const size_t total = static_cast<size_t>(P.B) * cells_y * cells_x;
   const size_t plane = static_cast<size_t>(P.hi) * P.wi;
@@ -668,12 +668,8 @@ __global__ void __launch_bounds__(256) resize_argmax_x4_kernel(const ArgmaxParam
 #pragma unroll
     for (int i = 0; i < 16; ++i) { best[i] = -INFINITY; arg[i] = 0; }
     const float* lb = P.logits + static_cast<size_t>(b) * P.NC * plane;
-    for (int c = 0; c < P.NC; ++c) {
-      const float* lp = lb + static_cast<size_t>(c) * plane;
-      const float tl = __ldg(lp + static_cast<size_t>(y0) * P.wi + x0);
-      const float tr = __ldg(lp + static_cast<size_t>(y0) * P.wi + x1);
-      const float bl = __ldg(lp + static_cast<size_t>(y1) * P.wi + x0);
-      const float br = __ldg(lp + static_cast<size_t>(y1) * P.wi + x1);
+    const int o00 = y0 * P.wi + x0, o01 = y0 * P.wi + x1, o10 = y1 * P.wi + x0, o11 = y1 * P.wi + x1;
+    auto scan = [&](int c, float tl, float tr, float bl, float br) {
       // a + (b - a) * t with the differences hoisted: the very same rounded operations as lerp_nofma, fewer of them
       const float dtop = __fsub_rn(tr, tl), dbot = __fsub_rn(br, bl);
 #pragma unroll
@@ -687,6 +683,21 @@ __global__ void __launch_bounds__(256) resize_argmax_x4_kernel(const ArgmaxParam
           if (v > best[dy * 4 + dx]) { best[dy * 4 + dx] = v; arg[dy * 4 + dx] = c; }
         }
       }
+    };
+    int c = 0;
+    for (; c + 3 <= P.NC; c += 3) {   // three classes per trip: twelve independent loads in flight
+      float q[3][4];
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const float* lp = lb + static_cast<size_t>(c + u) * plane;
+        q[u][0] = __ldg(lp + o00); q[u][1] = __ldg(lp + o01); q[u][2] = __ldg(lp + o10); q[u][3] = __ldg(lp + o11);
+      }
+#pragma unroll
+      for (int u = 0; u < 3; ++u) scan(c + u, q[u][0], q[u][1], q[u][2], q[u][3]);
+    }
+    for (; c < P.NC; ++c) {
+      const float* lp = lb + static_cast<size_t>(c) * plane;
+      scan(c, __ldg(lp + o00), __ldg(lp + o01), __ldg(lp + o10), __ldg(lp + o11));
     }
     uint8_t* ob = P.labels + static_cast<size_t>(b) * P.ho * P.wo;
 #pragma unroll
