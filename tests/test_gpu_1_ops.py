@@ -91,7 +91,8 @@ def test_resize_bilinear(gpu, B, hi, wi, C, ho, wo):
 
 
 @pytest.mark.parametrize('B,NC,hi,wi,ho,wo', [(2, 21, 128, 128, 512, 512), (1, 19, 25, 19, 100, 76), (1, 21, 32, 32, 512, 512),
-                                               (1, 5, 9, 7, 36, 28), (1, 150, 16, 16, 64, 64), (1, 3, 10, 10, 33, 47), (1, 21, 1, 1, 4, 4)])
+                                               (1, 5, 9, 7, 36, 28), (1, 150, 16, 16, 64, 64), (1, 3, 10, 10, 33, 47), (1, 21, 1, 1, 4, 4),
+                                               (2, 21, 16, 24, 128, 192), (1, 19, 8, 8, 256, 256), (1, 4, 5, 3, 60, 36)])
 def test_resize_argmax_bit_exact(gpu, B, NC, hi, wi, ho, wo):
     """pred_resize + np.argmax (model.py:76, deeplab.py:99): integer output, bit exact incl. first-max ties."""
     rng = np.random.default_rng(NC * hi + wo)

@@ -344,6 +344,21 @@ cudaError_t launch_dwpw(int KB, const DwPwParams& P, const CUtensorMap* tmap_out
   }
 }
 
+int grid_for(size_t items, int num_sms);
+
+// pred_resize + argmax: integer scales that are multiples of 4 share corners per 4x4 output block (mem_kernels.cuh)
+cudaError_t launch_resize_argmax(const ArgmaxParams& P, bool force_generic, int num_sms, cudaStream_t st) {
+  const int S = P.hi > 0 ? P.ho / P.hi : 0;
+  if (!force_generic && S >= 4 && S % 4 == 0 && P.ho == S * P.hi && P.wo == S * P.wi) {
+    ArgmaxIntParams Q{P, S};
+    const size_t threads = static_cast<size_t>(P.B) * (P.hi + 1) * (S / 4) * (P.wi + 1) * (S / 4);
+    resize_argmax_x4_kernel<<<static_cast<unsigned>((threads + 127) / 128), 128, 0, st>>>(Q);
+  } else {
+    resize_argmax_generic_kernel<<<grid_for(static_cast<size_t>(P.B) * P.ho * P.wo, num_sms), 256, 0, st>>>(P);
+  }
+  return cudaGetLastError();
+}
+
 int grid_for(size_t items, int num_sms) {
   size_t g = (items + 255) / 256;
   const size_t cap = static_cast<size_t>(num_sms) * 8;
@@ -1227,11 +1242,7 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
         ArgmaxParams P{};
         P.logits = c->logits; P.labels = static_cast<uint8_t*>(d_out); P.B = g.B; P.NC = g.NC; P.hi = c->ho; P.wi = c->wo;
         P.ho = g.H; P.wo = g.W; P.sy = sy; P.sx = sx;
-        if (g.H == 4 * c->ho && g.W == 4 * c->wo)
-          resize_argmax_x4_kernel<<<static_cast<unsigned>((static_cast<size_t>(g.B) * (c->ho + 1) * (c->wo + 1) + 127) / 128), 128, 0, st>>>(P);
-        else
-          resize_argmax_generic_kernel<<<grid_for(static_cast<size_t>(g.B) * g.H * g.W, c->num_sms), 256, 0, st>>>(P);
-        L.end("resize_argmax", cudaGetLastError());
+        L.end("resize_argmax", launch_resize_argmax(P, false, c->num_sms, st));
       }
     } else if (g.out_mode == DLV3P_OUT_SOFTMAX || g.out_mode == DLV3P_OUT_LOGITS_FULL) {
       if (L.begin("resize_dense")) {
@@ -1506,11 +1517,7 @@ int dlv3p_op_resize_argmax(int device, const float* logits_planar, int B, int NC
   ArgmaxParams P{};
   P.logits = logits_planar; P.labels = labels; P.B = B; P.NC = NC; P.hi = hi; P.wi = wi; P.ho = ho; P.wo = wo;
   P.sy = static_cast<float>(hi) / static_cast<float>(ho); P.sx = static_cast<float>(wi) / static_cast<float>(wo);
-  if (ho == 4 * hi && wo == 4 * wi)
-    resize_argmax_x4_kernel<<<static_cast<unsigned>((static_cast<size_t>(B) * (hi + 1) * (wi + 1) + 127) / 128), 128, 0, st>>>(P);
-  else
-    resize_argmax_generic_kernel<<<grid_for(static_cast<size_t>(B) * ho * wo, sms), 256, 0, st>>>(P);
-  CU_TRY(nullptr, cudaGetLastError());
+  CU_TRY(nullptr, launch_resize_argmax(P, false, sms, st));
   CU_TRY(nullptr, cudaStreamSynchronize(st));
   return DLV3P_OK;
 }
@@ -1609,11 +1616,7 @@ int dlv3p_op_time(int device, int op, const int64_t* d, int ndims, int iters, in
     for (size_t i = 0; i < n; ++i) { sd = sd * 1664525u + 1013904223u; h[i] = static_cast<float>(sd >> 8) / 8388608.0f - 1.0f; }
     P.logits = tmp.put(h);
     P.labels = tmp.alloc<uint8_t>(static_cast<size_t>(P.B) * P.ho * P.wo);
-    const bool x4 = P.ho == 4 * P.hi && P.wo == 4 * P.wi && !(flags & 1);
-    rc = run([&] {
-      if (x4) resize_argmax_x4_kernel<<<static_cast<unsigned>((static_cast<size_t>(P.B) * (P.hi + 1) * (P.wi + 1) + 127) / 128), 128, 0, st>>>(P);
-      else resize_argmax_generic_kernel<<<grid_for(static_cast<size_t>(P.B) * P.ho * P.wo, sms), 256, 0, st>>>(P);
-    });
+    rc = run([&] { launch_resize_argmax(P, (flags & 1) != 0, sms, st); });
   } else if (op == 4 && ndims >= 4) {   // ASPP depthwise slab kernel {B,h,w,C} at OS16 rates
     AsppDwParams P{};
     P.B = static_cast<int>(d[0]); P.h = static_cast<int>(d[1]); P.w_ = static_cast<int>(d[2]); P.C = static_cast<int>(d[3]);

@@ -83,6 +83,22 @@ __device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsign
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+__device__ __forceinline__ unsigned long long fsub2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// Packed product with its OWN rounding.  ptxas contracts `mul.rn.f32x2` + `add.rn.f32x2` into one FFMA2 (single
+// rounding; checked with tools/ubench/contract_check.cu), which would break the oracle's a + (b - a) * t operation
+// order.  fma(a, b, +0) rounds exactly like the product and is not contracted with the following add.
+__device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(0ull));
+  return d;
+}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  return (static_cast<unsigned long long>(__float_as_uint(hi)) << 32) | __float_as_uint(lo);
+}
 
 // kSmem = false: inputs straight from global memory (large maps; every load is a coalesced 128-byte line)
 // kSmem = true : inputs from a shared-memory slab [h*w pixels][64 channels] staged once per (image, chunk)
@@ -600,29 +616,46 @@ __global__ void __launch_bounds__(256) resize_bilinear_x4_kernel(const ResizePar
     const int y0 = max(m, 0), y1 = min(m + 1, P.hi - 1), x0 = max(k, 0), x1 = min(k + 1, P.wi - 1);
     const __nv_bfloat16* xb = P.x + static_cast<size_t>(b) * P.hi * P.wi * P.C;
     for (int vec = lane; vec < vecs; vec += 32) {
-      float tl[8], tr[8], bl[8], br[8];
-      unpack8(ldg_nc_v4(xb + (static_cast<size_t>(y0) * P.wi + x0) * P.C + vec * 8), tl);
-      unpack8(ldg_nc_v4(xb + (static_cast<size_t>(y0) * P.wi + x1) * P.C + vec * 8), tr);
-      unpack8(ldg_nc_v4(xb + (static_cast<size_t>(y1) * P.wi + x0) * P.C + vec * 8), bl);
-      unpack8(ldg_nc_v4(xb + (static_cast<size_t>(y1) * P.wi + x1) * P.C + vec * 8), br);
+      // packed fp32x2 arithmetic (sub / mul / add .rn.f32x2, no FMA): the same rounded operations as lerp_nofma on each
+      // element, half the instructions
+      unsigned long long tl[4], dt[4], bl[4], db[4];
+      {
+        const uint4 a = ldg_nc_v4(xb + (static_cast<size_t>(y0) * P.wi + x0) * P.C + vec * 8);
+        const uint4 bq = ldg_nc_v4(xb + (static_cast<size_t>(y0) * P.wi + x1) * P.C + vec * 8);
+        const uint4 cq = ldg_nc_v4(xb + (static_cast<size_t>(y1) * P.wi + x0) * P.C + vec * 8);
+        const uint4 d = ldg_nc_v4(xb + (static_cast<size_t>(y1) * P.wi + x1) * P.C + vec * 8);
+        const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w}, cv[4] = {cq.x, cq.y, cq.z, cq.w}, dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tl[c] = f32x2_from_bf16x2(av[c]);
+          dt[c] = fsub2(f32x2_from_bf16x2(bv[c]), tl[c]);      // tr - tl
+          bl[c] = f32x2_from_bf16x2(cv[c]);
+          db[c] = fsub2(f32x2_from_bf16x2(dv[c]), bl[c]);      // br - bl
+        }
+      }
 #pragma unroll
       for (int dx = 0; dx < 4; ++dx) {
         const int X = X0 + dx;
         if (X < 0 || X >= P.wo) continue;
-        float top[8], bot[8];
+        const unsigned long long txx = pack2(tx[dx], tx[dx]);
+        unsigned long long top[4], dv[4];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          top[c] = lerp_nofma(tl[c], tr[c], tx[dx]);
-          bot[c] = lerp_nofma(bl[c], br[c], tx[dx]);
+        for (int c = 0; c < 4; ++c) {
+          top[c] = fadd2(tl[c], fmul2(dt[c], txx));
+          const unsigned long long bot = fadd2(bl[c], fmul2(db[c], txx));
+          dv[c] = fsub2(bot, top[c]);
         }
 #pragma unroll
         for (int dy = 0; dy < 4; ++dy) {
           const int Y = Y0 + dy;
           if (Y < 0 || Y >= P.ho) continue;
-          float o[8];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) o[c] = lerp_nofma(top[c], bot[c], ty[dy]);
-          stg_v4(P.out + ((static_cast<size_t>(b) * P.ho + Y) * P.wo + X) * P.ldo + P.col_off + vec * 8, pack8(o));
+          const unsigned long long tyy = pack2(ty[dy], ty[dy]);
+          uint4 o;
+          o.x = f32x2_to_bf16x2(fadd2(top[0], fmul2(dv[0], tyy)));
+          o.y = f32x2_to_bf16x2(fadd2(top[1], fmul2(dv[1], tyy)));
+          o.z = f32x2_to_bf16x2(fadd2(top[2], fmul2(dv[2], tyy)));
+          o.w = f32x2_to_bf16x2(fadd2(top[3], fmul2(dv[3], tyy)));
+          stg_v4(P.out + ((static_cast<size_t>(b) * P.ho + Y) * P.wo + X) * P.ldo + P.col_off + vec * 8, o);
         }
       }
     }
@@ -639,19 +672,28 @@ struct ArgmaxParams {
   float sy, sx;
 };
 
-// integer scale S (even): thread = one low-res cell -> an S x 4 strip handled as (S/4) x ... ; specialised S = 4:
-// outputs Y in [4m+2, 4m+6), X in [4k+2, 4k+6) share the corners (m, m+1) x (k, k+1); m, k start at -1.
-__global__ void __launch_bounds__(128) resize_argmax_x4_kernel(const ArgmaxParams P) {
-  const int cells_x = P.wi + 1, cells_y = P.hi + 1;
-  const size_t total = static_cast<size_t>(P.B) * cells_y * cells_x;
+// integer scale S (multiple of 4; S = 4 for the decoder models, 8 / 16 / 32 for the *_lite models that resize the
+// OS-resolution logits directly): the S x S outputs Y in [S*m + S/2, S*m + 3S/2), X likewise, share the four corner
+// pixels (m, m+1) x (k, k+1) (m, k start at -1).  One thread owns a 4 x 4 block of them: corners loaded once per class,
+// horizontal lerps once per column.
+struct ArgmaxIntParams {
+  ArgmaxParams a;
+  int S;   // ho / hi == wo / wi
+};
+__global__ void __launch_bounds__(128) resize_argmax_x4_kernel(const ArgmaxIntParams Q) {
+  const ArgmaxParams& P = Q.a;
+  const int S = Q.S, sub = S >> 2;
+  const int gx_n = (P.wi + 1) * sub, gy_n = (P.hi + 1) * sub;
+  const size_t total = static_cast<size_t>(P.B) * gy_n * gx_n;
   const size_t plane = static_cast<size_t>(P.hi) * P.wi;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int k = static_cast<int>(idx % cells_x) - 1;
-    size_t r = idx / cells_x;
-    const int m = static_cast<int>(r % cells_y) - 1;
-    const int b = static_cast<int>(r / cells_y);
-    const int X0 = 4 * k + 2, Y0 = 4 * m + 2;
+    const int gx = static_cast<int>(idx % gx_n);
+    size_t r = idx / gx_n;
+    const int gy = static_cast<int>(r % gy_n);
+    const int b = static_cast<int>(r / gy_n);
+    const int k = gx / sub - 1, m = gy / sub - 1;
+    const int X0 = S * k + (S >> 1) + 4 * (gx % sub), Y0 = S * m + (S >> 1) + 4 * (gy % sub);
     // per-output coordinates through the generic formula (bit-identical to the generic kernel / oracle)
     int ylo[4], yhi[4], xlo[4], xhi[4];
     float ty[4], tx[4];
