@@ -1,0 +1,213 @@
+// aspp_dw_gather.cuh — ASPP depthwise kernel for LARGE feature maps (Cityscapes OS8: 128 x 256 map, rates 12/24/36),
+// where neither the whole map (aspp_dw_fast.cuh) nor a halo tile (the halo is the dilation) fits in shared memory.
+//
+// Replaces `aspp{1,2,3}_depthwise` + `_depthwise_BN` + ReLU and the AveragePooling2D partial sums of the image-pooling
+// branch (reference deeplabv3p/models/layers.py:146-153 -> :100-104, :132) in one pass over x per rate.
+//
+// A dilation-r 3x3 conv is r*r independent dense 3x3 convs on the phase images x[pi + r*a, pj + r*t].  A CTA gathers a
+// batch of phase images of one (image, 32-channel group, rate) into shared memory with 16-byte cp.async (zero fill past
+// the map edge = 'same' padding), all loads in flight at once, then half-warps (16 lanes x bf16x2 = the 32 channels) run
+// the dense 3x3 conv on one 8-column segment of one phase image each with a three-row register window: every input is
+// read from HBM once per rate and from shared memory 1.25 times.  Two CTAs per SM overlap one CTA's gather
+// with the others' arithmetic.
+#pragma once
+
+#include "mem_kernels.cuh"
+#include "aspp_dw_fast.cuh"
+
+namespace dlv3p {
+
+constexpr int kGatherThreads = 256;
+constexpr int kGatherTS = 8;                 // output columns per segment
+constexpr int kGatherSmemBudget = 80 * 1024; // phase images per CTA batch (2 CTAs per SM)
+constexpr int kGatherSlack = 512;            // the last segment of the last row reads up to 7 pixels past its image
+constexpr int kGatherSmemBytes = kGatherSmemBudget + (9 * 32 + 32 + 16 * 32) * 4;
+
+struct AsppGatherParams {
+  const __nv_bfloat16* x;   // [B,h,w,C]
+  const float* w;           // [3][9][C]  BN scale folded
+  const float* shift;       // [3][C]
+  __nv_bfloat16* out;       // [3][C/64][B*h*w][64]   (K-block-major, same as the other ASPP depthwise kernels)
+  float* pool_partial;      // [B][pool_slots][C]: one slot per rate-0 batch
+  const uint32_t* batches;  // [num_batches] packed (ri << 28 | nph << 20 | first phase)
+  int B, h, w_, C, nchunks;
+  int rates[3];
+  int na[3], nt[3];         // phase-image extent ceil(h / r), ceil(w / r)
+  int nseg[3];              // ceil(nt / 8)
+  int num_batches;          // per (image, channel group)
+  int pool_slots;           // number of rate-0 batches
+  int debug;
+};
+
+// one (phase image, 8-column segment) on a half-warp.  img = this lane's view of the zero-bordered phase image
+// [na + 2][nt + 2][32 ch] bf16 in shared memory: no bounds checks, every load is base + immediate offset.
+template <int RC>   // RC > 0: the rate as a compile-time constant (divisions and store offsets fold), 0: runtime rate
+__device__ __forceinline__ void aspp_gather_item(const AsppGatherParams& P, const uint8_t* img, int ri, int pi, int pj, int seg,
+                                                 uint8_t* out_lane, const unsigned long long (&wt)[9], unsigned long long sh,
+                                                 unsigned long long& psum) {
+  constexpr int TS = kGatherTS;
+  const int r = RC ? RC : P.rates[ri];
+  const int NA = P.na[ri];
+  const int pitch = (P.nt[ri] + 2) * 64;                 // bytes per padded row
+  const int t0 = seg * TS;
+  const int j0 = pj + r * t0;
+  const int nvalid = j0 < P.w_ ? (P.w_ - j0 + r - 1) / r : 0;   // outputs of this segment that exist (warp-half uniform)
+  const uint8_t* base = img + t0 * 64;                   // padded row 0 (= row -1), padded column t0 (= column t0 - 1)
+  auto load_row = [&](int q, unsigned long long (&row)[TS + 2]) {   // q = -1 .. NA
+    const uint8_t* p = base + (q + 1) * pitch;
+#pragma unroll
+    for (int t = 0; t < TS + 2; ++t) row[t] = f32x2_from_bf16x2(*reinterpret_cast<const uint32_t*>(p + t * 64));
+  };
+  auto emit = [&](int a, const unsigned long long (&top)[TS + 2], const unsigned long long (&mid)[TS + 2],
+                  const unsigned long long (&bot)[TS + 2]) {
+    const int i = pi + r * a;
+    if (i >= P.h) return;
+    uint8_t* orow = out_lane + (static_cast<size_t>(i) * P.w_ + j0) * 128;
+#pragma unroll
+    for (int t = 0; t < TS; ++t) {
+      unsigned long long acc = sh;
+      ffma2_acc(acc, wt[0], top[t]); ffma2_acc(acc, wt[1], top[t + 1]); ffma2_acc(acc, wt[2], top[t + 2]);
+      ffma2_acc(acc, wt[3], mid[t]); ffma2_acc(acc, wt[4], mid[t + 1]); ffma2_acc(acc, wt[5], mid[t + 2]);
+      ffma2_acc(acc, wt[6], bot[t]); ffma2_acc(acc, wt[7], bot[t + 1]); ffma2_acc(acc, wt[8], bot[t + 2]);
+      if (t < nvalid) {
+        if (!(P.debug & 1)) *reinterpret_cast<uint32_t*>(orow + t * r * 128) = f32x2_to_bf16x2_relu(acc);
+        psum = fadd2(psum, mid[t + 1]);
+      }
+    }
+  };
+  unsigned long long ra[TS + 2], rb[TS + 2], rc[TS + 2];
+  load_row(-1, ra);
+  load_row(0, rb);
+  for (int a = 0; a < NA; a += 3) {
+    load_row(a + 1, rc);
+    emit(a, ra, rb, rc);
+    if (a + 1 < NA) {
+      load_row(a + 2, ra);
+      emit(a + 1, rb, rc, ra);
+    }
+    if (a + 2 < NA) {
+      load_row(a + 3, rb);
+      emit(a + 2, rc, ra, rb);
+    }
+  }
+}
+
+template <int RC>
+__device__ __forceinline__ void aspp_gather_body(const AsppGatherParams& P, uint8_t* gather_smem, int batch, int grp, int b, uint32_t e) {
+  uint8_t* s_img = gather_smem;
+  float* s_w = reinterpret_cast<float*>(s_img + kGatherSmemBudget);   // [9][32] taps of this CTA's rate
+  float* s_shift = s_w + 9 * 32;                                       // [32]
+  float* s_red = s_shift + 32;                                         // [16][32]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int hw = lane >> 4, l16 = lane & 15;
+  const int hwid = warp * 2 + hw;                                      // half-warp 0..15
+  const int ri = static_cast<int>(e >> 28), nph = static_cast<int>((e >> 20) & 0xFF), ph0 = static_cast<int>(e & 0xFFFFF);
+  const int r = RC ? RC : P.rates[ri];
+  const int NA = P.na[ri], NT = P.nt[ri];
+  const int rows_per_img = NA + 2, ntp = NT + 2;
+  const int img_bytes = rows_per_img * ntp * 64;
+
+  // ---- gather: a warp per padded image row, lanes over its (pixel, 8-channel quarter) 16-byte chunks; cp.async with
+  //      src-size 0 zero-fills the border and the pixels past the map edge ('same' padding).  No division in the loops:
+  //      (phase, row) advance incrementally, the per-lane column offsets are computed once per phase.
+  {
+    const uint8_t* xb = reinterpret_cast<const uint8_t*>(P.x) + (static_cast<size_t>(b) * P.h * P.w_ * P.C + grp * 32) * 2;
+    const uint32_t px_stride = static_cast<uint32_t>(P.C) * 2;
+    const uint32_t row_stride = static_cast<uint32_t>(P.w_) * px_stride;
+    const int nchunk = ntp * 4;
+    int ph = 0, a = warp - 1;                       // padded row index a + 1 of phase ph
+    while (a > NA) { a -= rows_per_img; ++ph; }
+    int cur_ph = -1, pi = 0;
+    uint32_t coff[4];                               // this lane's chunk offsets within a map row (0xFFFFFFFF: zero fill)
+    while (ph < nph) {
+      if (ph != cur_ph) {
+        cur_ph = ph;
+        const int phase = ph0 + ph;
+        pi = phase / r;
+        const int pj = phase - pi * r;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = lane + 32 * k;
+          const int t = (c >> 2) - 1;
+          const int j = pj + r * t;
+          coff[k] = (c < nchunk && t >= 0 && j < P.w_) ? static_cast<uint32_t>(j) * px_stride + (c & 3) * 16 : 0xFFFFFFFFu;
+        }
+      }
+      const int i = pi + r * a;
+      const bool row_ok = a >= 0 && a < NA && i < P.h;
+      const uint8_t* src_row = xb + static_cast<size_t>(row_ok ? i : 0) * row_stride;
+      const uint32_t dst_row = smem_u32(s_img + ph * img_bytes + (a + 1) * ntp * 64) + lane * 16;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (lane + 32 * k < nchunk) {
+          const bool ok = row_ok && coff[k] != 0xFFFFFFFFu;
+          const uint8_t* src = ok ? src_row + coff[k] : xb;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_row + k * 512), "l"(src), "r"(ok ? 16 : 0) : "memory");
+        }
+      }
+      a += kGatherThreads / 32;
+      while (a > NA) { a -= rows_per_img; ++ph; }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int i = tid; i < 9 * 32; i += kGatherThreads) s_w[i] = __ldg(P.w + (static_cast<size_t>(ri) * 9 + (i >> 5)) * P.C + grp * 32 + (i & 31));
+  if (tid < 32) s_shift[tid] = __ldg(P.shift + static_cast<size_t>(ri) * P.C + grp * 32 + tid);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  unsigned long long wt[9], sh;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float2 v = *reinterpret_cast<const float2*>(s_w + t * 32 + l16 * 2);
+    wt[t] = pack2(v.x, v.y);
+  }
+  {
+    const float2 v = *reinterpret_cast<const float2*>(s_shift + l16 * 2);
+    sh = pack2(v.x, v.y);
+  }
+  uint8_t* out_lane = reinterpret_cast<uint8_t*>(P.out) +
+                      ((static_cast<size_t>(ri) * P.nchunks + (grp >> 1)) * P.B + b) * P.h * P.w_ * 128 + (grp & 1) * 64 + l16 * 4;
+  const int nseg = P.nseg[ri];
+  const int items = nph * nseg;
+  unsigned long long psum = 0ull;
+  for (int it = hwid; it < items; it += 16) {
+    const int ph = it / nseg, seg = it - ph * nseg;
+    const int phase = ph0 + ph;
+    const int pi = phase / r, pj = phase - pi * r;
+    aspp_gather_item<RC>(P, s_img + ph * img_bytes + l16 * 4, ri, pi, pj, seg, out_lane, wt, sh, psum);
+  }
+  // ---- image-pooling partial sums: the rate-0 batches cover every pixel exactly once
+  if (ri == 0) {
+    s_red[hwid * 32 + l16 * 2] = __uint_as_float(static_cast<uint32_t>(psum));
+    s_red[hwid * 32 + l16 * 2 + 1] = __uint_as_float(static_cast<uint32_t>(psum >> 32));
+    __syncthreads();
+    if (tid < 32) {
+      float s = 0.0f;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) s += s_red[q * 32 + tid];
+      P.pool_partial[(static_cast<size_t>(b) * P.pool_slots + batch) * P.C + grp * 32 + tid] = s;   // rate-0 batches come first
+    }
+  }
+}
+
+// grid = B * (C / 32) * num_batches, block 256, dynamic smem = kGatherSmemBytes
+__global__ void __launch_bounds__(kGatherThreads, 2) aspp_dw_gather_kernel(const __grid_constant__ AsppGatherParams P) {
+  extern __shared__ __align__(128) uint8_t gather_smem[];
+  const int ngroups = P.C >> 5;
+  int bid = blockIdx.x;
+  const int batch = bid % P.num_batches; bid /= P.num_batches;
+  const int grp = bid % ngroups;
+  const int b = bid / ngroups;
+  const uint32_t e = __ldg(P.batches + batch);
+  switch (P.rates[e >> 28]) {   // the reference's rates (layers.py:118-125) as compile-time constants, anything else at run time
+    case 6: aspp_gather_body<6>(P, gather_smem, batch, grp, b, e); break;
+    case 12: aspp_gather_body<12>(P, gather_smem, batch, grp, b, e); break;
+    case 18: aspp_gather_body<18>(P, gather_smem, batch, grp, b, e); break;
+    case 24: aspp_gather_body<24>(P, gather_smem, batch, grp, b, e); break;
+    case 36: aspp_gather_body<36>(P, gather_smem, batch, grp, b, e); break;
+    default: aspp_gather_body<0>(P, gather_smem, batch, grp, b, e); break;
+  }
+}
+
+}  // namespace dlv3p

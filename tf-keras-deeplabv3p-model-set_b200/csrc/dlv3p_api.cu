@@ -24,6 +24,7 @@
 #include "pw_gemm.cuh"
 #include "pw_gemm2.cuh"
 #include "aspp_dw_fast.cuh"
+#include "aspp_dw_gather.cuh"
 
 using namespace dlv3p;
 
@@ -266,6 +267,51 @@ bool aspp_fast_supported(const AsppDwParams& P) {
   if (off || P.nrates != 3 || P.C % 32 != 0) return false;
   return P.h == 32 && P.w_ == 32 && P.rates[0] == 6 && P.rates[1] == 12 && P.rates[2] == 18;
 }
+
+// large / odd-sized maps: cp.async gather of phase images (aspp_dw_gather.cuh).  Fills the geometry part of the plan and the
+// batch table; returns false when a phase image does not fit the shared-memory budget (-> generic kernels).
+bool plan_aspp_gather(int h, int w, int C, const int rates[3], AsppGatherParams* G, std::vector<uint32_t>* table) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("DLV3P_NO_ASPP_GATHER"); off = (e && e[0] == '1') ? 1 : 0; }
+  if (off || C % 32 != 0) return false;
+  table->clear();
+  G->pool_slots = 0;
+  for (int i = 0; i < 3; ++i) {
+    const int r = rates[i];
+    G->rates[i] = r;
+    G->na[i] = ceil_div(h, r);
+    G->nt[i] = ceil_div(w, r);
+    G->nseg[i] = ceil_div(G->nt[i], kGatherTS);
+    const int img_bytes = (G->na[i] + 2) * (G->nt[i] + 2) * 64;   // zero-bordered phase image, 32 channels
+    if (img_bytes + kGatherSlack > kGatherSmemBudget || r * r > 0xFFFFF || (G->nt[i] + 2) * 4 > 128) return false;   // <= 4 chunks per lane and row
+    int cap = (kGatherSmemBudget - kGatherSlack) / img_bytes;
+    if (cap > 255) cap = 255;
+    // phases per CTA: the batch that keeps the 16 half-warps busiest (items = phases x column segments), larger on ties
+    int per = 1;
+    double best = 0.0;
+    for (int n = 1; n <= cap; ++n) {
+      const int items = n * G->nseg[i];
+      const double util = static_cast<double>(items) / (16.0 * ceil_div(items, 16));
+      if (util >= best) { best = util; per = n; }
+    }
+    for (int ph = 0; ph < r * r; ph += per) {
+      const int n = r * r - ph < per ? r * r - ph : per;
+      table->push_back((static_cast<uint32_t>(i) << 28) | (static_cast<uint32_t>(n) << 20) | static_cast<uint32_t>(ph));
+      if (i == 0) ++G->pool_slots;
+    }
+  }
+  G->h = h; G->w_ = w; G->C = C; G->nchunks = ceil_div(C, 64);
+  G->num_batches = static_cast<int>(table->size());
+  return true;
+}
+cudaError_t launch_aspp_gather(const AsppGatherParams& G, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(aspp_dw_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmemBytes);
+  if (e != cudaSuccess) return e;
+  const long long blocks = static_cast<long long>(G.B) * (G.C / 32) * G.num_batches;
+  aspp_dw_gather_kernel<<<static_cast<unsigned>(blocks), kGatherThreads, kGatherSmemBytes, st>>>(G);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_aspp_fast(const AsppDwParams& P, cudaStream_t st) {
   return launch_aspp_fast_t<32, 32, 6, 12, 18>(P, st);
 }
@@ -438,6 +484,10 @@ struct dlv3p_ctx {
   AsppDwParams aspp_plan{};
   bool aspp_slab = false;               // small maps: shared-memory slab kernel
   bool aspp_fast = false;               // geometry-specialised kernel (aspp_dw_fast.cuh)
+  bool aspp_gather = false;             // cp.async phase-image gather kernel (aspp_dw_gather.cuh)
+  AsppGatherParams gather_plan{};
+  std::vector<uint32_t> gather_table;
+  uint32_t* gather_table_dev = nullptr;
   size_t aspp_slab_smem = 0;
 
   // packed weights
@@ -742,7 +792,8 @@ int dlv3p_create(const dlv3p_config* cfg, int device, dlv3p_ctx** out) {
       c->aspp_slab_smem = static_cast<size_t>(ceil_div(px, 256)) * 32768 + (27 * 64 + 3 * 64 + 16 * 64) * sizeof(float) + 16;
       c->aspp_slab = c->aspp_slab_smem <= 220 * 1024;
       c->aspp_fast = aspp_fast_supported(A);
-      A.pool_items = c->aspp_slab ? 1 : A.item_off[1];
+      c->aspp_gather = !c->aspp_fast && plan_aspp_gather(c->h, c->w, g.Cin, c->rates, &c->gather_plan, &c->gather_table);
+      A.pool_items = c->aspp_gather ? c->gather_plan.pool_slots : (c->aspp_slab ? 1 : A.item_off[1]);
       A.total_warps = static_cast<long long>(g.B) * A.item_off[3] * A.nchunks;
       c->nbands = A.pool_items;
     }
@@ -876,6 +927,7 @@ int dlv3p_finalize_weights(dlv3p_ctx* c) {
       }
       if ((r = upload(c, &c->aspp_dw_w, dw))) return r;
       if ((r = upload(c, &c->aspp_items, build_aspp_items(c->aspp_plan)))) return r;
+      if (c->aspp_gather && (r = upload(c, &c->gather_table_dev, c->gather_table))) return r;
       if ((r = upload(c, &c->aspp_dw_shift, dsh))) return r;
     }
     {
@@ -1124,6 +1176,12 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
       P.tmap_slab = &c->d_tm[TM_FEAT_SLAB]; P.item_table = c->aspp_items;
       if (c->aspp_fast) {
         cudaError_t e = launch_aspp_fast(P, st);
+        (void)e;
+      } else if (c->aspp_gather) {
+        AsppGatherParams G = c->gather_plan;
+        G.x = feat; G.w = c->aspp_dw_w; G.shift = c->aspp_dw_shift; G.out = c->dw_out; G.pool_partial = c->pool_partial;
+        G.batches = c->gather_table_dev; G.B = g.B;
+        cudaError_t e = launch_aspp_gather(G, st);
         (void)e;
       } else if (c->aspp_slab) {
         cudaError_t e = cudaFuncSetAttribute(aspp_dw_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->aspp_slab_smem));

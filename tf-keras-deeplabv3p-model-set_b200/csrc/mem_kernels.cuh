@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(256) resize_bilinear_kernel(const ResizeParams
 // The 4x4 outputs Y in [4m+2, 4m+6), X in [4k+2, 4k+6) share the four corner pixels (m, m+1) x (k, k+1): corners are
 // loaded and unpacked once, the horizontal lerps once per column.  Same operations in the same order as the generic
 // kernel / the oracle (top/bottom lerp, then vertical), so the result is bit identical.
-__global__ void __launch_bounds__(256) resize_bilinear_x4_kernel(const ResizeParams P) {
+__global__ void __launch_bounds__(256, 2) resize_bilinear_x4_kernel(const ResizeParams P) {
   const int cells_x = P.wi + 1, cells_y = P.hi + 1;
   const int total = P.B * cells_y * cells_x;
   const int lane = threadIdx.x & 31;
