@@ -54,6 +54,31 @@ HBM_BYTES_PER_IMG = {
 }
 
 
+# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum, MB) from one `ncu --set full` capture of this
+# very command at batch 32 (profiles/r01b_ncu_full_step_summary.csv): the `traffic` field of the roofline line.
+NCU_DRAM_MB_PER_LAUNCH_B32 = {
+    'decoder_conv0_sepconv': 318.99 + 228.08,
+    'decoder_conv1_sepconv': 268.62 + 223.52,
+    'aspp_dw_pool': 135.89 + 348.99,
+    'aspp_branches_gemm': 541.19 + 14.41,
+    'concat_projection_gemm': 67.69 + 2.37,
+    'feature_projection0_gemm': 268.96 + 26.32,
+    'classifier_gemm': 268.48 + 8.03,
+    'decoder_resize': 16.90 + 225.32,
+    'resize_argmax': 44.06 + 0.10,
+    'pool_proj': 1.46,
+}
+
+
+# algorithmic HBM bytes per image of the fused SepConv kernels (read the input once, write the 256-channel output once)
+ALGO_BYTES_PER_IMG = {
+    'decoder_conv0_sepconv': 16384 * 304 * 2 + 16384 * 256 * 2,
+    'decoder_conv1_sepconv': 16384 * 256 * 2 + 16384 * 256 * 2,
+    'aspp_branches_gemm': 4 * 1024 * 2048 * 2 + 4 * 1024 * 256 * 2,
+    'concat_projection_gemm': 1024 * 1024 * 2 + 1024 * 256 * 2,
+}
+
+
 def load_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -281,6 +306,12 @@ def main():
             ach = byt / (prof[dom] / 1000.0) / 1e9
             roof = {'kernel': dom, 'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / peaks['hbm_gbs'],
                     'traffic': None, 'peak_source': peaks['src']}
+        if B == CFG['B'] and not args.unfused and dom in NCU_DRAM_MB_PER_LAUNCH_B32:
+            roof['traffic'] = NCU_DRAM_MB_PER_LAUNCH_B32[dom] * 1e6
+            roof['traffic_unit'] = 'bytes per launch (ncu dram read+write, profiles/r01b_ncu_full_step_summary.csv)'
+            roof['algorithmic_bytes'] = (HBM_BYTES_PER_IMG.get(dom) or ALGO_BYTES_PER_IMG.get(dom, 0)) * B
+            roof['dram_gbs'] = roof['traffic'] / (prof[dom] / 1000.0) / 1e9          # second roof of the fused kernels: HBM
+            roof['dram_frac_of_hbm_peak'] = roof['dram_gbs'] / peaks['hbm_gbs']
         roof['kernel_ms'] = prof[dom]
         roof['share_of_step'] = prof[dom] / step_ms_prof
         gemm_flop = sum(GEMM_FLOP_PER_IMG[k] for k in prof if k in GEMM_FLOP_PER_IMG) * B
