@@ -139,7 +139,10 @@ int dlv3p_forward(dlv3p_ctx* ctx, const void* d_feat, const void* d_skip, void* 
                   void* cuda_stream);
 
 /* Same call with HOST buffers (pageable or pinned): H2D copies, forward, D2H copy, and a
- * stream synchronize — the end-to-end path model.predict()+np.argmax takes (deeplab.py:96-99). */
+ * stream synchronize — the end-to-end path model.predict()+np.argmax takes (deeplab.py:96-99).
+ * Batches of 8 or more (divisible by 4) are pipelined in four sub-batches over two internal contexts so the H2D
+ * copy of one sub-batch overlaps the kernels of the previous one (pinned buffers needed for the overlap; images are
+ * independent, the result is identical).  dlv3p_read_tap then still refers to the last dlv3p_forward. */
 int dlv3p_forward_host(dlv3p_ctx* ctx, const void* h_feat, const void* h_skip, void* h_out);
 
 int dlv3p_input_bytes(const dlv3p_ctx* ctx, size_t* feat_bytes, size_t* skip_bytes);

@@ -99,6 +99,21 @@ def test_forward_host_equals_device_forward_and_is_deterministic(gpu):
     hd.close()
 
 
+def test_forward_host_pipeline_equals_device_forward(gpu):
+    """B >= 8: dlv3p_forward_host runs four sub-batches on two child contexts (H2D of one overlaps the kernels of the
+    previous); images are independent, so the labels must equal one full-batch device forward bit for bit."""
+    cfg = R.HeadConfig(B=8, H=128, W=128, OS=16, Cin=256, Cskip=64, NC=21)
+    W = R.make_weights(cfg, 11)
+    feat, skip = R.make_inputs(cfg, 12)
+    hd = make_head(cfg, W)
+    a = hd(feat, skip)
+    b = hd.predict_host(feat, skip)
+    c = hd.predict_host(feat, skip)
+    assert np.array_equal(a, b) and np.array_equal(b, c)
+    assert hd.ctx.launch_count()[0] >= 4 * 9       # four sub-batch forwards
+    hd.close()
+
+
 def test_block_level_layers(gpu):
     """ASPP_block / Decoder_block as separate drop-in objects (layers.py:114, :199) chained by the caller."""
     import dlv3p_b200

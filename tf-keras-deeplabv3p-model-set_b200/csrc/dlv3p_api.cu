@@ -468,6 +468,8 @@ struct dlv3p_ctx {
   size_t ws_bytes = 0;
   __nv_bfloat16 *feat_bf16 = nullptr, *skip_bf16 = nullptr;  // cast targets / forward_host staging
   void *in_feat_stage = nullptr, *in_skip_stage = nullptr;   // forward_host raw staging (in_dtype)
+  dlv3p_ctx* pipe[2] = {nullptr, nullptr};                   // forward_host pipeline: two quarter-batch child contexts
+  bool pipe_failed = false;
   void* out_stage = nullptr;
   __nv_bfloat16* dw_out = nullptr;     // [3][Cin/64][M1][64]  K-block-major
   float* pool_partial = nullptr;       // [B][nbands][Cin]
@@ -852,6 +854,7 @@ void dlv3p_destroy(dlv3p_ctx* c) {
   for (cudaEvent_t ev : {c->ev_fork, c->ev_dw, c->ev_pool, c->ev_fp0})
     if (ev) cudaEventDestroy(ev);
   for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
+  for (dlv3p_ctx* ch : c->pipe) dlv3p_destroy(ch);
   delete c;
 }
 
@@ -1336,18 +1339,72 @@ int dlv3p_forward(dlv3p_ctx* c, const void* d_feat, const void* d_skip, void* d_
   return forward_impl(c, d_feat, d_skip, d_out, static_cast<cudaStream_t>(cuda_stream));
 }
 
+// forward_host pipeline: the step is PCIe bound (inputs are ~50x the device time), so the batch goes through in
+// kPipeChunks sub-batches on two child contexts (own stream, own staging, own workspace, same weights): the H2D copy of
+// chunk i+1 overlaps the kernels of chunk i and the D2H of chunk i-1.  Images are independent, so the result is the
+// same as one full-batch forward (tests/test_gpu_2_head.py).
+constexpr int kPipeChunks = 4;
+static int make_pipe_children(dlv3p_ctx* c) {
+  dlv3p_config cfg = c->cfg;
+  cfg.B = c->cfg.B / kPipeChunks;
+  for (int k = 0; k < 2; ++k) {
+    dlv3p_ctx* ch = nullptr;
+    int r = dlv3p_create(&cfg, c->device, &ch);
+    if (r) return r;
+    c->pipe[k] = ch;
+    for (const WeightSlot& w : c->weights)
+      if ((r = dlv3p_set_weight(ch, w.layer.c_str(), w.var.c_str(), w.data.data(), w.shape.data(), static_cast<int>(w.shape.size())))) return r;
+    if ((r = dlv3p_finalize_weights(ch))) return r;
+    size_t fb = 0, sb = 0, ob = 0;
+    dlv3p_input_bytes(ch, &fb, &sb);
+    if ((r = dlv3p_output_bytes(ch, &ob))) return r;
+    if (cudaMalloc(&ch->in_feat_stage, fb) != cudaSuccess || (sb && cudaMalloc(&ch->in_skip_stage, sb) != cudaSuccess) ||
+        cudaMalloc(&ch->out_stage, ob) != cudaSuccess)
+      return DLV3P_ERR_NOMEM;
+  }
+  return DLV3P_OK;
+}
+
 int dlv3p_forward_host(dlv3p_ctx* c, const void* h_feat, const void* h_skip, void* h_out) {
   if (!c || !h_feat || !h_out) return fail(c, DLV3P_ERR_INVALID, "null argument");
   if (c->plan_only) return fail(c, DLV3P_ERR_STATE, "plan-only context (device -1): there is no CPU path");
+  if (!c->finalized) return fail(c, DLV3P_ERR_STATE, "dlv3p_finalize_weights has not been called");
   CU_TRY(c, cudaSetDevice(c->device));
   size_t fb = 0, sb = 0, ob = 0;
   dlv3p_input_bytes(c, &fb, &sb);
   int r = dlv3p_output_bytes(c, &ob);
   if (r) return r;
+  if (sb && !h_skip) return fail(c, DLV3P_ERR_INVALID, "decoder stage needs the skip feature");
+
+  static int no_pipe = -1;
+  if (no_pipe < 0) { const char* e = getenv("DLV3P_NO_HOST_PIPELINE"); no_pipe = (e && e[0] == '1') ? 1 : 0; }
+  if (!no_pipe && !c->pipe_failed && c->cfg.B >= 2 * kPipeChunks && c->cfg.B % kPipeChunks == 0) {
+    if (!c->pipe[0] && make_pipe_children(c) != DLV3P_OK) {   // e.g. out of memory: fall back to the one-shot path below
+      for (dlv3p_ctx*& ch : c->pipe) { dlv3p_destroy(ch); ch = nullptr; }
+      c->pipe_failed = true;
+      CU_TRY(c, cudaSetDevice(c->device));
+    }
+    if (c->pipe[0]) {
+      const size_t cf = fb / kPipeChunks, cs = sb / kPipeChunks, co = ob / kPipeChunks;
+      for (int i = 0; i < kPipeChunks; ++i) {
+        dlv3p_ctx* ch = c->pipe[i & 1];
+        cudaStream_t st = ch->own_stream;   // chunk i-2 on this child is ordered before chunk i by the stream
+        CU_TRY(c, cudaMemcpyAsync(ch->in_feat_stage, static_cast<const char*>(h_feat) + i * cf, cf, cudaMemcpyHostToDevice, st));
+        if (sb) CU_TRY(c, cudaMemcpyAsync(ch->in_skip_stage, static_cast<const char*>(h_skip) + i * cs, cs, cudaMemcpyHostToDevice, st));
+        r = forward_impl(ch, ch->in_feat_stage, sb ? ch->in_skip_stage : nullptr, ch->out_stage, st);
+        if (r) return fail(c, r, ch->err);
+        CU_TRY(c, cudaMemcpyAsync(static_cast<char*>(h_out) + i * co, ch->out_stage, co, cudaMemcpyDeviceToHost, st));
+      }
+      CU_TRY(c, cudaStreamSynchronize(c->pipe[0]->own_stream));
+      CU_TRY(c, cudaStreamSynchronize(c->pipe[1]->own_stream));
+      c->launches_last = kPipeChunks * c->pipe[0]->launches_last;
+      c->launches_total += c->launches_last;
+      return DLV3P_OK;
+    }
+  }
   if (!c->in_feat_stage) CU_TRY(c, cudaMalloc(&c->in_feat_stage, fb));
   if (sb && !c->in_skip_stage) CU_TRY(c, cudaMalloc(&c->in_skip_stage, sb));
   if (!c->out_stage) CU_TRY(c, cudaMalloc(&c->out_stage, ob));
-  if (sb && !h_skip) return fail(c, DLV3P_ERR_INVALID, "decoder stage needs the skip feature");
   cudaStream_t st = c->own_stream;
   CU_TRY(c, cudaMemcpyAsync(c->in_feat_stage, h_feat, fb, cudaMemcpyHostToDevice, st));
   if (sb) CU_TRY(c, cudaMemcpyAsync(c->in_skip_stage, h_skip, sb, cudaMemcpyHostToDevice, st));
