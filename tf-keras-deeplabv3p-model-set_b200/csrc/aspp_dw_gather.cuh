@@ -5,12 +5,16 @@
 // branch (reference deeplabv3p/models/layers.py:146-153 -> :100-104, :132) in one pass over x per rate.
 //
 // A dilation-r 3x3 conv is r*r independent dense 3x3 convs on the phase images x[pi + r*a, pj + r*t].  A CTA gathers a
-// batch of phase images of one (image, 32-channel group, rate) into shared memory with 16-byte cp.async (zero fill past
-// the map edge = 'same' padding), all loads in flight at once, then half-warps (16 lanes x bf16x2 = the 32 channels) run
+// batch of phase images of one (image, 32-channel group, rate) into shared memory — ONE TMA load per phase image
+// through a per-phase strided tensor map {C, ceil((w-pj)/r), ceil((h-pi)/r), B} (box origin (-1,-1): the zero border and
+// everything past the map edge is TMA zero fill = 'same' padding); a 16-byte cp.async gather of the same data is limited
+// by the SM's outstanding-request capacity (1.41 ms at cfg 3 vs the TMA's in-flight depth).  Half-warps (16 lanes x bf16x2 = the 32 channels) then run
 // the dense 3x3 conv on one 8-column segment of one phase image each with a three-row register window: every input is
 // read from HBM once per rate and from shared memory 1.25 times.  Two CTAs per SM overlap one CTA's gather
 // with the others' arithmetic.
 #pragma once
+
+#include <cuda.h>
 
 #include "mem_kernels.cuh"
 #include "aspp_dw_fast.cuh"
@@ -18,10 +22,8 @@
 namespace dlv3p {
 
 constexpr int kGatherThreads = 256;
-constexpr int kGatherTS = 8;                 // output columns per segment
 constexpr int kGatherSmemBudget = 80 * 1024; // phase images per CTA batch (2 CTAs per SM)
-constexpr int kGatherSlack = 512;            // the last segment of the last row reads up to 7 pixels past its image
-constexpr int kGatherSmemBytes = kGatherSmemBudget + (9 * 32 + 32 + 16 * 32) * 4;
+constexpr int kGatherSmemBytes = kGatherSmemBudget + (9 * 32 + 32 + 16 * 32) * 4 + 16;
 
 struct AsppGatherParams {
   const __nv_bfloat16* x;   // [B,h,w,C]
@@ -30,28 +32,32 @@ struct AsppGatherParams {
   __nv_bfloat16* out;       // [3][C/64][B*h*w][64]   (K-block-major, same as the other ASPP depthwise kernels)
   float* pool_partial;      // [B][pool_slots][C]: one slot per rate-0 batch
   const uint32_t* batches;  // [num_batches] packed (ri << 28 | nph << 20 | first phase)
+  const CUtensorMap* maps;  // [sum r*r] per-phase tensor maps over x, rate-major (device memory)
+  int map_off[3];           // first map of each rate
   int B, h, w_, C, nchunks;
   int rates[3];
   int na[3], nt[3];         // phase-image extent ceil(h / r), ceil(w / r)
-  int nseg[3];              // ceil(nt / 8)
+  int ts[3];                // output columns per segment: 8 or 6, whichever wastes fewer columns of nt
+  int nseg[3];              // ceil(nt / ts)
   int num_batches;          // per (image, channel group)
   int pool_slots;           // number of rate-0 batches
   int debug;
 };
 
-// one (phase image, 8-column segment) on a half-warp.  img = this lane's view of the zero-bordered phase image
-// [na + 2][nt + 2][32 ch] bf16 in shared memory: no bounds checks, every load is base + immediate offset.
-template <int RC>   // RC > 0: the rate as a compile-time constant (divisions and store offsets fold), 0: runtime rate
+// one (phase image, TS-column segment) on a half-warp.  img = this lane's view of the zero-bordered phase image
+// [na + 2][nseg * TS + 2][32 ch] bf16 in shared memory: no bounds checks, every load is base + immediate offset, and
+// everything past the map edge reads as zero (so the pooling sum needs no mask and only the store is predicated).
+template <int RC, int TS>   // RC > 0: the rate as a compile-time constant (divisions and store offsets fold), 0: runtime rate
 __device__ __forceinline__ void aspp_gather_item(const AsppGatherParams& P, const uint8_t* img, int ri, int pi, int pj, int seg,
                                                  uint8_t* out_lane, const unsigned long long (&wt)[9], unsigned long long sh,
                                                  unsigned long long& psum) {
-  constexpr int TS = kGatherTS;
   const int r = RC ? RC : P.rates[ri];
   const int NA = P.na[ri];
-  const int pitch = (P.nt[ri] + 2) * 64;                 // bytes per padded row
+  const int pitch = (P.nseg[ri] * TS + 2) * 64;          // bytes per padded row
   const int t0 = seg * TS;
   const int j0 = pj + r * t0;
-  const int nvalid = j0 < P.w_ ? (P.w_ - j0 + r - 1) / r : 0;   // outputs of this segment that exist (warp-half uniform)
+  int nvalid = j0 < P.w_ ? (P.w_ - j0 + r - 1) / r : 0;  // outputs of this segment that exist (uniform per half-warp)
+  if (P.debug & 1) nvalid = 0;
   const uint8_t* base = img + t0 * 64;                   // padded row 0 (= row -1), padded column t0 (= column t0 - 1)
   auto load_row = [&](int q, unsigned long long (&row)[TS + 2]) {   // q = -1 .. NA
     const uint8_t* p = base + (q + 1) * pitch;
@@ -61,7 +67,7 @@ __device__ __forceinline__ void aspp_gather_item(const AsppGatherParams& P, cons
   auto emit = [&](int a, const unsigned long long (&top)[TS + 2], const unsigned long long (&mid)[TS + 2],
                   const unsigned long long (&bot)[TS + 2]) {
     const int i = pi + r * a;
-    if (i >= P.h) return;
+    const int nv = i < P.h ? nvalid : 0;                 // rows past the map: zero inputs, nothing stored
     uint8_t* orow = out_lane + (static_cast<size_t>(i) * P.w_ + j0) * 128;
 #pragma unroll
     for (int t = 0; t < TS; ++t) {
@@ -69,10 +75,8 @@ __device__ __forceinline__ void aspp_gather_item(const AsppGatherParams& P, cons
       ffma2_acc(acc, wt[0], top[t]); ffma2_acc(acc, wt[1], top[t + 1]); ffma2_acc(acc, wt[2], top[t + 2]);
       ffma2_acc(acc, wt[3], mid[t]); ffma2_acc(acc, wt[4], mid[t + 1]); ffma2_acc(acc, wt[5], mid[t + 2]);
       ffma2_acc(acc, wt[6], bot[t]); ffma2_acc(acc, wt[7], bot[t + 1]); ffma2_acc(acc, wt[8], bot[t + 2]);
-      if (t < nvalid) {
-        if (!(P.debug & 1)) *reinterpret_cast<uint32_t*>(orow + t * r * 128) = f32x2_to_bf16x2_relu(acc);
-        psum = fadd2(psum, mid[t + 1]);
-      }
+      psum = fadd2(psum, mid[t + 1]);
+      if (t < nv) *reinterpret_cast<uint32_t*>(orow + t * r * 128) = f32x2_to_bf16x2_relu(acc);
     }
   };
   unsigned long long ra[TS + 2], rb[TS + 2], rc[TS + 2];
@@ -105,56 +109,27 @@ __device__ __forceinline__ void aspp_gather_body(const AsppGatherParams& P, uint
   const int ri = static_cast<int>(e >> 28), nph = static_cast<int>((e >> 20) & 0xFF), ph0 = static_cast<int>(e & 0xFFFFF);
   const int r = RC ? RC : P.rates[ri];
   const int NA = P.na[ri], NT = P.nt[ri];
-  const int rows_per_img = NA + 2, ntp = NT + 2;
+  const int ts = P.ts[ri];
+  const int rows_per_img = NA + 2, ntp = P.nseg[ri] * ts + 2;   // padded so that every segment's window stays inside its row
   const int img_bytes = rows_per_img * ntp * 64;
 
-  // ---- gather: a warp per padded image row, lanes over its (pixel, 8-channel quarter) 16-byte chunks; cp.async with
-  //      src-size 0 zero-fills the border and the pixels past the map edge ('same' padding).  No division in the loops:
-  //      (phase, row) advance incrementally, the per-lane column offsets are computed once per phase.
-  {
-    const uint8_t* xb = reinterpret_cast<const uint8_t*>(P.x) + (static_cast<size_t>(b) * P.h * P.w_ * P.C + grp * 32) * 2;
-    const uint32_t px_stride = static_cast<uint32_t>(P.C) * 2;
-    const uint32_t row_stride = static_cast<uint32_t>(P.w_) * px_stride;
-    const int nchunk = ntp * 4;
-    int ph = 0, a = warp - 1;                       // padded row index a + 1 of phase ph
-    while (a > NA) { a -= rows_per_img; ++ph; }
-    int cur_ph = -1, pi = 0;
-    uint32_t coff[4];                               // this lane's chunk offsets within a map row (0xFFFFFFFF: zero fill)
-    while (ph < nph) {
-      if (ph != cur_ph) {
-        cur_ph = ph;
-        const int phase = ph0 + ph;
-        pi = phase / r;
-        const int pj = phase - pi * r;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int c = lane + 32 * k;
-          const int t = (c >> 2) - 1;
-          const int j = pj + r * t;
-          coff[k] = (c < nchunk && t >= 0 && j < P.w_) ? static_cast<uint32_t>(j) * px_stride + (c & 3) * 16 : 0xFFFFFFFFu;
-        }
-      }
-      const int i = pi + r * a;
-      const bool row_ok = a >= 0 && a < NA && i < P.h;
-      const uint8_t* src_row = xb + static_cast<size_t>(row_ok ? i : 0) * row_stride;
-      const uint32_t dst_row = smem_u32(s_img + ph * img_bytes + (a + 1) * ntp * 64) + lane * 16;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (lane + 32 * k < nchunk) {
-          const bool ok = row_ok && coff[k] != 0xFFFFFFFFu;
-          const uint8_t* src = ok ? src_row + coff[k] : xb;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_row + k * 512), "l"(src), "r"(ok ? 16 : 0) : "memory");
-        }
-      }
-      a += kGatherThreads / 32;
-      while (a > NA) { a -= rows_per_img; ++ph; }
+  // ---- gather: one TMA load per phase image, all in flight at once
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_red + 16 * 32);
+  if (tid == 0) {
+    mbar_init(s_bar, 1);
+    fence_barrier_init();
+    if (!(P.debug & 4)) {   // debug bit 2: no gather (stale shared memory)
+      mbar_arrive_expect_tx(s_bar, static_cast<uint32_t>(nph * img_bytes));
+      const CUtensorMap* m = P.maps + P.map_off[ri] + ph0;
+      for (int ph = 0; ph < nph; ++ph) tma_load_4d(s_img + ph * img_bytes, m + ph, s_bar, grp * 32, -1, -1, b, kEvictNormal);
+    } else {
+      mbar_arrive(s_bar);
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
   }
   for (int i = tid; i < 9 * 32; i += kGatherThreads) s_w[i] = __ldg(P.w + (static_cast<size_t>(ri) * 9 + (i >> 5)) * P.C + grp * 32 + (i & 31));
   if (tid < 32) s_shift[tid] = __ldg(P.shift + static_cast<size_t>(ri) * P.C + grp * 32 + tid);
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
+  mbar_wait(s_bar, 0);
 
   unsigned long long wt[9], sh;
 #pragma unroll
@@ -171,11 +146,12 @@ __device__ __forceinline__ void aspp_gather_body(const AsppGatherParams& P, uint
   const int nseg = P.nseg[ri];
   const int items = nph * nseg;
   unsigned long long psum = 0ull;
-  for (int it = hwid; it < items; it += 16) {
+  for (int it = hwid; it < items && !(P.debug & 2); it += 16) {   // debug bit 1: gather only
     const int ph = it / nseg, seg = it - ph * nseg;
     const int phase = ph0 + ph;
     const int pi = phase / r, pj = phase - pi * r;
-    aspp_gather_item<RC>(P, s_img + ph * img_bytes + l16 * 4, ri, pi, pj, seg, out_lane, wt, sh, psum);
+    if (ts == 8) aspp_gather_item<RC, 8>(P, s_img + ph * img_bytes + l16 * 4, ri, pi, pj, seg, out_lane, wt, sh, psum);
+    else aspp_gather_item<RC, 6>(P, s_img + ph * img_bytes + l16 * 4, ri, pi, pj, seg, out_lane, wt, sh, psum);
   }
   // ---- image-pooling partial sums: the rate-0 batches cover every pixel exactly once
   if (ri == 0) {

@@ -281,10 +281,13 @@ bool plan_aspp_gather(int h, int w, int C, const int rates[3], AsppGatherParams*
     G->rates[i] = r;
     G->na[i] = ceil_div(h, r);
     G->nt[i] = ceil_div(w, r);
-    G->nseg[i] = ceil_div(G->nt[i], kGatherTS);
-    const int img_bytes = (G->na[i] + 2) * (G->nt[i] + 2) * 64;   // zero-bordered phase image, 32 channels
-    if (img_bytes + kGatherSlack > kGatherSmemBudget || r * r > 0xFFFFF || (G->nt[i] + 2) * 4 > 128) return false;   // <= 4 chunks per lane and row
-    int cap = (kGatherSmemBudget - kGatherSlack) / img_bytes;
+    G->ts[i] = ceil_div(G->nt[i], 6) * 6 < ceil_div(G->nt[i], 8) * 8 ? 6 : 8;   // fewer padded columns wins, 8 on ties
+    G->nseg[i] = ceil_div(G->nt[i], G->ts[i]);
+    const int ntp = G->nseg[i] * G->ts[i] + 2;
+    const int img_bytes = (G->na[i] + 2) * ntp * 64;   // zero-bordered phase image, 32 channels
+    if (img_bytes > kGatherSmemBudget || r * r > 0xFFFFF || ntp > 256 || G->na[i] + 2 > 256 || r > h || r > w) return false;   // TMA box limits; every phase has pixels
+    G->map_off[i] = i == 0 ? 0 : G->map_off[i - 1] + rates[i - 1] * rates[i - 1];
+    int cap = kGatherSmemBudget / img_bytes;
     if (cap > 255) cap = 255;
     // phases per CTA: the batch that keeps the 16 half-warps busiest (items = phases x column segments), larger on ties
     int per = 1;
@@ -302,6 +305,37 @@ bool plan_aspp_gather(int h, int w, int C, const int rates[3], AsppGatherParams*
   }
   G->h = h; G->w_ = w; G->C = C; G->nchunks = ceil_div(C, 64);
   G->num_batches = static_cast<int>(table->size());
+  return true;
+}
+
+// per-phase strided tensor maps of the gather kernel over x [B,h,w,C]: {C, ceil((w-pj)/r), ceil((h-pi)/r), B}, element
+// (c, t, a, b) = x[b, pi + r*a, pj + r*t, c]; box {32, ntp, na+2, 1} is one zero-bordered phase image of a 32-channel group
+bool encode_gather_maps(const AsppGatherParams& G, const void* x, int B, std::vector<CUtensorMap>* maps, std::string* err) {
+  EncodeTiledFn fn = get_encode_fn(err);
+  if (!fn) return false;
+  maps->clear();
+  const uint64_t C = static_cast<uint64_t>(G.C), W = static_cast<uint64_t>(G.w_), H = static_cast<uint64_t>(G.h);
+  for (int i = 0; i < 3; ++i) {
+    const int r = G.rates[i];
+    const uint32_t ntp = static_cast<uint32_t>(G.nseg[i] * G.ts[i] + 2);
+    for (int ph = 0; ph < r * r; ++ph) {
+      const int pi = ph / r, pj = ph % r;
+      CUtensorMap tm;
+      cuuint64_t gdim[4] = {C, (W - pj + r - 1) / r, (H - pi + r - 1) / r, static_cast<cuuint64_t>(B)};
+      cuuint64_t gstride[3] = {static_cast<cuuint64_t>(r) * C * 2, static_cast<cuuint64_t>(r) * W * C * 2, H * W * C * 2};
+      cuuint32_t box[4] = {32, ntp, static_cast<cuuint32_t>(G.na[i] + 2), 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      const char* base = static_cast<const char*>(x) + (static_cast<uint64_t>(pi) * W + pj) * C * 2;
+      CUresult rc = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(base), gdim, gstride, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (rc != CUDA_SUCCESS) {
+        if (err) *err = fmt("cuTensorMapEncodeTiled(gather rate %d phase %d) -> %d", r, ph, (int)rc);
+        return false;
+      }
+      maps->push_back(tm);
+    }
+  }
   return true;
 }
 cudaError_t launch_aspp_gather(const AsppGatherParams& G, cudaStream_t st) {
@@ -490,6 +524,8 @@ struct dlv3p_ctx {
   AsppGatherParams gather_plan{};
   std::vector<uint32_t> gather_table;
   uint32_t* gather_table_dev = nullptr;
+  CUtensorMap* gather_maps_dev = nullptr;   // per-phase tensor maps over the feature buffer (re-encoded when the pointer changes)
+  const void* gather_maps_ptr = nullptr;
   size_t aspp_slab_smem = 0;
 
   // packed weights
@@ -1184,6 +1220,16 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
         AsppGatherParams G = c->gather_plan;
         G.x = feat; G.w = c->aspp_dw_w; G.shift = c->aspp_dw_shift; G.out = c->dw_out; G.pool_partial = c->pool_partial;
         G.batches = c->gather_table_dev; G.B = g.B;
+        if (c->gather_maps_ptr != feat) {   // per-phase tensor maps follow the feature buffer (one-time for a fixed buffer)
+          std::vector<CUtensorMap> maps;
+          if (!encode_gather_maps(G, feat, g.B, &maps, &terr)) return fail(c, DLV3P_ERR_CUDA, terr);
+          if (!c->gather_maps_dev && dev_alloc(c, &c->gather_maps_dev, maps.size())) return DLV3P_ERR_NOMEM;
+          CU_TRY(c, cudaMemcpyAsync(c->gather_maps_dev, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
+          CU_TRY(c, cudaStreamSynchronize(st));   // the host vector goes away
+          c->gather_maps_ptr = feat;
+        }
+        G.maps = c->gather_maps_dev;
+        { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DLV3P_ASPP_DEBUG"); dbg = e ? atoi(e) : 0; } G.debug = dbg; }   // attribution runs only
         cudaError_t e = launch_aspp_gather(G, st);
         (void)e;
       } else if (c->aspp_slab) {
