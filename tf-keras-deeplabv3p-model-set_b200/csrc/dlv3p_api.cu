@@ -462,7 +462,7 @@ struct WeightSlot {
 enum TmSlot {
   TM_FEAT = 0, TM_DW1, TM_DW2, TM_DW3, TM_CONCAT, TM_SKIP, TM_DECIN, TM_DEC0, TM_CLS_IN,
   TM_W_ASPP0, TM_W_ASPP1, TM_W_ASPP2, TM_W_ASPP3, TM_W_PROJ, TM_W_FP0, TM_W_DEC0, TM_W_DEC1, TM_W_CLS,
-  TM_O_ASPP0, TM_O_ASPP1, TM_O_ASPP2, TM_O_ASPP3, TM_O_PROJ, TM_O_FP0, TM_O_DEC0, TM_O_DEC1, TM_FEAT_SLAB, TM_O4_DEC0, TM_O4_DEC1, TM_O4S_DEC0, TM_O4S_DEC1,
+  TM_O_ASPP0, TM_O_ASPP1, TM_O_ASPP2, TM_O_ASPP3, TM_O_PROJ, TM_O_FP0, TM_O_DEC0, TM_O_DEC1, TM_FEAT_SLAB, TM_O4_DEC0, TM_O4_DEC1, TM_O4S_DEC0, TM_O4S_DEC1, TM_DECSKIP,
   TM_COUNT
 };
 
@@ -511,7 +511,9 @@ struct dlv3p_ctx {
   float* b4 = nullptr;                 // [B][256]
   __nv_bfloat16* concat = nullptr;     // [M1][Ccat]
   __nv_bfloat16* aspp_out = nullptr;   // [M1][256]
-  __nv_bfloat16* dec_in = nullptr;     // [M2][304]
+  __nv_bfloat16* dec_in = nullptr;     // [M2][304]  (unfused decoder only)
+  __nv_bfloat16* dec_up = nullptr;     // [M2][256]  upsampled ASPP output   } the decoder concat of the fused path: two tensors,
+  __nv_bfloat16* dec_skip = nullptr;   // [M2][64]   projected skip (48 valid) } full-line rows, no 608-byte pitch
   __nv_bfloat16* dec_tmp = nullptr;    // [M2][304]  (unfused path: depthwise output)
   __nv_bfloat16* dec0 = nullptr;       // [M2][256]
   __nv_bfloat16* dec1 = nullptr;       // [M2][256]
@@ -848,7 +850,13 @@ int dlv3p_create(const dlv3p_config* cfg, int device, dlv3p_ctx** out) {
     if (g.in_dtype == DLV3P_DTYPE_FP32 && (r = dev_alloc(c, &c->feat_bf16, static_cast<size_t>(c->M1) * g.Cin))) return bail(r, c->err);
   }
   if (c->st_dec) {
-    if ((r = dev_alloc(c, &c->dec_in, static_cast<size_t>(c->M2) * 304))) return bail(r, c->err);
+    if (g.flags & DLV3P_FLAG_UNFUSED_DECODER) {
+      if ((r = dev_alloc(c, &c->dec_in, static_cast<size_t>(c->M2) * 304))) return bail(r, c->err);
+    } else {
+      if ((r = dev_alloc(c, &c->dec_up, static_cast<size_t>(c->M2) * 256))) return bail(r, c->err);
+      if ((r = dev_alloc(c, &c->dec_skip, static_cast<size_t>(c->M2) * 64))) return bail(r, c->err);
+      if (!c->plan_only && cudaMemset(c->dec_skip, 0, static_cast<size_t>(c->M2) * 64 * 2) != cudaSuccess) return bail(DLV3P_ERR_CUDA, "cudaMemset failed");
+    }
     if ((g.flags & DLV3P_FLAG_UNFUSED_DECODER) && (r = dev_alloc(c, &c->dec_tmp, static_cast<size_t>(c->M2) * 304))) return bail(r, c->err);
     if ((r = dev_alloc(c, &c->dec0, static_cast<size_t>(c->M2) * 256))) return bail(r, c->err);
     if ((r = dev_alloc(c, &c->dec1, static_cast<size_t>(c->M2) * 256))) return bail(r, c->err);
@@ -1031,7 +1039,9 @@ int dlv3p_finalize_weights(dlv3p_ctx* c) {
     ok = ok && enc2(TM_W_FP0, c->pw_fp0.w, c->pw_fp0.Npad, c->pw_fp0.Kpad, c->pw_fp0.Kpad, w_box_rows(c->pw_fp0.Npad));
     ok = ok && enc2(TM_W_DEC0, c->pw_dec0.w, 256, c->pw_dec0.Kpad, c->pw_dec0.Kpad, w_box_rows(256));
     ok = ok && enc2(TM_W_DEC1, c->pw_dec1.w, 256, c->pw_dec1.Kpad, c->pw_dec1.Kpad, w_box_rows(256));
-    ok = ok && encode_2d_out(&c->h_tm[TM_O_FP0], c->dec_in + 256, c->M2, 48, 304, &terr);
+    const bool split_concat = !(g.flags & DLV3P_FLAG_UNFUSED_DECODER);
+    ok = ok && (split_concat ? encode_2d_out(&c->h_tm[TM_O_FP0], c->dec_skip, c->M2, 48, 64, &terr)
+                             : encode_2d_out(&c->h_tm[TM_O_FP0], c->dec_in + 256, c->M2, 48, 304, &terr));
     ok = ok && encode_2d_out(&c->h_tm[TM_O_DEC0], c->dec0, c->M2, 256, 256, &terr);
     ok = ok && encode_2d_out(&c->h_tm[TM_O_DEC1], c->dec1, c->M2, 256, 256, &terr);
     ok = ok && encode_4d_out(&c->h_tm[TM_O4_DEC0], c->dec0, g.B, c->hs, c->ws, 256, &terr);
@@ -1042,7 +1052,8 @@ int dlv3p_finalize_weights(dlv3p_ctx* c) {
       ok = ok && enc2(TM_DECIN, c->dec_tmp, c->M2, 304, 304, 128);
       ok = ok && enc2(TM_DEC0, c->dec_tmp, c->M2, 256, 256, 128);
     } else {
-      ok = ok && encode_4d_halo(&c->h_tm[TM_DECIN], c->dec_in, g.B, c->hs, c->ws, 304, 304, kDwHaloW, kDwHaloH, &terr);
+      ok = ok && encode_4d_halo(&c->h_tm[TM_DECIN], c->dec_up, g.B, c->hs, c->ws, 256, 256, kDwHaloW, kDwHaloH, &terr);
+      ok = ok && encode_4d_halo(&c->h_tm[TM_DECSKIP], c->dec_skip, g.B, c->hs, c->ws, 48, 64, kDwHaloW, kDwHaloH, &terr);
       ok = ok && encode_4d_halo(&c->h_tm[TM_DEC0], c->dec0, g.B, c->hs, c->ws, 256, 256, kDwHaloW, kDwHaloH, &terr);
     }
     if (c->skip_bf16) {
@@ -1188,7 +1199,8 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
       PwProblem& p = PL.prob[0];
       p.tmap_a = &c->d_tm[TM_SKIP]; p.tmap_w = &c->d_tm[TM_W_FP0]; p.tmap_out = &c->d_tm[TM_O_FP0];
       p.scale = c->pw_fp0.scale; p.shift = c->pw_fp0.shift; p.img_shift = nullptr;
-      p.out = c->dec_in; p.K = g.Cskip; p.N = 48; p.ldo = 304; p.col_off = 256; p.relu = 1; p.epi = kEpiBf16;
+      const bool split = !(g.flags & DLV3P_FLAG_UNFUSED_DECODER);
+      p.out = split ? c->dec_skip : c->dec_in; p.K = g.Cskip; p.N = 48; p.ldo = split ? 64 : 304; p.col_off = split ? 0 : 256; p.relu = 1; p.epi = kEpiBf16;
       L.end("feature_projection0_gemm", launch_pw(64, PL, c->num_sms, s_));
     }
   };
@@ -1287,8 +1299,9 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
   if (c->st_dec) {
     if (L.begin("decoder_resize")) {
       ResizeParams P{};
-      P.x = x256; P.out = c->dec_in; P.B = g.B; P.hi = c->h; P.wi = c->w; P.C = 256; P.ho = c->hs; P.wo = c->ws;
-      P.ldo = 304; P.col_off = 0;
+      const bool split = !(g.flags & DLV3P_FLAG_UNFUSED_DECODER);
+      P.x = x256; P.out = split ? c->dec_up : c->dec_in; P.B = g.B; P.hi = c->h; P.wi = c->w; P.C = 256; P.ho = c->hs; P.wo = c->ws;
+      P.ldo = split ? 256 : 304; P.col_off = 0;
       P.sy = static_cast<float>(c->h) / static_cast<float>(c->hs); P.sx = static_cast<float>(c->w) / static_cast<float>(c->ws);
       if (c->hs == 4 * c->h && c->ws == 4 * c->w)
         resize_bilinear_x4_kernel<<<grid_for(static_cast<size_t>(g.B) * (c->h + 1) * (c->w + 1) * 32, c->num_sms), 256, 0, st>>>(P);
@@ -1323,6 +1336,7 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
       } else if (L.begin(s.name)) {
         DwPwParams P{};
         P.tmap_x = &c->d_tm[s.tm_x]; P.tmap_w = &c->d_tm[s.tm_w];
+        if (s.tm_x == TM_DECIN) { P.tmap_x2 = &c->d_tm[TM_DECSKIP]; P.kb_split = 4; }   // conv0: K blocks 0-3 upsampled ASPP, block 4 projected skip
         P.dw_w = s.dw->w; P.dw_shift = s.dw->shift; P.scale = s.pw->scale; P.shift = s.pw->shift; P.out = s.out;
         P.tmap_out = &c->d_tm[s.tm_o == TM_O_DEC0 ? TM_O4_DEC0 : TM_O4_DEC1];
         P.B = g.B; P.H = c->hs; P.W = c->ws; P.tiles_x = tiles_x; P.tiles_y = tiles_y; P.num_tiles = g.B * tiles_x * tiles_y;
@@ -1509,6 +1523,18 @@ int dlv3p_read_tap(dlv3p_ctx* c, const char* name, float* host_out, size_t host_
     return DLV3P_OK;
   }
   else if (n == "decoder_in" && c->dec_in) { src = c->dec_in; elems = static_cast<size_t>(c->M2) * 304; }
+  else if (n == "decoder_in" && c->dec_up) {   // fused path: the concat exists as two tensors
+    elems = static_cast<size_t>(c->M2) * 304;
+    if (host_elems < elems) return fail(c, DLV3P_ERR_INVALID, "tap buffer too small");
+    std::vector<uint16_t> up(static_cast<size_t>(c->M2) * 256), sk(static_cast<size_t>(c->M2) * 64);
+    CU_TRY(c, cudaMemcpy(up.data(), c->dec_up, up.size() * 2, cudaMemcpyDeviceToHost));
+    CU_TRY(c, cudaMemcpy(sk.data(), c->dec_skip, sk.size() * 2, cudaMemcpyDeviceToHost));
+    for (int m = 0; m < c->M2; ++m) {
+      for (int j = 0; j < 256; ++j) host_out[static_cast<size_t>(m) * 304 + j] = bf16_to_f32(up[static_cast<size_t>(m) * 256 + j]);
+      for (int j = 0; j < 48; ++j) host_out[static_cast<size_t>(m) * 304 + 256 + j] = bf16_to_f32(sk[static_cast<size_t>(m) * 64 + j]);
+    }
+    return DLV3P_OK;
+  }
   else if (n == "decoder_conv0" && c->dec0) { src = c->dec0; elems = static_cast<size_t>(c->M2) * 256; }
   else if (n == "decoder_out" && c->dec1) { src = c->dec1; elems = static_cast<size_t>(c->M2) * 256; }
   else if (n == "logits" && c->logits) { src = c->logits; elems = static_cast<size_t>(c->cfg.B) * c->cfg.NC * c->ho * c->wo; is_f32 = true; }

@@ -32,6 +32,9 @@ constexpr int kDwBN = 256;
 
 struct DwPwParams {
   const CUtensorMap* tmap_x;  // 4D {C, W, H, B} bf16, box {64, 18, 10, 1}, no swizzle
+  const CUtensorMap* tmap_x2; // optional second input tensor (same geometry): K blocks kb >= kb_split come from it at channel
+                              // (kb - kb_split) * 64 — the decoder concat [upsampled ASPP | projected skip] without a concat buffer
+  int kb_split;
   const CUtensorMap* tmap_w;  // 2D [256, KB*64] bf16 K-major, box {64, 128}, SWIZZLE_128B
   const float* dw_w;          // [9][KB*64] fp32 depthwise taps with the BN scale folded in, zero padded
   const float* dw_shift;      // [KB*64]    fp32 depthwise BN shift, zero padded
@@ -146,8 +149,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) dwpw_gemm_kernel(const __grid_c
           const uint32_t ph = (c / kDwInStages) & 1;
           mbar_wait(&in_empty[si], ph ^ 1);
           mbar_arrive_expect_tx(&in_full[si], kDwInStageBytes);
-          tma_load_4d(smem_in + si * kDwInStageBytes, P.tmap_x, &in_full[si], kb * 64, tx * kDwTW - 1,
-                      ty * kDwTH - 1, b, kEvictNormal);
+          const bool second = P.tmap_x2 != nullptr && kb >= P.kb_split;
+          tma_load_4d(smem_in + si * kDwInStageBytes, second ? P.tmap_x2 : P.tmap_x, &in_full[si], (second ? kb - P.kb_split : kb) * 64,
+                      tx * kDwTW - 1, ty * kDwTH - 1, b, kEvictNormal);
         }
       }
     }

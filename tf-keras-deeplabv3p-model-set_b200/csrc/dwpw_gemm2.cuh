@@ -132,7 +132,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDw2Threads, 1) dwpw
             continue;
           }
           mbar_arrive_expect_tx(&in_full[si], kDwInStageBytes);
-          tma_load_4d(smem_in + si * kDwInStageBytes, P.tmap_x, &in_full[si], kb * 64, tx * kDwTW - 1, ty * kDwTH - 1, b, kEvictNormal);
+          const bool second = P.tmap_x2 != nullptr && kb >= P.kb_split;
+          tma_load_4d(smem_in + si * kDwInStageBytes, second ? P.tmap_x2 : P.tmap_x, &in_full[si], (second ? kb - P.kb_split : kb) * 64,
+                      tx * kDwTW - 1, ty * kDwTH - 1, b, kEvictNormal);
         }
       }
     }
