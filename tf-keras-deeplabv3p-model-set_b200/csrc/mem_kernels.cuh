@@ -711,19 +711,29 @@ __global__ void __launch_bounds__(128) resize_argmax_x4_kernel(const ArgmaxIntPa
     for (int i = 0; i < 16; ++i) { best[i] = -INFINITY; arg[i] = 0; }
     const float* lb = P.logits + static_cast<size_t>(b) * P.NC * plane;
     const int o00 = y0 * P.wi + x0, o01 = y0 * P.wi + x1, o10 = y1 * P.wi + x0, o11 = y1 * P.wi + x1;
+    // a + (b - a) * t with the differences hoisted — the very same rounded operations as lerp_nofma — on packed fp32
+    // pairs (two columns / two rows per instruction; fmul2 = fma(a, b, +0) so ptxas cannot contract it with the add)
+    const unsigned long long tx01 = pack2(tx[0], tx[1]), tx23 = pack2(tx[2], tx[3]);
+    const unsigned long long ty01 = pack2(ty[0], ty[1]), ty23 = pack2(ty[2], ty[3]);
     auto scan = [&](int c, float tl, float tr, float bl, float br) {
-      // a + (b - a) * t with the differences hoisted: the very same rounded operations as lerp_nofma, fewer of them
       const float dtop = __fsub_rn(tr, tl), dbot = __fsub_rn(br, bl);
+      const unsigned long long tl2 = pack2(tl, tl), bl2 = pack2(bl, bl), dt2 = pack2(dtop, dtop), db2 = pack2(dbot, dbot);
+      unsigned long long top2[2], dv2[2];
+      top2[0] = fadd2(tl2, fmul2(dt2, tx01));
+      top2[1] = fadd2(tl2, fmul2(dt2, tx23));
+      dv2[0] = fsub2(fadd2(bl2, fmul2(db2, tx01)), top2[0]);
+      dv2[1] = fsub2(fadd2(bl2, fmul2(db2, tx23)), top2[1]);
 #pragma unroll
       for (int dx = 0; dx < 4; ++dx) {
-        const float top = __fadd_rn(tl, __fmul_rn(dtop, tx[dx]));
-        const float bot = __fadd_rn(bl, __fmul_rn(dbot, tx[dx]));
-        const float dv = __fsub_rn(bot, top);
+        const float top = __uint_as_float(static_cast<uint32_t>(top2[dx >> 1] >> ((dx & 1) * 32)));
+        const float dv = __uint_as_float(static_cast<uint32_t>(dv2[dx >> 1] >> ((dx & 1) * 32)));
+        const unsigned long long t2 = pack2(top, top), d2 = pack2(dv, dv);
+        const unsigned long long v01 = fadd2(t2, fmul2(d2, ty01)), v23 = fadd2(t2, fmul2(d2, ty23));
+        const float v[4] = {__uint_as_float(static_cast<uint32_t>(v01)), __uint_as_float(static_cast<uint32_t>(v01 >> 32)),
+                            __uint_as_float(static_cast<uint32_t>(v23)), __uint_as_float(static_cast<uint32_t>(v23 >> 32))};
 #pragma unroll
-        for (int dy = 0; dy < 4; ++dy) {
-          const float v = __fadd_rn(top, __fmul_rn(dv, ty[dy]));
-          if (v > best[dy * 4 + dx]) { best[dy * 4 + dx] = v; arg[dy * 4 + dx] = c; }
-        }
+        for (int dy = 0; dy < 4; ++dy)
+          if (v[dy] > best[dy * 4 + dx]) { best[dy * 4 + dx] = v[dy]; arg[dy * 4 + dx] = c; }
       }
     };
     int c = 0;
