@@ -1,0 +1,111 @@
+"""keras_bridge: reading the head's configuration and weights off a reference tf.keras model BY LAYER NAME.
+TensorFlow is not installable here, so the model is a duck-typed stub with the reference's layer names, variable names
+('<layer>/<var>:0') and HWIO shapes (SURVEY.md §8(b) weight-layout contract)."""
+import numpy as np
+import pytest
+
+from oracle import head_ref as R
+from tests.common import make_head
+
+
+class _Var:
+    def __init__(self, name, a):
+        self.name, self._a, self.shape = name, a, a.shape
+
+    def numpy(self):
+        return self._a
+
+
+class _Tensor:
+    def __init__(self, shape):
+        self.shape = list(shape)
+
+
+class _Layer:
+    def __init__(self, name, weights, in_shape=None):
+        self.name, self.weights = name, weights
+        self.input = _Tensor(in_shape) if in_shape else None
+
+
+class StubKerasModel:
+    """get_layer(name) over the head layers of get_deeplabv3p_model (model.py:51-117); raises ValueError like Keras."""
+
+    def __init__(self, cfg, W, classifier_name='conv_upsample', scope=''):
+        self.input = _Tensor([None, cfg.H, cfg.W, 3])
+        self.layers = {}
+        byl = {}
+        for (layer, var), a in W.items():
+            byl.setdefault(layer, []).append(_Var('%s%s/%s:0' % (scope, layer, var), np.asarray(a, np.float32)))
+        for layer, ws in byl.items():
+            name = classifier_name if layer == 'conv_upsample' else layer
+            in_shape = None
+            if layer == 'aspp0':
+                in_shape = [None, cfg.h, cfg.w, cfg.Cin]
+            elif layer == 'feature_projection0':
+                in_shape = [None, cfg.hs, cfg.ws, cfg.Cskip]
+            self.layers[name] = _Layer(name, ws, in_shape)
+
+    def get_layer(self, name):
+        if name not in self.layers:
+            raise ValueError('No such layer: %s' % name)
+        return self.layers[name]
+
+
+CASES = [dict(B=2, H=128, W=128, OS=16, Cin=256, Cskip=64, NC=21),
+         dict(B=1, H=128, W=96, OS=8, Cin=64, Cskip=24, NC=19),
+         dict(B=1, H=128, W=128, OS=16, Cin=160, Cskip=24, NC=21, lite=True, decoder=False)]
+
+
+@pytest.mark.parametrize('kw', CASES)
+def test_describe_head_reads_the_configuration(kw):
+    from dlv3p_b200 import keras_bridge as kb
+    cfg = R.HeadConfig(**kw)
+    d = kb.describe_head(StubKerasModel(cfg, R.make_weights(cfg, 3)))
+    assert (d['H'], d['W'], d['h'], d['w'], d['Cin'], d['NC'], d['OS']) == (cfg.H, cfg.W, cfg.h, cfg.w, cfg.Cin, cfg.NC, cfg.OS)
+    assert d['lite'] == cfg.lite and d['decoder'] == cfg.decoder
+    if cfg.decoder:
+        assert (d['hs'], d['ws'], d['Cskip']) == (cfg.hs, cfg.ws, cfg.Cskip)
+
+
+@pytest.mark.parametrize('classifier_name,scope', [('conv_upsample', ''), ('logits_semantic', 'model_1/')])
+def test_weights_are_read_by_layer_name(classifier_name, scope):
+    import dlv3p_b200
+    from dlv3p_b200 import keras_bridge as kb
+    cfg = R.HeadConfig(**CASES[0])
+    W = R.make_weights(cfg, 5)
+    model = StubKerasModel(cfg, W, classifier_name, scope)
+    plan = dlv3p_b200.DeepLabHead(cfg.B, cfg.H, cfg.W, cfg.OS, cfg.Cin, cfg.Cskip, cfg.NC, device=-1)   # plan-only: no GPU needed
+    got = kb.head_weights_from_keras(model, plan)
+    assert set(got) == set(W)
+    for k in W:
+        assert np.array_equal(got[k], np.asarray(W[k], np.float32))
+    # error behaviour: a missing layer / variable / wrong shape is reported by name
+    del model.layers['aspp2_pointwise_BN']
+    with pytest.raises(KeyError, match='aspp2_pointwise_BN'):
+        kb.head_weights_from_keras(model, plan)
+    plan.close()
+
+
+def test_not_a_deeplab_model_is_rejected():
+    from dlv3p_b200 import keras_bridge as kb
+
+    class Empty:
+        input = _Tensor([None, 64, 64, 3])
+
+        def get_layer(self, name):
+            raise ValueError(name)
+    with pytest.raises(ValueError, match='aspp0'):
+        kb.describe_head(Empty())
+
+
+@pytest.mark.gpu
+def test_head_from_keras_equals_direct_head(gpu):
+    from dlv3p_b200 import keras_bridge as kb
+    cfg = R.HeadConfig(**CASES[0])
+    W = R.make_weights(cfg, 9)
+    feat, skip = R.make_inputs(cfg, 10)
+    a = make_head(cfg, W)(feat, skip)
+    hd = kb.head_from_keras(StubKerasModel(cfg, W, 'logits_semantic'), batch=cfg.B)
+    b = hd.predict_host(feat, skip)                # fp32 features in, as a TF backbone would hand them over
+    assert np.array_equal(a, b)
+    hd.close()

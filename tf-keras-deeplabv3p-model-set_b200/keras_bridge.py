@@ -1,0 +1,135 @@
+"""Bridge from a reference tf.keras DeepLabV3+ model to the B200 head — the reference-side binding of INTEGRATION.md
+as a module.  TensorFlow is OPTIONAL and imported lazily: everything except `accelerate()` only needs an object that
+quacks like a Keras model (`get_layer(name)`, layer `.weights` with `.name` / `.numpy()`, `.input.shape`), which is what
+the unit tests use (TensorFlow is not installable in this image).
+
+The reference model object stays untouched: `model.load_weights(path, by_name=False)` (model.py:102-103),
+`load_model(..., custom_objects=get_custom_objects())` (eval.py:566-571) and every tool that addresses layers by name
+keep working, because the head's weights are READ from the reference's own layers by name:
+
+    model = get_deeplabv3p_model(...); model.load_weights('xception.h5')         # reference code, unchanged
+    fast = dlv3p_b200.keras_bridge.accelerate(model, batch=32)                    # backbone stays in TF
+    labels = fast(images)                                                          # uint8 [B,H,W] == np.argmax(model.predict(images), -1)
+
+The head's inputs are found structurally, not per backbone: `aspp0` consumes the ASPP input (layers.py:141) and
+`feature_projection0` consumes the skip feature (layers.py:209) in every constructor of deeplabv3p/models/.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from . import ffi
+from .head import DeepLabHead
+
+_CLASSIFIER_NAMES = ('conv_upsample', 'logits_semantic')   # model.py:75 / deeplabv3p_xception.py:218
+
+
+def _var_basename(name: str) -> str:
+    """'decoder_conv0_depthwise/depthwise_kernel:0' -> 'depthwise_kernel' (TF1/TF2 scopes, optional ':0')."""
+    return name.split('/')[-1].split(':')[0]
+
+
+def _get_layer(model, name: str):
+    try:
+        return model.get_layer(name)
+    except (ValueError, KeyError):
+        return None
+
+
+def _static_shape(t) -> Tuple[int, ...]:
+    shp = getattr(t, 'shape', t)
+    shp = shp.as_list() if hasattr(shp, 'as_list') else list(shp)
+    return tuple(-1 if d is None else int(d) for d in shp)
+
+
+def describe_head(model) -> Dict[str, object]:
+    """Read the head's configuration off a reference model: which variant was built and with which static shapes
+    (the reference requires static spatial shapes too: layers.py:129, :205)."""
+    aspp0 = _get_layer(model, 'aspp0')
+    if aspp0 is None:
+        raise ValueError('not a DeepLabV3+ model of the reference: no layer named aspp0')
+    cls = next((l for l in (_get_layer(model, n) for n in _CLASSIFIER_NAMES) if l is not None), None)
+    if cls is None:
+        raise ValueError('no classifier layer (conv_upsample / logits_semantic)')
+    fshape = _static_shape(aspp0.input)
+    in_shape = _static_shape(model.input)
+    fp0 = _get_layer(model, 'feature_projection0')
+    cfg = {
+        'H': in_shape[1], 'W': in_shape[2], 'h': fshape[1], 'w': fshape[2], 'Cin': fshape[3],
+        'lite': _get_layer(model, 'aspp1_depthwise') is None,          # ASPP_Lite_block has no atrous branches (layers.py:166-196)
+        'decoder': fp0 is not None,
+        'NC': _static_shape(next(w for w in cls.weights if _var_basename(w.name) == 'kernel'))[-1],
+        'classifier_layer': cls.name,
+    }
+    if min(cfg['H'], cfg['W'], cfg['h'], cfg['w']) <= 0:
+        raise ValueError('the head needs static spatial shapes (so does the reference: layers.py:129, :205)')
+    cfg['OS'] = cfg['H'] // cfg['h']
+    if cfg['decoder']:
+        sshape = _static_shape(fp0.input)
+        cfg.update(hs=sshape[1], ws=sshape[2], Cskip=sshape[3])
+    else:
+        cfg.update(hs=0, ws=0, Cskip=0)
+    return cfg
+
+
+def head_weights_from_keras(model, head: DeepLabHead) -> Dict[Tuple[str, str], np.ndarray]:
+    """{(layer, var): fp32 array} for every weight the head declares, read from the reference model BY LAYER NAME."""
+    out = {}
+    for layer, var, shape in head.weight_specs():
+        names = _CLASSIFIER_NAMES if layer == 'conv_upsample' else (layer,)
+        kl = next((l for l in (_get_layer(model, n) for n in names) if l is not None), None)
+        if kl is None:
+            raise KeyError('the model has no layer named %s' % layer)
+        found = next((w for w in kl.weights if _var_basename(w.name) == var), None)
+        if found is None:
+            raise KeyError('layer %s has no variable %s (has: %s)' % (layer, var, [_var_basename(w.name) for w in kl.weights]))
+        a = np.asarray(found.numpy(), np.float32)
+        if tuple(a.shape) != tuple(shape):
+            raise ValueError('%s/%s has shape %s, the head expects %s' % (layer, var, a.shape, tuple(shape)))
+        out[(layer, var)] = a
+    return out
+
+
+def head_from_keras(model, batch: int, device: int = 0, out_mode: int = ffi.OUT_LABELS_U8,
+                    in_dtype: int = ffi.DTYPE_FP32) -> DeepLabHead:
+    """Build a libdlv3p context for the head of `model` and load the model's own head weights into it.
+    in_dtype defaults to fp32 because that is what a TF backbone hands over; the cast to bf16 happens on the device."""
+    d = describe_head(model)
+    head = DeepLabHead(batch, d['H'], d['W'], d['OS'], d['Cin'], d['Cskip'], d['NC'], lite=d['lite'], decoder=d['decoder'],
+                       out_mode=out_mode, in_dtype=in_dtype, device=device, h=d['h'], w=d['w'], hs=d['hs'], ws=d['ws'])
+    head.set_weights(head_weights_from_keras(model, head))
+    return head
+
+
+class AcceleratedDeepLab:
+    """`model.predict` + `np.argmax` (deeplab.py:96-99) with the head on libdlv3p: the backbone runs in TensorFlow up to
+    the two tensors the head consumes, the rest is one dlv3p_forward_host call."""
+
+    def __init__(self, backbone, head: DeepLabHead, decoder: bool):
+        self.backbone, self.head, self.decoder = backbone, head, decoder
+
+    def __call__(self, images: np.ndarray) -> np.ndarray:
+        feats = self.backbone(images, training=False)
+        if self.decoder:
+            feat, skip = (np.ascontiguousarray(t.numpy(), np.float32) for t in feats)
+            return self.head.predict_host(feat, skip)
+        feat = feats[0] if isinstance(feats, (list, tuple)) else feats
+        return self.head.predict_host(np.ascontiguousarray(feat.numpy(), np.float32))
+
+    predict = __call__
+
+
+def accelerate(model, batch: int, device: int = 0, out_mode: int = ffi.OUT_LABELS_U8) -> AcceleratedDeepLab:
+    """Needs TensorFlow (the reference's own dependency): splits `model` at the head's inputs."""
+    try:
+        import tensorflow as tf   # noqa: WPS433 (optional dependency, imported where it is needed)
+    except ImportError as e:       # pragma: no cover - TensorFlow is absent from this image
+        raise ImportError('accelerate() runs the backbone in TensorFlow; use head_from_keras() / DeepLabHead without it') from e
+    d = describe_head(model)
+    outs = [model.get_layer('aspp0').input]
+    if d['decoder']:
+        outs.append(model.get_layer('feature_projection0').input)
+    backbone = tf.keras.Model(model.input, outs, name='dlv3p_backbone')
+    return AcceleratedDeepLab(backbone, head_from_keras(model, batch, device=device, out_mode=out_mode), d['decoder'])
