@@ -346,8 +346,17 @@ cudaError_t launch_aspp_gather(const AsppGatherParams& G, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+template <int H, int W, int R>
+cudaError_t launch_aspp_fast3_t(const AsppDwParams& P, cudaStream_t st) {
+  using Cfg = AsppFast3Cfg<H, W, R>;
+  cudaError_t e = cudaFuncSetAttribute(aspp_dw_fast3_kernel<H, W, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  aspp_dw_fast3_kernel<H, W, R><<<P.B * (P.C / 32), Cfg::kThreads, Cfg::kSmemBytes, st>>>(P);
+  return cudaGetLastError();
+}
 cudaError_t launch_aspp_fast(const AsppDwParams& P, cudaStream_t st) {
-  return launch_aspp_fast_t<32, 32, 6, 12, 18>(P, st);
+  if (P.debug & 16) return launch_aspp_fast_t<32, 32, 6, 12, 18>(P, st);   // A/B: one phase image per rate
+  return launch_aspp_fast3_t<32, 32, 6>(P, st);                            // one phase image for the three rates (r, 2r, 3r)
 }
 
 cudaError_t launch_pw(int BN, const PwLaunch& L, int num_sms, cudaStream_t st) {
