@@ -198,6 +198,7 @@ def main():
     ap.add_argument('--batch', type=int, default=CFG['B'], help='per-GPU batch (default: the BASELINE config)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--unfused', action='store_true', help='A/B: standalone decoder depthwise kernels')
+    ap.add_argument('--strong', action='store_true', help='strong scaling: the global batch stays --batch, each rank takes batch / N images')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -228,6 +229,8 @@ def main():
         torch.cuda.synchronize()
 
     B = args.batch
+    if args.strong:   # fixed global batch, contiguous shards (sizes differ by at most one image)
+        B = max(1, dlv3p_b200.sharding.shard_batch(args.batch, world, rank)[1])
     flags = ffi.FLAG_UNFUSED_DECODER if args.unfused else 0
     head = dlv3p_b200.DeepLabHead(B, CFG['H'], CFG['W'], CFG['OS'], CFG['Cin'], CFG['Cskip'], CFG['NC'], device=local_rank, flags=flags)
     head.set_weights(random_weights(head.weight_specs()))
@@ -293,7 +296,7 @@ def main():
 
     if rank == 0:
         peaks = load_peaks()
-        value = dlv3p_b200.sharding.aggregate_throughput(B, args.steps, world, ms)
+        value = (args.batch * args.steps / (ms / 1000.0)) if args.strong else dlv3p_b200.sharding.aggregate_throughput(B, args.steps, world, ms)
         # dominant kernel and its roofline
         dom = max(prof, key=prof.get)
         step_ms_prof = sum(prof.values())
@@ -326,9 +329,9 @@ def main():
             kernels[k] = d
         line = {
             'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong' if args.strong else 'weak', 'vs_baseline': None, 'dtype': 'bf16',
             'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'batch_per_gpu': B, 'global_batch': B * world, 'sharding': 'batch (independent images, no collective)',
+            'config': {'workload': WORKLOAD, 'batch_per_gpu': B, 'global_batch': args.batch if args.strong else B * world, 'sharding': 'batch (independent images, no collective)',
                        'l2': 'inputs 402 MB/step per GPU > 126 MB L2 (no flush needed)', 'decoder': 'unfused' if args.unfused else 'fused'},
             'e2e': {'value': B * world * e2e_steps / (e2e_ms / 1000.0), 'unit': 'images/s', 'h2d_bytes_per_step': fb + sb,
                     'd2h_bytes_per_step': ob, 'steps': e2e_steps, 'labels_equal_device_path': labels_ok},
