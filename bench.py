@@ -55,17 +55,17 @@ HBM_BYTES_PER_IMG = {
 
 
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum, MB) from one `ncu --set full` capture of this
-# very command at batch 32 (profiles/r01b_ncu_full_step_summary.csv): the `traffic` field of the roofline line.
+# very command at batch 32 (profiles/r01c_ncu_full_step_summary.csv): the `traffic` field of the roofline line.
 NCU_DRAM_MB_PER_LAUNCH_B32 = {
-    'decoder_conv0_sepconv': 318.99 + 228.08,
-    'decoder_conv1_sepconv': 268.62 + 223.52,
-    'aspp_dw_pool': 135.89 + 348.99,
-    'aspp_branches_gemm': 541.19 + 14.41,
-    'concat_projection_gemm': 67.69 + 2.37,
-    'feature_projection0_gemm': 268.96 + 26.32,
-    'classifier_gemm': 268.48 + 8.03,
-    'decoder_resize': 16.90 + 225.32,
-    'resize_argmax': 44.06 + 0.10,
+    'decoder_conv0_sepconv': 335.77 + 228.12,
+    'decoder_conv1_sepconv': 268.63 + 224.47,
+    'aspp_dw_pool': 134.87 + 350.28,
+    'aspp_branches_gemm': 541.21 + 14.98,
+    'concat_projection_gemm': 67.69 + 2.27,
+    'feature_projection0_gemm': 268.51 + 10.40,
+    'classifier_gemm': 268.48 + 7.82,
+    'decoder_resize': 16.86 + 215.53,
+    'resize_argmax': 44.06 + 0.21,
     'pool_proj': 1.46,
 }
 
@@ -312,7 +312,7 @@ def main():
                     'traffic': None, 'peak_source': peaks['src']}
         if B == CFG['B'] and not args.unfused and dom in NCU_DRAM_MB_PER_LAUNCH_B32:
             roof['traffic'] = NCU_DRAM_MB_PER_LAUNCH_B32[dom] * 1e6
-            roof['traffic_unit'] = 'bytes per launch (ncu dram read+write, profiles/r01b_ncu_full_step_summary.csv)'
+            roof['traffic_unit'] = 'bytes per launch (ncu dram read+write, profiles/r01c_ncu_full_step_summary.csv)'
             roof['algorithmic_bytes'] = (HBM_BYTES_PER_IMG.get(dom) or ALGO_BYTES_PER_IMG.get(dom, 0)) * B
             roof['dram_gbs'] = roof['traffic'] / (prof[dom] / 1000.0) / 1e9          # second roof of the fused kernels: HBM
             roof['dram_frac_of_hbm_peak'] = roof['dram_gbs'] / peaks['hbm_gbs']
