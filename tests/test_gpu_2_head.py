@@ -146,6 +146,27 @@ def test_cfg1_mobilenetv2_os16_512(gpu):
     hd.close()
 
 
+@pytest.mark.parametrize('kw', [
+    dict(B=1, H=136, W=200, OS=16, Cin=96, Cskip=16, NC=150),     # odd tile count (phantom tile of the CTA pair), 150 classes (ADE20K), MobileNetV3-small channels
+    dict(B=3, H=96, W=96, OS=8, Cin=64, Cskip=24, NC=2),         # OS8 rates 12/24/36 on a 12x12 map (rates == map size), binary labels
+    dict(B=1, H=64, W=64, OS=32, Cin=704, Cskip=128, NC=21),     # OS32 rates 3/6/9 on a 2x2 map, PeleeNet channels
+])
+def test_edge_geometries(gpu, kw):
+    """Geometries at the edges of the kernels' assumptions: partial / phantom tiles, rates >= map size, many or few
+    classes, channel counts that are not multiples of 64."""
+    cfg = R.HeadConfig(**kw)
+    W = R.make_weights(cfg, 31)
+    feat, skip = R.make_inputs(cfg, 32, relu_feat=False)
+    hd = make_head(cfg, W)
+    labels = hd(feat, skip)
+    logits = planar_to_nhwc(hd.tap('logits'))
+    o32 = R.head_forward_torch(feat, skip, W, cfg, 'fp32')
+    o16 = R.head_forward_torch(feat, skip, W, cfg, 'bf16')
+    assert rel_err(logits, o32['logits'].numpy()) < LOGIT_TOL
+    check_labels(labels, o16, 'edge %s' % (kw,))
+    hd.close()
+
+
 def test_cfg2_xception_os16_512_batch2(gpu):
     """BASELINE configs[1] shapes (Xception OS16 512x512 VOC) at a batch the oracle finishes in seconds."""
     cfg = R.HeadConfig(B=2, H=512, W=512, OS=16, Cin=2048, Cskip=256, NC=21)
