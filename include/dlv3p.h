@@ -202,6 +202,16 @@ int dlv3p_op_resize_bilinear(int device, const void* x_bf16, int B, int hi, int 
 int dlv3p_op_resize_argmax(int device, const float* logits_planar, int B, int NC, int hi, int wi,
                            int ho, int wo, uint8_t* labels, void* cuda_stream);
 
+/* Training-mode batch statistics of CustomBatchNormalization / SyncBatchNormalization (layers.py:63-70) — the SyncBN half of
+ * the cfg-5 exchange.  x: device bf16 [M, C] (NHWC as [pixels, channels]).  d_stats: device fp32 [2*C + 1] =
+ * sum_x | sum_x2 | row count; with several replicas the caller all-reduces (SUM) d_stats over NCCL (sharding.py), then
+ * dlv3p_op_bn_apply normalises with mean = sum/n, var = sum2/n - mean^2 (biased) read from DEVICE memory.
+ * Both calls are asynchronous on the stream.  d_scratch: dlv3p_op_bn_scratch_bytes(C) bytes of device memory. */
+size_t dlv3p_op_bn_scratch_bytes(int C);
+int dlv3p_op_bn_stats(int device, const void* x_bf16, int64_t M, int C, float* d_stats, void* d_scratch, void* cuda_stream);
+int dlv3p_op_bn_apply(int device, const void* x_bf16, int64_t M, int C, const float* d_stats, const float* d_gamma,
+                      const float* d_beta, float eps, int relu, void* y_bf16, void* cuda_stream);
+
 /* Benchmark aid (tools/kbench.py): average ms per launch of ONE operator on synthetic device data (CUDA events).
  * op 0 pointwise {M,K,N}; 1 fused sepconv {B,H,W,C}; 2 resize {B,hi,wi,C,ho,wo}; 3 resize_argmax {B,NC,hi,wi,ho,wo}.
  * flags: per-kernel debug bits (skip stores / stencil / MMA) to attribute time; results are then meaningless. */

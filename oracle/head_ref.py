@@ -531,3 +531,27 @@ def standin_backbone(image_nhwc: np.ndarray, cfg: HeadConfig, seed: int = 99):
     feat = lift(grads(f), cfg.Cin, True).astype(np.float32)
     skip = lift(grads(s), cfg.Cskip, False).astype(np.float32) if cfg.decoder else None
     return feat, skip
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Training-mode (Sync)BatchNormalization, layers.py:63-70 with train.py:143-158 (SURVEY.md §8(c) "SyncBN training"):
+# per replica sum_x, sum_x2 over (N,H,W), count; all-reduce SUM; mean = sum/n, var = sum2/n - mean^2 (biased).
+def bn_train_stats(x):
+    """x [..., C] -> float64 [2C+1] = sum_x | sum_x2 | rows of ONE replica."""
+    C = x.shape[-1]
+    x2 = np.asarray(x, np.float64).reshape(-1, C)
+    return np.concatenate([x2.sum(0), (x2 * x2).sum(0), [float(x2.shape[0])]])
+
+
+def sync_bn_train(x_shards, gamma, beta, eps=1e-5, relu=True):
+    """List of per-replica tensors [..., C] -> (list of normalised tensors, mean, biased variance) with GLOBAL statistics."""
+    C = x_shards[0].shape[-1]
+    st = sum(bn_train_stats(s) for s in x_shards)
+    mean = st[:C] / st[2 * C]
+    var = st[C:2 * C] / st[2 * C] - mean * mean
+    inv = np.asarray(gamma, np.float64) / np.sqrt(var + eps)
+    outs = []
+    for s in x_shards:
+        y = (np.asarray(s, np.float64) - mean) * inv + np.asarray(beta, np.float64)
+        outs.append(np.maximum(y, 0.0) if relu else y)
+    return outs, mean, var

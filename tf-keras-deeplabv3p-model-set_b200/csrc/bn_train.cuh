@@ -1,0 +1,91 @@
+// bn_train.cuh — training-mode batch statistics and normalisation of CustomBatchNormalization /
+// SyncBatchNormalization (reference deeplabv3p/models/layers.py:63-70; SURVEY.md §8(c) "SyncBN training"):
+//   per replica  sum_x[c], sum_x2[c] over the (N,H,W) rows, row count          (bn_stats_*_kernel)
+//   all-reduce(SUM) of [sum_x | sum_x2 | count] over the replicas              (NCCL, by the caller: sharding.py)
+//   mean = sum_x / n, var = sum_x2 / n - mean^2 (biased), y = (x - mean) * gamma * rsqrt(var + eps) + beta [ReLU]
+// The statistics are the first half of the cfg-5 training step's exchange; the backward kernels are not built yet.
+// Memory bound: x is read once per kernel, 4-byte bf16x2 loads (one 128-byte line per warp and row), fixed reduction
+// tree (deterministic: no atomics).
+#pragma once
+
+#include "sm100_prims.cuh"
+
+namespace dlv3p {
+
+constexpr int kBnBands = 64;   // row bands of the first reduction stage
+
+// grid (ceil(C/64), kBnBands), block 256: warp w of band b strides over the band's rows; lane = channels 2l, 2l+1.
+// partial: [kBnBands][2][C] fp32
+__global__ void __launch_bounds__(256) bn_stats_partial_kernel(const __nv_bfloat16* __restrict__ x, long long M, int C,
+                                                               float* __restrict__ partial) {
+  __shared__ float s_red[8][2][64];
+  const int chunk = blockIdx.x, band = blockIdx.y;
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int c0 = chunk * 64 + lane * 2;
+  const long long rows_per_band = (M + kBnBands - 1) / kBnBands;
+  const long long r0 = band * rows_per_band, r1 = min(M, r0 + rows_per_band);
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  if (c0 < C) {
+    const __nv_bfloat16* xb = x + c0;
+    for (long long r = r0 + wp; r < r1; r += 8) {
+      const uint32_t v = __ldg(reinterpret_cast<const unsigned int*>(xb + r * C));
+      const float a = bf16_lo(v), b = bf16_hi(v);
+      s0 += a; s1 += b;
+      q0 = fmaf(a, a, q0); q1 = fmaf(b, b, q1);
+    }
+  }
+  s_red[wp][0][lane * 2] = s0; s_red[wp][0][lane * 2 + 1] = s1;
+  s_red[wp][1][lane * 2] = q0; s_red[wp][1][lane * 2 + 1] = q1;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, j = threadIdx.x & 63;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += s_red[w][which][j];
+    const int c = chunk * 64 + j;
+    if (c < C) partial[(static_cast<size_t>(band) * 2 + which) * C + c] = s;
+  }
+}
+// stats: [2*C + 1] fp32 = sum_x | sum_x2 | row count
+__global__ void bn_stats_final_kernel(const float* __restrict__ partial, long long M, int C, float* __restrict__ stats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 2 * C) {
+    const int which = i / C, c = i - which * C;
+    float s = 0.f;
+    for (int b = 0; b < kBnBands; ++b) s += partial[(static_cast<size_t>(b) * 2 + which) * C + c];
+    stats[i] = s;
+  }
+  if (i == 0) stats[2 * C] = static_cast<float>(M);
+}
+// y = (x - mean) * gamma * rsqrt(var + eps) + beta, statistics read from DEVICE memory (no host round trip after the
+// all-reduce).  One thread = 8 channels of one row (16-byte accesses).
+__global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long M, int C, const float* __restrict__ stats,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int relu,
+                                                       __nv_bfloat16* __restrict__ y) {
+  const int vecs = C >> 3;
+  const long long total = M * vecs;
+  const float inv_n = 1.0f / stats[2 * C];
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int vec = static_cast<int>(idx % vecs);
+    const uint4 raw = ldg_nc_v4(x + idx * 8);
+    const uint32_t in[4] = {raw.x, raw.y, raw.z, raw.w};
+    uint32_t out[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v[2] = {bf16_lo(in[k]), bf16_hi(in[k])};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = vec * 8 + k * 2 + h;
+        const float mean = stats[c] * inv_n;
+        const float var = fmaxf(stats[C + c] * inv_n - mean * mean, 0.0f);
+        const float sc = gamma[c] * rsqrtf(var + eps);
+        v[h] = (v[h] - mean) * sc + beta[c];
+        if (relu) v[h] = fmaxf(v[h], 0.0f);
+      }
+      out[k] = pack_bf16x2(v[0], v[1]);
+    }
+    stg_v4(y + idx * 8, make_uint4(out[0], out[1], out[2], out[3]));
+  }
+}
+
+}  // namespace dlv3p

@@ -25,6 +25,7 @@
 #include "pw_gemm2.cuh"
 #include "aspp_dw_fast.cuh"
 #include "aspp_dw_gather.cuh"
+#include "bn_train.cuh"
 
 using namespace dlv3p;
 
@@ -1701,6 +1702,32 @@ int dlv3p_op_resize_bilinear(int device, const void* x_bf16, int B, int hi, int 
     resize_bilinear_kernel<<<dim3(ho, B), 256, 0, st>>>(P);
   CU_TRY(nullptr, cudaGetLastError());
   CU_TRY(nullptr, cudaStreamSynchronize(st));
+  return DLV3P_OK;
+}
+
+size_t dlv3p_op_bn_scratch_bytes(int C) { return static_cast<size_t>(kBnBands) * 2 * (C > 0 ? C : 0) * sizeof(float); }
+
+int dlv3p_op_bn_stats(int device, const void* x_bf16, int64_t M, int C, float* d_stats, void* d_scratch, void* cuda_stream) {
+  int sms = 0, r = op_prolog(device, &sms);
+  if (r) return r;
+  if (!x_bf16 || !d_stats || !d_scratch || M < 1 || C < 2 || C % 2) return fail(nullptr, DLV3P_ERR_INVALID, "op_bn_stats: bad arguments (C even)");
+  if (M >= (1ll << 24)) return fail(nullptr, DLV3P_ERR_UNSUPPORTED, "op_bn_stats: the row count travels as fp32 (M < 2^24 per replica)");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  bn_stats_partial_kernel<<<dim3(ceil_div(C, 64), kBnBands), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x_bf16), M, C, static_cast<float*>(d_scratch));
+  bn_stats_final_kernel<<<ceil_div(2 * C, 256), 256, 0, st>>>(static_cast<const float*>(d_scratch), M, C, d_stats);
+  CU_TRY(nullptr, cudaGetLastError());
+  return DLV3P_OK;   // asynchronous: the caller all-reduces d_stats on the same stream / after an event
+}
+
+int dlv3p_op_bn_apply(int device, const void* x_bf16, int64_t M, int C, const float* d_stats, const float* d_gamma, const float* d_beta,
+                      float eps, int relu, void* y_bf16, void* cuda_stream) {
+  int sms = 0, r = op_prolog(device, &sms);
+  if (r) return r;
+  if (!x_bf16 || !d_stats || !d_gamma || !d_beta || !y_bf16 || M < 1 || C < 8 || C % 8) return fail(nullptr, DLV3P_ERR_INVALID, "op_bn_apply: bad arguments (C % 8)");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  bn_apply_kernel<<<grid_for(static_cast<size_t>(M) * (C / 8), sms), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x_bf16), M, C, d_stats, d_gamma, d_beta, eps, relu,
+                                                                                  static_cast<__nv_bfloat16*>(y_bf16));
+  CU_TRY(nullptr, cudaGetLastError());
   return DLV3P_OK;
 }
 

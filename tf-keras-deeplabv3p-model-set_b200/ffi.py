@@ -73,6 +73,9 @@ SYMBOLS = [
     ('dlv3p_op_resize_bilinear', _i, [_i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     ('dlv3p_op_resize_argmax', _i, [_i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     ('dlv3p_op_time', _i, [_i, _i, C.POINTER(C.c_int64), _i, _i, _i, _fp]),
+    ('dlv3p_op_bn_scratch_bytes', C.c_size_t, [_i]),
+    ('dlv3p_op_bn_stats', _i, [_i, _vp, C.c_int64, _i, _vp, _vp, _vp]),
+    ('dlv3p_op_bn_apply', _i, [_i, _vp, C.c_int64, _i, _vp, _vp, _vp, C.c_float, _i, _vp, _vp]),
 ]
 
 _lib = None
@@ -349,6 +352,35 @@ def op_resize_argmax(logits_planar: np.ndarray, ho: int, wo: int, device=0) -> n
     do = DeviceBuffer(B * ho * wo, device)
     _check(load_library().dlv3p_op_resize_argmax(device, dl.ptr, B, NC, hi, wi, ho, wo, do.ptr, None))
     return do.download((B, ho, wo), np.uint8)
+
+
+def bn_stats(x_ptr: int, M: int, Cc: int, stats_ptr: int, scratch_ptr: int, stream=None, device=0) -> None:
+    """Device pointers in and out, asynchronous: stats fp32 [2C+1] = sum_x | sum_x2 | rows (all-reduce it across replicas)."""
+    _check(load_library().dlv3p_op_bn_stats(device, x_ptr, M, Cc, stats_ptr, scratch_ptr, stream))
+
+
+def bn_apply(x_ptr: int, M: int, Cc: int, stats_ptr: int, gamma_ptr: int, beta_ptr: int, eps: float, relu: bool, y_ptr: int,
+             stream=None, device=0) -> None:
+    _check(load_library().dlv3p_op_bn_apply(device, x_ptr, M, Cc, stats_ptr, gamma_ptr, beta_ptr, eps, int(relu), y_ptr, stream))
+
+
+def bn_scratch_bytes(Cc: int) -> int:
+    return int(load_library().dlv3p_op_bn_scratch_bytes(Cc))
+
+
+def op_bn_train(x_bits: np.ndarray, gamma: np.ndarray, beta: np.ndarray, eps: float = 1e-5, relu: bool = True, device=0):
+    """Single-replica training-mode BN on host arrays: returns (y bf16 bits [M,C], stats fp32 [2C+1])."""
+    M, Cc = x_bits.shape
+    dx = DeviceBuffer.from_numpy(x_bits, device)
+    dst = DeviceBuffer((2 * Cc + 1) * 4, device)
+    dsc = DeviceBuffer(bn_scratch_bytes(Cc), device)
+    dg = DeviceBuffer.from_numpy(np.ascontiguousarray(gamma, np.float32), device)
+    db = DeviceBuffer.from_numpy(np.ascontiguousarray(beta, np.float32), device)
+    dy = DeviceBuffer(M * Cc * 2, device)
+    bn_stats(dx.ptr, M, Cc, dst.ptr, dsc.ptr, None, device)
+    bn_apply(dx.ptr, M, Cc, dst.ptr, dg.ptr, db.ptr, eps, relu, dy.ptr, None, device)
+    synchronize(device)
+    return dy.download((M, Cc), np.uint16), dst.download((2 * Cc + 1,), np.float32)
 
 
 def op_time(op: int, dims: Sequence[int], iters: int = 20, flags: int = 0, device: int = 0) -> float:
