@@ -266,7 +266,8 @@ bool aspp_fast_supported(const AsppDwParams& P) {
   static int off = -1;
   if (off < 0) { const char* e = getenv("DLV3P_NO_ASPP_FAST"); off = (e && e[0] == '1') ? 1 : 0; }
   if (off || P.nrates != 3 || P.C % 32 != 0) return false;
-  return P.h == 32 && P.w_ == 32 && P.rates[0] == 6 && P.rates[1] == 12 && P.rates[2] == 18;
+  // OS16 maps of 512x512 (the BASELINE configurations), 384x384, 256x256 and 128x128 inputs
+  return P.h == P.w_ && (P.h == 32 || P.h == 24 || P.h == 16 || P.h == 8) && P.rates[0] == 6 && P.rates[1] == 12 && P.rates[2] == 18;
 }
 
 // large / odd-sized maps: cp.async gather of phase images (aspp_dw_gather.cuh).  Fills the geometry part of the plan and the
@@ -356,8 +357,14 @@ cudaError_t launch_aspp_fast3_t(const AsppDwParams& P, cudaStream_t st) {
   return cudaGetLastError();
 }
 cudaError_t launch_aspp_fast(const AsppDwParams& P, cudaStream_t st) {
-  if (P.debug & 16) return launch_aspp_fast_t<32, 32, 6, 12, 18>(P, st);   // A/B: one phase image per rate
-  return launch_aspp_fast3_t<32, 32, 6>(P, st);                            // one phase image for the three rates (r, 2r, 3r)
+  if ((P.debug & 16) && P.h == 32) return launch_aspp_fast_t<32, 32, 6, 12, 18>(P, st);   // A/B: one phase image per rate
+  switch (P.h) {   // one phase image for the three rates (r, 2r, 3r)
+    case 32: return launch_aspp_fast3_t<32, 32, 6>(P, st);
+    case 24: return launch_aspp_fast3_t<24, 24, 6>(P, st);
+    case 16: return launch_aspp_fast3_t<16, 16, 6>(P, st);
+    case 8: return launch_aspp_fast3_t<8, 8, 6>(P, st);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 cudaError_t launch_pw(int BN, const PwLaunch& L, int num_sms, cudaStream_t st) {
