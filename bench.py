@@ -183,7 +183,7 @@ def run_reference(args, rank, world):
     line = {'impl': 'reference', 'metric': METRIC, 'value': res['value'], 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': steps,
             'warmup': args.warmup, 'ms_per_step': 1000.0 * 2 / res['value'], 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD + ' [reference arm: batch 2 per step on host cores]'},
+            'config': {'workload': WORKLOAD, 'reference_arm': 'oracle port on host cores, bounded sample: batch 2 per step'},
             'cpu_baseline': res,
             'e2e': {'value': res['value'], 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
