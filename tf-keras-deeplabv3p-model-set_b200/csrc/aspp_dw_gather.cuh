@@ -9,8 +9,8 @@
 // through a per-phase strided tensor map {C, ceil((w-pj)/r), ceil((h-pi)/r), B} (box origin (-1,-1): the zero border and
 // everything past the map edge is TMA zero fill = 'same' padding); a 16-byte cp.async gather of the same data is limited
 // by the SM's outstanding-request capacity (1.41 ms at cfg 3 vs the TMA's in-flight depth).  Half-warps (16 lanes x bf16x2 = the 32 channels) then run
-// the dense 3x3 conv on one 8-column segment of one phase image each with a three-row register window: every input is
-// read from HBM once per rate and from shared memory 1.25 times.  Two CTAs per SM overlap one CTA's gather
+// the dense 3x3 conv on one 4-column segment of one phase image each with a three-row register window: every input is
+// read from HBM once per rate and from shared memory 1.5 times.  Three CTAs per SM overlap one CTA's gather
 // with the others' arithmetic.
 #pragma once
 
@@ -22,7 +22,7 @@
 namespace dlv3p {
 
 constexpr int kGatherThreads = 256;
-constexpr int kGatherSmemBudget = 80 * 1024; // phase images per CTA batch (2 CTAs per SM)
+constexpr int kGatherSmemBudget = 70 * 1024; // phase images per CTA batch (3 CTAs per SM)
 constexpr int kGatherSmemBytes = kGatherSmemBudget + (9 * 32 + 32 + 16 * 32) * 4 + 16;
 
 struct AsppGatherParams {
@@ -37,7 +37,7 @@ struct AsppGatherParams {
   int B, h, w_, C, nchunks;
   int rates[3];
   int na[3], nt[3];         // phase-image extent ceil(h / r), ceil(w / r)
-  int ts[3];                // output columns per segment: 8 or 6, whichever wastes fewer columns of nt
+  int ts[3];                // output columns per segment (4: 36 row registers -> three CTAs per SM; measured better than 6 / 8 with two)
   int nseg[3];              // ceil(nt / ts)
   int num_batches;          // per (image, channel group)
   int pool_slots;           // number of rate-0 batches
@@ -150,8 +150,7 @@ __device__ __forceinline__ void aspp_gather_body(const AsppGatherParams& P, uint
     const int ph = it / nseg, seg = it - ph * nseg;
     const int phase = ph0 + ph;
     const int pi = phase / r, pj = phase - pi * r;
-    if (ts == 8) aspp_gather_item<RC, 8>(P, s_img + ph * img_bytes + l16 * 4, ri, pi, pj, seg, out_lane, wt, sh, psum);
-    else aspp_gather_item<RC, 6>(P, s_img + ph * img_bytes + l16 * 4, ri, pi, pj, seg, out_lane, wt, sh, psum);
+    aspp_gather_item<RC, 4>(P, s_img + ph * img_bytes + l16 * 4, ri, pi, pj, seg, out_lane, wt, sh, psum);
   }
   // ---- image-pooling partial sums: the rate-0 batches cover every pixel exactly once
   if (ri == 0) {
@@ -168,7 +167,7 @@ __device__ __forceinline__ void aspp_gather_body(const AsppGatherParams& P, uint
 }
 
 // grid = B * (C / 32) * num_batches, block 256, dynamic smem = kGatherSmemBytes
-__global__ void __launch_bounds__(kGatherThreads, 2) aspp_dw_gather_kernel(const __grid_constant__ AsppGatherParams P) {
+__global__ void __launch_bounds__(kGatherThreads, 3) aspp_dw_gather_kernel(const __grid_constant__ AsppGatherParams P) {
   extern __shared__ __align__(128) uint8_t gather_smem[];
   const int ngroups = P.C >> 5;
   int bid = blockIdx.x;

@@ -283,7 +283,7 @@ bool plan_aspp_gather(int h, int w, int C, const int rates[3], AsppGatherParams*
     G->rates[i] = r;
     G->na[i] = ceil_div(h, r);
     G->nt[i] = ceil_div(w, r);
-    G->ts[i] = ceil_div(G->nt[i], 6) * 6 < ceil_div(G->nt[i], 8) * 8 ? 6 : 8;   // fewer padded columns wins, 8 on ties
+    G->ts[i] = 4;   // four output columns per segment: 36 row registers, three CTAs per SM
     G->nseg[i] = ceil_div(G->nt[i], G->ts[i]);
     const int ntp = G->nseg[i] * G->ts[i] + 2;
     const int img_bytes = (G->na[i] + 2) * ntp * 64;   // zero-bordered phase image, 32 channels
