@@ -113,3 +113,31 @@ def test_image_pool_branch_is_a_per_image_bias():
     full = R.conv1x1(np.concatenate([R.resize_bilinear(b4, (4, 4)), rest], -1), k)
     split = R.conv1x1(rest, k[:, :, 256:]) + R.conv1x1(b4, k[:, :, :256])
     assert np.abs(full - split).max() < 2e-4
+
+
+# ---- pins produced by EXECUTING the reference's own TensorFlow-free functions (tests/golden/make_ref_pins.py) ----------
+def _pins():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_pins.npz'))
+
+
+@pytest.mark.parametrize('k', [0, 1, 2, 3])
+def test_metrics_reproduce_the_reference_functions(k):
+    """deeplabv3p/metrics.py::mIOU and eval.py::generate_matrix, incl. missing classes and the ignore label 255."""
+    z = _pins()
+    gt, pr, nc = z['gt_%d' % k], z['pred_%d' % k], int(z['nc_%d' % k])
+    assert R.mIOU(gt, pr) == float(z['miou_%d' % k])
+    assert np.array_equal(R.generate_matrix(gt, pr, nc), z['confusion_%d' % k])
+
+
+def test_preprocessing_reproduces_the_reference_functions():
+    """common/data_utils.py: normalize_image, denormalize_image, preprocess_image (PIL bicubic), mask_resize (cv2 nearest)."""
+    import os
+    from PIL import Image
+    z = _pins()
+    assert np.array_equal(R.normalize_image(z['image_u8'].astype(np.float32)), z['normalize'])
+    assert np.array_equal(R.denormalize_image(z['normalize']), z['denormalize'])
+    assert np.array_equal(R.mask_resize(z['mask_in'], (27, 36)), z['mask_resize_27x36'])
+    jpg = '/root/reference/example/2007_000039.jpg'
+    if os.path.exists(jpg):                      # the example image itself lives in the reference tree (build container only)
+        assert np.array_equal(R.preprocess_image(Image.open(jpg), (48, 64)), z['preprocess_2007_000039_48x64'])
