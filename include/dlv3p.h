@@ -202,6 +202,13 @@ int dlv3p_op_resize_bilinear(int device, const void* x_bf16, int B, int hi, int 
 int dlv3p_op_resize_argmax(int device, const float* logits_planar, int B, int NC, int hi, int wi,
                            int ho, int wo, uint8_t* labels, void* cuda_stream);
 
+/* Confusion-matrix accumulation of the evaluation loop (eval.py:368-373 generate_matrix and its running sum, :403-443):
+ * d_confusion[gt * NC + pred] += 1 for every pixel with gt < NC (the ignore label 255 is skipped).  Device uint8 label
+ * maps (16-byte aligned), device uint64 [NC*NC] matrix that is ACCUMULATED across calls; asynchronous on the stream.
+ * Integer work, bit exact. */
+int dlv3p_op_confusion_matrix(int device, const uint8_t* d_pred, const uint8_t* d_gt, int64_t n, int NC,
+                              unsigned long long* d_confusion, void* cuda_stream);
+
 /* Training-mode batch statistics of CustomBatchNormalization / SyncBatchNormalization (layers.py:63-70) — the SyncBN half of
  * the cfg-5 exchange.  x: device bf16 [M, C] (NHWC as [pixels, channels]).  d_stats: device fp32 [2*C + 1] =
  * sum_x | sum_x2 | row count; with several replicas the caller all-reduces (SUM) d_stats over NCCL (sharding.py), then

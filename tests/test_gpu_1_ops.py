@@ -131,3 +131,25 @@ def test_fused_sepconv_is_deterministic_and_batch_independent(gpu):
         assert np.array_equal(a, b), 'C=%d: run-to-run difference on %d elements' % (C, (a != b).sum())
         for rep in range(1, 12):
             assert np.array_equal(a[:2], a[2 * rep:2 * rep + 2]), 'C=%d: batch slot %d differs from slot 0' % (C, rep)
+
+
+@pytest.mark.parametrize('nc,n', [(21, 512 * 512), (2, 1000), (150, 33 * 47), (256, 4096), (64, 17)])
+def test_confusion_matrix_bit_exact(gpu, nc, n):
+    """eval.py:368-373 generate_matrix (+ the running sum over images): integer work, bit exact, ignore label 255."""
+    rng = np.random.default_rng(nc + n)
+    gt = rng.integers(0, nc, size=n).astype(np.uint8)
+    pr = np.where(rng.random(n) < 0.8, gt, rng.integers(0, nc, size=n)).astype(np.uint8)
+    if nc < 255:
+        gt[rng.random(n) < 0.05] = 255
+    ref = R.generate_matrix(gt, pr, nc)
+    assert np.array_equal(ffi.op_confusion_matrix(pr, gt, nc), ref)
+    assert np.array_equal(ffi.op_confusion_matrix(pr, gt, nc, repeat=3), 3 * ref)
+
+
+def test_confusion_matrix_equals_the_reference_output(gpu):
+    """Against the output of the reference's own generate_matrix (tests/golden/ref_pins.npz, make_ref_pins.py)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_pins.npz'))
+    for k in range(4):
+        got = ffi.op_confusion_matrix(z['pred_%d' % k], z['gt_%d' % k], int(z['nc_%d' % k]))
+        assert np.array_equal(got, z['confusion_%d' % k])

@@ -1712,6 +1712,20 @@ int dlv3p_op_resize_bilinear(int device, const void* x_bf16, int B, int hi, int 
   return DLV3P_OK;
 }
 
+int dlv3p_op_confusion_matrix(int device, const uint8_t* d_pred, const uint8_t* d_gt, int64_t n, int NC, unsigned long long* d_confusion,
+                              void* cuda_stream) {
+  int sms = 0, r = op_prolog(device, &sms);
+  if (r) return r;
+  if (!d_pred || !d_gt || !d_confusion || n < 1 || NC < 1 || NC > 256) return fail(nullptr, DLV3P_ERR_INVALID, "op_confusion_matrix: bad arguments (1 <= NC <= 256)");
+  if ((reinterpret_cast<uintptr_t>(d_pred) | reinterpret_cast<uintptr_t>(d_gt)) & 15) return fail(nullptr, DLV3P_ERR_INVALID, "op_confusion_matrix: label buffers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  ConfusionParams P{d_pred, d_gt, n, NC, d_confusion};
+  const size_t smem = NC <= 64 ? static_cast<size_t>(NC) * NC * sizeof(unsigned int) : 0;
+  confusion_matrix_kernel<<<grid_for(static_cast<size_t>(n / 16 + 1), sms), 256, smem, st>>>(P);
+  CU_TRY(nullptr, cudaGetLastError());
+  return DLV3P_OK;   // asynchronous; d_confusion is ACCUMULATED (zero it once per evaluation)
+}
+
 size_t dlv3p_op_bn_scratch_bytes(int C) { return static_cast<size_t>(kBnBands) * 2 * (C > 0 ? C : 0) * sizeof(float); }
 
 int dlv3p_op_bn_stats(int device, const void* x_bf16, int64_t M, int C, float* d_stats, void* d_scratch, void* cuda_stream) {

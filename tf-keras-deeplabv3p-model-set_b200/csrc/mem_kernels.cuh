@@ -857,4 +857,51 @@ __global__ void planar_to_nhwc_kernel(const float* __restrict__ in, float* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Confusion-matrix accumulation of the evaluation loop (reference eval.py:368-373 generate_matrix + the running sum of
+// eval.py:403-443): confusion[gt * NC + pred] += 1 for every pixel with gt < NC (255 = ignore label is skipped).
+// Integer work: bit exact.  Block-private histogram in shared memory for NC <= 64, global atomics above.
+struct ConfusionParams {
+  const uint8_t* pred;
+  const uint8_t* gt;
+  long long n;
+  int NC;
+  unsigned long long* confusion;   // [NC][NC], accumulated
+};
+__global__ void __launch_bounds__(256) confusion_matrix_kernel(const ConfusionParams P) {
+  extern __shared__ unsigned int s_hist[];   // [NC*NC] when NC <= 64
+  const int bins = P.NC * P.NC;
+  const bool priv = P.NC <= 64;
+  if (priv) {
+    for (int i = threadIdx.x; i < bins; i += blockDim.x) s_hist[i] = 0u;
+    __syncthreads();
+  }
+  const long long n16 = P.n >> 4;
+  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < n16; v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 g = ldg_nc_v4(P.gt + v * 16), q = ldg_nc_v4(P.pred + v * 16);
+    const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, pw[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int gt = (gw[k >> 2] >> ((k & 3) * 8)) & 0xFF, pr = (pw[k >> 2] >> ((k & 3) * 8)) & 0xFF;
+      if (gt < P.NC && pr < P.NC) {
+        if (priv) atomicAdd(&s_hist[gt * P.NC + pr], 1u);
+        else atomicAdd(&P.confusion[gt * P.NC + pr], 1ull);
+      }
+    }
+  }
+  if (blockIdx.x == 0)   // tail (n % 16 pixels)
+    for (long long i = n16 * 16 + threadIdx.x; i < P.n; i += blockDim.x) {
+      const int gt = P.gt[i], pr = P.pred[i];
+      if (gt < P.NC && pr < P.NC) {
+        if (priv) atomicAdd(&s_hist[gt * P.NC + pr], 1u);
+        else atomicAdd(&P.confusion[gt * P.NC + pr], 1ull);
+      }
+    }
+  if (priv) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < bins; i += blockDim.x)
+      if (s_hist[i]) atomicAdd(&P.confusion[i], static_cast<unsigned long long>(s_hist[i]));
+  }
+}
+
 }  // namespace dlv3p

@@ -73,6 +73,7 @@ SYMBOLS = [
     ('dlv3p_op_resize_bilinear', _i, [_i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     ('dlv3p_op_resize_argmax', _i, [_i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     ('dlv3p_op_time', _i, [_i, _i, C.POINTER(C.c_int64), _i, _i, _i, _fp]),
+    ('dlv3p_op_confusion_matrix', _i, [_i, _vp, _vp, C.c_int64, _i, _vp, _vp]),
     ('dlv3p_op_bn_scratch_bytes', C.c_size_t, [_i]),
     ('dlv3p_op_bn_stats', _i, [_i, _vp, C.c_int64, _i, _vp, _vp, _vp]),
     ('dlv3p_op_bn_apply', _i, [_i, _vp, C.c_int64, _i, _vp, _vp, _vp, C.c_float, _i, _vp, _vp]),
@@ -352,6 +353,19 @@ def op_resize_argmax(logits_planar: np.ndarray, ho: int, wo: int, device=0) -> n
     do = DeviceBuffer(B * ho * wo, device)
     _check(load_library().dlv3p_op_resize_argmax(device, dl.ptr, B, NC, hi, wi, ho, wo, do.ptr, None))
     return do.download((B, ho, wo), np.uint8)
+
+
+def op_confusion_matrix(pred: np.ndarray, gt: np.ndarray, num_classes: int, device=0, repeat: int = 1) -> np.ndarray:
+    """generate_matrix (eval.py:368-373) on the device: uint8 label maps -> int64 [NC, NC]; `repeat` accumulates the
+    same maps several times (the evaluation loop's running sum)."""
+    p = np.ascontiguousarray(pred, np.uint8).reshape(-1)
+    g = np.ascontiguousarray(gt, np.uint8).reshape(-1)
+    dp, dg = DeviceBuffer.from_numpy(p, device), DeviceBuffer.from_numpy(g, device)
+    dc = DeviceBuffer.from_numpy(np.zeros(num_classes * num_classes, np.uint64), device)
+    for _ in range(repeat):
+        _check(load_library().dlv3p_op_confusion_matrix(device, dp.ptr, dg.ptr, p.size, num_classes, dc.ptr, None))
+    synchronize(device)
+    return dc.download((num_classes, num_classes), np.uint64).astype(np.int64)
 
 
 def bn_stats(x_ptr: int, M: int, Cc: int, stats_ptr: int, scratch_ptr: int, stream=None, device=0) -> None:
