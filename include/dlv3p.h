@@ -62,6 +62,7 @@ enum { /* variant */
 
 enum { /* in_dtype of the feature / skip tensors handed to forward */
   DLV3P_DTYPE_BF16 = 0,
+  DLV3P_DTYPE_FP16 = 1, /* the reference's --mixed_precision activations; converted to bf16 on device */
   DLV3P_DTYPE_FP32 = 2 /* converted to bf16 on device by a cast kernel */
 };
 

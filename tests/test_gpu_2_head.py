@@ -88,6 +88,16 @@ def test_fp32_inputs_are_cast_on_device(gpu):
     assert np.array_equal(a, b)
 
 
+def test_fp16_inputs_are_cast_on_device(gpu):
+    """The reference's --mixed_precision hands fp16 activations over: fp16 -> bf16 on the device, same labels as feeding
+    the fp16-rounded values through the bf16 path."""
+    cfg, W, feat, skip, z = load_case('head_small_full')
+    f16, s16 = feat.astype(np.float16), skip.astype(np.float16)
+    a = make_head(cfg, W, in_dtype=ffi.DTYPE_BF16)(f16.astype(np.float32), s16.astype(np.float32))
+    b = make_head(cfg, W, in_dtype=ffi.DTYPE_FP16)(f16, s16)
+    assert np.array_equal(a, b)
+
+
 def test_forward_host_equals_device_forward_and_is_deterministic(gpu):
     cfg, W, feat, skip, _ = load_case('head_small_os8')
     hd = make_head(cfg, W)

@@ -767,8 +767,8 @@ int dlv3p_create(const dlv3p_config* cfg, int device, dlv3p_ctx** out) {
   }
   if (c->st_dec && (g.Cskip < 8 || g.Cskip % 8)) return bail(DLV3P_ERR_INVALID, "Cskip must be a positive multiple of 8");
   if (c->st_tail && (g.NC < 1 || g.NC > 256)) return bail(DLV3P_ERR_INVALID, "NC must be in 1..256");
-  if (g.in_dtype != DLV3P_DTYPE_BF16 && g.in_dtype != DLV3P_DTYPE_FP32)
-    return bail(DLV3P_ERR_UNSUPPORTED, "in_dtype: only bf16 (0) and fp32 (2) are implemented");
+  if (g.in_dtype != DLV3P_DTYPE_BF16 && g.in_dtype != DLV3P_DTYPE_FP16 && g.in_dtype != DLV3P_DTYPE_FP32)
+    return bail(DLV3P_ERR_UNSUPPORTED, "in_dtype: bf16 (0), fp16 (1) and fp32 (2) are implemented");
   if (c->st_tail) {
     if (g.out_mode < DLV3P_OUT_LABELS_U8 || g.out_mode > DLV3P_OUT_LOGITS_FULL) return bail(DLV3P_ERR_INVALID, "out_mode does not match a TAIL stage");
   } else if (g.out_mode != DLV3P_OUT_FEATURES_BF16 && g.out_mode != DLV3P_OUT_FEATURES_FP32) {
@@ -864,7 +864,7 @@ int dlv3p_create(const dlv3p_config* cfg, int device, dlv3p_ctx** out) {
     if ((r = dev_alloc(c, &c->b4, B * 256))) return bail(r, c->err);
     if ((r = dev_alloc(c, &c->concat, static_cast<size_t>(c->M1) * c->Ccat))) return bail(r, c->err);
     if ((r = dev_alloc(c, &c->aspp_out, static_cast<size_t>(c->M1) * 256))) return bail(r, c->err);
-    if (g.in_dtype == DLV3P_DTYPE_FP32 && (r = dev_alloc(c, &c->feat_bf16, static_cast<size_t>(c->M1) * g.Cin))) return bail(r, c->err);
+    if (g.in_dtype != DLV3P_DTYPE_BF16 && (r = dev_alloc(c, &c->feat_bf16, static_cast<size_t>(c->M1) * g.Cin))) return bail(r, c->err);
   }
   if (c->st_dec) {
     if (g.flags & DLV3P_FLAG_UNFUSED_DECODER) {
@@ -877,12 +877,12 @@ int dlv3p_create(const dlv3p_config* cfg, int device, dlv3p_ctx** out) {
     if ((g.flags & DLV3P_FLAG_UNFUSED_DECODER) && (r = dev_alloc(c, &c->dec_tmp, static_cast<size_t>(c->M2) * 304))) return bail(r, c->err);
     if ((r = dev_alloc(c, &c->dec0, static_cast<size_t>(c->M2) * 256))) return bail(r, c->err);
     if ((r = dev_alloc(c, &c->dec1, static_cast<size_t>(c->M2) * 256))) return bail(r, c->err);
-    if (g.in_dtype == DLV3P_DTYPE_FP32 && (r = dev_alloc(c, &c->skip_bf16, static_cast<size_t>(c->M2) * g.Cskip))) return bail(r, c->err);
-    if (!c->st_aspp && g.in_dtype == DLV3P_DTYPE_FP32 && (r = dev_alloc(c, &c->feat_bf16, static_cast<size_t>(c->M1) * 256))) return bail(r, c->err);
+    if (g.in_dtype != DLV3P_DTYPE_BF16 && (r = dev_alloc(c, &c->skip_bf16, static_cast<size_t>(c->M2) * g.Cskip))) return bail(r, c->err);
+    if (!c->st_aspp && g.in_dtype != DLV3P_DTYPE_BF16 && (r = dev_alloc(c, &c->feat_bf16, static_cast<size_t>(c->M1) * 256))) return bail(r, c->err);
   }
   if (c->st_tail) {
     if ((r = dev_alloc(c, &c->logits, B * g.NC * c->ho * c->wo))) return bail(r, c->err);
-    if (!c->st_aspp && !c->st_dec && g.in_dtype == DLV3P_DTYPE_FP32 && (r = dev_alloc(c, &c->feat_bf16, static_cast<size_t>(c->Mc) * 256))) return bail(r, c->err);
+    if (!c->st_aspp && !c->st_dec && g.in_dtype != DLV3P_DTYPE_BF16 && (r = dev_alloc(c, &c->feat_bf16, static_cast<size_t>(c->Mc) * 256))) return bail(r, c->err);
   }
   if ((r = dev_alloc(c, &c->d_tm, TM_COUNT))) return bail(r, c->err);
   std::memset(c->h_tm, 0, sizeof(c->h_tm));
@@ -1170,18 +1170,18 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
   const __nv_bfloat16* feat = nullptr;
   const __nv_bfloat16* skip = nullptr;
   const size_t feat_elems = c->st_aspp ? static_cast<size_t>(c->M1) * g.Cin : (c->st_dec ? static_cast<size_t>(c->M1) * 256 : static_cast<size_t>(c->Mc) * 256);
-  if (g.in_dtype == DLV3P_DTYPE_FP32) {
-    if (L.begin("cast_f32_bf16")) {
-      cast_f32_bf16_kernel<<<grid_for(feat_elems / 8, c->num_sms), 256, 0, st>>>(static_cast<const float*>(d_feat), c->feat_bf16, feat_elems / 8);
-      L.end("cast_f32_bf16", cudaGetLastError());
-    }
+  if (g.in_dtype != DLV3P_DTYPE_BF16) {   // fp32 (a TF backbone's default) or fp16 (the reference's --mixed_precision): cast on the device
+    auto cast = [&](const void* src, __nv_bfloat16* dst, size_t n8) {
+      if (L.begin("cast_to_bf16")) {
+        if (g.in_dtype == DLV3P_DTYPE_FP32) cast_f32_bf16_kernel<<<grid_for(n8, c->num_sms), 256, 0, st>>>(static_cast<const float*>(src), dst, n8);
+        else cast_f16_bf16_kernel<<<grid_for(n8, c->num_sms), 256, 0, st>>>(static_cast<const __half*>(src), dst, n8);
+        L.end("cast_to_bf16", cudaGetLastError());
+      }
+    };
+    cast(d_feat, c->feat_bf16, feat_elems / 8);
     feat = c->feat_bf16;
     if (c->st_dec) {
-      const size_t n = static_cast<size_t>(c->M2) * g.Cskip;
-      if (L.begin("cast_f32_bf16")) {
-        cast_f32_bf16_kernel<<<grid_for(n / 8, c->num_sms), 256, 0, st>>>(static_cast<const float*>(d_skip), c->skip_bf16, n / 8);
-        L.end("cast_f32_bf16", cudaGetLastError());
-      }
+      cast(d_skip, c->skip_bf16, static_cast<size_t>(c->M2) * g.Cskip / 8);
       skip = c->skip_bf16;
     }
   } else {

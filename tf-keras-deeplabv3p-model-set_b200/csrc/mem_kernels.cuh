@@ -10,6 +10,8 @@
 //   resize_dense_kernel   pred_resize (+ Softmax) materialised, for callers that want the reference output
 #pragma once
 
+#include <cuda_fp16.h>
+
 #include "sm100_prims.cuh"
 
 namespace dlv3p {
@@ -31,6 +33,21 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16
     const float4 a = __ldg(reinterpret_cast<const float4*>(in) + 2 * i);
     const float4 b = __ldg(reinterpret_cast<const float4*>(in) + 2 * i + 1);
     stg_v4(out + 8 * i, make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w)));
+  }
+}
+__global__ void cast_f16_bf16_kernel(const __half* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n8) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint4 r = ldg_nc_v4(in + 8 * i);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __half2 h = *reinterpret_cast<const __half2*>(&w[k]);
+      const float2 f = __half22float2(h);
+      o[k] = pack_bf16x2(f.x, f.y);
+    }
+    stg_v4(out + 8 * i, make_uint4(o[0], o[1], o[2], o[3]));
   }
 }
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t n8) {

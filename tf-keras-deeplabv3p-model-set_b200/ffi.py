@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, 'libdlv3p.so')
 # ---- enums (mirror include/dlv3p.h) ----------------------------------------------------------
 STAGE_ASPP, STAGE_DECODER, STAGE_TAIL = 1, 2, 4
 VARIANT_ASPP, VARIANT_ASPP_LITE = 0, 1
-DTYPE_BF16, DTYPE_FP32 = 0, 2
+DTYPE_BF16, DTYPE_FP16, DTYPE_FP32 = 0, 1, 2
 OUT_LABELS_U8, OUT_LOGITS_LOWRES, OUT_SOFTMAX, OUT_LOGITS_FULL, OUT_FEATURES_BF16, OUT_FEATURES_FP32 = range(6)
 FLAG_UNFUSED_DECODER = 1
 

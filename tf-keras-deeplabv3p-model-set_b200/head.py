@@ -92,6 +92,8 @@ class _Block:
     def _prep(self, a: np.ndarray) -> np.ndarray:
         if self.ctx.cfg.in_dtype == ffi.DTYPE_FP32:
             return np.ascontiguousarray(a, np.float32)
+        if self.ctx.cfg.in_dtype == ffi.DTYPE_FP16:
+            return np.ascontiguousarray(a, np.float16)
         if a.dtype == np.uint16:
             return np.ascontiguousarray(a)
         return ffi.f32_to_bf16_bits(a)
