@@ -1,0 +1,427 @@
+"""GPU parity tests of the training-step operators (include/dlv3p_train.h) and of the whole head training step
+(dlv3p_b200.train.HeadTrainer) against the oracle (oracle/train_ref.py: fp32 torch.autograd restatement of the reference's
+Keras graph, loss and optimizer).  Floating point: bf16 operands / activations, fp32 accumulation.  Tolerances are written
+at each assert: one bf16 rounding (2^-8 relative) for single operators, and for whole-step gradients a relative L2 error per
+tensor (the north star's logits tolerance is 1e-2 relative; gradients pass through ~25 bf16 rounding points each way)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from oracle import head_ref as R
+from oracle import train_ref as TR
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _t():
+    import torch
+    return torch
+
+
+def _call(name, *args):
+    import torch
+    from dlv3p_b200 import train_ffi
+    train_ffi.call(name, 0, *args, torch.cuda.current_stream().cuda_stream)
+
+
+def _bf(a):
+    torch = _t()
+    return torch.from_numpy(np.ascontiguousarray(a, np.float32)).cuda().to(torch.bfloat16).contiguous()
+
+
+def rel_l2(a, ref):
+    a, ref = np.asarray(a, np.float64), np.asarray(ref, np.float64)
+    return float(np.linalg.norm(a - ref) / max(np.linalg.norm(ref), 1e-30))
+
+
+# ---------------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize('M,N,K,out_fp32,splits', [
+    (300, 256, 2048, 0, 1),      # forward, ragged M
+    (1000, 48, 256, 0, 1),       # feature_projection0 shape (BN = 64 kernel)
+    (256, 2048, 256, 0, 1),      # data gradient: 8 N tiles
+    (512, 304, 256, 0, 1),       # N not a multiple of 256 (second tile ragged)
+    (304, 256, 4096, 1, 5),      # weight gradient: split-K, fp32 out
+    (2048, 256, 1024, 1, 3),
+    (256, 24, 8192, 1, 16),      # classifier weight gradient (padded NC)
+    (8, 256, 64, 0, 1),          # image pooling: one row group
+    (64, 256, 8, 1, 1),          # image pooling weight gradient: K = 8
+    (640, 72, 200, 1, 1),        # K not a multiple of 64, N between tiles
+])
+def test_gemm_nt(gpu, M, N, K, out_fp32, splits):
+    torch = _t()
+    from dlv3p_b200 import train_ffi
+    g = torch.Generator(device='cuda').manual_seed(M + N + K)
+    a = torch.randn(M, K, device='cuda', generator=g).to(torch.bfloat16)
+    b = torch.randn(N, K, device='cuda', generator=g).to(torch.bfloat16)
+    ldd = N if N % 8 == 0 else N + (8 - N % 8)
+    d = torch.full((M, ldd), 7.0, device='cuda', dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    part = torch.empty(max(1, train_ffi.gemm_partial_bytes(M, N, splits) // 4), device='cuda', dtype=torch.float32)
+    _call('dlv3p_train_gemm_nt', a.data_ptr(), K, b.data_ptr(), K, M, N, K, d.data_ptr(), ldd, out_fp32, splits, part.data_ptr())
+    torch.cuda.synchronize()
+    ref = a.double() @ b.double().t()
+    got = d[:, :N].double()
+    scale = float(ref.abs().max())
+    tol = (2.0 ** -8 if not out_fp32 else 1e-5) * scale            # one bf16 rounding of the result, or fp32 accumulation order
+    assert float((got - ref).abs().max()) <= tol
+    if ldd > N:
+        assert float((d[:, N:].float() - 7.0).abs().max()) == 0.0   # padding columns untouched
+
+
+def test_gemm_nt_strided_operands_and_output_slice(gpu):
+    """A read from a concat slice (lda > K), output written into a slice of a wider buffer."""
+    torch = _t()
+    g = torch.Generator(device='cuda').manual_seed(5)
+    M, N, K = 384, 256, 256
+    abuf = torch.randn(M, 1280, device='cuda', generator=g).to(torch.bfloat16)
+    b = torch.randn(N, K, device='cuda', generator=g).to(torch.bfloat16)
+    out = torch.zeros(M, 1280, device='cuda', dtype=torch.bfloat16)
+    _call('dlv3p_train_gemm_nt', abuf.data_ptr() + 512 * 2, 1280, b.data_ptr(), K, M, N, K, out.data_ptr() + 768 * 2, 1280, 0, 1, 0)
+    torch.cuda.synchronize()
+    ref = abuf[:, 512:768].double() @ b.double().t()
+    assert float((out[:, 768:1024].double() - ref).abs().max()) <= 2.0 ** -8 * float(ref.abs().max())
+    assert float(out[:, :768].abs().max()) == 0.0 and float(out[:, 1024:].abs().max()) == 0.0
+
+
+def test_gemm_rejects_bad_arguments(gpu):
+    import dlv3p_b200
+    torch = _t()
+    a = torch.zeros(64, 256, device='cuda', dtype=torch.bfloat16)
+    with pytest.raises(dlv3p_b200.Dlv3pError):
+        _call('dlv3p_train_gemm_nt', a.data_ptr(), 60, a.data_ptr(), 64, 64, 64, 60, a.data_ptr(), 64, 0, 1, 0)     # K % 8
+    with pytest.raises(dlv3p_b200.Dlv3pError):
+        _call('dlv3p_train_gemm_nt', a.data_ptr(), 256, a.data_ptr(), 256, 64, 64, 256, a.data_ptr(), 64, 1, 4, 0)  # split-K without partials
+
+
+@pytest.mark.parametrize('Rr,Cc', [(1024, 304), (130, 24), (8, 2048), (131072 // 8, 256)])
+def test_transpose(gpu, Rr, Cc):
+    torch = _t()
+    x = torch.randn(Rr, Cc, device='cuda').to(torch.bfloat16)
+    y = torch.zeros(Cc, Rr, device='cuda', dtype=torch.bfloat16)
+    _call('dlv3p_train_transpose', x.data_ptr(), Rr, Cc, Cc, y.data_ptr(), Rr)
+    torch.cuda.synchronize()
+    assert torch.equal(y, x.t().contiguous())
+
+
+# ---------------------------------------------------------------------------------------------------- BN backward
+@pytest.mark.parametrize('M,C,relu,ld', [(4096, 256, 1, 1280), (1000, 48, 1, 304), (777 * 8, 304, 0, 304), (16, 256, 1, 256)])
+def test_bn_training_forward_and_backward(gpu, M, C, relu, ld):
+    torch = _t()
+    from dlv3p_b200 import ffi, train_ffi
+    g = torch.Generator(device='cuda').manual_seed(M + C)
+    x = (torch.randn(M, C, device='cuda', generator=g) * 1.3 + 0.2).to(torch.bfloat16)
+    gamma = torch.rand(C, device='cuda', generator=g) + 0.5
+    beta = torch.randn(C, device='cuda', generator=g) * 0.1
+    ybuf = torch.zeros(M, ld, device='cuda', dtype=torch.bfloat16)
+    dybuf = torch.zeros(M, ld, device='cuda', dtype=torch.bfloat16)
+    off = ld - C - (ld - C) % 8
+    dybuf[:, off:off + C] = (torch.randn(M, C, device='cuda', generator=g) * 1e-3).to(torch.bfloat16)
+    stats = torch.zeros(2 * C + 1, device='cuda')
+    scratch = torch.zeros(max(ffi.bn_scratch_bytes(C), train_ffi.scratch_bytes(C)) // 4 + 16, device='cuda')
+    s = torch.cuda.current_stream().cuda_stream
+    ffi.bn_stats(x.data_ptr(), M, C, stats.data_ptr(), scratch.data_ptr(), s, 0)
+    _call('dlv3p_train_bn_apply', x.data_ptr(), M, C, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-5, relu, ybuf.data_ptr() + off * 2, ld)
+    sums = torch.zeros(2 * C, device='cuda')
+    dx = torch.zeros(M, C, device='cuda', dtype=torch.bfloat16)
+    _call('dlv3p_train_bn_bwd_stats', dybuf.data_ptr() + off * 2, ld, ybuf.data_ptr() + off * 2, ld, x.data_ptr(), M, C, stats.data_ptr(), 1e-5, relu,
+          sums.data_ptr(), scratch.data_ptr())
+    _call('dlv3p_train_bn_bwd_apply', dybuf.data_ptr() + off * 2, ld, ybuf.data_ptr() + off * 2, ld, x.data_ptr(), M, C, stats.data_ptr(), sums.data_ptr(),
+          gamma.data_ptr(), 1e-5, relu, dx.data_ptr())
+    torch.cuda.synchronize()
+    # reference: torch autograd in fp64 on the same bf16 inputs
+    xr = x.double().requires_grad_(True)
+    gr, br = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    yr = torch.nn.functional.batch_norm(xr, None, None, gr, br, training=True, eps=1e-5)
+    if relu:
+        yr = torch.relu(yr)
+    dy = dybuf[:, off:off + C].double()
+    yr.backward(dy)
+    y = ybuf[:, off:off + C].double()
+    assert float((y - yr.detach()).abs().max()) <= 2.0 ** -8 * max(1.0, float(yr.abs().max()))
+    # the ReLU mask of the kernel comes from ITS bf16 output; exclude elements whose reference output is within rounding of 0
+    assert rel_l2(sums[:C].cpu().numpy(), br.grad.cpu().numpy()) < 5e-3
+    assert rel_l2(sums[C:].cpu().numpy(), gr.grad.cpu().numpy()) < 5e-3
+    assert rel_l2(dx.float().cpu().numpy(), xr.grad.cpu().numpy()) < 1e-2
+    assert float(ybuf[:, :off].abs().max()) == 0.0 if off else True
+
+
+# ---------------------------------------------------------------------------------------------------- depthwise
+@pytest.mark.parametrize('B,H,W,C,rate', [(2, 32, 32, 64, 6), (1, 16, 24, 304, 1), (2, 8, 8, 16, 18), (1, 33, 17, 8, 2)])
+def test_depthwise_forward_dgrad_wgrad(gpu, B, H, W, C, rate):
+    torch = _t()
+    from dlv3p_b200 import train_ffi
+    F = torch.nn.functional
+    g = torch.Generator(device='cuda').manual_seed(B * H + C + rate)
+    x = torch.randn(B, H, W, C, device='cuda', generator=g).to(torch.bfloat16)
+    taps = (torch.randn(3, 3, C, device='cuda', generator=g) * 0.3).contiguous()
+    dy = torch.randn(B, H, W, C, device='cuda', generator=g).to(torch.bfloat16)
+    out = torch.zeros_like(x)
+    dx = torch.zeros_like(x)
+    dw = torch.zeros(9, C, device='cuda')
+    scratch = torch.zeros(train_ffi.scratch_bytes(C) // 4 + 16, device='cuda')
+    _call('dlv3p_train_depthwise', x.data_ptr(), B, H, W, C, rate, taps.data_ptr(), 0, out.data_ptr())
+    _call('dlv3p_train_depthwise', dy.data_ptr(), B, H, W, C, rate, taps.data_ptr(), 1, dx.data_ptr())
+    _call('dlv3p_train_depthwise_wgrad', x.data_ptr(), dy.data_ptr(), B, H, W, C, rate, dw.data_ptr(), scratch.data_ptr())
+    torch.cuda.synchronize()
+    xr = x.double().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = taps.double().permute(2, 0, 1).unsqueeze(1).requires_grad_(True)     # (C,1,3,3)
+    yr = F.conv2d(xr, wr, None, padding=rate, dilation=rate, groups=C)
+    yr.backward(dy.double().permute(0, 3, 1, 2))
+    ref_y = yr.detach().permute(0, 2, 3, 1)
+    assert float((out.double() - ref_y).abs().max()) <= 2.0 ** -8 * max(1.0, float(ref_y.abs().max()))
+    ref_dx = xr.grad.permute(0, 2, 3, 1)
+    assert float((dx.double() - ref_dx).abs().max()) <= 2.0 ** -8 * max(1.0, float(ref_dx.abs().max()))
+    ref_dw = wr.grad.squeeze(1).permute(1, 2, 0).reshape(9, C)
+    assert float((dw.double() - ref_dw).abs().max()) <= 1e-4 * max(1.0, float(ref_dw.abs().max()))
+
+
+# ---------------------------------------------------------------------------------------------------- bilinear
+@pytest.mark.parametrize('B,hi,wi,C,ho,wo', [(2, 32, 32, 256, 128, 128), (1, 8, 8, 16, 32, 32), (1, 9, 5, 8, 33, 17), (1, 4, 4, 8, 4, 4), (1, 16, 16, 8, 8, 8)])
+def test_resize_adjoint_nhwc(gpu, B, hi, wi, C, ho, wo):
+    torch = _t()
+    F = torch.nn.functional
+    g = torch.Generator(device='cuda').manual_seed(hi * wo + C)
+    ld = C + 48
+    dybuf = torch.randn(B, ho, wo, ld, device='cuda', generator=g).to(torch.bfloat16)
+    dx = torch.zeros(B, hi, wi, C, device='cuda', dtype=torch.bfloat16)
+    _call('dlv3p_train_resize_bwd', dybuf.data_ptr(), ld, B, hi, wi, C, ho, wo, dx.data_ptr())
+    torch.cuda.synchronize()
+    xr = torch.zeros(B, C, hi, wi, device='cuda', dtype=torch.float64, requires_grad=True)
+    F.interpolate(xr, size=(ho, wo), mode='bilinear', align_corners=False).backward(dybuf[..., :C].double().permute(0, 3, 1, 2))
+    ref = xr.grad.permute(0, 2, 3, 1)
+    assert float((dx.double() - ref).abs().max()) <= 2.0 ** -8 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize('B,NC,hi,wi,H,W', [(2, 21, 32, 32, 128, 128), (1, 5, 8, 8, 32, 32), (1, 3, 7, 9, 25, 31)])
+def test_loss_and_its_gradient(gpu, B, NC, hi, wi, H, W):
+    """pred_resize + Softmax + sparse CE (ignore 255) and d(loss)/d(low-res logits) vs torch autograd."""
+    torch = _t()
+    from dlv3p_b200 import train_ffi
+    F = torch.nn.functional
+    g = torch.Generator(device='cuda').manual_seed(NC + H)
+    NCp = (NC + 7) // 8 * 8
+    logits = torch.zeros(B * hi * wi, NCp, device='cuda')
+    logits[:, :NC] = torch.randn(B * hi * wi, NC, device='cuda', generator=g) * 3
+    bias = torch.randn(NC, device='cuda', generator=g) * 0.1
+    rng = np.random.default_rng(3)
+    lab = rng.integers(0, NC, size=(B, H, W)).astype(np.uint8)
+    lab[rng.random(lab.shape) < 0.1] = 255
+    labels = torch.from_numpy(lab).cuda()
+    inv_norm = 1.0 / (2 * B * H * W)                      # as if a second replica held the other half of the global batch
+    dfull = torch.zeros(B, NC, H, W, device='cuda')
+    loss = torch.zeros(2, device='cuda')
+    scratch = torch.zeros(train_ffi.loss_scratch_bytes() // 4 + 16, device='cuda')
+    dlow = torch.zeros(B * hi * wi, NCp, device='cuda', dtype=torch.bfloat16)
+    _call('dlv3p_train_softmax_ce', logits.data_ptr(), NCp, bias.data_ptr(), labels.data_ptr(), B, NC, hi, wi, H, W, 255, inv_norm, dfull.data_ptr(),
+          loss.data_ptr(), scratch.data_ptr())
+    _call('dlv3p_train_resize_bwd_planar', dfull.data_ptr(), B, NC, hi, wi, H, W, dlow.data_ptr(), NCp)
+    torch.cuda.synchronize()
+    zr = logits[:, :NC].double().reshape(B, hi, wi, NC).permute(0, 3, 1, 2).requires_grad_(True)
+    full = F.interpolate(zr + bias.double().view(1, NC, 1, 1), size=(H, W), mode='bilinear', align_corners=False)
+    prob = torch.softmax(full, dim=1)
+    lt = torch.from_numpy(lab.astype(np.int64)).cuda()
+    valid = lt != 255
+    pl = prob.gather(1, lt.clamp(max=NC - 1).unsqueeze(1)).squeeze(1)
+    ref_loss = (-torch.log(pl.clamp(1e-7, 1 - 1e-7)) * valid).sum() * inv_norm
+    ref_loss.backward()
+    assert abs(float(loss[0]) - float(ref_loss)) <= 1e-4 * abs(float(ref_loss))
+    assert int(loss[1]) == int(valid.sum())
+    ref_dlow = zr.grad.permute(0, 2, 3, 1).reshape(-1, NC)
+    assert float((dlow[:, :NC].double() - ref_dlow).abs().max()) <= 2.0 ** -8 * float(ref_dlow.abs().max())
+    assert float(dlow[:, NC:].abs().max()) == 0.0 if NCp > NC else True
+
+
+# ---------------------------------------------------------------------------------------------------- small operators
+def test_pool_broadcast_add_dropout_sgd_cast(gpu):
+    torch = _t()
+    from dlv3p_b200 import train_ffi
+    g = torch.Generator(device='cuda').manual_seed(11)
+    B, npix, C, ld = 3, 100, 72, 136
+    x = torch.randn(B * npix, ld, device='cuda', generator=g).to(torch.bfloat16)
+    out = torch.zeros(B, C, device='cuda', dtype=torch.bfloat16)
+    _call('dlv3p_train_rows_reduce', x.data_ptr() + 64 * 2, ld, B, npix, C, 1.0 / npix, out.data_ptr(), 0)
+    ref = x[:, 64:64 + C].float().reshape(B, npix, C).mean(1)
+    torch.cuda.synchronize()
+    assert float((out.float() - ref).abs().max()) <= 2.0 ** -8 * float(ref.abs().max()) + 1e-6
+    dst = torch.randn(B * npix, ld, device='cuda', generator=g).to(torch.bfloat16)
+    before = dst.clone()
+    _call('dlv3p_train_bcast_rows', out.data_ptr(), B, npix, C, 0.5, dst.data_ptr() + 64 * 2, ld, 1)
+    torch.cuda.synchronize()
+    want = before[:, 64:64 + C].float() + 0.5 * out.float().repeat_interleave(npix, 0)
+    assert float((dst[:, 64:64 + C].float() - want).abs().max()) <= 2.0 ** -8 * float(want.abs().max())
+    assert torch.equal(dst[:, :64], before[:, :64])
+    n = 4096
+    a, b = torch.randn(n, device='cuda', generator=g).to(torch.bfloat16), torch.randn(n, device='cuda', generator=g).to(torch.bfloat16)
+    c = torch.zeros_like(a)
+    _call('dlv3p_train_add', a.data_ptr(), b.data_ptr(), c.data_ptr(), n)
+    d = torch.zeros_like(a)
+    _call('dlv3p_train_dropout', a.data_ptr(), d.data_ptr(), n, 12345, 0.5)
+    torch.cuda.synchronize()
+    assert torch.equal(c, (a.float() + b.float()).to(torch.bfloat16))
+    keep = torch.from_numpy(train_ffi.dropout_keep_mask(n, 12345, 0.5)).cuda()
+    assert torch.equal(d, torch.where(keep, (a.float() * 2).to(torch.bfloat16), torch.zeros_like(a)))
+    w, gr, v = (torch.randn(1000, device='cuda', generator=g) for _ in range(3))
+    w0, v0 = w.clone(), v.clone()
+    _call('dlv3p_train_sgd', w.data_ptr(), gr.data_ptr(), v.data_ptr(), 1000, 0.01, 0.9, 2e-5, 1.0)
+    wb = torch.zeros(1000, device='cuda', dtype=torch.bfloat16)
+    _call('dlv3p_train_cast_bf16', w.data_ptr(), wb.data_ptr(), 1000)
+    torch.cuda.synchronize()
+    v1 = 0.9 * v0 - 0.01 * (gr + 2 * 2e-5 * w0)
+    assert torch.allclose(v, v1, rtol=1e-5, atol=1e-6) and torch.allclose(w, w0 + v1, rtol=1e-5, atol=1e-6)   # fp32, one fma of difference
+    assert torch.equal(wb, w.to(torch.bfloat16))
+
+
+# ---------------------------------------------------------------------------------------------------- the whole step
+def _step_case(B=2, seed=21):
+    cfg = R.HeadConfig(B=B, H=320, W=320, OS=16, Cin=64, Cskip=32, NC=21)      # 20x20 map: all three atrous rates reach neighbours
+    W = R.make_weights(cfg, seed)
+    feat, skip = R.make_inputs(cfg, seed + 1)
+    feat, skip = R.bf16_round(feat), R.bf16_round(skip)
+    labels = TR.make_labels(cfg, seed + 2)
+    return cfg, W, feat, skip, labels
+
+
+# Tolerances of the whole-step comparison.  The step is ill-conditioned at random initialisation: every training-mode
+# BatchNorm backward subtracts the projections of the incoming gradient on {1, xhat}, and what is left is an order of magnitude
+# smaller than what came in (measured: a 0.3 % difference in d(loss)/d(y) becomes 4 % behind decoder_conv1_pointwise_BN, in
+# the oracle as well as here — rounding ONLY the GEMM weights to bf16 in the fp32 oracle moves the deep gradients by 5-10 %,
+# and the oracle's own bf16 mode sits 15-35 % from its fp32 mode there; tools/train_diag.py prints the table).
+# Kernel-level parity is asserted operator by operator above (one bf16 rounding against fp64 autograd).  Here:
+#   * against the bf16-mode oracle (same rounding points): loss 2e-3; gradients nearest the loss 5e-3; every gradient tensor
+#     within GRAD_TOL relative L2; the whole gradient vector's cosine >= 0.998 (a wrong tap, scale or mask gives O(1) errors);
+#   * against the fp32-mode oracle (reference semantics): loss 1e-2 (the north star's bf16 tolerance) and the gradients nearest
+#     the loss 4e-2, where the conditioning has not yet amplified the forward's bf16 error.
+GRAD_TOL = 0.12
+HEAD_KEYS = [('conv_upsample', 'kernel'), ('conv_upsample', 'bias'), ('decoder_conv1_pointwise_BN', 'gamma'), ('decoder_conv1_pointwise_BN', 'beta')]
+
+
+def _compare_step(tr_grads, d_feat, d_skip, loss, ref, cfg, ref32=None):
+    assert abs(loss - ref['loss']) <= 2e-3 * abs(ref['loss']), (loss, ref['loss'])
+    worst = {}
+    dot = n1 = n2 = 0.0
+    for key, g in ref['grads'].items():
+        got = np.asarray(tr_grads[key], np.float64)
+        g = np.asarray(g, np.float64).reshape(got.shape)
+        worst[key] = rel_l2(got, g)
+        dot += float((got * g).sum()); n1 += float((got * got).sum()); n2 += float((g * g).sum())
+    worst['d_feat'] = rel_l2(d_feat, ref['d_feat'].reshape(d_feat.shape))
+    worst['d_skip'] = rel_l2(d_skip, ref['d_skip'].reshape(d_skip.shape))
+    cosine = dot / np.sqrt(n1 * n2)
+    print('whole-gradient cosine %.5f; worst tensor rel-L2 vs the bf16-mode oracle: %.4f (%s)' % ((cosine,) + max((v, str(k)) for k, v in worst.items())))
+    bad = {k: v for k, v in worst.items() if not v < GRAD_TOL}
+    assert not bad, 'gradient mismatch: %s' % bad
+    assert cosine >= 0.998, cosine
+    for key in HEAD_KEYS:
+        assert worst[key] < 5e-3, (key, worst[key])
+    if ref32 is not None:
+        assert abs(loss - ref32['loss']) <= 1e-2 * abs(ref32['loss']), (loss, ref32['loss'])
+        for key in HEAD_KEYS:
+            assert rel_l2(tr_grads[key], np.asarray(ref32['grads'][key]).reshape(tr_grads[key].shape)) < 4e-2, key
+    return worst
+
+
+def test_head_training_step_matches_the_oracle(gpu):
+    """forward + loss + backward (with Dropout) on one replica, then the SGD update and the moving statistics."""
+    torch = _t()
+    from dlv3p_b200 import train, train_ffi
+    cfg, W, feat, skip, labels = _step_case()
+    tr = train.HeadTrainer(cfg.B, cfg.H, cfg.W, cfg.OS, cfg.Cin, cfg.Cskip, cfg.NC, W, device=0, seed=5)
+    f, s, l = _bf(feat), _bf(skip), torch.from_numpy(labels).cuda()
+    tr.forward_backward(f, s, l)
+    torch.cuda.synchronize()
+    keep = train_ffi.dropout_keep_mask(cfg.B * cfg.h * cfg.w * 256, train.dropout_seed(5, 0, 0), 0.5)
+    ref = TR.head_train_forward_backward(feat, skip, labels, W, cfg, keep_mask=keep, mode='bf16')
+    ref32 = TR.head_train_forward_backward(feat, skip, labels, W, cfg, keep_mask=keep, mode='fp32')
+    grads = tr.get_grads()
+    _compare_step(grads, tr.T['dfeat'].float().cpu().numpy(), tr.T['dskip'].float().cpu().numpy(), tr.loss(), ref, cfg, ref32)
+    # update: weights after one SGD-momentum step with the l2 term, moving statistics with momentum 0.99
+    tr.all_reduce_gradients()
+    tr.apply_gradients()
+    torch.cuda.synchronize()
+    Wn, _ = TR.sgd_momentum_update(W, {k: np.asarray(v).reshape(np.asarray(W[k]).shape) for k, v in ref['grads'].items()}, {})
+    Wn = TR.moving_update(Wn, ref['batch_stats'])
+    got = tr.get_weights()
+    for key, wref in Wn.items():
+        w0 = np.asarray(W[key], np.float32)
+        delta_ref = np.asarray(wref, np.float32) - w0
+        delta = got[key].reshape(w0.shape) - w0
+        if np.abs(delta_ref).max() == 0:
+            assert np.abs(delta).max() == 0
+        else:
+            assert rel_l2(delta, delta_ref) < GRAD_TOL, key
+    # determinism: the same step on a fresh trainer gives bit-identical gradients
+    tr2 = train.HeadTrainer(cfg.B, cfg.H, cfg.W, cfg.OS, cfg.Cin, cfg.Cskip, cfg.NC, W, device=0, seed=5)
+    tr2.forward_backward(f, s, l)
+    torch.cuda.synchronize()
+    g2 = tr2.get_grads()
+    assert all(np.array_equal(grads[k], g2[k]) for k in grads)
+
+
+def test_training_reduces_the_loss(gpu):
+    torch = _t()
+    from dlv3p_b200 import train
+    cfg, W, feat, skip, labels = _step_case(B=2, seed=33)
+    tr = train.HeadTrainer(cfg.B, cfg.H, cfg.W, cfg.OS, cfg.Cin, cfg.Cskip, cfg.NC, W, device=0, seed=1, lr=0.05)
+    f, s, l = _bf(feat), _bf(skip), torch.from_numpy(labels).cuda()
+    losses = []
+    for _ in range(12):
+        tr.train_step(f, s, l)
+        losses.append(tr.loss())
+    assert np.isfinite(losses).all() and losses[-1] < losses[0] - 0.05, losses      # random labels: only the class prior can be learned
+
+
+def _ddp_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from dlv3p_b200 import train
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    cfg, W, feat, skip, labels = _step_case(B=2 * world, seed=44)
+    Bl = cfg.B // world
+    sl = slice(rank * Bl, (rank + 1) * Bl)
+    tr = train.HeadTrainer(Bl, cfg.H, cfg.W, cfg.OS, cfg.Cin, cfg.Cskip, cfg.NC, W, device=rank, seed=9)
+    f = torch.from_numpy(feat[sl]).cuda().to(torch.bfloat16).contiguous()
+    s = torch.from_numpy(skip[sl]).cuda().to(torch.bfloat16).contiguous()
+    l = torch.from_numpy(labels[sl]).cuda().contiguous()
+    tr.forward_backward(f, s, l)
+    tr.all_reduce_gradients()
+    torch.cuda.synchronize()
+    q.put((rank, tr.get_grads(), tr.T['dfeat'].float().cpu().numpy(), tr.T['dskip'].float().cpu().numpy(), tr.loss()))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_step_two_gpus_nccl(gpu):
+    """Two replicas (SyncBN statistics + gradient all-reduce over NCCL) == the oracle on the global batch."""
+    torch = _t()
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs (gpurun --gpus 2)')
+    import torch.multiprocessing as mp
+    from dlv3p_b200 import train, train_ffi
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = sorted([q.get(timeout=600) for _ in ps], key=lambda t: t[0])
+    for p in ps:
+        p.join(timeout=60)
+    cfg, W, feat, skip, labels = _step_case(B=4, seed=44)
+    n_local = 2 * cfg.h * cfg.w * 256
+    keep = np.concatenate([train_ffi.dropout_keep_mask(n_local, train.dropout_seed(9, 0, r), 0.5) for r in range(2)])
+    ref = TR.head_train_forward_backward(feat, skip, labels, W, cfg, keep_mask=keep, mode='bf16')
+    d_feat = np.concatenate([g[2].reshape(2, cfg.h, cfg.w, cfg.Cin) for g in got])
+    d_skip = np.concatenate([g[3].reshape(2, cfg.hs, cfg.ws, cfg.Cskip) for g in got])
+    for k in got[0][1]:
+        assert np.array_equal(got[0][1][k], got[1][1][k]), 'replicas disagree on %s after the all-reduce' % (k,)
+    _compare_step(got[0][1], d_feat, d_skip, got[0][4], ref, cfg)

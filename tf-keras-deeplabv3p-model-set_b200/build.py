@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'csrc', 'dlv3p_api.cu')
 OUT = os.path.join(HERE, 'libdlv3p.so')
-DEPS = [os.path.join(HERE, 'csrc', f) for f in ('dlv3p_api.cu', 'pw_gemm.cuh', 'pw_gemm2.cuh', 'dwpw_gemm2.cuh', 'aspp_dw_fast.cuh', 'aspp_dw_gather.cuh', 'bn_train.cuh', 'dwpw_gemm.cuh', 'mem_kernels.cuh', 'sm100_prims.cuh')] + \
-       [os.path.join(os.path.dirname(HERE), 'include', 'dlv3p.h')]
+DEPS = [os.path.join(HERE, 'csrc', f) for f in ('dlv3p_api.cu', 'pw_gemm.cuh', 'pw_gemm2.cuh', 'dwpw_gemm2.cuh', 'aspp_dw_fast.cuh', 'aspp_dw_gather.cuh', 'bn_train.cuh', 'tgemm.cuh', 'train_kernels.cuh', 'train_api.cuh', 'dwpw_gemm.cuh', 'mem_kernels.cuh', 'sm100_prims.cuh')] + \
+       [os.path.join(os.path.dirname(HERE), 'include', 'dlv3p.h'), os.path.join(os.path.dirname(HERE), 'include', 'dlv3p_train.h')]
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
               '-shared', '-Xcompiler', '-fPIC', '-cudart', 'static']

@@ -1596,11 +1596,16 @@ struct TmpDev {
   }
 };
 int op_prolog(int device, int* num_sms) {
+  static int cached_sms[64] = {};   // per-device SM count (cudaGetDeviceProperties costs ~100 us per call)
   CU_TRY(nullptr, cudaSetDevice(device));
-  cudaDeviceProp p;
-  CU_TRY(nullptr, cudaGetDeviceProperties(&p, device));
-  if (p.major != 10) return fail(nullptr, DLV3P_ERR_UNSUPPORTED, fmt("device sm_%d%d: kernels are sm_100a only", p.major, p.minor));
-  *num_sms = p.multiProcessorCount;
+  if (device < 0 || device >= 64 || !cached_sms[device]) {
+    cudaDeviceProp p;
+    CU_TRY(nullptr, cudaGetDeviceProperties(&p, device));
+    if (p.major != 10) return fail(nullptr, DLV3P_ERR_UNSUPPORTED, fmt("device sm_%d%d: kernels are sm_100a only", p.major, p.minor));
+    if (device < 0 || device >= 64) { *num_sms = p.multiProcessorCount; return 0; }
+    cached_sms[device] = p.multiProcessorCount;
+  }
+  *num_sms = cached_sms[device];
   return 0;
 }
 }  // namespace
@@ -1904,3 +1909,6 @@ int dlv3p_op_time(int device, int op, const int64_t* d, int ndims, int iters, in
 }
 
 }  // extern "C"
+
+// training-step operators (include/dlv3p_train.h)
+#include "train_api.cuh"

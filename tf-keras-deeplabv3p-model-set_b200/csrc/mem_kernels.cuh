@@ -510,6 +510,7 @@ struct DwParams {
   __nv_bfloat16* out;      // [B,H,W,C]
   int B, H, W, C, rate, relu;
   int wstride;             // row stride of w (>= C; packed taps may be zero padded)
+  int flip;                // 1: tap (u,v) reads w[2-u][2-v] — the data gradient of the same convolution (training); shift may be NULL
 };
 __global__ void __launch_bounds__(256) depthwise3x3_kernel(const DwParams P) {
   const int vecs = P.C >> 3;
@@ -524,11 +525,14 @@ __global__ void __launch_bounds__(256) depthwise3x3_kernel(const DwParams P) {
     const int b = static_cast<int>(pix / P.H);
     const int c0 = vec * 8;
     float acc[8];
-    {
+    if (P.shift) {
       const float4 s0 = __ldg(reinterpret_cast<const float4*>(P.shift + c0));
       const float4 s1 = __ldg(reinterpret_cast<const float4*>(P.shift + c0 + 4));
       acc[0] = s0.x; acc[1] = s0.y; acc[2] = s0.z; acc[3] = s0.w;
       acc[4] = s1.x; acc[5] = s1.y; acc[6] = s1.z; acc[7] = s1.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
     }
     const __nv_bfloat16* xb = P.x + static_cast<size_t>(b) * P.H * P.W * P.C + c0;
 #pragma unroll
@@ -541,8 +545,9 @@ __global__ void __launch_bounds__(256) depthwise3x3_kernel(const DwParams P) {
         if (jj < 0 || jj >= P.W) continue;
         float xv[8];
         unpack8(ldg_nc_v4(xb + (static_cast<size_t>(ii) * P.W + jj) * P.C), xv);
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(P.w + (u * 3 + v) * P.wstride + c0));
-        const float4 w1 = __ldg(reinterpret_cast<const float4*>(P.w + (u * 3 + v) * P.wstride + c0 + 4));
+        const int tap = P.flip ? 8 - (u * 3 + v) : u * 3 + v;
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(P.w + tap * P.wstride + c0));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(P.w + tap * P.wstride + c0 + 4));
         acc[0] = fmaf(xv[0], w0.x, acc[0]); acc[1] = fmaf(xv[1], w0.y, acc[1]);
         acc[2] = fmaf(xv[2], w0.z, acc[2]); acc[3] = fmaf(xv[3], w0.w, acc[3]);
         acc[4] = fmaf(xv[4], w1.x, acc[4]); acc[5] = fmaf(xv[5], w1.y, acc[5]);

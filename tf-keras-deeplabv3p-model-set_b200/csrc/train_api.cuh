@@ -1,0 +1,301 @@
+// train_api.cuh — C ABI (include/dlv3p_train.h) of the training-step operators; included at the end of dlv3p_api.cu so it
+// shares that file's helpers (tensor-map encoding, error strings).  Every entry point is asynchronous on the caller's
+// stream and allocates nothing: the SM count is cached per device, tensor maps travel as kernel parameters.
+#pragma once
+
+#include "../../include/dlv3p_train.h"
+#include "tgemm.cuh"
+#include "train_kernels.cuh"
+
+namespace {
+
+int train_prolog(int device, int* num_sms) {
+  static int cached_sms[64] = {};
+  if (device < 0 || device >= 64) return fail(nullptr, DLV3P_ERR_INVALID, "bad device index");
+  CU_TRY(nullptr, cudaSetDevice(device));
+  if (!cached_sms[device]) {
+    int major = 0, sms = 0;
+    CU_TRY(nullptr, cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    CU_TRY(nullptr, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    if (major != 10) return fail(nullptr, DLV3P_ERR_UNSUPPORTED, fmt("device sm_%d: kernels are sm_100a only", major));
+    cached_sms[device] = sms;
+  }
+  *num_sms = cached_sms[device];
+  return 0;
+}
+
+template <int BN>
+cudaError_t launch_tgemm_t(const TgLaunch& L, int num_sms, cudaStream_t st) {
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(tgemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TgCfg<BN>::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_done[dev & 63] = true;
+  }
+  const int items = L.m_tiles * L.n_tiles * L.splits;
+  const int grid = items < num_sms ? items : num_sms;
+  tgemm_kernel<BN><<<grid, kTgThreads, TgCfg<BN>::kSmemBytes, st>>>(L);
+  return cudaGetLastError();
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+size_t dlv3p_train_gemm_partial_bytes(int64_t M, int N, int splits) {
+  return splits > 1 ? static_cast<size_t>(splits) * static_cast<size_t>(M) * static_cast<size_t>(N) * sizeof(float) : 0;
+}
+
+int dlv3p_train_gemm_nt(int device, const void* a, int64_t lda, const void* b, int64_t ldb, int64_t M, int N, int64_t K, void* d, int64_t ldd,
+                        int out_fp32, int splits, void* d_partial, void* cuda_stream) {
+  int sms = 0, r = train_prolog(device, &sms);
+  if (r) return r;
+  if (!a || !b || !d || M < 1 || N < 1 || K < 8 || K % 8 || lda % 8 || ldb % 8 || lda < K || ldb < K || ldd < N || !aligned16(a) || !aligned16(b) ||
+      M > (1ll << 30) || K > (1ll << 30))
+    return fail(nullptr, DLV3P_ERR_INVALID, "train_gemm_nt: bad arguments (K, lda, ldb multiples of 8; 16-byte aligned operands)");
+  if (!out_fp32 && (ldd % 8 || !aligned16(d))) return fail(nullptr, DLV3P_ERR_INVALID, "train_gemm_nt: bf16 output needs ldd % 8 == 0 and a 16-byte aligned base");
+  if (out_fp32 && (ldd % 4 || !aligned16(d))) return fail(nullptr, DLV3P_ERR_INVALID, "train_gemm_nt: fp32 output needs ldd % 4 == 0 and a 16-byte aligned base");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const int BN = N > 64 ? 256 : 64;
+  TgLaunch L{};
+  std::string terr;
+  if (!encode_2d_sw128(&L.tmap_a, a, M, K, lda, 128, &terr) || !encode_2d_sw128(&L.tmap_b, b, N, K, ldb, BN >= 128 ? 128 : BN, &terr))
+    return fail(nullptr, DLV3P_ERR_CUDA, terr);
+  L.M = static_cast<int>(M); L.N = N; L.K = static_cast<int>(K);
+  L.m_tiles = ceil_div(L.M, kTgBM); L.n_tiles = ceil_div(N, BN);
+  L.kblocks = ceil_div(L.K, kTgBK);
+  if (splits < 1) splits = 1;
+  if (splits > L.kblocks) splits = L.kblocks;
+  L.kb_per_split = ceil_div(L.kblocks, splits);
+  L.splits = ceil_div(L.kblocks, L.kb_per_split);
+  if (L.splits > 1) {
+    if (!d_partial || (N % 4)) return fail(nullptr, DLV3P_ERR_INVALID, "train_gemm_nt: split-K needs d_partial and N % 4 == 0");
+    L.out = d_partial; L.ldd = N; L.out_mode = kTgOutPartial;
+  } else {
+    L.out = d; L.ldd = ldd; L.out_mode = out_fp32 ? kTgOutF32 : kTgOutBf16;
+  }
+  CU_TRY(nullptr, BN == 256 ? launch_tgemm_t<256>(L, sms, st) : launch_tgemm_t<64>(L, sms, st));
+  if (L.splits > 1) {
+    tgemm_reduce_kernel<<<grid_for(static_cast<size_t>(M) * N, sms), 256, 0, st>>>(static_cast<const float*>(d_partial), L.splits, M, N, d, ldd, out_fp32);
+    CU_TRY(nullptr, cudaGetLastError());
+  }
+  return DLV3P_OK;
+}
+
+int dlv3p_train_transpose(int device, const void* in, int64_t R, int C, int64_t ld_in, void* out, int64_t ld_out, void* cuda_stream) {
+  int sms = 0, r = train_prolog(device, &sms);
+  if (r) return r;
+  if (!in || !out || R < 2 || C < 2 || R % 2 || C % 2 || ld_in % 2 || ld_out % 2 || ld_in < C || ld_out < R)
+    return fail(nullptr, DLV3P_ERR_INVALID, "train_transpose: bad arguments (R, C, strides even)");
+  transpose_bf16_kernel<<<dim3(static_cast<unsigned>((R + 63) / 64), ceil_div(C, 64)), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+      static_cast<const __nv_bfloat16*>(in), R, C, ld_in, static_cast<__nv_bfloat16*>(out), ld_out);
+  CU_TRY(nullptr, cudaGetLastError());
+  return DLV3P_OK;
+}
+
+int dlv3p_train_bn_apply(int device, const void* x, int64_t M, int C, const float* d_stats, const float* d_gamma, const float* d_beta, float eps, int relu,
+                         void* y, int64_t ldy, void* cuda_stream) {
+  int sms = 0, r = train_prolog(device, &sms);
+  if (r) return r;
+  if (!x || !d_stats || !d_gamma || !d_beta || !y || M < 1 || C < 8 || C % 8 || ldy % 8 || ldy < C || !aligned16(y))
+    return fail(nullptr, DLV3P_ERR_INVALID, "train_bn_apply: bad arguments (C % 8, ldy % 8)");
+  bn_apply_ld_kernel<<<grid_for(static_cast<size_t>(M) * (C / 8), sms), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), M, C, d_stats, d_gamma, d_beta, eps, relu, static_cast<__nv_bfloat16*>(y), ldy);
+  CU_TRY(nullptr, cudaGetLastError());
+  return DLV3P_OK;
+}
+
+size_t dlv3p_train_scratch_bytes(int C) { return static_cast<size_t>(kTrBands) * 9 * (C > 0 ? C : 0) * sizeof(float); }
+
+int dlv3p_train_bn_bwd_stats(int device, const void* dy, int64_t ld_dy, const void* y, int64_t ld_y, const void* x, int64_t M, int C, const float* d_stats,
+                             float eps, int relu, float* d_sums, void* d_scratch, void* cuda_stream) {
+  int sms = 0, r = train_prolog(device, &sms);
+  if (r) return r;
+  if (!dy || !x || !d_stats || !d_sums || !d_scratch || (relu && !y) || M < 1 || C < 2 || C % 2 || ld_dy % 2 || ld_y % 2)
+    return fail(nullptr, DLV3P_ERR_INVALID, "train_bn_bwd_stats: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  bn_bwd_stats_partial_kernel<<<dim3(ceil_div(C, 64), kTrBands), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dy), ld_dy, static_cast<const __nv_bfloat16*>(y), ld_y,
+                                                                                static_cast<const __nv_bfloat16*>(x), M, C, d_stats, eps, relu,
+                                                                                static_cast<float*>(d_scratch));
+  bands_final_kernel<<<ceil_div(2 * C, 256), 256, 0, st>>>(static_cast<const float*>(d_scratch), kTrBands, 2 * C, d_sums);
+  CU_TRY(nullptr, cudaGetLastError());
+  return DLV3P_OK;
+}
+
+int dlv3p_train_bn_bwd_apply(int device, const void* dy, int64_t ld_dy, const void* y, int64_t ld_y, const void* x, int64_t M, int C, const float* d_stats,
+                             const float* d_sums, const float* d_gamma, float eps, int relu, void* dx, void* cuda_stream) {
+  int sms = 0, r = train_prolog(device, &sms);
+  if (r) return r;
+  if (!dy || !x || !d_stats || !d_sums || !d_gamma || !dx || (relu && !y) || M < 1 || C < 8 || C % 8 || ld_dy % 8 || ld_y % 8 || !aligned16(dy) ||
+      (relu && !aligned16(y)))
+    return fail(nullptr, DLV3P_ERR_INVALID, "train_bn_bwd_apply: bad arguments (C % 8, strides % 8, 16-byte aligned slices)");
+  bn_bwd_apply_kernel<<<grid_for(static_cast<size_t>(M) * (C / 8), sms), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+      static_cast<const __nv_bfloat16*>(dy), ld_dy, static_cast<const __nv_bfloat16*>(y), ld_y, static_cast<const __nv_bfloat16*>(x), M, C, d_stats, d_sums,
+      d_gamma, eps, relu, static_cast<__nv_bfloat16*>(dx));
+  CU_TRY(nullptr, cudaGetLastError());
+  return DLV3P_OK;
+}
+
+int dlv3p_train_depthwise(int device, const void* x, int B, int H, int W_, int C, int rate, const float* d_taps, int flip, void* out, void* cuda_stream) {
+  int sms = 0, r = train_prolog(device, &sms);
+  if (r) return r;
+  if (!x || !d_taps || !out || B < 1 || H < 1 || W_ < 1 || C < 8 || C % 8 || rate < 1 || !aligned16(d_taps))
+    return fail(nullptr, DLV3P_ERR_INVALID, "train_depthwise: bad arguments (C % 8)");
+  DwParams P{};
+  P.x = static_cast<const __nv_bfloat16*>(x); P.w = d_taps; P.shift = nullptr; P.out = static_cast<__nv_bfloat16*>(out);
+  P.B = B; P.H = H; P.W = W_; P.C = C; P.rate = rate; P.relu = 0; P.wstride = C; P.flip = flip ? 1 : 0;
+  depthwise3x3_kernel<<<grid_for(static_cast<size_t>(B) * H * W_ * (C / 8), sms), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(P);
+  CU_TRY(nullptr, cudaGetLastError());
+  return DLV3P_OK;
+}
+
+int dlv3p_train_depthwise_wgrad(int device, const void* x, const void* dy, int B, int H, int W_, int C, int rate, float* d_dw, void* d_scratch,
+                                void* cuda_stream) {
+  int sms = 0, r = train_prolog(device, &sms);
+  if (r) return r;
+  if (!x || !dy || !d_dw || !d_scratch || B < 1 || H < 1 || W_ < 1 || C < 2 || C % 2 || rate < 1)
+    return fail(nullptr, DLV3P_ERR_INVALID, "train_depthwise_wgrad: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  dw_wgrad_partial_kernel<<<dim3(ceil_div(C, 64), kTrBands), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), B, H, W_, C, rate,
+                                                                            static_cast<float*>(d_scratch));
+  bands_final_kernel<<<ceil_div(9 * C, 256), 256, 0, st>>>(static_cast<const float*>(d_scratch), kTrBands, 9 * C, d_dw);
+  CU_TRY(nullptr, cudaGetLastError());
+  return DLV3P_OK;
+}
+
+int dlv3p_train_resize(int device, const void* x, int B, int hi, int wi, int C, int ho, int wo, void* out, int64_t ld_out, void* cuda_stream) {
+  int sms = 0, r = train_prolog(device, &sms);
+  if (r) return r;
+  if (!x || !out || C < 8 || C % 8 || hi < 1 || wi < 1 || ho < 1 || wo < 1 || ld_out % 8 || ld_out < C || !aligned16(out))
+    return fail(nullptr, DLV3P_ERR_INVALID, "train_resize: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  ResizeParams P{};
+  P.x = static_cast<const __nv_bfloat16*>(x); P.out = static_cast<__nv_bfloat16*>(out);
+  P.B = B; P.hi = hi; P.wi = wi; P.C = C; P.ho = ho; P.wo = wo; P.ldo = static_cast<int>(ld_out); P.col_off = 0;
+  P.sy = static_cast<float>(hi) / static_cast<float>(ho); P.sx = static_cast<float>(wi) / static_cast<float>(wo);
+  if (ho == 4 * hi && wo == 4 * wi)
+    resize_bilinear_x4_kernel<<<grid_for(static_cast<size_t>(B) * (hi + 1) * (wi + 1) * 32, sms), 256, 0, st>>>(P);
+  else
+    resize_bilinear_kernel<<<dim3(ho, B), 256, 0, st>>>(P);
+  CU_TRY(nullptr, cudaGetLastError());
+  return DLV3P_OK;
+}
+
+int dlv3p_train_resize_bwd(int device, const void* dy, int64_t ld_dy, int B, int hi, int wi, int C, int ho, int wo, void* dx, void* cuda_stream) {
+  int sms = 0, r = train_prolog(device, &sms);
+  if (r) return r;
+  if (!dy || !dx || C < 8 || C % 8 || hi < 1 || wi < 1 || ho < 1 || wo < 1 || ld_dy % 8 || ld_dy < C || !aligned16(dy))
+    return fail(nullptr, DLV3P_ERR_INVALID, "train_resize_bwd: bad arguments");
+  ResizeBwdParams P{};
+  P.dy = static_cast<const __nv_bfloat16*>(dy); P.dx = static_cast<__nv_bfloat16*>(dx); P.ld_dy = ld_dy;
+  P.B = B; P.hi = hi; P.wi = wi; P.C = C; P.ho = ho; P.wo = wo;
+  P.sy = static_cast<float>(hi) / static_cast<float>(ho); P.sx = static_cast<float>(wi) / static_cast<float>(wo);
+  resize_bwd_nhwc_kernel<<<grid_for(static_cast<size_t>(B) * hi * wi * (C / 8), sms), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(P);
+  CU_TRY(nullptr, cudaGetLastError());
+  return DLV3P_OK;
+}
+
+namespace { constexpr int kLossBlocks = 148 * 8; }
+size_t dlv3p_train_loss_scratch_bytes(void) { return static_cast<size_t>(kLossBlocks) * 2 * sizeof(float); }
+
+int dlv3p_train_softmax_ce(int device, const float* logits, int64_t ldl, const float* bias, const uint8_t* labels, int B, int NC, int hi, int wi, int H, int W_,
+                           int ignore_index, float inv_norm, float* d_full, float* d_loss, void* d_scratch, void* cuda_stream) {
+  int sms = 0, r = train_prolog(device, &sms);
+  if (r) return r;
+  if (!logits || !bias || !labels || !d_full || !d_loss || !d_scratch || B < 1 || NC < 1 || NC > 256 || hi < 1 || wi < 1 || H < 1 || W_ < 1 || ldl < NC)
+    return fail(nullptr, DLV3P_ERR_INVALID, "train_softmax_ce: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  LossParams P{};
+  P.logits = logits; P.bias = bias; P.labels = labels; P.d_full = d_full; P.block_part = static_cast<float*>(d_scratch); P.ldl = ldl;
+  P.B = B; P.NC = NC; P.hi = hi; P.wi = wi; P.H = H; P.W = W_; P.ignore = ignore_index;
+  P.sy = static_cast<float>(hi) / static_cast<float>(H); P.sx = static_cast<float>(wi) / static_cast<float>(W_);
+  P.inv_norm = inv_norm;
+  const size_t total = static_cast<size_t>(B) * H * W_;
+  int grid = static_cast<int>((total + 255) / 256);
+  if (grid > kLossBlocks) grid = kLossBlocks;
+  softmax_ce_kernel<<<grid, 256, 0, st>>>(P);
+  loss_final_kernel<<<1, 32, 0, st>>>(static_cast<const float*>(d_scratch), grid, inv_norm, d_loss);
+  CU_TRY(nullptr, cudaGetLastError());
+  return DLV3P_OK;
+}
+
+int dlv3p_train_resize_bwd_planar(int device, const float* d_full, int B, int NC, int hi, int wi, int H, int W_, void* dx, int64_t ld_dx, void* cuda_stream) {
+  int sms = 0, r = train_prolog(device, &sms);
+  if (r) return r;
+  if (!d_full || !dx || B < 1 || NC < 1 || hi < 1 || wi < 1 || H < 1 || W_ < 1 || ld_dx < NC)
+    return fail(nullptr, DLV3P_ERR_INVALID, "train_resize_bwd_planar: bad arguments");
+  ResizeBwdPlanarParams P{};
+  P.dy = d_full; P.dx = static_cast<__nv_bfloat16*>(dx); P.ld_dx = ld_dx; P.B = B; P.NC = NC; P.hi = hi; P.wi = wi; P.ho = H; P.wo = W_;
+  P.sy = static_cast<float>(hi) / static_cast<float>(H); P.sx = static_cast<float>(wi) / static_cast<float>(W_);
+  resize_bwd_planar_kernel<<<grid_for(static_cast<size_t>(B) * NC * hi * wi, sms), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(P);
+  CU_TRY(nullptr, cudaGetLastError());
+  return DLV3P_OK;
+}
+
+int dlv3p_train_rows_reduce(int device, const void* x, int64_t ld, int B, int npix, int C, float scale, void* out, int out_fp32, void* cuda_stream) {
+  int sms = 0, r = train_prolog(device, &sms);
+  if (r) return r;
+  if (!x || !out || B < 1 || npix < 1 || C < 2 || C % 2 || ld % 2 || ld < C) return fail(nullptr, DLV3P_ERR_INVALID, "train_rows_reduce: bad arguments");
+  rows_reduce_kernel<<<dim3(ceil_div(C, 64), B), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(static_cast<const __nv_bfloat16*>(x), ld, npix, C, scale,
+                                                                                                 out_fp32 ? nullptr : static_cast<__nv_bfloat16*>(out),
+                                                                                                 out_fp32 ? static_cast<float*>(out) : nullptr);
+  CU_TRY(nullptr, cudaGetLastError());
+  return DLV3P_OK;
+}
+
+int dlv3p_train_bcast_rows(int device, const void* src, int B, int npix, int C, float scale, void* dst, int64_t ld, int accumulate, void* cuda_stream) {
+  int sms = 0, r = train_prolog(device, &sms);
+  if (r) return r;
+  if (!src || !dst || B < 1 || npix < 1 || C < 8 || C % 8 || ld % 8 || ld < C || !aligned16(dst) || !aligned16(src))
+    return fail(nullptr, DLV3P_ERR_INVALID, "train_bcast_rows: bad arguments");
+  bcast_rows_kernel<<<grid_for(static_cast<size_t>(B) * npix * (C / 8), sms), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), B, npix, C, scale, static_cast<__nv_bfloat16*>(dst), ld, accumulate);
+  CU_TRY(nullptr, cudaGetLastError());
+  return DLV3P_OK;
+}
+
+int dlv3p_train_add(int device, const void* a, const void* b, void* out, int64_t n, void* cuda_stream) {
+  int sms = 0, r = train_prolog(device, &sms);
+  if (r) return r;
+  if (!a || !b || !out || n < 8 || n % 8) return fail(nullptr, DLV3P_ERR_INVALID, "train_add: bad arguments (n % 8)");
+  add_bf16_kernel<<<grid_for(static_cast<size_t>(n / 8), sms), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+      static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), static_cast<__nv_bfloat16*>(out), static_cast<size_t>(n / 8));
+  CU_TRY(nullptr, cudaGetLastError());
+  return DLV3P_OK;
+}
+
+int dlv3p_train_dropout(int device, const void* x, void* out, int64_t n, uint32_t seed, float rate, void* cuda_stream) {
+  int sms = 0, r = train_prolog(device, &sms);
+  if (r) return r;
+  if (!x || !out || n < 8 || n % 8 || n >= (1ll << 32) || !(rate >= 0.0f) || !(rate < 1.0f)) return fail(nullptr, DLV3P_ERR_INVALID, "train_dropout: bad arguments");
+  const uint32_t threshold = static_cast<uint32_t>(static_cast<double>(rate) * 4294967296.0);
+  dropout_kernel<<<grid_for(static_cast<size_t>(n / 8), sms), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), static_cast<size_t>(n / 8), seed, threshold, 1.0f / (1.0f - rate));
+  CU_TRY(nullptr, cudaGetLastError());
+  return DLV3P_OK;
+}
+
+int dlv3p_train_sgd(int device, float* w, const float* g, float* v, int64_t n, float lr, float momentum, float l2, float gscale, void* cuda_stream) {
+  int sms = 0, r = train_prolog(device, &sms);
+  if (r) return r;
+  if (!w || !g || !v || n < 1) return fail(nullptr, DLV3P_ERR_INVALID, "train_sgd: bad arguments");
+  sgd_kernel<<<grid_for(static_cast<size_t>(n), sms), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(w, g, v, static_cast<size_t>(n), lr, momentum, l2, gscale);
+  CU_TRY(nullptr, cudaGetLastError());
+  return DLV3P_OK;
+}
+
+int dlv3p_train_cast_bf16(int device, const float* in, void* out, int64_t n, void* cuda_stream) {
+  int sms = 0, r = train_prolog(device, &sms);
+  if (r) return r;
+  if (!in || !out || n < 1) return fail(nullptr, DLV3P_ERR_INVALID, "train_cast_bf16: bad arguments");
+  cast_f32_bf16_any_kernel<<<grid_for(static_cast<size_t>(n), sms), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(in, static_cast<__nv_bfloat16*>(out),
+                                                                                                                      static_cast<size_t>(n));
+  CU_TRY(nullptr, cudaGetLastError());
+  return DLV3P_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,458 @@
+// train_kernels.cuh — the memory-bound kernels of the head's TRAINING step (BASELINE cfg 5; reference train.py:143-169
+// with MirroredStrategy, SyncBatchNormalization layers.py:63-70, loss deeplabv3p/loss.py:121-156, SGD momentum
+// common/model_utils.py:122-123, l2(2e-5) regulariser layers.py:12-21).  The GEMMs are in tgemm.cuh; the forward
+// statistics kernels in bn_train.cuh; the depthwise / bilinear forward kernels are shared with inference (mem_kernels.cuh).
+//   bn_apply_ld_kernel          y = BN(x) [ReLU], output into a concat slice (row stride ldy)
+//   bn_bwd_stats_* / _apply     SyncBN backward: per-replica sum(g), sum(g * xhat) (all-reduced by the caller), then dx
+//   dw_wgrad_*                  depthwise 3x3 (dilated) weight gradient: 9 per-channel reductions over all pixels
+//   resize_bwd_nhwc_kernel      adjoint of tf.image.resize bilinear (gather form: deterministic, no atomics)
+//   softmax_ce_kernel           pred_resize + Softmax + sparse CE with ignore_index, loss and d(logits) at full resolution
+//   resize_bwd_planar_kernel    adjoint of pred_resize on the planar fp32 gradient -> bf16 rows for the classifier GEMMs
+//   rows_reduce / bcast_rows    image pooling (mean over pixels) and its adjoint, per-image column sums
+//   dropout / add / sgd         Dropout(0.5) with a counter-based mask, gradient accumulation, SGD-momentum + L2 update
+// Every reduction uses a fixed tree (no atomics): results are bit-reproducible run to run.
+#pragma once
+
+#include "mem_kernels.cuh"
+
+namespace dlv3p {
+
+constexpr int kTrBands = 64;
+
+__device__ __forceinline__ void bn_consts(const float* __restrict__ stats, int C, int c, float eps, float& mean, float& invstd) {
+  const float inv_n = 1.0f / stats[2 * C];
+  mean = stats[c] * inv_n;
+  const float var = fmaxf(stats[C + c] * inv_n - mean * mean, 0.0f);
+  invstd = rsqrtf(var + eps);
+}
+
+// y[row*ldy + c] = (x - mean) * gamma * invstd + beta [ReLU]; x dense [M, C]; one thread = 8 channels of one row
+__global__ void __launch_bounds__(256) bn_apply_ld_kernel(const __nv_bfloat16* __restrict__ x, long long M, int C, const float* __restrict__ stats,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int relu,
+                                                          __nv_bfloat16* __restrict__ y, long long ldy) {
+  const int vecs = C >> 3;
+  const long long total = M * vecs;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int vec = static_cast<int>(idx % vecs);
+    const long long row = idx / vecs;
+    float v[8];
+    unpack8(ldg_nc_v4(x + idx * 8), v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = vec * 8 + k;
+      float mean, invstd;
+      bn_consts(stats, C, c, eps, mean, invstd);
+      v[k] = (v[k] - mean) * (gamma[c] * invstd) + beta[c];
+      if (relu) v[k] = fmaxf(v[k], 0.0f);
+    }
+    stg_v4(y + row * ldy + vec * 8, pack8(v));
+  }
+}
+
+// grid (ceil(C/64), kTrBands), block 256.  g = dy * (y > 0) when relu; partial [kTrBands][2][C] = sum g | sum g*xhat
+__global__ void __launch_bounds__(256) bn_bwd_stats_partial_kernel(const __nv_bfloat16* __restrict__ dy, long long ld_dy, const __nv_bfloat16* __restrict__ y,
+                                                                   long long ld_y, const __nv_bfloat16* __restrict__ x, long long M, int C,
+                                                                   const float* __restrict__ stats, float eps, int relu, float* __restrict__ partial) {
+  __shared__ float s_red[8][2][64];
+  const int chunk = blockIdx.x, band = blockIdx.y;
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int c0 = chunk * 64 + lane * 2;
+  const long long rows_per_band = (M + kTrBands - 1) / kTrBands;
+  const long long r0 = band * rows_per_band, r1 = min(M, r0 + rows_per_band);
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  if (c0 < C) {
+    float m0, i0, m1, i1;
+    bn_consts(stats, C, c0, eps, m0, i0);
+    bn_consts(stats, C, c0 + 1, eps, m1, i1);
+    for (long long r = r0 + wp; r < r1; r += 8) {
+      const uint32_t dv = __ldg(reinterpret_cast<const unsigned int*>(dy + r * ld_dy + c0));
+      float g0 = bf16_lo(dv), g1 = bf16_hi(dv);
+      if (relu) {
+        const uint32_t yv = __ldg(reinterpret_cast<const unsigned int*>(y + r * ld_y + c0));
+        if (!(bf16_lo(yv) > 0.0f)) g0 = 0.0f;
+        if (!(bf16_hi(yv) > 0.0f)) g1 = 0.0f;
+      }
+      const uint32_t xv = __ldg(reinterpret_cast<const unsigned int*>(x + r * C + c0));
+      s0 += g0; s1 += g1;
+      q0 = fmaf(g0, (bf16_lo(xv) - m0) * i0, q0);
+      q1 = fmaf(g1, (bf16_hi(xv) - m1) * i1, q1);
+    }
+  }
+  s_red[wp][0][lane * 2] = s0; s_red[wp][0][lane * 2 + 1] = s1;
+  s_red[wp][1][lane * 2] = q0; s_red[wp][1][lane * 2 + 1] = q1;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, j = threadIdx.x & 63;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += s_red[w][which][j];
+    const int c = chunk * 64 + j;
+    if (c < C) partial[(static_cast<size_t>(band) * 2 + which) * C + c] = s;
+  }
+}
+// sums[2C] = sum over bands (fixed order)
+__global__ void bands_final_kernel(const float* __restrict__ partial, int bands, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float s = 0.f;
+    for (int b = 0; b < bands; ++b) s += partial[static_cast<size_t>(b) * n + i];
+    out[i] = s;
+  }
+}
+// dx = gamma * invstd * (g - S1/n - xhat * S2/n), n = GLOBAL row count (stats[2C], all-reduced), sums all-reduced
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, long long ld_dy, const __nv_bfloat16* __restrict__ y,
+                                                           long long ld_y, const __nv_bfloat16* __restrict__ x, long long M, int C,
+                                                           const float* __restrict__ stats, const float* __restrict__ sums, const float* __restrict__ gamma,
+                                                           float eps, int relu, __nv_bfloat16* __restrict__ dx) {
+  const int vecs = C >> 3;
+  const long long total = M * vecs;
+  const float inv_n = 1.0f / stats[2 * C];
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int vec = static_cast<int>(idx % vecs);
+    const long long row = idx / vecs;
+    float g[8], xv[8], yv[8];
+    unpack8(ldg_nc_v4(dy + row * ld_dy + vec * 8), g);
+    unpack8(ldg_nc_v4(x + idx * 8), xv);
+    if (relu) unpack8(ldg_nc_v4(y + row * ld_y + vec * 8), yv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = vec * 8 + k;
+      float mean, invstd;
+      bn_consts(stats, C, c, eps, mean, invstd);
+      float gg = g[k];
+      if (relu && !(yv[k] > 0.0f)) gg = 0.0f;
+      const float xh = (xv[k] - mean) * invstd;
+      g[k] = gamma[c] * invstd * (gg - sums[c] * inv_n - xh * sums[C + c] * inv_n);
+    }
+    stg_v4(dx + idx * 8, pack8(g));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ depthwise wgrad
+// dW[u][v][c] = sum_{b,i,j} x[b, i+(u-1)d, j+(v-1)d, c] * dy[b,i,j,c]   ('same' zero padding).
+// grid (ceil(C/64), kTrBands), block 256: warp strides over the band's pixels, lane = channel pair.  partial [bands][9][C]
+__global__ void __launch_bounds__(256) dw_wgrad_partial_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int B, int H, int W,
+                                                               int C, int rate, float* __restrict__ partial) {
+  __shared__ float s_red[8][9][64];
+  const int chunk = blockIdx.x, band = blockIdx.y;
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int c0 = chunk * 64 + lane * 2;
+  const long long npix = static_cast<long long>(B) * H * W;
+  const long long per_band = (npix + kTrBands - 1) / kTrBands;
+  const long long p0 = band * per_band, p1 = min(npix, p0 + per_band);
+  float a0[9], a1[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) { a0[t] = 0.f; a1[t] = 0.f; }
+  if (c0 < C) {
+    for (long long p = p0 + wp; p < p1; p += 8) {
+      const int j = static_cast<int>(p % W);
+      const long long r = p / W;
+      const int i = static_cast<int>(r % H);
+      const long long img = (r / H) * H * W;
+      const uint32_t dv = __ldg(reinterpret_cast<const unsigned int*>(dy + p * C + c0));
+      const float g0 = bf16_lo(dv), g1 = bf16_hi(dv);
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int ii = i + (u - 1) * rate;
+        if (ii < 0 || ii >= H) continue;
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+          const int jj = j + (v - 1) * rate;
+          if (jj < 0 || jj >= W) continue;
+          const uint32_t xv = __ldg(reinterpret_cast<const unsigned int*>(x + (img + static_cast<long long>(ii) * W + jj) * C + c0));
+          a0[u * 3 + v] = fmaf(bf16_lo(xv), g0, a0[u * 3 + v]);
+          a1[u * 3 + v] = fmaf(bf16_hi(xv), g1, a1[u * 3 + v]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) { s_red[wp][t][lane * 2] = a0[t]; s_red[wp][t][lane * 2 + 1] = a1[t]; }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 9 * 64; e += 256) {
+    const int t = e >> 6, j = e & 63;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += s_red[w][t][j];
+    const int c = chunk * 64 + j;
+    if (c < C) partial[(static_cast<size_t>(band) * 9 + t) * C + c] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ bilinear adjoint
+// outputs Y whose source coordinate falls in (i-1, i+1) touch input i; the range below is conservative and every
+// candidate's weight is recomputed with the forward's own resize_coord, so forward and adjoint agree exactly.
+__device__ __forceinline__ void adjoint_range(int i, float scale, int n_out, int& a, int& b) {
+  a = max(0, static_cast<int>(floorf((static_cast<float>(i) - 0.5f) / scale - 0.5f)) - 1);
+  b = min(n_out - 1, static_cast<int>(ceilf((static_cast<float>(i) + 1.5f) / scale - 0.5f)) + 1);
+}
+__device__ __forceinline__ float adjoint_weight(int Y, float scale, int n_in, int i) {
+  int lo, hi;
+  float t;
+  resize_coord(Y, scale, n_in, lo, hi, t);
+  return (lo == i ? 1.0f - t : 0.0f) + (hi == i ? t : 0.0f);
+}
+// dx[b,i,j,:] = sum_{Y,X} wy(Y,i) wx(X,j) dy[b,Y,X,:]; dy bf16 [B,ho,wo] rows of stride ld_dy, dx dense bf16 [B,hi,wi,C]
+struct ResizeBwdParams {
+  const __nv_bfloat16* dy;
+  __nv_bfloat16* dx;
+  long long ld_dy;
+  int B, hi, wi, C, ho, wo;
+  float sy, sx;
+};
+__global__ void __launch_bounds__(256) resize_bwd_nhwc_kernel(const ResizeBwdParams P) {
+  const int vecs = P.C >> 3;
+  const long long total = static_cast<long long>(P.B) * P.hi * P.wi * vecs;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int vec = static_cast<int>(idx % vecs);
+    long long r = idx / vecs;
+    const int j = static_cast<int>(r % P.wi);
+    r /= P.wi;
+    const int i = static_cast<int>(r % P.hi);
+    const int b = static_cast<int>(r / P.hi);
+    int ya, yb, xa, xb;
+    adjoint_range(i, P.sy, P.ho, ya, yb);
+    adjoint_range(j, P.sx, P.wo, xa, xb);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int Y = ya; Y <= yb; ++Y) {
+      const float wy = adjoint_weight(Y, P.sy, P.hi, i);
+      if (wy == 0.0f) continue;
+      const __nv_bfloat16* rowp = P.dy + (static_cast<long long>(b) * P.ho + Y) * P.wo * P.ld_dy + vec * 8;
+      for (int X = xa; X <= xb; ++X) {
+        const float wgt = wy * adjoint_weight(X, P.sx, P.wi, j);
+        if (wgt == 0.0f) continue;
+        float g[8];
+        unpack8(ldg_nc_v4(rowp + X * P.ld_dy), g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, g[k], acc[k]);
+      }
+    }
+    stg_v4(P.dx + idx * 8, pack8(acc));
+  }
+}
+// planar fp32 gradient [B, NC, ho, wo] -> bf16 rows [B*hi*wi, ld_dx] (columns >= NC are left untouched: zero padding)
+struct ResizeBwdPlanarParams {
+  const float* dy;
+  __nv_bfloat16* dx;
+  long long ld_dx;
+  int B, NC, hi, wi, ho, wo;
+  float sy, sx;
+};
+__global__ void __launch_bounds__(256) resize_bwd_planar_kernel(const ResizeBwdPlanarParams P) {
+  const long long total = static_cast<long long>(P.B) * P.NC * P.hi * P.wi;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int j = static_cast<int>(idx % P.wi);
+    long long r = idx / P.wi;
+    const int i = static_cast<int>(r % P.hi);
+    r /= P.hi;
+    const int c = static_cast<int>(r % P.NC);
+    const int b = static_cast<int>(r / P.NC);
+    int ya, yb, xa, xb;
+    adjoint_range(i, P.sy, P.ho, ya, yb);
+    adjoint_range(j, P.sx, P.wo, xa, xb);
+    const float* plane = P.dy + (static_cast<long long>(b) * P.NC + c) * P.ho * P.wo;
+    float acc = 0.f;
+    for (int Y = ya; Y <= yb; ++Y) {
+      const float wy = adjoint_weight(Y, P.sy, P.hi, i);
+      if (wy == 0.0f) continue;
+      for (int X = xa; X <= xb; ++X) {
+        const float wgt = wy * adjoint_weight(X, P.sx, P.wi, j);
+        if (wgt != 0.0f) acc = fmaf(wgt, __ldg(plane + static_cast<long long>(Y) * P.wo + X), acc);
+      }
+    }
+    P.dx[((static_cast<long long>(b) * P.hi + i) * P.wi + j) * P.ld_dx + c] = __float2bfloat16_rn(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ loss
+// pred_resize (model.py:76) + Softmax (model.py:86) + SparseCategoricalCrossEntropy with ignore_index (loss.py:121-156):
+//   p = softmax(bilinear(logits) + bias); loss_px = -log(clip(p[label], 1e-7, 1 - 1e-7)) * (label != ignore)
+//   d(logits_full)[c] = (p[c] - [c == label]) * valid * inv_norm  (zero where the clip is active), inv_norm = 1 / (global B * H * W)
+// logits: fp32 rows [B*hi*wi, ldl] (the classifier GEMM output, bias not yet added).  d_full: planar fp32 [B, NC, H, W].
+// block_part: [gridDim.x][2] = sum of loss_px | number of valid pixels of the block.
+struct LossParams {
+  const float* logits;
+  const float* bias;
+  const uint8_t* labels;
+  float* d_full;
+  float* block_part;
+  long long ldl;
+  int B, NC, hi, wi, H, W, ignore;
+  float sy, sx, inv_norm;
+};
+__device__ __forceinline__ float interp_logit(const float* p00, const float* p01, const float* p10, const float* p11, int c, float tx, float ty, float bias) {
+  const float tl = __ldg(p00 + c), tr = __ldg(p01 + c), bl = __ldg(p10 + c), br = __ldg(p11 + c);
+  const float top = lerp_nofma(tl, tr, tx), bot = lerp_nofma(bl, br, tx);
+  return lerp_nofma(top, bot, ty) + bias;
+}
+__global__ void __launch_bounds__(256) softmax_ce_kernel(const LossParams P) {
+  __shared__ float s_loss[8], s_cnt[8];
+  const long long total = static_cast<long long>(P.B) * P.H * P.W;
+  const long long plane = static_cast<long long>(P.H) * P.W;
+  float loss_acc = 0.f, cnt_acc = 0.f;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int X = static_cast<int>(idx % P.W);
+    long long r = idx / P.W;
+    const int Y = static_cast<int>(r % P.H);
+    const int b = static_cast<int>(r / P.H);
+    int y0, y1, x0, x1;
+    float ty, tx;
+    resize_coord(Y, P.sy, P.hi, y0, y1, ty);
+    resize_coord(X, P.sx, P.wi, x0, x1, tx);
+    const float* base = P.logits + static_cast<long long>(b) * P.hi * P.wi * P.ldl;
+    const float* p00 = base + (static_cast<long long>(y0) * P.wi + x0) * P.ldl;
+    const float* p01 = base + (static_cast<long long>(y0) * P.wi + x1) * P.ldl;
+    const float* p10 = base + (static_cast<long long>(y1) * P.wi + x0) * P.ldl;
+    const float* p11 = base + (static_cast<long long>(y1) * P.wi + x1) * P.ldl;
+    const int label = P.labels[idx];
+    const bool valid = label != P.ignore && label < P.NC;
+    float m = -3.0e38f;
+    for (int c = 0; c < P.NC; ++c) m = fmaxf(m, interp_logit(p00, p01, p10, p11, c, tx, ty, __ldg(P.bias + c)));
+    float s = 0.f;
+    for (int c = 0; c < P.NC; ++c) s += __expf(interp_logit(p00, p01, p10, p11, c, tx, ty, __ldg(P.bias + c)) - m);
+    const float inv_s = 1.0f / s;
+    float pl = 1.0f;
+    if (valid) pl = __expf(interp_logit(p00, p01, p10, p11, label, tx, ty, __ldg(P.bias + label)) - m) * inv_s;
+    const bool clipped = pl < 1e-7f || pl > 1.0f - 1e-7f;
+    const float gscale = (valid && !clipped) ? P.inv_norm : 0.0f;
+    float* d = P.d_full + static_cast<long long>(b) * P.NC * plane + static_cast<long long>(Y) * P.W + X;
+    for (int c = 0; c < P.NC; ++c) {
+      const float p = __expf(interp_logit(p00, p01, p10, p11, c, tx, ty, __ldg(P.bias + c)) - m) * inv_s;
+      d[c * plane] = (p - (c == label ? 1.0f : 0.0f)) * gscale;
+    }
+    if (valid) {
+      loss_acc -= __logf(fminf(fmaxf(pl, 1e-7f), 1.0f - 1e-7f));
+      cnt_acc += 1.0f;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    loss_acc += __shfl_xor_sync(0xFFFFFFFFu, loss_acc, o);
+    cnt_acc += __shfl_xor_sync(0xFFFFFFFFu, cnt_acc, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s_loss[threadIdx.x >> 5] = loss_acc; s_cnt[threadIdx.x >> 5] = cnt_acc; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float l = 0.f, n = 0.f;
+    for (int w = 0; w < 8; ++w) { l += s_loss[w]; n += s_cnt[w]; }
+    P.block_part[2 * blockIdx.x] = l;
+    P.block_part[2 * blockIdx.x + 1] = n;
+  }
+}
+// out[0] = sum of loss_px * inv_norm (this replica's share of the global mean loss), out[1] = valid pixels
+__global__ void loss_final_kernel(const float* __restrict__ block_part, int nblocks, float inv_norm, float* __restrict__ out) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double l = 0.0, n = 0.0;
+    for (int i = 0; i < nblocks; ++i) { l += block_part[2 * i]; n += block_part[2 * i + 1]; }
+    out[0] = static_cast<float>(l * inv_norm);
+    out[1] = static_cast<float>(n);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ pooling / broadcast
+// out[b][c] = scale * sum_p x[(b*npix + p) * ld + c]   (image pooling: scale = 1/npix, layers.py:132; column sums: scale = 1)
+// grid (ceil(C/64), B), block 256; out bf16 [B, C] (or fp32 when out_f32)
+__global__ void __launch_bounds__(256) rows_reduce_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int npix, int C, float scale,
+                                                          __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32) {
+  __shared__ float s_red[8][64];
+  const int chunk = blockIdx.x, b = blockIdx.y;
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int c0 = chunk * 64 + lane * 2;
+  float s0 = 0.f, s1 = 0.f;
+  if (c0 < C) {
+    const __nv_bfloat16* xb = x + static_cast<long long>(b) * npix * ld + c0;
+    for (int p = wp; p < npix; p += 8) {
+      const uint32_t v = __ldg(reinterpret_cast<const unsigned int*>(xb + p * ld));
+      s0 += bf16_lo(v); s1 += bf16_hi(v);
+    }
+  }
+  s_red[wp][lane * 2] = s0; s_red[wp][lane * 2 + 1] = s1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += s_red[w][threadIdx.x];
+    const int c = chunk * 64 + threadIdx.x;
+    if (c < C) {
+      if (out_f32) out_f32[static_cast<long long>(b) * C + c] = s * scale;
+      else out_bf16[static_cast<long long>(b) * C + c] = __float2bfloat16_rn(s * scale);
+    }
+  }
+}
+// dst[(b*npix + p) * ld + c] (+)= scale * src[b*C + c]   (aspp_resize of a 1x1 map = broadcast, layers.py:138; and its use
+// as the adjoint of the image pooling mean)
+__global__ void __launch_bounds__(256) bcast_rows_kernel(const __nv_bfloat16* __restrict__ src, int B, int npix, int C, float scale,
+                                                         __nv_bfloat16* __restrict__ dst, long long ld, int accumulate) {
+  const int vecs = C >> 3;
+  const long long total = static_cast<long long>(B) * npix * vecs;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int vec = static_cast<int>(idx % vecs);
+    const long long row = idx / vecs;
+    const int b = static_cast<int>(row / npix);
+    float v[8];
+    unpack8(ldg_nc_v4(src + static_cast<long long>(b) * C + vec * 8), v);
+    __nv_bfloat16* d = dst + row * ld + vec * 8;
+    if (accumulate) {
+      float o[8];
+      unpack8(*reinterpret_cast<const uint4*>(d), o);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], scale, o[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] *= scale;
+    }
+    stg_v4(d, pack8(v));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ elementwise
+__global__ void __launch_bounds__(256) add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ out, size_t n8) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float x[8], y[8];
+    unpack8(*reinterpret_cast<const uint4*>(a + 8 * i), x);
+    unpack8(*reinterpret_cast<const uint4*>(b + 8 * i), y);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] += y[k];
+    stg_v4(out + 8 * i, pack8(x));
+  }
+}
+// Dropout(rate) (layers.py:161) with a counter-based mask: element e is kept iff fmix32(e * 0x9E3779B1 + seed) >= rate * 2^32;
+// kept values are scaled by 1 / (1 - rate).  The same call with the same seed applies the mask to the gradient.
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+__global__ void __launch_bounds__(256) dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, size_t n8, uint32_t seed,
+                                                      uint32_t threshold, float keep_scale) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float v[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + 8 * i), v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t e = static_cast<uint32_t>(8 * i + k);
+      v[k] = fmix32(e * 0x9E3779B1u + seed) >= threshold ? v[k] * keep_scale : 0.0f;
+    }
+    stg_v4(out + 8 * i, pack8(v));
+  }
+}
+// SGD with momentum (Keras: v <- m v - lr g; w <- w + v; common/model_utils.py:122-123) with the l2 regulariser's gradient
+// (layers.py:12-21: loss += l2 * sum w^2 -> g += 2 l2 w) folded in.  fp32 master weights.
+__global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ v, size_t n, float lr, float momentum,
+                                                  float l2, float gscale) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float wi = w[i];
+    const float gi = fmaf(2.0f * l2, wi, g[i] * gscale);
+    const float vi = momentum * v[i] - lr * gi;
+    v[i] = vi;
+    w[i] = wi + vi;
+  }
+}
+// fp32 -> bf16 for any n (the weight copies the GEMMs read)
+__global__ void __launch_bounds__(256) cast_f32_bf16_any_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    out[i] = __float2bfloat16_rn(in[i]);
+}
+
+}  // namespace dlv3p

@@ -1,0 +1,459 @@
+"""Training step of the DeepLabV3+ head on B200 (BASELINE cfg 5): forward in training mode (SyncBatchNormalization with
+batch statistics, Dropout active), sparse softmax cross-entropy with ignore_index, backward, gradient all-reduce and
+SGD-momentum update — every operator a libdlv3p.so kernel (include/dlv3p_train.h), one process per GPU.
+
+Reference: train.py:143-169 (model.compile + fit under tf.distribute.MirroredStrategy: per-replica forward / backward,
+SyncBN statistics and gradients summed over the replicas), graph deeplabv3p/models/layers.py:74-219 + model.py:75-86,
+loss deeplabv3p/loss.py:121-156 (SparseCategoricalCrossEntropy, ignore_index 255, Keras mean over every pixel), optimizer
+common/model_utils.py:122-123 (SGD, momentum 0.9, lr 1e-2 default train.py:280-286), regulariser l2(2e-5) on the conv
+kernels and biases (layers.py:12-21; inert for depthwise kernels, :24-31), BN momentum 0.99 / eps 1e-5.
+
+torch is plumbing only: device memory (tensors), the CUDA stream, and torch.distributed (NCCL over NVLink) for the two
+exchanges of the step — the per-layer SyncBN statistics (forward: sum x | sum x^2 | n, backward: sum g | sum g*xhat) and ONE
+all-reduce of the flat fp32 gradient bucket.  No torch operator touches an activation.
+
+Scope: the full head (ASPP_block + Decoder_block + tail) — the Xception / ResNet50 / MobileNetV2 non-lite models.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from . import ffi
+from . import train_ffi as tf_
+from .head import atrous_rates
+
+L2_COEF = 2e-5       # layers.py:12
+BN_MOMENTUM = 0.99   # Keras BatchNormalization default, kept by CustomBatchNormalization (layers.py:63-70)
+
+
+def _rup(v: int, a: int) -> int:
+    return (v + a - 1) // a * a
+
+
+def dropout_seed(base_seed: int, step: int, rank: int) -> int:
+    """Seed of the Dropout mask replica `rank` draws at step `step` (tests rebuild the mask with train_ffi.dropout_keep_mask)."""
+    return (base_seed * 0x9E3779B1 + step * 0x85EBCA6B + rank * 0xC2B2AE35 + 0x27D4EB2F) & 0xFFFFFFFF
+
+
+class HeadTrainer:
+    """One replica of the data-parallel training step.  All tensors live on `device`; feed bf16 NHWC features and uint8
+    labels already resident in HBM (the backbone is outside this path; d_feat / d_skip are returned for it)."""
+
+    def __init__(self, B: int, H: int, W: int, OS: int, Cin: int, Cskip: int, NC: int, weights: Dict[Tuple[str, str], np.ndarray],
+                 device: int = 0, lr: float = 1e-2, momentum: float = 0.9, l2: float = L2_COEF, bn_momentum: float = BN_MOMENTUM,
+                 eps: float = 1e-5, dropout: float = 0.5, seed: int = 0, ignore_index: int = 255, global_batch: Optional[int] = None,
+                 process_group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch = torch
+        if not torch.cuda.is_available():
+            raise ffi.Dlv3pError(-2, 'HeadTrainer needs a CUDA device: there is no CPU path')
+        tf_.lib()
+        self.B, self.H, self.W, self.OS, self.Cin, self.Cs, self.NC = B, H, W, OS, Cin, Cskip, NC
+        self.rates = atrous_rates(OS)
+        self.h, self.w = -(-H // OS), -(-W // OS)
+        self.hs, self.ws = -(-H // 4), -(-W // 4)
+        self.M1, self.M2 = B * self.h * self.w, B * self.hs * self.ws
+        if Cin % 8 or Cskip % 8 or self.M1 % 8 or self.M2 % 8:
+            raise ffi.Dlv3pError(-1, 'HeadTrainer: Cin, Cskip and the pixel counts per replica must be multiples of 8')
+        self.NCp = _rup(NC, 8)
+        self.Bp = _rup(B, 8)
+        self.dev = device
+        self.tdev = torch.device('cuda', device)
+        self.lr, self.momentum, self.l2, self.bn_momentum, self.eps = lr, momentum, l2, bn_momentum, eps
+        self.drop_rate, self.seed, self.ignore = dropout, seed, ignore_index
+        self.pg = process_group
+        self.dist = dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1) else None
+        self.world = dist.get_world_size(process_group) if self.dist else 1
+        self.rank = dist.get_rank(process_group) if self.dist else 0
+        self.global_batch = global_batch if global_batch is not None else B * self.world
+        self.step_count = 0
+        self.launches = 0
+        self.debug_taps = None          # set to {} to snapshot intermediate gradients (diagnostics / tests)
+        self._layout_params()
+        self._alloc()
+        self.set_weights(weights)
+
+    # ------------------------------------------------------------------------------------------------ parameters
+    def _conv_specs(self):
+        Cin, Cs, NCp = self.Cin, self.Cs, self.NCp
+        return [('image_pooling', Cin, 256), ('aspp0', Cin, 256), ('aspp1_pointwise', Cin, 256), ('aspp2_pointwise', Cin, 256),
+                ('aspp3_pointwise', Cin, 256), ('concat_projection', 1280, 256), ('feature_projection0', Cs, 48),
+                ('decoder_conv0_pointwise', 304, 256), ('decoder_conv1_pointwise', 256, 256), ('conv_upsample', 256, NCp)]
+
+    def _dw_specs(self):
+        return [('aspp1_depthwise', self.Cin), ('aspp2_depthwise', self.Cin), ('aspp3_depthwise', self.Cin),
+                ('decoder_conv0_depthwise', 304), ('decoder_conv1_depthwise', 256)]
+
+    def _bn_specs(self):
+        Cin = self.Cin
+        return [('image_pooling_BN', 256), ('aspp0_BN', 256),
+                ('aspp1_depthwise_BN', Cin), ('aspp1_pointwise_BN', 256), ('aspp2_depthwise_BN', Cin), ('aspp2_pointwise_BN', 256),
+                ('aspp3_depthwise_BN', Cin), ('aspp3_pointwise_BN', 256), ('concat_projection_BN', 256), ('feature_projection0_BN', 48),
+                ('decoder_conv0_depthwise_BN', 304), ('decoder_conv0_pointwise_BN', 256), ('decoder_conv1_depthwise_BN', 256),
+                ('decoder_conv1_pointwise_BN', 256)]
+
+    def _layout_params(self):
+        """Flat fp32 layout: [A: 1x1 kernels [K,N] + classifier bias (l2-regularised)] [B: depthwise taps [9,C]]
+        [C: per BN layer beta | gamma].  A and B are all-reduced; C's gradients come out of the SyncBN backward exchange
+        already summed over the global batch."""
+        off = 0
+        self.off: Dict[Tuple[str, str], Tuple[int, Tuple[int, ...]]] = {}
+        for name, K, N in self._conv_specs():
+            self.off[(name, 'kernel')] = (off, (K, N))
+            off = _rup(off + K * N, 8)
+        self.off[('conv_upsample', 'bias')] = (off, (self.NCp,))
+        off = _rup(off + self.NCp, 8)
+        self.endA = off
+        for name, Cc in self._dw_specs():
+            self.off[(name, 'depthwise_kernel')] = (off, (9, Cc))
+            off = _rup(off + 9 * Cc, 8)
+        self.endB = off
+        for name, Cc in self._bn_specs():
+            self.off[(name, 'beta')] = (off, (Cc,))
+            self.off[(name, 'gamma')] = (off + Cc, (Cc,))
+            off = _rup(off + 2 * Cc, 8)
+        self.nparams = off
+        # forward statistics: per BN layer [sum x | sum x^2 | n], 4-float aligned
+        soff = 0
+        self.stat_off: Dict[str, Tuple[int, int]] = {}
+        for name, Cc in self._bn_specs():
+            self.stat_off[name] = (soff, Cc)
+            soff = _rup(soff + 2 * Cc + 1, 4)
+        self.nstats = soff
+        self.nbn = sum(c for _, c in self._bn_specs())
+
+    def _alloc(self):
+        t = self.torch
+        dv = self.tdev
+        bf, f32 = t.bfloat16, t.float32
+        z = lambda *s, dtype=bf: t.zeros(*s, dtype=dtype, device=dv)
+        self.params, self.grads, self.velocity = z(self.nparams, dtype=f32), z(self.nparams, dtype=f32), z(self.nparams, dtype=f32)
+        self.w_kn = z(self.endA)                 # bf16 copy of region A (Keras [K,N] layout: the dgrad operand)
+        self.w_nk = z(self.endA)                 # transposed copies [N,K]: the forward operand
+        self.stats = z(self.nstats, dtype=f32)
+        self.moving_mean, self.moving_var = z(self.nbn, dtype=f32), t.ones(self.nbn, dtype=f32, device=dv)
+        B, Bp, M1, M2, Cin, Cs, NCp = self.B, self.Bp, self.M1, self.M2, self.Cin, self.Cs, self.NCp
+        T = {}
+        T['pool'], T['r4'], T['b4'] = z(Bp, Cin), z(Bp, 256), z(Bp, 256)
+        T['r0'], T['concat'], T['rp'], T['yproj'], T['aspp_out'] = z(M1, 256), z(M1, 1280), z(M1, 256), z(M1, 256), z(M1, 256)
+        for i in (1, 2, 3):
+            T['d%d' % i], T['a%d' % i], T['p%d' % i] = z(M1, Cin), z(M1, Cin), z(M1, 256)
+        T['dcat'], T['rs'] = z(M2, 304), z(M2, 48)
+        T['c0d'], T['c0a'], T['c0p'], T['y0'] = z(M2, 304), z(M2, 304), z(M2, 256), z(M2, 256)
+        T['c1d'], T['c1a'], T['c1p'], T['y1'] = z(M2, 256), z(M2, 256), z(M2, 256), z(M2, 256)
+        T['logits'] = z(M2, NCp, dtype=f32)
+        T['dfull'] = z(B, self.NC, self.H, self.W, dtype=f32)
+        T['loss'] = z(2, dtype=f32)
+        T['bias_stats'] = z(2 * NCp + 4, dtype=f32)
+        # backward
+        T['dlow'] = z(M2, NCp)
+        T['g256a'], T['g256b'], T['g256c'] = z(M2, 256), z(M2, 256), z(M2, 256)   # gradient buffers at decoder resolution
+        T['g304a'], T['g304b'] = z(M2, 304), z(M2, 304)
+        T['drs'], T['dskip'] = z(M2, 48), z(M2, Cs)
+        T['da_out'], T['drp'], T['dconcat'] = z(M1, 256), z(M1, 256), z(M1, 1280)
+        T['gA'], T['gB'] = z(M1, Cin), z(M1, Cin)
+        T['dfeat'], T['dfeat_tmp'] = z(M1, Cin), z(M1, Cin)
+        T['g1_256'] = z(M1, 256)
+        T['db4'], T['dr4'], T['dpool'] = z(Bp, 256), z(Bp, 256), z(Bp, Cin)
+        T['featT'] = z(Cin, M1)
+        T['xT'] = z(max(Cin * M1, 304 * M2, 1280 * M1, Cs * M2, Cin * Bp))
+        T['dyT'] = z(max(256 * M2, 256 * M1, 256 * Bp, NCp * M2))
+        self.sms = ffi.device_info(self.dev)['sm_count']
+        T['partial'] = z(16 * 1024 * 1024 + self.sms * 2 * 128 * 256, dtype=f32)
+        maxC = max(Cin, 304, 256)
+        T['scratch'] = z(tf_.scratch_bytes(maxC) // 4 + 64, dtype=f32)
+        T['bn_scratch'] = z(ffi.bn_scratch_bytes(maxC) // 4 + 64, dtype=f32)
+        T['loss_scratch'] = z(tf_.loss_scratch_bytes() // 4 + 16, dtype=f32)
+        self.T = T
+        # gather indices for the vectorised moving-statistics update
+        sx, sq, nn = [], [], []
+        for name, Cc in self._bn_specs():
+            o, _ = self.stat_off[name]
+            sx += list(range(o, o + Cc)); sq += list(range(o + Cc, o + 2 * Cc)); nn += [o + 2 * Cc] * Cc
+        self._ix = tuple(t.tensor(v, dtype=t.long, device=dv) for v in (sx, sq, nn))
+
+    def view(self, flat, key):
+        o, shape = self.off[key]
+        n = int(np.prod(shape))
+        return flat[o:o + n].view(*shape)
+
+    def set_weights(self, W: Dict[Tuple[str, str], np.ndarray]) -> None:
+        """Keras-layout arrays keyed (layer, variable) — the inventory of dlv3p_weight_info / SURVEY §8(b)."""
+        t = self.torch
+        host = np.zeros(self.nparams, np.float32)
+
+        def put(key, arr):
+            o, shape = self.off[key]
+            host[o:o + arr.size] = np.asarray(arr, np.float32).reshape(-1)
+
+        for name, K, N in self._conv_specs():
+            k = np.asarray(W[(name, 'kernel')], np.float32).reshape(K, -1)
+            if name == 'conv_upsample':
+                k = np.concatenate([k, np.zeros((K, self.NCp - self.NC), np.float32)], axis=1)
+            put((name, 'kernel'), k)
+        put(('conv_upsample', 'bias'), np.concatenate([np.asarray(W[('conv_upsample', 'bias')], np.float32), np.zeros(self.NCp - self.NC, np.float32)]))
+        for name, Cc in self._dw_specs():
+            put((name, 'depthwise_kernel'), np.asarray(W[(name, 'depthwise_kernel')], np.float32).reshape(9, Cc))
+        mm, mv = [], []
+        for name, Cc in self._bn_specs():
+            put((name, 'beta'), W[(name, 'beta')]); put((name, 'gamma'), W[(name, 'gamma')])
+            mm.append(np.asarray(W[(name, 'moving_mean')], np.float32)); mv.append(np.asarray(W[(name, 'moving_variance')], np.float32))
+        self.params.copy_(t.from_numpy(host))
+        self.moving_mean.copy_(t.from_numpy(np.concatenate(mm))); self.moving_var.copy_(t.from_numpy(np.concatenate(mv)))
+        self.velocity.zero_()
+        self._refresh_bf16()
+        t.cuda.synchronize(self.tdev)
+
+    def get_weights(self) -> Dict[Tuple[str, str], np.ndarray]:
+        """Current fp32 master weights and moving statistics in the Keras layout (what model.save would write)."""
+        host = self.params.detach().cpu().numpy()
+        out = {}
+        for key, (o, shape) in self.off.items():
+            a = host[o:o + int(np.prod(shape))].reshape(shape).copy()
+            name, var = key
+            if var == 'kernel':
+                a = a[:, :self.NC] if name == 'conv_upsample' else a
+                a = a.reshape(1, 1, *a.shape)
+            elif var == 'bias':
+                a = a[:self.NC]
+            elif var == 'depthwise_kernel':
+                a = a.reshape(3, 3, shape[1], 1)
+            out[key] = a
+        mm, mv = self.moving_mean.cpu().numpy(), self.moving_var.cpu().numpy()
+        o = 0
+        for name, Cc in self._bn_specs():
+            out[(name, 'moving_mean')] = mm[o:o + Cc].copy(); out[(name, 'moving_variance')] = mv[o:o + Cc].copy()
+            o += Cc
+        return out
+
+    def get_grads(self) -> Dict[Tuple[str, str], np.ndarray]:
+        host = self.grads.detach().cpu().numpy()
+        out = {}
+        for key, (o, shape) in self.off.items():
+            a = host[o:o + int(np.prod(shape))].reshape(shape).copy()
+            if key == ('conv_upsample', 'kernel'):
+                a = a[:, :self.NC]
+            elif key == ('conv_upsample', 'bias'):
+                a = a[:self.NC]
+            out[key] = a
+        return out
+
+    # ------------------------------------------------------------------------------------------------ helpers
+    def _s(self):
+        return self.torch.cuda.current_stream(self.tdev).cuda_stream
+
+    def _call(self, name, *args):
+        tf_.call(name, self.dev, *args, self._s())
+        self.launches += 1
+
+    @staticmethod
+    def _p(tensor, off_elems: int = 0) -> int:
+        return tensor.data_ptr() + off_elems * tensor.element_size()
+
+    def _wp(self, flat, key) -> int:
+        return self._p(flat, self.off[key][0])
+
+    def _allreduce(self, tensor):
+        if self.dist:
+            self.dist.all_reduce(tensor, op=self.dist.ReduceOp.SUM, group=self.pg)
+
+    def _refresh_bf16(self):
+        """bf16 operand copies of the 1x1 kernels after an update: [K,N] (dgrad) and its transpose [N,K] (forward)."""
+        self._call('dlv3p_train_cast_bf16', self._p(self.params), self._p(self.w_kn), self.endA)
+        for name, K, N in self._conv_specs():
+            o = self.off[(name, 'kernel')][0]
+            self._call('dlv3p_train_transpose', self._p(self.w_kn, o), K, N, N, self._p(self.w_nk, o), K)
+
+    def _gemm(self, a, lda, b, ldb, M, N, K, d, ldd, out_fp32=0, splits=1):
+        self._call('dlv3p_train_gemm_nt', a, lda, b, ldb, M, N, K, d, ldd, out_fp32, splits, self._p(self.T['partial']))
+
+    def _conv_fwd(self, name, x_ptr, ldx, M, out_ptr, ldo, out_fp32=0):
+        _, (K, N) = self.off[(name, 'kernel')]
+        self._gemm(x_ptr, ldx, self._wp(self.w_nk, (name, 'kernel')), K, M, N, K, out_ptr, ldo, out_fp32)
+
+    def _conv_dgrad(self, name, dy_ptr, ld_dy, M, dx_ptr, ldx):
+        _, (K, N) = self.off[(name, 'kernel')]
+        self._gemm(dy_ptr, ld_dy, self._wp(self.w_kn, (name, 'kernel')), N, M, K, N, dx_ptr, ldx)
+
+    def _conv_wgrad(self, name, xT_ptr, dy_ptr, M):
+        """dW[K,N] = X^T dY.  xT_ptr: X already transposed [K, M] (row stride M); dY dense [M, N] bf16 is transposed here."""
+        _, (K, N) = self.off[(name, 'kernel')]
+        T = self.T
+        self._call('dlv3p_train_transpose', dy_ptr, M, N, N, self._p(T['dyT']), M)
+        tiles = -(-K // 128) * -(-N // (256 if N > 64 else 64))
+        kblocks = -(-M // 64)
+        splits = max(1, min(kblocks, self.sms // tiles, (T['partial'].numel()) // max(1, K * N)))
+        self._gemm(xT_ptr, M, self._p(T['dyT']), M, K, N, M, self._wp(self.grads, (name, 'kernel')), N, 1, splits)
+
+    def _transpose_x(self, x_ptr, M, K, ld, dst=None) -> int:
+        dst = self._p(self.T['xT']) if dst is None else dst
+        self._call('dlv3p_train_transpose', x_ptr, M, K, ld, dst, M)
+        return dst
+
+    def _bn_fwd(self, name, x, M, y_ptr, ldy, relu=1):
+        o, Cc = self.stat_off[name]
+        st = self.stats[o:o + 2 * Cc + 1]
+        self._call('dlv3p_op_bn_stats', self._p(x), M, Cc, self._p(self.stats, o), self._p(self.T['bn_scratch']))
+        self._allreduce(st)
+        self._call('dlv3p_train_bn_apply', self._p(x), M, Cc, self._p(self.stats, o), self._wp(self.params, (name, 'gamma')),
+                   self._wp(self.params, (name, 'beta')), self.eps, relu, y_ptr, ldy)
+
+    def _bn_bwd(self, name, dy_ptr, ld_dy, y_ptr, ld_y, x, M, dx, relu=1):
+        o, Cc = self.stat_off[name]
+        go = self.off[(name, 'beta')][0]                      # grads[go : go+2C] = d(beta) | d(gamma) = sum g | sum g*xhat
+        self._call('dlv3p_train_bn_bwd_stats', dy_ptr, ld_dy, y_ptr, ld_y, self._p(x), M, Cc, self._p(self.stats, o), self.eps, relu,
+                   self._p(self.grads, go), self._p(self.T['scratch']))
+        self._allreduce(self.grads[go:go + 2 * Cc])
+        self._call('dlv3p_train_bn_bwd_apply', dy_ptr, ld_dy, y_ptr, ld_y, self._p(x), M, Cc, self._p(self.stats, o), self._p(self.grads, go),
+                   self._wp(self.params, (name, 'gamma')), self.eps, relu, self._p(dx))
+
+    def _sep_fwd(self, prefix, x, Bn, Hh, Ww, Cc, rate, d, a, p, y_ptr, ldy):
+        """SepConv_BN (depth_activation=True, layers.py:98-109) in training mode; keeps d (raw depthwise), a (BN+ReLU), p (raw pointwise)."""
+        M = Bn * Hh * Ww
+        self._call('dlv3p_train_depthwise', self._p(x), Bn, Hh, Ww, Cc, rate, self._wp(self.params, (prefix + '_depthwise', 'depthwise_kernel')), 0, self._p(d))
+        self._bn_fwd(prefix + '_depthwise_BN', d, M, self._p(a), Cc)
+        self._conv_fwd(prefix + '_pointwise', self._p(a), Cc, M, self._p(p), 256)
+        self._bn_fwd(prefix + '_pointwise_BN', p, M, y_ptr, ldy)
+
+    def _tap(self, name, buf):
+        if self.debug_taps is not None:
+            self.debug_taps[name] = buf.detach().float().cpu().numpy().copy()
+
+    def _sep_bwd(self, prefix, x, Bn, Hh, Ww, Cc, rate, d, a, p, y_ptr, ld_y, dy_ptr, ld_dy, g_pw, g_a, g_d, dx):
+        """Backward of _sep_fwd.  g_pw [M,256], g_a / g_d [M,Cc] are scratch gradients; dx [M,Cc] receives d(loss)/d(x)."""
+        M = Bn * Hh * Ww
+        self._bn_bwd(prefix + '_pointwise_BN', dy_ptr, ld_dy, y_ptr, ld_y, p, M, g_pw)
+        self._tap(prefix + '/p', g_pw)
+        self._conv_wgrad(prefix + '_pointwise', self._transpose_x(self._p(a), M, Cc, Cc), self._p(g_pw), M)
+        self._conv_dgrad(prefix + '_pointwise', self._p(g_pw), 256, M, self._p(g_a), Cc)
+        self._tap(prefix + '/a', g_a)
+        self._bn_bwd(prefix + '_depthwise_BN', self._p(g_a), Cc, self._p(a), Cc, d, M, g_d)
+        self._tap(prefix + '/d', g_d)
+        self._call('dlv3p_train_depthwise_wgrad', self._p(x), self._p(g_d), Bn, Hh, Ww, Cc, rate,
+                   self._wp(self.grads, (prefix + '_depthwise', 'depthwise_kernel')), self._p(self.T['scratch']))
+        self._call('dlv3p_train_depthwise', self._p(g_d), Bn, Hh, Ww, Cc, rate, self._wp(self.params, (prefix + '_depthwise', 'depthwise_kernel')), 1, self._p(dx))
+
+    # ------------------------------------------------------------------------------------------------ the step
+    def forward_backward(self, feat, skip, labels):
+        """feat bf16 [B,h,w,Cin], skip bf16 [B,hs,ws,Cs], labels uint8 [B,H,W] (CUDA tensors).  Leaves the loss in
+        self.T['loss'][0] (this replica's share of the global mean), all weight gradients in self.grads (BN gradients global,
+        the rest per replica until all_reduce_gradients) and d(loss)/d(feat), d(loss)/d(skip) in self.T['dfeat'] / ['dskip']."""
+        T = self.T
+        P = self._p
+        B, Bp, M1, M2, Cin, Cs, NC, NCp = self.B, self.Bp, self.M1, self.M2, self.Cin, self.Cs, self.NC, self.NCp
+        h, w, hs, ws = self.h, self.w, self.hs, self.ws
+        npix1 = h * w
+        assert feat.is_contiguous() and skip.is_contiguous() and labels.is_contiguous()
+        # ---------------- ASPP_block (layers.py:114-163)
+        self._call('dlv3p_train_rows_reduce', P(feat), Cin, B, npix1, Cin, 1.0 / npix1, P(T['pool']), 0)
+        self._conv_fwd('image_pooling', P(T['pool']), Cin, Bp, P(T['r4']), 256)
+        self._bn_fwd('image_pooling_BN', T['r4'], B, P(T['b4']), 256)
+        self._call('dlv3p_train_bcast_rows', P(T['b4']), B, npix1, 256, 1.0, P(T['concat']), 1280, 0)
+        self._conv_fwd('aspp0', P(feat), Cin, M1, P(T['r0']), 256)
+        self._bn_fwd('aspp0_BN', T['r0'], M1, P(T['concat'], 256), 1280)
+        for i in (1, 2, 3):
+            self._sep_fwd('aspp%d' % i, feat, B, h, w, Cin, self.rates[i - 1], T['d%d' % i], T['a%d' % i], T['p%d' % i], P(T['concat'], 256 * (i + 1)), 1280)
+        self._conv_fwd('concat_projection', P(T['concat']), 1280, M1, P(T['rp']), 256)
+        self._bn_fwd('concat_projection_BN', T['rp'], M1, P(T['yproj']), 256)
+        dseed = dropout_seed(self.seed, self.step_count, self.rank)
+        if self.drop_rate > 0:
+            self._call('dlv3p_train_dropout', P(T['yproj']), P(T['aspp_out']), M1 * 256, dseed, self.drop_rate)
+            aspp_out = T['aspp_out']
+        else:
+            aspp_out = T['yproj']
+        # ---------------- Decoder_block (layers.py:199-219)
+        self._call('dlv3p_train_resize', P(aspp_out), B, h, w, 256, hs, ws, P(T['dcat']), 304)
+        self._conv_fwd('feature_projection0', P(skip), Cs, M2, P(T['rs']), 48)
+        self._bn_fwd('feature_projection0_BN', T['rs'], M2, P(T['dcat'], 256), 304)
+        self._sep_fwd('decoder_conv0', T['dcat'], B, hs, ws, 304, 1, T['c0d'], T['c0a'], T['c0p'], P(T['y0']), 256)
+        self._sep_fwd('decoder_conv1', T['y0'], B, hs, ws, 256, 1, T['c1d'], T['c1a'], T['c1p'], P(T['y1']), 256)
+        # ---------------- tail + loss (model.py:75-86, loss.py:121-156)
+        self._conv_fwd('conv_upsample', P(T['y1']), 256, M2, P(T['logits']), NCp, 1)
+        inv_norm = 1.0 / (float(self.global_batch) * self.H * self.W)
+        self._call('dlv3p_train_softmax_ce', P(T['logits']), NCp, self._wp(self.params, ('conv_upsample', 'bias')), P(labels), B, NC, hs, ws, self.H, self.W,
+                   self.ignore, inv_norm, P(T['dfull']), P(T['loss']), P(T['loss_scratch']))
+        # ================ backward
+        self._call('dlv3p_train_resize_bwd_planar', P(T['dfull']), B, NC, hs, ws, self.H, self.W, P(T['dlow']), NCp)
+        # d(bias) = column sums of d(logits): the banded two-stage statistics kernel (sum x | sum x^2 | n), first NCp entries
+        self._call('dlv3p_op_bn_stats', P(T['dlow']), M2, NCp, P(T['bias_stats']), P(T['bn_scratch']))
+        self.view(self.grads, ('conv_upsample', 'bias')).copy_(T['bias_stats'][:NCp])
+        self._conv_wgrad('conv_upsample', self._transpose_x(P(T['y1']), M2, 256, 256), P(T['dlow']), M2)
+        self._conv_dgrad('conv_upsample', P(T['dlow']), NCp, M2, P(T['g256a']), 256)
+        self._tap('logits', T['dlow'])
+        self._tap('decoder_conv1/y', T['g256a'])
+        # decoder_conv1: dy = g256a, x = y0; scratch g256b / g256c; dx overwrites g256a (dy is dead after the first BN backward)
+        self._sep_bwd('decoder_conv1', T['y0'], B, hs, ws, 256, 1, T['c1d'], T['c1a'], T['c1p'], P(T['y1']), 256, P(T['g256a']), 256,
+                      T['g256b'], T['g256c'], T['g256b'], T['g256a'])
+        # decoder_conv0: dy = g256a, x = dcat (304 channels); dx overwrites g304a
+        self._sep_bwd('decoder_conv0', T['dcat'], B, hs, ws, 304, 1, T['c0d'], T['c0a'], T['c0p'], P(T['y0']), 256, P(T['g256a']), 256,
+                      T['g256b'], T['g304a'], T['g304b'], T['g304a'])
+        # feature_projection0 (+BN+ReLU): dy = g304b[:, 256:304], y = dcat[:, 256:304]
+        self._bn_bwd('feature_projection0_BN', P(T['g304a'], 256), 304, P(T['dcat'], 256), 304, T['rs'], M2, T['drs'])
+        self._conv_wgrad('feature_projection0', self._transpose_x(P(skip), M2, Cs, Cs), P(T['drs']), M2)
+        self._conv_dgrad('feature_projection0', P(T['drs']), 48, M2, P(T['dskip']), Cs)
+        # decoder_resize adjoint, Dropout mask
+        self._call('dlv3p_train_resize_bwd', P(T['g304a']), 304, B, h, w, 256, hs, ws, P(T['da_out']))
+        if self.drop_rate > 0:
+            self._call('dlv3p_train_dropout', P(T['da_out']), P(T['da_out']), M1 * 256, dseed, self.drop_rate)
+        # concat_projection
+        self._bn_bwd('concat_projection_BN', P(T['da_out']), 256, P(T['yproj']), 256, T['rp'], M1, T['drp'])
+        self._conv_wgrad('concat_projection', self._transpose_x(P(T['concat']), M1, 1280, 1280), P(T['drp']), M1)
+        self._conv_dgrad('concat_projection', P(T['drp']), 256, M1, P(T['dconcat']), 1280)
+        # aspp0
+        featT = self._transpose_x(P(feat), M1, Cin, Cin, dst=P(T['featT']))
+        self._bn_bwd('aspp0_BN', P(T['dconcat'], 256), 1280, P(T['concat'], 256), 1280, T['r0'], M1, T['g1_256'])
+        self._conv_wgrad('aspp0', featT, P(T['g1_256']), M1)
+        self._conv_dgrad('aspp0', P(T['g1_256']), 256, M1, P(T['dfeat']), Cin)
+        # aspp1..3
+        for i in (1, 2, 3):
+            self._aspp_branch_bwd(i, feat)
+            self._call('dlv3p_train_add', P(T['dfeat']), P(T['dfeat_tmp']), P(T['dfeat']), M1 * Cin)
+        # image pooling branch: column sums per image of d(concat)[:, 0:256] -> BN -> 1x1 -> broadcast / npix
+        self._call('dlv3p_train_rows_reduce', P(T['dconcat']), 1280, B, npix1, 256, 1.0, P(T['db4']), 0)
+        self._bn_bwd('image_pooling_BN', P(T['db4']), 256, P(T['b4']), 256, T['r4'], B, T['dr4'])
+        self._conv_wgrad('image_pooling', self._transpose_x(P(T['pool']), Bp, Cin, Cin), P(T['dr4']), Bp)
+        self._conv_dgrad('image_pooling', P(T['dr4']), 256, Bp, P(T['dpool']), Cin)
+        self._call('dlv3p_train_bcast_rows', P(T['dpool']), B, npix1, Cin, 1.0 / npix1, P(T['dfeat']), Cin, 1)
+
+    def _aspp_branch_bwd(self, i, feat):
+        T = self.T
+        self._sep_bwd('aspp%d' % i, feat, self.B, self.h, self.w, self.Cin, self.rates[i - 1], T['d%d' % i], T['a%d' % i], T['p%d' % i],
+                      self._p(T['concat'], 256 * (i + 1)), 1280, self._p(T['dconcat'], 256 * (i + 1)), 1280, T['g1_256'], T['gA'], T['gB'], T['dfeat_tmp'])
+
+    def all_reduce_gradients(self):
+        """ONE all-reduce (SUM) of the flat fp32 bucket holding every 1x1 kernel, the classifier bias and every depthwise kernel
+        (regions A|B; the loss is normalised by the GLOBAL batch, so the sum is the gradient of the global mean loss —
+        MirroredStrategy semantics, train.py:143-158).  BN gradients are already global."""
+        self._allreduce(self.grads[:self.endB])
+
+    def apply_gradients(self):
+        P = self._p
+        self._call('dlv3p_train_sgd', P(self.params), P(self.grads), P(self.velocity), self.endA, self.lr, self.momentum, self.l2, 1.0)
+        n = self.nparams - self.endA
+        self._call('dlv3p_train_sgd', P(self.params, self.endA), P(self.grads, self.endA), P(self.velocity, self.endA), n, self.lr, self.momentum, 0.0, 1.0)
+        self._refresh_bf16()
+        # moving statistics (Keras: moving <- moving * m + batch * (1 - m), biased variance); a handful of vector ops on <= 10k floats
+        sx, sq, nn = self._ix
+        n_ = self.stats[nn]
+        mean = self.stats[sx] / n_
+        var = (self.stats[sq] / n_ - mean * mean).clamp_(min=0)
+        m = self.bn_momentum
+        self.moving_mean.mul_(m).add_(mean, alpha=1 - m)
+        self.moving_var.mul_(m).add_(var, alpha=1 - m)
+
+    def train_step(self, feat, skip, labels) -> None:
+        """One optimizer step (fit's train_step): forward, loss, backward, gradient all-reduce, SGD update.  Asynchronous; read
+        the loss with .loss() (synchronises)."""
+        self.forward_backward(feat, skip, labels)
+        self.all_reduce_gradients()
+        self.apply_gradients()
+        self.step_count += 1
+
+    def loss(self) -> float:
+        """Global mean loss of the last step (sums the replicas' shares; synchronises)."""
+        v = self.T['loss'][:1].clone()
+        self._allreduce(v)
+        return float(v.item())

@@ -1,0 +1,80 @@
+"""ctypes binding of the training-step operators of libdlv3p.so (include/dlv3p_train.h).
+
+Plain device pointers (ints) and sizes in, nothing out: every call is asynchronous on the CUDA stream given.  There is no
+fallback: a missing library or a non-sm_100 device raises Dlv3pError."""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import ffi
+
+_vp, _i, _i64, _sz, _f, _u32 = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float, C.c_uint32
+
+# every symbol include/dlv3p_train.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ('dlv3p_train_gemm_partial_bytes', _sz, [_i64, _i, _i]),
+    ('dlv3p_train_gemm_nt', _i, [_i, _vp, _i64, _vp, _i64, _i64, _i, _i64, _vp, _i64, _i, _i, _vp, _vp]),
+    ('dlv3p_train_transpose', _i, [_i, _vp, _i64, _i, _i64, _vp, _i64, _vp]),
+    ('dlv3p_train_bn_apply', _i, [_i, _vp, _i64, _i, _vp, _vp, _vp, _f, _i, _vp, _i64, _vp]),
+    ('dlv3p_train_scratch_bytes', _sz, [_i]),
+    ('dlv3p_train_bn_bwd_stats', _i, [_i, _vp, _i64, _vp, _i64, _vp, _i64, _i, _vp, _f, _i, _vp, _vp, _vp]),
+    ('dlv3p_train_bn_bwd_apply', _i, [_i, _vp, _i64, _vp, _i64, _vp, _i64, _i, _vp, _vp, _vp, _f, _i, _vp, _vp]),
+    ('dlv3p_train_depthwise', _i, [_i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
+    ('dlv3p_train_depthwise_wgrad', _i, [_i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    ('dlv3p_train_resize', _i, [_i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i64, _vp]),
+    ('dlv3p_train_resize_bwd', _i, [_i, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    ('dlv3p_train_loss_scratch_bytes', _sz, []),
+    ('dlv3p_train_softmax_ce', _i, [_i, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
+    ('dlv3p_train_resize_bwd_planar', _i, [_i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i64, _vp]),
+    ('dlv3p_train_rows_reduce', _i, [_i, _vp, _i64, _i, _i, _i, _f, _vp, _i, _vp]),
+    ('dlv3p_train_bcast_rows', _i, [_i, _vp, _i, _i, _i, _f, _vp, _i64, _i, _vp]),
+    ('dlv3p_train_add', _i, [_i, _vp, _vp, _vp, _i64, _vp]),
+    ('dlv3p_train_dropout', _i, [_i, _vp, _vp, _i64, _u32, _f, _vp]),
+    ('dlv3p_train_sgd', _i, [_i, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _vp]),
+    ('dlv3p_train_cast_bf16', _i, [_i, _vp, _vp, _i64, _vp]),
+]
+
+_typed = False
+
+
+def lib() -> C.CDLL:
+    global _typed
+    L = ffi.load_library()
+    if not _typed:
+        for name, res, args in SYMBOLS:
+            fn = getattr(L, name)          # AttributeError == header / library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _typed = True
+    return L
+
+
+def call(name: str, *args) -> None:
+    """Invoke an int-returning entry point; raises Dlv3pError with the library's message on a negative status."""
+    ffi._check(getattr(lib(), name)(*args))
+
+
+def scratch_bytes(C_: int) -> int:
+    return int(lib().dlv3p_train_scratch_bytes(C_))
+
+
+def loss_scratch_bytes() -> int:
+    return int(lib().dlv3p_train_loss_scratch_bytes())
+
+
+def gemm_partial_bytes(M: int, N: int, splits: int) -> int:
+    return int(lib().dlv3p_train_gemm_partial_bytes(M, N, splits))
+
+
+def dropout_keep_mask(n: int, seed: int, rate: float):
+    """The mask dlv3p_train_dropout applies, restated in numpy (host-side bookkeeping and tests): element e is kept iff
+    fmix32(e * 0x9E3779B1 + seed) >= rate * 2^32."""
+    import numpy as np
+    e = np.arange(n, dtype=np.uint64)
+    h = (e * 0x9E3779B1 + (seed & 0xFFFFFFFF)) & 0xFFFFFFFF
+    h ^= h >> 16
+    h = (h * 0x85EBCA6B) & 0xFFFFFFFF
+    h ^= h >> 13
+    h = (h * 0xC2B2AE35) & 0xFFFFFFFF
+    h ^= h >> 16
+    return h >= int(float(rate) * 4294967296.0)
