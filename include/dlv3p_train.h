@@ -32,6 +32,11 @@ extern "C" {
 size_t dlv3p_train_gemm_partial_bytes(int64_t M, int N, int splits);
 int dlv3p_train_gemm_nt(int device, const void* a_bf16, int64_t lda, const void* b_bf16, int64_t ldb, int64_t M, int N, int64_t K,
                         void* d, int64_t ldd, int out_fp32, int splits, void* d_partial, void* cuda_stream);
+/* D[M, N] = A[K, M]^T * B[K, N]: both operands with the CONTRACTION index as the row (bf16 [K, M] row stride lda, [K, N] row stride
+ * ldb; M, N, K, strides multiples of 8) — the weight gradient dW[Cin, Cout] = X[pixels, Cin]^T dY[pixels, Cout] read straight from
+ * the NHWC activations (MN-major tcgen05 operand descriptors), no transpose pass.  Output / split-K as dlv3p_train_gemm_nt. */
+int dlv3p_train_gemm_tn(int device, const void* a_bf16, int64_t lda, const void* b_bf16, int64_t ldb, int64_t M, int N, int64_t K,
+                        void* d, int64_t ldd, int out_fp32, int splits, void* d_partial, void* cuda_stream);
 /* out[c][r] = in[r][c]; bf16, R and C even. */
 int dlv3p_train_transpose(int device, const void* in_bf16, int64_t R, int C, int64_t ld_in, void* out_bf16, int64_t ld_out, void* cuda_stream);
 
@@ -85,8 +90,10 @@ int dlv3p_train_bcast_rows(int device, const void* src_bf16, int B, int npix, in
                            void* cuda_stream);
 /* out = a + b (bf16, n % 8 == 0; in place allowed). */
 int dlv3p_train_add(int device, const void* a_bf16, const void* b_bf16, void* out_bf16, int64_t n, void* cuda_stream);
-/* Dropout(rate) (layers.py:161, :194) with a counter-based mask (seed, element index); the same call masks the gradient. */
-int dlv3p_train_dropout(int device, const void* x_bf16, void* out_bf16, int64_t n, uint32_t seed, float rate, void* cuda_stream);
+/* Dropout(rate) (layers.py:161, :194) with a counter-based mask (seed, element index); the same call masks the gradient.
+ * d_seed != NULL: the seed is read from device memory at execution time (a captured CUDA graph then draws a new mask per replay). */
+int dlv3p_train_dropout(int device, const void* x_bf16, void* out_bf16, int64_t n, uint32_t seed, const uint32_t* d_seed, float rate,
+                        void* cuda_stream);
 /* SGD(momentum) step on fp32 master weights with the l2 regulariser folded in: g' = gscale*g + 2*l2*w; v = m*v - lr*g'; w += v
  * (common/model_utils.py:122-123, layers.py:12-21). */
 int dlv3p_train_sgd(int device, float* w, const float* g, float* v, int64_t n, float lr, float momentum, float l2, float gscale, void* cuda_stream);

@@ -77,6 +77,30 @@ def test_gemm_nt(gpu, M, N, K, out_fp32, splits):
         assert float((d[:, N:].float() - 7.0).abs().max()) == 0.0   # padding columns untouched
 
 
+@pytest.mark.parametrize('M,N,K,splits,lda,ldb', [
+    (2048, 256, 8192, 9, 2048, 256),      # ASPP pointwise weight gradient
+    (304, 256, 16384, 49, 304, 256),      # decoder_conv0 pointwise: M tail inside the third 64-channel group
+    (256, 24, 4096, 16, 256, 24),         # classifier (padded NC)
+    (256, 48, 4096, 8, 256, 304),         # feature_projection0: dY read from a concat slice
+    (64, 256, 8, 1, 64, 256),             # image pooling: 8 contraction rows
+    (1280, 256, 1000, 4, 1280, 256),      # contraction tail (1000 % 64 != 0)
+])
+def test_gemm_tn(gpu, M, N, K, splits, lda, ldb):
+    """D[M,N] = A[K,M]^T B[K,N]: MN-major tcgen05 operands, the weight gradient without a transpose pass."""
+    torch = _t()
+    from dlv3p_b200 import train_ffi
+    g = torch.Generator(device='cuda').manual_seed(M + N + K)
+    abuf = torch.randn(K, lda, device='cuda', generator=g).to(torch.bfloat16)
+    bbuf = torch.randn(K, ldb, device='cuda', generator=g).to(torch.bfloat16)
+    boff = ldb - N - (ldb - N) % 8
+    d = torch.zeros(M, N, device='cuda', dtype=torch.float32)
+    part = torch.empty(max(1, train_ffi.gemm_partial_bytes(M, N, splits) // 4), device='cuda', dtype=torch.float32)
+    _call('dlv3p_train_gemm_tn', abuf.data_ptr(), lda, bbuf.data_ptr() + boff * 2, ldb, M, N, K, d.data_ptr(), N, 1, splits, part.data_ptr())
+    torch.cuda.synchronize()
+    ref = abuf[:, :M].double().t() @ bbuf[:, boff:boff + N].double()
+    assert float((d.double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+
+
 def test_gemm_nt_strided_operands_and_output_slice(gpu):
     """A read from a concat slice (lda > K), output written into a slice of a wider buffer."""
     torch = _t()
@@ -264,11 +288,17 @@ def test_pool_broadcast_add_dropout_sgd_cast(gpu):
     c = torch.zeros_like(a)
     _call('dlv3p_train_add', a.data_ptr(), b.data_ptr(), c.data_ptr(), n)
     d = torch.zeros_like(a)
-    _call('dlv3p_train_dropout', a.data_ptr(), d.data_ptr(), n, 12345, 0.5)
+    _call('dlv3p_train_dropout', a.data_ptr(), d.data_ptr(), n, 12345, 0, 0.5)
     torch.cuda.synchronize()
     assert torch.equal(c, (a.float() + b.float()).to(torch.bfloat16))
     keep = torch.from_numpy(train_ffi.dropout_keep_mask(n, 12345, 0.5)).cuda()
     assert torch.equal(d, torch.where(keep, (a.float() * 2).to(torch.bfloat16), torch.zeros_like(a)))
+    seed_t = torch.tensor([777], device='cuda', dtype=torch.int32)
+    d2 = torch.zeros_like(a)
+    _call('dlv3p_train_dropout', a.data_ptr(), d2.data_ptr(), n, 1, seed_t.data_ptr(), 0.5)        # seed from device memory wins
+    torch.cuda.synchronize()
+    keep2 = torch.from_numpy(train_ffi.dropout_keep_mask(n, 777, 0.5)).cuda()
+    assert torch.equal(d2, torch.where(keep2, (a.float() * 2).to(torch.bfloat16), torch.zeros_like(a)))
     w, gr, v = (torch.randn(1000, device='cuda', generator=g) for _ in range(3))
     w0, v0 = w.clone(), v.clone()
     _call('dlv3p_train_sgd', w.data_ptr(), gr.data_ptr(), v.data_ptr(), 1000, 0.01, 0.9, 2e-5, 1.0)
@@ -308,10 +338,13 @@ def _compare_step(tr_grads, d_feat, d_skip, loss, ref, cfg, ref32=None):
     assert abs(loss - ref['loss']) <= 2e-3 * abs(ref['loss']), (loss, ref['loss'])
     worst = {}
     dot = n1 = n2 = 0.0
+    # a gradient that is zero in exact arithmetic (a depthwise tap no pixel reaches; a scale BatchNorm removes) is rounding noise in
+    # both implementations: errors are taken relative to max(|ref|, 2 % of the median gradient-tensor norm)
+    floor = 0.02 * float(np.median([np.linalg.norm(np.asarray(g, np.float64)) for g in ref['grads'].values()]))
     for key, g in ref['grads'].items():
         got = np.asarray(tr_grads[key], np.float64)
         g = np.asarray(g, np.float64).reshape(got.shape)
-        worst[key] = rel_l2(got, g)
+        worst[key] = float(np.linalg.norm(got - g) / max(np.linalg.norm(g), floor))
         dot += float((got * g).sum()); n1 += float((got * got).sum()); n2 += float((g * g).sum())
     worst['d_feat'] = rel_l2(d_feat, ref['d_feat'].reshape(d_feat.shape))
     worst['d_skip'] = rel_l2(d_skip, ref['d_skip'].reshape(d_skip.shape))

@@ -26,6 +26,7 @@
 #include "aspp_dw_fast.cuh"
 #include "aspp_dw_gather.cuh"
 #include "bn_train.cuh"
+#include "train_kernels.cuh"
 
 using namespace dlv3p;
 
@@ -1731,7 +1732,10 @@ int dlv3p_op_confusion_matrix(int device, const uint8_t* d_pred, const uint8_t* 
   return DLV3P_OK;   // asynchronous; d_confusion is ACCUMULATED (zero it once per evaluation)
 }
 
-size_t dlv3p_op_bn_scratch_bytes(int C) { return static_cast<size_t>(kBnBands) * 2 * (C > 0 ? C : 0) * sizeof(float); }
+size_t dlv3p_op_bn_scratch_bytes(int C) {
+  const size_t a = static_cast<size_t>(kBnBands) * 2 * (C > 0 ? C : 0), b = col_scratch_floats(C, 2);
+  return (a > b ? a : b) * sizeof(float);
+}
 
 int dlv3p_op_bn_stats(int device, const void* x_bf16, int64_t M, int C, float* d_stats, void* d_scratch, void* cuda_stream) {
   int sms = 0, r = op_prolog(device, &sms);
@@ -1739,8 +1743,14 @@ int dlv3p_op_bn_stats(int device, const void* x_bf16, int64_t M, int C, float* d
   if (!x_bf16 || !d_stats || !d_scratch || M < 1 || C < 2 || C % 2) return fail(nullptr, DLV3P_ERR_INVALID, "op_bn_stats: bad arguments (C even)");
   if (M >= (1ll << 24)) return fail(nullptr, DLV3P_ERR_UNSUPPORTED, "op_bn_stats: the row count travels as fp32 (M < 2^24 per replica)");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-  bn_stats_partial_kernel<<<dim3(ceil_div(C, 64), kBnBands), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x_bf16), M, C, static_cast<float*>(d_scratch));
-  bn_stats_final_kernel<<<ceil_div(2 * C, 256), 256, 0, st>>>(static_cast<const float*>(d_scratch), M, C, d_stats);
+  if (C % 8 == 0) {   // 16-byte loads, ~4 blocks per SM in flight
+    const int bands = col_bands(C);
+    bn_stats_vec_kernel<<<dim3(ceil_div(C, 256), bands), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x_bf16), M, C, bands, static_cast<float*>(d_scratch));
+    bands_final_kernel<<<ceil_div(2 * C, 32), dim3(32, 8), 0, st>>>(static_cast<const float*>(d_scratch), bands, 2 * C, d_stats, 2 * C, static_cast<float>(M));
+  } else {
+    bn_stats_partial_kernel<<<dim3(ceil_div(C, 64), kBnBands), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x_bf16), M, C, static_cast<float*>(d_scratch));
+    bn_stats_final_kernel<<<ceil_div(2 * C, 256), 256, 0, st>>>(static_cast<const float*>(d_scratch), M, C, d_stats);
+  }
   CU_TRY(nullptr, cudaGetLastError());
   return DLV3P_OK;   // asynchronous: the caller all-reduces d_stats on the same stream / after an event
 }
@@ -1751,8 +1761,9 @@ int dlv3p_op_bn_apply(int device, const void* x_bf16, int64_t M, int C, const fl
   if (r) return r;
   if (!x_bf16 || !d_stats || !d_gamma || !d_beta || !y_bf16 || M < 1 || C < 8 || C % 8) return fail(nullptr, DLV3P_ERR_INVALID, "op_bn_apply: bad arguments (C % 8)");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-  bn_apply_kernel<<<grid_for(static_cast<size_t>(M) * (C / 8), sms), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x_bf16), M, C, d_stats, d_gamma, d_beta, eps, relu,
-                                                                                  static_cast<__nv_bfloat16*>(y_bf16));
+  if (C > 4096) return fail(nullptr, DLV3P_ERR_UNSUPPORTED, "op_bn_apply: C <= 4096");
+  bn_apply_vec_kernel<<<grid_for(static_cast<size_t>(M) * (C / 8), sms), 256, 2 * C * sizeof(float), st>>>(static_cast<const __nv_bfloat16*>(x_bf16), M, C, d_stats, d_gamma,
+                                                                                                          d_beta, eps, relu, static_cast<__nv_bfloat16*>(y_bf16), C);
   CU_TRY(nullptr, cudaGetLastError());
   return DLV3P_OK;
 }

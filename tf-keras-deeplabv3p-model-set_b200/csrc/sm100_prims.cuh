@@ -204,6 +204,25 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr_byte
 // advance the start address by `bytes` inside the swizzle atom (K step of 16 bf16 = 32 bytes)
 __device__ __forceinline__ uint64_t smem_desc_advance(uint64_t desc, uint32_t bytes) { return desc + (bytes >> 4); }
 
+// MN-major operand tile ("transposed" operand: the M / N index is contiguous in memory, as in a weight-gradient GEMM that
+// contracts over pixels): TMA boxes of [64 contraction rows][64 elements = 128 bytes], 128-byte swizzle, one box per group of
+// 64 M/N elements stored back to back.  Canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: rows of the
+// contraction index are 128 bytes apart, 8-row groups SBO = 1024 bytes apart, 64-element M/N groups LBO = box size apart.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr_bytes, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr_bytes >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// same instruction descriptor with both operands MN-major (bits 15 / 16)
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+
 // UMMA instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, shape M x N (K = 16)
 //   [4,6) D format (1 = f32)  [7,10) A format (1 = bf16)  [10,13) B format (1 = bf16)
 //   [15] A major (0 = K)  [16] B major (0 = K)  [17,23) N >> 3  [24,29) M >> 4

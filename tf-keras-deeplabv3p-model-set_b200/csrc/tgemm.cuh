@@ -43,7 +43,10 @@ struct TgCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 256;
 };
 
-template <int BN>
+// TN = false: D = A[M,K] * B[N,K]^T (operands K-major).  TN = true: D[M,N] = A[Kc,M]^T * B[Kc,N] — both operands MN-major, read
+// straight from the [pixels, channels] activations and activation gradients: the weight gradient without a transpose pass.
+// (tensor maps then use boxes of {64 channels, 64 pixels}; a stage holds 2 + BN/64 boxes.)
+template <int BN, bool TN = false>
 __global__ void __launch_bounds__(kTgThreads, 1) tgemm_kernel(const __grid_constant__ TgLaunch L) {
   using Cfg = TgCfg<BN>;
   constexpr int kStages = Cfg::kStages;
@@ -97,16 +100,25 @@ __global__ void __launch_bounds__(kTgThreads, 1) tgemm_kernel(const __grid_const
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if constexpr (TN) {
+#pragma unroll
+            for (int g = 0; g < kTgBM / 64; ++g)
+              tma_load_2d(smem_a + stage * (kTgBM * 128) + g * 8192, &L.tmap_a, &full_bar[stage], mt * kTgBM + g * 64, kb * kTgBK, kEvictNormal);
+#pragma unroll
+            for (int g = 0; g < BN / 64; ++g)
+              tma_load_2d(smem_b + stage * (BN * 128) + g * 8192, &L.tmap_b, &full_bar[stage], nt * BN + g * 64, kb * kTgBK, kEvictNormal);
+          } else {
           tma_load_2d(smem_a + stage * (kTgBM * 128), &L.tmap_a, &full_bar[stage], kb * kTgBK, mt * kTgBM, kEvictNormal);
           tma_load_2d(smem_b + stage * (BN * 128), &L.tmap_b, &full_bar[stage], kb * kTgBK, nt * BN, kEvictNormal);
           if constexpr (BN > 128)
             tma_load_2d(smem_b + stage * (BN * 128) + 128 * 128, &L.tmap_b, &full_bar[stage], kb * kTgBK, nt * BN + 128, kEvictNormal);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc_bf16(kTgBM, BN);
+    constexpr uint32_t idesc = TN ? make_idesc_bf16_mn(kTgBM, BN) : make_idesc_bf16(kTgBM, BN);
     uint32_t stage = 0, phase = 0, it = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
       const int split = item / tiles;
@@ -120,11 +132,13 @@ __global__ void __launch_bounds__(kTgThreads, 1) tgemm_kernel(const __grid_const
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
         if (elect_one()) {
-          const uint64_t da = make_smem_desc_sw128(smem_u32(smem_a + stage * (kTgBM * 128)));
-          const uint64_t db = make_smem_desc_sw128(smem_u32(smem_b + stage * (BN * 128)));
+          const uint32_t sa = smem_u32(smem_a + stage * (kTgBM * 128)), sb = smem_u32(smem_b + stage * (BN * 128));
+          const uint64_t da = TN ? make_smem_desc_sw128_mn(sa, 8192) : make_smem_desc_sw128(sa);
+          const uint64_t db = TN ? make_smem_desc_sw128_mn(sb, 8192) : make_smem_desc_sw128(sb);
+          constexpr uint32_t kstep = TN ? 16 * 128 : 32;   // 16 contraction rows of 128 bytes | 16 elements inside the 128-byte row
 #pragma unroll
           for (int k = 0; k < kTgBK / 16; ++k)
-            umma_bf16_ss(tmem_d, smem_desc_advance(da, k * 32), smem_desc_advance(db, k * 32), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_bf16_ss(tmem_d, smem_desc_advance(da, k * kstep), smem_desc_advance(db, k * kstep), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
         }

@@ -24,20 +24,24 @@ int train_prolog(int device, int* num_sms) {
   return 0;
 }
 
-template <int BN>
+template <int BN, bool TN>
 cudaError_t launch_tgemm_t(const TgLaunch& L, int num_sms, cudaStream_t st) {
   static bool attr_done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(tgemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TgCfg<BN>::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(tgemm_kernel<BN, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TgCfg<BN>::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_done[dev & 63] = true;
   }
   const int items = L.m_tiles * L.n_tiles * L.splits;
   const int grid = items < num_sms ? items : num_sms;
-  tgemm_kernel<BN><<<grid, kTgThreads, TgCfg<BN>::kSmemBytes, st>>>(L);
+  tgemm_kernel<BN, TN><<<grid, kTgThreads, TgCfg<BN>::kSmemBytes, st>>>(L);
   return cudaGetLastError();
+}
+// 2D bf16 [rows, cols] row-major (ld elements), box {64 cols, 64 rows}, 128B swizzle: MN-major operand boxes
+bool encode_2d_sw128_box64(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, std::string* err) {
+  return encode_2d_sw128(tm, base, rows, cols, ld, 64, err);
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -50,21 +54,25 @@ size_t dlv3p_train_gemm_partial_bytes(int64_t M, int N, int splits) {
   return splits > 1 ? static_cast<size_t>(splits) * static_cast<size_t>(M) * static_cast<size_t>(N) * sizeof(float) : 0;
 }
 
-int dlv3p_train_gemm_nt(int device, const void* a, int64_t lda, const void* b, int64_t ldb, int64_t M, int N, int64_t K, void* d, int64_t ldd,
-                        int out_fp32, int splits, void* d_partial, void* cuda_stream) {
+static int train_gemm_impl(bool tn, int device, const void* a, int64_t lda, const void* b, int64_t ldb, int64_t M, int N, int64_t K, void* d, int64_t ldd,
+                           int out_fp32, int splits, void* d_partial, void* cuda_stream) {
   int sms = 0, r = train_prolog(device, &sms);
   if (r) return r;
-  if (!a || !b || !d || M < 1 || N < 1 || K < 8 || K % 8 || lda % 8 || ldb % 8 || lda < K || ldb < K || ldd < N || !aligned16(a) || !aligned16(b) ||
-      M > (1ll << 30) || K > (1ll << 30))
-    return fail(nullptr, DLV3P_ERR_INVALID, "train_gemm_nt: bad arguments (K, lda, ldb multiples of 8; 16-byte aligned operands)");
-  if (!out_fp32 && (ldd % 8 || !aligned16(d))) return fail(nullptr, DLV3P_ERR_INVALID, "train_gemm_nt: bf16 output needs ldd % 8 == 0 and a 16-byte aligned base");
-  if (out_fp32 && (ldd % 4 || !aligned16(d))) return fail(nullptr, DLV3P_ERR_INVALID, "train_gemm_nt: fp32 output needs ldd % 4 == 0 and a 16-byte aligned base");
+  const int64_t amin = tn ? M : K, bmin = tn ? N : K;
+  if (!a || !b || !d || M < 1 || N < 1 || K < 8 || K % 8 || lda % 8 || ldb % 8 || lda < amin || ldb < bmin || ldd < N || !aligned16(a) || !aligned16(b) ||
+      M > (1ll << 30) || K > (1ll << 30) || (tn && (M % 8 || N % 8)))
+    return fail(nullptr, DLV3P_ERR_INVALID, "train_gemm: bad arguments (K, lda, ldb multiples of 8; 16-byte aligned operands)");
+  if (!out_fp32 && (ldd % 8 || !aligned16(d))) return fail(nullptr, DLV3P_ERR_INVALID, "train_gemm: bf16 output needs ldd % 8 == 0 and a 16-byte aligned base");
+  if (out_fp32 && (ldd % 4 || !aligned16(d))) return fail(nullptr, DLV3P_ERR_INVALID, "train_gemm: fp32 output needs ldd % 4 == 0 and a 16-byte aligned base");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   const int BN = N > 64 ? 256 : 64;
   TgLaunch L{};
   std::string terr;
-  if (!encode_2d_sw128(&L.tmap_a, a, M, K, lda, 128, &terr) || !encode_2d_sw128(&L.tmap_b, b, N, K, ldb, BN >= 128 ? 128 : BN, &terr))
+  if (tn) {   // operands [K, M] and [K, N]: boxes of 64 channels x 64 contraction rows
+    if (!encode_2d_sw128_box64(&L.tmap_a, a, K, M, lda, &terr) || !encode_2d_sw128_box64(&L.tmap_b, b, K, N, ldb, &terr)) return fail(nullptr, DLV3P_ERR_CUDA, terr);
+  } else if (!encode_2d_sw128(&L.tmap_a, a, M, K, lda, 128, &terr) || !encode_2d_sw128(&L.tmap_b, b, N, K, ldb, BN >= 128 ? 128 : BN, &terr)) {
     return fail(nullptr, DLV3P_ERR_CUDA, terr);
+  }
   L.M = static_cast<int>(M); L.N = N; L.K = static_cast<int>(K);
   L.m_tiles = ceil_div(L.M, kTgBM); L.n_tiles = ceil_div(N, BN);
   L.kblocks = ceil_div(L.K, kTgBK);
@@ -73,17 +81,29 @@ int dlv3p_train_gemm_nt(int device, const void* a, int64_t lda, const void* b, i
   L.kb_per_split = ceil_div(L.kblocks, splits);
   L.splits = ceil_div(L.kblocks, L.kb_per_split);
   if (L.splits > 1) {
-    if (!d_partial || (N % 4)) return fail(nullptr, DLV3P_ERR_INVALID, "train_gemm_nt: split-K needs d_partial and N % 4 == 0");
+    if (!d_partial || (N % 4)) return fail(nullptr, DLV3P_ERR_INVALID, "train_gemm: split-K needs d_partial and N % 4 == 0");
     L.out = d_partial; L.ldd = N; L.out_mode = kTgOutPartial;
   } else {
     L.out = d; L.ldd = ldd; L.out_mode = out_fp32 ? kTgOutF32 : kTgOutBf16;
   }
-  CU_TRY(nullptr, BN == 256 ? launch_tgemm_t<256>(L, sms, st) : launch_tgemm_t<64>(L, sms, st));
+  cudaError_t e;
+  if (tn) e = BN == 256 ? launch_tgemm_t<256, true>(L, sms, st) : launch_tgemm_t<64, true>(L, sms, st);
+  else e = BN == 256 ? launch_tgemm_t<256, false>(L, sms, st) : launch_tgemm_t<64, false>(L, sms, st);
+  CU_TRY(nullptr, e);
   if (L.splits > 1) {
     tgemm_reduce_kernel<<<grid_for(static_cast<size_t>(M) * N, sms), 256, 0, st>>>(static_cast<const float*>(d_partial), L.splits, M, N, d, ldd, out_fp32);
     CU_TRY(nullptr, cudaGetLastError());
   }
   return DLV3P_OK;
+}
+
+int dlv3p_train_gemm_nt(int device, const void* a, int64_t lda, const void* b, int64_t ldb, int64_t M, int N, int64_t K, void* d, int64_t ldd,
+                        int out_fp32, int splits, void* d_partial, void* cuda_stream) {
+  return train_gemm_impl(false, device, a, lda, b, ldb, M, N, K, d, ldd, out_fp32, splits, d_partial, cuda_stream);
+}
+int dlv3p_train_gemm_tn(int device, const void* a, int64_t lda, const void* b, int64_t ldb, int64_t M, int N, int64_t K, void* d, int64_t ldd,
+                        int out_fp32, int splits, void* d_partial, void* cuda_stream) {
+  return train_gemm_impl(true, device, a, lda, b, ldb, M, N, K, d, ldd, out_fp32, splits, d_partial, cuda_stream);
 }
 
 int dlv3p_train_transpose(int device, const void* in, int64_t R, int C, int64_t ld_in, void* out, int64_t ld_out, void* cuda_stream) {
@@ -103,13 +123,20 @@ int dlv3p_train_bn_apply(int device, const void* x, int64_t M, int C, const floa
   if (r) return r;
   if (!x || !d_stats || !d_gamma || !d_beta || !y || M < 1 || C < 8 || C % 8 || ldy % 8 || ldy < C || !aligned16(y))
     return fail(nullptr, DLV3P_ERR_INVALID, "train_bn_apply: bad arguments (C % 8, ldy % 8)");
-  bn_apply_ld_kernel<<<grid_for(static_cast<size_t>(M) * (C / 8), sms), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+  if (C > 4096) return fail(nullptr, DLV3P_ERR_UNSUPPORTED, "train_bn_apply: C <= 4096");
+  bn_apply_vec_kernel<<<grid_for(static_cast<size_t>(M) * (C / 8), sms), 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(cuda_stream)>>>(
       static_cast<const __nv_bfloat16*>(x), M, C, d_stats, d_gamma, d_beta, eps, relu, static_cast<__nv_bfloat16*>(y), ldy);
   CU_TRY(nullptr, cudaGetLastError());
   return DLV3P_OK;
 }
 
-size_t dlv3p_train_scratch_bytes(int C) { return static_cast<size_t>(kTrBands) * 9 * (C > 0 ? C : 0) * sizeof(float); }
+size_t dlv3p_train_scratch_bytes(int C) {
+  const size_t c = C > 0 ? C : 0;
+  size_t a = static_cast<size_t>(kTrBands) * 9 * c, b = col_scratch_floats(C, 2), d = static_cast<size_t>(kDwWgradBlocks) * 9 * c;
+  if (b > a) a = b;
+  if (d > a) a = d;
+  return a * sizeof(float);
+}
 
 int dlv3p_train_bn_bwd_stats(int device, const void* dy, int64_t ld_dy, const void* y, int64_t ld_y, const void* x, int64_t M, int C, const float* d_stats,
                              float eps, int relu, float* d_sums, void* d_scratch, void* cuda_stream) {
@@ -118,10 +145,18 @@ int dlv3p_train_bn_bwd_stats(int device, const void* dy, int64_t ld_dy, const vo
   if (!dy || !x || !d_stats || !d_sums || !d_scratch || (relu && !y) || M < 1 || C < 2 || C % 2 || ld_dy % 2 || ld_y % 2)
     return fail(nullptr, DLV3P_ERR_INVALID, "train_bn_bwd_stats: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-  bn_bwd_stats_partial_kernel<<<dim3(ceil_div(C, 64), kTrBands), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dy), ld_dy, static_cast<const __nv_bfloat16*>(y), ld_y,
-                                                                                static_cast<const __nv_bfloat16*>(x), M, C, d_stats, eps, relu,
-                                                                                static_cast<float*>(d_scratch));
-  bands_final_kernel<<<ceil_div(2 * C, 256), 256, 0, st>>>(static_cast<const float*>(d_scratch), kTrBands, 2 * C, d_sums);
+  if (C % 8 == 0 && ld_dy % 8 == 0 && ld_y % 8 == 0 && aligned16(dy) && (!relu || aligned16(y))) {
+    const int bands = col_bands(C);
+    bn_bwd_stats_vec_kernel<<<dim3(ceil_div(C, 256), bands), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dy), ld_dy, static_cast<const __nv_bfloat16*>(y), ld_y,
+                                                                            static_cast<const __nv_bfloat16*>(x), M, C, d_stats, eps, relu, bands,
+                                                                            static_cast<float*>(d_scratch));
+    bands_final_kernel<<<ceil_div(2 * C, 32), dim3(32, 8), 0, st>>>(static_cast<const float*>(d_scratch), bands, 2 * C, d_sums);
+  } else {
+    bn_bwd_stats_partial_kernel<<<dim3(ceil_div(C, 64), kTrBands), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dy), ld_dy, static_cast<const __nv_bfloat16*>(y), ld_y,
+                                                                                  static_cast<const __nv_bfloat16*>(x), M, C, d_stats, eps, relu,
+                                                                                  static_cast<float*>(d_scratch));
+    bands_final_kernel<<<ceil_div(2 * C, 32), dim3(32, 8), 0, st>>>(static_cast<const float*>(d_scratch), kTrBands, 2 * C, d_sums);
+  }
   CU_TRY(nullptr, cudaGetLastError());
   return DLV3P_OK;
 }
@@ -133,7 +168,8 @@ int dlv3p_train_bn_bwd_apply(int device, const void* dy, int64_t ld_dy, const vo
   if (!dy || !x || !d_stats || !d_sums || !d_gamma || !dx || (relu && !y) || M < 1 || C < 8 || C % 8 || ld_dy % 8 || ld_y % 8 || !aligned16(dy) ||
       (relu && !aligned16(y)))
     return fail(nullptr, DLV3P_ERR_INVALID, "train_bn_bwd_apply: bad arguments (C % 8, strides % 8, 16-byte aligned slices)");
-  bn_bwd_apply_kernel<<<grid_for(static_cast<size_t>(M) * (C / 8), sms), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+  if (C > 4096) return fail(nullptr, DLV3P_ERR_UNSUPPORTED, "train_bn_bwd_apply: C <= 4096");
+  bn_bwd_apply_vec_kernel<<<grid_for(static_cast<size_t>(M) * (C / 8), sms), 256, 3 * C * sizeof(float), static_cast<cudaStream_t>(cuda_stream)>>>(
       static_cast<const __nv_bfloat16*>(dy), ld_dy, static_cast<const __nv_bfloat16*>(y), ld_y, static_cast<const __nv_bfloat16*>(x), M, C, d_stats, d_sums,
       d_gamma, eps, relu, static_cast<__nv_bfloat16*>(dx));
   CU_TRY(nullptr, cudaGetLastError());
@@ -160,9 +196,17 @@ int dlv3p_train_depthwise_wgrad(int device, const void* x, const void* dy, int B
   if (!x || !dy || !d_dw || !d_scratch || B < 1 || H < 1 || W_ < 1 || C < 2 || C % 2 || rate < 1)
     return fail(nullptr, DLV3P_ERR_INVALID, "train_depthwise_wgrad: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-  dw_wgrad_partial_kernel<<<dim3(ceil_div(C, 64), kTrBands), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), B, H, W_, C, rate,
-                                                                            static_cast<float*>(d_scratch));
-  bands_final_kernel<<<ceil_div(9 * C, 256), 256, 0, st>>>(static_cast<const float*>(d_scratch), kTrBands, 9 * C, d_dw);
+  if (C % 8 == 0) {
+    const long long npix = static_cast<long long>(B) * H * W_;
+    const int G = npix < kDwWgradBlocks ? static_cast<int>(npix) : kDwWgradBlocks;
+    dw_wgrad_vec_kernel<<<dim3(G, ceil_div(C / 8, 256)), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), B, H, W_, C, rate,
+                                                                        static_cast<float*>(d_scratch));
+    bands_final_kernel<<<ceil_div(9 * C, 32), dim3(32, 8), 0, st>>>(static_cast<const float*>(d_scratch), G, 9 * C, d_dw);
+  } else {
+    dw_wgrad_partial_kernel<<<dim3(ceil_div(C, 64), kTrBands), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), B, H, W_, C, rate,
+                                                                              static_cast<float*>(d_scratch));
+    bands_final_kernel<<<ceil_div(9 * C, 32), dim3(32, 8), 0, st>>>(static_cast<const float*>(d_scratch), kTrBands, 9 * C, d_dw);
+  }
   CU_TRY(nullptr, cudaGetLastError());
   return DLV3P_OK;
 }
@@ -268,13 +312,13 @@ int dlv3p_train_add(int device, const void* a, const void* b, void* out, int64_t
   return DLV3P_OK;
 }
 
-int dlv3p_train_dropout(int device, const void* x, void* out, int64_t n, uint32_t seed, float rate, void* cuda_stream) {
+int dlv3p_train_dropout(int device, const void* x, void* out, int64_t n, uint32_t seed, const uint32_t* d_seed, float rate, void* cuda_stream) {
   int sms = 0, r = train_prolog(device, &sms);
   if (r) return r;
   if (!x || !out || n < 8 || n % 8 || n >= (1ll << 32) || !(rate >= 0.0f) || !(rate < 1.0f)) return fail(nullptr, DLV3P_ERR_INVALID, "train_dropout: bad arguments");
   const uint32_t threshold = static_cast<uint32_t>(static_cast<double>(rate) * 4294967296.0);
   dropout_kernel<<<grid_for(static_cast<size_t>(n / 8), sms), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), static_cast<size_t>(n / 8), seed, threshold, 1.0f / (1.0f - rate));
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), static_cast<size_t>(n / 8), seed, d_seed, threshold, 1.0f / (1.0f - rate));
   CU_TRY(nullptr, cudaGetLastError());
   return DLV3P_OK;
 }

@@ -13,6 +13,7 @@
 // Every reduction uses a fixed tree (no atomics): results are bit-reproducible run to run.
 #pragma once
 
+#include "bn_train.cuh"
 #include "mem_kernels.cuh"
 
 namespace dlv3p {
@@ -90,14 +91,26 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_partial_kernel(const __nv_bf
     if (c < C) partial[(static_cast<size_t>(band) * 2 + which) * C + c] = s;
   }
 }
-// sums[2C] = sum over bands (fixed order)
-__global__ void bands_final_kernel(const float* __restrict__ partial, int bands, int n, float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// out[i] = sum over bands of partial[b][i], fixed order: block (32, 8) — the 8 rows of threads take interleaved bands (independent
+// loads in flight), then one pass over shared memory.  extra_index >= 0: out[extra_index] = extra_value (the BN row count).
+__global__ void __launch_bounds__(256) bands_final_kernel(const float* __restrict__ partial, int bands, int n, float* __restrict__ out,
+                                                          int extra_index = -1, float extra_value = 0.0f) {
+  __shared__ float s_part[8][33];
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
   if (i < n) {
-    float s = 0.f;
-    for (int b = 0; b < bands; ++b) s += partial[static_cast<size_t>(b) * n + i];
-    out[i] = s;
+#pragma unroll 4
+    for (int b = threadIdx.y; b < bands; b += 8) s += __ldg(partial + static_cast<size_t>(b) * n + i);
   }
+  s_part[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_part[w][threadIdx.x];
+    out[i] = t;
+  }
+  if (extra_index >= 0 && blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0) out[extra_index] = extra_value;
 }
 // dx = gamma * invstd * (g - S1/n - xhat * S2/n), n = GLOBAL row count (stats[2C], all-reduced), sums all-reduced
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, long long ld_dy, const __nv_bfloat16* __restrict__ y,
@@ -240,6 +253,7 @@ struct ResizeBwdPlanarParams {
   int B, NC, hi, wi, ho, wo;
   float sy, sx;
 };
+constexpr int kAdjMaxSpan = 24;   // candidate outputs per input and axis held in registers (covers scales up to x8)
 __global__ void __launch_bounds__(256) resize_bwd_planar_kernel(const ResizeBwdPlanarParams P) {
   const long long total = static_cast<long long>(P.B) * P.NC * P.hi * P.wi;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -254,12 +268,30 @@ __global__ void __launch_bounds__(256) resize_bwd_planar_kernel(const ResizeBwdP
     adjoint_range(j, P.sx, P.wo, xa, xb);
     const float* plane = P.dy + (static_cast<long long>(b) * P.NC + c) * P.ho * P.wo;
     float acc = 0.f;
-    for (int Y = ya; Y <= yb; ++Y) {
-      const float wy = adjoint_weight(Y, P.sy, P.hi, i);
-      if (wy == 0.0f) continue;
-      for (int X = xa; X <= xb; ++X) {
-        const float wgt = wy * adjoint_weight(X, P.sx, P.wi, j);
-        if (wgt != 0.0f) acc = fmaf(wgt, __ldg(plane + static_cast<long long>(Y) * P.wo + X), acc);
+    if (xb - xa < kAdjMaxSpan) {
+      float wx[kAdjMaxSpan];   // the horizontal weights once per thread instead of once per (Y, X)
+#pragma unroll
+      for (int k = 0; k < kAdjMaxSpan; ++k) wx[k] = (xa + k <= xb) ? adjoint_weight(xa + k, P.sx, P.wi, j) : 0.0f;
+      for (int Y = ya; Y <= yb; ++Y) {
+        const float wy = adjoint_weight(Y, P.sy, P.hi, i);
+        if (wy == 0.0f) continue;
+        const float* rowp = plane + static_cast<long long>(Y) * P.wo + xa;
+        float racc = 0.f;
+#pragma unroll
+        for (int k = 0; k < kAdjMaxSpan; ++k)
+          if (xa + k <= xb && wx[k] != 0.0f) racc = fmaf(wx[k], __ldg(rowp + k), racc);
+        acc = fmaf(wy, racc, acc);
+      }
+    } else {
+      for (int Y = ya; Y <= yb; ++Y) {
+        const float wy = adjoint_weight(Y, P.sy, P.hi, i);
+        if (wy == 0.0f) continue;
+        float racc = 0.f;
+        for (int X = xa; X <= xb; ++X) {
+          const float wgt = adjoint_weight(X, P.sx, P.wi, j);
+          if (wgt != 0.0f) racc = fmaf(wgt, __ldg(plane + static_cast<long long>(Y) * P.wo + X), racc);
+        }
+        acc = fmaf(wy, racc, acc);
       }
     }
     P.dx[((static_cast<long long>(b) * P.hi + i) * P.wi + j) * P.ld_dx + c] = __float2bfloat16_rn(acc);
@@ -425,7 +457,8 @@ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
   return h;
 }
 __global__ void __launch_bounds__(256) dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, size_t n8, uint32_t seed,
-                                                      uint32_t threshold, float keep_scale) {
+                                                      const uint32_t* __restrict__ d_seed, uint32_t threshold, float keep_scale) {
+  if (d_seed) seed = *d_seed;    // seed in device memory: a captured CUDA graph draws a new mask at every replay
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float v[8];
     unpack8(*reinterpret_cast<const uint4*>(x + 8 * i), v);
@@ -454,5 +487,150 @@ __global__ void __launch_bounds__(256) cast_f32_bf16_any_kernel(const float* __r
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
     out[i] = __float2bfloat16_rn(in[i]);
 }
+
+
+// ------------------------------------------------------------------------------------------------ vectorised variants (C % 8 == 0)
+// SyncBN backward statistics, same structure as bn_stats_vec_kernel.  partial [bands][2][C] = sum g | sum g * xhat
+__global__ void __launch_bounds__(256) bn_bwd_stats_vec_kernel(const __nv_bfloat16* __restrict__ dy, long long ld_dy, const __nv_bfloat16* __restrict__ y,
+                                                               long long ld_y, const __nv_bfloat16* __restrict__ x, long long M, int C,
+                                                               const float* __restrict__ stats, float eps, int relu, int bands, float* __restrict__ partial) {
+  __shared__ float s_red[8][32][17];
+  const int chunk = blockIdx.x, band = blockIdx.y;
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int c0 = chunk * 256 + lane * 8;
+  const long long rows_per_band = (M + bands - 1) / bands;
+  const long long r0 = band * rows_per_band, r1 = min(M, r0 + rows_per_band);
+  float acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+  if (c0 < C) {
+    float mean[8], invstd[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bn_consts(stats, C, c0 + k, eps, mean[k], invstd[k]);
+#pragma unroll 2
+    for (long long r = r0 + wp; r < r1; r += 8) {
+      float g[8], xv[8];
+      unpack8(ldg_nc_v4(dy + r * ld_dy + c0), g);
+      unpack8(ldg_nc_v4(x + r * C + c0), xv);
+      if (relu) {
+        float yv[8];
+        unpack8(ldg_nc_v4(y + r * ld_y + c0), yv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (!(yv[k] > 0.0f)) g[k] = 0.0f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { acc[k] += g[k]; acc[8 + k] = fmaf(g[k], (xv[k] - mean[k]) * invstd[k], acc[8 + k]); }
+    }
+  }
+  col_reduce_store(acc, s_red, chunk, band, C, partial);
+}
+// dx = A*g + Bc*x + Cc with per-channel A = gamma*invstd, Bc = -A*invstd*S2/n, Cc = -A*S1/n - Bc*mean (the expansion of
+// gamma*invstd*(g - S1/n - xhat*S2/n)), computed once per block into shared memory (dynamic smem: 3*C floats)
+__global__ void __launch_bounds__(256) bn_bwd_apply_vec_kernel(const __nv_bfloat16* __restrict__ dy, long long ld_dy, const __nv_bfloat16* __restrict__ y,
+                                                               long long ld_y, const __nv_bfloat16* __restrict__ x, long long M, int C,
+                                                               const float* __restrict__ stats, const float* __restrict__ sums, const float* __restrict__ gamma,
+                                                               float eps, int relu, __nv_bfloat16* __restrict__ dx) {
+  extern __shared__ float s_coef[];   // [C] A | [C] Bc | [C] Cc
+  {
+    const float inv_n = 1.0f / stats[2 * C];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float mean, invstd;
+      bn_consts(stats, C, c, eps, mean, invstd);
+      const float A = gamma[c] * invstd;
+      const float Bc = -A * invstd * (sums[C + c] * inv_n);
+      s_coef[c] = A;
+      s_coef[C + c] = Bc;
+      s_coef[2 * C + c] = -A * (sums[c] * inv_n) - Bc * mean;
+    }
+  }
+  __syncthreads();
+  const int vecs = C >> 3;
+  const long long total = M * vecs;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int vec = static_cast<int>(idx % vecs);
+    const long long row = idx / vecs;
+    float g[8], xv[8];
+    unpack8(ldg_nc_v4(dy + row * ld_dy + vec * 8), g);
+    unpack8(ldg_nc_v4(x + idx * 8), xv);
+    if (relu) {
+      float yv[8];
+      unpack8(ldg_nc_v4(y + row * ld_y + vec * 8), yv);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (!(yv[k] > 0.0f)) g[k] = 0.0f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = vec * 8 + k;
+      g[k] = fmaf(s_coef[c], g[k], fmaf(s_coef[C + c], xv[k], s_coef[2 * C + c]));
+    }
+    stg_v4(dx + idx * 8, pack8(g));
+  }
+}
+
+// depthwise weight gradient, vectorised: one thread = 8 channels of one pixel (16-byte loads), 72 accumulators in registers.
+// A block covers min(C/8, 256) channel vectors x ppb pixels per iteration and walks a CONTIGUOUS pixel range, so the x
+// neighbours of the same image row come out of L1.  grid (pixel blocks G, ceil(vecs / 256)); partial [G][9][C].
+constexpr int kDwWgradBlocks = 296;
+__global__ void __launch_bounds__(256) dw_wgrad_vec_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int B, int H, int W,
+                                                           int C, int rate, float* __restrict__ partial) {
+  __shared__ float s_red[256][9];
+  const int vecs = C >> 3;
+  const int vpb = vecs < 256 ? vecs : 256;          // channel vectors per block
+  const int ppb = 256 / vpb;                        // pixels per iteration
+  const int tv = threadIdx.x % vpb, tp = threadIdx.x / vpb;
+  const int vec = blockIdx.y * 256 + tv;
+  const bool active = tp < ppb && vec < vecs;
+  const long long npix = static_cast<long long>(B) * H * W;
+  const long long per_block = (npix + gridDim.x - 1) / gridDim.x;
+  const long long p0 = blockIdx.x * per_block, p1 = min(npix, p0 + per_block);
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[t][k] = 0.f;
+  if (active) {
+    for (long long p = p0 + tp; p < p1; p += ppb) {
+      const int j = static_cast<int>(p % W);
+      const long long r = p / W;
+      const int i = static_cast<int>(r % H);
+      const long long img = (r / H) * H * W;
+      float g[8];
+      unpack8(ldg_nc_v4(dy + p * C + vec * 8), g);
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int ii = i + (u - 1) * rate;
+        if (ii < 0 || ii >= H) continue;
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+          const int jj = j + (v - 1) * rate;
+          if (jj < 0 || jj >= W) continue;
+          float xv[8];
+          unpack8(ldg_nc_v4(x + (img + static_cast<long long>(ii) * W + jj) * C + vec * 8), xv);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[u * 3 + v][k] = fmaf(xv[k], g[k], acc[u * 3 + v][k]);
+        }
+      }
+    }
+  }
+  // reduce the ppb pixel lanes (fixed order), one channel of the vector at a time
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < 9; ++t) s_red[threadIdx.x][t] = acc[t][k];
+    __syncthreads();
+    if (tp == 0 && vec < vecs) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        float s = 0.f;
+        for (int q = 0; q < ppb; ++q) s += s_red[q * vpb + tv][t];
+        partial[(static_cast<size_t>(blockIdx.x) * 9 + t) * C + vec * 8 + k] = s;
+      }
+    }
+  }
+}
+
 
 }  // namespace dlv3p

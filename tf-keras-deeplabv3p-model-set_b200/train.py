@@ -44,7 +44,7 @@ class HeadTrainer:
     def __init__(self, B: int, H: int, W: int, OS: int, Cin: int, Cskip: int, NC: int, weights: Dict[Tuple[str, str], np.ndarray],
                  device: int = 0, lr: float = 1e-2, momentum: float = 0.9, l2: float = L2_COEF, bn_momentum: float = BN_MOMENTUM,
                  eps: float = 1e-5, dropout: float = 0.5, seed: int = 0, ignore_index: int = 255, global_batch: Optional[int] = None,
-                 process_group=None):
+                 process_group=None, graph: bool = True, wgrad_tn: bool = True):
         import torch
         import torch.distributed as dist
         self.torch = torch
@@ -72,6 +72,9 @@ class HeadTrainer:
         self.step_count = 0
         self.launches = 0
         self.debug_taps = None          # set to {} to snapshot intermediate gradients (diagnostics / tests)
+        self.use_graph, self.wgrad_tn = graph, wgrad_tn
+        self._graph = None
+        self._static_in = None
         self._layout_params()
         self._alloc()
         self.set_weights(weights)
@@ -134,6 +137,10 @@ class HeadTrainer:
         self.w_kn = z(self.endA)                 # bf16 copy of region A (Keras [K,N] layout: the dgrad operand)
         self.w_nk = z(self.endA)                 # transposed copies [N,K]: the forward operand
         self.stats = z(self.nstats, dtype=f32)
+        # Dropout seed of the CURRENT step in device memory (int32 bit pattern of dropout_seed(seed, step, rank)); advanced on the device
+        # at the end of every step so that a captured CUDA graph draws a fresh mask per replay
+        s0 = dropout_seed(self.seed, 0, self.rank)
+        self.seed_t = t.tensor([s0 - (1 << 32) if s0 >= (1 << 31) else s0], dtype=t.int32, device=dv)
         self.moving_mean, self.moving_var = z(self.nbn, dtype=f32), t.ones(self.nbn, dtype=f32, device=dv)
         B, Bp, M1, M2, Cin, Cs, NCp = self.B, self.Bp, self.M1, self.M2, self.Cin, self.Cs, self.NCp
         T = {}
@@ -158,9 +165,9 @@ class HeadTrainer:
         T['dfeat'], T['dfeat_tmp'] = z(M1, Cin), z(M1, Cin)
         T['g1_256'] = z(M1, 256)
         T['db4'], T['dr4'], T['dpool'] = z(Bp, 256), z(Bp, 256), z(Bp, Cin)
-        T['featT'] = z(Cin, M1)
-        T['xT'] = z(max(Cin * M1, 304 * M2, 1280 * M1, Cs * M2, Cin * Bp))
-        T['dyT'] = z(max(256 * M2, 256 * M1, 256 * Bp, NCp * M2))
+        if not self.wgrad_tn:
+            T['xT'] = z(max(Cin * M1, 304 * M2, 1280 * M1, Cs * M2, Cin * Bp))
+            T['dyT'] = z(max(256 * M2, 256 * M1, 256 * Bp, NCp * M2))
         self.sms = ffi.device_info(self.dev)['sm_count']
         T['partial'] = z(16 * 1024 * 1024 + self.sms * 2 * 128 * 256, dtype=f32)
         maxC = max(Cin, 304, 256)
@@ -278,20 +285,20 @@ class HeadTrainer:
         _, (K, N) = self.off[(name, 'kernel')]
         self._gemm(dy_ptr, ld_dy, self._wp(self.w_kn, (name, 'kernel')), N, M, K, N, dx_ptr, ldx)
 
-    def _conv_wgrad(self, name, xT_ptr, dy_ptr, M):
-        """dW[K,N] = X^T dY.  xT_ptr: X already transposed [K, M] (row stride M); dY dense [M, N] bf16 is transposed here."""
+    def _conv_wgrad(self, name, x_ptr, ldx, dy_ptr, ld_dy, M):
+        """dW[K,N] = X[M,K]^T dY[M,N]: the MN-major tcgen05 GEMM reads both straight from the [pixels, channels] tensors;
+        the long contraction over pixels is split so that ~one wave of CTAs is busy (fp32 partials, fixed-order reduce)."""
         _, (K, N) = self.off[(name, 'kernel')]
         T = self.T
-        self._call('dlv3p_train_transpose', dy_ptr, M, N, N, self._p(T['dyT']), M)
         tiles = -(-K // 128) * -(-N // (256 if N > 64 else 64))
         kblocks = -(-M // 64)
         splits = max(1, min(kblocks, self.sms // tiles, (T['partial'].numel()) // max(1, K * N)))
-        self._gemm(xT_ptr, M, self._p(T['dyT']), M, K, N, M, self._wp(self.grads, (name, 'kernel')), N, 1, splits)
-
-    def _transpose_x(self, x_ptr, M, K, ld, dst=None) -> int:
-        dst = self._p(self.T['xT']) if dst is None else dst
-        self._call('dlv3p_train_transpose', x_ptr, M, K, ld, dst, M)
-        return dst
+        if self.wgrad_tn:
+            self._call('dlv3p_train_gemm_tn', x_ptr, ldx, dy_ptr, ld_dy, K, N, M, self._wp(self.grads, (name, 'kernel')), N, 1, splits, self._p(T['partial']))
+        else:   # A/B path: explicit transposes + the K-major kernel
+            self._call('dlv3p_train_transpose', x_ptr, M, K, ldx, self._p(T['xT']), M)
+            self._call('dlv3p_train_transpose', dy_ptr, M, N, ld_dy, self._p(T['dyT']), M)
+            self._gemm(self._p(T['xT']), M, self._p(T['dyT']), M, K, N, M, self._wp(self.grads, (name, 'kernel')), N, 1, splits)
 
     def _bn_fwd(self, name, x, M, y_ptr, ldy, relu=1):
         o, Cc = self.stat_off[name]
@@ -327,7 +334,7 @@ class HeadTrainer:
         M = Bn * Hh * Ww
         self._bn_bwd(prefix + '_pointwise_BN', dy_ptr, ld_dy, y_ptr, ld_y, p, M, g_pw)
         self._tap(prefix + '/p', g_pw)
-        self._conv_wgrad(prefix + '_pointwise', self._transpose_x(self._p(a), M, Cc, Cc), self._p(g_pw), M)
+        self._conv_wgrad(prefix + '_pointwise', self._p(a), Cc, self._p(g_pw), 256, M)
         self._conv_dgrad(prefix + '_pointwise', self._p(g_pw), 256, M, self._p(g_a), Cc)
         self._tap(prefix + '/a', g_a)
         self._bn_bwd(prefix + '_depthwise_BN', self._p(g_a), Cc, self._p(a), Cc, d, M, g_d)
@@ -358,9 +365,8 @@ class HeadTrainer:
             self._sep_fwd('aspp%d' % i, feat, B, h, w, Cin, self.rates[i - 1], T['d%d' % i], T['a%d' % i], T['p%d' % i], P(T['concat'], 256 * (i + 1)), 1280)
         self._conv_fwd('concat_projection', P(T['concat']), 1280, M1, P(T['rp']), 256)
         self._bn_fwd('concat_projection_BN', T['rp'], M1, P(T['yproj']), 256)
-        dseed = dropout_seed(self.seed, self.step_count, self.rank)
         if self.drop_rate > 0:
-            self._call('dlv3p_train_dropout', P(T['yproj']), P(T['aspp_out']), M1 * 256, dseed, self.drop_rate)
+            self._call('dlv3p_train_dropout', P(T['yproj']), P(T['aspp_out']), M1 * 256, 0, P(self.seed_t), self.drop_rate)
             aspp_out = T['aspp_out']
         else:
             aspp_out = T['yproj']
@@ -380,7 +386,7 @@ class HeadTrainer:
         # d(bias) = column sums of d(logits): the banded two-stage statistics kernel (sum x | sum x^2 | n), first NCp entries
         self._call('dlv3p_op_bn_stats', P(T['dlow']), M2, NCp, P(T['bias_stats']), P(T['bn_scratch']))
         self.view(self.grads, ('conv_upsample', 'bias')).copy_(T['bias_stats'][:NCp])
-        self._conv_wgrad('conv_upsample', self._transpose_x(P(T['y1']), M2, 256, 256), P(T['dlow']), M2)
+        self._conv_wgrad('conv_upsample', P(T['y1']), 256, P(T['dlow']), NCp, M2)
         self._conv_dgrad('conv_upsample', P(T['dlow']), NCp, M2, P(T['g256a']), 256)
         self._tap('logits', T['dlow'])
         self._tap('decoder_conv1/y', T['g256a'])
@@ -392,20 +398,19 @@ class HeadTrainer:
                       T['g256b'], T['g304a'], T['g304b'], T['g304a'])
         # feature_projection0 (+BN+ReLU): dy = g304b[:, 256:304], y = dcat[:, 256:304]
         self._bn_bwd('feature_projection0_BN', P(T['g304a'], 256), 304, P(T['dcat'], 256), 304, T['rs'], M2, T['drs'])
-        self._conv_wgrad('feature_projection0', self._transpose_x(P(skip), M2, Cs, Cs), P(T['drs']), M2)
+        self._conv_wgrad('feature_projection0', P(skip), Cs, P(T['drs']), 48, M2)
         self._conv_dgrad('feature_projection0', P(T['drs']), 48, M2, P(T['dskip']), Cs)
         # decoder_resize adjoint, Dropout mask
         self._call('dlv3p_train_resize_bwd', P(T['g304a']), 304, B, h, w, 256, hs, ws, P(T['da_out']))
         if self.drop_rate > 0:
-            self._call('dlv3p_train_dropout', P(T['da_out']), P(T['da_out']), M1 * 256, dseed, self.drop_rate)
+            self._call('dlv3p_train_dropout', P(T['da_out']), P(T['da_out']), M1 * 256, 0, P(self.seed_t), self.drop_rate)
         # concat_projection
         self._bn_bwd('concat_projection_BN', P(T['da_out']), 256, P(T['yproj']), 256, T['rp'], M1, T['drp'])
-        self._conv_wgrad('concat_projection', self._transpose_x(P(T['concat']), M1, 1280, 1280), P(T['drp']), M1)
+        self._conv_wgrad('concat_projection', P(T['concat']), 1280, P(T['drp']), 256, M1)
         self._conv_dgrad('concat_projection', P(T['drp']), 256, M1, P(T['dconcat']), 1280)
         # aspp0
-        featT = self._transpose_x(P(feat), M1, Cin, Cin, dst=P(T['featT']))
         self._bn_bwd('aspp0_BN', P(T['dconcat'], 256), 1280, P(T['concat'], 256), 1280, T['r0'], M1, T['g1_256'])
-        self._conv_wgrad('aspp0', featT, P(T['g1_256']), M1)
+        self._conv_wgrad('aspp0', P(feat), Cin, P(T['g1_256']), 256, M1)
         self._conv_dgrad('aspp0', P(T['g1_256']), 256, M1, P(T['dfeat']), Cin)
         # aspp1..3
         for i in (1, 2, 3):
@@ -414,7 +419,7 @@ class HeadTrainer:
         # image pooling branch: column sums per image of d(concat)[:, 0:256] -> BN -> 1x1 -> broadcast / npix
         self._call('dlv3p_train_rows_reduce', P(T['dconcat']), 1280, B, npix1, 256, 1.0, P(T['db4']), 0)
         self._bn_bwd('image_pooling_BN', P(T['db4']), 256, P(T['b4']), 256, T['r4'], B, T['dr4'])
-        self._conv_wgrad('image_pooling', self._transpose_x(P(T['pool']), Bp, Cin, Cin), P(T['dr4']), Bp)
+        self._conv_wgrad('image_pooling', P(T['pool']), Cin, P(T['dr4']), 256, Bp)
         self._conv_dgrad('image_pooling', P(T['dr4']), 256, Bp, P(T['dpool']), Cin)
         self._call('dlv3p_train_bcast_rows', P(T['dpool']), B, npix1, Cin, 1.0 / npix1, P(T['dfeat']), Cin, 1)
 
@@ -444,12 +449,43 @@ class HeadTrainer:
         self.moving_mean.mul_(m).add_(mean, alpha=1 - m)
         self.moving_var.mul_(m).add_(var, alpha=1 - m)
 
-    def train_step(self, feat, skip, labels) -> None:
-        """One optimizer step (fit's train_step): forward, loss, backward, gradient all-reduce, SGD update.  Asynchronous; read
-        the loss with .loss() (synchronises)."""
+    def _advance_seed(self):
+        self.seed_t.add_(0x85EBCA6B - (1 << 32))        # dropout_seed is linear in the step: + 0x85EBCA6B (mod 2^32)
+
+    def _step_body(self, feat, skip, labels):
         self.forward_backward(feat, skip, labels)
         self.all_reduce_gradients()
         self.apply_gradients()
+        self._advance_seed()
+
+    def train_step(self, feat, skip, labels) -> None:
+        """One optimizer step (fit's train_step): forward, loss, backward, gradient all-reduce, SGD update.  Asynchronous; read
+        the loss with .loss() (synchronises).  The first call runs the ~150 kernels one by one; with graph=True the second call
+        captures the whole step (kernels, NCCL all-reduces, the seed increment) into ONE CUDA graph that later calls replay: the
+        step is launch bound otherwise (average kernel 25 us, ~35 us of host work per launch through ctypes).  Inputs are copied
+        into static buffers the graph reads."""
+        t = self.torch
+        if not self.use_graph:
+            self._step_body(feat, skip, labels)
+        elif self.step_count == 0:
+            self._static_in = (t.empty_like(feat), t.empty_like(skip), t.empty_like(labels))
+            for dst, src in zip(self._static_in, (feat, skip, labels)):
+                dst.copy_(src)
+            self._step_body(*self._static_in)
+        else:
+            for dst, src in zip(self._static_in, (feat, skip, labels)):
+                if dst.data_ptr() != src.data_ptr():
+                    dst.copy_(src)
+            if self._graph is None:
+                t.cuda.synchronize(self.tdev)
+                g = t.cuda.CUDAGraph()
+                n0 = self.launches
+                with t.cuda.graph(g):
+                    self._step_body(*self._static_in)
+                self._graph, self.launches_per_step = g, self.launches - n0
+                self.launches = n0
+            self._graph.replay()
+            self.launches += self.launches_per_step
         self.step_count += 1
 
     def loss(self) -> float:

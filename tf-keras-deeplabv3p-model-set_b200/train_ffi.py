@@ -14,6 +14,7 @@ _vp, _i, _i64, _sz, _f, _u32 = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_f
 SYMBOLS = [
     ('dlv3p_train_gemm_partial_bytes', _sz, [_i64, _i, _i]),
     ('dlv3p_train_gemm_nt', _i, [_i, _vp, _i64, _vp, _i64, _i64, _i, _i64, _vp, _i64, _i, _i, _vp, _vp]),
+    ('dlv3p_train_gemm_tn', _i, [_i, _vp, _i64, _vp, _i64, _i64, _i, _i64, _vp, _i64, _i, _i, _vp, _vp]),
     ('dlv3p_train_transpose', _i, [_i, _vp, _i64, _i, _i64, _vp, _i64, _vp]),
     ('dlv3p_train_bn_apply', _i, [_i, _vp, _i64, _i, _vp, _vp, _vp, _f, _i, _vp, _i64, _vp]),
     ('dlv3p_train_scratch_bytes', _sz, [_i]),
@@ -29,7 +30,7 @@ SYMBOLS = [
     ('dlv3p_train_rows_reduce', _i, [_i, _vp, _i64, _i, _i, _i, _f, _vp, _i, _vp]),
     ('dlv3p_train_bcast_rows', _i, [_i, _vp, _i, _i, _i, _f, _vp, _i64, _i, _vp]),
     ('dlv3p_train_add', _i, [_i, _vp, _vp, _vp, _i64, _vp]),
-    ('dlv3p_train_dropout', _i, [_i, _vp, _vp, _i64, _u32, _f, _vp]),
+    ('dlv3p_train_dropout', _i, [_i, _vp, _vp, _i64, _u32, _vp, _f, _vp]),
     ('dlv3p_train_sgd', _i, [_i, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _vp]),
     ('dlv3p_train_cast_bf16', _i, [_i, _vp, _vp, _i64, _vp]),
 ]
