@@ -413,6 +413,14 @@ def test_training_reduces_the_loss(gpu):
 
 
 def _ddp_worker(rank, world, port, q):
+    try:
+        _ddp_worker_body(rank, world, port, q)
+    except Exception as e:                       # the parent must not wait for a result that will never come
+        import traceback
+        q.put((rank, 'ERROR', traceback.format_exc(), str(e), None))
+
+
+def _ddp_worker_body(rank, world, port, q):
     import torch
     import torch.distributed as dist
     from dlv3p_b200 import train
@@ -422,7 +430,7 @@ def _ddp_worker(rank, world, port, q):
     cfg, W, feat, skip, labels = _step_case(B=2 * world, seed=44)
     Bl = cfg.B // world
     sl = slice(rank * Bl, (rank + 1) * Bl)
-    tr = train.HeadTrainer(Bl, cfg.H, cfg.W, cfg.OS, cfg.Cin, cfg.Cskip, cfg.NC, W, device=rank, seed=9)
+    tr = train.HeadTrainer(Bl, cfg.H, cfg.W, cfg.OS, cfg.Cin, cfg.Cskip, cfg.NC, W, device=rank, seed=9, graph=False)
     f = torch.from_numpy(feat[sl]).cuda().to(torch.bfloat16).contiguous()
     s = torch.from_numpy(skip[sl]).cuda().to(torch.bfloat16).contiguous()
     l = torch.from_numpy(labels[sl]).cuda().contiguous()
@@ -446,9 +454,13 @@ def test_data_parallel_step_two_gpus_nccl(gpu):
     ps = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in ps:
         p.start()
-    got = sorted([q.get(timeout=600) for _ in ps], key=lambda t: t[0])
+    got = sorted([q.get(timeout=240) for _ in ps], key=lambda t: t[0])
     for p in ps:
-        p.join(timeout=60)
+        p.join(timeout=30)
+        if p.is_alive():
+            p.terminate()
+    for g in got:
+        assert not (isinstance(g[1], str) and g[1] == 'ERROR'), g[2]
     cfg, W, feat, skip, labels = _step_case(B=4, seed=44)
     n_local = 2 * cfg.h * cfg.w * 256
     keep = np.concatenate([train_ffi.dropout_keep_mask(n_local, train.dropout_seed(9, 0, r), 0.5) for r in range(2)])

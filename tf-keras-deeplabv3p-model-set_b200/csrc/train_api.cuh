@@ -46,6 +46,26 @@ bool encode_2d_sw128_box64(CUtensorMap* tm, const void* base, uint64_t rows, uin
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// band-tiled depthwise kernels: output rows per band R such that (R + 2*rate) rows x W pixels x 64 bytes fit ~96 KB of shared memory
+// (two CTAs per SM); 0 = the map is too wide for a useful band (falls back to the generic kernel)
+constexpr int kDwBandSmem = 96 * 1024;
+int dw_band_rows(int H, int W_, int rate, int* smem_bytes) {
+  const int row_bytes = W_ * 64;
+  const int max_rows = kDwBandSmem / row_bytes;
+  int R;
+  if (max_rows >= H) R = H;                       // the whole map in one band (halo clipped by the borders)
+  else R = max_rows - 2 * rate;
+  if (R < 4 || R * 2 < 2 * rate) return 0;        // halo would dominate
+  int rows = R + 2 * rate;
+  if (rows > H) rows = H;
+  *smem_bytes = rows * row_bytes < 8 * 9 * 32 * 4 ? 8 * 9 * 32 * 4 : rows * row_bytes;
+  return R;
+}
+template <class K>
+cudaError_t ensure_smem(K kernel, int bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
 }  // namespace
 
 extern "C" {
@@ -181,10 +201,21 @@ int dlv3p_train_depthwise(int device, const void* x, int B, int H, int W_, int C
   if (r) return r;
   if (!x || !d_taps || !out || B < 1 || H < 1 || W_ < 1 || C < 8 || C % 8 || rate < 1 || !aligned16(d_taps))
     return fail(nullptr, DLV3P_ERR_INVALID, "train_depthwise: bad arguments (C % 8)");
-  DwParams P{};
-  P.x = static_cast<const __nv_bfloat16*>(x); P.w = d_taps; P.shift = nullptr; P.out = static_cast<__nv_bfloat16*>(out);
-  P.B = B; P.H = H; P.W = W_; P.C = C; P.rate = rate; P.relu = 0; P.wstride = C; P.flip = flip ? 1 : 0;
-  depthwise3x3_kernel<<<grid_for(static_cast<size_t>(B) * H * W_ * (C / 8), sms), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(P);
+  int smem = 0;
+  const int R = dw_band_rows(H, W_, rate, &smem);
+  if (R > 0) {
+    static bool attr_done[64] = {};
+    if (!attr_done[device]) { CU_TRY(nullptr, ensure_smem(dw_band_kernel, kDwBandSmem + 1024)); attr_done[device] = true; }
+    DwBandParams Q{};
+    Q.x = static_cast<const __nv_bfloat16*>(x); Q.w = d_taps; Q.out = static_cast<__nv_bfloat16*>(out);
+    Q.B = B; Q.H = H; Q.W = W_; Q.C = C; Q.rate = rate; Q.flip = flip ? 1 : 0; Q.R = R;
+    dw_band_kernel<<<dim3(ceil_div(H, R), ceil_div(C, 32), B), 256, smem, static_cast<cudaStream_t>(cuda_stream)>>>(Q);
+  } else {
+    DwParams P{};
+    P.x = static_cast<const __nv_bfloat16*>(x); P.w = d_taps; P.shift = nullptr; P.out = static_cast<__nv_bfloat16*>(out);
+    P.B = B; P.H = H; P.W = W_; P.C = C; P.rate = rate; P.relu = 0; P.wstride = C; P.flip = flip ? 1 : 0;
+    depthwise3x3_kernel<<<grid_for(static_cast<size_t>(B) * H * W_ * (C / 8), sms), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(P);
+  }
   CU_TRY(nullptr, cudaGetLastError());
   return DLV3P_OK;
 }
@@ -196,7 +227,18 @@ int dlv3p_train_depthwise_wgrad(int device, const void* x, const void* dy, int B
   if (!x || !dy || !d_dw || !d_scratch || B < 1 || H < 1 || W_ < 1 || C < 2 || C % 2 || rate < 1)
     return fail(nullptr, DLV3P_ERR_INVALID, "train_depthwise_wgrad: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-  if (C % 8 == 0) {
+  int smem = 0;
+  const int R = C % 8 == 0 ? dw_band_rows(H, W_, rate, &smem) : 0;
+  if (R > 0 && static_cast<long long>(B) * ceil_div(H, R) <= kDwWgradBlocks) {
+    static bool attr_done[64] = {};
+    if (!attr_done[device]) { CU_TRY(nullptr, ensure_smem(dw_band_wgrad_kernel, kDwBandSmem + 1024)); attr_done[device] = true; }
+    DwBandParams Q{};
+    Q.x = static_cast<const __nv_bfloat16*>(x); Q.dy = static_cast<const __nv_bfloat16*>(dy); Q.partial = static_cast<float*>(d_scratch);
+    Q.B = B; Q.H = H; Q.W = W_; Q.C = C; Q.rate = rate; Q.R = R;
+    const int bands = ceil_div(H, R);
+    dw_band_wgrad_kernel<<<dim3(bands, ceil_div(C, 32), B), 256, smem, st>>>(Q);
+    bands_final_kernel<<<ceil_div(9 * C, 32), dim3(32, 8), 0, st>>>(static_cast<const float*>(d_scratch), B * bands, 9 * C, d_dw);
+  } else if (C % 8 == 0) {
     const long long npix = static_cast<long long>(B) * H * W_;
     const int G = npix < kDwWgradBlocks ? static_cast<int>(npix) : kDwWgradBlocks;
     dw_wgrad_vec_kernel<<<dim3(G, ceil_div(C / 8, 256)), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), B, H, W_, C, rate,
@@ -261,8 +303,9 @@ int dlv3p_train_softmax_ce(int device, const float* logits, int64_t ldl, const f
   const size_t total = static_cast<size_t>(B) * H * W_;
   int grid = static_cast<int>((total + 255) / 256);
   if (grid > kLossBlocks) grid = kLossBlocks;
-  softmax_ce_kernel<<<grid, 256, 0, st>>>(P);
-  loss_final_kernel<<<1, 32, 0, st>>>(static_cast<const float*>(d_scratch), grid, inv_norm, d_loss);
+  if (NC <= 32) softmax_ce_small_kernel<<<grid, 256, 0, st>>>(P);
+  else softmax_ce_kernel<<<grid, 256, 0, st>>>(P);
+  loss_final_kernel<<<1, 256, 0, st>>>(static_cast<const float*>(d_scratch), grid, inv_norm, d_loss);
   CU_TRY(nullptr, cudaGetLastError());
   return DLV3P_OK;
 }

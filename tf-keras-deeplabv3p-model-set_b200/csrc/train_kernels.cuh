@@ -373,13 +373,88 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const LossParams P) {
     P.block_part[2 * blockIdx.x + 1] = n;
   }
 }
-// out[0] = sum of loss_px * inv_norm (this replica's share of the global mean loss), out[1] = valid pixels
-__global__ void loss_final_kernel(const float* __restrict__ block_part, int nblocks, float inv_norm, float* __restrict__ out) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    double l = 0.0, n = 0.0;
-    for (int i = 0; i < nblocks; ++i) { l += block_part[2 * i]; n += block_part[2 * i + 1]; }
-    out[0] = static_cast<float>(l * inv_norm);
-    out[1] = static_cast<float>(n);
+// out[0] = sum of loss_px * inv_norm (this replica's share of the global mean loss), out[1] = valid pixels.  One block of 256:
+// thread t adds block partials t, t+256, ... in double, then a fixed tree (deterministic).
+__global__ void __launch_bounds__(256) loss_final_kernel(const float* __restrict__ block_part, int nblocks, float inv_norm, float* __restrict__ out) {
+  __shared__ double s_l[256], s_n[256];
+  double l = 0.0, n = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += 256) { l += block_part[2 * i]; n += block_part[2 * i + 1]; }
+  s_l[threadIdx.x] = l; s_n[threadIdx.x] = n;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { s_l[threadIdx.x] += s_l[threadIdx.x + o]; s_n[threadIdx.x] += s_n[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[0] = static_cast<float>(s_l[0] * inv_norm);
+    out[1] = static_cast<float>(s_n[0]);
+  }
+}
+
+// NC <= 32: the interpolated logits of a pixel stay in registers — one interpolation and one exp per class instead of three
+// interpolations and two exps (the generic kernel recomputes them per pass because it cannot index a register array)
+__global__ void __launch_bounds__(256) softmax_ce_small_kernel(const LossParams P) {
+  __shared__ float s_loss[8], s_cnt[8];
+  const long long total = static_cast<long long>(P.B) * P.H * P.W;
+  const long long plane = static_cast<long long>(P.H) * P.W;
+  float loss_acc = 0.f, cnt_acc = 0.f;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int X = static_cast<int>(idx % P.W);
+    long long r = idx / P.W;
+    const int Y = static_cast<int>(r % P.H);
+    const int b = static_cast<int>(r / P.H);
+    int y0, y1, x0, x1;
+    float ty, tx;
+    resize_coord(Y, P.sy, P.hi, y0, y1, ty);
+    resize_coord(X, P.sx, P.wi, x0, x1, tx);
+    const float* base = P.logits + static_cast<long long>(b) * P.hi * P.wi * P.ldl;
+    const float* p00 = base + (static_cast<long long>(y0) * P.wi + x0) * P.ldl;
+    const float* p01 = base + (static_cast<long long>(y0) * P.wi + x1) * P.ldl;
+    const float* p10 = base + (static_cast<long long>(y1) * P.wi + x0) * P.ldl;
+    const float* p11 = base + (static_cast<long long>(y1) * P.wi + x1) * P.ldl;
+    const int label = P.labels[idx];
+    const bool valid = label != P.ignore && label < P.NC;
+    float z[32];
+    float m = -3.0e38f;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      z[c] = c < P.NC ? interp_logit(p00, p01, p10, p11, c, tx, ty, __ldg(P.bias + c)) : -3.0e38f;
+      m = fmaxf(m, z[c]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      z[c] = c < P.NC ? __expf(z[c] - m) : 0.0f;
+      s += z[c];
+    }
+    const float inv_s = 1.0f / s;
+    float pl = 1.0f;
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      if (valid && c == label) pl = z[c] * inv_s;
+    const bool clipped = pl < 1e-7f || pl > 1.0f - 1e-7f;
+    const float gscale = (valid && !clipped) ? P.inv_norm : 0.0f;
+    float* d = P.d_full + static_cast<long long>(b) * P.NC * plane + static_cast<long long>(Y) * P.W + X;
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      if (c < P.NC) d[c * plane] = (z[c] * inv_s - (c == label ? 1.0f : 0.0f)) * gscale;
+    if (valid) {
+      loss_acc -= __logf(fminf(fmaxf(pl, 1e-7f), 1.0f - 1e-7f));
+      cnt_acc += 1.0f;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    loss_acc += __shfl_xor_sync(0xFFFFFFFFu, loss_acc, o);
+    cnt_acc += __shfl_xor_sync(0xFFFFFFFFu, cnt_acc, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s_loss[threadIdx.x >> 5] = loss_acc; s_cnt[threadIdx.x >> 5] = cnt_acc; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float l = 0.f, n = 0.f;
+    for (int w = 0; w < 8; ++w) { l += s_loss[w]; n += s_cnt[w]; }
+    P.block_part[2 * blockIdx.x] = l;
+    P.block_part[2 * blockIdx.x + 1] = n;
   }
 }
 
@@ -632,5 +707,149 @@ __global__ void __launch_bounds__(256) dw_wgrad_vec_kernel(const __nv_bfloat16* 
   }
 }
 
+
+
+// ------------------------------------------------------------------------------------------------ band-tiled depthwise (training)
+// The generic depthwise kernels read every activation nine times through L2 (dilated taps never share a cache line): they are
+// L2-bandwidth bound at ~1 TB/s of useful traffic.  Here a CTA stages ONE band of image rows (+ `rate` halo rows above and
+// below, clipped at the image border) of a 32-channel group in shared memory with cp.async and serves all nine taps from
+// there: x crosses L2 once (plus the halo).  grid (bands, ceil(C/32), B), block 256 = 64 pixel lanes x 4 channel vectors.
+// A whole 32x32 ASPP map is one band (64 KB); the 128-wide decoder maps take 10-row bands.
+struct DwBandParams {
+  const __nv_bfloat16* x;    // [B,H,W,C] input of the convolution (forward: activations; data gradient: dy)
+  const __nv_bfloat16* dy;   // weight gradient only: [B,H,W,C]
+  const float* w;            // [9][C] taps (forward / data gradient)
+  __nv_bfloat16* out;        // [B,H,W,C]
+  float* partial;            // weight gradient: [B * bands][9][C]
+  int B, H, W, C, rate, flip, R;   // R: output rows per band
+};
+__device__ __forceinline__ void cp_async_16(uint32_t smem_addr, const void* gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// stages rows [ylo, yhi) of channel group cg of image b: tile[(row - ylo) * W + px][4 x 16 B]; channels >= C are zero filled
+__device__ __forceinline__ void dw_band_load(const DwBandParams& P, uint8_t* tile, int b, int cg, int ylo, int yhi) {
+  const int chunks = (yhi - ylo) * P.W * 4;
+  const uint32_t tbase = smem_u32(tile);
+  for (int e = threadIdx.x; e < chunks; e += blockDim.x) {
+    const int v = e & 3, pix = e >> 2;
+    const int c = cg * 32 + v * 8;
+    if (c < P.C)
+      cp_async_16(tbase + e * 16, P.x + (static_cast<long long>(b) * P.H * P.W + static_cast<long long>(ylo) * P.W + pix) * P.C + c);
+    else
+      *reinterpret_cast<uint4*>(tile + e * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+}
+__global__ void __launch_bounds__(256) dw_band_kernel(const DwBandParams P) {
+  extern __shared__ __align__(16) uint8_t dw_tile[];
+  const int band = blockIdx.x, cg = blockIdx.y, b = blockIdx.z;
+  const int y0 = band * P.R, y1 = min(P.H, y0 + P.R);
+  const int ylo = max(0, y0 - P.rate), yhi = min(P.H, y1 + P.rate);
+  dw_band_load(P, dw_tile, b, cg, ylo, yhi);
+  const int tv = threadIdx.x & 3;
+  const int c0 = cg * 32 + tv * 8;
+  if (c0 >= P.C) return;
+  float wt[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int tap = P.flip ? 8 - t : t;
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(P.w + tap * P.C + c0));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(P.w + tap * P.C + c0 + 4));
+    wt[t][0] = w0.x; wt[t][1] = w0.y; wt[t][2] = w0.z; wt[t][3] = w0.w; wt[t][4] = w1.x; wt[t][5] = w1.y; wt[t][6] = w1.z; wt[t][7] = w1.w;
+  }
+  const uint32_t tbase = smem_u32(dw_tile);
+  const int npx = (y1 - y0) * P.W;
+  for (int q = threadIdx.x >> 2; q < npx; q += 64) {
+    const int i = y0 + q / P.W, j = q % P.W;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int ii = i + (u - 1) * P.rate;
+      if (ii < 0 || ii >= P.H) continue;
+#pragma unroll
+      for (int v = 0; v < 3; ++v) {
+        const int jj = j + (v - 1) * P.rate;
+        if (jj < 0 || jj >= P.W) continue;
+        float xv[8];
+        unpack8(lds_v4(tbase + (((ii - ylo) * P.W + jj) * 4 + tv) * 16), xv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(xv[k], wt[u * 3 + v][k], acc[k]);
+      }
+    }
+    stg_v4(P.out + ((static_cast<long long>(b) * P.H + i) * P.W + j) * P.C + c0, pack8(acc));
+  }
+}
+// weight gradient on the same tiles: x (with halo) from shared memory, dy straight from global (each element is used once).
+// 72 accumulators per thread; the 64 pixel lanes are reduced by warp shuffles, then across the 8 warps through shared memory.
+__global__ void __launch_bounds__(256) dw_band_wgrad_kernel(const DwBandParams P) {
+  extern __shared__ __align__(16) uint8_t dw_tile[];
+  const int band = blockIdx.x, cg = blockIdx.y, b = blockIdx.z;
+  const int y0 = band * P.R, y1 = min(P.H, y0 + P.R);
+  const int ylo = max(0, y0 - P.rate), yhi = min(P.H, y1 + P.rate);
+  dw_band_load(P, dw_tile, b, cg, ylo, yhi);
+  const int tv = threadIdx.x & 3, lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int c0 = cg * 32 + tv * 8;
+  const bool active = c0 < P.C;
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[t][k] = 0.f;
+  const uint32_t tbase = smem_u32(dw_tile);
+  const int npx = (y1 - y0) * P.W;
+  if (active) {
+    for (int q = threadIdx.x >> 2; q < npx; q += 64) {
+      const int i = y0 + q / P.W, j = q % P.W;
+      float g[8];
+      unpack8(ldg_nc_v4(P.dy + ((static_cast<long long>(b) * P.H + i) * P.W + j) * P.C + c0), g);
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int ii = i + (u - 1) * P.rate;
+        if (ii < 0 || ii >= P.H) continue;
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+          const int jj = j + (v - 1) * P.rate;
+          if (jj < 0 || jj >= P.W) continue;
+          float xv[8];
+          unpack8(lds_v4(tbase + (((ii - ylo) * P.W + jj) * 4 + tv) * 16), xv);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[u * 3 + v][k] = fmaf(xv[k], g[k], acc[u * 3 + v][k]);
+        }
+      }
+    }
+  }
+  // lanes tv, tv+4, ..., tv+28 of a warp hold the same channels: butterfly over lane bits 2..4 (fixed order)
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float v = acc[t][k];
+      v += __shfl_xor_sync(0xFFFFFFFFu, v, 4);
+      v += __shfl_xor_sync(0xFFFFFFFFu, v, 8);
+      v += __shfl_xor_sync(0xFFFFFFFFu, v, 16);
+      acc[t][k] = v;
+    }
+  __syncthreads();                                    // everyone is done with the tile: reuse it as [8 warps][9][32 ch] floats
+  float* s_red = reinterpret_cast<float*>(dw_tile);
+  if (lane < 4) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s_red[(wp * 9 + t) * 32 + lane * 8 + k] = acc[t][k];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 9 * 32; e += 256) {
+    const int t = e >> 5, ch = e & 31;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += s_red[(w * 9 + t) * 32 + ch];
+    const int c = cg * 32 + ch;
+    if (c < P.C) P.partial[(static_cast<size_t>(b * gridDim.x + band) * 9 + t) * P.C + c] = s;
+  }
+}
 
 }  // namespace dlv3p

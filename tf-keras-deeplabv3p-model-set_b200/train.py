@@ -73,6 +73,7 @@ class HeadTrainer:
         self.launches = 0
         self.debug_taps = None          # set to {} to snapshot intermediate gradients (diagnostics / tests)
         self.use_graph, self.wgrad_tn = graph, wgrad_tn
+        self.graph_error_mode = 'global' if self.world == 1 else 'thread_local'   # NCCL's watchdog thread polls events during capture
         self._graph = None
         self._static_in = None
         self._layout_params()
@@ -480,7 +481,7 @@ class HeadTrainer:
                 t.cuda.synchronize(self.tdev)
                 g = t.cuda.CUDAGraph()
                 n0 = self.launches
-                with t.cuda.graph(g):
+                with t.cuda.graph(g, capture_error_mode=self.graph_error_mode):
                     self._step_body(*self._static_in)
                 self._graph, self.launches_per_step = g, self.launches - n0
                 self.launches = n0

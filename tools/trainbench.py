@@ -67,8 +67,14 @@ def main():
                           'unit': 'images/s', 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms / a.steps, 'dtype': 'bf16',
                           'config': {'workload': 'cfg5 Xception OS16 %dx%d head train step, %d img/GPU, global batch %d' % (a.size, a.size, a.batch, a.batch * world)},
                           'gpu_launches_per_step': launches, 'cuda_graph': not a.no_graph, 'wgrad': 'transpose+NT' if a.no_tn else 'TN (MN-major operands)', 'loss': loss, 'phases': phases}))
+    # teardown: drop the captured graph (it holds NCCL kernels) before the process group goes away, and leave without the
+    # collective destructor — destroy_process_group() after a graph capture with NCCL inside has been seen to hang at exit
+    tr._graph = None
+    torch.cuda.synchronize()
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == '__main__':
