@@ -210,6 +210,15 @@ int dlv3p_op_resize_argmax(int device, const float* logits_planar, int B, int NC
 int dlv3p_op_confusion_matrix(int device, const uint8_t* d_pred, const uint8_t* d_gt, int64_t n, int NC,
                               unsigned long long* d_confusion, void* cuda_stream);
 
+/* Image pre / post-processing of the demo and evaluation loops (deeplab.py:81-109, eval.py:403-443), device
+ * pointers, asynchronous on the stream, bit exact against the reference's own numpy / cv2 code (tests/golden/ref_pins.npz):
+ *   normalize_image    common/data_utils.py:403-416  uint8 [n] -> float32(x)/127.5 - 1 as fp32, or as bf16 (out_bf16 = 1: the head's input dtype)
+ *   denormalize_image  common/data_utils.py:419-433  fp32 [n] -> uint8(x*127.5 + 127.5), truncating
+ *   mask_resize        common/data_utils.py:457-477  cv2.resize(mask, (wo, ho), INTER_NEAREST) of B uint8 label maps [hi, wi] -> [ho, wo] */
+int dlv3p_op_normalize_image(int device, const uint8_t* d_img_u8, int64_t n, void* d_out, int out_bf16, void* cuda_stream);
+int dlv3p_op_denormalize_image(int device, const float* d_img_f32, int64_t n, uint8_t* d_out_u8, void* cuda_stream);
+int dlv3p_op_mask_resize_nearest(int device, const uint8_t* d_mask, int B, int hi, int wi, int ho, int wo, uint8_t* d_out, void* cuda_stream);
+
 /* Training-mode batch statistics of CustomBatchNormalization / SyncBatchNormalization (layers.py:63-70) — the SyncBN half of
  * the cfg-5 exchange.  x: device bf16 [M, C] (NHWC as [pixels, channels]).  d_stats: device fp32 [2*C + 1] =
  * sum_x | sum_x2 | row count; with several replicas the caller all-reduces (SUM) d_stats over NCCL (sharding.py), then

@@ -1,6 +1,8 @@
 """GPU parity tests, operator level (several cases exceed 148 tiles so that every persistent CTA loops over more
 than one tile — barrier phase wrap-around, both TMEM accumulator stages): each CUDA kernel through the C ABI vs the oracle on the same seeded
 inputs.  Integer outputs (labels) must be bit exact; bf16 outputs within one bf16 rounding of the fp32 result."""
+import os
+
 import numpy as np
 import pytest
 
@@ -153,3 +155,34 @@ def test_confusion_matrix_equals_the_reference_output(gpu):
     for k in range(4):
         got = ffi.op_confusion_matrix(z['pred_%d' % k], z['gt_%d' % k], int(z['nc_%d' % k]))
         assert np.array_equal(got, z['confusion_%d' % k])
+
+
+# ---------------------------------------------------------------------------------------------------- N4: image pre / post-processing
+@pytest.mark.gpu
+def test_image_pre_post_processing_matches_the_reference_outputs(gpu):
+    """normalize_image / denormalize_image / mask_resize on the device, bit exact against outputs of the reference's OWN functions
+    (tests/golden/ref_pins.npz, generated by executing common/data_utils.py:403-477 — see tests/golden/make_ref_pins.py)."""
+    from dlv3p_b200 import ffi
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_pins.npz'))
+    assert np.array_equal(ffi.op_normalize_image(z['image_u8']), z['normalize'])
+    assert np.array_equal(ffi.op_denormalize_image(z['normalize']), z['denormalize'])
+    assert np.array_equal(ffi.op_mask_resize(z['mask_in'], (27, 36)), z['mask_resize_27x36'])
+    # every uint8 value; bf16 output = round-to-nearest-even of the fp32 result (the head's input dtype)
+    allv = np.arange(256, dtype=np.uint8)
+    ref = allv.astype(np.float32) / 127.5 - 1
+    assert np.array_equal(ffi.op_normalize_image(allv), ref)
+    assert np.array_equal(ffi.op_normalize_image(allv, out_bf16=True), ffi.f32_to_bf16_bits(ref))
+    assert np.array_equal(ffi.op_denormalize_image(ref), (ref * 127.5 + 127.5).astype(np.uint8))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('hi,wi,ho,wo', [(512, 512, 375, 500), (512, 512, 1024, 2048), (128, 96, 13, 7), (5, 7, 500, 333), (1, 1, 9, 9), (64, 64, 64, 64)])
+def test_mask_resize_is_cv2_inter_nearest(gpu, hi, wi, ho, wo):
+    """The reference's mask_resize IS cv2.resize(INTER_NEAREST) (common/data_utils.py:476): compare with cv2 itself, batched."""
+    import cv2
+    from dlv3p_b200 import ffi
+    rng = np.random.default_rng(hi * 7 + wo)
+    masks = rng.integers(0, 21, size=(3, hi, wi)).astype(np.uint8)
+    got = ffi.op_mask_resize(masks, (wo, ho))
+    for b in range(3):
+        assert np.array_equal(got[b], cv2.resize(masks[b], (wo, ho), interpolation=cv2.INTER_NEAREST))

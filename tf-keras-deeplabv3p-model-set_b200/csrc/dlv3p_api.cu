@@ -1732,6 +1732,35 @@ int dlv3p_op_confusion_matrix(int device, const uint8_t* d_pred, const uint8_t* 
   return DLV3P_OK;   // asynchronous; d_confusion is ACCUMULATED (zero it once per evaluation)
 }
 
+// ---- image pre / post-processing of the demo and evaluation loops
+int dlv3p_op_normalize_image(int device, const uint8_t* d_img, int64_t n, void* d_out, int out_bf16, void* cuda_stream) {
+  int sms = 0, r = op_prolog(device, &sms);
+  if (r) return r;
+  if (!d_img || !d_out || n < 1) return fail(nullptr, DLV3P_ERR_INVALID, "op_normalize_image: bad arguments");
+  normalize_image_kernel<<<grid_for(static_cast<size_t>(n), sms), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+      d_img, static_cast<size_t>(n), out_bf16 ? nullptr : static_cast<float*>(d_out), out_bf16 ? static_cast<__nv_bfloat16*>(d_out) : nullptr);
+  CU_TRY(nullptr, cudaGetLastError());
+  return DLV3P_OK;
+}
+int dlv3p_op_denormalize_image(int device, const float* d_img, int64_t n, uint8_t* d_out, void* cuda_stream) {
+  int sms = 0, r = op_prolog(device, &sms);
+  if (r) return r;
+  if (!d_img || !d_out || n < 1) return fail(nullptr, DLV3P_ERR_INVALID, "op_denormalize_image: bad arguments");
+  denormalize_image_kernel<<<grid_for(static_cast<size_t>(n), sms), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(d_img, static_cast<size_t>(n), d_out);
+  CU_TRY(nullptr, cudaGetLastError());
+  return DLV3P_OK;
+}
+int dlv3p_op_mask_resize_nearest(int device, const uint8_t* d_mask, int B, int hi, int wi, int ho, int wo, uint8_t* d_out, void* cuda_stream) {
+  int sms = 0, r = op_prolog(device, &sms);
+  if (r) return r;
+  if (!d_mask || !d_out || B < 1 || hi < 1 || wi < 1 || ho < 1 || wo < 1) return fail(nullptr, DLV3P_ERR_INVALID, "op_mask_resize_nearest: bad arguments");
+  // OpenCV resizeNN: inv_scale = (double)dsize / ssize; ifx = 1. / inv_scale
+  const double ifx = 1.0 / (static_cast<double>(wo) / wi), ify = 1.0 / (static_cast<double>(ho) / hi);
+  mask_resize_nearest_kernel<<<grid_for(static_cast<size_t>(B) * ho * wo, sms), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(d_mask, B, hi, wi, ho, wo, ify, ifx, d_out);
+  CU_TRY(nullptr, cudaGetLastError());
+  return DLV3P_OK;
+}
+
 size_t dlv3p_op_bn_scratch_bytes(int C) {
   const size_t a = static_cast<size_t>(kBnBands) * 2 * (C > 0 ? C : 0), b = col_scratch_floats(C, 2);
   return (a > b ? a : b) * sizeof(float);

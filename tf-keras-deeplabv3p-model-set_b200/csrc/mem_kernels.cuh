@@ -926,4 +926,39 @@ __global__ void __launch_bounds__(256) confusion_matrix_kernel(const ConfusionPa
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ image pre / post-processing (N4)
+// normalize_image (common/data_utils.py:403-416): float32(x) / 127.5 - 1 — an IEEE division and a subtraction, like numpy (no
+// reciprocal multiply, no contraction), so the result is bit identical.  out: fp32, or bf16 (the head's input dtype) when asked.
+__global__ void __launch_bounds__(256) normalize_image_kernel(const uint8_t* __restrict__ in, size_t n, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float v = __fsub_rn(__fdiv_rn(static_cast<float>(in[i]), 127.5f), 1.0f);
+    if (out_f32) out_f32[i] = v;
+    else out_bf16[i] = __float2bfloat16_rn(v);
+  }
+}
+// denormalize_image (:419-433): (x * 127.5 + 127.5).astype(uint8) — separate multiply and add in fp32, truncation toward zero;
+// values outside [0, 256) are clamped (numpy's cast is undefined there)
+__global__ void __launch_bounds__(256) denormalize_image_kernel(const float* __restrict__ in, size_t n, uint8_t* __restrict__ out) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float v = __fadd_rn(__fmul_rn(in[i], 127.5f), 127.5f);
+    out[i] = static_cast<uint8_t>(min(255, max(0, static_cast<int>(v))));
+  }
+}
+// mask_resize (:457-477) = cv2.resize(mask, (wo, ho), interpolation=cv2.INTER_NEAREST): sx = min(floor(x * ifx), wi - 1) with
+// ifx = 1 / (wo / wi) in DOUBLE precision, computed on the host exactly like OpenCV's resizeNN; integer work, bit exact.
+__global__ void __launch_bounds__(256) mask_resize_nearest_kernel(const uint8_t* __restrict__ in, int B, int hi, int wi, int ho, int wo, double ify, double ifx,
+                                                                  uint8_t* __restrict__ out) {
+  const size_t total = static_cast<size_t>(B) * ho * wo;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int X = static_cast<int>(idx % wo);
+    size_t r = idx / wo;
+    const int Y = static_cast<int>(r % ho);
+    const int b = static_cast<int>(r / ho);
+    const int sx = min(static_cast<int>(floor(X * ifx)), wi - 1);
+    const int sy = min(static_cast<int>(floor(Y * ify)), hi - 1);
+    out[idx] = in[(static_cast<size_t>(b) * hi + sy) * wi + sx];
+  }
+}
+
 }  // namespace dlv3p

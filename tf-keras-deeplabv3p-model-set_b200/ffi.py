@@ -74,6 +74,9 @@ SYMBOLS = [
     ('dlv3p_op_resize_argmax', _i, [_i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     ('dlv3p_op_time', _i, [_i, _i, C.POINTER(C.c_int64), _i, _i, _i, _fp]),
     ('dlv3p_op_confusion_matrix', _i, [_i, _vp, _vp, C.c_int64, _i, _vp, _vp]),
+    ('dlv3p_op_normalize_image', _i, [_i, _vp, C.c_int64, _vp, _i, _vp]),
+    ('dlv3p_op_denormalize_image', _i, [_i, _vp, C.c_int64, _vp, _vp]),
+    ('dlv3p_op_mask_resize_nearest', _i, [_i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     ('dlv3p_op_bn_scratch_bytes', C.c_size_t, [_i]),
     ('dlv3p_op_bn_stats', _i, [_i, _vp, C.c_int64, _i, _vp, _vp, _vp]),
     ('dlv3p_op_bn_apply', _i, [_i, _vp, C.c_int64, _i, _vp, _vp, _vp, C.c_float, _i, _vp, _vp]),
@@ -366,6 +369,39 @@ def op_confusion_matrix(pred: np.ndarray, gt: np.ndarray, num_classes: int, devi
         _check(load_library().dlv3p_op_confusion_matrix(device, dp.ptr, dg.ptr, p.size, num_classes, dc.ptr, None))
     synchronize(device)
     return dc.download((num_classes, num_classes), np.uint64).astype(np.int64)
+
+
+def op_normalize_image(image_u8: np.ndarray, out_bf16: bool = False, device=0) -> np.ndarray:
+    """normalize_image (common/data_utils.py:403-416) on the device: uint8 -> float32 x/127.5 - 1 (or bf16 bit patterns as uint16)."""
+    a = np.ascontiguousarray(image_u8, np.uint8)
+    din = DeviceBuffer.from_numpy(a.reshape(-1), device)
+    dout = DeviceBuffer(a.size * (2 if out_bf16 else 4), device)
+    _check(load_library().dlv3p_op_normalize_image(device, din.ptr, a.size, dout.ptr, int(out_bf16), None))
+    synchronize(device)
+    return dout.download(a.shape, np.uint16 if out_bf16 else np.float32)
+
+
+def op_denormalize_image(image_f32: np.ndarray, device=0) -> np.ndarray:
+    """denormalize_image (common/data_utils.py:419-433) on the device: float32 -> uint8."""
+    a = np.ascontiguousarray(image_f32, np.float32)
+    din = DeviceBuffer.from_numpy(a.reshape(-1), device)
+    dout = DeviceBuffer(a.size, device)
+    _check(load_library().dlv3p_op_denormalize_image(device, din.ptr, a.size, dout.ptr, None))
+    synchronize(device)
+    return dout.download(a.shape, np.uint8)
+
+
+def op_mask_resize(mask: np.ndarray, target_size: Tuple[int, int], device=0) -> np.ndarray:
+    """mask_resize (common/data_utils.py:457-477): cv2 INTER_NEAREST resize of uint8 label maps [..., hi, wi] to target_size = (width, height)."""
+    a = np.ascontiguousarray(mask, np.uint8)
+    hi, wi = a.shape[-2:]
+    wo, ho = int(target_size[0]), int(target_size[1])
+    B = a.size // (hi * wi)
+    din = DeviceBuffer.from_numpy(a.reshape(-1), device)
+    dout = DeviceBuffer(B * ho * wo, device)
+    _check(load_library().dlv3p_op_mask_resize_nearest(device, din.ptr, B, hi, wi, ho, wo, dout.ptr, None))
+    synchronize(device)
+    return dout.download(a.shape[:-2] + (ho, wo), np.uint8)
 
 
 def bn_stats(x_ptr: int, M: int, Cc: int, stats_ptr: int, scratch_ptr: int, stream=None, device=0) -> None:

@@ -99,6 +99,15 @@ class HeadTrainer:
                 ('decoder_conv0_depthwise_BN', 304), ('decoder_conv0_pointwise_BN', 256), ('decoder_conv1_depthwise_BN', 256),
                 ('decoder_conv1_pointwise_BN', 256)]
 
+    # BN layers grouped by data dependence (one all-reduce per group)
+    FWD_GROUPS = [['image_pooling_BN', 'aspp0_BN', 'aspp1_depthwise_BN', 'aspp2_depthwise_BN', 'aspp3_depthwise_BN', 'feature_projection0_BN'],
+                  ['aspp1_pointwise_BN', 'aspp2_pointwise_BN', 'aspp3_pointwise_BN'], ['concat_projection_BN'],
+                  ['decoder_conv0_depthwise_BN'], ['decoder_conv0_pointwise_BN'], ['decoder_conv1_depthwise_BN'], ['decoder_conv1_pointwise_BN']]
+    BWD_GROUPS = [['decoder_conv1_pointwise_BN'], ['decoder_conv1_depthwise_BN'], ['decoder_conv0_pointwise_BN'], ['decoder_conv0_depthwise_BN'],
+                  ['feature_projection0_BN', 'concat_projection_BN'],
+                  ['aspp0_BN', 'aspp1_pointwise_BN', 'aspp2_pointwise_BN', 'aspp3_pointwise_BN', 'image_pooling_BN'],
+                  ['aspp1_depthwise_BN', 'aspp2_depthwise_BN', 'aspp3_depthwise_BN']]
+
     def _layout_params(self):
         """Flat fp32 layout: [A: 1x1 kernels [K,N] + classifier bias (l2-regularised)] [B: depthwise taps [9,C]]
         [C: per BN layer beta | gamma].  A and B are all-reduced; C's gradients come out of the SyncBN backward exchange
@@ -115,17 +124,21 @@ class HeadTrainer:
             self.off[(name, 'depthwise_kernel')] = (off, (9, Cc))
             off = _rup(off + 9 * Cc, 8)
         self.endB = off
-        for name, Cc in self._bn_specs():
+        # BN parameters / gradients in the order the BACKWARD pass meets the layers, and forward statistics in the order the
+        # FORWARD pass does: BN layers whose inputs are independent sit next to each other and share ONE all-reduce of their
+        # SyncBN vectors (14 collectives per step instead of 28)
+        chan = dict(self._bn_specs())
+        for name in [n for grp in self.BWD_GROUPS for n in grp]:
+            Cc = chan[name]
             self.off[(name, 'beta')] = (off, (Cc,))
             self.off[(name, 'gamma')] = (off + Cc, (Cc,))
             off = _rup(off + 2 * Cc, 8)
         self.nparams = off
-        # forward statistics: per BN layer [sum x | sum x^2 | n], 4-float aligned
         soff = 0
         self.stat_off: Dict[str, Tuple[int, int]] = {}
-        for name, Cc in self._bn_specs():
-            self.stat_off[name] = (soff, Cc)
-            soff = _rup(soff + 2 * Cc + 1, 4)
+        for name in [n for grp in self.FWD_GROUPS for n in grp]:
+            self.stat_off[name] = (soff, chan[name])
+            soff = _rup(soff + 2 * chan[name] + 1, 4)
         self.nstats = soff
         self.nbn = sum(c for _, c in self._bn_specs())
 
@@ -162,7 +175,9 @@ class HeadTrainer:
         T['g304a'], T['g304b'] = z(M2, 304), z(M2, 304)
         T['drs'], T['dskip'] = z(M2, 48), z(M2, Cs)
         T['da_out'], T['drp'], T['dconcat'] = z(M1, 256), z(M1, 256), z(M1, 1280)
-        T['gA'], T['gB'] = z(M1, Cin), z(M1, Cin)
+        T['gB'] = z(M1, Cin)
+        for i in (1, 2, 3):
+            T['gp%d' % i], T['ga%d' % i] = z(M1, 256), z(M1, Cin)
         T['dfeat'], T['dfeat_tmp'] = z(M1, Cin), z(M1, Cin)
         T['g1_256'] = z(M1, 256)
         T['db4'], T['dr4'], T['dpool'] = z(Bp, 256), z(Bp, 256), z(Bp, Cin)
@@ -301,22 +316,47 @@ class HeadTrainer:
             self._call('dlv3p_train_transpose', dy_ptr, M, N, ld_dy, self._p(T['dyT']), M)
             self._gemm(self._p(T['xT']), M, self._p(T['dyT']), M, K, N, M, self._wp(self.grads, (name, 'kernel')), N, 1, splits)
 
-    def _bn_fwd(self, name, x, M, y_ptr, ldy, relu=1):
+    def _bn_stats(self, name, x, M):
         o, Cc = self.stat_off[name]
-        st = self.stats[o:o + 2 * Cc + 1]
         self._call('dlv3p_op_bn_stats', self._p(x), M, Cc, self._p(self.stats, o), self._p(self.T['bn_scratch']))
-        self._allreduce(st)
+
+    def _sync_stats(self, group):
+        """ONE all-reduce (SUM) of the contiguous [sum x | sum x^2 | n] vectors of a group of independent BN layers."""
+        o0 = self.stat_off[group[0]][0]
+        o1, c1 = self.stat_off[group[-1]]
+        self._allreduce(self.stats[o0:o1 + 2 * c1 + 1])
+
+    def _bn_apply(self, name, x, M, y_ptr, ldy, relu=1):
+        o, Cc = self.stat_off[name]
         self._call('dlv3p_train_bn_apply', self._p(x), M, Cc, self._p(self.stats, o), self._wp(self.params, (name, 'gamma')),
                    self._wp(self.params, (name, 'beta')), self.eps, relu, y_ptr, ldy)
 
-    def _bn_bwd(self, name, dy_ptr, ld_dy, y_ptr, ld_y, x, M, dx, relu=1):
+    def _bn_fwd(self, name, x, M, y_ptr, ldy, relu=1):
+        self._bn_stats(name, x, M)
+        self._sync_stats([name])
+        self._bn_apply(name, x, M, y_ptr, ldy, relu)
+
+    def _bn_bwd_stats(self, name, dy_ptr, ld_dy, y_ptr, ld_y, x, M, relu=1):
         o, Cc = self.stat_off[name]
         go = self.off[(name, 'beta')][0]                      # grads[go : go+2C] = d(beta) | d(gamma) = sum g | sum g*xhat
         self._call('dlv3p_train_bn_bwd_stats', dy_ptr, ld_dy, y_ptr, ld_y, self._p(x), M, Cc, self._p(self.stats, o), self.eps, relu,
                    self._p(self.grads, go), self._p(self.T['scratch']))
-        self._allreduce(self.grads[go:go + 2 * Cc])
+
+    def _sync_bn_grads(self, group):
+        g0 = self.off[(group[0], 'beta')][0]
+        g1, (c1,) = self.off[(group[-1], 'beta')]
+        self._allreduce(self.grads[g0:g1 + 2 * c1])
+
+    def _bn_bwd_apply(self, name, dy_ptr, ld_dy, y_ptr, ld_y, x, M, dx, relu=1):
+        o, Cc = self.stat_off[name]
+        go = self.off[(name, 'beta')][0]
         self._call('dlv3p_train_bn_bwd_apply', dy_ptr, ld_dy, y_ptr, ld_y, self._p(x), M, Cc, self._p(self.stats, o), self._p(self.grads, go),
                    self._wp(self.params, (name, 'gamma')), self.eps, relu, self._p(dx))
+
+    def _bn_bwd(self, name, dy_ptr, ld_dy, y_ptr, ld_y, x, M, dx, relu=1):
+        self._bn_bwd_stats(name, dy_ptr, ld_dy, y_ptr, ld_y, x, M, relu)
+        self._sync_bn_grads([name])
+        self._bn_bwd_apply(name, dy_ptr, ld_dy, y_ptr, ld_y, x, M, dx, relu)
 
     def _sep_fwd(self, prefix, x, Bn, Hh, Ww, Cc, rate, d, a, p, y_ptr, ldy):
         """SepConv_BN (depth_activation=True, layers.py:98-109) in training mode; keeps d (raw depthwise), a (BN+ReLU), p (raw pointwise)."""
@@ -355,15 +395,33 @@ class HeadTrainer:
         h, w, hs, ws = self.h, self.w, self.hs, self.ws
         npix1 = h * w
         assert feat.is_contiguous() and skip.is_contiguous() and labels.is_contiguous()
-        # ---------------- ASPP_block (layers.py:114-163)
+        # ---------------- ASPP_block (layers.py:114-163) + the decoder's skip projection (:209-213), phase by phase:
+        # phase 1: everything that depends only on the inputs — raw outputs, their statistics, ONE exchange, then the six BN+ReLU
         self._call('dlv3p_train_rows_reduce', P(feat), Cin, B, npix1, Cin, 1.0 / npix1, P(T['pool']), 0)
         self._conv_fwd('image_pooling', P(T['pool']), Cin, Bp, P(T['r4']), 256)
-        self._bn_fwd('image_pooling_BN', T['r4'], B, P(T['b4']), 256)
-        self._call('dlv3p_train_bcast_rows', P(T['b4']), B, npix1, 256, 1.0, P(T['concat']), 1280, 0)
+        self._bn_stats('image_pooling_BN', T['r4'], B)
         self._conv_fwd('aspp0', P(feat), Cin, M1, P(T['r0']), 256)
-        self._bn_fwd('aspp0_BN', T['r0'], M1, P(T['concat'], 256), 1280)
+        self._bn_stats('aspp0_BN', T['r0'], M1)
         for i in (1, 2, 3):
-            self._sep_fwd('aspp%d' % i, feat, B, h, w, Cin, self.rates[i - 1], T['d%d' % i], T['a%d' % i], T['p%d' % i], P(T['concat'], 256 * (i + 1)), 1280)
+            self._call('dlv3p_train_depthwise', P(feat), B, h, w, Cin, self.rates[i - 1], self._wp(self.params, ('aspp%d_depthwise' % i, 'depthwise_kernel')), 0,
+                       P(T['d%d' % i]))
+            self._bn_stats('aspp%d_depthwise_BN' % i, T['d%d' % i], M1)
+        self._conv_fwd('feature_projection0', P(skip), Cs, M2, P(T['rs']), 48)
+        self._bn_stats('feature_projection0_BN', T['rs'], M2)
+        self._sync_stats(self.FWD_GROUPS[0])
+        self._bn_apply('image_pooling_BN', T['r4'], B, P(T['b4']), 256)
+        self._call('dlv3p_train_bcast_rows', P(T['b4']), B, npix1, 256, 1.0, P(T['concat']), 1280, 0)
+        self._bn_apply('aspp0_BN', T['r0'], M1, P(T['concat'], 256), 1280)
+        for i in (1, 2, 3):
+            self._bn_apply('aspp%d_depthwise_BN' % i, T['d%d' % i], M1, P(T['a%d' % i]), Cin)
+        self._bn_apply('feature_projection0_BN', T['rs'], M2, P(T['dcat'], 256), 304)
+        # phase 2: the three atrous pointwise convs
+        for i in (1, 2, 3):
+            self._conv_fwd('aspp%d_pointwise' % i, P(T['a%d' % i]), Cin, M1, P(T['p%d' % i]), 256)
+            self._bn_stats('aspp%d_pointwise_BN' % i, T['p%d' % i], M1)
+        self._sync_stats(self.FWD_GROUPS[1])
+        for i in (1, 2, 3):
+            self._bn_apply('aspp%d_pointwise_BN' % i, T['p%d' % i], M1, P(T['concat'], 256 * (i + 1)), 1280)
         self._conv_fwd('concat_projection', P(T['concat']), 1280, M1, P(T['rp']), 256)
         self._bn_fwd('concat_projection_BN', T['rp'], M1, P(T['yproj']), 256)
         if self.drop_rate > 0:
@@ -373,8 +431,6 @@ class HeadTrainer:
             aspp_out = T['yproj']
         # ---------------- Decoder_block (layers.py:199-219)
         self._call('dlv3p_train_resize', P(aspp_out), B, h, w, 256, hs, ws, P(T['dcat']), 304)
-        self._conv_fwd('feature_projection0', P(skip), Cs, M2, P(T['rs']), 48)
-        self._bn_fwd('feature_projection0_BN', T['rs'], M2, P(T['dcat'], 256), 304)
         self._sep_fwd('decoder_conv0', T['dcat'], B, hs, ws, 304, 1, T['c0d'], T['c0a'], T['c0p'], P(T['y0']), 256)
         self._sep_fwd('decoder_conv1', T['y0'], B, hs, ws, 256, 1, T['c1d'], T['c1a'], T['c1p'], P(T['y1']), 256)
         # ---------------- tail + loss (model.py:75-86, loss.py:121-156)
@@ -397,37 +453,54 @@ class HeadTrainer:
         # decoder_conv0: dy = g256a, x = dcat (304 channels); dx overwrites g304a
         self._sep_bwd('decoder_conv0', T['dcat'], B, hs, ws, 304, 1, T['c0d'], T['c0a'], T['c0p'], P(T['y0']), 256, P(T['g256a']), 256,
                       T['g256b'], T['g304a'], T['g304b'], T['g304a'])
-        # feature_projection0 (+BN+ReLU): dy = g304b[:, 256:304], y = dcat[:, 256:304]
-        self._bn_bwd('feature_projection0_BN', P(T['g304a'], 256), 304, P(T['dcat'], 256), 304, T['rs'], M2, T['drs'])
-        self._conv_wgrad('feature_projection0', P(skip), Cs, P(T['drs']), 48, M2)
-        self._conv_dgrad('feature_projection0', P(T['drs']), 48, M2, P(T['dskip']), Cs)
-        # decoder_resize adjoint, Dropout mask
+        # decoder_resize adjoint and the Dropout mask give d(loss)/d(concat_projection output); together with the skip projection
+        # (dy = g304a[:, 256:304]) that is one group of two independent BN backwards: statistics, ONE exchange, then both applies
         self._call('dlv3p_train_resize_bwd', P(T['g304a']), 304, B, h, w, 256, hs, ws, P(T['da_out']))
         if self.drop_rate > 0:
             self._call('dlv3p_train_dropout', P(T['da_out']), P(T['da_out']), M1 * 256, 0, P(self.seed_t), self.drop_rate)
-        # concat_projection
-        self._bn_bwd('concat_projection_BN', P(T['da_out']), 256, P(T['yproj']), 256, T['rp'], M1, T['drp'])
+        self._bn_bwd_stats('feature_projection0_BN', P(T['g304a'], 256), 304, P(T['dcat'], 256), 304, T['rs'], M2)
+        self._bn_bwd_stats('concat_projection_BN', P(T['da_out']), 256, P(T['yproj']), 256, T['rp'], M1)
+        self._sync_bn_grads(self.BWD_GROUPS[4])
+        self._bn_bwd_apply('feature_projection0_BN', P(T['g304a'], 256), 304, P(T['dcat'], 256), 304, T['rs'], M2, T['drs'])
+        self._bn_bwd_apply('concat_projection_BN', P(T['da_out']), 256, P(T['yproj']), 256, T['rp'], M1, T['drp'])
+        self._conv_wgrad('feature_projection0', P(skip), Cs, P(T['drs']), 48, M2)
+        self._conv_dgrad('feature_projection0', P(T['drs']), 48, M2, P(T['dskip']), Cs)
         self._conv_wgrad('concat_projection', P(T['concat']), 1280, P(T['drp']), 256, M1)
         self._conv_dgrad('concat_projection', P(T['drp']), 256, M1, P(T['dconcat']), 1280)
-        # aspp0
-        self._bn_bwd('aspp0_BN', P(T['dconcat'], 256), 1280, P(T['concat'], 256), 1280, T['r0'], M1, T['g1_256'])
+        # the five BN layers that feed the concat: aspp0, the three atrous pointwise convs, the image pooling branch
+        self._call('dlv3p_train_rows_reduce', P(T['dconcat']), 1280, B, npix1, 256, 1.0, P(T['db4']), 0)
+        names = ['aspp0_BN', 'aspp1_pointwise_BN', 'aspp2_pointwise_BN', 'aspp3_pointwise_BN']
+        raws = [T['r0'], T['p1'], T['p2'], T['p3']]
+        gout = [T['g1_256'], T['gp1'], T['gp2'], T['gp3']]
+        for k, (name, raw) in enumerate(zip(names, raws)):
+            self._bn_bwd_stats(name, P(T['dconcat'], 256 * (k + 1)), 1280, P(T['concat'], 256 * (k + 1)), 1280, raw, M1)
+        self._bn_bwd_stats('image_pooling_BN', P(T['db4']), 256, P(T['b4']), 256, T['r4'], B)
+        self._sync_bn_grads(self.BWD_GROUPS[5])
+        for k, (name, raw, g) in enumerate(zip(names, raws, gout)):
+            self._bn_bwd_apply(name, P(T['dconcat'], 256 * (k + 1)), 1280, P(T['concat'], 256 * (k + 1)), 1280, raw, M1, g)
+        self._bn_bwd_apply('image_pooling_BN', P(T['db4']), 256, P(T['b4']), 256, T['r4'], B, T['dr4'])
+        # aspp0 and the image pooling branch end here
         self._conv_wgrad('aspp0', P(feat), Cin, P(T['g1_256']), 256, M1)
         self._conv_dgrad('aspp0', P(T['g1_256']), 256, M1, P(T['dfeat']), Cin)
-        # aspp1..3
-        for i in (1, 2, 3):
-            self._aspp_branch_bwd(i, feat)
-            self._call('dlv3p_train_add', P(T['dfeat']), P(T['dfeat_tmp']), P(T['dfeat']), M1 * Cin)
-        # image pooling branch: column sums per image of d(concat)[:, 0:256] -> BN -> 1x1 -> broadcast / npix
-        self._call('dlv3p_train_rows_reduce', P(T['dconcat']), 1280, B, npix1, 256, 1.0, P(T['db4']), 0)
-        self._bn_bwd('image_pooling_BN', P(T['db4']), 256, P(T['b4']), 256, T['r4'], B, T['dr4'])
         self._conv_wgrad('image_pooling', P(T['pool']), Cin, P(T['dr4']), 256, Bp)
         self._conv_dgrad('image_pooling', P(T['dr4']), 256, Bp, P(T['dpool']), Cin)
         self._call('dlv3p_train_bcast_rows', P(T['dpool']), B, npix1, Cin, 1.0 / npix1, P(T['dfeat']), Cin, 1)
-
-    def _aspp_branch_bwd(self, i, feat):
-        T = self.T
-        self._sep_bwd('aspp%d' % i, feat, self.B, self.h, self.w, self.Cin, self.rates[i - 1], T['d%d' % i], T['a%d' % i], T['p%d' % i],
-                      self._p(T['concat'], 256 * (i + 1)), 1280, self._p(T['dconcat'], 256 * (i + 1)), 1280, T['g1_256'], T['gA'], T['gB'], T['dfeat_tmp'])
+        # atrous branches: pointwise gradients, then the three depthwise BN backwards as one group
+        for i in (1, 2, 3):
+            self._tap('aspp%d/p' % i, T['gp%d' % i])
+            self._conv_wgrad('aspp%d_pointwise' % i, P(T['a%d' % i]), Cin, P(T['gp%d' % i]), 256, M1)
+            self._conv_dgrad('aspp%d_pointwise' % i, P(T['gp%d' % i]), 256, M1, P(T['ga%d' % i]), Cin)
+            self._tap('aspp%d/a' % i, T['ga%d' % i])
+            self._bn_bwd_stats('aspp%d_depthwise_BN' % i, P(T['ga%d' % i]), Cin, P(T['a%d' % i]), Cin, T['d%d' % i], M1)
+        self._sync_bn_grads(self.BWD_GROUPS[6])
+        for i in (1, 2, 3):
+            name = 'aspp%d_depthwise' % i
+            self._bn_bwd_apply(name + '_BN', P(T['ga%d' % i]), Cin, P(T['a%d' % i]), Cin, T['d%d' % i], M1, T['gB'])
+            self._tap('aspp%d/d' % i, T['gB'])
+            self._call('dlv3p_train_depthwise_wgrad', P(feat), P(T['gB']), B, h, w, Cin, self.rates[i - 1], self._wp(self.grads, (name, 'depthwise_kernel')),
+                       P(T['scratch']))
+            self._call('dlv3p_train_depthwise', P(T['gB']), B, h, w, Cin, self.rates[i - 1], self._wp(self.params, (name, 'depthwise_kernel')), 1, P(T['dfeat_tmp']))
+            self._call('dlv3p_train_add', P(T['dfeat']), P(T['dfeat_tmp']), P(T['dfeat']), M1 * Cin)
 
     def all_reduce_gradients(self):
         """ONE all-reduce (SUM) of the flat fp32 bucket holding every 1x1 kernel, the classifier bias and every depthwise kernel
