@@ -37,48 +37,29 @@ def dropout_seed(base_seed: int, step: int, rank: int) -> int:
     return (base_seed * 0x9E3779B1 + step * 0x85EBCA6B + rank * 0xC2B2AE35 + 0x27D4EB2F) & 0xFFFFFFFF
 
 
-class HeadTrainer:
-    """One replica of the data-parallel training step.  All tensors live on `device`; feed bf16 NHWC features and uint8
-    labels already resident in HBM (the backbone is outside this path; d_feat / d_skip are returned for it)."""
+class TrainLayout:
+    """Host-side layout of the training state (no CUDA needed): where every parameter / gradient lives in the flat fp32 buffers, where
+    every BN layer's SyncBN vector lives, and which contiguous spans each collective of the step exchanges.  The world_size-2 gloo
+    test on CPU (tests/test_dist_cpu.py) drives exactly these spans."""
 
-    def __init__(self, B: int, H: int, W: int, OS: int, Cin: int, Cskip: int, NC: int, weights: Dict[Tuple[str, str], np.ndarray],
-                 device: int = 0, lr: float = 1e-2, momentum: float = 0.9, l2: float = L2_COEF, bn_momentum: float = BN_MOMENTUM,
-                 eps: float = 1e-5, dropout: float = 0.5, seed: int = 0, ignore_index: int = 255, global_batch: Optional[int] = None,
-                 process_group=None, graph: bool = True, wgrad_tn: bool = True):
-        import torch
-        import torch.distributed as dist
-        self.torch = torch
-        if not torch.cuda.is_available():
-            raise ffi.Dlv3pError(-2, 'HeadTrainer needs a CUDA device: there is no CPU path')
-        tf_.lib()
-        self.B, self.H, self.W, self.OS, self.Cin, self.Cs, self.NC = B, H, W, OS, Cin, Cskip, NC
-        self.rates = atrous_rates(OS)
-        self.h, self.w = -(-H // OS), -(-W // OS)
-        self.hs, self.ws = -(-H // 4), -(-W // 4)
-        self.M1, self.M2 = B * self.h * self.w, B * self.hs * self.ws
-        if Cin % 8 or Cskip % 8 or self.M1 % 8 or self.M2 % 8:
-            raise ffi.Dlv3pError(-1, 'HeadTrainer: Cin, Cskip and the pixel counts per replica must be multiples of 8')
+    def __init__(self, Cin: int, Cskip: int, NC: int):
+        self.Cin, self.Cs, self.NC = Cin, Cskip, NC
         self.NCp = _rup(NC, 8)
-        self.Bp = _rup(B, 8)
-        self.dev = device
-        self.tdev = torch.device('cuda', device)
-        self.lr, self.momentum, self.l2, self.bn_momentum, self.eps = lr, momentum, l2, bn_momentum, eps
-        self.drop_rate, self.seed, self.ignore = dropout, seed, ignore_index
-        self.pg = process_group
-        self.dist = dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1) else None
-        self.world = dist.get_world_size(process_group) if self.dist else 1
-        self.rank = dist.get_rank(process_group) if self.dist else 0
-        self.global_batch = global_batch if global_batch is not None else B * self.world
-        self.step_count = 0
-        self.launches = 0
-        self.debug_taps = None          # set to {} to snapshot intermediate gradients (diagnostics / tests)
-        self.use_graph, self.wgrad_tn = graph, wgrad_tn
-        self.graph_error_mode = 'global' if self.world == 1 else 'thread_local'   # NCCL's watchdog thread polls events during capture
-        self._graph = None
-        self._static_in = None
         self._layout_params()
-        self._alloc()
-        self.set_weights(weights)
+
+    def stats_span(self, group) -> Tuple[int, int]:
+        """[begin, end) in the forward-statistics buffer of one group of independent BN layers: ONE all-reduce."""
+        o1, c1 = self.stat_off[group[-1]]
+        return self.stat_off[group[0]][0], o1 + 2 * c1 + 1
+
+    def bn_grad_span(self, group) -> Tuple[int, int]:
+        """[begin, end) in the gradient buffer of the d(beta) | d(gamma) vectors of one backward group: ONE all-reduce."""
+        g1, (c1,) = self.off[(group[-1], 'beta')]
+        return self.off[(group[0], 'beta')][0], g1 + 2 * c1
+
+    def bucket_span(self) -> Tuple[int, int]:
+        """[begin, end) of the gradient bucket all-reduced once per step (1x1 kernels, classifier bias, depthwise kernels)."""
+        return 0, self.endB
 
     # ------------------------------------------------------------------------------------------------ parameters
     def _conv_specs(self):
@@ -141,6 +122,49 @@ class HeadTrainer:
             soff = _rup(soff + 2 * chan[name] + 1, 4)
         self.nstats = soff
         self.nbn = sum(c for _, c in self._bn_specs())
+
+
+class HeadTrainer(TrainLayout):
+    """One replica of the data-parallel training step.  All tensors live on `device`; feed bf16 NHWC features and uint8
+    labels already resident in HBM (the backbone is outside this path; d_feat / d_skip are returned for it)."""
+
+    def __init__(self, B: int, H: int, W: int, OS: int, Cin: int, Cskip: int, NC: int, weights: Dict[Tuple[str, str], np.ndarray],
+                 device: int = 0, lr: float = 1e-2, momentum: float = 0.9, l2: float = L2_COEF, bn_momentum: float = BN_MOMENTUM,
+                 eps: float = 1e-5, dropout: float = 0.5, seed: int = 0, ignore_index: int = 255, global_batch: Optional[int] = None,
+                 process_group=None, graph: bool = True, wgrad_tn: bool = True):
+        import torch
+        import torch.distributed as dist
+        self.torch = torch
+        if not torch.cuda.is_available():
+            raise ffi.Dlv3pError(-2, 'HeadTrainer needs a CUDA device: there is no CPU path')
+        tf_.lib()
+        self.B, self.H, self.W, self.OS, self.Cin, self.Cs, self.NC = B, H, W, OS, Cin, Cskip, NC
+        self.rates = atrous_rates(OS)
+        self.h, self.w = -(-H // OS), -(-W // OS)
+        self.hs, self.ws = -(-H // 4), -(-W // 4)
+        self.M1, self.M2 = B * self.h * self.w, B * self.hs * self.ws
+        if Cin % 8 or Cskip % 8 or self.M1 % 8 or self.M2 % 8:
+            raise ffi.Dlv3pError(-1, 'HeadTrainer: Cin, Cskip and the pixel counts per replica must be multiples of 8')
+        TrainLayout.__init__(self, Cin, Cskip, NC)
+        self.Bp = _rup(B, 8)
+        self.dev = device
+        self.tdev = torch.device('cuda', device)
+        self.lr, self.momentum, self.l2, self.bn_momentum, self.eps = lr, momentum, l2, bn_momentum, eps
+        self.drop_rate, self.seed, self.ignore = dropout, seed, ignore_index
+        self.pg = process_group
+        self.dist = dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1) else None
+        self.world = dist.get_world_size(process_group) if self.dist else 1
+        self.rank = dist.get_rank(process_group) if self.dist else 0
+        self.global_batch = global_batch if global_batch is not None else B * self.world
+        self.step_count = 0
+        self.launches = 0
+        self.debug_taps = None          # set to {} to snapshot intermediate gradients (diagnostics / tests)
+        self.use_graph, self.wgrad_tn = graph, wgrad_tn
+        self.graph_error_mode = 'global' if self.world == 1 else 'thread_local'   # NCCL's watchdog thread polls events during capture
+        self._graph = None
+        self._static_in = None
+        self._alloc()
+        self.set_weights(weights)
 
     def _alloc(self):
         t = self.torch
@@ -322,9 +346,8 @@ class HeadTrainer:
 
     def _sync_stats(self, group):
         """ONE all-reduce (SUM) of the contiguous [sum x | sum x^2 | n] vectors of a group of independent BN layers."""
-        o0 = self.stat_off[group[0]][0]
-        o1, c1 = self.stat_off[group[-1]]
-        self._allreduce(self.stats[o0:o1 + 2 * c1 + 1])
+        b, e = self.stats_span(group)
+        self._allreduce(self.stats[b:e])
 
     def _bn_apply(self, name, x, M, y_ptr, ldy, relu=1):
         o, Cc = self.stat_off[name]
@@ -343,9 +366,8 @@ class HeadTrainer:
                    self._p(self.grads, go), self._p(self.T['scratch']))
 
     def _sync_bn_grads(self, group):
-        g0 = self.off[(group[0], 'beta')][0]
-        g1, (c1,) = self.off[(group[-1], 'beta')]
-        self._allreduce(self.grads[g0:g1 + 2 * c1])
+        b, e = self.bn_grad_span(group)
+        self._allreduce(self.grads[b:e])
 
     def _bn_bwd_apply(self, name, dy_ptr, ld_dy, y_ptr, ld_y, x, M, dx, relu=1):
         o, Cc = self.stat_off[name]
@@ -506,7 +528,8 @@ class HeadTrainer:
         """ONE all-reduce (SUM) of the flat fp32 bucket holding every 1x1 kernel, the classifier bias and every depthwise kernel
         (regions A|B; the loss is normalised by the GLOBAL batch, so the sum is the gradient of the global mean loss —
         MirroredStrategy semantics, train.py:143-158).  BN gradients are already global."""
-        self._allreduce(self.grads[:self.endB])
+        b, e = self.bucket_span()
+        self._allreduce(self.grads[b:e])
 
     def apply_gradients(self):
         P = self._p
