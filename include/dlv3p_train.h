@@ -76,9 +76,11 @@ int dlv3p_train_resize_bwd(int device, const void* dy_bf16, int64_t ld_dy, int B
 size_t dlv3p_train_loss_scratch_bytes(void);
 int dlv3p_train_softmax_ce(int device, const float* logits, int64_t ldl, const float* bias, const uint8_t* labels, int B, int NC, int hi, int wi,
                            int H, int W, int ignore_index, float inv_norm, float* d_full, float* d_loss, void* d_scratch, void* cuda_stream);
-/* adjoint of pred_resize: planar fp32 [B,NC,H,W] -> bf16 rows [B*hi*wi, ld_dx] (columns >= NC untouched). */
+/* adjoint of pred_resize: planar fp32 [B,NC,H,W] -> bf16 rows [B*hi*wi, ld_dx] (columns >= NC untouched).  With d_scratch
+ * (dlv3p_train_resize_bwd_planar_scratch_bytes(B, NC, hi, W) bytes) the adjoint runs as two separable passes; NULL = one pass. */
+size_t dlv3p_train_resize_bwd_planar_scratch_bytes(int B, int NC, int hi, int W);
 int dlv3p_train_resize_bwd_planar(int device, const float* d_full, int B, int NC, int hi, int wi, int H, int W, void* dx_bf16, int64_t ld_dx,
-                                  void* cuda_stream);
+                                  void* d_scratch, void* cuda_stream);
 
 /* out[b][c] = scale * sum over the image's npix rows of x[., c] (x rows of stride ld): AveragePooling2D over the whole map
  * (layers.py:132) with scale = 1/npix; per-image column sums (adjoint of the aspp_resize broadcast) with scale = 1.

@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
 // flight whatever C is.  Fixed reduction order (warps through smem, bands by the final kernel): deterministic.
 __host__ __device__ inline int col_bands(int C) {
   const int chunks = (C + 255) / 256;
-  int b = (4 * 148 + chunks - 1) / chunks;
-  return b < 8 ? 8 : (b > 256 ? 256 : b);
+  int b = (3 * 148 + chunks - 1) / chunks;
+  return b < 8 ? 8 : (b > 1024 ? 1024 : b);
 }
 // floats of scratch the banded column reductions need for `nq` quantities per channel (monotonic in C)
 __host__ __device__ inline size_t col_scratch_floats(int C, int nq) {
@@ -157,6 +157,8 @@ __global__ void bn_stats_vec_final_kernel(const float* __restrict__ partial, int
 }
 // y[row*ldy + c] = x*scale[c] + shift[c] [ReLU] with scale = gamma * rsqrt(var + eps), shift = beta - mean * scale computed ONCE
 // per block into shared memory (dynamic smem: 2*C floats); the element loop is pure streaming.
+// Idx = unsigned int whenever M * C/8 < 2^32 (always, at the reference's sizes): 64-bit division per element is what bounded the first version
+template <typename Idx>
 __global__ void __launch_bounds__(256) bn_apply_vec_kernel(const __nv_bfloat16* __restrict__ x, long long M, int C, const float* __restrict__ stats,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int relu,
                                                            __nv_bfloat16* __restrict__ y, long long ldy) {
@@ -172,13 +174,13 @@ __global__ void __launch_bounds__(256) bn_apply_vec_kernel(const __nv_bfloat16* 
     }
   }
   __syncthreads();
-  const int vecs = C >> 3;
-  const long long total = M * vecs;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int vec = static_cast<int>(idx % vecs);
-    const long long row = idx / vecs;
+  const Idx vecs = static_cast<Idx>(C >> 3);
+  const Idx total = static_cast<Idx>(M) * vecs;
+  for (Idx idx = blockIdx.x * static_cast<Idx>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<Idx>(gridDim.x) * blockDim.x) {
+    const Idx row = idx / vecs;
+    const int vec = static_cast<int>(idx - row * vecs);
     float v[8];
-    unpack8_bn(ldg_nc_v4(x + idx * 8), v);
+    unpack8_bn(ldg_nc_v4(x + static_cast<size_t>(idx) * 8), v);
     const float4 s0 = *reinterpret_cast<const float4*>(s_coef + vec * 8), s1 = *reinterpret_cast<const float4*>(s_coef + vec * 8 + 4);
     const float4 t0 = *reinterpret_cast<const float4*>(s_coef + C + vec * 8), t1 = *reinterpret_cast<const float4*>(s_coef + C + vec * 8 + 4);
     v[0] = fmaf(v[0], s0.x, t0.x); v[1] = fmaf(v[1], s0.y, t0.y); v[2] = fmaf(v[2], s0.z, t0.z); v[3] = fmaf(v[3], s0.w, t0.w);
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(256) bn_apply_vec_kernel(const __nv_bfloat16* 
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.0f);
     }
-    stg_v4(y + row * ldy + vec * 8, make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
+    stg_v4(y + static_cast<long long>(row) * ldy + vec * 8, make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
   }
 }
 

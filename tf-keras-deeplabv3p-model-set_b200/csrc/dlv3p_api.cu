@@ -1775,7 +1775,7 @@ int dlv3p_op_bn_stats(int device, const void* x_bf16, int64_t M, int C, float* d
   if (C % 8 == 0) {   // 16-byte loads, ~4 blocks per SM in flight
     const int bands = col_bands(C);
     bn_stats_vec_kernel<<<dim3(ceil_div(C, 256), bands), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x_bf16), M, C, bands, static_cast<float*>(d_scratch));
-    bands_final_kernel<<<ceil_div(2 * C, 32), dim3(32, 8), 0, st>>>(static_cast<const float*>(d_scratch), bands, 2 * C, d_stats, 2 * C, static_cast<float>(M));
+    bands_final_kernel<<<ceil_div(2 * C, 32), dim3(32, kFinalRows), 0, st>>>(static_cast<const float*>(d_scratch), bands, 2 * C, d_stats, 2 * C, static_cast<float>(M));
   } else {
     bn_stats_partial_kernel<<<dim3(ceil_div(C, 64), kBnBands), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x_bf16), M, C, static_cast<float*>(d_scratch));
     bn_stats_final_kernel<<<ceil_div(2 * C, 256), 256, 0, st>>>(static_cast<const float*>(d_scratch), M, C, d_stats);
@@ -1791,7 +1791,7 @@ int dlv3p_op_bn_apply(int device, const void* x_bf16, int64_t M, int C, const fl
   if (!x_bf16 || !d_stats || !d_gamma || !d_beta || !y_bf16 || M < 1 || C < 8 || C % 8) return fail(nullptr, DLV3P_ERR_INVALID, "op_bn_apply: bad arguments (C % 8)");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   if (C > 4096) return fail(nullptr, DLV3P_ERR_UNSUPPORTED, "op_bn_apply: C <= 4096");
-  bn_apply_vec_kernel<<<grid_for(static_cast<size_t>(M) * (C / 8), sms), 256, 2 * C * sizeof(float), st>>>(static_cast<const __nv_bfloat16*>(x_bf16), M, C, d_stats, d_gamma,
+  bn_apply_vec_kernel<unsigned long long><<<grid_for(static_cast<size_t>(M) * (C / 8), sms), 256, 2 * C * sizeof(float), st>>>(static_cast<const __nv_bfloat16*>(x_bf16), M, C, d_stats, d_gamma,
                                                                                                           d_beta, eps, relu, static_cast<__nv_bfloat16*>(y_bf16), C);
   CU_TRY(nullptr, cudaGetLastError());
   return DLV3P_OK;

@@ -144,8 +144,12 @@ int dlv3p_train_bn_apply(int device, const void* x, int64_t M, int C, const floa
   if (!x || !d_stats || !d_gamma || !d_beta || !y || M < 1 || C < 8 || C % 8 || ldy % 8 || ldy < C || !aligned16(y))
     return fail(nullptr, DLV3P_ERR_INVALID, "train_bn_apply: bad arguments (C % 8, ldy % 8)");
   if (C > 4096) return fail(nullptr, DLV3P_ERR_UNSUPPORTED, "train_bn_apply: C <= 4096");
-  bn_apply_vec_kernel<<<grid_for(static_cast<size_t>(M) * (C / 8), sms), 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(cuda_stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), M, C, d_stats, d_gamma, d_beta, eps, relu, static_cast<__nv_bfloat16*>(y), ldy);
+  if (static_cast<unsigned long long>(M) * (C / 8) < 0xF0000000ull)
+    bn_apply_vec_kernel<unsigned int><<<grid_for(static_cast<size_t>(M) * (C / 8), sms), 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(cuda_stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), M, C, d_stats, d_gamma, d_beta, eps, relu, static_cast<__nv_bfloat16*>(y), ldy);
+  else
+    bn_apply_vec_kernel<unsigned long long><<<grid_for(static_cast<size_t>(M) * (C / 8), sms), 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(cuda_stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), M, C, d_stats, d_gamma, d_beta, eps, relu, static_cast<__nv_bfloat16*>(y), ldy);
   CU_TRY(nullptr, cudaGetLastError());
   return DLV3P_OK;
 }
@@ -170,12 +174,12 @@ int dlv3p_train_bn_bwd_stats(int device, const void* dy, int64_t ld_dy, const vo
     bn_bwd_stats_vec_kernel<<<dim3(ceil_div(C, 256), bands), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dy), ld_dy, static_cast<const __nv_bfloat16*>(y), ld_y,
                                                                             static_cast<const __nv_bfloat16*>(x), M, C, d_stats, eps, relu, bands,
                                                                             static_cast<float*>(d_scratch));
-    bands_final_kernel<<<ceil_div(2 * C, 32), dim3(32, 8), 0, st>>>(static_cast<const float*>(d_scratch), bands, 2 * C, d_sums);
+    bands_final_kernel<<<ceil_div(2 * C, 32), dim3(32, kFinalRows), 0, st>>>(static_cast<const float*>(d_scratch), bands, 2 * C, d_sums);
   } else {
     bn_bwd_stats_partial_kernel<<<dim3(ceil_div(C, 64), kTrBands), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dy), ld_dy, static_cast<const __nv_bfloat16*>(y), ld_y,
                                                                                   static_cast<const __nv_bfloat16*>(x), M, C, d_stats, eps, relu,
                                                                                   static_cast<float*>(d_scratch));
-    bands_final_kernel<<<ceil_div(2 * C, 32), dim3(32, 8), 0, st>>>(static_cast<const float*>(d_scratch), kTrBands, 2 * C, d_sums);
+    bands_final_kernel<<<ceil_div(2 * C, 32), dim3(32, kFinalRows), 0, st>>>(static_cast<const float*>(d_scratch), kTrBands, 2 * C, d_sums);
   }
   CU_TRY(nullptr, cudaGetLastError());
   return DLV3P_OK;
@@ -189,9 +193,14 @@ int dlv3p_train_bn_bwd_apply(int device, const void* dy, int64_t ld_dy, const vo
       (relu && !aligned16(y)))
     return fail(nullptr, DLV3P_ERR_INVALID, "train_bn_bwd_apply: bad arguments (C % 8, strides % 8, 16-byte aligned slices)");
   if (C > 4096) return fail(nullptr, DLV3P_ERR_UNSUPPORTED, "train_bn_bwd_apply: C <= 4096");
-  bn_bwd_apply_vec_kernel<<<grid_for(static_cast<size_t>(M) * (C / 8), sms), 256, 3 * C * sizeof(float), static_cast<cudaStream_t>(cuda_stream)>>>(
-      static_cast<const __nv_bfloat16*>(dy), ld_dy, static_cast<const __nv_bfloat16*>(y), ld_y, static_cast<const __nv_bfloat16*>(x), M, C, d_stats, d_sums,
-      d_gamma, eps, relu, static_cast<__nv_bfloat16*>(dx));
+  if (static_cast<unsigned long long>(M) * (C / 8) < 0xF0000000ull)
+    bn_bwd_apply_vec_kernel<unsigned int><<<grid_for(static_cast<size_t>(M) * (C / 8), sms), 256, 3 * C * sizeof(float), static_cast<cudaStream_t>(cuda_stream)>>>(
+        static_cast<const __nv_bfloat16*>(dy), ld_dy, static_cast<const __nv_bfloat16*>(y), ld_y, static_cast<const __nv_bfloat16*>(x), M, C, d_stats, d_sums,
+        d_gamma, eps, relu, static_cast<__nv_bfloat16*>(dx));
+  else
+    bn_bwd_apply_vec_kernel<unsigned long long><<<grid_for(static_cast<size_t>(M) * (C / 8), sms), 256, 3 * C * sizeof(float), static_cast<cudaStream_t>(cuda_stream)>>>(
+        static_cast<const __nv_bfloat16*>(dy), ld_dy, static_cast<const __nv_bfloat16*>(y), ld_y, static_cast<const __nv_bfloat16*>(x), M, C, d_stats, d_sums,
+        d_gamma, eps, relu, static_cast<__nv_bfloat16*>(dx));
   CU_TRY(nullptr, cudaGetLastError());
   return DLV3P_OK;
 }
@@ -237,17 +246,17 @@ int dlv3p_train_depthwise_wgrad(int device, const void* x, const void* dy, int B
     Q.B = B; Q.H = H; Q.W = W_; Q.C = C; Q.rate = rate; Q.R = R;
     const int bands = ceil_div(H, R);
     dw_band_wgrad_kernel<<<dim3(bands, ceil_div(C, 32), B), 256, smem, st>>>(Q);
-    bands_final_kernel<<<ceil_div(9 * C, 32), dim3(32, 8), 0, st>>>(static_cast<const float*>(d_scratch), B * bands, 9 * C, d_dw);
+    bands_final_kernel<<<ceil_div(9 * C, 32), dim3(32, kFinalRows), 0, st>>>(static_cast<const float*>(d_scratch), B * bands, 9 * C, d_dw);
   } else if (C % 8 == 0) {
     const long long npix = static_cast<long long>(B) * H * W_;
     const int G = npix < kDwWgradBlocks ? static_cast<int>(npix) : kDwWgradBlocks;
     dw_wgrad_vec_kernel<<<dim3(G, ceil_div(C / 8, 256)), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), B, H, W_, C, rate,
                                                                         static_cast<float*>(d_scratch));
-    bands_final_kernel<<<ceil_div(9 * C, 32), dim3(32, 8), 0, st>>>(static_cast<const float*>(d_scratch), G, 9 * C, d_dw);
+    bands_final_kernel<<<ceil_div(9 * C, 32), dim3(32, kFinalRows), 0, st>>>(static_cast<const float*>(d_scratch), G, 9 * C, d_dw);
   } else {
     dw_wgrad_partial_kernel<<<dim3(ceil_div(C, 64), kTrBands), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), B, H, W_, C, rate,
                                                                               static_cast<float*>(d_scratch));
-    bands_final_kernel<<<ceil_div(9 * C, 32), dim3(32, 8), 0, st>>>(static_cast<const float*>(d_scratch), kTrBands, 9 * C, d_dw);
+    bands_final_kernel<<<ceil_div(9 * C, 32), dim3(32, kFinalRows), 0, st>>>(static_cast<const float*>(d_scratch), kTrBands, 9 * C, d_dw);
   }
   CU_TRY(nullptr, cudaGetLastError());
   return DLV3P_OK;
@@ -310,15 +319,27 @@ int dlv3p_train_softmax_ce(int device, const float* logits, int64_t ldl, const f
   return DLV3P_OK;
 }
 
-int dlv3p_train_resize_bwd_planar(int device, const float* d_full, int B, int NC, int hi, int wi, int H, int W_, void* dx, int64_t ld_dx, void* cuda_stream) {
+size_t dlv3p_train_resize_bwd_planar_scratch_bytes(int B, int NC, int hi, int W_) {
+  return static_cast<size_t>(B > 0 ? B : 0) * (NC > 0 ? NC : 0) * (hi > 0 ? hi : 0) * (W_ > 0 ? W_ : 0) * sizeof(float);
+}
+
+int dlv3p_train_resize_bwd_planar(int device, const float* d_full, int B, int NC, int hi, int wi, int H, int W_, void* dx, int64_t ld_dx, void* d_scratch,
+                                  void* cuda_stream) {
   int sms = 0, r = train_prolog(device, &sms);
   if (r) return r;
   if (!d_full || !dx || B < 1 || NC < 1 || hi < 1 || wi < 1 || H < 1 || W_ < 1 || ld_dx < NC)
     return fail(nullptr, DLV3P_ERR_INVALID, "train_resize_bwd_planar: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   ResizeBwdPlanarParams P{};
   P.dy = d_full; P.dx = static_cast<__nv_bfloat16*>(dx); P.ld_dx = ld_dx; P.B = B; P.NC = NC; P.hi = hi; P.wi = wi; P.ho = H; P.wo = W_;
   P.sy = static_cast<float>(hi) / static_cast<float>(H); P.sx = static_cast<float>(wi) / static_cast<float>(W_);
-  resize_bwd_planar_kernel<<<grid_for(static_cast<size_t>(B) * NC * hi * wi, sms), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(P);
+  const unsigned long long nv = static_cast<unsigned long long>(B) * NC * hi * W_;
+  if (d_scratch && nv < 0xF0000000ull) {   // separable: vertical pass into the scratch, then horizontal
+    resize_bwd_planar_v_kernel<<<grid_for(static_cast<size_t>(nv), sms), 256, 0, st>>>(P, static_cast<float*>(d_scratch));
+    resize_bwd_planar_h_kernel<<<grid_for(static_cast<size_t>(B) * NC * hi * wi, sms), 256, 0, st>>>(P, static_cast<const float*>(d_scratch));
+  } else {
+    resize_bwd_planar_kernel<<<grid_for(static_cast<size_t>(B) * NC * hi * wi, sms), 256, 0, st>>>(P);
+  }
   CU_TRY(nullptr, cudaGetLastError());
   return DLV3P_OK;
 }

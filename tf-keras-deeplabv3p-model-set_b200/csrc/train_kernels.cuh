@@ -91,23 +91,24 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_partial_kernel(const __nv_bf
     if (c < C) partial[(static_cast<size_t>(band) * 2 + which) * C + c] = s;
   }
 }
-// out[i] = sum over bands of partial[b][i], fixed order: block (32, 8) — the 8 rows of threads take interleaved bands (independent
-// loads in flight), then one pass over shared memory.  extra_index >= 0: out[extra_index] = extra_value (the BN row count).
-__global__ void __launch_bounds__(256) bands_final_kernel(const float* __restrict__ partial, int bands, int n, float* __restrict__ out,
-                                                          int extra_index = -1, float extra_value = 0.0f) {
-  __shared__ float s_part[8][33];
+// out[i] = sum over bands of partial[b][i], fixed order: block (32, kFinalRows) — the rows of threads take interleaved bands
+// (independent loads in flight), then one pass over shared memory.  extra_index >= 0: out[extra_index] = extra_value (the BN row count).
+constexpr int kFinalRows = 32;
+__global__ void __launch_bounds__(32 * kFinalRows) bands_final_kernel(const float* __restrict__ partial, int bands, int n, float* __restrict__ out,
+                                                                      int extra_index = -1, float extra_value = 0.0f) {
+  __shared__ float s_part[kFinalRows][33];
   const int i = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
   if (i < n) {
 #pragma unroll 4
-    for (int b = threadIdx.y; b < bands; b += 8) s += __ldg(partial + static_cast<size_t>(b) * n + i);
+    for (int b = threadIdx.y; b < bands; b += kFinalRows) s += __ldg(partial + static_cast<size_t>(b) * n + i);
   }
   s_part[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && i < n) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += s_part[w][threadIdx.x];
+    for (int w = 0; w < kFinalRows; ++w) t += s_part[w][threadIdx.x];
     out[i] = t;
   }
   if (extra_index >= 0 && blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0) out[extra_index] = extra_value;
@@ -295,6 +296,47 @@ __global__ void __launch_bounds__(256) resize_bwd_planar_kernel(const ResizeBwdP
       }
     }
     P.dx[((static_cast<long long>(b) * P.hi + i) * P.wi + j) * P.ld_dx + c] = __float2bfloat16_rn(acc);
+  }
+}
+
+// Separable form of the same adjoint (bilinear weights factor into wy * wx): a vertical pass into an fp32 scratch [B, NC, hi, wo]
+// (loads coalesced along X, ~2*scale rows each) and a horizontal pass (~2*scale taps) — 2 x ~10 loads per output instead of ~12 x 12.
+__global__ void __launch_bounds__(256) resize_bwd_planar_v_kernel(const ResizeBwdPlanarParams P, float* __restrict__ tmp) {
+  const unsigned total = static_cast<unsigned>(P.B) * P.NC * P.hi * P.wo;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const unsigned X = idx % P.wo;
+    unsigned r = idx / P.wo;
+    const int i = static_cast<int>(r % P.hi);
+    const unsigned bc = r / P.hi;
+    int ya, yb;
+    adjoint_range(i, P.sy, P.ho, ya, yb);
+    const float* col = P.dy + static_cast<size_t>(bc) * P.ho * P.wo + X;
+    float acc = 0.f;
+    for (int Y = ya; Y <= yb; ++Y) {
+      const float wy = adjoint_weight(Y, P.sy, P.hi, i);
+      if (wy != 0.0f) acc = fmaf(wy, __ldg(col + static_cast<size_t>(Y) * P.wo), acc);
+    }
+    tmp[idx] = acc;
+  }
+}
+__global__ void __launch_bounds__(256) resize_bwd_planar_h_kernel(const ResizeBwdPlanarParams P, const float* __restrict__ tmp) {
+  const unsigned total = static_cast<unsigned>(P.B) * P.NC * P.hi * P.wi;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int j = static_cast<int>(idx % P.wi);
+    unsigned r = idx / P.wi;
+    const int i = static_cast<int>(r % P.hi);
+    r /= P.hi;
+    const int c = static_cast<int>(r % P.NC);
+    const int b = static_cast<int>(r / P.NC);
+    int xa, xb;
+    adjoint_range(j, P.sx, P.wo, xa, xb);
+    const float* row = tmp + (static_cast<size_t>(b * P.NC + c) * P.hi + i) * P.wo;
+    float acc = 0.f;
+    for (int X = xa; X <= xb; ++X) {
+      const float wx = adjoint_weight(X, P.sx, P.wi, j);
+      if (wx != 0.0f) acc = fmaf(wx, __ldg(row + X), acc);
+    }
+    P.dx[((static_cast<size_t>(b) * P.hi + i) * P.wi + j) * P.ld_dx + c] = __float2bfloat16_rn(acc);
   }
 }
 
@@ -602,6 +644,7 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_vec_kernel(const __nv_bfloat
 }
 // dx = A*g + Bc*x + Cc with per-channel A = gamma*invstd, Bc = -A*invstd*S2/n, Cc = -A*S1/n - Bc*mean (the expansion of
 // gamma*invstd*(g - S1/n - xhat*S2/n)), computed once per block into shared memory (dynamic smem: 3*C floats)
+template <typename Idx>
 __global__ void __launch_bounds__(256) bn_bwd_apply_vec_kernel(const __nv_bfloat16* __restrict__ dy, long long ld_dy, const __nv_bfloat16* __restrict__ y,
                                                                long long ld_y, const __nv_bfloat16* __restrict__ x, long long M, int C,
                                                                const float* __restrict__ stats, const float* __restrict__ sums, const float* __restrict__ gamma,
@@ -620,14 +663,15 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_vec_kernel(const __nv_bfloat
     }
   }
   __syncthreads();
-  const int vecs = C >> 3;
-  const long long total = M * vecs;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int vec = static_cast<int>(idx % vecs);
-    const long long row = idx / vecs;
+  const Idx vecs = static_cast<Idx>(C >> 3);
+  const Idx total = static_cast<Idx>(M) * vecs;
+  for (Idx idx = blockIdx.x * static_cast<Idx>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<Idx>(gridDim.x) * blockDim.x) {
+    const Idx row_i = idx / vecs;
+    const int vec = static_cast<int>(idx - row_i * vecs);
+    const long long row = static_cast<long long>(row_i);
     float g[8], xv[8];
     unpack8(ldg_nc_v4(dy + row * ld_dy + vec * 8), g);
-    unpack8(ldg_nc_v4(x + idx * 8), xv);
+    unpack8(ldg_nc_v4(x + static_cast<size_t>(idx) * 8), xv);
     if (relu) {
       float yv[8];
       unpack8(ldg_nc_v4(y + row * ld_y + vec * 8), yv);
@@ -640,7 +684,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_vec_kernel(const __nv_bfloat
       const int c = vec * 8 + k;
       g[k] = fmaf(s_coef[c], g[k], fmaf(s_coef[C + c], xv[k], s_coef[2 * C + c]));
     }
-    stg_v4(dx + idx * 8, pack8(g));
+    stg_v4(dx + static_cast<size_t>(idx) * 8, pack8(g));
   }
 }
 

@@ -192,6 +192,7 @@ class HeadTrainer(TrainLayout):
         T['logits'] = z(M2, NCp, dtype=f32)
         T['dfull'] = z(B, self.NC, self.H, self.W, dtype=f32)
         T['loss'] = z(2, dtype=f32)
+        T['adj_tmp'] = z(B, self.NC, self.hs, self.W, dtype=f32)      # vertical pass of the separable pred_resize adjoint
         T['bias_stats'] = z(2 * NCp + 4, dtype=f32)
         # backward
         T['dlow'] = z(M2, NCp)
@@ -461,7 +462,7 @@ class HeadTrainer(TrainLayout):
         self._call('dlv3p_train_softmax_ce', P(T['logits']), NCp, self._wp(self.params, ('conv_upsample', 'bias')), P(labels), B, NC, hs, ws, self.H, self.W,
                    self.ignore, inv_norm, P(T['dfull']), P(T['loss']), P(T['loss_scratch']))
         # ================ backward
-        self._call('dlv3p_train_resize_bwd_planar', P(T['dfull']), B, NC, hs, ws, self.H, self.W, P(T['dlow']), NCp)
+        self._call('dlv3p_train_resize_bwd_planar', P(T['dfull']), B, NC, hs, ws, self.H, self.W, P(T['dlow']), NCp, P(T['adj_tmp']))
         # d(bias) = column sums of d(logits): the banded two-stage statistics kernel (sum x | sum x^2 | n), first NCp entries
         self._call('dlv3p_op_bn_stats', P(T['dlow']), M2, NCp, P(T['bias_stats']), P(T['bn_scratch']))
         self.view(self.grads, ('conv_upsample', 'bias')).copy_(T['bias_stats'][:NCp])
