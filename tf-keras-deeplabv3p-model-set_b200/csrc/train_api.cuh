@@ -334,8 +334,8 @@ int dlv3p_train_resize_bwd_planar(int device, const float* d_full, int B, int NC
   P.dy = d_full; P.dx = static_cast<__nv_bfloat16*>(dx); P.ld_dx = ld_dx; P.B = B; P.NC = NC; P.hi = hi; P.wi = wi; P.ho = H; P.wo = W_;
   P.sy = static_cast<float>(hi) / static_cast<float>(H); P.sx = static_cast<float>(wi) / static_cast<float>(W_);
   const unsigned long long nv = static_cast<unsigned long long>(B) * NC * hi * W_;
-  if (d_scratch && nv < 0xF0000000ull) {   // separable: vertical pass into the scratch, then horizontal
-    resize_bwd_planar_v_kernel<<<grid_for(static_cast<size_t>(nv), sms), 256, 0, st>>>(P, static_cast<float*>(d_scratch));
+  if (d_scratch && nv < 0xF0000000ull && hi <= 65535 && B * NC <= 65535) {   // separable: vertical pass into the scratch, then horizontal
+    resize_bwd_planar_v_kernel<<<dim3(ceil_div(W_, 256), hi, B * NC), 256, 0, st>>>(P, static_cast<float*>(d_scratch));
     resize_bwd_planar_h_kernel<<<grid_for(static_cast<size_t>(B) * NC * hi * wi, sms), 256, 0, st>>>(P, static_cast<const float*>(d_scratch));
   } else {
     resize_bwd_planar_kernel<<<grid_for(static_cast<size_t>(B) * NC * hi * wi, sms), 256, 0, st>>>(P);

@@ -301,23 +301,29 @@ __global__ void __launch_bounds__(256) resize_bwd_planar_kernel(const ResizeBwdP
 
 // Separable form of the same adjoint (bilinear weights factor into wy * wx): a vertical pass into an fp32 scratch [B, NC, hi, wo]
 // (loads coalesced along X, ~2*scale rows each) and a horizontal pass (~2*scale taps) — 2 x ~10 loads per output instead of ~12 x 12.
+// grid (ceil(wo / 256), hi, B * NC): a block works on ONE input row i, so the vertical weights are computed once per block
 __global__ void __launch_bounds__(256) resize_bwd_planar_v_kernel(const ResizeBwdPlanarParams P, float* __restrict__ tmp) {
-  const unsigned total = static_cast<unsigned>(P.B) * P.NC * P.hi * P.wo;
-  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const unsigned X = idx % P.wo;
-    unsigned r = idx / P.wo;
-    const int i = static_cast<int>(r % P.hi);
-    const unsigned bc = r / P.hi;
-    int ya, yb;
-    adjoint_range(i, P.sy, P.ho, ya, yb);
-    const float* col = P.dy + static_cast<size_t>(bc) * P.ho * P.wo + X;
-    float acc = 0.f;
-    for (int Y = ya; Y <= yb; ++Y) {
-      const float wy = adjoint_weight(Y, P.sy, P.hi, i);
-      if (wy != 0.0f) acc = fmaf(wy, __ldg(col + static_cast<size_t>(Y) * P.wo), acc);
-    }
-    tmp[idx] = acc;
+  __shared__ float s_wy[64];
+  const int i = blockIdx.y;
+  const unsigned bc = blockIdx.z;
+  int ya, yb;
+  adjoint_range(i, P.sy, P.ho, ya, yb);
+  const int span = min(yb - ya + 1, 64);
+  if (threadIdx.x < span) s_wy[threadIdx.x] = adjoint_weight(ya + threadIdx.x, P.sy, P.hi, i);
+  __syncthreads();
+  const int X = blockIdx.x * 256 + threadIdx.x;
+  if (X >= P.wo) return;
+  const float* col = P.dy + (static_cast<size_t>(bc) * P.ho + ya) * P.wo + X;
+  float acc = 0.f;
+  for (int k = 0; k < span; ++k) {
+    const float wy = s_wy[k];
+    if (wy != 0.0f) acc = fmaf(wy, __ldg(col + static_cast<size_t>(k) * P.wo), acc);
   }
+  for (int Y = ya + span; Y <= yb; ++Y) {      // scales beyond x32 (never at the reference's sizes)
+    const float wy = adjoint_weight(Y, P.sy, P.hi, i);
+    if (wy != 0.0f) acc = fmaf(wy, __ldg(P.dy + (static_cast<size_t>(bc) * P.ho + Y) * P.wo + X), acc);
+  }
+  tmp[(static_cast<size_t>(bc) * P.hi + i) * P.wo + X] = acc;
 }
 __global__ void __launch_bounds__(256) resize_bwd_planar_h_kernel(const ResizeBwdPlanarParams P, const float* __restrict__ tmp) {
   const unsigned total = static_cast<unsigned>(P.B) * P.NC * P.hi * P.wi;
