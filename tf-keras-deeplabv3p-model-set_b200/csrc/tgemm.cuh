@@ -28,11 +28,13 @@ enum TgOut : int { kTgOutBf16 = 0, kTgOutF32 = 1, kTgOutPartial = 2 };
 struct TgLaunch {
   CUtensorMap tmap_a;   // [M, K] bf16, box {64, 128}, SWIZZLE_128B
   CUtensorMap tmap_b;   // [N, K] bf16, box {64, min(BN, 128)}, SWIZZLE_128B
+  CUtensorMap tmap_d;   // bf16 output [M, N] (row stride ldd), box {64, 32}, SWIZZLE_128B: the TMA-store epilogue (tma_store != 0)
   void* out;            // bf16 [M, ldd] | fp32 [M, ldd] | fp32 partials [splits][M][N]
   long long ldd;
   int M, N, K;
   int m_tiles, n_tiles, splits, kblocks, kb_per_split;
   int out_mode;
+  int tma_store;        // bf16 output through swizzled smem + cp.async.bulk.tensor stores (full 128-byte lines, asynchronous)
 };
 
 template <int BN>
@@ -40,7 +42,8 @@ struct TgCfg {
   static constexpr int kStageBytes = kTgBM * 128 + BN * 128;
   static constexpr int kStages = (BN >= 256) ? 4 : 6;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 256;
+  static constexpr int kStoreBytes = 4 * 2 * 4096;   // 4 epilogue warps x 2 buffers x [32 rows x 128 B]
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + 256;
 };
 
 // TN = false: D = A[M,K] * B[N,K]^T (operands K-major).  TN = true: D[M,N] = A[Kc,M]^T * B[Kc,N] — both operands MN-major, read
@@ -55,7 +58,8 @@ __global__ void __launch_bounds__(kTgThreads, 1) tgemm_kernel(const __grid_const
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * (kTgBM * 128);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* smem_c = smem + kStages * Cfg::kStageBytes;     // epilogue staging (1024-byte aligned)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + Cfg::kStoreBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tmem_full = bars + 2 * kStages;
@@ -79,6 +83,7 @@ __global__ void __launch_bounds__(kTgThreads, 1) tgemm_kernel(const __grid_const
     fence_barrier_init();
     tma_prefetch_desc(&L.tmap_a);
     tma_prefetch_desc(&L.tmap_b);
+    if (L.tma_store) tma_prefetch_desc(&L.tmap_d);
   }
   if (warp == 1) {
     tmem_alloc(tmem_base_ptr, Cfg::kTmemCols);
@@ -149,6 +154,7 @@ __global__ void __launch_bounds__(kTgThreads, 1) tgemm_kernel(const __grid_const
   } else {
     const int q = warp & 3;
     uint32_t it = 0;
+    uint32_t store_buf = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
       const int split = item / tiles, t = item - split * tiles;
       const int mt = t / L.n_tiles, nt = t - mt * L.n_tiles;
@@ -160,6 +166,37 @@ __global__ void __launch_bounds__(kTgThreads, 1) tgemm_kernel(const __grid_const
       const bool row_ok = row < L.M;
       const int n0 = nt * BN;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      if (L.tma_store) {
+        // bf16 rows staged in 128B-swizzled smem (16-byte chunk index XOR (row & 7)) and written by TMA: whole 128-byte lines,
+        // rows / columns past M / N clipped by the tensor map; double buffered per warp
+        uint8_t* my_c = smem_c + (warp - 2) * 2 * 4096;
+#pragma unroll 1
+        for (int cb = 0; cb < BN / 64; ++cb) {
+          if (n0 + cb * 64 >= L.N) break;   // uniform
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          const uint32_t cbuf = smem_u32(my_c + store_buf * 4096) + lane * 128;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(taddr + cb * 64 + half * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint32_t chunk = static_cast<uint32_t>(half * 4 + (j >> 3)) ^ static_cast<uint32_t>(lane & 7);
+              sts_v4(cbuf + chunk * 16, make_uint4(pack_bf16x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), pack_bf16x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])),
+                                                  pack_bf16x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])), pack_bf16x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]))));
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&L.tmap_d, my_c + store_buf * 4096, n0 + cb * 64, mt * kTgBM + q * 32);
+            tma_store_commit();
+          }
+          store_buf ^= 1;
+        }
+      } else {
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         if (n0 + c0 >= L.N) break;   // uniform
@@ -198,9 +235,11 @@ __global__ void __launch_bounds__(kTgThreads, 1) tgemm_kernel(const __grid_const
         }
         __syncwarp();
       }
+      }
       tcgen05_fence_before();
       mbar_arrive(&tmem_empty[acc]);
     }
+    if (L.tma_store && lane == 0) tma_store_wait_all<0>();   // bulk stores complete before the smem goes away
   }
 
   tcgen05_fence_before();
