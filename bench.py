@@ -350,4 +350,18 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    if '--train' in sys.argv:      # cfg-5 training step of the head: tools/trainbench.py (same launch conventions; its own JSON line)
+        import runpy
+        sys.argv = [a for a in sys.argv if a != '--train']
+        keep = [sys.argv[0]]
+        i = 1
+        while i < len(sys.argv):
+            if sys.argv[i] in ('--steps', '--warmup', '--batch') and i + 1 < len(sys.argv):
+                keep += sys.argv[i:i + 2]
+                i += 2
+            else:
+                i += 2 if sys.argv[i] == '--gpus' else 1
+        sys.argv = keep
+        runpy.run_path(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'tools', 'trainbench.py'), run_name='__main__')
+    else:
+        main()

@@ -15,6 +15,10 @@ class _Var:
     def numpy(self):
         return self._a
 
+    def assign(self, a):
+        assert a.shape == self._a.shape
+        self._a = np.array(a, np.float32)
+
 
 class _Tensor:
     def __init__(self, shape):
@@ -109,3 +113,21 @@ def test_head_from_keras_equals_direct_head(gpu):
     b = hd.predict_host(feat, skip)                # fp32 features in, as a TF backbone would hand them over
     assert np.array_equal(a, b)
     hd.close()
+
+
+def test_head_weights_and_load_into_round_trip():
+    """keras_bridge.head_weights(model) -> (training) -> keras_bridge.load_into(model, weights): by layer name, shapes checked."""
+    from dlv3p_b200 import keras_bridge as kb
+    cfg = R.HeadConfig(B=1, H=128, W=128, OS=16, Cin=64, Cskip=32, NC=21)
+    W = R.make_weights(cfg, 5)
+    model = StubKerasModel(cfg, W, classifier_name='logits_semantic')
+    got = kb.head_weights(model)                       # plan-only context: no GPU needed
+    assert set(got) == set(W) and all(np.array_equal(got[k], np.asarray(W[k], np.float32)) for k in W)
+    new = {k: v + 1.0 for k, v in got.items()}
+    assert kb.load_into(model, new) == len(W)
+    again = kb.head_weights(model)
+    assert all(np.array_equal(again[k], new[k]) for k in new)
+    with pytest.raises(ValueError):
+        kb.load_into(model, {('aspp0', 'kernel'): np.zeros((1, 1, 3, 3), np.float32)})
+    with pytest.raises(KeyError):
+        kb.load_into(model, {('no_such_layer', 'kernel'): np.zeros((1,), np.float32)})

@@ -92,6 +92,43 @@ def head_weights_from_keras(model, head: DeepLabHead) -> Dict[Tuple[str, str], n
     return out
 
 
+def _head_layer(model, layer: str):
+    names = _CLASSIFIER_NAMES if layer == 'conv_upsample' else (layer,)
+    return next((l for l in (_get_layer(model, n) for n in names) if l is not None), None)
+
+
+def head_weights(model) -> Dict[Tuple[str, str], np.ndarray]:
+    """Every head weight of a reference model, keyed (layer, variable) in the Keras layout — what `DeepLabHead.set_weights` and
+    `train.HeadTrainer` take.  Needs no GPU: the inventory comes from a plan-only context (`dlv3p_create(device=-1)`)."""
+    d = describe_head(model)
+    plan = DeepLabHead(1, d['H'], d['W'], d['OS'], d['Cin'], d['Cskip'], d['NC'], lite=d['lite'], decoder=d['decoder'], device=-1,
+                       h=d['h'], w=d['w'], hs=d['hs'], ws=d['ws'])
+    try:
+        return head_weights_from_keras(model, plan)
+    finally:
+        plan.close()
+
+
+def load_into(model, weights: Dict[Tuple[str, str], np.ndarray]) -> int:
+    """Write head weights (e.g. `HeadTrainer.get_weights()` after training) back into the reference model's own layers BY NAME, variable
+    by variable (`variable.assign`), so `model.save` / `model.save_weights` (train.py:196-203) store them.  Returns the number of
+    variables written; raises on a missing layer / variable or a shape mismatch."""
+    n = 0
+    for (layer, var), a in weights.items():
+        kl = _head_layer(model, layer)
+        if kl is None:
+            raise KeyError('the model has no layer named %s' % layer)
+        target = next((w for w in kl.weights if _var_basename(w.name) == var), None)
+        if target is None:
+            raise KeyError('layer %s has no variable %s' % (layer, var))
+        a = np.asarray(a, np.float32)
+        if tuple(_static_shape(target)) != tuple(a.shape):
+            raise ValueError('%s/%s has shape %s, got %s' % (layer, var, tuple(_static_shape(target)), a.shape))
+        target.assign(a)
+        n += 1
+    return n
+
+
 def head_from_keras(model, batch: int, device: int = 0, out_mode: int = ffi.OUT_LABELS_U8,
                     in_dtype: int = ffi.DTYPE_FP32) -> DeepLabHead:
     """Build a libdlv3p context for the head of `model` and load the model's own head weights into it.
