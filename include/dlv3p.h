@@ -210,6 +210,14 @@ int dlv3p_op_resize_argmax(int device, const float* logits_planar, int B, int NC
 int dlv3p_op_confusion_matrix(int device, const uint8_t* d_pred, const uint8_t* d_gt, int64_t n, int NC,
                               unsigned long long* d_confusion, void* cuda_stream);
 
+/* Pixel counts behind the reference's training metric Jaccard (deeplabv3p/metrics.py:30-45; train.py:141 metrics={'pred_mask': Jaccard}):
+ * per image b and class i in 0..NC:  d_counts[b][0][i] = #(gt == i and pred == i), [b][1][i] = #(gt == i), [b][2][i] = #(pred == i)
+ * (uint64 [B][3][NC+1], ACCUMULATED; zero it first).  Device uint8 label maps [B, n_per_image]; asynchronous; integer work, bit exact.
+ * The float part (IoU per image, mean over the images that contain the class, mean over the classes present) is host arithmetic on
+ * 3*(NC+1) numbers per image: dlv3p_b200.metrics.jaccard. */
+int dlv3p_op_jaccard_counts(int device, const uint8_t* d_pred, const uint8_t* d_gt, int B, int64_t n_per_image, int NC,
+                            unsigned long long* d_counts, void* cuda_stream);
+
 /* Image pre / post-processing of the demo and evaluation loops (deeplab.py:81-109, eval.py:403-443), device
  * pointers, asynchronous on the stream, bit exact against the reference's own numpy / cv2 code (tests/golden/ref_pins.npz):
  *   normalize_image    common/data_utils.py:403-416  uint8 [n] -> float32(x)/127.5 - 1 as fp32, or as bf16 (out_bf16 = 1: the head's input dtype)

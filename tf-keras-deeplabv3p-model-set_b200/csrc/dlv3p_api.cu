@@ -1732,6 +1732,21 @@ int dlv3p_op_confusion_matrix(int device, const uint8_t* d_pred, const uint8_t* 
   return DLV3P_OK;   // asynchronous; d_confusion is ACCUMULATED (zero it once per evaluation)
 }
 
+int dlv3p_op_jaccard_counts(int device, const uint8_t* d_pred, const uint8_t* d_gt, int B, int64_t n_per_image, int NC, unsigned long long* d_counts,
+                            void* cuda_stream) {
+  int sms = 0, r = op_prolog(device, &sms);
+  if (r) return r;
+  if (!d_pred || !d_gt || !d_counts || B < 1 || B > 65535 || n_per_image < 1 || NC < 1 || NC > 254)
+    return fail(nullptr, DLV3P_ERR_INVALID, "op_jaccard_counts: bad arguments (1 <= NC <= 254)");
+  int bpi = static_cast<int>((n_per_image + 256 * 16 - 1) / (256 * 16));
+  const int cap = (8 * sms + B - 1) / B;
+  if (bpi > cap) bpi = cap;
+  if (bpi < 1) bpi = 1;
+  jaccard_counts_kernel<<<dim3(bpi, B), 256, 3 * (NC + 1) * sizeof(unsigned int), static_cast<cudaStream_t>(cuda_stream)>>>(d_pred, d_gt, n_per_image, NC, d_counts);
+  CU_TRY(nullptr, cudaGetLastError());
+  return DLV3P_OK;   // asynchronous; d_counts is ACCUMULATED
+}
+
 // ---- image pre / post-processing of the demo and evaluation loops
 int dlv3p_op_normalize_image(int device, const uint8_t* d_img, int64_t n, void* d_out, int out_bf16, void* cuda_stream) {
   int sms = 0, r = op_prolog(device, &sms);

@@ -961,4 +961,30 @@ __global__ void __launch_bounds__(256) mask_resize_nearest_kernel(const uint8_t*
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ Jaccard metric counts (N3)
+// The training metric of the reference (deeplabv3p/metrics.py:30-45, compiled in at train.py:141): per image and per class i in
+// 0..NC the pixel counts  inter = #(gt == i & pred == i), true = #(gt == i), pred = #(pred == i)  (union = true + pred - inter; a
+// pixel with the ignore label 255 belongs to no true class but still counts for the class it was predicted as).  Integer work,
+// bit exact; the tiny float part (per-image IoU, means over the images / classes that are present) stays on the host.
+// counts: [B][3][NC + 1] uint64, ACCUMULATED.  grid (blocks per image, B); block-private histograms in shared memory.
+__global__ void __launch_bounds__(256) jaccard_counts_kernel(const uint8_t* __restrict__ pred, const uint8_t* __restrict__ gt, long long n_per_image, int NC,
+                                                             unsigned long long* __restrict__ counts) {
+  extern __shared__ unsigned int s_cnt[];   // [3][NC + 1]
+  const int bins = NC + 1;
+  for (int i = threadIdx.x; i < 3 * bins; i += blockDim.x) s_cnt[i] = 0u;
+  __syncthreads();
+  const uint8_t* p = pred + static_cast<long long>(blockIdx.y) * n_per_image;
+  const uint8_t* g = gt + static_cast<long long>(blockIdx.y) * n_per_image;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_per_image; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int t = g[i], q = p[i];
+    if (t <= NC) atomicAdd(&s_cnt[bins + t], 1u);
+    if (q <= NC) atomicAdd(&s_cnt[2 * bins + q], 1u);
+    if (t == q && t <= NC) atomicAdd(&s_cnt[t], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * bins; i += blockDim.x)
+    if (s_cnt[i]) atomicAdd(&counts[static_cast<long long>(blockIdx.y) * 3 * bins + i], static_cast<unsigned long long>(s_cnt[i]));
+}
+
 }  // namespace dlv3p

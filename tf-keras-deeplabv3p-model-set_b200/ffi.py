@@ -74,6 +74,7 @@ SYMBOLS = [
     ('dlv3p_op_resize_argmax', _i, [_i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     ('dlv3p_op_time', _i, [_i, _i, C.POINTER(C.c_int64), _i, _i, _i, _fp]),
     ('dlv3p_op_confusion_matrix', _i, [_i, _vp, _vp, C.c_int64, _i, _vp, _vp]),
+    ('dlv3p_op_jaccard_counts', _i, [_i, _vp, _vp, _i, C.c_int64, _i, _vp, _vp]),
     ('dlv3p_op_normalize_image', _i, [_i, _vp, C.c_int64, _vp, _i, _vp]),
     ('dlv3p_op_denormalize_image', _i, [_i, _vp, C.c_int64, _vp, _vp]),
     ('dlv3p_op_mask_resize_nearest', _i, [_i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
