@@ -76,6 +76,12 @@ int dlv3p_train_resize_bwd(int device, const void* dy_bf16, int64_t ld_dy, int B
 size_t dlv3p_train_loss_scratch_bytes(void);
 int dlv3p_train_softmax_ce(int device, const float* logits, int64_t ldl, const float* bias, const uint8_t* labels, int B, int NC, int hi, int wi,
                            int H, int W, int ignore_index, float inv_norm, float* d_full, float* d_loss, void* d_scratch, void* cuda_stream);
+/* The same with the reference's other two losses (train.py:114-138): kind 0 = dlv3p_train_softmax_ce; kind 1 =
+ * WeightedSparseCategoricalCrossEntropy (loss.py:159-192: -w[label] * log p, device class weights [NC], no clip); kind 2 =
+ * SparseSoftmaxFocalLoss (loss.py:60-118: -alpha * (1-p)^gamma * log(clip(p, 1e-15)); reference defaults gamma 2, alpha 0.25). */
+int dlv3p_train_softmax_loss(int device, const float* logits, int64_t ldl, const float* bias, const uint8_t* labels, int B, int NC, int hi, int wi,
+                             int H, int W, int ignore_index, float inv_norm, int kind, const float* d_class_weights, float focal_gamma,
+                             float focal_alpha, float* d_full, float* d_loss, void* d_scratch, void* cuda_stream);
 /* adjoint of pred_resize: planar fp32 [B,NC,H,W] -> bf16 rows [B*hi*wi, ld_dx] (columns >= NC untouched).  With d_scratch
  * (dlv3p_train_resize_bwd_planar_scratch_bytes(B, NC, hi, W) bytes) the adjoint runs as two separable passes; NULL = one pass. */
 size_t dlv3p_train_resize_bwd_planar_scratch_bytes(int B, int NC, int hi, int W);

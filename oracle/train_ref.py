@@ -39,7 +39,8 @@ def _trainable(key: Key) -> bool:
 
 def head_train_forward_backward(feat: np.ndarray, skip: np.ndarray, labels: np.ndarray, W: Dict[Key, np.ndarray], cfg: R.HeadConfig,
                                 keep_mask: Optional[np.ndarray] = None, drop_rate: float = 0.5, ignore_index: int = 255,
-                                dtype=None, mode: str = 'fp32'):
+                                dtype=None, mode: str = 'fp32', loss: str = 'crossentropy', class_weights=None, focal_gamma: float = 2.0,
+                                focal_alpha: float = 0.25):
     """feat [B,h,w,Cin], skip [B,hs,ws,Cs] fp32 NHWC (the GLOBAL batch), labels uint8 [B,H,W].  keep_mask: bool [B*h*w*256]
     Dropout keep mask in NHWC element order (None = no dropout).  Returns dict with
       loss (float, mean over every pixel of the batch, without the l2 term), grads {(layer,var): array in Keras layout},
@@ -123,7 +124,14 @@ def head_train_forward_backward(feat: np.ndarray, skip: np.ndarray, labels: np.n
     lab = torch.tensor(np.asarray(labels).astype(np.int64))
     valid = (lab != ignore_index) & (lab < cfg.NC)
     p_lab = prob.gather(1, lab.clamp(max=cfg.NC - 1).unsqueeze(1)).squeeze(1)
-    px = -torch.log(p_lab.clamp(CLIP, 1.0 - CLIP)) * valid.to(dt)
+    if loss == 'focal':                                            # SparseSoftmaxFocalLoss, loss.py:60-118 (class weights ignored, train.py:131-135)
+        pc = p_lab.clamp(1e-15, 1.0 - 1e-15)
+        px = focal_alpha * torch.pow(1.0 - pc, focal_gamma) * (-torch.log(pc)) * valid.to(dt)
+    elif class_weights is not None:                                # WeightedSparseCategoricalCrossEntropy, loss.py:159-192 (no clip)
+        wv = torch.tensor(np.asarray(class_weights), dtype=dt)[lab.clamp(max=cfg.NC - 1)]
+        px = -torch.log(p_lab) * wv * valid.to(dt)
+    else:                                                          # SparseCategoricalCrossEntropy, loss.py:121-156
+        px = -torch.log(p_lab.clamp(CLIP, 1.0 - CLIP)) * valid.to(dt)
     loss = px.sum() / float(cfg.B * cfg.H * cfg.W)
     loss.backward()
     grads = {k: v.grad.numpy().copy() for k, v in P.items() if v.requires_grad and v.grad is not None}

@@ -268,6 +268,47 @@ def test_loss_and_its_gradient(gpu, B, NC, hi, wi, H, W):
     assert float(dlow[:, NC:].abs().max()) == 0.0 if NCp > NC else True
 
 
+@pytest.mark.parametrize('kind', [1, 2])
+def test_weighted_and_focal_losses(gpu, kind):
+    """WeightedSparseCategoricalCrossEntropy (loss.py:159-192) and SparseSoftmaxFocalLoss (loss.py:60-118) and their gradients vs autograd."""
+    torch = _t()
+    from dlv3p_b200 import train_ffi
+    F = torch.nn.functional
+    B, NC, hi, wi, H, W = 2, 21, 16, 16, 64, 64
+    g = torch.Generator(device='cuda').manual_seed(kind)
+    NCp = 24
+    logits = torch.zeros(B * hi * wi, NCp, device='cuda')
+    logits[:, :NC] = torch.randn(B * hi * wi, NC, device='cuda', generator=g) * 3
+    bias = torch.randn(NC, device='cuda', generator=g) * 0.1
+    cw = torch.rand(NC, device='cuda', generator=g) * 2 + 0.1
+    rng = np.random.default_rng(kind)
+    lab = rng.integers(0, NC, size=(B, H, W)).astype(np.uint8)
+    lab[rng.random(lab.shape) < 0.1] = 255
+    labels = torch.from_numpy(lab).cuda()
+    inv_norm = 1.0 / (B * H * W)
+    dfull = torch.zeros(B, NC, H, W, device='cuda')
+    loss = torch.zeros(2, device='cuda')
+    scratch = torch.zeros(train_ffi.loss_scratch_bytes() // 4 + 16, device='cuda')
+    _call('dlv3p_train_softmax_loss', logits.data_ptr(), NCp, bias.data_ptr(), labels.data_ptr(), B, NC, hi, wi, H, W, 255, inv_norm, kind, cw.data_ptr(), 2.0, 0.25,
+          dfull.data_ptr(), loss.data_ptr(), scratch.data_ptr())
+    torch.cuda.synchronize()
+    zr = logits[:, :NC].double().reshape(B, hi, wi, NC).permute(0, 3, 1, 2)
+    full = (F.interpolate(zr + bias.double().view(1, NC, 1, 1), size=(H, W), mode='bilinear', align_corners=False)).requires_grad_(True)
+    prob = torch.softmax(full, dim=1)
+    lt = torch.from_numpy(lab.astype(np.int64)).cuda()
+    valid = lt != 255
+    pl = prob.gather(1, lt.clamp(max=NC - 1).unsqueeze(1)).squeeze(1)
+    if kind == 1:
+        px = -torch.log(pl) * cw.double()[lt.clamp(max=NC - 1)]
+    else:
+        pc = pl.clamp(1e-15, 1 - 1e-15)
+        px = 0.25 * (1 - pc) ** 2.0 * (-torch.log(pc))
+    ref_loss = (px * valid).sum() * inv_norm
+    ref_loss.backward()
+    assert abs(float(loss[0]) - float(ref_loss)) <= 2e-4 * abs(float(ref_loss))
+    assert float((dfull.double() - full.grad).abs().max()) <= 2e-4 * float(full.grad.abs().max())      # fp32 with fast exp / log / pow
+
+
 # ---------------------------------------------------------------------------------------------------- small operators
 def test_pool_broadcast_add_dropout_sgd_cast(gpu):
     torch = _t()

@@ -113,3 +113,20 @@ def test_dropout_mask_restatement():
     m2 = train_ffi.dropout_keep_mask(1 << 16, dropout_seed(3, 0, 1), 0.5)
     assert (m != m2).mean() > 0.4                                   # replicas draw different masks
     assert train_ffi.dropout_keep_mask(64, 1, 0.0).all()
+
+
+@pytest.mark.parametrize('kw', [dict(loss='focal'), dict(class_weights=[0.5, 2.0, 1.0, 0.1, 3.0])])
+def test_oracle_loss_variants_match_finite_differences(kw):
+    """The focal and the class-weighted losses of the reference (loss.py:60-118, :159-192) through the same oracle."""
+    import torch
+    cfg, W, feat, skip, labels = _tiny()
+    W64 = {k: np.asarray(v, np.float64) for k, v in W.items()}
+    run = lambda Wp: TR.head_train_forward_backward(feat.astype(np.float64), skip.astype(np.float64), labels, Wp, cfg, dtype=torch.float64, **kw)
+    out = run(W64)
+    key, idx, eps = ('conv_upsample', 'kernel'), (0, 0, 3, 2), 1e-5
+    Wp, Wm = dict(W64), dict(W64)
+    Wp[key] = W64[key].copy(); Wp[key][idx] += eps
+    Wm[key] = W64[key].copy(); Wm[key][idx] -= eps
+    fd = (run(Wp)['loss'] - run(Wm)['loss']) / (2 * eps)
+    assert abs(fd - out['grads'][key][idx]) <= 1e-7 + 1e-4 * abs(fd)
+    assert out['loss'] != TR.head_train_forward_backward(feat.astype(np.float64), skip.astype(np.float64), labels, W64, cfg, dtype=torch.float64)['loss']

@@ -305,18 +305,21 @@ int dlv3p_train_resize_bwd(int device, const void* dy, int64_t ld_dy, int B, int
 namespace { constexpr int kLossBlocks = 148 * 8; }
 size_t dlv3p_train_loss_scratch_bytes(void) { return static_cast<size_t>(kLossBlocks) * 2 * sizeof(float); }
 
-int dlv3p_train_softmax_ce(int device, const float* logits, int64_t ldl, const float* bias, const uint8_t* labels, int B, int NC, int hi, int wi, int H, int W_,
-                           int ignore_index, float inv_norm, float* d_full, float* d_loss, void* d_scratch, void* cuda_stream) {
+int dlv3p_train_softmax_loss(int device, const float* logits, int64_t ldl, const float* bias, const uint8_t* labels, int B, int NC, int hi, int wi, int H, int W_,
+                             int ignore_index, float inv_norm, int kind, const float* d_class_weights, float focal_gamma, float focal_alpha, float* d_full,
+                             float* d_loss, void* d_scratch, void* cuda_stream) {
   int sms = 0, r = train_prolog(device, &sms);
   if (r) return r;
-  if (!logits || !bias || !labels || !d_full || !d_loss || !d_scratch || B < 1 || NC < 1 || NC > 256 || hi < 1 || wi < 1 || H < 1 || W_ < 1 || ldl < NC)
-    return fail(nullptr, DLV3P_ERR_INVALID, "train_softmax_ce: bad arguments");
+  if (!logits || !bias || !labels || !d_full || !d_loss || !d_scratch || B < 1 || NC < 1 || NC > 256 || hi < 1 || wi < 1 || H < 1 || W_ < 1 || ldl < NC ||
+      kind < 0 || kind > 2 || (kind == 1 && !d_class_weights))
+    return fail(nullptr, DLV3P_ERR_INVALID, "train_softmax_loss: bad arguments (kind 0 CE, 1 weighted CE + class weights, 2 focal)");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   LossParams P{};
   P.logits = logits; P.bias = bias; P.labels = labels; P.d_full = d_full; P.block_part = static_cast<float*>(d_scratch); P.ldl = ldl;
   P.B = B; P.NC = NC; P.hi = hi; P.wi = wi; P.H = H; P.W = W_; P.ignore = ignore_index;
   P.sy = static_cast<float>(hi) / static_cast<float>(H); P.sx = static_cast<float>(wi) / static_cast<float>(W_);
   P.inv_norm = inv_norm;
+  P.kind = kind; P.class_w = d_class_weights; P.gamma = focal_gamma; P.alpha = focal_alpha;
   const size_t total = static_cast<size_t>(B) * H * W_;
   int grid = static_cast<int>((total + 255) / 256);
   if (grid > kLossBlocks) grid = kLossBlocks;
@@ -325,6 +328,12 @@ int dlv3p_train_softmax_ce(int device, const float* logits, int64_t ldl, const f
   loss_final_kernel<<<1, 256, 0, st>>>(static_cast<const float*>(d_scratch), grid, inv_norm, d_loss);
   CU_TRY(nullptr, cudaGetLastError());
   return DLV3P_OK;
+}
+
+int dlv3p_train_softmax_ce(int device, const float* logits, int64_t ldl, const float* bias, const uint8_t* labels, int B, int NC, int hi, int wi, int H, int W_,
+                           int ignore_index, float inv_norm, float* d_full, float* d_loss, void* d_scratch, void* cuda_stream) {
+  return dlv3p_train_softmax_loss(device, logits, ldl, bias, labels, B, NC, hi, wi, H, W_, ignore_index, inv_norm, 0, nullptr, 0.0f, 0.0f, d_full, d_loss, d_scratch,
+                                  cuda_stream);
 }
 
 size_t dlv3p_train_resize_bwd_planar_scratch_bytes(int B, int NC, int hi, int W_) {

@@ -361,7 +361,32 @@ struct LossParams {
   long long ldl;
   int B, NC, hi, wi, H, W, ignore;
   float sy, sx, inv_norm;
+  int kind;                 // 0 SparseCategoricalCrossEntropy (loss.py:121-156) | 1 Weighted... (:159-192) | 2 SparseSoftmaxFocalLoss (:60-118)
+  const float* class_w;     // kind 1: per-class weights [NC]
+  float gamma, alpha;       // kind 2
 };
+// per-pixel loss value and the scalar S with d(loss)/d(logit_k) = S * (p_k - [k == label]) for the three losses of the reference
+// (all are functions of the label's probability p only):
+//   CE        -log(clip(p, 1e-7, 1-1e-7))                      S = 1 (0 where the clip is active)
+//   weighted  -w[label] * log(p)                               S = w[label]
+//   focal     -alpha * (1-p)^gamma * log(clip(p, 1e-15, .))    S = alpha * ((1-p)^gamma - gamma * (1-p)^(gamma-1) * p * log(p))
+__device__ __forceinline__ void loss_terms(const LossParams& P, float pl, int label, float& loss_px, float& S) {
+  if (P.kind == 1) {
+    const float w = __ldg(P.class_w + label);
+    loss_px = -w * __logf(fmaxf(pl, 1.0e-37f));
+    S = w;
+  } else if (P.kind == 2) {
+    const bool clipped = pl < 1e-15f;
+    const float p = fmaxf(pl, 1e-15f), q = 1.0f - p, lg = __logf(p);
+    const float qg = __powf(q, P.gamma);
+    loss_px = -P.alpha * qg * lg;
+    S = clipped ? 0.0f : P.alpha * (qg - P.gamma * __powf(q, P.gamma - 1.0f) * p * lg);
+  } else {
+    const bool clipped = pl < 1e-7f || pl > 1.0f - 1e-7f;
+    loss_px = -__logf(fminf(fmaxf(pl, 1e-7f), 1.0f - 1e-7f));
+    S = clipped ? 0.0f : 1.0f;
+  }
+}
 __device__ __forceinline__ float interp_logit(const float* p00, const float* p01, const float* p10, const float* p11, int c, float tx, float ty, float bias) {
   const float tl = __ldg(p00 + c), tr = __ldg(p01 + c), bl = __ldg(p10 + c), br = __ldg(p11 + c);
   const float top = lerp_nofma(tl, tr, tx), bot = lerp_nofma(bl, br, tx);
@@ -395,15 +420,16 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const LossParams P) {
     const float inv_s = 1.0f / s;
     float pl = 1.0f;
     if (valid) pl = __expf(interp_logit(p00, p01, p10, p11, label, tx, ty, __ldg(P.bias + label)) - m) * inv_s;
-    const bool clipped = pl < 1e-7f || pl > 1.0f - 1e-7f;
-    const float gscale = (valid && !clipped) ? P.inv_norm : 0.0f;
+    float loss_px = 0.0f, S = 0.0f;
+    if (valid) loss_terms(P, pl, label, loss_px, S);
+    const float gscale = S * P.inv_norm;
     float* d = P.d_full + static_cast<long long>(b) * P.NC * plane + static_cast<long long>(Y) * P.W + X;
     for (int c = 0; c < P.NC; ++c) {
       const float p = __expf(interp_logit(p00, p01, p10, p11, c, tx, ty, __ldg(P.bias + c)) - m) * inv_s;
       d[c * plane] = (p - (c == label ? 1.0f : 0.0f)) * gscale;
     }
     if (valid) {
-      loss_acc -= __logf(fminf(fmaxf(pl, 1e-7f), 1.0f - 1e-7f));
+      loss_acc += loss_px;
       cnt_acc += 1.0f;
     }
   }
@@ -480,14 +506,15 @@ __global__ void __launch_bounds__(256) softmax_ce_small_kernel(const LossParams 
 #pragma unroll
     for (int c = 0; c < 32; ++c)
       if (valid && c == label) pl = z[c] * inv_s;
-    const bool clipped = pl < 1e-7f || pl > 1.0f - 1e-7f;
-    const float gscale = (valid && !clipped) ? P.inv_norm : 0.0f;
+    float loss_px = 0.0f, S = 0.0f;
+    if (valid) loss_terms(P, pl, label, loss_px, S);
+    const float gscale = S * P.inv_norm;
     float* d = P.d_full + static_cast<long long>(b) * P.NC * plane + static_cast<long long>(Y) * P.W + X;
 #pragma unroll
     for (int c = 0; c < 32; ++c)
       if (c < P.NC) d[c * plane] = (z[c] * inv_s - (c == label ? 1.0f : 0.0f)) * gscale;
     if (valid) {
-      loss_acc -= __logf(fminf(fmaxf(pl, 1e-7f), 1.0f - 1e-7f));
+      loss_acc += loss_px;
       cnt_acc += 1.0f;
     }
   }

@@ -131,7 +131,8 @@ class HeadTrainer(TrainLayout):
     def __init__(self, B: int, H: int, W: int, OS: int, Cin: int, Cskip: int, NC: int, weights: Dict[Tuple[str, str], np.ndarray],
                  device: int = 0, lr: float = 1e-2, momentum: float = 0.9, l2: float = L2_COEF, bn_momentum: float = BN_MOMENTUM,
                  eps: float = 1e-5, dropout: float = 0.5, seed: int = 0, ignore_index: int = 255, global_batch: Optional[int] = None,
-                 process_group=None, graph: bool = True, wgrad_tn: bool = True):
+                 process_group=None, graph: bool = True, wgrad_tn: bool = True, loss: str = 'crossentropy', class_weights=None,
+                 focal_gamma: float = 2.0, focal_alpha: float = 0.25):
         import torch
         import torch.distributed as dist
         self.torch = torch
@@ -160,6 +161,14 @@ class HeadTrainer(TrainLayout):
         self.launches = 0
         self.debug_taps = None          # set to {} to snapshot intermediate gradients (diagnostics / tests)
         self.use_graph, self.wgrad_tn = graph, wgrad_tn
+        # train.py:114-138: --loss crossentropy (optionally class weighted, --weighted_type balanced) | focal (ignores the weights)
+        if loss not in ('crossentropy', 'focal'):
+            raise ValueError('invalid loss type {}'.format(loss))
+        self.loss_kind = 2 if loss == 'focal' else (1 if class_weights is not None else 0)
+        self.focal_gamma, self.focal_alpha = focal_gamma, focal_alpha
+        self._class_weights = None if class_weights is None else np.asarray(class_weights, np.float32).reshape(-1)
+        if self._class_weights is not None and self._class_weights.size != NC:
+            raise ValueError('class_weights must have one entry per class')
         self.graph_error_mode = 'global' if self.world == 1 else 'thread_local'   # NCCL's watchdog thread polls events during capture
         self._graph = None
         self._static_in = None
@@ -192,6 +201,7 @@ class HeadTrainer(TrainLayout):
         T['logits'] = z(M2, NCp, dtype=f32)
         T['dfull'] = z(B, self.NC, self.H, self.W, dtype=f32)
         T['loss'] = z(2, dtype=f32)
+        T['class_w'] = t.ones(max(self.NC, 1), dtype=f32, device=dv) if self._class_weights is None else t.from_numpy(self._class_weights).to(dv)
         T['adj_tmp'] = z(B, self.NC, self.hs, self.W, dtype=f32)      # vertical pass of the separable pred_resize adjoint
         T['bias_stats'] = z(2 * NCp + 4, dtype=f32)
         # backward
@@ -459,8 +469,8 @@ class HeadTrainer(TrainLayout):
         # ---------------- tail + loss (model.py:75-86, loss.py:121-156)
         self._conv_fwd('conv_upsample', P(T['y1']), 256, M2, P(T['logits']), NCp, 1)
         inv_norm = 1.0 / (float(self.global_batch) * self.H * self.W)
-        self._call('dlv3p_train_softmax_ce', P(T['logits']), NCp, self._wp(self.params, ('conv_upsample', 'bias')), P(labels), B, NC, hs, ws, self.H, self.W,
-                   self.ignore, inv_norm, P(T['dfull']), P(T['loss']), P(T['loss_scratch']))
+        self._call('dlv3p_train_softmax_loss', P(T['logits']), NCp, self._wp(self.params, ('conv_upsample', 'bias')), P(labels), B, NC, hs, ws, self.H, self.W,
+                   self.ignore, inv_norm, self.loss_kind, P(T['class_w']), self.focal_gamma, self.focal_alpha, P(T['dfull']), P(T['loss']), P(T['loss_scratch']))
         # ================ backward
         self._call('dlv3p_train_resize_bwd_planar', P(T['dfull']), B, NC, hs, ws, self.H, self.W, P(T['dlow']), NCp, P(T['adj_tmp']))
         # d(bias) = column sums of d(logits): the banded two-stage statistics kernel (sum x | sum x^2 | n), first NCp entries

@@ -26,6 +26,7 @@ SYMBOLS = [
     ('dlv3p_train_resize_bwd', _i, [_i, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     ('dlv3p_train_loss_scratch_bytes', _sz, []),
     ('dlv3p_train_softmax_ce', _i, [_i, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
+    ('dlv3p_train_softmax_loss', _i, [_i, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp, _f, _f, _vp, _vp, _vp, _vp]),
     ('dlv3p_train_resize_bwd_planar_scratch_bytes', _sz, [_i, _i, _i, _i]),
     ('dlv3p_train_resize_bwd_planar', _i, [_i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i64, _vp, _vp]),
     ('dlv3p_train_rows_reduce', _i, [_i, _vp, _i64, _i, _i, _i, _f, _vp, _i, _vp]),
