@@ -303,9 +303,13 @@ class HeadTrainer(TrainLayout):
     def _s(self):
         return self.torch.cuda.current_stream(self.tdev).cuda_stream
 
+    # kernels behind one entry point (two-stage reductions launch a partial and a final kernel)
+    _KERNELS_PER_CALL = {'dlv3p_op_bn_stats': 2, 'dlv3p_train_bn_bwd_stats': 2, 'dlv3p_train_depthwise_wgrad': 2, 'dlv3p_train_softmax_loss': 2,
+                         'dlv3p_train_softmax_ce': 2, 'dlv3p_train_resize_bwd_planar': 2}
+
     def _call(self, name, *args):
         tf_.call(name, self.dev, *args, self._s())
-        self.launches += 1
+        self.launches += self._KERNELS_PER_CALL.get(name, 1)
 
     @staticmethod
     def _p(tensor, off_elems: int = 0) -> int:
@@ -327,6 +331,7 @@ class HeadTrainer(TrainLayout):
 
     def _gemm(self, a, lda, b, ldb, M, N, K, d, ldd, out_fp32=0, splits=1):
         self._call('dlv3p_train_gemm_nt', a, lda, b, ldb, M, N, K, d, ldd, out_fp32, splits, self._p(self.T['partial']))
+        self.launches += 1 if splits > 1 else 0          # the split-K reduction
 
     def _conv_fwd(self, name, x_ptr, ldx, M, out_ptr, ldo, out_fp32=0):
         _, (K, N) = self.off[(name, 'kernel')]
@@ -346,6 +351,7 @@ class HeadTrainer(TrainLayout):
         splits = max(1, min(kblocks, self.sms // tiles, (T['partial'].numel()) // max(1, K * N)))
         if self.wgrad_tn:
             self._call('dlv3p_train_gemm_tn', x_ptr, ldx, dy_ptr, ld_dy, K, N, M, self._wp(self.grads, (name, 'kernel')), N, 1, splits, self._p(T['partial']))
+            self.launches += 1 if splits > 1 else 0      # the split-K reduction
         else:   # A/B path: explicit transposes + the K-major kernel
             self._call('dlv3p_train_transpose', x_ptr, M, K, ldx, self._p(T['xT']), M)
             self._call('dlv3p_train_transpose', dy_ptr, M, N, ld_dy, self._p(T['dyT']), M)
