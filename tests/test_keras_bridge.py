@@ -131,3 +131,47 @@ def test_head_weights_and_load_into_round_trip():
         kb.load_into(model, {('aspp0', 'kernel'): np.zeros((1, 1, 3, 3), np.float32)})
     with pytest.raises(KeyError):
         kb.load_into(model, {('no_such_layer', 'kernel'): np.zeros((1,), np.float32)})
+
+
+class _H5Dataset:
+    """h5py.Dataset stand-in: `ds[()]` returns the array."""
+
+    def __init__(self, a):
+        self._a, self.shape = np.asarray(a), np.asarray(a).shape
+
+    def __getitem__(self, idx):
+        return self._a
+
+
+def _h5_tree(cfg, W, scope_twice=True, classifier='conv_upsample'):
+    """The group layout Keras writes: /<layer>/<layer>/<var>:0 (plus a backbone layer that must be ignored)."""
+    root = {}
+    for (layer, var), a in W.items():
+        name = classifier if layer == 'conv_upsample' else layer
+        g = root.setdefault(name, {})
+        if scope_twice:
+            g = g.setdefault(name, {})
+        g['%s:0' % var] = _H5Dataset(a)
+    root['entry_flow_conv1_1'] = {'entry_flow_conv1_1': {'kernel:0': _H5Dataset(np.zeros((3, 3, 3, 32), np.float32))}}
+    return root
+
+
+@pytest.mark.parametrize('scope_twice,classifier', [(True, 'conv_upsample'), (False, 'logits_semantic')])
+def test_h5_export_maps_datasets_by_layer_name(tmp_path, scope_twice, classifier):
+    """tools/h5_to_npz.py on an h5py-shaped tree (h5py itself is absent here): head datasets by name, backbone ignored, npz round trip."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location('h5_to_npz', os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools', 'h5_to_npz.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cfg = R.HeadConfig(B=1, H=128, W=128, OS=16, Cin=64, Cskip=32, NC=21)
+    W = R.make_weights(cfg, 3)
+    got = mod.head_weights_from_h5(_h5_tree(cfg, W, scope_twice, classifier))
+    assert set(got) == {'%s/%s' % k for k in W}
+    assert all(np.array_equal(got['%s/%s' % k], np.asarray(v, np.float32)) for k, v in W.items())
+    path = str(tmp_path / 'head.npz')
+    np.savez(path, **got)
+    with np.load(path) as z:
+        assert sorted(z.files) == sorted(got)
+    with pytest.raises(ValueError):
+        mod.head_weights_from_h5({'entry_flow_conv1_1': {'kernel:0': _H5Dataset(np.zeros(3))}})

@@ -239,8 +239,11 @@ class HeadTrainer(TrainLayout):
         return flat[o:o + n].view(*shape)
 
     def set_weights(self, W: Dict[Tuple[str, str], np.ndarray]) -> None:
-        """Keras-layout arrays keyed (layer, variable) — the inventory of dlv3p_weight_info / SURVEY §8(b)."""
+        """Keras-layout arrays keyed (layer, variable) or "layer/variable" (the npz of tools/h5_to_npz.py) — the inventory of
+        dlv3p_weight_info / SURVEY §8(b); `logits_semantic` is accepted for `conv_upsample`."""
         t = self.torch
+        W = {(tuple(k.split('/', 1)) if isinstance(k, str) else tuple(k)): v for k, v in W.items()}
+        W = {(('conv_upsample', k[1]) if k[0] == 'logits_semantic' else k): v for k, v in W.items()}
         host = np.zeros(self.nparams, np.float32)
 
         def put(key, arr):
