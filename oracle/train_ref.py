@@ -13,7 +13,8 @@ Reference sites restated (paths relative to /root/reference):
                              SyncBatchNormalization under MirroredStrategy = statistics of the GLOBAL batch)
   Dropout(0.5)               layers.py:161 (after concat_projection; the mask is an input here)
   loss                       deeplabv3p/loss.py:121-156 SparseCategoricalCrossEntropy(ignore_index=255) on the Softmax output:
-                             K.categorical_crossentropy clips p to [1e-7, 1-1e-7]; pixels with the ignore label contribute 0;
+                             under model.fit (graph mode) K.categorical_crossentropy sees a Softmax op and takes its logits path
+                             (softmax_cross_entropy_with_logits, no clip): -log p; pixels with the ignore label contribute 0;
                              Keras averages over ALL pixels of the global batch (train.py:143-158: per-replica sums / global batch)
   regulariser                layers.py:12-21 l2(2e-5) on Conv2D kernels and biases (inert for depthwise kernels, :24-31)
   optimizer                  common/model_utils.py:122-123 SGD(momentum=0.9, nesterov=False): v <- m v - lr g ; w <- w + v
@@ -28,7 +29,6 @@ from . import head_ref as R
 
 L2_COEF = 2e-5
 BN_MOMENTUM = 0.99
-CLIP = 1e-7
 
 Key = Tuple[str, str]
 
@@ -131,7 +131,7 @@ def head_train_forward_backward(feat: np.ndarray, skip: np.ndarray, labels: np.n
         wv = torch.tensor(np.asarray(class_weights), dtype=dt)[lab.clamp(max=cfg.NC - 1)]
         px = -torch.log(p_lab) * wv * valid.to(dt)
     else:                                                          # SparseCategoricalCrossEntropy, loss.py:121-156
-        px = -torch.log(p_lab.clamp(CLIP, 1.0 - CLIP)) * valid.to(dt)
+        px = -torch.log(p_lab.clamp_min(1e-37)) * valid.to(dt)
     loss = px.sum() / float(cfg.B * cfg.H * cfg.W)
     loss.backward()
     grads = {k: v.grad.numpy().copy() for k, v in P.items() if v.requires_grad and v.grad is not None}

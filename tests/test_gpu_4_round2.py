@@ -1,0 +1,209 @@
+"""GPU parity tests added in round 2 (VERDICT r01 "what's weak" 1-3): the configurations the first round never compared with the
+oracle at their real sizes, the CUDA-graph replay against the eager step, the data-parallel exchange on ONE GPU (two processes
+over gloo, so the single-GPU driver box exercises it), weight refresh through the host pipeline, and the north star's label bar
+(>= 99.9 % of ALL pixels) for the configurations that meet it."""
+import os
+
+import numpy as np
+import pytest
+
+from dlv3p_b200 import ffi
+from oracle import head_ref as R
+from oracle import train_ref as TR
+from tests.common import label_agreement, make_head, planar_to_nhwc, rel_err
+from tests.test_gpu_3_train import _bf, _compare_step, _free_port, _step_case, _t
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 1e-2
+
+
+# ---------------------------------------------------------------------------------------------------- cfg 3 at its real size
+def test_cfg3_cityscapes_os8_full_size(gpu):
+    """BASELINE configs[2] at the real 1024x2048 (128x256 map, rates 12/24/36: the gather kernel with 2016 tensor maps), one image
+    against the oracle, then batch independence at the real batch of 8."""
+    cfg = R.HeadConfig(B=1, H=1024, W=2048, OS=8, Cin=2048, Cskip=256, NC=19)
+    W = R.make_weights(cfg, 77)
+    feat, skip = R.make_inputs(cfg, 79)
+    hd = make_head(cfg, W)
+    labels = hd(feat, skip)
+    logits = planar_to_nhwc(hd.tap('logits'))
+    o32 = R.head_forward_torch(feat, skip, W, cfg, 'fp32')
+    o16 = R.head_forward_torch(feat, skip, W, cfg, 'bf16')
+    assert rel_err(logits, o32['logits'].numpy()) < LOGIT_TOL
+    assert rel_err(logits, o16['logits'].numpy()) < 8e-3
+    overall, decided, worst = label_agreement(labels, o16['labels'].numpy(), o16['logits_full'].numpy(), LOGIT_TOL)
+    o32_overall = float((labels == o32['labels'].numpy()).mean())
+    print('cfg3 1024x2048: label agreement vs bf16-mode oracle %.5f (decided pixels %.5f, worst mismatch margin %.4f); vs fp32 oracle %.5f'
+          % (overall, decided, worst, o32_overall))
+    assert decided >= 0.999 and worst < LOGIT_TOL
+    assert overall >= 0.998, overall          # measured 0.9983 in round 1 at 256x512: thin margins under random weights
+    hd.close()
+    # batch independence at B = 8: slots holding the same image give the same labels as the single-image run
+    cfg8 = R.HeadConfig(B=8, H=1024, W=2048, OS=8, Cin=2048, Cskip=256, NC=19)
+    hd8 = make_head(cfg8, W)
+    f8 = np.ascontiguousarray(np.broadcast_to(ffi.f32_to_bf16_bits(feat), (8,) + feat.shape[1:]))
+    s8 = np.ascontiguousarray(np.broadcast_to(ffi.f32_to_bf16_bits(skip), (8,) + skip.shape[1:]))
+    out8 = hd8(f8, s8)
+    for b in range(8):
+        assert np.array_equal(out8[b], labels[0]), 'batch slot %d differs from the single-image run' % b
+    hd8.close()
+
+
+# ---------------------------------------------------------------------------------------------------- label bar of the north star
+@pytest.mark.parametrize('name,kw,relu_feat', [
+    ('cfg1', dict(B=1, H=512, W=512, OS=16, Cin=320, Cskip=24, NC=21), False),
+    ('cfg2', dict(B=2, H=512, W=512, OS=16, Cin=2048, Cskip=256, NC=21), True),
+    ('cfg4a', dict(B=2, H=512, W=512, OS=16, Cin=160, Cskip=24, NC=21, lite=True, decoder=False), False),
+    ('cfg4b', dict(B=2, H=512, W=512, OS=16, Cin=160, Cskip=24, NC=21, lite=True, decoder=True), False),
+])
+def test_overall_label_agreement_meets_the_north_star(gpu, name, kw, relu_feat):
+    """north_star: 'argmax label maps must agree on at least 99.9 % of pixels' — asserted over ALL pixels (no margin filter)
+    against the oracle with the same rounding points, for every BASELINE configuration that meets it."""
+    cfg = R.HeadConfig(**kw)
+    W = R.make_weights(cfg, 1234)
+    feat, skip = R.make_inputs(cfg, 1236, relu_feat=relu_feat)
+    hd = make_head(cfg, W)
+    labels = hd(feat, skip)
+    o16 = R.head_forward_torch(feat, skip, W, cfg, 'bf16')
+    agree = float((labels == o16['labels'].numpy()).mean())
+    print('%s: overall label agreement %.5f' % (name, agree))
+    assert agree >= 0.999, '%s: %.5f' % (name, agree)
+    hd.close()
+
+
+# ---------------------------------------------------------------------------------------------------- weight refresh
+def test_weight_refresh_reaches_the_host_pipeline(gpu):
+    """set_weights(W1); predict_host; set_weights(W2); predict_host must equal the device forward with W2: dlv3p_forward_host's
+    sub-batch contexts are rebuilt when the parent's weights change; repeated refreshes do not grow the workspace."""
+    cfg = R.HeadConfig(B=8, H=128, W=128, OS=16, Cin=256, Cskip=64, NC=21)
+    W1, W2 = R.make_weights(cfg, 11), R.make_weights(cfg, 12)
+    feat, skip = R.make_inputs(cfg, 13)
+    hd = make_head(cfg, W1)
+    a1 = hd.predict_host(feat, skip)
+    ws0 = hd.ctx.workspace_bytes()
+    hd.set_weights(W2)
+    b2 = hd.predict_host(feat, skip)
+    d2 = hd(feat, skip)
+    assert np.array_equal(b2, d2)
+    assert not np.array_equal(a1, b2)
+    fresh = make_head(cfg, W2)
+    assert np.array_equal(fresh(feat, skip), d2)
+    for _ in range(3):
+        hd.set_weights(W1)
+    assert hd.ctx.workspace_bytes() == ws0
+    assert np.array_equal(hd.predict_host(feat, skip), a1)
+    with pytest.raises(ValueError):
+        hd.predict_host(feat[:4], skip[:4])                      # partial batch: ValueError, not an out-of-bounds copy
+    with pytest.raises(ValueError):
+        hd.predict_host(feat, skip, out=np.empty((8, 128, 128), np.int32))
+    hd.close(); fresh.close()
+
+
+# ---------------------------------------------------------------------------------------------------- cfg 5 at its real shapes
+def test_cfg5_training_step_at_the_benchmarked_shapes(gpu):
+    """The whole training step at the shapes bench.py times (Cin 2048, Cskip 256, 512x512: split-K weight gradients over 8192 /
+    131072 pixels, the 32x32 band kernels) against the oracle in bf16 mode; two images keep the CPU autograd run to a minute."""
+    torch = _t()
+    from dlv3p_b200 import train, train_ffi
+    cfg = R.HeadConfig(B=2, H=512, W=512, OS=16, Cin=2048, Cskip=256, NC=21)
+    W = R.make_weights(cfg, 51)
+    feat, skip = R.make_inputs(cfg, 52)
+    feat, skip = R.bf16_round(feat), R.bf16_round(skip)
+    labels = TR.make_labels(cfg, 53)
+    tr = train.HeadTrainer(cfg.B, cfg.H, cfg.W, cfg.OS, cfg.Cin, cfg.Cskip, cfg.NC, W, device=0, seed=6, graph=False)
+    f, s, l = _bf(feat), _bf(skip), torch.from_numpy(labels).cuda()
+    tr.forward_backward(f, s, l)
+    torch.cuda.synchronize()
+    keep = train_ffi.dropout_keep_mask(cfg.B * cfg.h * cfg.w * 256, train.dropout_seed(6, 0, 0), 0.5)
+    ref = TR.head_train_forward_backward(feat, skip, labels, W, cfg, keep_mask=keep, mode='bf16')
+    _compare_step(tr.get_grads(), tr.T['dfeat'].float().cpu().numpy(), tr.T['dskip'].float().cpu().numpy(), tr.loss(), ref, cfg)
+
+
+# ---------------------------------------------------------------------------------------------------- CUDA graph == eager
+def test_cuda_graph_replay_equals_the_eager_step(gpu):
+    """Every benchmark number of the training step is the CUDA-graph path: after 3 steps (eager, capture, replay) the weights, the
+    moving statistics and the loss must equal those of a trainer that launches every kernel eagerly, bit for bit."""
+    torch = _t()
+    from dlv3p_b200 import train
+    cfg, W, feat, skip, labels = _step_case(B=2, seed=61)
+    f, s, l = _bf(feat), _bf(skip), torch.from_numpy(labels).cuda()
+    out = []
+    for graph in (False, True):
+        tr = train.HeadTrainer(cfg.B, cfg.H, cfg.W, cfg.OS, cfg.Cin, cfg.Cskip, cfg.NC, W, device=0, seed=7, lr=0.05, graph=graph)
+        losses = []
+        for step in range(4):
+            if step == 3:
+                tr.lr = 0.02           # a learning-rate schedule step: the captured graph is dropped and re-captured with the new value
+            tr.train_step(f, s, l)
+            losses.append(tr.loss())
+        torch.cuda.synchronize()
+        out.append((losses, tr.get_weights(), tr.velocity.cpu().numpy().copy()))
+        assert (tr._graph is not None) == graph
+    (la, wa, va), (lb, wb, vb) = out
+    assert la == lb, (la, lb)
+    assert np.array_equal(va, vb)
+    for k in wa:
+        assert np.array_equal(wa[k], wb[k]), 'graph replay and eager step disagree on %s' % (k,)
+
+
+# ---------------------------------------------------------------------------------------------------- world size 2 on ONE GPU
+def _one_gpu_worker(rank, world, port, q):
+    try:
+        import torch
+        import torch.distributed as dist
+        from dlv3p_b200 import train
+        os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+        torch.cuda.set_device(0)
+        dist.init_process_group('gloo', rank=rank, world_size=world)
+        cfg, W, feat, skip, labels = _step_case(B=2 * world, seed=44)
+        Bl = cfg.B // world
+        sl = slice(rank * Bl, (rank + 1) * Bl)
+        # exactly _ddp_worker_body of test_gpu_3_train.py, with both replicas on cuda:0 and gloo carrying the CUDA tensors
+        tr = train.HeadTrainer(Bl, cfg.H, cfg.W, cfg.OS, cfg.Cin, cfg.Cskip, cfg.NC, W, device=0, seed=9, graph=False)
+        f = torch.from_numpy(feat[sl]).cuda().to(torch.bfloat16).contiguous()
+        s = torch.from_numpy(skip[sl]).cuda().to(torch.bfloat16).contiguous()
+        l = torch.from_numpy(labels[sl]).cuda().contiguous()
+        tr.forward_backward(f, s, l)
+        tr.all_reduce_gradients()
+        torch.cuda.synchronize()
+        grads, loss = tr.get_grads(), tr.loss()
+        tr.apply_gradients()
+        torch.cuda.synchronize()
+        q.put((rank, grads, tr.T['dfeat'].float().cpu().numpy(), tr.T['dskip'].float().cpu().numpy(), loss, tr.get_weights()))
+        dist.destroy_process_group()
+    except Exception as e:
+        import traceback
+        q.put((rank, 'ERROR', traceback.format_exc(), str(e), None, None))
+
+
+def test_data_parallel_step_two_processes_one_gpu(gpu):
+    """The data-parallel training step (SyncBN statistic exchanges + the gradient all-reduce) with world size 2 on a SINGLE GPU:
+    two processes share cuda:0, gloo carries the same spans NCCL would.  Result == the oracle on the global batch, replicas
+    bit-identical after the exchange (gradients and updated weights)."""
+    import torch.multiprocessing as mp
+    from dlv3p_b200 import train, train_ffi
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_one_gpu_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = sorted([q.get(timeout=300) for _ in ps], key=lambda t: t[0])
+    for p in ps:
+        p.join(timeout=30)
+        if p.is_alive():
+            p.terminate()
+    for g in got:
+        assert not (isinstance(g[1], str) and g[1] == 'ERROR'), g[2]
+    cfg, W, feat, skip, labels = _step_case(B=4, seed=44)
+    n_local = 2 * cfg.h * cfg.w * 256
+    keep = np.concatenate([train_ffi.dropout_keep_mask(n_local, train.dropout_seed(9, 0, r), 0.5) for r in range(2)])
+    ref = TR.head_train_forward_backward(feat, skip, labels, W, cfg, keep_mask=keep, mode='bf16')
+    d_feat = np.concatenate([g[2].reshape(2, cfg.h, cfg.w, cfg.Cin) for g in got])
+    d_skip = np.concatenate([g[3].reshape(2, cfg.hs, cfg.ws, cfg.Cskip) for g in got])
+    for k in got[0][1]:
+        assert np.array_equal(got[0][1][k], got[1][1][k]), 'replicas disagree on the gradient of %s after the all-reduce' % (k,)
+    for k in got[0][5]:
+        assert np.array_equal(got[0][5][k], got[1][5][k]), 'replicas disagree on %s after the update' % (k,)
+    _compare_step(got[0][1], d_feat, d_skip, got[0][4], ref, cfg)

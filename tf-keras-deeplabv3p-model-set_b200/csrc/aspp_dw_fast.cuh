@@ -181,114 +181,4 @@ __global__ void __maxnreg__(112) aspp_dw_fast3_kernel(const __grid_constant__ As
   }
 }
 
-template <int H, int W, int R0, int R1, int R2>
-struct AsppFastCfg {
-  static_assert(R0 % 2 == 0 && R1 % 2 == 0 && R2 % 2 == 0 && W % 2 == 0, "phase pairing needs even rates and width");
-  static constexpr int kPix = H * W;
-  static constexpr int kBoxes = (kPix + 255) / 256;                 // TMA boxes of 256 pixels x 32 channels (16 KB)
-  static constexpr int kItems0 = R0 * (R0 / 2), kItems1 = R1 * (R1 / 2), kItems2 = R2 * (R2 / 2);   // warp items (phase pairs)
-  static constexpr int kBatch1 = 2, kBatch2 = 4;                    // light items are fetched in batches
-  static constexpr int kUnits0 = kItems0, kUnits1 = (kItems1 + kBatch1 - 1) / kBatch1, kUnits2 = (kItems2 + kBatch2 - 1) / kBatch2;
-  static constexpr int kUnits = kUnits0 + kUnits1 + kUnits2;
-  static constexpr int kSmemBytes = kBoxes * 16384 + (27 * 32 + 3 * 32 + 8 * 32) * 4 + 32;
-};
-
-// grid = B * (C / 32) CTAs, block 256.  P.tmap_slab: 2D [B*H*W, C] bf16 view of x, box {32, 256}, no swizzle.
-template <int H, int W, int R0, int R1, int R2>
-__global__ void __launch_bounds__(kAsppFastThreads, 3) aspp_dw_fast_kernel(const __grid_constant__ AsppDwParams P) {
-  using Cfg = AsppFastCfg<H, W, R0, R1, R2>;
-  extern __shared__ __align__(128) uint8_t fast_smem[];
-  uint8_t* s_slab = fast_smem;
-  float* s_w = reinterpret_cast<float*>(s_slab + Cfg::kBoxes * 16384);   // [3][9][32]
-  float* s_shift = s_w + 27 * 32;                                         // [3][32]
-  float* s_red = s_shift + 3 * 32;                                        // [8][32]
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_red + 8 * 32);
-  int* s_next = reinterpret_cast<int*>(s_bar + 1);
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int hw = lane >> 4, l16 = lane & 15;
-  const int ngroups = P.C >> 5;
-  const int b = blockIdx.x / ngroups, grp = blockIdx.x - b * ngroups;   // 32-channel group
-  if (tid == 0) {
-    mbar_init(s_bar, 1);
-    fence_barrier_init();
-    *s_next = 0;
-    mbar_arrive_expect_tx(s_bar, static_cast<uint32_t>(Cfg::kBoxes) * 16384u);
-    for (int q = 0; q < Cfg::kBoxes; ++q)
-      tma_load_2d(s_slab + q * 16384, P.tmap_slab, s_bar, grp * 32, b * Cfg::kPix + q * 256, kEvictFirst);
-  }
-  for (int i = tid; i < 27 * 32; i += kAsppFastThreads) s_w[i] = __ldg(P.w + static_cast<size_t>(i >> 5) * P.C + grp * 32 + (i & 31));
-  if (tid < 3 * 32) s_shift[tid] = __ldg(P.shift + static_cast<size_t>(tid >> 5) * P.C + grp * 32 + (tid & 31));
-  __syncthreads();
-  mbar_wait(s_bar, 0);
-
-  const uint8_t* slab_lane = s_slab + l16 * 4;
-  // image-pooling partial sums: warp = 1/8 of the pixels, half-warp = every other pixel
-  {
-    float sx = 0.0f, sy = 0.0f;
-    constexpr int kPer = (Cfg::kPix + 7) / 8;
-#pragma unroll 8
-    for (int k = hw; k < kPer; k += 2) {
-      const int p = warp * kPer + k;
-      if (p < Cfg::kPix) {
-        const uint32_t v = *reinterpret_cast<const uint32_t*>(slab_lane + p * 64);
-        sx += bf16_lo(v);
-        sy += bf16_hi(v);
-      }
-    }
-    sx += __shfl_xor_sync(0xFFFFFFFFu, sx, 16);
-    sy += __shfl_xor_sync(0xFFFFFFFFu, sy, 16);
-    if (hw == 0) {
-      s_red[warp * 32 + l16 * 2] = sx;
-      s_red[warp * 32 + l16 * 2 + 1] = sy;
-    }
-  }
-
-  const bool store = !(P.debug & 1);
-  const size_t rate_stride = static_cast<size_t>(P.nchunks) * P.B * Cfg::kPix * 128;   // bytes per rate
-  uint8_t* out0 = reinterpret_cast<uint8_t*>(P.out) + (static_cast<size_t>(grp >> 1) * P.B + b) * Cfg::kPix * 128 + (grp & 1) * 64 + l16 * 4;
-  unsigned long long wt[9], sh = 0ull;
-  int cur = -1;
-  auto load_taps = [&](int ri) {
-    if (ri == cur) return;
-    cur = ri;
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const float2 v = *reinterpret_cast<const float2*>(s_w + (ri * 9 + t) * 32 + l16 * 2);
-      wt[t] = (static_cast<unsigned long long>(__float_as_uint(v.y)) << 32) | __float_as_uint(v.x);
-    }
-    const float2 s = *reinterpret_cast<const float2*>(s_shift + ri * 32 + l16 * 2);
-    sh = (static_cast<unsigned long long>(__float_as_uint(s.y)) << 32) | __float_as_uint(s.x);
-  };
-  for (;;) {
-    int u = 0;
-    if (lane == 0) u = atomicAdd(s_next, 1);
-    u = __shfl_sync(0xFFFFFFFFu, u, 0);
-    if (u >= Cfg::kUnits) break;
-    if (u < Cfg::kUnits0) {
-      load_taps(0);
-      aspp_fast_item<H, W, R0>(slab_lane, out0, u / (R0 / 2), 2 * (u % (R0 / 2)) + hw, wt, sh, store);
-    } else if (u < Cfg::kUnits0 + Cfg::kUnits1) {
-      load_taps(1);
-      const int first = (u - Cfg::kUnits0) * Cfg::kBatch1;
-#pragma unroll 1
-      for (int it = first; it < first + Cfg::kBatch1 && it < Cfg::kItems1; ++it)
-        aspp_fast_item<H, W, R1>(slab_lane, out0 + rate_stride, it / (R1 / 2), 2 * (it % (R1 / 2)) + hw, wt, sh, store);
-    } else {
-      load_taps(2);
-      const int first = (u - Cfg::kUnits0 - Cfg::kUnits1) * Cfg::kBatch2;
-#pragma unroll 1
-      for (int it = first; it < first + Cfg::kBatch2 && it < Cfg::kItems2; ++it)
-        aspp_fast_item<H, W, R2>(slab_lane, out0 + 2 * rate_stride, it / (R2 / 2), 2 * (it % (R2 / 2)) + hw, wt, sh, store);
-    }
-  }
-  __syncthreads();
-  if (tid < 32) {
-    float s = 0.0f;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) s += s_red[q * 32 + tid];
-    P.pool_partial[static_cast<size_t>(b) * P.C + grp * 32 + tid] = s;   // pool_items == 1 on this path
-  }
-}
-
 }  // namespace dlv3p

@@ -18,7 +18,6 @@
 #include <vector>
 
 #include "../../include/dlv3p.h"
-#include "dwpw_gemm.cuh"
 #include "dwpw_gemm2.cuh"
 #include "mem_kernels.cuh"
 #include "pw_gemm.cuh"
@@ -228,7 +227,7 @@ cudaError_t launch_pw_t(const PwLaunch& L, int num_sms, cudaStream_t st) {
   pw_gemm_kernel<BN><<<grid, kPwThreads, PwCfg<BN>::kSmemBytes, st>>>(L);
   return cudaGetLastError();
 }
-// CTA-pair (cta_group::2) variant for the 256-wide bf16 GEMMs; DLV3P_NO_CTA2=1 selects the 1-CTA kernel (A/B runs)
+// CTA-pair (cta_group::2) variant for the 256-wide bf16 GEMMs
 cudaError_t launch_pw2(const PwLaunch& L, int num_sms, cudaStream_t st) {
   static bool attr_done[64] = {};
   int dev = 0;
@@ -243,30 +242,11 @@ cudaError_t launch_pw2(const PwLaunch& L, int num_sms, cudaStream_t st) {
   pw_gemm2_kernel<<<grid, kPwThreads, kPw2SmemBytes, st>>>(L);
   return cudaGetLastError();
 }
-bool use_cta2() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("DLV3P_NO_CTA2");
-    v = (e && e[0] == '1') ? 0 : 1;
-  }
-  return v == 1;
-}
-
 
 // geometry-specialised ASPP depthwise kernel (aspp_dw_fast.cuh): instantiated for the feature maps the reference's
-// 512x512 configurations produce; every other geometry runs the generic slab / phase kernels
-template <int H, int W, int R0, int R1, int R2>
-cudaError_t launch_aspp_fast_t(const AsppDwParams& P, cudaStream_t st) {
-  using Cfg = AsppFastCfg<H, W, R0, R1, R2>;
-  cudaError_t e = cudaFuncSetAttribute(aspp_dw_fast_kernel<H, W, R0, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-  if (e != cudaSuccess) return e;
-  aspp_dw_fast_kernel<H, W, R0, R1, R2><<<P.B * (P.C / 32), kAsppFastThreads, Cfg::kSmemBytes, st>>>(P);
-  return cudaGetLastError();
-}
+// 512x512 configurations produce; larger / odd maps run the gather kernel, tiny or unaligned ones the slab / phase kernels
 bool aspp_fast_supported(const AsppDwParams& P) {
-  static int off = -1;
-  if (off < 0) { const char* e = getenv("DLV3P_NO_ASPP_FAST"); off = (e && e[0] == '1') ? 1 : 0; }
-  if (off || P.nrates != 3 || P.C % 32 != 0) return false;
+  if (P.nrates != 3 || P.C % 32 != 0) return false;
   // OS16 maps of 512x512 (the BASELINE configurations), 384x384, 256x256 and 128x128 inputs
   return P.h == P.w_ && (P.h == 32 || P.h == 24 || P.h == 16 || P.h == 8) && P.rates[0] == 6 && P.rates[1] == 12 && P.rates[2] == 18;
 }
@@ -274,9 +254,7 @@ bool aspp_fast_supported(const AsppDwParams& P) {
 // large / odd-sized maps: cp.async gather of phase images (aspp_dw_gather.cuh).  Fills the geometry part of the plan and the
 // batch table; returns false when a phase image does not fit the shared-memory budget (-> generic kernels).
 bool plan_aspp_gather(int h, int w, int C, const int rates[3], AsppGatherParams* G, std::vector<uint32_t>* table) {
-  static int off = -1;
-  if (off < 0) { const char* e = getenv("DLV3P_NO_ASPP_GATHER"); off = (e && e[0] == '1') ? 1 : 0; }
-  if (off || C % 32 != 0) return false;
+  if (C % 32 != 0) return false;
   table->clear();
   G->pool_slots = 0;
   for (int i = 0; i < 3; ++i) {
@@ -358,7 +336,6 @@ cudaError_t launch_aspp_fast3_t(const AsppDwParams& P, cudaStream_t st) {
   return cudaGetLastError();
 }
 cudaError_t launch_aspp_fast(const AsppDwParams& P, cudaStream_t st) {
-  if ((P.debug & 16) && P.h == 32) return launch_aspp_fast_t<32, 32, 6, 12, 18>(P, st);   // A/B: one phase image per rate
   switch (P.h) {   // one phase image for the three rates (r, 2r, 3r)
     case 32: return launch_aspp_fast3_t<32, 32, 6>(P, st);
     case 24: return launch_aspp_fast3_t<24, 24, 6>(P, st);
@@ -369,7 +346,7 @@ cudaError_t launch_aspp_fast(const AsppDwParams& P, cudaStream_t st) {
 }
 
 cudaError_t launch_pw(int BN, const PwLaunch& L, int num_sms, cudaStream_t st) {
-  if (BN == 256 && use_cta2() && !(L.debug & 8)) {
+  if (BN == 256) {
     bool all_bf16 = true;
     for (int i = 0; i < L.num_problems; ++i)   // short-K problems are store bound: the pair brings nothing there (measured)
       all_bf16 = all_bf16 && L.prob[i].epi != kEpiPlanarF32 && L.prob[i].N == 256 && L.prob[i].K >= 512;
@@ -383,21 +360,6 @@ cudaError_t launch_pw(int BN, const PwLaunch& L, int num_sms, cudaStream_t st) {
   }
 }
 
-template <int KB, int AS, int IS>
-cudaError_t launch_dwpw_t(const DwPwParams& P, int num_sms, cudaStream_t st) {
-  static bool attr_done[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!attr_done[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(dwpw_gemm_kernel<KB, AS, IS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         DwPwCfg<KB, AS, IS>::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    attr_done[dev & 63] = true;
-  }
-  const int grid = P.num_tiles < num_sms ? P.num_tiles : num_sms;
-  dwpw_gemm_kernel<KB, AS, IS><<<grid, kDwThreads, DwPwCfg<KB, AS, IS>::kSmemBytes, st>>>(P);
-  return cudaGetLastError();
-}
 template <int KB>
 cudaError_t launch_dwpw2_t(const DwPw2Params& P2, int num_sms, cudaStream_t st) {
   const DwPwParams& P = P2.base;
@@ -414,30 +376,21 @@ cudaError_t launch_dwpw2_t(const DwPw2Params& P2, int num_sms, cudaStream_t st) 
   dwpw_gemm2_kernel<KB><<<grid, kDw2Threads, DwPw2Cfg<KB>::kSmemBytes, st>>>(P2);
   return cudaGetLastError();
 }
-// CTA-pair kernel by default; debug bit 3 (or DLV3P_NO_CTA2=1) selects the 1-CTA kernel for A/B runs
-// h_scale / h_shift: HOST copies of the pointwise BN scale / shift (256 each) for the pair kernel's constant-bank epilogue
+// fused SepConv_BN on CTA pairs (dwpw_gemm2.cuh).  h_scale / h_shift: HOST copies of the pointwise BN scale / shift (256 each)
+// for the kernel's constant-bank epilogue
 cudaError_t launch_dwpw(int KB, const DwPwParams& P, const CUtensorMap* tmap_out32, const float* h_scale, const float* h_shift, int num_sms, cudaStream_t st) {
-  if (use_cta2() && !(P.debug & 8) && h_scale && h_shift && tmap_out32) {
-    DwPw2Params P2;
-    P2.base = P;
-    P2.tmap_out32 = tmap_out32;
-    std::memcpy(P2.scale_c, h_scale, sizeof(P2.scale_c));
-    std::memcpy(P2.shift_c, h_shift, sizeof(P2.shift_c));
-    switch (KB) {
-      case 1: return launch_dwpw2_t<1>(P2, num_sms, st);
-      case 2: return launch_dwpw2_t<2>(P2, num_sms, st);
-      case 3: return launch_dwpw2_t<3>(P2, num_sms, st);
-      case 4: return launch_dwpw2_t<4>(P2, num_sms, st);
-      case 5: return launch_dwpw2_t<5>(P2, num_sms, st);
-      default: return cudaErrorInvalidValue;
-    }
-  }
+  if (!h_scale || !h_shift || !tmap_out32) return cudaErrorInvalidValue;
+  DwPw2Params P2;
+  P2.base = P;
+  P2.tmap_out32 = tmap_out32;
+  std::memcpy(P2.scale_c, h_scale, sizeof(P2.scale_c));
+  std::memcpy(P2.shift_c, h_shift, sizeof(P2.shift_c));
   switch (KB) {
-    case 1: return launch_dwpw_t<1, 2, 4>(P, num_sms, st);
-    case 2: return launch_dwpw_t<2, 2, 4>(P, num_sms, st);
-    case 3: return launch_dwpw_t<3, 2, 2>(P, num_sms, st);
-    case 4: return launch_dwpw_t<4, 2, 2>(P, num_sms, st);
-    case 5: return launch_dwpw_t<5, 1, 2>(P, num_sms, st);
+    case 1: return launch_dwpw2_t<1>(P2, num_sms, st);
+    case 2: return launch_dwpw2_t<2>(P2, num_sms, st);
+    case 3: return launch_dwpw2_t<3>(P2, num_sms, st);
+    case 4: return launch_dwpw2_t<4>(P2, num_sms, st);
+    case 5: return launch_dwpw2_t<5>(P2, num_sms, st);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -517,7 +470,9 @@ struct dlv3p_ctx {
 
   // device memory
   std::vector<void*> allocs;
-  size_t ws_bytes = 0;
+  std::vector<void*> weight_allocs;   // uploaded at finalize; released and rebuilt when the weights change (no growth per refresh)
+  bool in_finalize = false;
+  size_t ws_bytes = 0, weight_bytes = 0;
   __nv_bfloat16 *feat_bf16 = nullptr, *skip_bf16 = nullptr;  // cast targets / forward_host staging
   void *in_feat_stage = nullptr, *in_skip_stage = nullptr;   // forward_host raw staging (in_dtype)
   dlv3p_ctx* pipe[2] = {nullptr, nullptr};                   // forward_host pipeline: two quarter-batch child contexts
@@ -597,10 +552,32 @@ int dev_alloc(dlv3p_ctx* c, T** p, size_t count) {
   }
   cudaError_t e = cudaMalloc(&q, bytes);
   if (e != cudaSuccess) return fail(c, DLV3P_ERR_NOMEM, fmt("cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)));
-  c->allocs.push_back(q);
+  if (c->in_finalize) {
+    c->weight_allocs.push_back(q);
+    c->weight_bytes += bytes;
+  } else {
+    c->allocs.push_back(q);
+  }
   c->ws_bytes += bytes;
   *p = reinterpret_cast<T*>(q);
   return 0;
+}
+// device buffers of a previous dlv3p_finalize_weights: the stream work that reads them is drained first
+void release_weight_allocs(dlv3p_ctx* c) {
+  if (c->weight_allocs.empty()) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (void* p : c->weight_allocs) cudaFree(p);
+  c->weight_allocs.clear();
+  c->ws_bytes -= c->weight_bytes;
+  c->weight_bytes = 0;
+}
+void drop_pipe_children(dlv3p_ctx* c) {
+  for (dlv3p_ctx*& ch : c->pipe) {
+    if (ch) dlv3p_destroy(ch);
+    ch = nullptr;
+  }
+  c->pipe_failed = false;
 }
 template <class T>
 int upload(dlv3p_ctx* c, T** p, const std::vector<T>& h) {
@@ -889,12 +866,9 @@ int dlv3p_create(const dlv3p_config* cfg, int device, dlv3p_ctx** out) {
   std::memset(c->h_tm, 0, sizeof(c->h_tm));
   if (!c->plan_only && cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(DLV3P_ERR_CUDA, "cudaStreamCreate failed");
   if (!c->plan_only) {
-    const char* e = getenv("DLV3P_NO_SIDE_STREAM");
-    if (!(e && e[0] == '1')) {
-      if (cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(DLV3P_ERR_CUDA, "cudaStreamCreate failed");
-      for (cudaEvent_t* ev : {&c->ev_fork, &c->ev_dw, &c->ev_pool, &c->ev_fp0})
-        if (cudaEventCreateWithFlags(ev, cudaEventDisableTiming) != cudaSuccess) return bail(DLV3P_ERR_CUDA, "cudaEventCreate failed");
-    }
+    if (cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(DLV3P_ERR_CUDA, "cudaStreamCreate failed");
+    for (cudaEvent_t* ev : {&c->ev_fork, &c->ev_dw, &c->ev_pool, &c->ev_fp0})
+      if (cudaEventCreateWithFlags(ev, cudaEventDisableTiming) != cudaSuccess) return bail(DLV3P_ERR_CUDA, "cudaEventCreate failed");
   }
   *out = c;
   return DLV3P_OK;
@@ -908,6 +882,7 @@ void dlv3p_destroy(dlv3p_ctx* c) {
   }
   cudaSetDevice(c->device);
   for (void* p : c->allocs) cudaFree(p);
+  for (void* p : c->weight_allocs) cudaFree(p);
   if (c->in_feat_stage) cudaFree(c->in_feat_stage);
   if (c->in_skip_stage) cudaFree(c->in_skip_stage);
   if (c->out_stage) cudaFree(c->out_stage);
@@ -950,6 +925,7 @@ int dlv3p_set_weight(dlv3p_ctx* c, const char* layer, const char* var, const flo
   s.data.assign(host, host + n);
   s.set = true;
   c->finalized = false;
+  drop_pipe_children(c);   // dlv3p_forward_host's sub-batch contexts hold copies of the old weights: rebuilt lazily
   return DLV3P_OK;
 }
 
@@ -960,6 +936,9 @@ int dlv3p_finalize_weights(dlv3p_ctx* c) {
   if (c->plan_only) return fail(c, DLV3P_ERR_STATE, "plan-only context (device -1): nothing can be uploaded or run; there is no CPU path");
   if (c->finalized) return DLV3P_OK;
   CU_TRY(c, cudaSetDevice(c->device));
+  release_weight_allocs(c);
+  struct Scope { dlv3p_ctx* c; ~Scope() { c->in_finalize = false; } } scope{c};
+  c->in_finalize = true;
   const dlv3p_config& g = c->cfg;
   int r = 0;
   std::string terr;
@@ -1259,7 +1238,6 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
           c->gather_maps_ptr = feat;
         }
         G.maps = c->gather_maps_dev;
-        { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DLV3P_ASPP_DEBUG"); dbg = e ? atoi(e) : 0; } G.debug = dbg; }   // attribution runs only
         cudaError_t e = launch_aspp_gather(G, st);
         (void)e;
       } else if (c->aspp_slab) {
@@ -1454,9 +1432,7 @@ int dlv3p_forward_host(dlv3p_ctx* c, const void* h_feat, const void* h_skip, voi
   if (r) return r;
   if (sb && !h_skip) return fail(c, DLV3P_ERR_INVALID, "decoder stage needs the skip feature");
 
-  static int no_pipe = -1;
-  if (no_pipe < 0) { const char* e = getenv("DLV3P_NO_HOST_PIPELINE"); no_pipe = (e && e[0] == '1') ? 1 : 0; }
-  if (!no_pipe && !c->pipe_failed && c->cfg.B >= 2 * kPipeChunks && c->cfg.B % kPipeChunks == 0) {
+  if (!c->pipe_failed && c->cfg.B >= 2 * kPipeChunks && c->cfg.B % kPipeChunks == 0) {
     if (!c->pipe[0] && make_pipe_children(c) != DLV3P_OK) {   // e.g. out of memory: fall back to the one-shot path below
       for (dlv3p_ctx*& ch : c->pipe) { dlv3p_destroy(ch); ch = nullptr; }
       c->pipe_failed = true;

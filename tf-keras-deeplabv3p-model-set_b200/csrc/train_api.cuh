@@ -105,13 +105,9 @@ static int train_gemm_impl(bool tn, int device, const void* a, int64_t lda, cons
     L.out = d_partial; L.ldd = N; L.out_mode = kTgOutPartial;
   } else {
     L.out = d; L.ldd = ldd; L.out_mode = out_fp32 ? kTgOutF32 : kTgOutBf16;
-    if (!out_fp32 && M >= 32) {   // TMA-store epilogue (DLV3P_TGEMM_DIRECT_STORE=1 keeps the per-thread stores: A/B runs)
-      static int direct = -1;
-      if (direct < 0) { const char* e = getenv("DLV3P_TGEMM_DIRECT_STORE"); direct = (e && e[0] == '1') ? 1 : 0; }
-      if (!direct) {
-        if (!encode_2d_out(&L.tmap_d, d, M, N, ldd, &terr)) return fail(nullptr, DLV3P_ERR_CUDA, terr);
-        L.tma_store = 1;
-      }
+    if (!out_fp32 && M >= 32) {   // TMA-store epilogue (tiny M keeps the per-thread stores)
+      if (!encode_2d_out(&L.tmap_d, d, M, N, ldd, &terr)) return fail(nullptr, DLV3P_ERR_CUDA, terr);
+      L.tma_store = 1;
     }
   }
   cudaError_t e;

@@ -367,7 +367,9 @@ struct LossParams {
 };
 // per-pixel loss value and the scalar S with d(loss)/d(logit_k) = S * (p_k - [k == label]) for the three losses of the reference
 // (all are functions of the label's probability p only):
-//   CE        -log(clip(p, 1e-7, 1-1e-7))                      S = 1 (0 where the clip is active)
+//   CE        -log(p)                                          S = 1   (under model.fit the Keras backend sees y_pred come out of a
+//             Softmax op and takes its logits path, softmax_cross_entropy_with_logits: no clip_by_value, so confidently wrong pixels
+//             keep their gradient; the [1e-7, 1-1e-7] clip only exists on the eager / non-Softmax path)
 //   weighted  -w[label] * log(p)                               S = w[label]
 //   focal     -alpha * (1-p)^gamma * log(clip(p, 1e-15, .))    S = alpha * ((1-p)^gamma - gamma * (1-p)^(gamma-1) * p * log(p))
 __device__ __forceinline__ void loss_terms(const LossParams& P, float pl, int label, float& loss_px, float& S) {
@@ -380,11 +382,11 @@ __device__ __forceinline__ void loss_terms(const LossParams& P, float pl, int la
     const float p = fmaxf(pl, 1e-15f), q = 1.0f - p, lg = __logf(p);
     const float qg = __powf(q, P.gamma);
     loss_px = -P.alpha * qg * lg;
-    S = clipped ? 0.0f : P.alpha * (qg - P.gamma * __powf(q, P.gamma - 1.0f) * p * lg);
+    const float qg1 = q > 0.0f ? __powf(q, P.gamma - 1.0f) : (P.gamma == 1.0f ? 1.0f : 0.0f);   // pow(0, 0) would be NaN
+    S = clipped ? 0.0f : P.alpha * (qg - P.gamma * qg1 * p * lg);
   } else {
-    const bool clipped = pl < 1e-7f || pl > 1.0f - 1e-7f;
-    loss_px = -__logf(fminf(fmaxf(pl, 1e-7f), 1.0f - 1e-7f));
-    S = clipped ? 0.0f : 1.0f;
+    loss_px = -__logf(fmaxf(pl, 1.0e-37f));
+    S = 1.0f;
   }
 }
 __device__ __forceinline__ float interp_logit(const float* p00, const float* p01, const float* p10, const float* p11, int c, float tx, float ty, float bias) {

@@ -208,9 +208,22 @@ class DeepLabHead(_Block):
     def predict_host(self, feat: np.ndarray, skip: Optional[np.ndarray] = None, out: Optional[np.ndarray] = None) -> np.ndarray:
         """model.predict + np.argmax equivalent with host buffers end to end (dlv3p_forward_host)."""
         shape, dt = self.output_shape_dtype()
+        fb, sb = self.ctx.input_bytes()
+        f = self._prep(feat)
+        if f.nbytes != fb:       # dlv3p_forward_host copies exactly fb / sb / output_bytes: a wrong batch or size would read / write past the arrays
+            raise ValueError('feature tensor has %d bytes, context expects %d' % (f.nbytes, fb))
+        s = None
+        if sb:
+            if skip is None:
+                raise ValueError('this block needs a skip feature')
+            s = self._prep(skip)
+            if s.nbytes != sb:
+                raise ValueError('skip tensor has %d bytes, context expects %d' % (s.nbytes, sb))
         if out is None:
             out = np.empty(shape, dt)
-        self.ctx.forward_host(self._prep(feat), None if skip is None else self._prep(skip), out)
+        elif not (isinstance(out, np.ndarray) and out.dtype == np.dtype(dt) and out.flags['C_CONTIGUOUS'] and out.nbytes == self.ctx.output_bytes()):
+            raise ValueError('out must be a C-contiguous %s array of shape %s' % (np.dtype(dt).name, tuple(shape)))
+        self.ctx.forward_host(f, s, out)
         return out
 
     def tap(self, name: str) -> np.ndarray:

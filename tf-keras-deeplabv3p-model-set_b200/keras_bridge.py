@@ -149,11 +149,24 @@ class AcceleratedDeepLab:
 
     def __call__(self, images: np.ndarray) -> np.ndarray:
         feats = self.backbone(images, training=False)
-        if self.decoder:
-            feat, skip = (np.ascontiguousarray(t.numpy(), np.float32) for t in feats)
-            return self.head.predict_host(feat, skip)
-        feat = feats[0] if isinstance(feats, (list, tuple)) else feats
-        return self.head.predict_host(np.ascontiguousarray(feat.numpy(), np.float32))
+        if not isinstance(feats, (list, tuple)):
+            feats = [feats]
+        arrs = [np.ascontiguousarray(t.numpy() if hasattr(t, 'numpy') else t, np.float32) for t in feats[:2 if self.decoder else 1]]
+        return self._predict_any_batch(arrs)
+
+    def _predict_any_batch(self, arrs) -> np.ndarray:
+        """The context has a static batch (head.B): a caller's batch is split into chunks of that size and the last, partial
+        chunk (e.g. the tail of an evaluation set) is zero padded — images are independent, the padding rows are dropped."""
+        n, B = arrs[0].shape[0], self.head.B
+        outs = []
+        for i in range(0, n, B):
+            chunk = [a[i:i + B] for a in arrs]
+            m = chunk[0].shape[0]
+            if m < B:
+                chunk = [np.concatenate([c, np.zeros((B - m,) + c.shape[1:], c.dtype)], axis=0) for c in chunk]
+            y = self.head.predict_host(*[np.ascontiguousarray(c) for c in chunk])
+            outs.append(y[:m].copy() if m < B or n > B else y)
+        return outs[0] if len(outs) == 1 else np.concatenate(outs, axis=0)
 
     predict = __call__
 

@@ -39,7 +39,7 @@ def aggregate_throughput(units_per_rank_per_step: int, steps: int, world_size: i
 # SyncBatchNormalization statistics (reference layers.py:63-70 with MirroredStrategy, train.py:143-158): the FORWARD half
 # of the cfg-5 exchange.  Every replica reduces its own rows to [sum_x | sum_x2 | row count], the replicas all-reduce (SUM)
 # that one small vector (<= 16 KB per layer: latency bound, NCCL LL protocol over NVLink), and normalise with the global
-# mean / biased variance.  The backward kernels and the gradient all-reduce are not built yet.
+# mean / biased variance.  The backward half ([sum g | sum g*xhat]) and the gradient all-reduce live in train.py (HeadTrainer).
 def allreduce_stats(stats):
     """In-place SUM all-reduce of a stats tensor [2C+1] = sum_x | sum_x2 | rows (torch tensor: cuda -> NCCL, cpu -> gloo).
     Identity when torch.distributed is not initialised."""

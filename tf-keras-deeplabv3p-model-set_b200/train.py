@@ -175,6 +175,23 @@ class HeadTrainer(TrainLayout):
         self._alloc()
         self.set_weights(weights)
 
+    # lr / momentum / l2 travel by value into dlv3p_train_sgd, so a captured CUDA graph has them baked in: changing one
+    # (ReduceLROnPlateau, the cosine / poly decay schedules of the reference's train.py:49-66, :192-215) drops the captured
+    # graph; the next train_step re-captures with the new value.
+    def _hyper(name):
+        def get(self):
+            return self.__dict__['_' + name]
+
+        def set_(self, v):
+            if self.__dict__.get('_' + name) != v:
+                self.__dict__['_' + name] = v
+                if self.__dict__.get('_graph') is not None:
+                    self.__dict__['_graph'] = None
+        return property(get, set_)
+
+    lr, momentum, l2 = _hyper('lr'), _hyper('momentum'), _hyper('l2')
+    del _hyper
+
     def _alloc(self):
         t = self.torch
         dv = self.tdev
