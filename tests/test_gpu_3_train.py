@@ -459,25 +459,29 @@ def test_training_reduces_the_loss(gpu):
     assert np.isfinite(losses).all() and losses[-1] < losses[0] - 0.05, losses      # random labels: only the class prior can be learned
 
 
-def _ddp_worker(rank, world, port, q):
+def _ddp_worker(rank, world, port, q, one_gpu=False):
     try:
-        _ddp_worker_body(rank, world, port, q)
+        _ddp_worker_body(rank, world, port, q, one_gpu)
     except Exception as e:                       # the parent must not wait for a result that will never come
         import traceback
         q.put((rank, 'ERROR', traceback.format_exc(), str(e), None))
 
 
-def _ddp_worker_body(rank, world, port, q):
+def _ddp_worker_body(rank, world, port, q, one_gpu=False):
     import torch
     import torch.distributed as dist
     from dlv3p_b200 import train
     os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    dev = 0 if one_gpu else rank
+    torch.cuda.set_device(dev)
+    if one_gpu:     # single-GPU box: both replicas on cuda:0, gloo carries the CUDA tensors (NCCL refuses two ranks on one device)
+        dist.init_process_group('gloo', rank=rank, world_size=world)
+    else:
+        dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
     cfg, W, feat, skip, labels = _step_case(B=2 * world, seed=44)
     Bl = cfg.B // world
     sl = slice(rank * Bl, (rank + 1) * Bl)
-    tr = train.HeadTrainer(Bl, cfg.H, cfg.W, cfg.OS, cfg.Cin, cfg.Cskip, cfg.NC, W, device=rank, seed=9, graph=False)
+    tr = train.HeadTrainer(Bl, cfg.H, cfg.W, cfg.OS, cfg.Cin, cfg.Cskip, cfg.NC, W, device=dev, seed=9, graph=False)
     f = torch.from_numpy(feat[sl]).cuda().to(torch.bfloat16).contiguous()
     s = torch.from_numpy(skip[sl]).cuda().to(torch.bfloat16).contiguous()
     l = torch.from_numpy(labels[sl]).cuda().contiguous()
@@ -489,16 +493,16 @@ def _ddp_worker_body(rank, world, port, q):
 
 
 def test_data_parallel_step_two_gpus_nccl(gpu):
-    """Two replicas (SyncBN statistics + gradient all-reduce over NCCL) == the oracle on the global batch."""
+    """Two replicas (SyncBN statistics + gradient all-reduce) == the oracle on the global batch: NCCL over NVLink when the box has
+    two GPUs, otherwise both replicas on cuda:0 over gloo (never skipped)."""
     torch = _t()
-    if torch.cuda.device_count() < 2:
-        pytest.skip('needs two GPUs (gpurun --gpus 2)')
+    one_gpu = torch.cuda.device_count() < 2
     import torch.multiprocessing as mp
     from dlv3p_b200 import train, train_ffi
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    ps = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    ps = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q, one_gpu)) for r in range(2)]
     for p in ps:
         p.start()
     got = sorted([q.get(timeout=240) for _ in ps], key=lambda t: t[0])

@@ -86,13 +86,17 @@ def test_bn_stats_and_apply_match_the_oracle(gpu, M, C, relu):
     assert np.abs(y - outs[0]).max() <= 2.0 ** -8 * max(1.0, np.abs(outs[0]).max())      # one bf16 rounding of the output
 
 
-def _nccl_worker(rank, world, port, q):
+def _nccl_worker(rank, world, port, q, one_gpu=False):
     import torch
     import torch.distributed as dist
     from dlv3p_b200 import sharding
     os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    if one_gpu:     # both replicas on cuda:0, gloo carries the CUDA statistics vector (NCCL refuses two ranks on one device)
+        torch.cuda.set_device(0)
+        dist.init_process_group('gloo', rank=rank, world_size=world)
+    else:
+        torch.cuda.set_device(rank)
+        dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
     rng = np.random.default_rng(9)
     C = 256
     shards = [R.bf16_round(rng.standard_normal((2 + r, 16, 16, C)).astype(np.float32)) for r in range(world)]
@@ -106,15 +110,15 @@ def _nccl_worker(rank, world, port, q):
 
 @pytest.mark.gpu
 def test_sync_bn_forward_two_gpus_nccl(gpu):
-    """Two replicas with different row counts: statistics kernel -> NCCL all-reduce -> normalisation kernel."""
+    """Two replicas with different row counts: statistics kernel -> all-reduce -> normalisation kernel.  NCCL over NVLink on a box
+    with two GPUs; on a single-GPU box the same exchange runs with both replicas on cuda:0 over gloo (never skipped)."""
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip('needs two GPUs (gpurun --gpus 2)')
+    one_gpu = torch.cuda.device_count() < 2
     import torch.multiprocessing as mp
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    ps = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    ps = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q, one_gpu)) for r in range(2)]
     for p in ps:
         p.start()
     got = sorted([q.get(timeout=300) for _ in ps], key=lambda t: t[0])
