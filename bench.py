@@ -1,14 +1,14 @@
 #!/usr/bin/env python3
-"""bench.py — headline benchmark of the DeepLabV3+ head hot path (BASELINE.json: images/sec, DeepLabV3+ Xception
-OS16 512x512 forward at 1/2/4/8 B200; ASPP %roofline).
+"""bench.py — headline benchmark (BASELINE.json: images/sec, DeepLabV3+ Xception OS16 512x512 forward at 1/2/4/8 B200; ASPP %roofline).
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (libdlv3p.so via ctypes)
   python bench.py --impl reference --gpus N --steps K ...   # the reference path's CPU restatement (oracle), host cores
   torchrun --nproc-per-node N ... bench.py --gpus N ...     # one rank per GPU; batch-sharded, no data-path collective
 
-One "step" = one forward of the head over one batch of synthetic backbone features (configs[1]: Xception OS16
-512x512, VOC 21 classes, batch 32 per GPU, bf16): ASPP -> Decoder -> classifier -> pred_resize -> argmax, uint8
-labels out.  The backbone is outside the hot path: the number is HEAD-ONLY images/s.
+One "step" = one forward of the WHOLE model over one batch of synthetic uint8 images (configs[1]: Xception OS16 512x512, VOC 21
+classes, batch 32 per GPU, bf16): normalize -> Xception backbone -> ASPP -> Decoder -> classifier -> pred_resize -> argmax, uint8
+labels out.  Sub-records on the same line: `aspp` (the metric's ASPP %roofline), `other_configs` (configs 0/2/3), `train` (configs[4],
+the head's data-parallel training step with its collectives).
 
 PyTorch is used here only as plumbing: CUDA events on the launch stream, device buffers for the synthetic inputs and
 torch.distributed (NCCL) for the barrier / max-over-ranks.  The measured path is the C ABI.
@@ -30,8 +30,8 @@ sys.path.insert(0, ROOT)
 
 # ---- workload: BASELINE.json configs[1] ---------------------------------------------------------------------------
 CFG = dict(B=32, H=512, W=512, OS=16, Cin=2048, Cskip=256, NC=21)
-WORKLOAD = 'DeepLabV3+ Xception OS16 512x512 VOC head (ASPP+decoder+classifier+resize+argmax), batch 32/GPU, bf16 forward'
-METRIC = 'images/sec DeepLabV3+ Xception OS16 512^2 fwd (head only)'
+WORKLOAD = 'DeepLabV3+ Xception OS16 512x512 VOC, WHOLE MODEL (Xception backbone + ASPP + decoder + classifier + resize + argmax), batch 32/GPU, bf16 forward'
+METRIC = 'images/sec DeepLabV3+ Xception OS16 512^2 fwd'
 
 # algorithmic work per image at this config (SURVEY.md §8(d), 2 FLOP per MAC; DESIGN.md "Measurement")
 GEMM_FLOP_PER_IMG = {
@@ -69,6 +69,11 @@ NCU_DRAM_MB_PER_LAUNCH_B32 = {
     'pool_proj': 1.46,
 }
 
+
+# DRAM traffic per step (dram__bytes_read.sum + dram__bytes_write.sum summed over a kernel function's launches, bytes) from one
+# `ncu --set full` capture of this command at batch 32; filled in from profiles/ once captured
+NCU_TRAFFIC = {}
+NCU_TRAFFIC_NOTE = ''
 
 # algorithmic HBM bytes per image of the fused SepConv kernels (read the input once, write the 256-channel output once)
 ALGO_BYTES_PER_IMG = {
@@ -151,42 +156,6 @@ class ClockSampler:
                     reasons.add(n)
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
                 'power_w_max': max(pw) if pw else None, 'samples': len(sm), 'reasons': sorted(reasons)}
-
-
-def cpu_reference_throughput(budget_s=20.0, batch=2, max_iters=20):
-    """The reference path restated with torch-CPU ops (oracle/head_ref.py), fp32, all host threads — TensorFlow is
-    not installable here: 'restatement, not TensorFlow'. Bounded sample of the same workload."""
-    import torch
-    from oracle import head_ref as R
-    torch.set_num_threads(max(1, os.cpu_count() or 1))      # torchrun pins OMP_NUM_THREADS=1: the CPU arm uses all host cores
-    cfg = R.HeadConfig(B=batch, H=CFG['H'], W=CFG['W'], OS=CFG['OS'], Cin=CFG['Cin'], Cskip=CFG['Cskip'], NC=CFG['NC'])
-    W = R.make_weights(cfg, 1234)
-    feat, skip = R.make_inputs(cfg, 1236)
-    tf, ts = torch.from_numpy(feat), torch.from_numpy(skip)
-    R.head_forward_torch(tf, ts, W, cfg, 'fp32')              # warm-up (thread pool, allocator)
-    t0 = time.perf_counter()
-    it = 0
-    while it < max_iters and (it < 2 or time.perf_counter() - t0 < budget_s):
-        R.head_forward_torch(tf, ts, W, cfg, 'fp32')
-        it += 1
-    dt = time.perf_counter() - t0
-    return {'value': batch * it / dt, 'unit': 'images/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-            'sample': '%d iterations of batch %d of the same workload, fp32 torch-CPU restatement incl. softmax+argmax (%.1f s)' % (it, batch, dt),
-            'host_cpus': os.cpu_count()}
-
-
-def run_reference(args, rank, world):
-    if rank != 0:
-        return
-    steps = max(1, args.steps)
-    res = cpu_reference_throughput(budget_s=min(120.0, 6.0 * steps), batch=2, max_iters=max(2, steps))
-    line = {'impl': 'reference', 'metric': METRIC, 'value': res['value'], 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': steps,
-            'warmup': args.warmup, 'ms_per_step': 1000.0 * 2 / res['value'], 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'reference_arm': 'oracle port on host cores, bounded sample: batch 2 per step'},
-            'cpu_baseline': res,
-            'e2e': {'value': res['value'], 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line))
 
 
 def aspp_block(prof, B, peaks):
@@ -308,6 +277,180 @@ def time_train_step(rank, world, local_rank, steps=10, warmup=3, batch=8):
     return rec
 
 
+KERNEL_OF = [('_shortcut_sample', 'subsample2_kernel'), ('_depthwise', 'bb_depthwise_kernel'), ('_pointwise', 'bb_gemm_kernel'),
+             ('_shortcut', 'bb_gemm_kernel'), ('entry_flow_conv1_1', 'stem_conv_kernel'), ('entry_flow_conv1_2', 'conv3x3_c32_kernel')]
+HEAD_GEMMS = ('aspp_branches_gemm', 'concat_projection_gemm', 'feature_projection0_gemm', 'decoder_conv0_sepconv', 'decoder_conv1_sepconv', 'classifier_gemm')
+
+
+def kernel_of(op_name):
+    for suffix, k in KERNEL_OF:
+        if op_name.endswith(suffix):
+            return k
+    return op_name      # head launches carry their own names
+
+
+def summarize_profile(prof_runs, B, peaks):
+    """prof_runs: list of per-forward [(name, ms, flops, bytes)].  Aggregates by kernel function; FLOPs / bytes are the algorithmic
+    figures the library reports per launch (backbone) or the table above (head)."""
+    n = len(prof_runs)
+    agg = {}
+    per_op = {}
+    for run in prof_runs:
+        for name, ms, fl, by in run:
+            if fl == 0 and name in GEMM_FLOP_PER_IMG:
+                fl = GEMM_FLOP_PER_IMG[name] * B
+            if by == 0:
+                by = (HBM_BYTES_PER_IMG.get(name) or ALGO_BYTES_PER_IMG.get(name, 0)) * B
+            k = kernel_of(name)
+            a = agg.setdefault(k, {'ms': 0.0, 'flops': 0.0, 'bytes': 0.0, 'launches': 0})
+            a['ms'] += ms / n; a['flops'] += fl / n; a['bytes'] += by / n; a['launches'] += 1.0 / n
+            per_op[name] = per_op.get(name, 0.0) + ms / n
+    return agg, per_op
+
+
+def run_whole_model(args, rank, world, local_rank):
+    """The headline: DeepLabV3+ Xception OS16 512x512 forward, WHOLE MODEL (backbone + head), uint8 images in, uint8 labels out."""
+    import torch
+    import dlv3p_b200
+    from dlv3p_b200 import ffi
+    B = args.batch
+    if args.strong:
+        B = max(1, dlv3p_b200.sharding.shard_batch(args.batch, world, rank)[1])
+    net = dlv3p_b200.DeepLabV3PlusXception((CFG['H'], CFG['W'], 3), CFG['NC'], CFG['OS'], batch=B, device=local_rank)
+    net.set_weights(random_weights(net.weight_specs()))
+    mdl = net.model
+    g = torch.Generator(device='cuda').manual_seed(1236 + rank)
+    images = torch.randint(0, 256, (B, CFG['H'], CFG['W'], 3), generator=g, device='cuda', dtype=torch.uint8)
+    out = torch.empty((B, CFG['H'], CFG['W']), device='cuda', dtype=torch.uint8)
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        mdl.forward(images.data_ptr(), out.data_ptr(), sp)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches_per_step = mdl.launch_count()
+    prof_runs = [mdl.profile(images.data_ptr(), out.data_ptr(), sp) for _ in range(max(3, min(5, args.steps)))]
+    # ---- end to end through the public host API: pinned uint8 images -> H2D -> backbone + head -> D2H labels, every step
+    ib, ob = mdl.input_bytes(), mdl.output_bytes()
+    pin_i, pin_o = ffi.PinnedBuffer(ib), ffi.PinnedBuffer(ob)
+    hi, ho = pin_i.view(np.uint8, (B, CFG['H'], CFG['W'], 3)), pin_o.view(np.uint8, (B, CFG['H'], CFG['W']))
+    hi[:] = images.cpu().numpy()
+    e2e_steps = max(3, min(args.steps, 10))
+    mdl.forward_host(hi, ho)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        mdl.forward_host(hi, ho)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1000.0
+    labels_ok = bool(np.array_equal(ho, out.cpu().numpy()))
+    ms, e2e_ms = dlv3p_b200.sharding.max_over_ranks([ms, e2e_ms], device='cuda')
+    ws = mdl.workspace_bytes()
+    net.close()
+    del images, out
+    torch.cuda.empty_cache()
+    return dict(B=B, ms=ms, clocks=clocks, launches_per_step=launches_per_step, prof_runs=prof_runs, ib=ib, ob=ob, e2e_steps=e2e_steps, e2e_ms=e2e_ms,
+                labels_ok=labels_ok, workspace_bytes=ws)
+
+
+def time_whole_model_cfg3(local_rank, steps=5):
+    """BASELINE configs[2], whole model: Xception OS8 1024x2048, 19 classes, batch 8 (N=1 only)."""
+    import torch
+    import dlv3p_b200
+    try:
+        net = dlv3p_b200.DeepLabV3PlusXception((1024, 2048, 3), 19, 8, batch=8, device=local_rank)
+        net.set_weights(random_weights(net.weight_specs()))
+        images = torch.randint(0, 256, (8, 1024, 2048, 3), device='cuda', dtype=torch.uint8)
+        out = torch.empty((8, 1024, 2048), device='cuda', dtype=torch.uint8)
+        sp = torch.cuda.current_stream().cuda_stream
+        for _ in range(3):
+            net.model.forward(images.data_ptr(), out.data_ptr(), sp)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            net.model.forward(images.data_ptr(), out.data_ptr(), sp)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        prof = net.model.profile(images.data_ptr(), out.data_ptr(), sp)
+        flops = sum(p[2] for p in prof) + 200.99e9 * 8
+        agg = {}
+        for name, t, fl, by in prof:
+            agg[kernel_of(name)] = agg.get(kernel_of(name), 0.0) + t
+        dom = max(agg, key=agg.get)
+        rec = {'ms_per_step': ms, 'images_per_s': 8 / ms * 1000.0, 'batch': 8, 'conv_tflops': flops / (ms / 1000.0) / 1e12, 'dominant_kernel': dom,
+               'dominant_kernel_ms': agg[dom], 'scope': 'whole model (Xception OS8 backbone + head)', 'workspace_gb': net.model.workspace_bytes() / 1e9}
+        net.close()
+        del images, out
+        torch.cuda.empty_cache()
+        return rec
+    except Exception as e:
+        return {'error': repr(e)[:200]}
+
+
+def cpu_whole_model_throughput(budget_s=20.0, batch=1, max_iters=8):
+    """The reference path restated with torch-CPU ops (oracle/xception_ref.py + oracle/head_ref.py), fp32, all host threads:
+    normalize_image -> Xception_body -> ASPP -> Decoder -> tail -> argmax.  'Restatement, not TensorFlow' (not installable here)."""
+    import torch
+    from oracle import head_ref as R
+    from oracle import xception_ref as X
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    Wb = X.make_weights(CFG['OS'], 4321)
+    cfg = R.HeadConfig(B=batch, H=CFG['H'], W=CFG['W'], OS=CFG['OS'], Cin=CFG['Cin'], Cskip=CFG['Cskip'], NC=CFG['NC'])
+    Wh = R.make_weights(cfg, 1234)
+    img = np.random.default_rng(5).integers(0, 256, (batch, CFG['H'], CFG['W'], 3)).astype(np.uint8)
+
+    def once():
+        f, s = X.forward_torch(R.normalize_image(img), Wb, CFG['OS'], 'fp32')
+        return R.head_forward_torch(f, s, Wh, cfg, 'fp32')
+
+    once()
+    t0 = time.perf_counter()
+    it = 0
+    while it < max_iters and (it < 2 or time.perf_counter() - t0 < budget_s):
+        once()
+        it += 1
+    dt = time.perf_counter() - t0
+    return {'value': batch * it / dt, 'unit': 'images/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': '%d iterations of batch %d of the same workload (whole model), fp32 torch-CPU restatement incl. softmax+argmax (%.1f s)' % (it, batch, dt),
+            'host_cpus': os.cpu_count()}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    res = cpu_whole_model_throughput(budget_s=min(120.0, 6.0 * steps), batch=1, max_iters=max(2, steps))
+    line = {'impl': 'reference', 'metric': METRIC, 'value': res['value'], 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': steps,
+            'warmup': args.warmup, 'ms_per_step': 1000.0 / res['value'], 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'reference_arm': 'oracle port (whole model) on host cores, bounded sample: batch 1 per step'},
+            'cpu_baseline': res,
+            'e2e': {'value': res['value'], 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -316,9 +459,8 @@ def main():
     ap.add_argument('--impl', default='dlv3p', choices=['dlv3p', 'reference'])
     ap.add_argument('--batch', type=int, default=CFG['B'], help='per-GPU batch (default: the BASELINE config)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--unfused', action='store_true', help='A/B: standalone decoder depthwise kernels')
     ap.add_argument('--no-train', action='store_true', help='skip the cfg-5 training-step sub-record')
-    ap.add_argument('--no-other-configs', action='store_true', help='skip the head-only timings of BASELINE configs 1/3/4 (N=1 only)')
+    ap.add_argument('--no-other-configs', action='store_true', help='skip the timings of BASELINE configs 1/3/4 (N=1 only)')
     ap.add_argument('--strong', action='store_true', help='strong scaling: the global batch stays --batch, each rank takes batch / N images')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -334,7 +476,6 @@ def main():
     import torch
     import torch.distributed as dist
     import dlv3p_b200
-    from dlv3p_b200 import ffi
 
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device — the hot path has no CPU fallback (use --impl reference for the CPU arm)')
@@ -344,80 +485,12 @@ def main():
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # keep stdout to the ONE JSON line (NCCL prints its banner there)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    B = args.batch
-    if args.strong:   # fixed global batch, contiguous shards (sizes differ by at most one image)
-        B = max(1, dlv3p_b200.sharding.shard_batch(args.batch, world, rank)[1])
-    flags = ffi.FLAG_UNFUSED_DECODER if args.unfused else 0
-    head = dlv3p_b200.DeepLabHead(B, CFG['H'], CFG['W'], CFG['OS'], CFG['Cin'], CFG['Cskip'], CFG['NC'], device=local_rank, flags=flags)
-    head.set_weights(random_weights(head.weight_specs()))
-    ctx = head.ctx
-
-    # synthetic backbone features, resident in HBM before the timed region (feat ~ relu(N(0,1)), skip ~ N(0,1))
-    g = torch.Generator(device='cuda').manual_seed(1236 + rank)
-    feat = torch.randn((B, 32, 32, CFG['Cin']), generator=g, device='cuda', dtype=torch.float32).clamp_(min=0).to(torch.bfloat16)
-    skip = torch.randn((B, 128, 128, CFG['Cskip']), generator=g, device='cuda', dtype=torch.float32).to(torch.bfloat16)
-    out = torch.empty((B, CFG['H'], CFG['W']), device='cuda', dtype=torch.uint8)
-    stream = torch.cuda.current_stream()
-    sp = stream.cuda_stream
-
-    def step():
-        ctx.forward(feat.data_ptr(), skip.data_ptr(), out.data_ptr(), sp)
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    # ---- timed region: exactly K steps, CUDA events on the launch stream, barrier + synchronize on both sides
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    launches_per_step = ctx.launch_count()[0]
-
-    # ---- per-kernel device times (CUDA events between launches, same stream): the roofline line
-    prof = {}
-    nprof = max(3, min(10, args.steps))
-    for _ in range(nprof):
-        for name, t in ctx.profile(feat.data_ptr(), skip.data_ptr(), out.data_ptr(), sp):
-            prof.setdefault(name, []).append(t)
-    prof = {k: float(np.mean(v)) for k, v in prof.items()}
-
-    # ---- end to end through the public host API: pinned host inputs -> H2D -> forward -> D2H labels, every step
-    fb, sb = ctx.input_bytes()
-    ob = ctx.output_bytes()
-    pin_f, pin_s, pin_o = ffi.PinnedBuffer(fb), ffi.PinnedBuffer(sb), ffi.PinnedBuffer(ob)
-    pin_f.view(np.uint16, (fb // 2,))[:] = feat.view(torch.int16).cpu().numpy().view(np.uint16).reshape(-1)
-    pin_s.view(np.uint16, (sb // 2,))[:] = skip.view(torch.int16).cpu().numpy().view(np.uint16).reshape(-1)
-    hf, hs, ho = pin_f.view(np.uint16, (fb // 2,)), pin_s.view(np.uint16, (sb // 2,)), pin_o.view(np.uint8, (ob,))
-    e2e_steps = max(3, min(args.steps, 10))
-    ctx.forward_host(hf, hs, ho)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        ctx.forward_host(hf, hs, ho)
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1000.0
-    labels_ok = bool(np.array_equal(ho.reshape(B, CFG['H'], CFG['W']), out.cpu().numpy()))
-
-    # ---- max over ranks (device-side timings; no data-path collective exists in this path)
-    ms, e2e_ms = dlv3p_b200.sharding.max_over_ranks([ms, e2e_ms], device='cuda')
-    head.close()
-    del feat, skip, out
-    torch.cuda.empty_cache()
-    other = time_other_configs(local_rank) if (world == 1 and not args.no_other_configs and not args.strong) else None
+    R_ = run_whole_model(args, rank, world, local_rank)
+    B, ms = R_['B'], R_['ms']
+    other = None
+    if world == 1 and not args.no_other_configs and not args.strong:
+        other = time_other_configs(local_rank)
+        other['cfg3_xception_os8_1024x2048_b8_whole_model'] = time_whole_model_cfg3(local_rank)
     train_rec = None
     if not args.no_train and not args.strong:
         try:
@@ -427,52 +500,51 @@ def main():
 
     if rank == 0:
         peaks = load_peaks()
+        step_s = ms / args.steps / 1000.0
         value = (args.batch * args.steps / (ms / 1000.0)) if args.strong else dlv3p_b200.sharding.aggregate_throughput(B, args.steps, world, ms)
-        # dominant kernel and its roofline
-        dom = max(prof, key=prof.get)
-        step_ms_prof = sum(prof.values())
-        if dom in GEMM_FLOP_PER_IMG and dom not in ('feature_projection0_gemm', 'classifier_gemm'):
-            ach = GEMM_FLOP_PER_IMG[dom] * B / (prof[dom] / 1000.0) / 1e12
-            # the timed region is milliseconds long (no sustained-clock regime): the burst figure is the denominator
-            roof = {'kernel': dom, 'bound': 'tensor', 'achieved': ach, 'peak': peaks['tflops_burst'], 'unit': 'TFLOP/s',
-                    'frac': ach / peaks['tflops_burst'], 'frac_of_sustained': ach / peaks['tflops_sustained'], 'traffic': None,
-                    'peak_source': peaks['src'] + ', burst bf16 (kernel event-timed inside a sub-second region)'}
+        agg, per_op = summarize_profile(R_['prof_runs'], B, peaks)
+        sum_ms = sum(a['ms'] for a in agg.values())
+        dom = max(agg, key=lambda k: agg[k]['ms'])
+        d = agg[dom]
+        tensor_bound = dom in ('bb_gemm_kernel', 'conv3x3_c32_kernel') or dom in HEAD_GEMMS
+        if tensor_bound:
+            ach = d['flops'] / (d['ms'] / 1000.0) / 1e12
+            roof = {'kernel': dom, 'bound': 'tensor', 'achieved': ach, 'peak': peaks['tflops_burst'], 'unit': 'TFLOP/s', 'frac': ach / peaks['tflops_burst'],
+                    'frac_of_sustained': ach / peaks['tflops_sustained'],
+                    'peak_source': peaks['src'] + ', burst bf16 (kernels event-timed inside a sub-second region)'}
         else:
-            byt = HBM_BYTES_PER_IMG.get(dom, 0) * B
-            ach = byt / (prof[dom] / 1000.0) / 1e9
-            roof = {'kernel': dom, 'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / peaks['hbm_gbs'],
-                    'traffic': None, 'peak_source': peaks['src']}
-        if B == CFG['B'] and not args.unfused and dom in NCU_DRAM_MB_PER_LAUNCH_B32:
-            roof['traffic'] = NCU_DRAM_MB_PER_LAUNCH_B32[dom] * 1e6
-            roof['traffic_unit'] = 'bytes per launch (ncu dram read+write, profiles/r01c_ncu_full_step_summary.csv)'
-            roof['algorithmic_bytes'] = (HBM_BYTES_PER_IMG.get(dom) or ALGO_BYTES_PER_IMG.get(dom, 0)) * B
-            roof['dram_gbs'] = roof['traffic'] / (prof[dom] / 1000.0) / 1e9          # second roof of the fused kernels: HBM
-            roof['dram_frac_of_hbm_peak'] = roof['dram_gbs'] / peaks['hbm_gbs']
-        roof['kernel_ms'] = prof[dom]
-        roof['share_of_step'] = prof[dom] / step_ms_prof
-        gemm_flop = sum(GEMM_FLOP_PER_IMG[k] for k in prof if k in GEMM_FLOP_PER_IMG) * B
+            ach = d['bytes'] / (d['ms'] / 1000.0) / 1e9
+            roof = {'kernel': dom, 'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / peaks['hbm_gbs'], 'peak_source': peaks['src']}
+        roof.update({'launches_per_step': round(d['launches']), 'kernel_ms_per_step': d['ms'], 'avg_launch_ms': d['ms'] / max(d['launches'], 1),
+                     'algorithmic_flops_per_step': d['flops'], 'algorithmic_bytes_per_step': d['bytes'], 'share_of_step': d['ms'] / sum_ms,
+                     'traffic': NCU_TRAFFIC.get(dom), 'traffic_note': NCU_TRAFFIC_NOTE if NCU_TRAFFIC.get(dom) else 'no ncu capture for this kernel yet'})
+        total_flops = sum(a['flops'] for a in agg.values())
         kernels = {}
-        for k, t in sorted(prof.items(), key=lambda kv: -kv[1]):
-            d = {'ms': round(t, 4)}
-            if k in GEMM_FLOP_PER_IMG:
-                d['tflops'] = round(GEMM_FLOP_PER_IMG[k] * B / (t / 1000.0) / 1e12, 1)
-            if k in HBM_BYTES_PER_IMG:
-                d['gbs'] = round(HBM_BYTES_PER_IMG[k] * B / (t / 1000.0) / 1e9, 1)
-            kernels[k] = d
+        for k, a in sorted(agg.items(), key=lambda kv: -kv[1]['ms']):
+            e = {'ms': round(a['ms'], 4), 'launches': round(a['launches'])}
+            if a['flops']:
+                e['tflops'] = round(a['flops'] / (a['ms'] / 1000.0) / 1e12, 1)
+            if a['bytes']:
+                e['algorithmic_gbs'] = round(a['bytes'] / (a['ms'] / 1000.0) / 1e9, 1)
+            kernels[k] = e
+        head_ms = sum(per_op.get(k, 0.0) for k in per_op if kernel_of(k) == k)
         line = {
             'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong' if args.strong else 'weak', 'vs_baseline': None, 'dtype': 'bf16',
             'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'batch_per_gpu': B, 'global_batch': args.batch if args.strong else B * world, 'sharding': 'batch (independent images, no collective)',
-                       'l2': 'inputs 402 MB/step per GPU > 126 MB L2 (no flush needed)', 'decoder': 'unfused' if args.unfused else 'fused'},
-            'e2e': {'value': B * world * e2e_steps / (e2e_ms / 1000.0), 'unit': 'images/s', 'h2d_bytes_per_step': fb + sb,
-                    'd2h_bytes_per_step': ob, 'steps': e2e_steps, 'labels_equal_device_path': labels_ok},
-            'gpu_launches': int(launches_per_step * args.steps),
-            'clocks': clocks,
+            'config': {'workload': WORKLOAD, 'batch_per_gpu': B, 'global_batch': args.batch if args.strong else B * world,
+                       'sharding': 'batch (independent images, no collective)',
+                       'l2': 'activations of one step (%.1f GB workspace) far exceed the 126 MB L2; every step streams them again (no flush needed)' % (R_['workspace_bytes'] / 1e9),
+                       'input': 'uint8 RGB images [B,512,512,3], normalised inside the first convolution', 'output': 'uint8 label maps [B,512,512]'},
+            'e2e': {'value': B * world * R_['e2e_steps'] / (R_['e2e_ms'] / 1000.0), 'unit': 'images/s', 'h2d_bytes_per_step': R_['ib'],
+                    'd2h_bytes_per_step': R_['ob'], 'steps': R_['e2e_steps'], 'labels_equal_device_path': R_['labels_ok']},
+            'gpu_launches': int(R_['launches_per_step'] * args.steps),
+            'clocks': R_['clocks'],
             'roofline': roof,
-            'whole_step': {'gemm_tflops': gemm_flop / (ms / args.steps / 1000.0) / 1e12, 'frac_of_tensor_peak': gemm_flop / (ms / args.steps / 1000.0) / 1e12 / peaks['tflops_burst'],
-                           'sum_kernel_ms': step_ms_prof},
-            'aspp': aspp_block(prof, B, peaks),
+            'whole_step': {'conv_tflops': total_flops / step_s / 1e12, 'frac_of_tensor_peak': total_flops / step_s / 1e12 / peaks['tflops_burst'],
+                           'algorithmic_flops_per_image': total_flops / B, 'sum_kernel_ms': sum_ms, 'launches': R_['launches_per_step'],
+                           'backbone_ms': sum_ms - head_ms, 'head_ms': head_ms},
+            'aspp': aspp_block(per_op, B, peaks),
             'kernels': kernels,
         }
         if other is not None:
@@ -480,7 +552,7 @@ def main():
         if train_rec is not None:
             line['train'] = train_rec
         if world == 1 and not args.no_cpu_baseline:
-            line['cpu_baseline'] = cpu_reference_throughput()
+            line['cpu_baseline'] = cpu_whole_model_throughput()
         print(json.dumps(line))
         sys.stdout.flush()
     if world > 1:

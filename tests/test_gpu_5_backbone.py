@@ -1,0 +1,243 @@
+"""GPU parity tests of the Xception backbone and of the whole model through the C ABI (include/dlv3p_model.h)
+against the oracle (oracle/xception_ref.py + oracle/head_ref.py).  Single operators are held to one bf16 rounding of the output
+against a float64 evaluation of the same operands; blocks and the whole network are compared with the oracle's bf16 mode (same
+rounding points) — a deep random network amplifies every perturbation (oracle/xception_ref.make_calibrated_weights), so the
+tolerances below are stated per depth and the oracle's own bf16-vs-fp32 gap is printed beside them."""
+import numpy as np
+import pytest
+
+import dlv3p_b200
+from dlv3p_b200 import ffi
+from oracle import head_ref as R
+from oracle import xception_ref as X
+from tests.common import label_agreement, planar_to_nhwc, rel_err
+
+pytestmark = pytest.mark.gpu
+
+BF16_ULP = 2.0 ** -8
+
+
+def _bits(a):
+    return R.to_bf16_bits(np.ascontiguousarray(a, np.float32))
+
+
+def _one_rounding(got_bits, ref64, what):
+    got = R.from_bf16_bits(got_bits).astype(np.float64)
+    err = np.abs(got - ref64)
+    tol = BF16_ULP * np.maximum(np.abs(ref64), 1e-2 * np.abs(ref64).max()) + 1e-6
+    assert (err <= tol).all(), '%s: max err %.3g at |ref| %.3g' % (what, err.max(), np.abs(ref64).flat[err.argmax()])
+
+
+# ---------------------------------------------------------------------------------------------------- single operators
+@pytest.mark.parametrize('H,W,dtype', [(64, 64, np.uint8), (37, 51, np.uint8), (32, 48, np.float32)])
+def test_stem_conv(gpu, H, W, dtype):
+    """entry_flow_conv1_1: normalize_image + Conv2D(32, 3, strides 2, 'same') + BN + ReLU; TensorFlow 'same' pads (0,1) on even sizes."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(H * W)
+    img = rng.integers(0, 256, (2, H, W, 3)).astype(np.uint8)
+    x = R.normalize_image(img)
+    src = img if dtype == np.uint8 else x
+    w = rng.normal(0, 0.3, (3, 3, 3, 32)).astype(np.float32)
+    scale, shift = rng.uniform(0.5, 1.5, 32).astype(np.float32), rng.normal(0, 0.1, 32).astype(np.float32)
+    got = ffi.op_stem_conv(src, w, scale, shift)
+    Ho, Wo = -(-H // 2), -(-W // 2)
+    ph, pw = max((Ho - 1) * 2 + 3 - H, 0), max((Wo - 1) * 2 + 3 - W, 0)
+    t = F.pad(torch.from_numpy(x.astype(np.float64)).permute(0, 3, 1, 2), (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2))
+    y = F.conv2d(t, torch.from_numpy(w.astype(np.float64)).permute(3, 2, 0, 1), None, 2)
+    y = torch.relu(y * torch.from_numpy(scale.astype(np.float64)).view(1, -1, 1, 1) + torch.from_numpy(shift.astype(np.float64)).view(1, -1, 1, 1))
+    assert got.shape == (2, Ho, Wo, 32)
+    _one_rounding(got, y.permute(0, 2, 3, 1).numpy(), 'stem')
+
+
+@pytest.mark.parametrize('B,H,W', [(2, 32, 32), (1, 19, 45), (3, 8, 16)])
+def test_conv3x3_implicit_gemm(gpu, B, H, W):
+    """entry_flow_conv1_2: the 64-byte-swizzle implicit GEMM (TMA im2col boxes, zero fill = 'same' padding), partial tiles."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(B * H + W)
+    x = R.bf16_round(np.maximum(rng.standard_normal((B, H, W, 32)), 0).astype(np.float32))
+    w = rng.normal(0, np.sqrt(2.0 / 288), (3, 3, 32, 64)).astype(np.float32)
+    scale, shift = rng.uniform(0.5, 1.5, 64).astype(np.float32), rng.normal(0, 0.1, 64).astype(np.float32)
+    got = ffi.op_conv3x3_c32(_bits(x), w, scale, shift)
+    y = F.conv2d(torch.from_numpy(x.astype(np.float64)).permute(0, 3, 1, 2), torch.from_numpy(R.bf16_round(w).astype(np.float64)).permute(3, 2, 0, 1), None, 1, 1)
+    y = torch.relu(y * torch.from_numpy(scale.astype(np.float64)).view(1, -1, 1, 1) + torch.from_numpy(shift.astype(np.float64)).view(1, -1, 1, 1))
+    _one_rounding(got, y.permute(0, 2, 3, 1).numpy(), 'conv3x3')
+
+
+@pytest.mark.parametrize('stride,rate,relu_in,relu_out', [(1, 1, True, False), (2, 1, True, False), (1, 2, True, False), (1, 2, False, True), (1, 4, False, True)])
+@pytest.mark.parametrize('B,H,W,C', [(2, 32, 32, 128), (1, 17, 23, 728), (2, 9, 40, 64)])
+def test_backbone_depthwise(gpu, stride, rate, relu_in, relu_out, B, H, W, C):
+    """[ReLU] -> depthwise 3x3 (stride 1 'same' / stride 2 after ZeroPadding2D, dilation) -> BN -> [ReLU]; odd sizes, C = 728 (partial group)."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(stride * 100 + rate * 10 + C)
+    x = R.bf16_round(rng.standard_normal((B, H, W, C)).astype(np.float32))
+    w = rng.normal(0, 0.3, (3, 3, C)).astype(np.float32)
+    scale, shift = rng.uniform(0.5, 1.5, C).astype(np.float32), rng.normal(0, 0.1, C).astype(np.float32)
+    got = ffi.op_bb_depthwise(_bits(x), w, stride, rate, relu_in, relu_out, scale, shift)
+    t = torch.from_numpy(x.astype(np.float64)).permute(0, 3, 1, 2)
+    if relu_in:
+        t = torch.relu(t)
+    k = torch.from_numpy((w * scale).astype(np.float32).astype(np.float64)).permute(2, 0, 1).unsqueeze(1)     # the kernel folds the BN scale into fp32 taps
+    if stride == 1:
+        y = F.conv2d(t, k, None, 1, rate, rate, groups=C)
+    else:
+        y = F.conv2d(F.pad(t, (rate, rate, rate, rate)), k, None, stride, 0, rate, groups=C)
+    y = y + torch.from_numpy(shift.astype(np.float64)).view(1, -1, 1, 1)
+    if relu_out:
+        y = torch.relu(y)
+    assert got.shape == (B, -(-H // stride), -(-W // stride), C)
+    _one_rounding(got, y.permute(0, 2, 3, 1).numpy(), 'depthwise s%d r%d' % (stride, rate))
+
+
+@pytest.mark.parametrize('M,K,N,relu,res', [
+    (2048, 728, 728, False, True),      # middle flow: K and N tails, residual sum
+    (300, 64, 128, False, False),       # entry block 1: ragged M, one K block, N < tile
+    (1024, 1536, 2048, True, False),    # exit flow: 8 N tiles, ReLU
+    (77, 256, 728, False, True),        # conv shortcut sum, M < one tile
+    (4096, 1024, 1536, True, False),
+])
+def test_backbone_pointwise(gpu, M, K, N, relu, res):
+    rng = np.random.default_rng(M + K + N)
+    a = R.bf16_round(rng.standard_normal((M, K)).astype(np.float32))
+    w = rng.normal(0, np.sqrt(2.0 / K), (K, N)).astype(np.float32)
+    scale, shift = rng.uniform(0.5, 1.5, N).astype(np.float32), rng.normal(0, 0.1, N).astype(np.float32)
+    r = R.bf16_round(rng.standard_normal((M, N)).astype(np.float32)) if res else None
+    got = ffi.op_bb_pointwise(_bits(a), w, scale, shift, relu, None if r is None else _bits(r))
+    y = a.astype(np.float64) @ R.bf16_round(w).astype(np.float64) * scale.astype(np.float64) + shift.astype(np.float64)
+    if relu:
+        y = np.maximum(y, 0)
+    if res:
+        y = y + r.astype(np.float64)
+    _one_rounding(got, y, 'pointwise %dx%dx%d' % (M, K, N))
+
+
+# ---------------------------------------------------------------------------------------------------- blocks and the whole backbone
+def _model_and_oracle(OS, H, W, B=2, seed=4321, NC=21, keep=True, out_mode=ffi.OUT_LABELS_U8, image_dtype=np.uint8):
+    Wb = X.make_calibrated_weights(OS, seed, size=64)
+    hcfg = R.HeadConfig(B=B, H=H, W=W, OS=OS, Cin=2048, Cskip=256, NC=NC)
+    Wh = R.make_weights(hcfg, seed + 5)
+    m = dlv3p_b200.DeepLabV3PlusXception((H, W, 3), NC, OS, batch=B, out_mode=out_mode, image_dtype=image_dtype, keep_intermediates=keep)
+    allw = dict(Wb)
+    allw.update(Wh)
+    m.set_weights(allw)
+    return m, Wb, Wh, hcfg
+
+
+@pytest.mark.parametrize('OS,H,W', [(16, 128, 128), (8, 96, 96), (32, 128, 160), (16, 100, 132)])
+def test_backbone_blocks_match_the_oracle(gpu, OS, H, W):
+    """Every block output of Xception_body against the oracle's bf16 mode (same rounding points), all three output strides
+    (stride-2 / dilated depthwise variants) and an odd input size."""
+    m, Wb, Wh, hcfg = _model_and_oracle(OS, H, W)
+    rng = np.random.default_rng(OS + H)
+    img = rng.integers(0, 256, (2, H, W, 3)).astype(np.uint8)
+    m(img)
+    t16, t32 = {}, {}
+    x = R.normalize_image(img)
+    f16, s16 = X.forward_torch(x, Wb, OS, 'bf16', taps=t16)
+    f32, s32 = X.forward_torch(x, Wb, OS, 'fp32', taps=t32)
+    worst = 0.0
+    for depth, name in enumerate(t16):
+        got = m.tap(name)
+        e16 = np.linalg.norm(got - t16[name]) / np.linalg.norm(t16[name])
+        e32 = np.linalg.norm(got - t32[name]) / np.linalg.norm(t32[name])
+        o32 = np.linalg.norm(t16[name] - t32[name]) / np.linalg.norm(t32[name])
+        print('%-22s rel-L2 vs bf16-mode oracle %.4f | vs fp32 oracle %.4f (oracle bf16 vs fp32: %.4f)' % (name, e16, e32, o32))
+        # same rounding points: what is left are 1-ulp flips of intermediates, amplified with depth like every other perturbation
+        assert e16 < (4e-3 if depth < 2 else 2.5e-2), (name, e16)
+        assert e32 < max(2.0 * o32, 1e-2), (name, e32, o32)
+        worst = max(worst, e16)
+    assert rel_err(m.tap('skip'), s16) < 1.5e-2
+    assert np.linalg.norm(m.tap('feature') - f16) / np.linalg.norm(f16) < 2.5e-2
+    m.close()
+
+
+def test_every_block_in_isolation(gpu):
+    """Block k fed the ORACLE's output of block k-1 (dlv3p_model_forward_from): no accumulated drift, every block of
+    Xception_body is held on its own to the head's block tolerance against the oracle's bf16 mode."""
+    OS, H, W = 16, 96, 96
+    m, Wb, Wh, hcfg = _model_and_oracle(OS, H, W)
+    img = np.random.default_rng(21).integers(0, 256, (2, H, W, 3)).astype(np.uint8)
+    m(img)
+    t16 = {}
+    X.forward_torch(R.normalize_image(img), Wb, OS, 'bf16', taps=t16)
+    names = list(t16)
+    out = m._bufs['out'].ptr
+    for prev, cur in zip(names[:-1], names[1:]):
+        m.model.forward_from(prev, t16[prev], out)
+        ffi.synchronize(0)
+        got = m.tap(cur)
+        e = np.linalg.norm(got - t16[cur]) / np.linalg.norm(t16[cur])
+        emax = rel_err(got, t16[cur])
+        assert e < 2e-3 and emax < 8e-3, (cur, e, emax)       # 1-ulp flips of the block's few internal roundings, nothing else
+    m.close()
+
+
+def test_whole_model_labels_and_logits(gpu):
+    """uint8 images -> labels through dlv3p_model_forward against oracle backbone + oracle head (bf16 mode)."""
+    H = W = 192
+    m, Wb, Wh, hcfg = _model_and_oracle(16, H, W, B=2, keep=False)
+    img = np.random.default_rng(3).integers(0, 256, (2, H, W, 3)).astype(np.uint8)
+    labels = m(img)
+    logits = planar_to_nhwc(m.tap('logits'))
+    x = R.normalize_image(img)
+    f16, s16 = X.forward_torch(x, Wb, 16, 'bf16')
+    f32, s32 = X.forward_torch(x, Wb, 16, 'fp32')
+    o16 = R.head_forward_torch(f16, s16, Wh, hcfg, 'bf16')
+    o32 = R.head_forward_torch(f32, s32, Wh, hcfg, 'fp32')
+    e16, e32 = rel_err(logits, o16['logits'].numpy()), rel_err(logits, o32['logits'].numpy())
+    gap = rel_err(o16['logits'].numpy(), o32['logits'].numpy())
+    overall, decided, worst = label_agreement(labels, o16['labels'].numpy(), o16['logits_full'].numpy(), 2e-2)
+    print('whole model: logits vs bf16-mode oracle %.4f, vs fp32 oracle %.4f (oracle bf16 vs fp32 %.4f); labels vs bf16-mode oracle %.5f (decided %.5f)'
+          % (e16, e32, gap, overall, decided))
+    # ~140 bf16 rounding points in a random network: flips of single roundings are amplified like any other perturbation; the oracle's
+    # own bf16 mode sits this far from its fp32 mode (printed), so that gap is the yardstick, not the head's 1e-2
+    assert e16 < max(1.5 * gap, 2e-2)
+    assert e32 < max(2.0 * gap, 2e-2)
+    assert decided >= 0.999 and overall >= 0.97
+    # the head alone on the backbone's OWN features: the head's usual tolerances
+    own = R.head_forward_torch(m.tap('feature'), m.tap('skip'), Wh, hcfg, 'bf16')
+    assert rel_err(logits, own['logits'].numpy()) < 8e-3
+    assert (labels == own['labels'].numpy()).mean() >= 0.999
+    m.close()
+
+
+def test_whole_model_host_path_dtypes_determinism_batch_independence(gpu):
+    H, W = 128, 160
+    rng = np.random.default_rng(9)
+    img = rng.integers(0, 256, (4, H, W, 3)).astype(np.uint8)
+    img[2:] = img[:2]
+    m, Wb, Wh, hcfg = _model_and_oracle(16, H, W, B=4, keep=False)
+    a = m(img)
+    b = m.predict(img)
+    c = m(img)
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+    assert np.array_equal(a[:2], a[2:])                                  # batch independence
+    assert m.model.launch_count() >= 130
+    mf, _, _, _ = _model_and_oracle(16, H, W, B=4, keep=False, image_dtype=np.float32)
+    assert np.array_equal(mf(R.normalize_image(img)), a)                # fp32 normalised input == uint8 input normalised on the device
+    m2, _, _, _ = _model_and_oracle(16, H, W, B=2, keep=False)
+    assert np.array_equal(m2(img[:2]), a[:2])
+    with pytest.raises(ValueError):
+        m.predict(img[:3])
+    prof = m.model.profile(m._bufs['img'].ptr, m._bufs['out'].ptr)
+    assert len(prof) == m.model.launch_count() and abs(sum(p[2] for p in prof) / 4 - X.conv_flops(H, W, 16)) / X.conv_flops(H, W, 16) < 1e-6
+    m.close(); mf.close(); m2.close()
+
+
+def test_whole_model_cfg2_shapes(gpu):
+    """BASELINE configs[1] at its real 512x512 (two images for the CPU oracle): feature / skip / logits against the bf16-mode oracle."""
+    m, Wb, Wh, hcfg = _model_and_oracle(16, 512, 512, B=2, keep=False)
+    img = np.random.default_rng(11).integers(0, 256, (2, 512, 512, 3)).astype(np.uint8)
+    labels = m(img)
+    x = R.normalize_image(img)
+    f16, s16 = X.forward_torch(x, Wb, 16, 'bf16')
+    ef = np.linalg.norm(m.tap('feature') - f16) / np.linalg.norm(f16)
+    es = np.linalg.norm(m.tap('skip') - s16) / np.linalg.norm(s16)
+    o16 = R.head_forward_torch(f16, s16, Wh, hcfg, 'bf16')
+    el = rel_err(planar_to_nhwc(m.tap('logits')), o16['logits'].numpy())
+    agree = float((labels == o16['labels'].numpy()).mean())
+    print('cfg2 whole model 512x512: feature rel-L2 %.4f, skip rel-L2 %.4f, logits rel %.4f, labels %.5f' % (ef, es, el, agree))
+    assert es < 1e-2 and ef < 3e-2 and el < 4e-2 and agree >= 0.96
+    m.close()

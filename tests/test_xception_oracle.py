@@ -58,3 +58,22 @@ def test_backbone_feeds_the_head_oracle():
     feat, skip = X.forward_torch(np.zeros((1, 64, 64, 3), np.float32), X.make_weights(16, 2), 16)
     out = R.head_forward(feat, skip, R.make_weights(cfg, 3), cfg, 'fp32')
     assert out['labels'].shape == (1, 64, 64)
+
+
+def test_shifted_add_depthwise_equals_grouped_conv():
+    """The oracle's fast depthwise formulation against torch's grouped conv2d (stride 1 'same', stride 2 after explicit padding, dilation)."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 24, 13, 17, generator=g, dtype=torch.float64)
+    k = torch.randn(3, 3, 24, 1, generator=g, dtype=torch.float64)
+    kt = k.permute(2, 3, 0, 1)
+    for stride, rate in ((1, 1), (2, 1), (1, 2), (1, 4)):
+        if stride == 1:
+            a = X.depthwise3x3(x, k, 1, rate, rate)
+            b = F.conv2d(x, kt, None, 1, rate, rate, groups=24)
+        else:
+            xp = F.pad(x, (rate, rate, rate, rate))
+            a = X.depthwise3x3(xp, k, stride, 0, rate)
+            b = F.conv2d(xp, kt, None, stride, 0, rate, groups=24)
+        assert a.shape == b.shape and float((a - b).abs().max()) < 1e-12

@@ -1,19 +1,23 @@
-"""Build libdlv3p.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+"""Build libdlv3p.so in-tree with nvcc for sm_100a (cross-compiles without a GPU): one object per translation unit, compiled in
+parallel, linked into ONE shared library."""
 from __future__ import annotations
 
 import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, 'csrc', 'dlv3p_api.cu')
+CSRC = os.path.join(HERE, 'csrc')
+UNITS = ['dlv3p_api.cu', 'xception_api.cu']          # head + training operators | Xception backbone + whole model
 OUT = os.path.join(HERE, 'libdlv3p.so')
-DEPS = [os.path.join(HERE, 'csrc', f) for f in ('dlv3p_api.cu', 'pw_gemm.cuh', 'pw_gemm2.cuh', 'dwpw_gemm2.cuh', 'aspp_dw_fast.cuh', 'aspp_dw_gather.cuh', 'bn_train.cuh', 'tgemm.cuh', 'train_kernels.cuh', 'train_api.cuh', 'dwpw_gemm.cuh', 'mem_kernels.cuh', 'sm100_prims.cuh')] + \
-       [os.path.join(os.path.dirname(HERE), 'include', 'dlv3p.h'), os.path.join(os.path.dirname(HERE), 'include', 'dlv3p_train.h')]
+OBJ_DIR = os.path.join(HERE, 'build')
+INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 
-NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
-              '-shared', '-Xcompiler', '-fPIC', '-cudart', 'static']
+ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
+CFLAGS = ARCH + ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC']
+LDFLAGS = ARCH + ['-shared', '-Xcompiler', '-fPIC', '-cudart', 'static']
 
 
 def find_nvcc() -> str:
@@ -23,23 +27,44 @@ def find_nvcc() -> str:
     raise RuntimeError('nvcc not found')
 
 
+def _deps():
+    d = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(('.cu', '.cuh'))]
+    return d + [os.path.join(INCLUDE, f) for f in sorted(os.listdir(INCLUDE)) if f.endswith('.h')]
+
+
 def up_to_date() -> bool:
     if not os.path.exists(OUT):
         return False
     t = os.path.getmtime(OUT)
-    return all(os.path.getmtime(d) <= t for d in DEPS)
+    return all(os.path.getmtime(d) <= t for d in _deps())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return OUT
-    cmd = [find_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', OUT, SRC]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    nvcc = find_nvcc()
+    os.makedirs(OBJ_DIR, exist_ok=True)
+
+    def compile_one(unit):
+        obj = os.path.join(OBJ_DIR, unit.replace('.cu', '.o'))
+        cmd = [nvcc] + CFLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', '-o', obj, os.path.join(CSRC, unit)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return unit, obj, res
+
+    with ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
+        results = list(ex.map(compile_one, UNITS))
+    objs = []
+    for unit, obj, res in results:
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError('nvcc failed compiling %s' % unit)
+        if verbose:
+            sys.stderr.write(res.stderr)
+        objs.append(obj)
+    res = subprocess.run([nvcc] + LDFLAGS + ['-o', OUT] + objs, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError('nvcc failed building libdlv3p.so')
-    if verbose:
-        sys.stderr.write(res.stderr)
+        raise RuntimeError('nvcc failed linking libdlv3p.so')
     return OUT
 
 

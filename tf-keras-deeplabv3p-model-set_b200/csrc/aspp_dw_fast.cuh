@@ -22,12 +22,6 @@ namespace dlv3p {
 
 constexpr int kAsppFastThreads = 256;
 
-__device__ __forceinline__ uint32_t f32x2_to_bf16x2_relu(unsigned long long v) {
-  uint32_t lo, hi, r;
-  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
-  return r;
-}
 
 template <int H, int W, int R>
 __device__ __forceinline__ void aspp_fast_item(const uint8_t* slab_lane, uint8_t* out_lane, int pi, int pj,

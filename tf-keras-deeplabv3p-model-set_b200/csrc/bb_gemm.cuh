@@ -1,0 +1,241 @@
+// bb_gemm.cuh — the pointwise (1x1) convolutions of the Xception backbone on tcgen05 CTA pairs:
+//   D[M, N] = bf16( acc(A[M, K] * W[K, N]) * scale[n] + shift[n]  [ReLU]  [+ residual[M, N]] )
+// = DeeplabConv2D(filters, (1,1)) -> CustomBatchNormalization [-> ReLU] [-> add([residual, shortcut])]
+// (reference: SepConv_BN deeplabv3p/models/layers.py:105-109 with depth_activation False / True; _xception_block's shortcut conv
+//  + BN and the residual add, deeplabv3p/models/deeplabv3p_xception.py:82-90).
+//
+// Same machine as pw_gemm2.cuh (two CTAs of a cluster share a 256 x 256 tile through cta_group::2; each stages its own 128 rows
+// of A and half of the weight tile; 2 TMEM accumulator stages; TMA-store epilogue) with what the backbone adds:
+//   * N up to 2048: work items are (M pair, N tile of 256); consecutive items share the A rows (L2 hits), weights stay L2 resident
+//   * K and N that are not multiples of 64 / 256 (728): TMA zero-fills the K tail, the store clips the N tail
+//   * the residual / shortcut tensor is added in fp32 in the epilogue, before the single bf16 rounding
+#pragma once
+
+#include <cuda.h>
+
+#include "dwpw_gemm.cuh"     // packed fp32x2 helpers
+#include "sm100_prims.cuh"
+
+namespace dlv3p {
+
+constexpr int kBbBM = 128;
+constexpr int kBbBK = 64;
+constexpr int kBbBN = 256;
+constexpr int kBbThreads = 192;
+constexpr int kBbStages = 6;
+constexpr int kBbStageBytes = kBbBM * 128 + (kBbBN / 2) * 128;   // A 16 KB + half of B 16 KB per CTA
+constexpr int kBbStoreBytes = 4 * 2 * 4096;
+constexpr int kBbSmemBytes = kBbStages * kBbStageBytes + kBbStoreBytes + 2 * kBbBN * 4 + 256;
+
+struct BbGemmParams {
+  const CUtensorMap* tmap_a;     // [M, K] bf16 row-major, box {64, 128}, SWIZZLE_128B
+  const CUtensorMap* tmap_w;     // [Npad, Kpad] bf16 K-major (Npad % 256 == 0, zero padded), box {64, 128}, SWIZZLE_128B
+  const CUtensorMap* tmap_out;   // [M, N] bf16 (row stride = N), box {64, 32}, SWIZZLE_128B
+  const float* scale;            // [Npad] folded BN
+  const float* shift;            // [Npad]
+  const __nv_bfloat16* residual; // optional [M, N] added before rounding
+  int M, K, N;
+  int relu;
+  int m_pairs, n_tiles;
+  int debug;                     // benchmark aid: bit0 = skip the stores
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBbThreads, 1) bb_gemm_kernel(const __grid_constant__ BbGemmParams P) {
+  constexpr int BN = kBbBN;
+  constexpr int kStages = kBbStages;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * (kBbBM * 128);
+  uint8_t* smem_c = smem + kStages * kBbStageBytes;
+  float* s_scale = reinterpret_cast<float*>(smem_c + kBbStoreBytes);
+  float* s_shift = s_scale + BN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + BN);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tmem_full = bars + 2 * kStages;
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int total_items = P.m_pairs * P.n_tiles;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int kblocks = (P.K + kBbBK - 1) / kBbBK;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 2);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 256);
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 1) {
+    tmem_alloc_2sm(tmem_base_ptr, 512);
+    tmem_relinquish_2sm();
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (elect_one()) {
+      uint32_t stage = 0, phase = 0;
+      for (int item = cluster_id; item < total_items; item += num_clusters) {
+        const int nt = item % P.n_tiles;
+        const int tile = (item / P.n_tiles) * 2 + static_cast<int>(rank);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kBbStageBytes);
+          else mbar_arrive_cluster(&full_bar[stage], 0);
+          tma_load_2d_2sm(smem_a + stage * (kBbBM * 128), P.tmap_a, &full_bar[stage], kb * kBbBK, tile * kBbBM, kEvictNormal);
+          tma_load_2d_2sm(smem_b + stage * ((BN / 2) * 128), P.tmap_w, &full_bar[stage], kb * kBbBK, nt * BN + static_cast<int>(rank) * (BN / 2), kEvictLast);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN);
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int item = cluster_id; item < total_items; item += num_clusters, ++it) {
+        const uint32_t acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint64_t da = make_smem_desc_sw128(smem_u32(smem_a + stage * (kBbBM * 128)));
+            const uint64_t db = make_smem_desc_sw128(smem_u32(smem_b + stage * ((BN / 2) * 128)));
+#pragma unroll
+            for (int k = 0; k < kBbBK / 16; ++k)
+              umma_bf16_ss_2sm(tmem_d, smem_desc_advance(da, k * 32), smem_desc_advance(db, k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[stage]);
+            if (kb == kblocks - 1) umma_commit_2sm(&tmem_full[acc]);
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5 of both CTAs)
+    const int q = warp & 3;
+    uint32_t it = 0;
+    uint32_t store_buf = 0;
+    int ss_nt = -1;
+    uint8_t* my_c = smem_c + (warp - 2) * 2 * 4096;
+    for (int item = cluster_id; item < total_items; item += num_clusters, ++it) {
+      const int nt = item % P.n_tiles;
+      const int tile = (item / P.n_tiles) * 2 + static_cast<int>(rank);
+      const uint32_t acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int n0 = nt * BN;
+      const int ncols = min(BN, P.N - n0);
+      const int row = tile * kBbBM + q * 32 + lane;
+      const bool row_ok = row < P.M;
+      if (nt != ss_nt) {      // this N tile's BN scale / shift into shared memory (no L1 next to ~220 KB of dynamic smem)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = (warp - 2) * 32 + lane; i < BN; i += 128) {
+          s_scale[i] = __ldg(P.scale + n0 + i);
+          s_shift[i] = __ldg(P.shift + n0 + i);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        ss_nt = nt;
+      }
+      const __nv_bfloat16* res_row = P.residual ? P.residual + static_cast<size_t>(row_ok ? row : 0) * P.N + n0 : nullptr;
+      // residual values of the first 32 columns are requested before the accumulator is waited for
+      uint4 rnext[4];
+      auto load_res = [&](int c0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          rnext[j] = make_uint4(0u, 0u, 0u, 0u);
+          if (res_row && row_ok && c0 + j * 8 < ncols) rnext[j] = ldg_nc_v4(res_row + c0 + j * 8);
+        }
+      };
+      load_res(0);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int cb = 0; cb < BN / 64; ++cb) {
+        if (cb * 64 >= ncols) break;
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        const uint32_t cbuf = smem_u32(my_c + store_buf * 4096) + lane * 128;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int c0 = cb * 64 + half * 32;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + c0, v);
+          uint4 rcur[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
+          if (c0 + 32 < BN) load_res(c0 + 32);            // next 32 columns in flight during this block's arithmetic
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const ulonglong2 s0 = *reinterpret_cast<const ulonglong2*>(s_scale + c0 + j);
+            const ulonglong2 s1 = *reinterpret_cast<const ulonglong2*>(s_scale + c0 + j + 4);
+            const ulonglong2 t0 = *reinterpret_cast<const ulonglong2*>(s_shift + c0 + j);
+            const ulonglong2 t1 = *reinterpret_cast<const ulonglong2*>(s_shift + c0 + j + 4);
+            unsigned long long y0 = f32x2_fma(f32x2_make(v[j + 0], v[j + 1]), s0.x, t0.x);
+            unsigned long long y1 = f32x2_fma(f32x2_make(v[j + 2], v[j + 3]), s0.y, t0.y);
+            unsigned long long y2 = f32x2_fma(f32x2_make(v[j + 4], v[j + 5]), s1.x, t1.x);
+            unsigned long long y3 = f32x2_fma(f32x2_make(v[j + 6], v[j + 7]), s1.y, t1.y);
+            if (P.relu) {                                    // ReLU belongs to the conv branch, before the add
+              y0 = f32x2_make(__float_as_uint(fmaxf(f32x2_lo(y0), 0.f)), __float_as_uint(fmaxf(f32x2_hi(y0), 0.f)));
+              y1 = f32x2_make(__float_as_uint(fmaxf(f32x2_lo(y1), 0.f)), __float_as_uint(fmaxf(f32x2_hi(y1), 0.f)));
+              y2 = f32x2_make(__float_as_uint(fmaxf(f32x2_lo(y2), 0.f)), __float_as_uint(fmaxf(f32x2_hi(y2), 0.f)));
+              y3 = f32x2_make(__float_as_uint(fmaxf(f32x2_lo(y3), 0.f)), __float_as_uint(fmaxf(f32x2_hi(y3), 0.f)));
+            }
+            if (P.residual) {
+              const uint4 r = rcur[j >> 3];
+              const unsigned long long one = f32x2_make(0x3F800000u, 0x3F800000u);
+              y0 = f32x2_fma(bf16x2_to_f32x2(r.x), one, y0);
+              y1 = f32x2_fma(bf16x2_to_f32x2(r.y), one, y1);
+              y2 = f32x2_fma(bf16x2_to_f32x2(r.z), one, y2);
+              y3 = f32x2_fma(bf16x2_to_f32x2(r.w), one, y3);
+            }
+            const uint32_t chunk = static_cast<uint32_t>(half * 4 + (j >> 3)) ^ static_cast<uint32_t>(lane & 7);
+            sts_v4(cbuf + chunk * 16, make_uint4(f32x2_to_bf16x2(y0), f32x2_to_bf16x2(y1), f32x2_to_bf16x2(y2), f32x2_to_bf16x2(y3)));
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && !(P.debug & 1)) {
+          tma_store_2d(P.tmap_out, my_c + store_buf * 4096, n0 + cb * 64, tile * kBbBM + q * 32);
+          tma_store_commit();
+        }
+        store_buf ^= 1;
+      }
+      tcgen05_fence_before();
+      if (leader) mbar_arrive(&tmem_empty[acc]);
+      else mbar_arrive_cluster(&tmem_empty[acc], 0);
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+}  // namespace dlv3p

@@ -37,6 +37,14 @@ class Config(C.Structure):
                [('bn_eps', C.c_float), ('flags', C.c_int32)]
 
 
+class ModelConfig(C.Structure):
+    """dlv3p_model_config (include/dlv3p_model.h)."""
+    _fields_ = [(n, C.c_int32) for n in ('B', 'H', 'W', 'OS', 'NC', 'img_dtype', 'out_mode', 'flags')]
+
+
+IMG_U8, IMG_F32 = 0, 1
+MODEL_FLAG_KEEP_ALL = 1
+
 # every symbol include/dlv3p.h declares: (name, restype, argtypes)
 _vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
 _fp = C.POINTER(C.c_float)
@@ -83,6 +91,32 @@ SYMBOLS = [
     ('dlv3p_op_bn_apply', _i, [_i, _vp, C.c_int64, _i, _vp, _vp, _vp, C.c_float, _i, _vp, _vp]),
 ]
 
+# every symbol include/dlv3p_model.h declares
+_dp = C.POINTER(C.c_double)
+MODEL_SYMBOLS = [
+    ('dlv3p_model_create', _i, [C.POINTER(ModelConfig), _i, C.POINTER(_vp)]),
+    ('dlv3p_model_destroy', None, [_vp]),
+    ('dlv3p_model_last_error', C.c_char_p, [_vp]),
+    ('dlv3p_model_num_weights', _i, [_vp]),
+    ('dlv3p_model_weight_info', _i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.POINTER(_i)]),
+    ('dlv3p_model_set_weight', _i, [_vp, C.c_char_p, C.c_char_p, _fp, C.POINTER(C.c_int64), _i]),
+    ('dlv3p_model_finalize_weights', _i, [_vp]),
+    ('dlv3p_model_forward', _i, [_vp, _vp, _vp, _vp]),
+    ('dlv3p_model_forward_host', _i, [_vp, _vp, _vp]),
+    ('dlv3p_model_input_bytes', _i, [_vp, C.POINTER(_sz)]),
+    ('dlv3p_model_output_bytes', _i, [_vp, C.POINTER(_sz)]),
+    ('dlv3p_model_workspace_bytes', _i, [_vp, C.POINTER(_sz)]),
+    ('dlv3p_model_read_tap', _i, [_vp, C.c_char_p, _fp, _sz]),
+    ('dlv3p_model_tap_shape', _i, [_vp, C.c_char_p, C.POINTER(C.c_int64)]),
+    ('dlv3p_model_forward_from', _i, [_vp, C.c_char_p, _fp, _sz, _vp, _vp]),
+    ('dlv3p_model_launch_count', _i, [_vp, C.POINTER(C.c_int64)]),
+    ('dlv3p_model_profile_forward', _i, [_vp, _vp, _vp, _vp, C.POINTER(C.c_char_p), _fp, _dp, _dp, _i]),
+    ('dlv3p_op_bb_depthwise', _i, [_i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _fp, _fp, _fp, _vp, _vp]),
+    ('dlv3p_op_bb_pointwise', _i, [_i, _vp, C.c_int64, _i, _i, _fp, _fp, _fp, _i, _vp, _vp, _vp]),
+    ('dlv3p_op_conv3x3_c32', _i, [_i, _vp, _i, _i, _i, _fp, _fp, _fp, _vp, _vp]),
+    ('dlv3p_op_stem_conv', _i, [_i, _vp, _i, _i, _i, _i, _fp, _fp, _fp, _vp, _vp]),
+]
+
 _lib = None
 
 
@@ -96,7 +130,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         raise ImportError('libdlv3p.so not found at %s — build it first: python -c "import __graft_entry__ as g; g.build()" '
                           '(there is no CPU / PyTorch fallback for this path)' % p)
     lib = C.CDLL(p)
-    for name, res, args in SYMBOLS:
+    for name, res, args in SYMBOLS + MODEL_SYMBOLS:
         fn = getattr(lib, name)          # AttributeError here == header/library mismatch
         fn.restype = res
         fn.argtypes = args
@@ -302,6 +336,112 @@ class Context:
             pass
 
 
+class Model:
+    """One dlv3p_model: the whole DeepLabV3+ Xception network (backbone + head) with static shapes on one device."""
+
+    def __init__(self, device: int = 0, **cfg):
+        self.lib = load_library()
+        self.cfg = ModelConfig()
+        for k, v in cfg.items():
+            if not hasattr(self.cfg, k):
+                raise TypeError('unknown model config field %r' % k)
+            setattr(self.cfg, k, v)
+        self.device = device
+        h = C.c_void_p()
+        st = self.lib.dlv3p_model_create(C.byref(self.cfg), device, C.byref(h))
+        if st < 0:
+            raise Dlv3pError(st, (self.lib.dlv3p_model_last_error(None) or b'').decode())
+        self.handle = h
+
+    def _check(self, st: int) -> int:
+        if st < 0:
+            raise Dlv3pError(st, (self.lib.dlv3p_model_last_error(self.handle) or b'').decode())
+        return st
+
+    def weight_specs(self) -> List[Tuple[str, str, Tuple[int, ...]]]:
+        out = []
+        for i in range(self.lib.dlv3p_model_num_weights(self.handle)):
+            layer, var = C.c_char_p(), C.c_char_p()
+            shape = (C.c_int64 * 4)()
+            rank = C.c_int()
+            self._check(self.lib.dlv3p_model_weight_info(self.handle, i, C.byref(layer), C.byref(var), shape, C.byref(rank)))
+            out.append((layer.value.decode(), var.value.decode(), tuple(int(shape[j]) for j in range(rank.value))))
+        return out
+
+    def set_weight(self, layer: str, var: str, value: np.ndarray):
+        a = np.ascontiguousarray(value, dtype=np.float32)
+        shape = (C.c_int64 * a.ndim)(*a.shape)
+        self._check(self.lib.dlv3p_model_set_weight(self.handle, layer.encode(), var.encode(), a.ctypes.data_as(_fp), shape, a.ndim))
+
+    def finalize(self):
+        self._check(self.lib.dlv3p_model_finalize_weights(self.handle))
+
+    def input_bytes(self) -> int:
+        o = C.c_size_t()
+        self._check(self.lib.dlv3p_model_input_bytes(self.handle, C.byref(o)))
+        return o.value
+
+    def output_bytes(self) -> int:
+        o = C.c_size_t()
+        self._check(self.lib.dlv3p_model_output_bytes(self.handle, C.byref(o)))
+        return o.value
+
+    def workspace_bytes(self) -> int:
+        o = C.c_size_t()
+        self._check(self.lib.dlv3p_model_workspace_bytes(self.handle, C.byref(o)))
+        return o.value
+
+    def forward(self, d_images: int, d_out: int, stream: int = 0):
+        self._check(self.lib.dlv3p_model_forward(self.handle, d_images, d_out, stream))
+
+    def forward_host(self, h_images: np.ndarray, h_out: np.ndarray):
+        self._check(self.lib.dlv3p_model_forward_host(self.handle, h_images.ctypes.data, h_out.ctypes.data))
+
+    def profile(self, d_images: int, d_out: int, stream: int = 0, max_kernels: int = 512):
+        """[(kernel name, ms, algorithmic flops, algorithmic bytes)] of one forward, backbone first."""
+        names = (C.c_char_p * max_kernels)()
+        ms = (C.c_float * max_kernels)()
+        fl = (C.c_double * max_kernels)()
+        by = (C.c_double * max_kernels)()
+        n = self._check(self.lib.dlv3p_model_profile_forward(self.handle, d_images, d_out, stream, names, ms, fl, by, max_kernels))
+        return [(names[i].decode(), float(ms[i]), float(fl[i]), float(by[i])) for i in range(n)]
+
+    def tap_shape(self, name: str) -> Optional[Tuple[int, ...]]:
+        shape = (C.c_int64 * 4)()
+        if self.lib.dlv3p_model_tap_shape(self.handle, name.encode(), shape) < 0:
+            return None
+        return tuple(int(v) for v in shape)
+
+    def read_tap(self, name: str, shape: Optional[Sequence[int]] = None) -> np.ndarray:
+        shape = self.tap_shape(name) if shape is None else tuple(shape)
+        if shape is None:
+            raise KeyError('tap %r is not a backbone tap: pass its shape (head taps, see dlv3p_read_tap)' % name)
+        out = np.empty(shape, dtype=np.float32)
+        self._check(self.lib.dlv3p_model_read_tap(self.handle, name.encode(), out.ctypes.data_as(_fp), out.size))
+        return out
+
+    def forward_from(self, tap: str, value: np.ndarray, d_out: int, stream: int = 0):
+        """Overwrite a backbone tap with `value` (fp32, rounded to bf16 on the way) and run only the kernels after it."""
+        a = np.ascontiguousarray(value, np.float32)
+        self._check(self.lib.dlv3p_model_forward_from(self.handle, tap.encode(), a.ctypes.data_as(_fp), a.size, d_out, stream))
+
+    def launch_count(self) -> int:
+        a = C.c_int64()
+        self._check(self.lib.dlv3p_model_launch_count(self.handle, C.byref(a)))
+        return a.value
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            self.lib.dlv3p_model_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 # ---- standalone operators (unit parity tests) -------------------------------------------------
 def _f(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float32).ctypes.data_as(_fp)
@@ -340,6 +480,51 @@ def op_sepconv(x_bits: np.ndarray, dw_hwc, dw_scale, dw_shift, pw_kn, pw_scale, 
     _check(load_library().dlv3p_op_sepconv(device, dx.ptr, B, H, W, Cc, rate, _f(arrs[0]), _f(arrs[1]), _f(arrs[2]), N,
                                            _f(arrs[3]), _f(arrs[4]), _f(arrs[5]), do.ptr, None))
     return do.download((B, H, W, N), np.uint16)
+
+
+def op_bb_depthwise(x_bits: np.ndarray, w_hwc: np.ndarray, stride: int = 1, rate: int = 1, relu_in: bool = True, relu_out: bool = False,
+                    scale=None, shift=None, device=0) -> np.ndarray:
+    """Backbone depthwise half of SepConv_BN (layers.py:88-104): x uint16 bf16 [B,H,W,C] -> uint16 bf16 [B,ceil(H/s),ceil(W/s),C]."""
+    B, H, W, Cc = x_bits.shape
+    Ho, Wo = -(-H // stride), -(-W // stride)
+    dx = DeviceBuffer.from_numpy(x_bits, device)
+    do = DeviceBuffer(B * Ho * Wo * Cc * 2, device)
+    _check(load_library().dlv3p_op_bb_depthwise(device, dx.ptr, B, H, W, Cc, stride, rate, int(relu_in), int(relu_out), _f(w_hwc), _f(scale), _f(shift), do.ptr, None))
+    return do.download((B, Ho, Wo, Cc), np.uint16)
+
+
+def op_bb_pointwise(a_bits: np.ndarray, w_kn: np.ndarray, scale=None, shift=None, relu: bool = False, residual_bits: Optional[np.ndarray] = None,
+                    device=0) -> np.ndarray:
+    """Backbone 1x1 conv + BN [+ReLU] [+residual]: a uint16 bf16 [M,K], w fp32 [K,N] (any N % 8 == 0) -> uint16 bf16 [M,N]."""
+    M, K = a_bits.shape
+    N = w_kn.shape[1]
+    da = DeviceBuffer.from_numpy(a_bits, device)
+    dr = None if residual_bits is None else DeviceBuffer.from_numpy(residual_bits, device)
+    do = DeviceBuffer(M * N * 2, device)
+    _check(load_library().dlv3p_op_bb_pointwise(device, da.ptr, M, K, N, _f(w_kn), _f(scale), _f(shift), int(relu), None if dr is None else dr.ptr, do.ptr, None))
+    return do.download((M, N), np.uint16)
+
+
+def op_conv3x3_c32(x_bits: np.ndarray, w_hwio: np.ndarray, scale=None, shift=None, device=0) -> np.ndarray:
+    """entry_flow_conv1_2: x uint16 bf16 [B,H,W,32], w fp32 [3,3,32,64] -> uint16 bf16 [B,H,W,64] (BN + ReLU)."""
+    B, H, W, Cc = x_bits.shape
+    assert Cc == 32 and tuple(w_hwio.shape) == (3, 3, 32, 64)
+    dx = DeviceBuffer.from_numpy(x_bits, device)
+    do = DeviceBuffer(B * H * W * 64 * 2, device)
+    _check(load_library().dlv3p_op_conv3x3_c32(device, dx.ptr, B, H, W, _f(w_hwio), _f(scale), _f(shift), do.ptr, None))
+    return do.download((B, H, W, 64), np.uint16)
+
+
+def op_stem_conv(img: np.ndarray, w_hwio: np.ndarray, scale=None, shift=None, device=0) -> np.ndarray:
+    """entry_flow_conv1_1: uint8 (normalised on the device) or fp32 [B,H,W,3], w fp32 [3,3,3,32] -> uint16 bf16 [B,ceil(H/2),ceil(W/2),32]."""
+    B, H, W, _ = img.shape
+    f32 = img.dtype != np.uint8
+    a = np.ascontiguousarray(img, np.float32 if f32 else np.uint8)
+    dx = DeviceBuffer.from_numpy(a, device)
+    Ho, Wo = -(-H // 2), -(-W // 2)
+    do = DeviceBuffer(B * Ho * Wo * 32 * 2, device)
+    _check(load_library().dlv3p_op_stem_conv(device, dx.ptr, IMG_F32 if f32 else IMG_U8, B, H, W, _f(w_hwio), _f(scale), _f(shift), do.ptr, None))
+    return do.download((B, Ho, Wo, 32), np.uint16)
 
 
 def op_resize_bilinear(x_bits: np.ndarray, ho: int, wo: int, device=0) -> np.ndarray:
