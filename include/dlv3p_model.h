@@ -34,8 +34,9 @@ enum { /* img_dtype */
 };
 
 enum { /* flags */
-  DLV3P_MODEL_FLAG_KEEP_ALL = 1 /* every intermediate keeps its own tensor (block-level parity taps); default: the 16 middle-flow
-                                   units ping-pong over four buffers and only the last unit's tap is meaningful */
+  DLV3P_MODEL_FLAG_KEEP_ALL = 1, /* every intermediate keeps its own tensor (block-level parity taps); default: the 16 middle-flow
+                                    units ping-pong over four buffers and only the last unit's tap is meaningful */
+  DLV3P_MODEL_FLAG_NO_PDL = 2    /* measurement aid: launch the backbone kernels without programmatic dependent launch */
 };
 
 typedef struct dlv3p_model_config {
@@ -106,6 +107,11 @@ int dlv3p_op_conv3x3_c32(int device, const void* x_bf16, int B, int H, int W, co
  * w_hwio: HOST fp32 [3,3,3,32]; out: device bf16 [B,ceil(H/2),ceil(W/2),32]. */
 int dlv3p_op_stem_conv(int device, const void* img, int img_dtype, int B, int H, int W, const float* w_hwio_fp32, const float* scale, const float* shift,
                        void* out_bf16, void* cuda_stream);
+
+/* Benchmark aid (tools/kbench_bb.py): average ms per launch of ONE backbone operator on synthetic device data (CUDA events).
+ * op 0 pointwise GEMM {M, K, N, residual, BN (0 = automatic)}; op 1 depthwise {B, H, W, C, stride, rate}.
+ * flags: per-kernel debug bits that switch parts of the kernel off to attribute time; results are then meaningless. */
+int dlv3p_op_bb_time(int device, int op, const int64_t* dims, int ndims, int iters, int flags, float* ms_out);
 
 #ifdef __cplusplus
 }

@@ -97,6 +97,8 @@ def test_backbone_depthwise(gpu, stride, rate, relu_in, relu_out, B, H, W, C):
     (1024, 1536, 2048, True, False),    # exit flow: 8 N tiles, ReLU
     (77, 256, 728, False, True),        # conv shortcut sum, M < one tile
     (4096, 1024, 1536, True, False),
+    (33000, 256, 1096, False, True),    # short last N tile (fewer residual boxes than the other tiles) on several rounds per CTA pair
+    (20000, 64, 1800, False, True),
 ])
 def test_backbone_pointwise(gpu, M, K, N, relu, res):
     rng = np.random.default_rng(M + K + N)

@@ -84,6 +84,8 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3x3_c32_kernel(const __grid
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_ptr;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     if (elect_one()) {

@@ -30,12 +30,14 @@ struct StemParams {
 __global__ void __launch_bounds__(128) stem_conv_kernel(const StemParams P) {
   __shared__ __align__(16) float s_w[27 * 32];
   __shared__ float s_scale[32], s_shift[32];
+  pdl_launch_dependents();
   for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) s_w[i] = P.w[i];
   if (threadIdx.x < 32) {
     s_scale[threadIdx.x] = P.scale[threadIdx.x];
     s_shift[threadIdx.x] = P.shift[threadIdx.x];
   }
   __syncthreads();
+  pdl_wait();          // the output buffer may still be read by the previous step's kernels
   const long long total = static_cast<long long>(P.B) * P.Ho * P.Wo;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= total) return;
@@ -101,6 +103,7 @@ struct BbDwParams {
   int B, C, Cpad, Ho, Wo;
   int tiles_x, tiles_y, cgroups;
   int relu_in, relu_out;
+  int debug;                   // benchmark aid: bit0 skip the global stores, bit1 skip the stencil arithmetic
 };
 
 template <int S, int R, int TH, int TW>
@@ -108,106 +111,161 @@ struct BbDwCfg {
   static constexpr int IH = (TH - 1) * S + 2 * R + 1;
   static constexpr int IW = (TW - 1) * S + 2 * R + 1;
   static constexpr int kInBytes = IH * IW * 128;
+  static constexpr int kTapBytes = 10 * 64 * 4 + 16;           // 9 taps + shift of the tile's 64 channels + the decoded item (g, tx, ty, b)
+  static constexpr int kStageBytes = (kInBytes + kTapBytes + 127) / 128 * 128;
+  static constexpr int kStages = 2;
   static constexpr int kBlocks = (TH / 4) * (TW / 4);          // 4 x 4 output blocks per tile
-  static constexpr int kWarps = kBlocks < 8 ? kBlocks : 8;
-  static constexpr int kThreads = kWarps * 32;
-  static constexpr int kSmemBytes = kInBytes + 128 + 16;       // + alignment slack + the mbarrier
+  static constexpr int kWarps = kBlocks < 8 ? kBlocks : 8;     // compute warps
+  static constexpr int kThreads = (kWarps + 1) * 32;           // + the producer warp
+  static constexpr int kSmemBytes = kStages * kStageBytes + 128 + 64;   // + alignment slack + the mbarriers
 };
 
-// CTA = (image, TH x TW output tile, 64-channel group): ONE TMA box brings the input window (halo included; out-of-bounds
-// rows / columns / channels arrive as zeros) into shared memory pixel-major [IH][IW][64 ch].  Warp = a 4 x 4 block of
-// output pixels, lane = one channel pair: every shared-memory access of a warp is one conflict-free 128-byte pixel row,
-// every global store one full 128-byte line of a pixel.  Rolling window over the input rows of the block: each input value
-// is loaded once per block and feeds up to nine packed-fp32 FMAs.
+// Persistent CTAs over (image, TH x TW output tile, 64-channel group) work items, channel group fastest (concurrent CTAs read
+// neighbouring 128-byte segments of the same pixels).  A producer warp keeps a 2-stage ring full: per item ONE TMA box brings the
+// input window (halo included; out-of-bounds rows / columns / channels arrive as zeros = ZeroPadding2D / 'same') into shared
+// memory pixel-major [IH][IW][64 ch], and the group's taps + shift next to it.  Compute warp = a 4 x 4 block of output pixels,
+// lane = one channel pair: every shared-memory access of a warp is one conflict-free 128-byte pixel row, every global store one
+// full 128-byte line of a pixel.  Rolling window over the input rows of the block: each input value is loaded once per block
+// and feeds up to nine packed-fp32 FMAs.
 template <int S, int R, int TH, int TW>
 __global__ void __launch_bounds__(BbDwCfg<S, R, TH, TW>::kThreads) bb_depthwise_kernel(const __grid_constant__ BbDwParams P) {
   using Cfg = BbDwCfg<S, R, TH, TW>;
   extern __shared__ __align__(128) uint8_t smem_dw[];
-  uint8_t* smem_in = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dw) + 127) & ~static_cast<uintptr_t>(127));
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_in + Cfg::kInBytes);
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dw) + 127) & ~static_cast<uintptr_t>(127));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);   // [kStages]
+  uint64_t* empty_bar = full_bar + Cfg::kStages;                                              // [kStages]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int t = blockIdx.x;
-  const int g = t % P.cgroups; t /= P.cgroups;
-  const int tx = t % P.tiles_x; t /= P.tiles_x;
-  const int ty = t % P.tiles_y;
-  const int b = t / P.tiles_y;
+  const int num_items = P.B * P.tiles_y * P.tiles_x * P.cgroups;
   if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], Cfg::kWarps);
+    }
     fence_barrier_init();
   }
+  pdl_launch_dependents();
   __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_arrive_expect_tx(bar, Cfg::kInBytes);
-    tma_load_4d(smem_in, P.tmap_x, bar, g * 64, tx * TW * S - R, ty * TH * S - R, b, kEvictNormal);
-  }
-  // taps + shift of this lane's channel pair (global, L2-resident; overlaps the TMA)
-  unsigned long long wt[9], sh;
-  {
-    const float* wp = P.w + g * 64 + lane * 2;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      const float2 w2 = __ldg(reinterpret_cast<const float2*>(wp + static_cast<size_t>(k) * P.Cpad));
-      wt[k] = pack_f32x2(w2.x, w2.y);
-    }
-    const float2 s2 = __ldg(reinterpret_cast<const float2*>(P.shift + g * 64 + lane * 2));
-    sh = pack_f32x2(s2.x, s2.y);
-  }
-  const bool ch_ok = g * 64 + lane * 2 < P.C;
-  mbar_wait(bar, 0);
-  constexpr int WW = 3 * S + 2 * R + 1;      // input window of a 4 x 4 output block
-  for (int bi = warp; bi < Cfg::kBlocks; bi += Cfg::kWarps) {
-    const int by = bi / (TW / 4), bx = bi % (TW / 4);
-    const uint32_t base = smem_u32(smem_in) + ((by * 4 * S) * Cfg::IW + bx * 4 * S) * 128 + lane * 4;
-    unsigned long long acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = sh;
-#pragma unroll
-    for (int wr = 0; wr < WW; ++wr) {
-      unsigned long long x[WW];
-#pragma unroll
-      for (int cc = 0; cc < WW; ++cc) {
-        // only the columns some tap of some output column reads
-        bool used = false;
-#pragma unroll
-        for (int oc = 0; oc < 4; ++oc)
-#pragma unroll
-          for (int dx = 0; dx < 3; ++dx) used = used || (oc * S + dx * R == cc);
-        if (used) {
-          uint32_t raw = lds_u32(base + (wr * Cfg::IW + cc) * 128);
-          if (P.relu_in) raw = relu_bf16x2(raw);
-          x[cc] = bf16x2_to_f32x2(raw);
-        } else {
-          x[cc] = 0ull;
-        }
+  if (warp == Cfg::kWarps) {
+    // ------------------------------------------------------------------ producer warp
+    pdl_wait();          // the input is the previous kernel's output; the compute warps are ordered behind this through full_bar
+    uint32_t stage = 0, phase = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      int t = item;
+      const int g = t % P.cgroups; t /= P.cgroups;
+      const int tx = t % P.tiles_x; t /= P.tiles_x;
+      const int ty = t % P.tiles_y;
+      const int b = t / P.tiles_y;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint8_t* st = smem + stage * Cfg::kStageBytes;
+      float* taps = reinterpret_cast<float*>(st + Cfg::kInBytes);
+      // taps [9][64] + shift [64] of this group: 640 floats, 20 per lane
+      for (int i = lane; i < 640; i += 32) {
+        const int k = i >> 6, c = i & 63;
+        taps[i] = k < 9 ? __ldg(P.w + static_cast<size_t>(k) * P.Cpad + g * 64 + c) : __ldg(P.shift + g * 64 + c);
       }
+      if (lane == 0) *reinterpret_cast<int4*>(taps + 640) = make_int4(g, tx, ty, b);   // decoded once: the consumers skip the divisions
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kInBytes);    // release semantics: the tap stores above are visible to the waiters
+        tma_load_4d(st, P.tmap_x, &full_bar[stage], g * 64, tx * TW * S - R, ty * TH * S - R, b, kEvictNormal);
+      }
+      if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+    }
+    return;
+  }
+  // -------------------------------------------------------------------- compute warps
+  constexpr int WW = 3 * S + 2 * R + 1;      // input window of a 4 x 4 output block
+  uint32_t stage = 0, phase = 0;
+  const uint32_t pstride = static_cast<uint32_t>(P.C) >> 1;            // one pixel / one output row in 32-bit words
+  const uint32_t rstride = static_cast<uint32_t>(P.Wo) * pstride;
+  for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    const uint8_t* st = smem + stage * Cfg::kStageBytes;
+    mbar_wait(&full_bar[stage], phase);
+    const int4 it4 = *reinterpret_cast<const int4*>(st + Cfg::kInBytes + 2560);
+    const int g = it4.x, tx = it4.y, ty = it4.z, b = it4.w;
+    unsigned long long wt[9], sh;
+    {
+      const float* tp = reinterpret_cast<const float*>(st + Cfg::kInBytes) + lane * 2;
 #pragma unroll
-      for (int orow = 0; orow < 4; ++orow) {
+      for (int k = 0; k < 9; ++k) {
+        const float2 w2 = *reinterpret_cast<const float2*>(tp + k * 64);
+        wt[k] = pack_f32x2(w2.x, w2.y);
+      }
+      const float2 s2 = *reinterpret_cast<const float2*>(tp + 9 * 64);
+      sh = pack_f32x2(s2.x, s2.y);
+    }
+    const bool ch_ok = g * 64 + lane * 2 < P.C;
+    for (int bi = warp; bi < Cfg::kBlocks; bi += Cfg::kWarps) {
+      const int by = bi / (TW / 4), bx = bi % (TW / 4);
+      const int oy0 = ty * TH + by * 4, ox0 = tx * TW + bx * 4;
+      if (oy0 >= P.Ho || ox0 >= P.Wo) continue;          // block entirely outside the image (partial tiles)
+      const uint32_t base = smem_u32(st) + ((by * 4 * S) * Cfg::IW + bx * 4 * S) * 128 + lane * 4;
+      unsigned long long acc[4][4];
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-          if (orow * S + dy * R != wr) continue;
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = sh;
+#pragma unroll
+      for (int wr = 0; wr < ((P.debug & 2) ? 0 : WW); ++wr) {
+        unsigned long long x[WW];
+#pragma unroll
+        for (int cc = 0; cc < WW; ++cc) {
+          // only the columns some tap of some output column reads
+          bool used = false;
 #pragma unroll
           for (int oc = 0; oc < 4; ++oc)
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx) ffma2(acc[orow][oc], wt[dy * 3 + dx], x[oc * S + dx * R]);
+            for (int dx = 0; dx < 3; ++dx) used = used || (oc * S + dx * R == cc);
+          if (used) {
+            uint32_t raw = lds_u32(base + (wr * Cfg::IW + cc) * 128);
+            if (P.relu_in) raw = relu_bf16x2(raw);
+            x[cc] = bf16x2_to_f32x2(raw);
+          } else {
+            x[cc] = 0ull;
+          }
+        }
+#pragma unroll
+        for (int orow = 0; orow < 4; ++orow) {
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            if (orow * S + dy * R != wr) continue;
+#pragma unroll
+            for (int oc = 0; oc < 4; ++oc)
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) ffma2(acc[orow][oc], wt[dy * 3 + dx], x[oc * S + dx * R]);
+          }
         }
       }
-    }
-    const int oy0 = ty * TH + by * 4, ox0 = tx * TW + bx * 4;
+      // one 64-bit address per block, 32-bit word offsets from there
+      uint32_t* o0 = reinterpret_cast<uint32_t*>(P.out + ((static_cast<size_t>(b) * P.Ho + oy0) * P.Wo + ox0) * P.C + g * 64) + lane;
+      if (P.relu_out) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int oy = oy0 + i;
-      if (oy >= P.Ho) continue;
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int ox = ox0 + j;
-        if (ox >= P.Wo || !ch_ok) continue;
-        const uint32_t v = P.relu_out ? f32x2_to_bf16x2_relu(acc[i][j]) : f32x2_to_bf16x2(acc[i][j]);
-        uint32_t* o = reinterpret_cast<uint32_t*>(P.out + ((static_cast<size_t>(b) * P.Ho + oy) * P.Wo + ox) * P.C + g * 64) + lane;
-        *o = v;
+          for (int j = 0; j < 4; ++j) acc[i][j] = static_cast<unsigned long long>(f32x2_to_bf16x2_relu(acc[i][j]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = static_cast<unsigned long long>(f32x2_to_bf16x2(acc[i][j]));
+      }
+      if (P.debug & 1) continue;
+      if (ch_ok && oy0 + 4 <= P.Ho && ox0 + 4 <= P.Wo) {      // interior block: 16 unpredicated stores
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o0[i * rstride + j * pstride] = static_cast<uint32_t>(acc[i][j]);
+      } else if (ch_ok) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (oy0 + i < P.Ho && ox0 + j < P.Wo) o0[i * rstride + j * pstride] = static_cast<uint32_t>(acc[i][j]);
       }
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[stage]);       // this warp is done reading the stage
+    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
   }
 }
 
@@ -215,6 +273,8 @@ __global__ void __launch_bounds__(BbDwCfg<S, R, TH, TW>::kThreads) bb_depthwise_
 // out[b, i, j, :] = x[b, 2i, 2j, :]  (16-byte vectors; C % 8 == 0)
 __global__ void __launch_bounds__(256) subsample2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int H, int W, int C,
                                                          int Ho, int Wo) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cv = C / 8;
   const long long total = static_cast<long long>(B) * Ho * Wo * cv;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {

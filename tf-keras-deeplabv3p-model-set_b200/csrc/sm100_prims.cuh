@@ -366,4 +366,11 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
                : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// launch_dependents: the next kernel of the stream (launched with programmaticStreamSerializationAllowed) may start its CTAs as
+// resources free up; wait: blocks until every prerequisite grid has completed and its memory is visible.  Both are no-ops in a
+// kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 }  // namespace dlv3p

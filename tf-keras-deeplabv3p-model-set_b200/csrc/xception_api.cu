@@ -15,6 +15,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/dlv3p_model.h"
@@ -96,6 +97,25 @@ bool tm_nhwc(CUtensorMap* tm, const void* base, uint64_t B, uint64_t H, uint64_t
   return tm_encode(tm, base, 4, d, s, b, sw, err);
 }
 
+// Launch with programmatic stream serialization: the kernel's prologue (barrier init, TMEM allocation, tap / weight preloads)
+// overlaps the tail of the previous kernel of the stream; every kernel of the backbone orders itself behind its producer with
+// griddepcontrol.wait before it touches an activation (sm100_prims.cuh).
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+bool g_pdl = true;      // per launch sequence (dlv3p_model_config.flags bit 1 turns it off for A/B measurements)
+
 // ---- depthwise kernel variants: (stride, rate) -> tile shape
 struct DwVariant { int S, R, TH, TW; };
 bool dw_variant(int stride, int rate, DwVariant* v) {
@@ -116,11 +136,15 @@ cudaError_t launch_dw_t(const BbDwParams& P, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr_done[dev & 63] = true;
   }
-  const long long blocks = static_cast<long long>(P.B) * P.tiles_y * P.tiles_x * P.cgroups;
-  bb_depthwise_kernel<S, R, TH, TW><<<static_cast<unsigned>(blocks), Cfg::kThreads, Cfg::kSmemBytes, st>>>(P);
-  return cudaGetLastError();
+  static int sms[64] = {};
+  if (!sms[dev & 63]) cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+  const long long items = static_cast<long long>(P.B) * P.tiles_y * P.tiles_x * P.cgroups;
+  const int per_sm = (227 * 1024) / (Cfg::kSmemBytes + 1024) > 0 ? (227 * 1024) / (Cfg::kSmemBytes + 1024) : 1;   // persistent: every CTA resident
+  const long long cap = static_cast<long long>(sms[dev & 63]) * (per_sm < 4 ? per_sm : 4);
+  return launch_pdl(g_pdl, bb_depthwise_kernel<S, R, TH, TW>, dim3(static_cast<unsigned>(items < cap ? items : cap)), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, P);
 }
 cudaError_t launch_dw(const DwVariant& v, const BbDwParams& P, cudaStream_t st) {
+  if (v.S == 1 && v.R == 1 && v.TH == 4) return launch_dw_t<1, 1, 4, 32>(P, st);
   if (v.S == 1 && v.R == 1) return launch_dw_t<1, 1, 8, 32>(P, st);
   if (v.S == 2 && v.R == 1) return launch_dw_t<2, 1, 8, 16>(P, st);
   if (v.S == 1 && v.R == 2) return launch_dw_t<1, 2, 8, 32>(P, st);
@@ -132,19 +156,41 @@ void dw_box(const DwVariant& v, uint32_t* bw, uint32_t* bh) {
   *bw = static_cast<uint32_t>((v.TW - 1) * v.S + 2 * v.R + 1);
 }
 
-cudaError_t launch_bb_gemm(const BbGemmParams& P, int num_sms, cudaStream_t st) {
+template <int BN, bool kRes>
+cudaError_t launch_bb_gemm_t(const BbGemmParams& P, int num_sms, cudaStream_t st) {
   static bool attr_done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(bb_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBbSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(bb_gemm_kernel<BN, kRes>, cudaFuncAttributeMaxDynamicSharedMemorySize, BbCfg<BN, kRes>::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_done[dev & 63] = true;
   }
   const int items = P.m_pairs * P.n_tiles;
   const int grid = 2 * items < num_sms ? 2 * items : (num_sms & ~1);
-  bb_gemm_kernel<<<grid, kBbThreads, kBbSmemBytes, st>>>(P);
-  return cudaGetLastError();
+  return launch_pdl(g_pdl, bb_gemm_kernel<BN, kRes>, dim3(grid), dim3(kBbThreads), BbCfg<BN, kRes>::kSmemBytes, st, P);
+}
+cudaError_t launch_bb_gemm(int BN, const BbGemmParams& P, int num_sms, cudaStream_t st) {
+  const bool res = P.tmap_res != nullptr;     // the residual variant trades pipeline stages for the residual staging buffers
+  switch (BN) {
+    case 256: return res ? launch_bb_gemm_t<256, true>(P, num_sms, st) : launch_bb_gemm_t<256, false>(P, num_sms, st);
+    case 192: return res ? launch_bb_gemm_t<192, true>(P, num_sms, st) : launch_bb_gemm_t<192, false>(P, num_sms, st);
+    case 128: return res ? launch_bb_gemm_t<128, true>(P, num_sms, st) : launch_bb_gemm_t<128, false>(P, num_sms, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+// N tile of a pointwise GEMM: the candidate that needs the fewest tile-columns over all rounds of the CTA pairs (work items are
+// (M pair, N tile); every round costs one tile of BN columns), larger tiles on ties (fewer passes over A)
+int pick_bb_bn(int M, int N, int num_sms) {
+  const int m_pairs = cdiv(cdiv(M, kBbBM), 2), clusters = num_sms / 2 > 0 ? num_sms / 2 : 1;
+  int best = 256;
+  long long best_cost = -1;
+  for (int bn : {256, 192, 128}) {
+    const long long items = static_cast<long long>(m_pairs) * cdiv(N, bn);
+    const long long cost = (items + clusters - 1) / clusters * bn;
+    if (best_cost < 0 || cost < best_cost) { best = bn; best_cost = cost; }
+  }
+  return best;
 }
 cudaError_t launch_conv3x3(const Conv3x3Params& P, int num_sms, cudaStream_t st) {
   static bool attr_done[64] = {};
@@ -156,8 +202,7 @@ cudaError_t launch_conv3x3(const Conv3x3Params& P, int num_sms, cudaStream_t st)
     attr_done[dev & 63] = true;
   }
   const int grid = P.num_tiles < num_sms ? P.num_tiles : num_sms;
-  conv3x3_c32_kernel<<<grid, kC3Threads, kC3SmemBytes, st>>>(P);
-  return cudaGetLastError();
+  return launch_pdl(g_pdl, conv3x3_c32_kernel, dim3(grid), dim3(kC3Threads), kC3SmemBytes, st, P);
 }
 
 // ---- host-side packing
@@ -220,7 +265,7 @@ struct Op {
   std::string bn;        // its BatchNormalization layer
   int in = -1, out = -1, res = -1;   // tensor indices
   int stride = 1, rate = 1, relu_in = 0, relu_out = 0;
-  int K = 0, N = 0, Kpad = 0, Npad = 0, Cpad = 0;
+  int K = 0, N = 0, Kpad = 0, Npad = 0, Cpad = 0, BN = 256;
   DwVariant dv{1, 1, 8, 32};
   // device weights
   uint16_t* w16 = nullptr;
@@ -613,7 +658,8 @@ int dlv3p_model_finalize_weights(dlv3p_model* m) {
       ok = ok && tm_nhwc(&m->h_tm[o.tm0], ti.p, ti.B, ti.H, ti.W, ti.C, 64, bw, bh, CU_TENSOR_MAP_SWIZZLE_NONE, &terr);
     } else if (o.kind == OP_PW) {
       o.Kpad = cdiv(o.K, 64) * 64;
-      o.Npad = cdiv(o.N, 256) * 256;
+      o.BN = pick_bb_bn(m->tensors[o.out].M(), o.N, m->num_sms);
+      o.Npad = cdiv(o.N, o.BN) * o.BN;
       if ((r = m_upload(m, &o.w16, pack_kn(MW(m, o.name, "kernel"), o.K, o.N, o.Npad, o.Kpad)))) return r;
       Fold f = mfold(m, o.bn, o.N);
       std::vector<float> s(o.Npad, 0.0f), t(o.Npad, 0.0f);
@@ -622,10 +668,11 @@ int dlv3p_model_finalize_weights(dlv3p_model* m) {
       if ((r = m_upload(m, &o.scale, s)) || (r = m_upload(m, &o.shift, t))) return r;
       const Tensor& ti = m->tensors[o.in];
       const Tensor& to = m->tensors[o.out];
-      o.tm0 = slot(); slot(); slot();
+      o.tm0 = slot(); slot(); slot(); slot();
       ok = ok && tm_2d(&m->h_tm[o.tm0], ti.p, ti.M(), o.K, o.K, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B, &terr);
-      ok = ok && tm_2d(&m->h_tm[o.tm0 + 1], o.w16, o.Npad, o.Kpad, o.Kpad, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B, &terr);
+      ok = ok && tm_2d(&m->h_tm[o.tm0 + 1], o.w16, o.Npad, o.Kpad, o.Kpad, 64, o.BN / 2, CU_TENSOR_MAP_SWIZZLE_128B, &terr);
       ok = ok && tm_2d(&m->h_tm[o.tm0 + 2], to.p, to.M(), o.N, o.N, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B, &terr);
+      if (o.res >= 0) ok = ok && tm_2d(&m->h_tm[o.tm0 + 3], m->tensors[o.res].p, to.M(), o.N, o.N, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B, &terr);
     }
     if (!ok) return mfail(m, DLV3P_ERR_CUDA, terr);
   }
@@ -665,6 +712,7 @@ int dlv3p_model_launch_count(const dlv3p_model* m, int64_t* last_forward) {
 static int run_backbone(dlv3p_model* m, const void* d_images, cudaStream_t st, int first_op = 0) {
   const dlv3p_model_config& g = m->cfg;
   m->launches_last = 0;
+  g_pdl = !(g.flags & DLV3P_MODEL_FLAG_NO_PDL) && !m->profiling;
   for (size_t oi = static_cast<size_t>(first_op); oi < m->ops.size(); ++oi) {
     Op& o = m->ops[oi];
     if (m->profiling) {
@@ -680,8 +728,7 @@ static int run_backbone(dlv3p_model* m, const void* d_images, cudaStream_t st, i
       P.img = d_images; P.img_f32 = g.img_dtype == DLV3P_IMG_F32; P.w = o.wf; P.scale = o.scale; P.shift = o.shift; P.out = to.p;
       P.B = g.B; P.H = g.H; P.W = g.W; P.Ho = to.H; P.Wo = to.W; P.pad_t = m->pad_t; P.pad_l = m->pad_l;
       const long long total = static_cast<long long>(to.B) * to.H * to.W;
-      stem_conv_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, st>>>(P);
-      e = cudaGetLastError();
+      e = launch_pdl(g_pdl, stem_conv_kernel, dim3(static_cast<unsigned>((total + 127) / 128)), dim3(128), 0, st, P);
     } else if (o.kind == OP_CONV3) {
       const Tensor& to = m->tensors[o.out];
       Conv3x3Params P{};
@@ -700,17 +747,17 @@ static int run_backbone(dlv3p_model* m, const void* d_images, cudaStream_t st, i
       const Tensor& to = m->tensors[o.out];
       BbGemmParams P{};
       P.tmap_a = &m->d_tm[o.tm0]; P.tmap_w = &m->d_tm[o.tm0 + 1]; P.tmap_out = &m->d_tm[o.tm0 + 2];
-      P.scale = o.scale; P.shift = o.shift; P.residual = o.res >= 0 ? m->tensors[o.res].p : nullptr;
-      P.M = to.M(); P.K = o.K; P.N = o.N; P.relu = o.relu_out; P.m_pairs = cdiv(cdiv(P.M, kBbBM), 2); P.n_tiles = o.Npad / kBbBN;
-      e = launch_bb_gemm(P, m->num_sms, st);
+      P.scale = o.scale; P.shift = o.shift; P.tmap_res = o.res >= 0 ? &m->d_tm[o.tm0 + 3] : nullptr;
+      P.M = to.M(); P.K = o.K; P.N = o.N; P.relu = o.relu_out; P.m_pairs = cdiv(cdiv(P.M, kBbBM), 2); P.n_tiles = o.Npad / o.BN;
+      e = launch_bb_gemm(o.BN, P, m->num_sms, st);
     } else {
       const Tensor& ti = m->tensors[o.in];
       const Tensor& to = m->tensors[o.out];
       const size_t n = to.elems() / 8;
       size_t gsz = (n + 255) / 256;
       if (gsz > static_cast<size_t>(m->num_sms) * 16) gsz = static_cast<size_t>(m->num_sms) * 16;
-      subsample2_kernel<<<static_cast<unsigned>(gsz), 256, 0, st>>>(ti.p, to.p, ti.B, ti.H, ti.W, ti.C, to.H, to.W);
-      e = cudaGetLastError();
+      e = launch_pdl(g_pdl, subsample2_kernel, dim3(static_cast<unsigned>(gsz)), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(ti.p), to.p, ti.B, ti.H, ti.W,
+                     ti.C, to.H, to.W);
     }
     if (e != cudaSuccess) return mfail(m, DLV3P_ERR_CUDA, mfmt("launch %s: %s", o.name.c_str(), cudaGetErrorString(e)));
     ++m->launches_last;
@@ -919,7 +966,8 @@ int dlv3p_op_bb_pointwise(int device, const void* a, int64_t M, int K, int N, co
   if (r) return r;
   if (!a || !w_kn || !out || M < 1 || K < 8 || K % 8 || N < 8 || N % 8) return mfail(nullptr, DLV3P_ERR_INVALID, "op_bb_pointwise: bad arguments (K % 8, N % 8)");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-  const int Kpad = cdiv(K, 64) * 64, Npad = cdiv(N, 256) * 256;
+  const int BN = pick_bb_bn(static_cast<int>(M), N, sms);
+  const int Kpad = cdiv(K, 64) * 64, Npad = cdiv(N, BN) * BN;
   Tmp tmp;
   uint16_t* dw = tmp.put(pack_kn(w_kn, K, N, Npad, Kpad));
   std::vector<float> s(Npad, 0.0f), t(Npad, 0.0f);
@@ -927,17 +975,100 @@ int dlv3p_op_bb_pointwise(int device, const void* a, int64_t M, int K, int N, co
   float* ds = tmp.put(s);
   float* dt = tmp.put(t);
   std::string terr;
-  std::vector<CUtensorMap> tm(3);
-  if (!tm_2d(&tm[0], a, M, K, K, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B, &terr) || !tm_2d(&tm[1], dw, Npad, Kpad, Kpad, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B, &terr) ||
-      !tm_2d(&tm[2], out, M, N, N, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B, &terr)) return mfail(nullptr, DLV3P_ERR_CUDA, terr);
+  std::vector<CUtensorMap> tm(4);
+  if (!tm_2d(&tm[0], a, M, K, K, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B, &terr) || !tm_2d(&tm[1], dw, Npad, Kpad, Kpad, 64, BN / 2, CU_TENSOR_MAP_SWIZZLE_128B, &terr) ||
+      !tm_2d(&tm[2], out, M, N, N, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B, &terr) ||
+      (residual && !tm_2d(&tm[3], residual, M, N, N, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B, &terr))) return mfail(nullptr, DLV3P_ERR_CUDA, terr);
   CUtensorMap* dtm = tmp.put(tm);
   if (!dw || !ds || !dt || !dtm) return mfail(nullptr, DLV3P_ERR_NOMEM, "op_bb_pointwise: cudaMalloc failed");
   BbGemmParams P{};
-  P.tmap_a = &dtm[0]; P.tmap_w = &dtm[1]; P.tmap_out = &dtm[2]; P.scale = ds; P.shift = dt; P.residual = static_cast<const __nv_bfloat16*>(residual);
-  P.M = static_cast<int>(M); P.K = K; P.N = N; P.relu = relu; P.m_pairs = cdiv(cdiv(P.M, kBbBM), 2); P.n_tiles = Npad / kBbBN;
-  MCU(nullptr, launch_bb_gemm(P, sms, st));
+  P.tmap_a = &dtm[0]; P.tmap_w = &dtm[1]; P.tmap_out = &dtm[2]; P.tmap_res = residual ? &dtm[3] : nullptr; P.scale = ds; P.shift = dt;
+  P.M = static_cast<int>(M); P.K = K; P.N = N; P.relu = relu; P.m_pairs = cdiv(cdiv(P.M, kBbBM), 2); P.n_tiles = Npad / BN;
+  MCU(nullptr, launch_bb_gemm(BN, P, sms, st));
   MCU(nullptr, cudaStreamSynchronize(st));
   return DLV3P_OK;
+}
+
+// Benchmark aid (tools/kbench_bb.py): average ms per launch of ONE backbone operator on synthetic device data (CUDA events).
+// op 0: pointwise GEMM {M, K, N, residual(0/1), BN (0 = pick)}; op 1: depthwise {B, H, W, C, stride, rate}.
+// flags: the kernels' debug bits (GEMM bit0 = skip the stores); results are then meaningless.
+int dlv3p_op_bb_time(int device, int op, const int64_t* d, int ndims, int iters, int flags, float* ms_out) {
+  int sms = 0, r = op_begin(device, &sms);
+  if (r) return r;
+  if (!d || !ms_out || iters < 1) return mfail(nullptr, DLV3P_ERR_INVALID, "op_bb_time: bad arguments");
+  Tmp tmp;
+  cudaStream_t st = nullptr;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  std::string terr;
+  auto fill = [&](size_t n) -> uint16_t* {
+    std::vector<uint16_t> h(n);
+    uint32_t sd = 12345u;
+    for (size_t i = 0; i < n; ++i) { sd = sd * 1664525u + 1013904223u; h[i] = bf16_rne(static_cast<float>((sd >> 16) & 0xFF) / 128.0f - 1.0f); }
+    return tmp.put(h);
+  };
+  auto run = [&](auto&& launch) -> int {
+    for (int i = 0; i < 3; ++i) launch();
+    if (cudaStreamSynchronize(st) != cudaSuccess) return mfail(nullptr, DLV3P_ERR_CUDA, mfmt("op_bb_time warmup: %s", cudaGetErrorString(cudaGetLastError())));
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < iters; ++i) launch();
+    cudaEventRecord(e1, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return mfail(nullptr, DLV3P_ERR_CUDA, mfmt("op_bb_time: %s", cudaGetErrorString(e)));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *ms_out = ms / iters;
+    return DLV3P_OK;
+  };
+  int rc = DLV3P_ERR_INVALID;
+  g_pdl = false;
+  if (op == 0 && ndims >= 3) {
+    const int M = static_cast<int>(d[0]), K = static_cast<int>(d[1]), N = static_cast<int>(d[2]);
+    const bool res = ndims > 3 && d[3];
+    const int BN = (ndims > 4 && d[4]) ? static_cast<int>(d[4]) : pick_bb_bn(M, N, sms);
+    const int Kpad = cdiv(K, 64) * 64, Npad = cdiv(N, BN) * BN;
+    uint16_t* a = fill(static_cast<size_t>(M) * K);
+    uint16_t* w = fill(static_cast<size_t>(Npad) * Kpad);
+    uint16_t* rr = fill(static_cast<size_t>(M) * N);
+    uint16_t* o = fill(static_cast<size_t>(M) * N);
+    float* s = tmp.put(std::vector<float>(Npad, 1.0f));
+    float* t = tmp.put(std::vector<float>(Npad, 0.0f));
+    std::vector<CUtensorMap> tm(4);
+    if (!tm_2d(&tm[0], a, M, K, K, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B, &terr) || !tm_2d(&tm[1], w, Npad, Kpad, Kpad, 64, BN / 2, CU_TENSOR_MAP_SWIZZLE_128B, &terr) ||
+        !tm_2d(&tm[2], o, M, N, N, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B, &terr) || !tm_2d(&tm[3], rr, M, N, N, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B, &terr))
+      return mfail(nullptr, DLV3P_ERR_CUDA, terr);
+    CUtensorMap* dtm = tmp.put(tm);
+    BbGemmParams P{};
+    P.tmap_a = &dtm[0]; P.tmap_w = &dtm[1]; P.tmap_out = &dtm[2]; P.tmap_res = res ? &dtm[3] : nullptr; P.scale = s; P.shift = t;
+    P.M = M; P.K = K; P.N = N; P.relu = 0; P.m_pairs = cdiv(cdiv(M, kBbBM), 2); P.n_tiles = Npad / BN; P.debug = flags;
+    rc = run([&] { launch_bb_gemm(BN, P, sms, st); });
+  } else if (op == 1 && ndims >= 6) {
+    const int B = static_cast<int>(d[0]), H = static_cast<int>(d[1]), W = static_cast<int>(d[2]), C = static_cast<int>(d[3]);
+    DwVariant v;
+    if (!dw_variant(static_cast<int>(d[4]), static_cast<int>(d[5]), &v)) return mfail(nullptr, DLV3P_ERR_UNSUPPORTED, "op_bb_time: depthwise variant");
+    if (ndims > 6 && d[6] == 4 && v.S == 1 && v.R == 1) v.TH = 4;      // experiment: half-height tiles, four CTAs per SM
+    const int Cpad = cdiv(C, 64) * 64, Ho = cdiv(H, v.S), Wo = cdiv(W, v.S);
+    uint16_t* x = fill(static_cast<size_t>(B) * H * W * C);
+    uint16_t* o = fill(static_cast<size_t>(B) * Ho * Wo * C);
+    float* w = tmp.put(std::vector<float>(static_cast<size_t>(9) * Cpad, 0.1f));
+    float* sh = tmp.put(std::vector<float>(Cpad, 0.0f));
+    std::vector<CUtensorMap> tm(1);
+    uint32_t bw, bh;
+    dw_box(v, &bw, &bh);
+    if (!tm_nhwc(&tm[0], x, B, H, W, C, 64, bw, bh, CU_TENSOR_MAP_SWIZZLE_NONE, &terr)) return mfail(nullptr, DLV3P_ERR_CUDA, terr);
+    CUtensorMap* dtm = tmp.put(tm);
+    BbDwParams P{};
+    P.tmap_x = dtm; P.w = w; P.shift = sh; P.out = reinterpret_cast<__nv_bfloat16*>(o); P.B = B; P.C = C; P.Cpad = Cpad; P.Ho = Ho; P.Wo = Wo;
+    P.tiles_x = cdiv(Wo, v.TW); P.tiles_y = cdiv(Ho, v.TH); P.cgroups = Cpad / 64; P.relu_in = 1; P.relu_out = 0; P.debug = flags;
+    rc = run([&] { launch_dw(v, P, st); });
+  } else {
+    rc = mfail(nullptr, DLV3P_ERR_INVALID, "op_bb_time: unknown op / too few dims");
+  }
+  g_pdl = true;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return rc;
 }
 
 int dlv3p_op_conv3x3_c32(int device, const void* x, int B, int H, int W, const float* w_hwio, const float* scale, const float* shift, void* out,

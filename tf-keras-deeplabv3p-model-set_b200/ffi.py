@@ -44,6 +44,7 @@ class ModelConfig(C.Structure):
 
 IMG_U8, IMG_F32 = 0, 1
 MODEL_FLAG_KEEP_ALL = 1
+MODEL_FLAG_NO_PDL = 2
 
 # every symbol include/dlv3p.h declares: (name, restype, argtypes)
 _vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
@@ -115,6 +116,7 @@ MODEL_SYMBOLS = [
     ('dlv3p_op_bb_pointwise', _i, [_i, _vp, C.c_int64, _i, _i, _fp, _fp, _fp, _i, _vp, _vp, _vp]),
     ('dlv3p_op_conv3x3_c32', _i, [_i, _vp, _i, _i, _i, _fp, _fp, _fp, _vp, _vp]),
     ('dlv3p_op_stem_conv', _i, [_i, _vp, _i, _i, _i, _i, _fp, _fp, _fp, _vp, _vp]),
+    ('dlv3p_op_bb_time', _i, [_i, _i, C.POINTER(C.c_int64), _i, _i, _i, _fp]),
 ]
 
 _lib = None
@@ -617,6 +619,14 @@ def op_bn_train(x_bits: np.ndarray, gamma: np.ndarray, beta: np.ndarray, eps: fl
     bn_apply(dx.ptr, M, Cc, dst.ptr, dg.ptr, db.ptr, eps, relu, dy.ptr, None, device)
     synchronize(device)
     return dy.download((M, Cc), np.uint16), dst.download((2 * Cc + 1,), np.float32)
+
+
+def op_bb_time(op: int, dims: Sequence[int], iters: int = 20, flags: int = 0, device: int = 0) -> float:
+    """ms per launch of one BACKBONE operator on synthetic data (benchmark aid, see include/dlv3p_model.h)."""
+    arr = (C.c_int64 * len(dims))(*dims)
+    ms = C.c_float()
+    _check(load_library().dlv3p_op_bb_time(device, op, arr, len(dims), iters, flags, C.byref(ms)))
+    return ms.value
 
 
 def op_time(op: int, dims: Sequence[int], iters: int = 20, flags: int = 0, device: int = 0) -> float:
