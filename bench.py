@@ -277,12 +277,14 @@ def time_train_step(rank, world, local_rank, steps=10, warmup=3, batch=8):
     return rec
 
 
-KERNEL_OF = [('_shortcut_sample', 'subsample2_kernel'), ('_depthwise', 'bb_depthwise_kernel'), ('_pointwise', 'bb_gemm_kernel'),
+KERNEL_OF = [('_shortcut_sample', 'subsample2_kernel'), ('_sepconv', 'bb_sepconv_kernel'), ('_depthwise', 'bb_depthwise_kernel'), ('_pointwise', 'bb_gemm_kernel'),
              ('_shortcut', 'bb_gemm_kernel'), ('entry_flow_conv1_1', 'stem_conv_kernel'), ('entry_flow_conv1_2', 'conv3x3_c32_kernel')]
 HEAD_GEMMS = ('aspp_branches_gemm', 'concat_projection_gemm', 'feature_projection0_gemm', 'decoder_conv0_sepconv', 'decoder_conv1_sepconv', 'classifier_gemm')
 
 
 def kernel_of(op_name):
+    if not op_name.startswith(('entry_flow', 'middle_flow', 'exit_flow')):
+        return op_name      # head launches carry their own names
     for suffix, k in KERNEL_OF:
         if op_name.endswith(suffix):
             return k
@@ -506,7 +508,7 @@ def main():
         sum_ms = sum(a['ms'] for a in agg.values())
         dom = max(agg, key=lambda k: agg[k]['ms'])
         d = agg[dom]
-        tensor_bound = dom in ('bb_gemm_kernel', 'conv3x3_c32_kernel') or dom in HEAD_GEMMS
+        tensor_bound = dom in ('bb_gemm_kernel', 'conv3x3_c32_kernel', 'bb_sepconv_kernel') or dom in HEAD_GEMMS
         if tensor_bound:
             ach = d['flops'] / (d['ms'] / 1000.0) / 1e12
             roof = {'kernel': dom, 'bound': 'tensor', 'achieved': ach, 'peak': peaks['tflops_burst'], 'unit': 'TFLOP/s', 'frac': ach / peaks['tflops_burst'],

@@ -36,7 +36,8 @@ enum { /* img_dtype */
 enum { /* flags */
   DLV3P_MODEL_FLAG_KEEP_ALL = 1, /* every intermediate keeps its own tensor (block-level parity taps); default: the 16 middle-flow
                                     units ping-pong over four buffers and only the last unit's tap is meaningful */
-  DLV3P_MODEL_FLAG_NO_PDL = 2    /* measurement aid: launch the backbone kernels without programmatic dependent launch */
+  DLV3P_MODEL_FLAG_NO_PDL = 2,   /* measurement aid: launch the backbone kernels without programmatic dependent launch */
+  DLV3P_MODEL_FLAG_UNFUSED_ENTRY = 4 /* measurement aid: the entry flow's SepConv_BN layers as depthwise kernel + GEMM (like the rest of the backbone) */
 };
 
 typedef struct dlv3p_model_config {

@@ -111,8 +111,7 @@ struct BbDwCfg {
   static constexpr int IH = (TH - 1) * S + 2 * R + 1;
   static constexpr int IW = (TW - 1) * S + 2 * R + 1;
   static constexpr int kInBytes = IH * IW * 128;
-  static constexpr int kTapBytes = 10 * 64 * 4 + 16;           // 9 taps + shift of the tile's 64 channels + the decoded item (g, tx, ty, b)
-  static constexpr int kStageBytes = (kInBytes + kTapBytes + 127) / 128 * 128;
+  static constexpr int kStageBytes = kInBytes + 128;           // + the decoded item (tx, ty, b)
   static constexpr int kStages = 2;
   static constexpr int kBlocks = (TH / 4) * (TW / 4);          // 4 x 4 output blocks per tile
   static constexpr int kWarps = kBlocks < 8 ? kBlocks : 8;     // compute warps
@@ -120,10 +119,11 @@ struct BbDwCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 128 + 64;   // + alignment slack + the mbarriers
 };
 
-// Persistent CTAs over (image, TH x TW output tile, 64-channel group) work items, channel group fastest (concurrent CTAs read
-// neighbouring 128-byte segments of the same pixels).  A producer warp keeps a 2-stage ring full: per item ONE TMA box brings the
-// input window (halo included; out-of-bounds rows / columns / channels arrive as zeros = ZeroPadding2D / 'same') into shared
-// memory pixel-major [IH][IW][64 ch], and the group's taps + shift next to it.  Compute warp = a 4 x 4 block of output pixels,
+// Persistent CTAs over (image, TH x TW output tile, 64-channel group) work items.  The grid is a multiple of the number of
+// channel groups, so a CTA keeps ONE group for its whole life (taps + shift live in registers) and walks the spatial tiles;
+// concurrent CTAs read neighbouring 128-byte segments of the same pixels.  A producer warp keeps a 2-stage ring full: per item ONE
+// TMA box brings the input window (halo included; out-of-bounds rows / columns / channels arrive as zeros = ZeroPadding2D /
+// 'same') into shared memory pixel-major [IH][IW][64 ch].  Compute warp = a 4 x 4 block of output pixels,
 // lane = one channel pair: every shared-memory access of a warp is one conflict-free 128-byte pixel row, every global store one
 // full 128-byte line of a pixel.  Rolling window over the input rows of the block: each input value is loaded once per block
 // and feeds up to nine packed-fp32 FMAs.
@@ -135,7 +135,9 @@ __global__ void __launch_bounds__(BbDwCfg<S, R, TH, TW>::kThreads) bb_depthwise_
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);   // [kStages]
   uint64_t* empty_bar = full_bar + Cfg::kStages;                                              // [kStages]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_items = P.B * P.tiles_y * P.tiles_x * P.cgroups;
+  const int num_tiles = P.B * P.tiles_y * P.tiles_x;
+  const int g = static_cast<int>(blockIdx.x) % P.cgroups;                 // gridDim.x % cgroups == 0 (host)
+  const int t_first = static_cast<int>(blockIdx.x) / P.cgroups, t_step = static_cast<int>(gridDim.x) / P.cgroups;
   if (threadIdx.x == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) {
       mbar_init(&full_bar[i], 1);
@@ -148,52 +150,45 @@ __global__ void __launch_bounds__(BbDwCfg<S, R, TH, TW>::kThreads) bb_depthwise_
   if (warp == Cfg::kWarps) {
     // ------------------------------------------------------------------ producer warp
     pdl_wait();          // the input is the previous kernel's output; the compute warps are ordered behind this through full_bar
-    uint32_t stage = 0, phase = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      int t = item;
-      const int g = t % P.cgroups; t /= P.cgroups;
-      const int tx = t % P.tiles_x; t /= P.tiles_x;
-      const int ty = t % P.tiles_y;
-      const int b = t / P.tiles_y;
-      mbar_wait(&empty_bar[stage], phase ^ 1);
-      uint8_t* st = smem + stage * Cfg::kStageBytes;
-      float* taps = reinterpret_cast<float*>(st + Cfg::kInBytes);
-      // taps [9][64] + shift [64] of this group: 640 floats, 20 per lane
-      for (int i = lane; i < 640; i += 32) {
-        const int k = i >> 6, c = i & 63;
-        taps[i] = k < 9 ? __ldg(P.w + static_cast<size_t>(k) * P.Cpad + g * 64 + c) : __ldg(P.shift + g * 64 + c);
-      }
-      if (lane == 0) *reinterpret_cast<int4*>(taps + 640) = make_int4(g, tx, ty, b);   // decoded once: the consumers skip the divisions
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kInBytes);    // release semantics: the tap stores above are visible to the waiters
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = t_first; t < num_tiles; t += t_step) {
+        const int tx = t % P.tiles_x;
+        const int r = t / P.tiles_x;
+        const int ty = r % P.tiles_y;
+        const int b = r / P.tiles_y;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = smem + stage * Cfg::kStageBytes;
+        *reinterpret_cast<int4*>(st + Cfg::kInBytes) = make_int4(tx, ty, b, 0);   // decoded once: the consumers skip the divisions
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kInBytes);                  // release: the store above is visible to the waiters
         tma_load_4d(st, P.tmap_x, &full_bar[stage], g * 64, tx * TW * S - R, ty * TH * S - R, b, kEvictNormal);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
-      if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
     }
     return;
   }
   // -------------------------------------------------------------------- compute warps
   constexpr int WW = 3 * S + 2 * R + 1;      // input window of a 4 x 4 output block
+  // taps + shift of this lane's channel pair: the CTA's group never changes
+  unsigned long long wt[9], sh;
+  {
+    const float* wp = P.w + g * 64 + lane * 2;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const float2 w2 = __ldg(reinterpret_cast<const float2*>(wp + static_cast<size_t>(k) * P.Cpad));
+      wt[k] = pack_f32x2(w2.x, w2.y);
+    }
+    const float2 s2 = __ldg(reinterpret_cast<const float2*>(P.shift + g * 64 + lane * 2));
+    sh = pack_f32x2(s2.x, s2.y);
+  }
   uint32_t stage = 0, phase = 0;
   const uint32_t pstride = static_cast<uint32_t>(P.C) >> 1;            // one pixel / one output row in 32-bit words
   const uint32_t rstride = static_cast<uint32_t>(P.Wo) * pstride;
-  for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+  for (int t = t_first; t < num_tiles; t += t_step) {
     const uint8_t* st = smem + stage * Cfg::kStageBytes;
     mbar_wait(&full_bar[stage], phase);
-    const int4 it4 = *reinterpret_cast<const int4*>(st + Cfg::kInBytes + 2560);
-    const int g = it4.x, tx = it4.y, ty = it4.z, b = it4.w;
-    unsigned long long wt[9], sh;
-    {
-      const float* tp = reinterpret_cast<const float*>(st + Cfg::kInBytes) + lane * 2;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        const float2 w2 = *reinterpret_cast<const float2*>(tp + k * 64);
-        wt[k] = pack_f32x2(w2.x, w2.y);
-      }
-      const float2 s2 = *reinterpret_cast<const float2*>(tp + 9 * 64);
-      sh = pack_f32x2(s2.x, s2.y);
-    }
+    const int4 it4 = *reinterpret_cast<const int4*>(st + Cfg::kInBytes);
+    const int tx = it4.x, ty = it4.y, b = it4.z;
     const bool ch_ok = g * 64 + lane * 2 < P.C;
     for (int bi = warp; bi < Cfg::kBlocks; bi += Cfg::kWarps) {
       const int by = bi / (TW / 4), bx = bi % (TW / 4);

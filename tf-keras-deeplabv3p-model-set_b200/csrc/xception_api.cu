@@ -22,6 +22,7 @@
 #include "bb_conv3x3.cuh"
 #include "bb_gemm.cuh"
 #include "bb_kernels.cuh"
+#include "bb_sepconv.cuh"
 
 using namespace dlv3p;
 
@@ -141,7 +142,10 @@ cudaError_t launch_dw_t(const BbDwParams& P, cudaStream_t st) {
   const long long items = static_cast<long long>(P.B) * P.tiles_y * P.tiles_x * P.cgroups;
   const int per_sm = (227 * 1024) / (Cfg::kSmemBytes + 1024) > 0 ? (227 * 1024) / (Cfg::kSmemBytes + 1024) : 1;   // persistent: every CTA resident
   const long long cap = static_cast<long long>(sms[dev & 63]) * (per_sm < 4 ? per_sm : 4);
-  return launch_pdl(g_pdl, bb_depthwise_kernel<S, R, TH, TW>, dim3(static_cast<unsigned>(items < cap ? items : cap)), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, P);
+  // a multiple of the channel groups: every CTA keeps one group (its taps stay in registers) and strides over the spatial tiles
+  long long grid = items < cap ? items : cap / P.cgroups * P.cgroups;
+  if (grid < P.cgroups) grid = P.cgroups;
+  return launch_pdl(g_pdl, bb_depthwise_kernel<S, R, TH, TW>, dim3(static_cast<unsigned>(grid)), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, P);
 }
 cudaError_t launch_dw(const DwVariant& v, const BbDwParams& P, cudaStream_t st) {
   if (v.S == 1 && v.R == 1 && v.TH == 4) return launch_dw_t<1, 1, 4, 32>(P, st);
@@ -191,6 +195,40 @@ int pick_bb_bn(int M, int N, int num_sms) {
     if (best_cost < 0 || cost < best_cost) { best = bn; best_cost = cost; }
   }
   return best;
+}
+template <int KB, int NB>
+cudaError_t launch_sepconv_t(const BbSepParams& Q, int num_sms, cudaStream_t st) {
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(bb_sepconv_kernel<KB, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BbSepCfg<KB, NB>::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_done[dev & 63] = true;
+  }
+  const int items = (Q.base.num_tiles + 1) / 2;
+  const int grid = 2 * items < num_sms ? 2 * items : (num_sms & ~1);
+  return launch_pdl(g_pdl, bb_sepconv_kernel<KB, NB, false>, dim3(grid), dim3(kSepThreads), BbSepCfg<KB, NB>::kSmemBytes, st, Q);
+}
+// fused SepConv_BN of the entry flow: C in {64, 128, 192, 256}, N in {128, 256}
+bool sepconv_supported(int C, int N, int stride, int rate, bool act) { return !act && stride == 1 && rate == 1 && C % 64 == 0 && C >= 64 && C <= 256 && (N == 128 || N == 256); }
+cudaError_t launch_sepconv(int KB, int NB, const BbSepParams& Q, int num_sms, cudaStream_t st) {
+  if (NB == 128) {
+    switch (KB) {
+      case 1: return launch_sepconv_t<1, 128>(Q, num_sms, st);
+      case 2: return launch_sepconv_t<2, 128>(Q, num_sms, st);
+      case 3: return launch_sepconv_t<3, 128>(Q, num_sms, st);
+      case 4: return launch_sepconv_t<4, 128>(Q, num_sms, st);
+    }
+  } else if (NB == 256) {
+    switch (KB) {
+      case 1: return launch_sepconv_t<1, 256>(Q, num_sms, st);
+      case 2: return launch_sepconv_t<2, 256>(Q, num_sms, st);
+      case 3: return launch_sepconv_t<3, 256>(Q, num_sms, st);
+      case 4: return launch_sepconv_t<4, 256>(Q, num_sms, st);
+    }
+  }
+  return cudaErrorInvalidValue;
 }
 cudaError_t launch_conv3x3(const Conv3x3Params& P, int num_sms, cudaStream_t st) {
   static bool attr_done[64] = {};
@@ -258,11 +296,12 @@ struct Tensor {
   size_t elems() const { return static_cast<size_t>(B) * H * W * C; }
   int M() const { return B * H * W; }
 };
-enum OpKind { OP_STEM, OP_CONV3, OP_DW, OP_PW, OP_SUB };
+enum OpKind { OP_STEM, OP_CONV3, OP_DW, OP_PW, OP_SUB, OP_SEP };
 struct Op {
   OpKind kind;
   std::string name;      // Keras layer name of the convolution the kernel computes
   std::string bn;        // its BatchNormalization layer
+  std::string prefix;    // OP_SEP: the SepConv_BN prefix (<prefix>_depthwise / _depthwise_BN / _pointwise / _pointwise_BN)
   int in = -1, out = -1, res = -1;   // tensor indices
   int stride = 1, rate = 1, relu_in = 0, relu_out = 0;
   int K = 0, N = 0, Kpad = 0, Npad = 0, Cpad = 0, BN = 256;
@@ -440,6 +479,19 @@ int build_plan(dlv3p_model* m) {
       const int st = i == 2 ? b.stride : 1;
       const Tensor ti = m->tensors[cur];
       const int oh = cdiv(ti.H, st), ow = cdiv(ti.W, st);
+      if (!pooled && sepconv_supported(c, b.depth[i], st, b.rate, b.act) && !(i == 2 && res >= 0) && !(g.flags & DLV3P_MODEL_FLAG_UNFUSED_ENTRY)) {
+        // entry flow: depthwise -> BN -> pointwise -> BN in ONE kernel, the depthwise output never leaves the SM (bb_sepconv.cuh)
+        const int n = b.depth[i];
+        const int tp = new_tensor(m, B, oh, ow, n);
+        Op f; f.kind = OP_SEP; f.prefix = p; f.name = p + "_sepconv"; f.in = cur; f.out = tp; f.K = c; f.N = n; f.Cpad = c;
+        f.relu_in = b.act ? 0 : 1; f.relu_out = b.act ? 1 : 0;
+        f.flops = 2.0 * B * oh * ow * (9.0 * c + static_cast<double>(c) * n); f.bytes = 2.0 * B * oh * ow * (c + n);
+        seq.push_back(f);
+        if (i == 1 && b.ret_skip) { m->t_skip = tp; m->taps["skip"] = tp; }
+        cur = tp;
+        c = n;
+        continue;
+      }
       const int td = pooled ? pooled_tensor(&pool_d, oh, ow, c) : new_tensor(m, B, oh, ow, c);
       Op d; d.kind = OP_DW; d.name = p + "_depthwise"; d.bn = p + "_depthwise_BN"; d.in = cur; d.out = td; d.stride = st; d.rate = b.rate;
       d.relu_in = b.act ? 0 : 1; d.relu_out = b.act ? 1 : 0; d.K = c; d.Cpad = cdiv(c, 64) * 64;
@@ -492,7 +544,12 @@ void register_block_weights(dlv3p_model* m) {
     const std::string block = o.name.substr(0, o.name.find(is_shortcut ? "_shortcut" : "_separable_conv"));
     if (block != cur_block) { flush(); cur_block = block; }
     if (is_shortcut) { shortcut.push_back(&o); continue; }
-    if (o.kind == OP_DW) {
+    if (o.kind == OP_SEP) {
+      add_w(m, o.prefix + "_depthwise", "depthwise_kernel", {3, 3, o.K, 1});
+      add_bn(m, o.prefix + "_depthwise_BN", o.K);
+      add_w(m, o.prefix + "_pointwise", "kernel", {1, 1, o.K, o.N});
+      add_bn(m, o.prefix + "_pointwise_BN", o.N);
+    } else if (o.kind == OP_DW) {
       add_w(m, o.name, "depthwise_kernel", {3, 3, o.K, 1});
       add_bn(m, o.bn, o.K);
     } else {
@@ -656,6 +713,21 @@ int dlv3p_model_finalize_weights(dlv3p_model* m) {
       dw_box(o.dv, &bw, &bh);
       o.tm0 = slot();
       ok = ok && tm_nhwc(&m->h_tm[o.tm0], ti.p, ti.B, ti.H, ti.W, ti.C, 64, bw, bh, CU_TENSOR_MAP_SWIZZLE_NONE, &terr);
+    } else if (o.kind == OP_SEP) {
+      Fold fd = mfold(m, o.prefix + "_depthwise_BN", o.K);
+      if ((r = m_upload(m, &o.wf, pack_taps(MW(m, o.prefix + "_depthwise", "depthwise_kernel"), fd.scale.data(), o.K, o.K)))) return r;
+      if ((r = m_upload(m, &o.shift, fd.shift))) return r;
+      if ((r = m_upload(m, &o.w16, pack_kn(MW(m, o.prefix + "_pointwise", "kernel"), o.K, o.N, o.N, o.K)))) return r;
+      Fold fp = mfold(m, o.prefix + "_pointwise_BN", o.N);
+      o.h_scale.assign(256, 0.0f); o.h_shift.assign(256, 0.0f);
+      std::memcpy(o.h_scale.data(), fp.scale.data(), o.N * sizeof(float));
+      std::memcpy(o.h_shift.data(), fp.shift.data(), o.N * sizeof(float));
+      const Tensor& ti = m->tensors[o.in];
+      const Tensor& to = m->tensors[o.out];
+      o.tm0 = slot(); slot(); slot();
+      ok = ok && tm_nhwc(&m->h_tm[o.tm0], ti.p, ti.B, ti.H, ti.W, ti.C, 64, kDwHaloW, kDwHaloH, CU_TENSOR_MAP_SWIZZLE_NONE, &terr);
+      ok = ok && tm_2d(&m->h_tm[o.tm0 + 1], o.w16, o.N, o.K, o.K, 64, o.N / 2, CU_TENSOR_MAP_SWIZZLE_128B, &terr);
+      ok = ok && tm_nhwc(&m->h_tm[o.tm0 + 2], to.p, to.B, to.H, to.W, to.C, 32, 16, 2, CU_TENSOR_MAP_SWIZZLE_64B, &terr);
     } else if (o.kind == OP_PW) {
       o.Kpad = cdiv(o.K, 64) * 64;
       o.BN = pick_bb_bn(m->tensors[o.out].M(), o.N, m->num_sms);
@@ -743,6 +815,17 @@ static int run_backbone(dlv3p_model* m, const void* d_images, cudaStream_t st, i
       P.tmap_x = &m->d_tm[o.tm0]; P.w = o.wf; P.shift = o.shift; P.out = to.p; P.B = to.B; P.C = to.C; P.Cpad = o.Cpad; P.Ho = to.H; P.Wo = to.W;
       P.tiles_x = cdiv(to.W, o.dv.TW); P.tiles_y = cdiv(to.H, o.dv.TH); P.cgroups = o.Cpad / 64; P.relu_in = o.relu_in; P.relu_out = o.relu_out;
       e = launch_dw(o.dv, P, st);
+    } else if (o.kind == OP_SEP) {
+      const Tensor& to = m->tensors[o.out];
+      BbSepParams Q{};
+      DwPwParams& P = Q.base;
+      P.tmap_x = &m->d_tm[o.tm0]; P.tmap_x2 = nullptr; P.kb_split = 0; P.tmap_w = &m->d_tm[o.tm0 + 1]; P.dw_w = o.wf; P.dw_shift = o.shift;
+      P.scale = nullptr; P.shift = nullptr; P.out = to.p; P.tmap_out = nullptr; P.B = to.B; P.H = to.H; P.W = to.W;
+      P.tiles_x = cdiv(to.W, kDwTW); P.tiles_y = cdiv(to.H, kDwTH); P.num_tiles = to.B * P.tiles_x * P.tiles_y; P.debug = 0;
+      Q.tmap_out32 = &m->d_tm[o.tm0 + 2];
+      std::memcpy(Q.scale_c, o.h_scale.data(), sizeof(Q.scale_c));
+      std::memcpy(Q.shift_c, o.h_shift.data(), sizeof(Q.shift_c));
+      e = launch_sepconv(o.K / 64, o.N, Q, m->num_sms, st);
     } else if (o.kind == OP_PW) {
       const Tensor& to = m->tensors[o.out];
       BbGemmParams P{};
