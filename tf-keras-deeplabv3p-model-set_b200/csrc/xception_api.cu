@@ -474,6 +474,7 @@ int build_plan(dlv3p_model* m) {
     }
     // --- three SepConv_BN
     int cur = x, c = cin;
+    bool relu_prev = false;      // the producer of `cur` already applied this block's pre-depthwise ReLU
     for (int i = 0; i < 3; ++i) {
       const std::string p = mfmt("%s_separable_conv%d", b.prefix.c_str(), i + 1);
       const int st = i == 2 ? b.stride : 1;
@@ -490,11 +491,12 @@ int build_plan(dlv3p_model* m) {
         if (i == 1 && b.ret_skip) { m->t_skip = tp; m->taps["skip"] = tp; }
         cur = tp;
         c = n;
+        relu_prev = false;
         continue;
       }
       const int td = pooled ? pooled_tensor(&pool_d, oh, ow, c) : new_tensor(m, B, oh, ow, c);
       Op d; d.kind = OP_DW; d.name = p + "_depthwise"; d.bn = p + "_depthwise_BN"; d.in = cur; d.out = td; d.stride = st; d.rate = b.rate;
-      d.relu_in = b.act ? 0 : 1; d.relu_out = b.act ? 1 : 0; d.K = c; d.Cpad = cdiv(c, 64) * 64;
+      d.relu_in = (b.act || relu_prev) ? 0 : 1; d.relu_out = b.act ? 1 : 0; d.K = c; d.Cpad = cdiv(c, 64) * 64;
       if (!dw_variant(st, b.rate, &d.dv)) return mfail(m, DLV3P_ERR_UNSUPPORTED, mfmt("depthwise stride %d rate %d is not built", st, b.rate));
       d.flops = 2.0 * B * oh * ow * 9 * c; d.bytes = 2.0 * c * (static_cast<double>(ti.M()) + static_cast<double>(B) * oh * ow);
       seq.push_back(d);
@@ -505,6 +507,12 @@ int build_plan(dlv3p_model* m) {
       else tp = (x == pool_a) ? pooled_tensor(&pool_b, oh, ow, n) : pooled_tensor(&pool_a, oh, ow, n);
       Op q; q.kind = OP_PW; q.name = p + "_pointwise"; q.bn = p + "_pointwise_BN"; q.in = td; q.out = tp; q.K = c; q.N = n;
       q.relu_out = b.act ? 1 : 0;
+      // depth_activation False: the output of separable_conv1 / 2 is read only by the next depthwise conv, which starts with a ReLU
+      // (layers.py:98-99) -> applied here, in the GEMM epilogue (bit identical: rounding is monotonic), unless the tensor is also the
+      // decoder's skip feature, which the head takes signed
+      const bool relu_moved = !b.act && i < 2 && !(i == 1 && b.ret_skip);
+      if (relu_moved) q.relu_out = 1;
+      relu_prev = relu_moved;
       q.flops = 2.0 * B * oh * ow * static_cast<double>(c) * n; q.bytes = 2.0 * B * oh * ow * (c + n);
       if (i == 2 && res >= 0) { q.res = res; q.bytes += 2.0 * B * oh * ow * n; }
       seq.push_back(q);
