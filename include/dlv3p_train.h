@@ -108,6 +108,25 @@ int dlv3p_train_sgd(int device, float* w, const float* g, float* v, int64_t n, f
 /* fp32 -> bf16 copy of a weight tensor (any n). */
 int dlv3p_train_cast_bf16(int device, const float* in, void* out_bf16, int64_t n, void* cuda_stream);
 
+/* --- the step's exchanges over NVLink peer memory (train.py:143-158: MirroredStrategy's in-graph all-reduces) -------------------
+ * One exchange buffer per replica, mapped by its peers through CUDA IPC; a collective is ONE small kernel per replica: publish a
+ * flag in every peer's buffer, wait for the peers' flags, sum the W payloads in rank order with peer loads (bit-identical on every
+ * replica), write the total to a local buffer.  No NCCL call, no host synchronisation: the whole step stays one CUDA graph.
+ *   dlv3p_p2p_create    allocates [flags | payload_floats fp32] on `device`, returns the 64-byte cudaIpcMemHandle_t to hand to the peers
+ *                       (any host channel: torch.distributed, MPI, a file)
+ *   dlv3p_p2p_connect   handles = world x 64 bytes in rank order; maps the peers' buffers
+ *   dlv3p_p2p_payload   device pointer of float `off` of THIS replica's payload area: the producing kernels write their partials there
+ *   dlv3p_p2p_allreduce collective number `slot` (< 64, distinct per collective of a step): d_out[0..n) = sum over replicas of
+ *                       payload[off .. off+n); off, n multiples of 4; asynchronous on the stream
+ *   dlv3p_p2p_advance   once per step after its last collective (advances the device-side epoch the flags carry) */
+typedef struct dlv3p_p2p dlv3p_p2p;
+int dlv3p_p2p_create(int device, int world, int rank, size_t payload_floats, dlv3p_p2p** out, uint8_t handle_out[64]);
+int dlv3p_p2p_connect(dlv3p_p2p* comm, const uint8_t* handles);
+void dlv3p_p2p_destroy(dlv3p_p2p* comm);
+void* dlv3p_p2p_payload(dlv3p_p2p* comm, size_t off);
+int dlv3p_p2p_allreduce(dlv3p_p2p* comm, int slot, size_t off, int n, float* d_out, void* cuda_stream);
+int dlv3p_p2p_advance(dlv3p_p2p* comm, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -148,7 +148,7 @@ def test_cuda_graph_replay_equals_the_eager_step(gpu):
 
 
 # ---------------------------------------------------------------------------------------------------- world size 2 on ONE GPU
-def _one_gpu_worker(rank, world, port, q):
+def _one_gpu_worker(rank, world, port, q, exchange):
     try:
         import torch
         import torch.distributed as dist
@@ -160,7 +160,7 @@ def _one_gpu_worker(rank, world, port, q):
         Bl = cfg.B // world
         sl = slice(rank * Bl, (rank + 1) * Bl)
         # exactly _ddp_worker_body of test_gpu_3_train.py, with both replicas on cuda:0 and gloo carrying the CUDA tensors
-        tr = train.HeadTrainer(Bl, cfg.H, cfg.W, cfg.OS, cfg.Cin, cfg.Cskip, cfg.NC, W, device=0, seed=9, graph=False)
+        tr = train.HeadTrainer(Bl, cfg.H, cfg.W, cfg.OS, cfg.Cin, cfg.Cskip, cfg.NC, W, device=0, seed=9, graph=False, exchange=exchange)
         f = torch.from_numpy(feat[sl]).cuda().to(torch.bfloat16).contiguous()
         s = torch.from_numpy(skip[sl]).cuda().to(torch.bfloat16).contiguous()
         l = torch.from_numpy(labels[sl]).cuda().contiguous()
@@ -171,22 +171,27 @@ def _one_gpu_worker(rank, world, port, q):
         tr.apply_gradients()
         torch.cuda.synchronize()
         q.put((rank, grads, tr.T['dfeat'].float().cpu().numpy(), tr.T['dskip'].float().cpu().numpy(), loss, tr.get_weights()))
+        dist.barrier()
+        tr.close()
         dist.destroy_process_group()
     except Exception as e:
         import traceback
         q.put((rank, 'ERROR', traceback.format_exc(), str(e), None, None))
 
 
-def test_data_parallel_step_two_processes_one_gpu(gpu):
+@pytest.mark.parametrize('exchange', ['p2p', 'nccl'])
+def test_data_parallel_step_two_processes_one_gpu(gpu, exchange):
     """The data-parallel training step (SyncBN statistic exchanges + the gradient all-reduce) with world size 2 on a SINGLE GPU:
-    two processes share cuda:0, gloo carries the same spans NCCL would.  Result == the oracle on the global batch, replicas
-    bit-identical after the exchange (gradients and updated weights)."""
+    two processes share cuda:0.  exchange 'p2p': the SyncBN vectors travel through the peer-memory one-shot all-reduce (CUDA IPC
+    mapping of the other process's buffer, flags, rank-ordered sums — the kernels the multi-GPU step runs over NVLink); 'nccl':
+    torch.distributed carries the same spans (gloo here).  Result == the oracle on the global batch, replicas bit-identical after
+    the exchange (gradients and updated weights)."""
     import torch.multiprocessing as mp
     from dlv3p_b200 import train, train_ffi
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    ps = [ctx.Process(target=_one_gpu_worker, args=(r, 2, port, q)) for r in range(2)]
+    ps = [ctx.Process(target=_one_gpu_worker, args=(r, 2, port, q, exchange)) for r in range(2)]
     for p in ps:
         p.start()
     got = sorted([q.get(timeout=300) for _ in ps], key=lambda t: t[0])

@@ -6,6 +6,7 @@
 #include "../../include/dlv3p_train.h"
 #include "tgemm.cuh"
 #include "train_kernels.cuh"
+#include "p2p_exchange.cuh"
 
 namespace {
 
@@ -415,6 +416,97 @@ int dlv3p_train_cast_bf16(int device, const float* in, void* out, int64_t n, voi
   if (!in || !out || n < 1) return fail(nullptr, DLV3P_ERR_INVALID, "train_cast_bf16: bad arguments");
   cast_f32_bf16_any_kernel<<<grid_for(static_cast<size_t>(n), sms), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(in, static_cast<__nv_bfloat16*>(out),
                                                                                                                       static_cast<size_t>(n));
+  CU_TRY(nullptr, cudaGetLastError());
+  return DLV3P_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------- peer-memory exchange
+struct dlv3p_p2p {
+  int device = 0, world = 1, rank = 0;
+  size_t payload_floats = 0;
+  uint8_t* local = nullptr;            // [flags | payload]
+  uint32_t* epoch = nullptr;           // device counter, starts at 1
+  P2pPeers peers{};
+  bool opened[kP2pMaxWorld] = {};
+};
+
+int dlv3p_p2p_create(int device, int world, int rank, size_t payload_floats, dlv3p_p2p** out, uint8_t handle_out[64]) {
+  int sms = 0, r = op_prolog(device, &sms);
+  if (r) return r;
+  if (!out || !handle_out || world < 1 || world > kP2pMaxWorld || rank < 0 || rank >= world) return fail(nullptr, DLV3P_ERR_INVALID, "p2p_create: bad arguments (world <= 16)");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  dlv3p_p2p* c = new dlv3p_p2p();
+  c->device = device; c->world = world; c->rank = rank; c->payload_floats = (payload_floats + 3) / 4 * 4;
+  const size_t bytes = kP2pFlagBytes + c->payload_floats * sizeof(float);
+  if (cudaMalloc(&c->local, bytes) != cudaSuccess || cudaMalloc(&c->epoch, sizeof(uint32_t)) != cudaSuccess) {
+    delete c;
+    return fail(nullptr, DLV3P_ERR_NOMEM, "p2p_create: cudaMalloc failed");
+  }
+  cudaMemset(c->local, 0, bytes);
+  const uint32_t one = 1;
+  cudaMemcpy(c->epoch, &one, sizeof(one), cudaMemcpyHostToDevice);
+  cudaIpcMemHandle_t h;
+  if (world > 1) {
+    cudaError_t e = cudaIpcGetMemHandle(&h, c->local);
+    if (e != cudaSuccess) {
+      cudaFree(c->local); cudaFree(c->epoch); delete c;
+      return fail(nullptr, DLV3P_ERR_CUDA, fmt("cudaIpcGetMemHandle: %s", cudaGetErrorString(e)));
+    }
+    std::memcpy(handle_out, &h, 64);
+  } else {
+    std::memset(handle_out, 0, 64);
+  }
+  c->peers.world = world; c->peers.rank = rank;
+  c->peers.base[rank] = c->local;
+  *out = c;
+  return DLV3P_OK;
+}
+
+// handles: world x 64 bytes in rank order (the entry of this rank is ignored)
+int dlv3p_p2p_connect(dlv3p_p2p* c, const uint8_t* handles) {
+  if (!c || (!handles && c->world > 1)) return fail(nullptr, DLV3P_ERR_INVALID, "p2p_connect: null argument");
+  CU_TRY(nullptr, cudaSetDevice(c->device));
+  for (int r = 0; r < c->world; ++r) {
+    if (r == c->rank || c->opened[r]) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handles + static_cast<size_t>(r) * 64, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(nullptr, DLV3P_ERR_CUDA, fmt("cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e)));
+    c->peers.base[r] = static_cast<uint8_t*>(p);
+    c->opened[r] = true;
+  }
+  return DLV3P_OK;
+}
+
+void dlv3p_p2p_destroy(dlv3p_p2p* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < c->world; ++r)
+    if (c->opened[r]) cudaIpcCloseMemHandle(c->peers.base[r]);
+  cudaFree(c->local);
+  cudaFree(c->epoch);
+  delete c;
+}
+
+// device pointer of float `off` of this replica's payload area (the producing kernels write their partial sums there)
+void* dlv3p_p2p_payload(dlv3p_p2p* c, size_t off) { return c ? c->local + kP2pFlagBytes + off * sizeof(float) : nullptr; }
+
+int dlv3p_p2p_allreduce(dlv3p_p2p* c, int slot, size_t off, int n, float* d_out, void* cuda_stream) {
+  if (!c || !d_out || slot < 0 || slot >= kP2pSlots || n < 1 || (n & 3) || (off & 3) || off + n > c->payload_floats)
+    return fail(nullptr, DLV3P_ERR_INVALID, "p2p_allreduce: bad arguments (slot < 64, off and n multiples of 4, inside the payload area)");
+  const int blocks = n >= 8192 ? 4 : 1;
+  p2p_allreduce_kernel<<<blocks, 512, 0, static_cast<cudaStream_t>(cuda_stream)>>>(c->peers, slot, c->epoch, off, n, d_out);
+  CU_TRY(nullptr, cudaGetLastError());
+  return DLV3P_OK;
+}
+
+// once per step, after the step's last collective: the next step's flags compare against epoch + 1
+int dlv3p_p2p_advance(dlv3p_p2p* c, void* cuda_stream) {
+  if (!c) return fail(nullptr, DLV3P_ERR_INVALID, "p2p_advance: null argument");
+  p2p_advance_epoch_kernel<<<1, 1, 0, static_cast<cudaStream_t>(cuda_stream)>>>(c->epoch);
   CU_TRY(nullptr, cudaGetLastError());
   return DLV3P_OK;
 }

@@ -35,6 +35,12 @@ SYMBOLS = [
     ('dlv3p_train_dropout', _i, [_i, _vp, _vp, _i64, _u32, _vp, _f, _vp]),
     ('dlv3p_train_sgd', _i, [_i, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _vp]),
     ('dlv3p_train_cast_bf16', _i, [_i, _vp, _vp, _i64, _vp]),
+    ('dlv3p_p2p_create', _i, [_i, _i, _i, _sz, C.POINTER(_vp), C.c_char_p]),
+    ('dlv3p_p2p_connect', _i, [_vp, C.c_char_p]),
+    ('dlv3p_p2p_destroy', None, [_vp]),
+    ('dlv3p_p2p_payload', _vp, [_vp, _sz]),
+    ('dlv3p_p2p_allreduce', _i, [_vp, _i, _sz, _i, _vp, _vp]),
+    ('dlv3p_p2p_advance', _i, [_vp, _vp]),
 ]
 
 _typed = False
@@ -81,3 +87,34 @@ def dropout_keep_mask(n: int, seed: int, rate: float):
     h = (h * 0xC2B2AE35) & 0xFFFFFFFF
     h ^= h >> 16
     return h >= int(float(rate) * 4294967296.0)
+
+
+class P2pExchange:
+    """One replica's end of the peer-memory exchange (dlv3p_p2p_*): create -> hand `handle` (64 bytes) to every peer ->
+    connect(all handles in rank order) -> allreduce(slot, off, n, out_ptr, stream) ... advance(stream) once per step."""
+
+    def __init__(self, device: int, world: int, rank: int, payload_floats: int):
+        self.world, self.rank = world, rank
+        h = C.c_void_p()
+        buf = C.create_string_buffer(64)
+        ffi._check(lib().dlv3p_p2p_create(device, world, rank, payload_floats, C.byref(h), buf))
+        self.handle_ptr, self.handle = h, buf.raw
+
+    def connect(self, handles) -> None:
+        blob = b''.join(bytes(x) for x in handles)
+        assert len(blob) == 64 * self.world
+        ffi._check(lib().dlv3p_p2p_connect(self.handle_ptr, blob))
+
+    def payload(self, off: int = 0) -> int:
+        return int(lib().dlv3p_p2p_payload(self.handle_ptr, off))
+
+    def allreduce(self, slot: int, off: int, n: int, out_ptr: int, stream) -> None:
+        ffi._check(lib().dlv3p_p2p_allreduce(self.handle_ptr, slot, off, n, out_ptr, stream))
+
+    def advance(self, stream) -> None:
+        ffi._check(lib().dlv3p_p2p_advance(self.handle_ptr, stream))
+
+    def close(self) -> None:
+        if getattr(self, 'handle_ptr', None):
+            lib().dlv3p_p2p_destroy(self.handle_ptr)
+            self.handle_ptr = None
