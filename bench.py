@@ -227,7 +227,6 @@ def time_other_configs(local_rank, steps=10):
 def time_train_step(rank, world, local_rank, steps=10, warmup=3, batch=8):
     """BASELINE configs[4]: the head's training step (forward in training mode, loss, backward, SyncBN exchanges, gradient
     all-reduce, SGD) at 8 images per GPU, replayed as one CUDA graph; max-over-ranks device time; replicas-identical check."""
-    import hashlib
     import torch
     import torch.distributed as dist
     from dlv3p_b200 import train
@@ -257,7 +256,7 @@ def time_train_step(rank, world, local_rank, steps=10, warmup=3, batch=8):
         ms = float(t.item())
     loss = tr.loss()
     # replicas hold identical weights after every step: compare a digest of the fp32 master weights over the ranks
-    digest = int.from_bytes(hashlib.sha256(tr.params.cpu().numpy().tobytes()).digest()[:7], 'little')
+    digest = tr.weights_digest() >> 2
     same = True
     if world > 1:
         d = torch.tensor([digest], device='cuda', dtype=torch.int64)
@@ -269,11 +268,14 @@ def time_train_step(rank, world, local_rank, steps=10, warmup=3, batch=8):
     rec = {'workload': 'cfg5: Xception OS16 512x512 head training step, SyncBN + Dropout + sparse CE + SGD, %d img/GPU, global batch %d, bf16' % (batch, batch * world),
            'ms_per_step': ms / steps, 'images_per_s': batch * world * steps / (ms / 1000.0), 'steps': steps, 'n_gpus': world,
            'gpu_launches_per_step': (tr.launches - l0) // steps, 'cuda_graph': True, 'loss': loss,
-           'collectives_per_step': {'syncbn_allreduce': len(spans), 'grad_allreduce': 1, 'backend': tr.comm_backend() if hasattr(tr, 'comm_backend') else ('nccl' if world > 1 else 'none')},
+           'collectives_per_step': {'syncbn_allreduce': len(spans), 'grad_allreduce': 1, 'backend': tr.comm_backend()},
            'bytes_per_collective': {'syncbn': [4 * (e - b) for b, e in spans], 'grad_bucket': 4 * (tr.bucket_span()[1] - tr.bucket_span()[0])},
-           'replicas_identical': same, 'scope': 'head only (backbone frozen / outside, train.py stage 1)'}
-    tr._graph = None
+           'replicas_identical': same, 'scope': 'head only (backbone frozen / outside, train.py stage 1)',
+           'host': 'dlv3p_trainer_step (C ABI): one CUDA graph per step, no torch / NCCL call inside the step'}
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    tr.close()
     return rec
 
 
@@ -315,6 +317,7 @@ def run_whole_model(args, rank, world, local_rank):
     import torch
     import dlv3p_b200
     from dlv3p_b200 import ffi
+    from tools import torch_plumbing
     B = args.batch
     if args.strong:
         B = max(1, dlv3p_b200.sharding.shard_batch(args.batch, world, rank)[1])
@@ -366,7 +369,7 @@ def run_whole_model(args, rank, world, local_rank):
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1000.0
     labels_ok = bool(np.array_equal(ho, out.cpu().numpy()))
-    ms, e2e_ms = dlv3p_b200.sharding.max_over_ranks([ms, e2e_ms], device='cuda')
+    ms, e2e_ms = torch_plumbing.max_over_ranks([ms, e2e_ms], device='cuda')
     ws = mdl.workspace_bytes()
     net.close()
     del images, out
@@ -558,12 +561,9 @@ def main():
         print(json.dumps(line))
         sys.stdout.flush()
     if world > 1:
-        # a CUDA graph with NCCL kernels inside was captured by the training sub-record: destroy_process_group() after that has
-        # been seen to hang at exit (tools/trainbench.py) -> barrier, flush, leave without the collective destructor
         dist.barrier()
         torch.cuda.synchronize()
-        sys.stdout.flush()
-        os._exit(0)
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':

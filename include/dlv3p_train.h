@@ -127,6 +127,56 @@ void* dlv3p_p2p_payload(dlv3p_p2p* comm, size_t off);
 int dlv3p_p2p_allreduce(dlv3p_p2p* comm, int slot, size_t off, int n, float* d_out, void* cuda_stream);
 int dlv3p_p2p_advance(dlv3p_p2p* comm, void* cuda_stream);
 
+/* --- the whole training step behind one handle (train.py:143-169: model.compile + fit under MirroredStrategy) --------------------
+ * dlv3p_trainer owns every device buffer of one replica (fp32 master weights, velocity, activations, gradients, SyncBN statistics,
+ * the peer-visible exchange buffer), strings the operators above into forward (training mode) -> loss -> backward -> exchanges ->
+ * SGD(momentum) + l2 -> Keras moving statistics, and replays the step as ONE CUDA graph.  No PyTorch, no NCCL: replicas exchange
+ * through peer memory (dlv3p_p2p_*); the host only hands the 64-byte IPC handles around once.
+ * Scope: the full head (ASPP_block + Decoder_block + tail), backbone frozen / outside (the reference's stage 1, train.py:177-187). */
+typedef struct dlv3p_trainer_config {
+  int32_t B, H, W, OS;        /* per-replica batch, model input size, output stride */
+  int32_t Cin, Cskip, NC;
+  int32_t world, rank;        /* data-parallel replicas (one process per GPU) */
+  int32_t global_batch;       /* loss normalisation 1 / (global_batch * H * W); 0 -> B * world */
+  int32_t ignore_index;       /* 255 in the reference (loss.py:121-156) */
+  int32_t loss_kind;          /* 0 sparse CE, 1 class-weighted CE (dlv3p_trainer_set_class_weights), 2 focal (train.py:114-138) */
+  uint32_t seed;              /* Dropout mask seed (counter based: seed, step, rank, element) */
+  float lr, momentum, l2;     /* SGD(momentum 0.9), lr 1e-2, l2(2e-5) defaults of the reference */
+  float bn_momentum, eps;     /* 0.99, 1e-5 */
+  float dropout;              /* 0.5 (layers.py:161) */
+  float focal_gamma, focal_alpha;
+} dlv3p_trainer_config;
+typedef struct dlv3p_trainer dlv3p_trainer;
+
+/* ipc_handle_out: this replica's exchange buffer (cudaIpcMemHandle_t); hand it to every peer, then dlv3p_trainer_connect with all
+ * handles in rank order (world == 1: nothing to connect). */
+int dlv3p_trainer_create(const dlv3p_trainer_config* cfg, int device, dlv3p_trainer** out, uint8_t ipc_handle_out[64]);
+int dlv3p_trainer_connect(dlv3p_trainer* t, const uint8_t* handles);
+void dlv3p_trainer_destroy(dlv3p_trainer* t);
+const char* dlv3p_trainer_last_error(const dlv3p_trainer* t);
+/* Weights by Keras layer / variable name (dlv3p_weight_info); arrays in the trainer's layouts: kernel [K, N], bias [NC],
+ * depthwise_kernel [9, C], BN vectors [C].  commit after the last set (velocity <- 0, bf16 operand copies). */
+int dlv3p_trainer_set_weight(dlv3p_trainer* t, const char* layer, const char* var, const float* host_fp32, int64_t n);
+int dlv3p_trainer_commit_weights(dlv3p_trainer* t);
+/* which: 0 master weight (or moving statistic), 1 gradient of the last step, 2 velocity */
+int dlv3p_trainer_get(dlv3p_trainer* t, int which, const char* layer, const char* var, float* host_fp32, int64_t n);
+int dlv3p_trainer_set_class_weights(dlv3p_trainer* t, const float* host_fp32, int n);
+int dlv3p_trainer_set_hyper(dlv3p_trainer* t, float lr, float momentum, float l2);   /* LR schedules: the captured graph is rebuilt */
+/* d_feat bf16 [B,h,w,Cin], d_skip bf16 [B,H/4,W/4,Cskip], d_labels uint8 [B,H,W]: device pointers, copied into the trainer's static
+ * buffers on its own stream (ordered behind `cuda_stream`); asynchronous.  use_graph: replay the captured step from the 2nd call on. */
+int dlv3p_trainer_step(dlv3p_trainer* t, const void* d_feat, const void* d_skip, const void* d_labels, int use_graph, void* cuda_stream);
+/* the step in three pieces (parity tests): forward + loss + backward | gradient exchange | update */
+int dlv3p_trainer_forward_backward(dlv3p_trainer* t, const void* d_feat, const void* d_skip, const void* d_labels, void* cuda_stream);
+int dlv3p_trainer_all_reduce_gradients(dlv3p_trainer* t, void* cuda_stream);
+int dlv3p_trainer_apply_gradients(dlv3p_trainer* t, void* cuda_stream);
+/* global mean loss of the last step and the valid pixels over all replicas (synchronises) */
+int dlv3p_trainer_loss(dlv3p_trainer* t, float* loss_out, float* valid_pixels_out);
+/* a named activation / gradient buffer as fp32: "dfeat" [B*h*w, Cin], "dskip" [B*hs*ws, Cskip], ... (parity tests, diagnostics) */
+int dlv3p_trainer_read(dlv3p_trainer* t, const char* name, float* host_fp32, int64_t n);
+int dlv3p_trainer_num_params(const dlv3p_trainer* t, int64_t* nparams, int64_t* nbn);
+int dlv3p_trainer_counters(const dlv3p_trainer* t, int64_t* launches, int64_t* steps, int* graph_captured);
+int dlv3p_trainer_weights_digest(dlv3p_trainer* t, uint64_t* digest);   /* FNV-1a of the fp32 master weights: replicas-identical check */
+
 #ifdef __cplusplus
 }
 #endif

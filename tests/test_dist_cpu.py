@@ -9,6 +9,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from dlv3p_b200 import sharding
+from tools import torch_plumbing
 
 
 def _free_port():
@@ -26,7 +27,7 @@ def _worker(rank, world, port, global_batch, q):
     owned = torch.zeros(global_batch, dtype=torch.int32)
     owned[start:start + count] = 1
     dist.all_reduce(owned)
-    ms = sharding.max_over_ranks([10.0 + rank, 5.0 - rank])
+    ms = torch_plumbing.max_over_ranks([10.0 + rank, 5.0 - rank])
     q.put((rank, start, count, owned.tolist(), ms))
     dist.destroy_process_group()
 
@@ -58,7 +59,7 @@ def test_shard_arithmetic_and_throughput():
         sharding.shard_batch(8, 2, 2)
     # weak scaling: 32 images per rank per step, 20 steps, 8 ranks, slowest rank 25 ms -> 204800 img/s
     assert sharding.aggregate_throughput(32, 20, 8, 25.0) == pytest.approx(204800.0)
-    assert sharding.max_over_ranks([1.5, 2.5]) == [1.5, 2.5]   # no process group: identity
+    assert torch_plumbing.max_over_ranks([1.5, 2.5]) == [1.5, 2.5]   # no process group: identity
 
 
 # ---------------------------------------------------------------------------------------------------- training step, N > 1 host logic

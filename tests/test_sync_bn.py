@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import head_ref as R
+from tools import torch_plumbing
 
 
 def _free_port():
@@ -28,7 +29,7 @@ def _gloo_worker(rank, world, port, q):
     C = 48
     shards = [rng.standard_normal((3 + r, 4, 5, C)).astype(np.float32) for r in range(world)]   # ragged replicas
     st = torch.from_numpy(R.bn_train_stats(shards[rank]))
-    sharding.allreduce_stats(st)
+    torch_plumbing.allreduce_stats(st)
     mean, var = sharding.moments_from_stats(st.numpy(), C)
     q.put((rank, mean, var))
     dist.destroy_process_group()
@@ -102,7 +103,7 @@ def _nccl_worker(rank, world, port, q, one_gpu=False):
     shards = [R.bf16_round(rng.standard_normal((2 + r, 16, 16, C)).astype(np.float32)) for r in range(world)]
     g, b = rng.uniform(0.5, 1.5, C).astype(np.float32), rng.normal(0, 0.1, C).astype(np.float32)
     x = torch.from_numpy(shards[rank]).cuda().to(torch.bfloat16)
-    y, stats = sharding.sync_batch_norm_forward(x, torch.from_numpy(g), torch.from_numpy(b))
+    y, stats = torch_plumbing.sync_batch_norm_forward(x, torch.from_numpy(g), torch.from_numpy(b))
     torch.cuda.synchronize()
     q.put((rank, y.float().cpu().numpy(), stats.cpu().numpy()))
     dist.destroy_process_group()

@@ -24,7 +24,7 @@ def test_train_header_symbols_are_exported_and_bound():
     from dlv3p_b200 import ffi, train_ffi
     text = open(os.path.join(ROOT, 'include', 'dlv3p_train.h')).read()
     text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
-    declared = sorted(set(re.findall(r'\b(dlv3p_(?:train|p2p)_[a-z0-9_]+)\s*\(', text)))
+    declared = sorted(set(re.findall(r'\b(dlv3p_(?:train|p2p|trainer)_[a-z0-9_]+)\s*\(', text)))
     assert len(declared) >= 20
     lib = ffi.load_library()
     for name in declared:

@@ -1943,3 +1943,4 @@ int dlv3p_op_time(int device, int op, const int64_t* d, int ndims, int iters, in
 
 // training-step operators (include/dlv3p_train.h)
 #include "train_api.cuh"
+#include "trainer_api.cuh"

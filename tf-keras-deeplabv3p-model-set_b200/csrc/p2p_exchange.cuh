@@ -83,4 +83,85 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2pPeers P, in
 
 __global__ void p2p_advance_epoch_kernel(uint32_t* epoch) { *epoch += 1u; }
 
+// ---- the gradient bucket (12.7 MB at cfg 5): two-shot all-reduce over the same buffers -------------------------------------------------
+// publish + wait of collective `slot`; every block waits itself, block 0 publishes: "every earlier kernel of my stream is complete"
+__device__ __forceinline__ void p2p_barrier(const P2pPeers& P, int slot, uint32_t epoch) {
+  if (threadIdx.x < P.world) {
+    uint32_t* mine = reinterpret_cast<uint32_t*>(P.base[P.rank]) + slot * kP2pMaxWorld;
+    if (blockIdx.x == 0) {
+      __threadfence_system();
+      st_release_sys(reinterpret_cast<uint32_t*>(P.base[threadIdx.x]) + slot * kP2pMaxWorld + P.rank, epoch);
+    }
+    const long long t0 = clock64();
+    while (static_cast<int32_t>(ld_acquire_sys(mine + threadIdx.x) - epoch) < 0) {
+      if (clock64() - t0 > DLV3P_P2P_TIMEOUT_CYCLES) {
+        printf("dlv3p: p2p barrier timeout rank %d waiting for rank %d slot %d epoch %u\n", P.rank, static_cast<int>(threadIdx.x), slot, epoch);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+}
+// shot 1 (reduce-scatter): replica r sums chunk r of every replica's [src_off, src_off + n) in rank order into its own [red_off + chunk r)
+__global__ void __launch_bounds__(512) p2p_reduce_scatter_kernel(const P2pPeers P, int slot, const uint32_t* __restrict__ epoch_ptr, size_t src_off,
+                                                                 size_t red_off, size_t n) {
+  p2p_barrier(P, slot, *epoch_ptr);
+  const size_t n4 = n >> 2, chunk4 = (n4 + P.world - 1) / P.world;
+  const size_t lo = chunk4 * P.rank, hi = lo + chunk4 < n4 ? lo + chunk4 : n4;
+  float* red = reinterpret_cast<float*>(P.base[P.rank] + kP2pFlagBytes) + red_off;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i0 = lo + blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i0 < hi; i0 += 2 * stride) {   // 2 x W peer loads in flight per thread
+    float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+    for (int r = 0; r < P.world; ++r) {       // rank order: every replica reduces its chunk, so the order only has to be FIXED
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const size_t i = i0 + u * stride;
+        if (i < hi) {
+          const float4 v = ld_peer_v4(reinterpret_cast<const float*>(P.base[r] + kP2pFlagBytes) + src_off + 4 * i);
+          acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const size_t i = i0 + u * stride;
+      if (i < hi) reinterpret_cast<float4*>(red)[i] = acc[u];
+    }
+  }
+}
+// shot 2 (all-gather): every replica copies chunk p of replica p's reduced area into dst (all replicas end with identical bits)
+__global__ void __launch_bounds__(512) p2p_all_gather_kernel(const P2pPeers P, int slot, const uint32_t* __restrict__ epoch_ptr, size_t red_off, size_t n,
+                                                             float* __restrict__ dst) {
+  p2p_barrier(P, slot, *epoch_ptr);
+  const size_t n4 = n >> 2, chunk4 = (n4 + P.world - 1) / P.world;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i0 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i0 < n4; i0 += 4 * stride) {   // four peer loads in flight per thread
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const size_t i = i0 + u * stride;
+      if (i < n4) v[u] = ld_peer_v4(reinterpret_cast<const float*>(P.base[static_cast<int>(i / chunk4)] + kP2pFlagBytes) + red_off + 4 * i);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const size_t i = i0 + u * stride;
+      if (i < n4) reinterpret_cast<float4*>(dst)[i] = v[u];
+    }
+  }
+}
+
+__global__ void add_u32_kernel(uint32_t* p, uint32_t inc) { *p += inc; }
+
+// Keras moving statistics from the (global) SyncBN sums: moving <- moving * m + batch * (1 - m), biased variance (layers.py:63-70)
+__global__ void moving_stats_kernel(const float* __restrict__ stats, const int* __restrict__ ix, int nbn, float momentum, float* __restrict__ mm,
+                                    float* __restrict__ mv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nbn) return;
+  const float n = stats[ix[2 * nbn + i]];
+  const float mean = stats[ix[i]] / n;
+  const float var = fmaxf(stats[ix[nbn + i]] / n - mean * mean, 0.0f);
+  mm[i] = mm[i] * momentum + mean * (1.0f - momentum);
+  mv[i] = mv[i] * momentum + var * (1.0f - momentum);
+}
+
 }  // namespace dlv3p

@@ -41,7 +41,31 @@ SYMBOLS = [
     ('dlv3p_p2p_payload', _vp, [_vp, _sz]),
     ('dlv3p_p2p_allreduce', _i, [_vp, _i, _sz, _i, _vp, _vp]),
     ('dlv3p_p2p_advance', _i, [_vp, _vp]),
+    ('dlv3p_trainer_create', _i, [_vp, _i, C.POINTER(_vp), C.c_char_p]),
+    ('dlv3p_trainer_connect', _i, [_vp, C.c_char_p]),
+    ('dlv3p_trainer_destroy', None, [_vp]),
+    ('dlv3p_trainer_last_error', C.c_char_p, [_vp]),
+    ('dlv3p_trainer_set_weight', _i, [_vp, C.c_char_p, C.c_char_p, C.POINTER(C.c_float), _i64]),
+    ('dlv3p_trainer_commit_weights', _i, [_vp]),
+    ('dlv3p_trainer_get', _i, [_vp, _i, C.c_char_p, C.c_char_p, C.POINTER(C.c_float), _i64]),
+    ('dlv3p_trainer_set_class_weights', _i, [_vp, C.POINTER(C.c_float), _i]),
+    ('dlv3p_trainer_set_hyper', _i, [_vp, _f, _f, _f]),
+    ('dlv3p_trainer_step', _i, [_vp, _vp, _vp, _vp, _i, _vp]),
+    ('dlv3p_trainer_forward_backward', _i, [_vp, _vp, _vp, _vp, _vp]),
+    ('dlv3p_trainer_all_reduce_gradients', _i, [_vp, _vp]),
+    ('dlv3p_trainer_apply_gradients', _i, [_vp, _vp]),
+    ('dlv3p_trainer_loss', _i, [_vp, C.POINTER(_f), C.POINTER(_f)]),
+    ('dlv3p_trainer_read', _i, [_vp, C.c_char_p, C.POINTER(C.c_float), _i64]),
+    ('dlv3p_trainer_num_params', _i, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
+    ('dlv3p_trainer_counters', _i, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i)]),
+    ('dlv3p_trainer_weights_digest', _i, [_vp, C.POINTER(C.c_uint64)]),
 ]
+
+
+class TrainerConfig(C.Structure):
+    """dlv3p_trainer_config (include/dlv3p_train.h)."""
+    _fields_ = [(n, C.c_int32) for n in ('B', 'H', 'W', 'OS', 'Cin', 'Cskip', 'NC', 'world', 'rank', 'global_batch', 'ignore_index', 'loss_kind')] + \
+               [('seed', C.c_uint32)] + [(n, C.c_float) for n in ('lr', 'momentum', 'l2', 'bn_momentum', 'eps', 'dropout', 'focal_gamma', 'focal_alpha')]
 
 _typed = False
 

@@ -23,16 +23,12 @@ def run(mode, drop):
         yy, xx = np.mgrid[0:cfg.H, 0:cfg.W]
         labels = np.stack([((yy // 32 + xx // 32 + b) % cfg.NC).astype(np.uint8) for b in range(cfg.B)])
     tr = train.HeadTrainer(cfg.B, cfg.H, cfg.W, cfg.OS, cfg.Cin, cfg.Cskip, cfg.NC, W, device=0, seed=5, dropout=drop)
-    tr.debug_taps = {}
     bf = lambda a: torch.from_numpy(a).cuda().to(torch.bfloat16).contiguous()
     tr.forward_backward(bf(feat), bf(skip), torch.from_numpy(labels).cuda())
     torch.cuda.synchronize()
     keep = train_ffi.dropout_keep_mask(cfg.B * cfg.h * cfg.w * 256, train.dropout_seed(5, 0, 0), drop) if drop > 0 else None
     ref = TR.head_train_forward_backward(feat, skip, labels, W, cfg, keep_mask=keep, drop_rate=drop, mode=os.environ.get('ORACLE_MODE', 'bf16'))
     print('== labels %s dropout %.1f: loss %.6f vs %.6f' % (mode, drop, tr.loss(), ref['loss']))
-    for k, v in tr.debug_taps.items():
-        r = ref['act_grads'][k]
-        print('  act %-22s %.4f' % (k, rel(v[:, :r.shape[-1]], r)))
     g = tr.get_grads()
     for k, v in ref['grads'].items():
         print('  w   %-40s %.4f' % ('/'.join(k), rel(g[k], v)))

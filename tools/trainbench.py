@@ -17,8 +17,6 @@ def main():
     ap.add_argument('--cskip', type=int, default=256)
     ap.add_argument('--size', type=int, default=512)
     ap.add_argument('--no-graph', action='store_true', help='launch the kernels one by one instead of replaying the captured CUDA graph')
-    ap.add_argument('--no-tn', action='store_true', help='weight gradients through explicit transposes + the K-major GEMM (A/B)')
-    ap.add_argument('--exchange', default='p2p', choices=['p2p', 'nccl'], help='SyncBN vectors: peer-memory one-shot all-reduce or ncclAllReduce')
     ap.add_argument('--profile', action='store_true', help='per-phase timing (forward / backward / all-reduce / update)')
     a = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -33,7 +31,7 @@ def main():
     from oracle import head_ref as R          # weight initialisation only (test infrastructure; nothing timed uses it)
     cfg = R.HeadConfig(B=a.batch, H=a.size, W=a.size, OS=16, Cin=a.cin, Cskip=a.cskip, NC=21)
     W = R.make_weights(cfg, 1234)
-    tr = train.HeadTrainer(a.batch, a.size, a.size, 16, a.cin, a.cskip, 21, W, device=local, seed=7, graph=not a.no_graph, wgrad_tn=not a.no_tn, exchange=a.exchange)
+    tr = train.HeadTrainer(a.batch, a.size, a.size, 16, a.cin, a.cskip, 21, W, device=local, seed=7, graph=not a.no_graph)
     g = torch.Generator(device='cuda').manual_seed(1234 + rank)
     feat = torch.randn(a.batch, cfg.h, cfg.w, a.cin, device='cuda', generator=g).clamp_(min=0).to(torch.bfloat16)
     skip = torch.randn(a.batch, cfg.hs, cfg.ws, a.cskip, device='cuda', generator=g).to(torch.bfloat16)
@@ -67,15 +65,13 @@ def main():
         print(json.dumps({'metric': 'images/sec DeepLabV3+ head training step (fwd+loss+bwd+SyncBN+grad all-reduce+SGD)', 'value': a.batch * world * a.steps / (ms / 1e3),
                           'unit': 'images/s', 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms / a.steps, 'dtype': 'bf16',
                           'config': {'workload': 'cfg5 Xception OS16 %dx%d head train step, %d img/GPU, global batch %d' % (a.size, a.size, a.batch, a.batch * world)},
-                          'gpu_launches_per_step': launches, 'cuda_graph': not a.no_graph, 'wgrad': 'transpose+NT' if a.no_tn else 'TN (MN-major operands)', 'loss': loss, 'phases': phases, 'exchange': tr.comm_backend()}))
-    # teardown: drop the captured graph (it holds NCCL kernels) before the process group goes away, and leave without the
-    # collective destructor — destroy_process_group() after a graph capture with NCCL inside has been seen to hang at exit
-    tr._graph = None
+                          'gpu_launches_per_step': launches, 'cuda_graph': not a.no_graph, 'loss': loss, 'phases': phases, 'exchange': tr.comm_backend()}))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-        sys.stdout.flush()
-        os._exit(0)
+    tr.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':
