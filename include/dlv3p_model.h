@@ -37,7 +37,11 @@ enum { /* flags */
   DLV3P_MODEL_FLAG_KEEP_ALL = 1, /* every intermediate keeps its own tensor (block-level parity taps); default: the 16 middle-flow
                                     units ping-pong over four buffers and only the last unit's tap is meaningful */
   DLV3P_MODEL_FLAG_NO_PDL = 2,   /* measurement aid: launch the backbone kernels without programmatic dependent launch */
-  DLV3P_MODEL_FLAG_UNFUSED_ENTRY = 4 /* measurement aid: the entry flow's SepConv_BN layers as depthwise kernel + GEMM (like the rest of the backbone) */
+  DLV3P_MODEL_FLAG_UNFUSED_ENTRY = 4, /* measurement aid: the entry flow's SepConv_BN layers as depthwise kernel + GEMM (like the rest of the backbone) */
+  DLV3P_MODEL_FLAG_FP32 = 8      /* PRECISION MODE: the whole model in plain fp32 arithmetic (the reference's default numerics, train.py:37-46):
+                                    weights as given, fp32 activations, CUDA-core kernels (csrc/f32_kernels.cuh).  Held to 1e-4 relative
+                                    against the fp32 oracle; a mode to prove results, not the performance path.  out_mode: labels or
+                                    low-resolution logits */
 };
 
 typedef struct dlv3p_model_config {

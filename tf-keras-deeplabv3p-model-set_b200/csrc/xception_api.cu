@@ -23,6 +23,7 @@
 #include "bb_gemm.cuh"
 #include "bb_kernels.cuh"
 #include "bb_sepconv.cuh"
+#include "f32_kernels.cuh"
 
 using namespace dlv3p;
 
@@ -314,6 +315,8 @@ struct Op {
   double flops = 0, bytes = 0;
 };
 
+struct BlockSpec { std::string prefix; int cin; int depth[3]; int shortcut /*0 conv, 1 sum, 2 none*/; int stride, rate; bool act; bool ret_skip; };
+
 struct dlv3p_model {
   dlv3p_model_config cfg{};
   int device = 0;
@@ -339,6 +342,15 @@ struct dlv3p_model {
   // profiling
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;
+  // fp32 precision mode (DLV3P_MODEL_FLAG_FP32): host copies of the head's weights, device fp32 weights, activation buffers, taps
+  bool fp32 = false;
+  std::map<std::string, std::vector<float>> head_w;
+  std::map<std::string, float*> f32_w;
+  std::vector<std::pair<float*, size_t>> f32_bufs;
+  size_t f32_next = 0;
+  struct F32Tap { float* p; int B, H, W, C; };
+  std::map<std::string, F32Tap> f32_taps;
+  std::vector<BlockSpec> f32_blocks;
 };
 
 namespace {
@@ -402,8 +414,6 @@ int new_tensor(dlv3p_model* m, int B, int H, int W, int C, const char* tap = nul
   return idx;
 }
 
-struct BlockSpec { std::string prefix; int cin; int depth[3]; int shortcut /*0 conv, 1 sum, 2 none*/; int stride, rate; bool act; bool ret_skip; };
-
 // the architecture walk of Xception_body (deeplabv3p_xception.py:96-163): registers weights, tensors and ops
 int build_plan(dlv3p_model* m) {
   const dlv3p_model_config& g = m->cfg;
@@ -420,6 +430,7 @@ int build_plan(dlv3p_model* m) {
   blocks.push_back({"exit_flow_block1", 728, {728, 1024, 1024}, 0, s32, r16, false, false});
   blocks.push_back({"exit_flow_block2", 1024, {1536, 1536, 2048}, 2, 1, r32, true, false});
 
+  m->f32_blocks = blocks;
   const int B = g.B;
   // entry_flow_conv1_1: Conv2D(32, 3, strides 2, 'same'): TensorFlow pads (total/2, total - total/2) per axis
   int h = cdiv(g.H, 2), w = cdiv(g.W, 2);
@@ -570,6 +581,212 @@ void register_block_weights(dlv3p_model* m) {
 
 }  // namespace
 
+
+// =====================================================================================================
+// fp32 precision mode (f32_kernels.cuh): the same graph in plain fp32, weights as given (no bf16 rounding anywhere)
+// =====================================================================================================
+namespace {
+
+int f32_grid(size_t items) {
+  size_t g = (items + 255) / 256;
+  if (g > 148 * 32) g = 148 * 32;
+  return static_cast<int>(g < 1 ? 1 : g);
+}
+const std::vector<float>* f32_host(const dlv3p_model* m, const std::string& key) {
+  auto it = m->windex.find(key);
+  if (it != m->windex.end()) return &m->weights[it->second].data;
+  auto ih = m->head_w.find(key);
+  return ih == m->head_w.end() ? nullptr : &ih->second;
+}
+int f32_put(dlv3p_model* m, const std::string& key, const std::vector<float>& h) {
+  float* d = nullptr;
+  if (cudaMalloc(&d, h.size() * sizeof(float) + 256) != cudaSuccess) return mfail(m, DLV3P_ERR_NOMEM, "fp32 mode: cudaMalloc failed");
+  cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice);
+  auto it = m->f32_w.find(key);
+  if (it != m->f32_w.end()) cudaFree(it->second);
+  m->f32_w[key] = d;
+  return 0;
+}
+
+int finalize_fp32(dlv3p_model* m) {
+  MCU(m, cudaSetDevice(m->device));
+  MCU(m, cudaDeviceSynchronize());
+  // every variable the whole model expects: backbone inventory + head inventory
+  const int n = dlv3p_model_num_weights(m);
+  for (int i = 0; i < n; ++i) {
+    const char *layer, *var;
+    int64_t shape[4];
+    int rank;
+    dlv3p_model_weight_info(m, i, &layer, &var, shape, &rank);
+    const std::string key = std::string(layer) + "/" + var;
+    const std::vector<float>* h = f32_host(m, key);
+    if (!h || h->empty()) return mfail(m, DLV3P_ERR_STATE, mfmt("weight %s was never set", key.c_str()));
+    const std::string v(var);
+    if (v == "kernel" || v == "depthwise_kernel" || v == "bias") {
+      int r = f32_put(m, key, *h);
+      if (r) return r;
+    } else if (v == "gamma") {      // fold the BatchNorm once: scale = gamma * rsqrt(var + eps), shift = beta - mean * scale
+      const std::string bn(layer);
+      const std::vector<float>*be = f32_host(m, bn + "/beta"), *mu = f32_host(m, bn + "/moving_mean"), *va = f32_host(m, bn + "/moving_variance");
+      if (!be || !mu || !va || be->empty() || mu->empty() || va->empty()) return mfail(m, DLV3P_ERR_STATE, mfmt("BatchNorm %s is incomplete", bn.c_str()));
+      const bool backbone = m->windex.count(key) != 0;
+      Fold f = fold_bn(h->data(), be->data(), mu->data(), va->data(), static_cast<int>(h->size()), backbone ? 1e-3f : 1e-5f);
+      int r = f32_put(m, bn + "/scale", f.scale);
+      if (r || (r = f32_put(m, bn + "/shift", f.shift))) return r;
+    }
+  }
+  m->finalized = true;
+  return DLV3P_OK;
+}
+
+struct F32Run {
+  dlv3p_model* m;
+  cudaStream_t st;
+  int rc = 0;
+  struct T { float* p; int B, H, W, C; int M() const { return B * H * W; } };
+  float* buf(size_t n) {
+    if (m->f32_next < m->f32_bufs.size() && m->f32_bufs[m->f32_next].second >= n) return m->f32_bufs[m->f32_next++].first;
+    float* d = nullptr;
+    if (cudaMalloc(&d, n * sizeof(float) + 256) != cudaSuccess) { rc = mfail(m, DLV3P_ERR_NOMEM, "fp32 mode: cudaMalloc failed"); return nullptr; }
+    if (m->f32_next < m->f32_bufs.size()) { cudaFree(m->f32_bufs[m->f32_next].first); m->f32_bufs[m->f32_next] = {d, n}; }
+    else m->f32_bufs.push_back({d, n});
+    ++m->f32_next;
+    return d;
+  }
+  T tensor(int B, int H, int W, int C) { return T{buf(static_cast<size_t>(B) * H * W * C), B, H, W, C}; }
+  const float* w(const std::string& key) {
+    auto it = m->f32_w.find(key);
+    if (it == m->f32_w.end()) { if (!rc) rc = mfail(m, DLV3P_ERR_STATE, mfmt("fp32 mode: missing %s", key.c_str())); return nullptr; }
+    return it->second;
+  }
+  void tap(const std::string& name, const T& t) { m->f32_taps[name] = {t.p, t.B, t.H, t.W, t.C}; }
+  void check(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess && !rc) rc = mfail(m, DLV3P_ERR_CUDA, mfmt("fp32 mode launch %s: %s", what, cudaGetErrorString(e)));
+    ++m->launches_last;
+  }
+  T conv(const T& x, const uint8_t* img, const std::string& name, const std::string& bn, int k, int stride, int pad_t, int pad_l, int Cout, int Ho, int Wo) {
+    T y = tensor(x.B, Ho, Wo, Cout);
+    if (rc) return y;
+    F32ConvParams P{x.p, img, w(name + "/kernel"), w(bn + "/scale"), w(bn + "/shift"), y.p, x.B, x.H, x.W, x.C, Ho, Wo, Cout, k, stride, pad_t, pad_l, 1};
+    if (!rc) f32_conv_kernel<<<f32_grid(static_cast<size_t>(y.M()) * Cout), 256, 0, st>>>(P);
+    check(name.c_str());
+    return y;
+  }
+  T depthwise(const T& x, const std::string& name, const std::string& bn, int stride, int rate, int relu_in, int relu_out) {
+    T y = tensor(x.B, cdiv(x.H, stride), cdiv(x.W, stride), x.C);
+    if (rc) return y;
+    F32DwParams P{x.p, w(name + "/depthwise_kernel"), w(bn + "/scale"), w(bn + "/shift"), y.p, x.B, x.H, x.W, x.C, y.H, y.W, stride, rate, relu_in, relu_out};
+    if (!rc) f32_depthwise_kernel<<<f32_grid(static_cast<size_t>(y.M()) * y.C), 256, 0, st>>>(P);
+    check(name.c_str());
+    return y;
+  }
+  // y[M, ldy @ col_off] = epi(a[M, K] * W[K, N])
+  void gemm(const float* a, int M, int K, int lda, const std::string& name, const float* scale, const float* shift, int relu, const float* residual, float* y,
+            int N, int ldy, int col_off, int sub_Ho = 0, int sub_Wo = 0, int sub_H = 0, int sub_W = 0) {
+    if (rc) return;
+    F32GemmParams P{a, w(name + "/kernel"), scale, shift, residual, y, M, K, N, lda, ldy, col_off, relu, sub_Ho, sub_Wo, sub_H, sub_W};
+    if (!rc) f32_gemm_kernel<<<dim3(cdiv(N, 64), cdiv(M, 64)), 256, 0, st>>>(P);
+    check(name.c_str());
+  }
+  T pointwise(const T& x, const std::string& name, const std::string& bn, int N, int relu, const float* residual) {
+    T y = tensor(x.B, x.H, x.W, N);
+    gemm(x.p, x.M(), x.C, x.C, name, w(bn + "/scale"), w(bn + "/shift"), relu, residual, y.p, N, N, 0);
+    return y;
+  }
+};
+
+int forward_fp32(dlv3p_model* m, const void* d_images, void* d_out, cudaStream_t st) {
+  const dlv3p_model_config& g = m->cfg;
+  m->launches_last = 0;
+  m->f32_next = 0;
+  F32Run R{m, st};
+  using T = F32Run::T;
+  // ---------------- Xception_body (deeplabv3p_xception.py:96-163)
+  const int h2 = cdiv(g.H, 2), w2 = cdiv(g.W, 2);
+  T img{const_cast<float*>(g.img_dtype == DLV3P_IMG_F32 ? static_cast<const float*>(d_images) : nullptr), g.B, g.H, g.W, 3};
+  T x = R.conv(img, g.img_dtype == DLV3P_IMG_U8 ? static_cast<const uint8_t*>(d_images) : nullptr, "entry_flow_conv1_1", "entry_flow_conv1_1_BN", 3, 2,
+               m->pad_t, m->pad_l, 32, h2, w2);
+  R.tap("entry_flow_conv1_1", x);
+  x = R.conv(x, nullptr, "entry_flow_conv1_2", "entry_flow_conv1_2_BN", 3, 1, 1, 1, 64, h2, w2);
+  R.tap("entry_flow_conv1_2", x);
+  T skip{};
+  for (const BlockSpec& b : m->f32_blocks) {
+    const T inp = x;
+    const float* res = nullptr;
+    if (b.shortcut == 0) {      // 1x1 conv (stride-2 sampling inside the GEMM's row addressing) -> BN
+      const int ho = cdiv(inp.H, b.stride), wo = cdiv(inp.W, b.stride);
+      T sc = R.tensor(inp.B, ho, wo, b.depth[2]);
+      R.gemm(inp.p, sc.M(), inp.C, inp.C, b.prefix + "_shortcut", R.w(b.prefix + "_shortcut_BN/scale"), R.w(b.prefix + "_shortcut_BN/shift"), 0, nullptr, sc.p,
+             b.depth[2], b.depth[2], 0, b.stride == 2 ? ho : 0, b.stride == 2 ? wo : 0, inp.H, inp.W);
+      res = sc.p;
+    } else if (b.shortcut == 1) {
+      res = inp.p;
+    }
+    T r = x;
+    for (int i = 0; i < 3; ++i) {
+      const std::string p = mfmt("%s_separable_conv%d", b.prefix.c_str(), i + 1);
+      T d = R.depthwise(r, p + "_depthwise", p + "_depthwise_BN", i == 2 ? b.stride : 1, b.rate, b.act ? 0 : 1, b.act ? 1 : 0);
+      r = R.pointwise(d, p + "_pointwise", p + "_pointwise_BN", b.depth[i], b.act ? 1 : 0, i == 2 ? res : nullptr);
+      if (i == 1 && b.ret_skip) skip = r;
+    }
+    x = r;
+    R.tap(b.prefix, x);
+  }
+  R.tap("feature", x);
+  R.tap("skip", skip);
+  // ---------------- ASPP_block (layers.py:114-163)
+  const int M1 = x.M(), npix = x.H * x.W, Cin = x.C;
+  int rates[3] = {6, 12, 18};
+  if (g.OS == 8) { rates[0] = 12; rates[1] = 24; rates[2] = 36; } else if (g.OS == 32) { rates[0] = 3; rates[1] = 6; rates[2] = 9; }
+  T concat = R.tensor(x.B, x.H, x.W, 1280);
+  {
+    float* pool = R.buf(static_cast<size_t>(x.B) * Cin);
+    float* b4 = R.buf(static_cast<size_t>(x.B) * 256);
+    if (!R.rc) f32_global_mean_kernel<<<cdiv(x.B * Cin, 256), 256, 0, st>>>(x.p, pool, x.B, npix, Cin);
+    R.check("image pooling mean");
+    R.gemm(pool, x.B, Cin, Cin, "image_pooling", R.w("image_pooling_BN/scale"), R.w("image_pooling_BN/shift"), 1, nullptr, b4, 256, 256, 0);
+    if (!R.rc) f32_bcast_kernel<<<f32_grid(static_cast<size_t>(M1) * 256), 256, 0, st>>>(b4, concat.p, x.B, npix, 256, 1280, 0);   // bilinear resize of a 1x1 map
+    R.check("aspp_resize");
+  }
+  R.gemm(x.p, M1, Cin, Cin, "aspp0", R.w("aspp0_BN/scale"), R.w("aspp0_BN/shift"), 1, nullptr, concat.p, 256, 1280, 256);
+  for (int i = 1; i <= 3; ++i) {
+    const std::string p = mfmt("aspp%d", i);
+    T d = R.depthwise(x, p + "_depthwise", p + "_depthwise_BN", 1, rates[i - 1], 0, 1);
+    R.gemm(d.p, M1, Cin, Cin, p + "_pointwise", R.w(p + "_pointwise_BN/scale"), R.w(p + "_pointwise_BN/shift"), 1, nullptr, concat.p, 256, 1280, 256 * (i + 1));
+  }
+  T aspp = R.tensor(x.B, x.H, x.W, 256);
+  R.gemm(concat.p, M1, 1280, 1280, "concat_projection", R.w("concat_projection_BN/scale"), R.w("concat_projection_BN/shift"), 1, nullptr, aspp.p, 256, 256, 0);
+  R.tap("aspp_out", aspp);
+  // ---------------- Decoder_block (layers.py:199-219)
+  T dec_in = R.tensor(skip.B, skip.H, skip.W, 304);
+  if (!R.rc) f32_resize_kernel<<<f32_grid(static_cast<size_t>(dec_in.M()) * 256), 256, 0, st>>>(aspp.p, dec_in.p, aspp.B, aspp.H, aspp.W, 256, skip.H, skip.W, 304, 0);
+  R.check("decoder_resize");
+  R.gemm(skip.p, skip.M(), skip.C, skip.C, "feature_projection0", R.w("feature_projection0_BN/scale"), R.w("feature_projection0_BN/shift"), 1, nullptr, dec_in.p, 48,
+         304, 256);
+  T d0 = R.depthwise(dec_in, "decoder_conv0_depthwise", "decoder_conv0_depthwise_BN", 1, 1, 0, 1);
+  T y0 = R.pointwise(d0, "decoder_conv0_pointwise", "decoder_conv0_pointwise_BN", 256, 1, nullptr);
+  T d1 = R.depthwise(y0, "decoder_conv1_depthwise", "decoder_conv1_depthwise_BN", 1, 1, 0, 1);
+  T y1 = R.pointwise(d1, "decoder_conv1_pointwise", "decoder_conv1_pointwise_BN", 256, 1, nullptr);
+  R.tap("decoder_out", y1);
+  // ---------------- tail (model.py:75-86, deeplab.py:99)
+  T lg = R.tensor(y1.B, y1.H, y1.W, g.NC);
+  R.gemm(y1.p, y1.M(), 256, 256, "conv_upsample", nullptr, R.w("conv_upsample/bias"), 0, nullptr, lg.p, g.NC, g.NC, 0);
+  float* planar = g.out_mode == DLV3P_OUT_LOGITS_LOWRES ? static_cast<float*>(d_out) : R.buf(static_cast<size_t>(lg.M()) * g.NC);
+  if (!R.rc) f32_to_planar_kernel<<<f32_grid(static_cast<size_t>(lg.M()) * g.NC), 256, 0, st>>>(lg.p, planar, lg.B, lg.H * lg.W, g.NC);
+  R.check("logits to planar");
+  m->f32_taps["logits"] = {planar, lg.B, g.NC, lg.H, lg.W};
+  if (R.rc) return R.rc;
+  if (g.out_mode == DLV3P_OUT_LABELS_U8) {
+    int r = dlv3p_op_resize_argmax(m->device, planar, lg.B, g.NC, lg.H, lg.W, g.H, g.W, static_cast<uint8_t*>(d_out), st);
+    if (r) return mfail(m, r, dlv3p_last_error(nullptr));
+    ++m->launches_last;
+  }
+  return DLV3P_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 const char* dlv3p_model_last_error(const dlv3p_model* m) { return m ? m->err.c_str() : g_model_tls_error.c_str(); }
@@ -604,8 +821,12 @@ int dlv3p_model_create(const dlv3p_model_config* cfg, int device, dlv3p_model** 
   int r = build_plan(m);
   if (r) return bail(r, m->err);
   register_block_weights(m);
-  // activations
+  m->fp32 = (g.flags & DLV3P_MODEL_FLAG_FP32) != 0;
+  if (m->fp32 && g.out_mode != DLV3P_OUT_LABELS_U8 && g.out_mode != DLV3P_OUT_LOGITS_LOWRES)
+    return bail(DLV3P_ERR_UNSUPPORTED, "fp32 precision mode writes labels or low-resolution logits");
+  // activations (the fp32 precision mode allocates its own fp32 buffers on its first forward)
   for (Tensor& t : m->tensors) {
+    if (m->fp32) break;
     void* p = nullptr;
     if ((r = m_alloc(m, &p, t.elems() * 2, false))) return bail(r, m->err);
     t.p = static_cast<__nv_bfloat16*>(p);
@@ -630,6 +851,8 @@ void dlv3p_model_destroy(dlv3p_model* m) {
     for (void* p : m->allocs) cudaFree(p);
     for (void* p : m->weight_allocs) cudaFree(p);
     if (m->d_tm) cudaFree(m->d_tm);
+    for (auto& kv : m->f32_w) cudaFree(kv.second);
+    for (auto& b : m->f32_bufs) cudaFree(b.first);
     if (m->in_stage) cudaFree(m->in_stage);
     if (m->out_stage) cudaFree(m->out_stage);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
@@ -659,6 +882,14 @@ int dlv3p_model_set_weight(dlv3p_model* m, const char* layer, const char* var, c
   if (it == m->windex.end()) {
     int r = dlv3p_set_weight(m->head, layer, var, host, shape, rank);
     if (r) return mfail(m, r, dlv3p_last_error(m->head));
+    if (m->fp32) {
+      size_t n = 1;
+      for (int i = 0; i < rank; ++i) n *= static_cast<size_t>(shape[i]);
+      std::string ln(layer);
+      if (ln == "logits_semantic") ln = "conv_upsample";
+      m->head_w[ln + "/" + var].assign(host, host + n);
+      m->finalized = false;
+    }
     return DLV3P_OK;
   }
   MWeight& s = m->weights[it->second];
@@ -679,6 +910,7 @@ int dlv3p_model_finalize_weights(dlv3p_model* m) {
   for (const MWeight& s : m->weights)
     if (!s.set) return mfail(m, DLV3P_ERR_STATE, mfmt("weight %s/%s was never set", s.layer.c_str(), s.var.c_str()));
   if (m->plan_only) return mfail(m, DLV3P_ERR_STATE, "plan-only model (device -1): nothing can be uploaded or run; there is no CPU path");
+  if (m->fp32) return finalize_fp32(m);
   int r = dlv3p_finalize_weights(m->head);
   if (r) return mfail(m, r, dlv3p_last_error(m->head));
   if (m->finalized) return DLV3P_OK;
@@ -862,6 +1094,7 @@ static int model_forward_impl(dlv3p_model* m, const void* d_images, void* d_out,
   if (!m->finalized) return mfail(m, DLV3P_ERR_STATE, "dlv3p_model_finalize_weights has not been called");
   if (!d_images || !d_out) return mfail(m, DLV3P_ERR_INVALID, "null image / output pointer");
   MCU(m, cudaSetDevice(m->device));
+  if (m->fp32) return forward_fp32(m, d_images, d_out, st);
   int r = run_backbone(m, d_images, st);
   if (r) return r;
   r = dlv3p_forward(m->head, m->tensors[m->t_feat].p, m->tensors[m->t_skip].p, d_out, st);
@@ -974,6 +1207,16 @@ int dlv3p_model_tap_shape(const dlv3p_model* m, const char* name, int64_t shape_
 int dlv3p_model_read_tap(dlv3p_model* m, const char* name, float* host_out, size_t host_elems) {
   if (!m || !name || !host_out) return mfail(m, DLV3P_ERR_INVALID, "null argument");
   if (m->plan_only) return mfail(m, DLV3P_ERR_STATE, "plan-only model (device -1): there is no CPU path");
+  if (m->fp32) {
+    auto ft = m->f32_taps.find(name);
+    if (ft == m->f32_taps.end()) return mfail(m, DLV3P_ERR_NAME, mfmt("no fp32 tap named %s (run a forward first)", name));
+    const size_t n = static_cast<size_t>(ft->second.B) * ft->second.H * ft->second.W * ft->second.C;
+    if (host_elems < n) return mfail(m, DLV3P_ERR_INVALID, mfmt("tap %s needs %zu elements, buffer has %zu", name, n, host_elems));
+    MCU(m, cudaSetDevice(m->device));
+    MCU(m, cudaDeviceSynchronize());
+    MCU(m, cudaMemcpy(host_out, ft->second.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return DLV3P_OK;
+  }
   auto it = m->taps.find(name);
   if (it == m->taps.end()) {
     int r = dlv3p_read_tap(m->head, name, host_out, host_elems);

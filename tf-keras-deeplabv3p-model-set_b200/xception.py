@@ -23,7 +23,8 @@ class DeepLabV3PlusXception:
     """Deeplabv3pXception + the prediction tail of model.py:75-86 in ONE native model context."""
 
     def __init__(self, input_shape: Sequence[int] = (512, 512, 3), num_classes: int = 21, OS: int = 16, batch: int = 1,
-                 out_mode: int = ffi.OUT_LABELS_U8, image_dtype=np.uint8, device: int = 0, keep_intermediates: bool = False, flags: int = 0):
+                 out_mode: int = ffi.OUT_LABELS_U8, image_dtype=np.uint8, device: int = 0, keep_intermediates: bool = False, flags: int = 0,
+                 precision: str = 'bf16'):
         if OS not in (8, 16, 32):
             raise ValueError('invalid output stride', OS)                      # deeplabv3p_xception.py:116-117
         if len(input_shape) == 3 and input_shape[2] != 3:
@@ -34,6 +35,13 @@ class DeepLabV3PlusXception:
             raise ValueError('image_dtype must be uint8 (raw RGB) or float32 (normalised to [-1, 1])')
         self.out_mode = out_mode
         self.device = device
+        # 'bf16': the tcgen05 performance path (bf16 operands and activations, fp32 accumulation); 'fp32': the precision mode — the
+        # whole model in plain fp32 arithmetic like the reference's default TensorFlow numerics (1e-4 against the fp32 oracle)
+        if precision not in ('bf16', 'fp32'):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.precision = precision
+        if precision == 'fp32':
+            flags |= ffi.MODEL_FLAG_FP32
         self.model = ffi.Model(device=device, B=self.B, H=self.H, W=self.W, OS=self.OS, NC=self.NC,
                                img_dtype=ffi.IMG_U8 if self.image_dtype == np.uint8 else ffi.IMG_F32, out_mode=out_mode,
                                flags=(ffi.MODEL_FLAG_KEEP_ALL if keep_intermediates else 0) | flags)
