@@ -38,6 +38,8 @@ enum { /* flags */
                                     units ping-pong over four buffers and only the last unit's tap is meaningful */
   DLV3P_MODEL_FLAG_NO_PDL = 2,   /* measurement aid: launch the backbone kernels without programmatic dependent launch */
   DLV3P_MODEL_FLAG_UNFUSED_ENTRY = 4, /* measurement aid: the entry flow's SepConv_BN layers as depthwise kernel + GEMM (like the rest of the backbone) */
+  DLV3P_MODEL_FLAG_FUSED_MIDDLE = 16, /* experiment (slower): the middle flow's SepConv_BN layers through the fused two-SM cluster kernel
+                                    (bb_sepwide.cuh) instead of depthwise kernel + GEMM */
   DLV3P_MODEL_FLAG_FP32 = 8      /* PRECISION MODE: the whole model in plain fp32 arithmetic (the reference's default numerics, train.py:37-46):
                                     weights as given, fp32 activations, CUDA-core kernels (csrc/f32_kernels.cuh).  Held to 1e-4 relative
                                     against the fp32 oracle; a mode to prove results, not the performance path.  out_mode: labels or
@@ -105,6 +107,12 @@ int dlv3p_op_bb_depthwise(int device, const void* x_bf16, int B, int H, int W, i
  * a, residual, out: device bf16; w_kn: HOST fp32 (Keras 1x1 kernel); K % 8 == 0, N % 8 == 0. */
 int dlv3p_op_bb_pointwise(int device, const void* a_bf16, int64_t M, int K, int N, const float* w_kn_fp32, const float* scale, const float* shift,
                           int relu, const void* residual_bf16, void* out_bf16, void* cuda_stream);
+/* Fused SepConv_BN of the middle flow (depth_activation False, layers.py:74-111; residual = _xception_block 'sum', deeplabv3p_xception.py:88-90):
+ * out = bf16(BN2(pointwise(bf16(BN1(depthwise3x3(relu_in ? relu(x) : x))))) [ReLU] [+ residual]).  x: device bf16 [B,H,W,C] (C % 8 == 0, C <= 768);
+ * dw_hwc: HOST fp32 [3,3,C]; w_kn: HOST fp32 [C,N] (656 < N <= 768, N % 8 == 0); residual / out: device bf16 [B,H,W,N]. */
+int dlv3p_op_bb_sepwide(int device, const void* x_bf16, int B, int H, int W, int C, int N, int relu_in, const float* dw_hwc_fp32, const float* dw_scale,
+                        const float* dw_shift, const float* w_kn_fp32, const float* scale, const float* shift, int relu_out, const void* residual_bf16,
+                        void* out_bf16, void* cuda_stream);
 /* Conv2D(64, 3x3, 'same') on 32 channels + scale/shift + ReLU (entry_flow_conv1_2).  x: device bf16 [B,H,W,32]; w_hwio: HOST fp32 [3,3,32,64]. */
 int dlv3p_op_conv3x3_c32(int device, const void* x_bf16, int B, int H, int W, const float* w_hwio_fp32, const float* scale, const float* shift,
                          void* out_bf16, void* cuda_stream);
@@ -114,7 +122,8 @@ int dlv3p_op_stem_conv(int device, const void* img, int img_dtype, int B, int H,
                        void* out_bf16, void* cuda_stream);
 
 /* Benchmark aid (tools/kbench_bb.py): average ms per launch of ONE backbone operator on synthetic device data (CUDA events).
- * op 0 pointwise GEMM {M, K, N, residual, BN (0 = automatic)}; op 1 depthwise {B, H, W, C, stride, rate}.
+ * op 0 pointwise GEMM {M, K, N, residual, BN (0 = automatic)}; op 1 depthwise {B, H, W, C, stride, rate}; op 2 fused middle-flow
+ * SepConv_BN {B, H, W, C, N, residual}.
  * flags: per-kernel debug bits that switch parts of the kernel off to attribute time; results are then meaningless. */
 int dlv3p_op_bb_time(int device, int op, const int64_t* dims, int ndims, int iters, int flags, float* ms_out);
 

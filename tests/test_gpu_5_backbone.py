@@ -115,6 +115,47 @@ def test_backbone_pointwise(gpu, M, K, N, relu, res):
     _one_rounding(got, y, 'pointwise %dx%dx%d' % (M, K, N))
 
 
+@pytest.mark.parametrize('B,H,W,C,N,relu_in,relu_out,res', [
+    (2, 32, 32, 728, 728, True, True, False),      # middle_flow_unit_k_separable_conv1: ReLU in, next layer's ReLU in the epilogue
+    (3, 32, 32, 728, 728, False, False, True),     # separable_conv3: residual sum; 24 tiles
+    (1, 19, 45, 728, 728, True, False, True),      # partial tiles on both axes
+    (40, 16, 16, 728, 728, False, True, False),    # 80 tiles: more than one tile per cluster (accumulator and stage reuse)
+    (2, 24, 32, 704, 760, True, False, True),      # other channel counts: 11 K blocks, N = 760
+])
+def test_backbone_sepwide_fused_middle_flow(gpu, B, H, W, C, N, relu_in, relu_out, res):
+    """The fused middle-flow SepConv_BN on two-SM clusters (N split over the pair, depthwise result shared through distributed shared
+    memory) against float64 with the depthwise result rounded to bf16 where the kernel rounds it (the A operand)."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(B * 1000 + H * 10 + N)
+    x = R.bf16_round(rng.standard_normal((B, H, W, C)).astype(np.float32))
+    dw = rng.normal(0, 0.3, (3, 3, C)).astype(np.float32)
+    ds, dt = rng.uniform(0.5, 1.5, C).astype(np.float32), rng.normal(0, 0.1, C).astype(np.float32)
+    w = rng.normal(0, np.sqrt(2.0 / C), (C, N)).astype(np.float32)
+    scale, shift = rng.uniform(0.5, 1.5, N).astype(np.float32), rng.normal(0, 0.1, N).astype(np.float32)
+    r = R.bf16_round(rng.standard_normal((B, H, W, N)).astype(np.float32)) if res else None
+    got = ffi.op_bb_sepwide(_bits(x), dw, w, relu_in, ds, dt, scale, shift, relu_out, None if r is None else _bits(r))
+    t = torch.from_numpy(x.astype(np.float64)).permute(0, 3, 1, 2)
+    if relu_in:
+        t = torch.relu(t)
+    k = torch.from_numpy((dw * ds).astype(np.float32).astype(np.float64)).permute(2, 0, 1).unsqueeze(1)
+    d = F.conv2d(t, k, None, 1, 1, 1, groups=C) + torch.from_numpy(dt.astype(np.float64)).view(1, -1, 1, 1)
+    a = R.bf16_round(d.permute(0, 2, 3, 1).numpy().astype(np.float32)).astype(np.float64)           # the A operand
+    y = a.reshape(-1, C) @ R.bf16_round(w).astype(np.float64) * scale.astype(np.float64) + shift.astype(np.float64)
+    if relu_out:
+        y = np.maximum(y, 0)
+    y = y.reshape(B, H, W, N)
+    if res:
+        y = y + r.astype(np.float64)
+    assert got.shape == (B, H, W, N)
+    # one output rounding, plus the rare 1-ulp flip of a bf16 A element (fp32 stencil vs float64: ~4 % of the outputs see one among their
+    # 728 terms, worth up to ulp(a) * |w| * scale ~ 2e-3 absolute) -> the absolute floor is 5 % of the largest output
+    got64 = R.from_bf16_bits(got).astype(np.float64)
+    err = np.abs(got64 - y)
+    tol = 1.5 * BF16_ULP * np.maximum(np.abs(y), 5e-2 * np.abs(y).max()) + 1e-6
+    assert (err <= tol).all(), 'sepwide: max err %.3g at |ref| %.3g, %d off' % (err.max(), np.abs(y).flat[err.argmax()], int((err > tol).sum()))
+
+
 # ---------------------------------------------------------------------------------------------------- blocks and the whole backbone
 def _model_and_oracle(OS, H, W, B=2, seed=4321, NC=21, keep=True, out_mode=ffi.OUT_LABELS_U8, image_dtype=np.uint8, precision='bf16'):
     Wb = X.make_calibrated_weights(OS, seed, size=64)

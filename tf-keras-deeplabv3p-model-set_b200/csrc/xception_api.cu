@@ -23,6 +23,7 @@
 #include "bb_gemm.cuh"
 #include "bb_kernels.cuh"
 #include "bb_sepconv.cuh"
+#include "bb_sepwide.cuh"
 #include "f32_kernels.cuh"
 
 using namespace dlv3p;
@@ -231,6 +232,26 @@ cudaError_t launch_sepconv(int KB, int NB, const BbSepParams& Q, int num_sms, cu
   }
   return cudaErrorInvalidValue;
 }
+// fused SepConv_BN of the middle flow (bb_sepwide.cuh): one cluster of two CTAs per 8 x 16-pixel tile
+bool sepwide_supported(int C, int N, int stride, int rate, bool act) {
+  return !act && stride == 1 && rate == 1 && C % 8 == 0 && C >= 64 && C <= 768 && N % 8 == 0 && N > 656 && N <= 768;
+}
+template <bool kReluIn>
+cudaError_t launch_sepwide_t(const BbWideParams& P, int num_sms, cudaStream_t st) {
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(bb_sepwide_kernel<kReluIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWideSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_done[dev & 63] = true;
+  }
+  const int grid = 2 * P.num_tiles < num_sms ? 2 * P.num_tiles : (num_sms & ~1);
+  return launch_pdl(g_pdl, bb_sepwide_kernel<kReluIn>, dim3(grid), dim3(kWideThreads), kWideSmemBytes, st, P);
+}
+cudaError_t launch_sepwide(const BbWideParams& P, bool relu_in, int num_sms, cudaStream_t st) {
+  return relu_in ? launch_sepwide_t<true>(P, num_sms, st) : launch_sepwide_t<false>(P, num_sms, st);
+}
 cudaError_t launch_conv3x3(const Conv3x3Params& P, int num_sms, cudaStream_t st) {
   static bool attr_done[64] = {};
   int dev = 0;
@@ -297,7 +318,7 @@ struct Tensor {
   size_t elems() const { return static_cast<size_t>(B) * H * W * C; }
   int M() const { return B * H * W; }
 };
-enum OpKind { OP_STEM, OP_CONV3, OP_DW, OP_PW, OP_SUB, OP_SEP };
+enum OpKind { OP_STEM, OP_CONV3, OP_DW, OP_PW, OP_SUB, OP_SEP, OP_WIDE };
 struct Op {
   OpKind kind;
   std::string name;      // Keras layer name of the convolution the kernel computes
@@ -309,7 +330,7 @@ struct Op {
   DwVariant dv{1, 1, 8, 32};
   // device weights
   uint16_t* w16 = nullptr;
-  float *wf = nullptr, *scale = nullptr, *shift = nullptr;
+  float *wf = nullptr, *scale = nullptr, *shift = nullptr, *dshift = nullptr;
   std::vector<float> h_scale, h_shift;
   int tm0 = -1;          // first tensor-map slot of the op
   double flops = 0, bytes = 0;
@@ -505,6 +526,27 @@ int build_plan(dlv3p_model* m) {
         relu_prev = false;
         continue;
       }
+      if (sepwide_supported(c, b.depth[i], st, b.rate, b.act) && (g.flags & DLV3P_MODEL_FLAG_FUSED_MIDDLE)) {
+        // middle flow: the same fusion with N split over a cluster of two SMs that share the depthwise result (bb_sepwide.cuh)
+        const int n = b.depth[i];
+        int tp;
+        if (!pooled) tp = new_tensor(m, B, oh, ow, n);
+        else if (i == 0) tp = pooled_tensor(&pool_p, oh, ow, n);
+        else if (i == 1) tp = pooled_tensor(&pool_d, oh, ow, n);
+        else tp = (x == pool_a) ? pooled_tensor(&pool_b, oh, ow, n) : pooled_tensor(&pool_a, oh, ow, n);
+        Op f; f.kind = OP_WIDE; f.prefix = p; f.name = p + "_sepconv"; f.in = cur; f.out = tp; f.K = c; f.N = n; f.Cpad = cdiv(c, 64) * 64;
+        f.relu_in = relu_prev ? 0 : 1;
+        const bool relu_moved = i < 2 && !(i == 1 && b.ret_skip);     // see the pointwise GEMM below
+        f.relu_out = relu_moved ? 1 : 0;
+        relu_prev = relu_moved;
+        f.flops = 2.0 * B * oh * ow * (9.0 * c + static_cast<double>(c) * n); f.bytes = 2.0 * B * oh * ow * (c + n);
+        if (i == 2 && res >= 0) { f.res = res; f.bytes += 2.0 * B * oh * ow * n; }
+        seq.push_back(f);
+        if (i == 1 && b.ret_skip) { m->t_skip = tp; m->taps["skip"] = tp; }
+        cur = tp;
+        c = n;
+        continue;
+      }
       const int td = pooled ? pooled_tensor(&pool_d, oh, ow, c) : new_tensor(m, B, oh, ow, c);
       Op d; d.kind = OP_DW; d.name = p + "_depthwise"; d.bn = p + "_depthwise_BN"; d.in = cur; d.out = td; d.stride = st; d.rate = b.rate;
       d.relu_in = (b.act || relu_prev) ? 0 : 1; d.relu_out = b.act ? 1 : 0; d.K = c; d.Cpad = cdiv(c, 64) * 64;
@@ -563,7 +605,7 @@ void register_block_weights(dlv3p_model* m) {
     const std::string block = o.name.substr(0, o.name.find(is_shortcut ? "_shortcut" : "_separable_conv"));
     if (block != cur_block) { flush(); cur_block = block; }
     if (is_shortcut) { shortcut.push_back(&o); continue; }
-    if (o.kind == OP_SEP) {
+    if (o.kind == OP_SEP || o.kind == OP_WIDE) {
       add_w(m, o.prefix + "_depthwise", "depthwise_kernel", {3, 3, o.K, 1});
       add_bn(m, o.prefix + "_depthwise_BN", o.K);
       add_w(m, o.prefix + "_pointwise", "kernel", {1, 1, o.K, o.N});
@@ -968,6 +1010,26 @@ int dlv3p_model_finalize_weights(dlv3p_model* m) {
       ok = ok && tm_nhwc(&m->h_tm[o.tm0], ti.p, ti.B, ti.H, ti.W, ti.C, 64, kDwHaloW, kDwHaloH, CU_TENSOR_MAP_SWIZZLE_NONE, &terr);
       ok = ok && tm_2d(&m->h_tm[o.tm0 + 1], o.w16, o.N, o.K, o.K, 64, o.N / 2, CU_TENSOR_MAP_SWIZZLE_128B, &terr);
       ok = ok && tm_nhwc(&m->h_tm[o.tm0 + 2], to.p, to.B, to.H, to.W, to.C, 32, 16, 2, CU_TENSOR_MAP_SWIZZLE_64B, &terr);
+    } else if (o.kind == OP_WIDE) {
+      Fold fd = mfold(m, o.prefix + "_depthwise_BN", o.K);
+      if ((r = m_upload(m, &o.wf, pack_taps(MW(m, o.prefix + "_depthwise", "depthwise_kernel"), fd.scale.data(), o.K, o.Cpad)))) return r;
+      std::vector<float> dsh(o.Cpad, 0.0f);
+      std::memcpy(dsh.data(), fd.shift.data(), o.K * sizeof(float));
+      float* d_dsh = nullptr;
+      if ((r = m_upload(m, &d_dsh, dsh))) return r;
+      if ((r = m_upload(m, &o.w16, pack_kn(MW(m, o.prefix + "_pointwise", "kernel"), o.K, o.N, o.N, o.K)))) return r;
+      Fold fp = mfold(m, o.prefix + "_pointwise_BN", o.N);
+      std::vector<float> s(768, 0.0f), t(768, 0.0f);
+      std::memcpy(s.data(), fp.scale.data(), o.N * sizeof(float));
+      std::memcpy(t.data(), fp.shift.data(), o.N * sizeof(float));
+      if ((r = m_upload(m, &o.scale, s)) || (r = m_upload(m, &o.shift, t))) return r;
+      o.dshift = d_dsh;
+      const Tensor& ti = m->tensors[o.in];
+      const Tensor& to = m->tensors[o.out];
+      o.tm0 = slot(); slot(); slot();
+      ok = ok && tm_nhwc(&m->h_tm[o.tm0], ti.p, ti.B, ti.H, ti.W, ti.C, 64, kDwHaloW, kDwHaloH, CU_TENSOR_MAP_SWIZZLE_NONE, &terr);
+      ok = ok && tm_2d(&m->h_tm[o.tm0 + 1], o.w16, o.N, o.K, o.K, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B, &terr);
+      ok = ok && tm_nhwc(&m->h_tm[o.tm0 + 2], to.p, to.B, to.H, to.W, to.C, 32, 16, 2, CU_TENSOR_MAP_SWIZZLE_64B, &terr);
     } else if (o.kind == OP_PW) {
       o.Kpad = cdiv(o.K, 64) * 64;
       o.BN = pick_bb_bn(m->tensors[o.out].M(), o.N, m->num_sms);
@@ -1066,6 +1128,14 @@ static int run_backbone(dlv3p_model* m, const void* d_images, cudaStream_t st, i
       std::memcpy(Q.scale_c, o.h_scale.data(), sizeof(Q.scale_c));
       std::memcpy(Q.shift_c, o.h_shift.data(), sizeof(Q.shift_c));
       e = launch_sepconv(o.K / 64, o.N, Q, m->num_sms, st);
+    } else if (o.kind == OP_WIDE) {
+      const Tensor& to = m->tensors[o.out];
+      BbWideParams P{};
+      P.tmap_x = &m->d_tm[o.tm0]; P.tmap_w = &m->d_tm[o.tm0 + 1]; P.tmap_out = &m->d_tm[o.tm0 + 2]; P.dw_w = o.wf; P.dw_shift = o.dshift;
+      P.scale = o.scale; P.shift = o.shift; P.res = o.res >= 0 ? m->tensors[o.res].p : nullptr; P.B = to.B; P.H = to.H; P.W = to.W; P.N = o.N;
+      P.KB = o.Cpad / 64; P.tiles_x = cdiv(to.W, kDwTW); P.tiles_y = cdiv(to.H, kDwTH); P.num_tiles = to.B * P.tiles_x * P.tiles_y;
+      P.relu_out = o.relu_out; P.debug = 0;
+      e = launch_sepwide(P, o.relu_in != 0, m->num_sms, st);
     } else if (o.kind == OP_PW) {
       const Tensor& to = m->tensors[o.out];
       BbGemmParams P{};
@@ -1323,6 +1393,39 @@ int dlv3p_op_bb_pointwise(int device, const void* a, int64_t M, int K, int N, co
   return DLV3P_OK;
 }
 
+int dlv3p_op_bb_sepwide(int device, const void* x, int B, int H, int W, int C, int N, int relu_in, const float* dw_hwc, const float* dw_scale,
+                        const float* dw_shift, const float* w_kn, const float* scale, const float* shift, int relu_out, const void* residual, void* out,
+                        void* cuda_stream) {
+  int sms = 0, r = op_begin(device, &sms);
+  if (r) return r;
+  if (!x || !dw_hwc || !w_kn || !out || B < 1 || H < 1 || W < 1) return mfail(nullptr, DLV3P_ERR_INVALID, "op_bb_sepwide: bad arguments");
+  if (!sepwide_supported(C, N, 1, 1, false)) return mfail(nullptr, DLV3P_ERR_UNSUPPORTED, "op_bb_sepwide: C % 8 == 0, 64 <= C <= 768, N % 8 == 0, 656 < N <= 768");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const int Cpad = cdiv(C, 64) * 64;
+  Tmp tmp;
+  float* dw = tmp.put(pack_taps(dw_hwc, dw_scale, C, Cpad));
+  std::vector<float> sh(Cpad, 0.0f), s(768, 0.0f), t(768, 0.0f);
+  if (dw_shift) std::memcpy(sh.data(), dw_shift, C * sizeof(float));
+  for (int i = 0; i < N; ++i) { s[i] = scale ? scale[i] : 1.0f; t[i] = shift ? shift[i] : 0.0f; }
+  float* dsh = tmp.put(sh);
+  float* ds = tmp.put(s);
+  float* dt = tmp.put(t);
+  uint16_t* w16 = tmp.put(pack_kn(w_kn, C, N, N, C));
+  std::string terr;
+  std::vector<CUtensorMap> tm(3);
+  if (!tm_nhwc(&tm[0], x, B, H, W, C, 64, kDwHaloW, kDwHaloH, CU_TENSOR_MAP_SWIZZLE_NONE, &terr) || !tm_2d(&tm[1], w16, N, C, C, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B, &terr) ||
+      !tm_nhwc(&tm[2], out, B, H, W, N, 32, 16, 2, CU_TENSOR_MAP_SWIZZLE_64B, &terr)) return mfail(nullptr, DLV3P_ERR_CUDA, terr);
+  CUtensorMap* dtm = tmp.put(tm);
+  if (!dw || !dsh || !ds || !dt || !w16 || !dtm) return mfail(nullptr, DLV3P_ERR_NOMEM, "op_bb_sepwide: cudaMalloc failed");
+  BbWideParams P{};
+  P.tmap_x = &dtm[0]; P.tmap_w = &dtm[1]; P.tmap_out = &dtm[2]; P.dw_w = dw; P.dw_shift = dsh; P.scale = ds; P.shift = dt;
+  P.res = static_cast<const __nv_bfloat16*>(residual); P.B = B; P.H = H; P.W = W; P.N = N; P.KB = Cpad / 64;
+  P.tiles_x = cdiv(W, kDwTW); P.tiles_y = cdiv(H, kDwTH); P.num_tiles = B * P.tiles_x * P.tiles_y; P.relu_out = relu_out;
+  MCU(nullptr, launch_sepwide(P, relu_in != 0, sms, st));
+  MCU(nullptr, cudaStreamSynchronize(st));
+  return DLV3P_OK;
+}
+
 // Benchmark aid (tools/kbench_bb.py): average ms per launch of ONE backbone operator on synthetic device data (CUDA events).
 // op 0: pointwise GEMM {M, K, N, residual(0/1), BN (0 = pick)}; op 1: depthwise {B, H, W, C, stride, rate}.
 // flags: the kernels' debug bits (GEMM bit0 = skip the stores); results are then meaningless.
@@ -1396,6 +1499,28 @@ int dlv3p_op_bb_time(int device, int op, const int64_t* d, int ndims, int iters,
     P.tmap_x = dtm; P.w = w; P.shift = sh; P.out = reinterpret_cast<__nv_bfloat16*>(o); P.B = B; P.C = C; P.Cpad = Cpad; P.Ho = Ho; P.Wo = Wo;
     P.tiles_x = cdiv(Wo, v.TW); P.tiles_y = cdiv(Ho, v.TH); P.cgroups = Cpad / 64; P.relu_in = 1; P.relu_out = 0; P.debug = flags;
     rc = run([&] { launch_dw(v, P, st); });
+  } else if (op == 2 && ndims >= 5) {      // fused middle-flow SepConv_BN {B, H, W, C, N, residual}
+    const int B = static_cast<int>(d[0]), H = static_cast<int>(d[1]), W = static_cast<int>(d[2]), C = static_cast<int>(d[3]), N = static_cast<int>(d[4]);
+    if (!sepwide_supported(C, N, 1, 1, false)) return mfail(nullptr, DLV3P_ERR_UNSUPPORTED, "op_bb_time: sepwide shape");
+    const bool res = ndims > 5 && d[5];
+    const int Cpad = cdiv(C, 64) * 64;
+    uint16_t* x = fill(static_cast<size_t>(B) * H * W * C);
+    uint16_t* o = fill(static_cast<size_t>(B) * H * W * N);
+    uint16_t* rr = fill(static_cast<size_t>(B) * H * W * N);
+    uint16_t* w = fill(static_cast<size_t>(N) * C);
+    float* dw = tmp.put(std::vector<float>(static_cast<size_t>(9) * Cpad, 0.1f));
+    float* sh = tmp.put(std::vector<float>(Cpad, 0.0f));
+    float* s = tmp.put(std::vector<float>(768, 1.0f));
+    float* t = tmp.put(std::vector<float>(768, 0.0f));
+    std::vector<CUtensorMap> tm(3);
+    if (!tm_nhwc(&tm[0], x, B, H, W, C, 64, kDwHaloW, kDwHaloH, CU_TENSOR_MAP_SWIZZLE_NONE, &terr) || !tm_2d(&tm[1], w, N, C, C, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B, &terr) ||
+        !tm_nhwc(&tm[2], o, B, H, W, N, 32, 16, 2, CU_TENSOR_MAP_SWIZZLE_64B, &terr)) return mfail(nullptr, DLV3P_ERR_CUDA, terr);
+    CUtensorMap* dtm = tmp.put(tm);
+    BbWideParams P{};
+    P.tmap_x = &dtm[0]; P.tmap_w = &dtm[1]; P.tmap_out = &dtm[2]; P.dw_w = dw; P.dw_shift = sh; P.scale = s; P.shift = t;
+    P.res = res ? reinterpret_cast<const __nv_bfloat16*>(rr) : nullptr; P.B = B; P.H = H; P.W = W; P.N = N; P.KB = Cpad / 64;
+    P.tiles_x = cdiv(W, kDwTW); P.tiles_y = cdiv(H, kDwTH); P.num_tiles = B * P.tiles_x * P.tiles_y; P.relu_out = 0; P.debug = flags;
+    rc = run([&] { launch_sepwide(P, true, sms, st); });
   } else {
     rc = mfail(nullptr, DLV3P_ERR_INVALID, "op_bb_time: unknown op / too few dims");
   }

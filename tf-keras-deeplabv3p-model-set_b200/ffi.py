@@ -116,6 +116,7 @@ MODEL_SYMBOLS = [
     ('dlv3p_model_profile_forward', _i, [_vp, _vp, _vp, _vp, C.POINTER(C.c_char_p), _fp, _dp, _dp, _i]),
     ('dlv3p_op_bb_depthwise', _i, [_i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _fp, _fp, _fp, _vp, _vp]),
     ('dlv3p_op_bb_pointwise', _i, [_i, _vp, C.c_int64, _i, _i, _fp, _fp, _fp, _i, _vp, _vp, _vp]),
+    ('dlv3p_op_bb_sepwide', _i, [_i, _vp, _i, _i, _i, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp, _i, _vp, _vp, _vp]),
     ('dlv3p_op_conv3x3_c32', _i, [_i, _vp, _i, _i, _i, _fp, _fp, _fp, _vp, _vp]),
     ('dlv3p_op_stem_conv', _i, [_i, _vp, _i, _i, _i, _i, _fp, _fp, _fp, _vp, _vp]),
     ('dlv3p_op_bb_time', _i, [_i, _i, C.POINTER(C.c_int64), _i, _i, _i, _fp]),
@@ -507,6 +508,19 @@ def op_bb_pointwise(a_bits: np.ndarray, w_kn: np.ndarray, scale=None, shift=None
     do = DeviceBuffer(M * N * 2, device)
     _check(load_library().dlv3p_op_bb_pointwise(device, da.ptr, M, K, N, _f(w_kn), _f(scale), _f(shift), int(relu), None if dr is None else dr.ptr, do.ptr, None))
     return do.download((M, N), np.uint16)
+
+
+def op_bb_sepwide(x_bits: np.ndarray, dw_hwc: np.ndarray, w_kn: np.ndarray, relu_in: bool = True, dw_scale=None, dw_shift=None, scale=None, shift=None,
+                  relu_out: bool = False, residual_bits: Optional[np.ndarray] = None, device=0) -> np.ndarray:
+    """Fused middle-flow SepConv_BN (layers.py:74-111, depth_activation False) [+ residual]: x uint16 bf16 [B,H,W,C] -> uint16 bf16 [B,H,W,N]."""
+    B, H, W, Cc = x_bits.shape
+    N = w_kn.shape[1]
+    dx = DeviceBuffer.from_numpy(x_bits, device)
+    dr = None if residual_bits is None else DeviceBuffer.from_numpy(residual_bits, device)
+    do = DeviceBuffer(B * H * W * N * 2, device)
+    _check(load_library().dlv3p_op_bb_sepwide(device, dx.ptr, B, H, W, Cc, N, int(relu_in), _f(dw_hwc), _f(dw_scale), _f(dw_shift), _f(w_kn), _f(scale), _f(shift),
+                                              int(relu_out), None if dr is None else dr.ptr, do.ptr, None))
+    return do.download((B, H, W, N), np.uint16)
 
 
 def op_conv3x3_c32(x_bits: np.ndarray, w_hwio: np.ndarray, scale=None, shift=None, device=0) -> np.ndarray:
