@@ -364,3 +364,23 @@ def test_example_images_whole_model_identical_miou(gpu, stem):
           % (stem, (lab32 == ref).mean(), (lab16 == ref).mean(), R.mIOU(gt, lab16), R.mIOU(gt, ref)))
     assert (lab16 == ref).mean() >= 0.95
     m32.close(); m16.close()
+
+
+def test_load_weights_from_a_keras_h5_file(gpu, tmp_path):
+    """model.load_weights(weights_path) (model.py:102-103): the whole model loaded from a Keras-layout .h5 (read by h5lite, matched by
+    layer / variable name) computes the same label maps, bit for bit, as the same weights given as a dict."""
+    from tests.h5_writer import write_h5
+    OS, H, W = 16, 64, 96
+    m, Wb, Wh, hcfg = _model_and_oracle(OS, H, W, keep=False)
+    allw = dict(Wb)
+    allw.update(Wh)
+    tree = {}
+    for (layer, var), a in allw.items():
+        tree.setdefault(layer, {layer: {}})[layer][var + ':0'] = np.asarray(a, np.float32)
+    p = str(tmp_path / 'deeplabv3p_xception.h5')
+    write_h5(p, {'model_weights': tree}, {'/model_weights': {'layer_names': np.array([k.encode() for k in tree])}})
+    m2 = dlv3p_b200.get_deeplabv3p_xception(21, (H, W), OS, batch=2, weights_path=p)
+    img = np.random.default_rng(8).integers(0, 256, (2, H, W, 3)).astype(np.uint8)
+    assert np.array_equal(m(img), m2(img))
+    m.close()
+    m2.close()

@@ -81,6 +81,14 @@ class _Block:
         with np.load(path) as z:
             self.set_weights({k: z[k] for k in z.files})
 
+    def load_weights(self, path: str) -> None:
+        """model.load_weights(weights_path, by_name=...) (model.py:102-103): a Keras `.h5` / `.hdf5` weight file (model.save() or
+        model.save_weights(); read by the dependency-free h5lite, matched by layer / variable name) or an `.npz` with 'layer/variable' keys."""
+        if path.endswith('.npz'):
+            return self.load_weights_npz(path)
+        from . import h5lite
+        self.set_weights(h5lite.keras_weights(path))
+
     # -- execution -------------------------------------------------------------------------
     def _dev(self, name: str, nbytes: int) -> ffi.DeviceBuffer:
         b = self._bufs.get(name)
@@ -249,5 +257,5 @@ def get_deeplabv3p_head(model_type: str, num_classes: int, model_input_shape: Tu
     head = DeepLabHead(batch, model_input_shape[0], model_input_shape[1], output_stride, cin, cskip, num_classes,
                        lite=lite, out_mode=out_mode, in_dtype=in_dtype, device=device)
     if weights_path:
-        head.load_weights_npz(weights_path)
+        head.load_weights(weights_path)
     return head

@@ -75,6 +75,14 @@ class DeepLabV3PlusXception:
         with np.load(path) as z:
             self.set_weights({k: z[k] for k in z.files})
 
+    def load_weights(self, path: str) -> None:
+        """model.load_weights(weights_path, by_name=...) (model.py:102-103): a Keras `.h5` / `.hdf5` weight file (model.save() or
+        model.save_weights(); read by the dependency-free h5lite, matched by layer / variable name) or an `.npz` with 'layer/variable' keys."""
+        if path.endswith('.npz'):
+            return self.load_weights_npz(path)
+        from . import h5lite
+        self.set_weights(h5lite.keras_weights(path))
+
     # -- execution -------------------------------------------------------------------------
     def output_shape_dtype(self):
         if self.out_mode == ffi.OUT_LABELS_U8:
@@ -139,5 +147,5 @@ def get_deeplabv3p_xception(num_classes: int, model_input_shape: Tuple[int, int]
     """get_deeplabv3p_model('xception', num_classes, model_input_shape, output_stride, weights_path) (model.py:51)."""
     m = DeepLabV3PlusXception((model_input_shape[0], model_input_shape[1], 3), num_classes, output_stride, batch, **kw)
     if weights_path:
-        m.load_weights_npz(weights_path)
+        m.load_weights(weights_path)
     return m

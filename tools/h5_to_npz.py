@@ -1,8 +1,10 @@
 """Export the DeepLabV3+ head weights of a reference Keras `.h5` file to the `.npz` the B200 head loads
 (`DeepLabHead.load_weights_npz`, `get_deeplabv3p_head(weights_path=...)`, `HeadTrainer(weights=dict(np.load(...)))`).
 
-Run it where `h5py` exists (it ships with the reference's TensorFlow install; it is not in this image):
-    python tools/h5_to_npz.py model.h5 head.npz
+    python tools/h5_to_npz.py model.h5 head.npz            # the head's layers
+    python tools/h5_to_npz.py --all model.h5 model.npz     # every layer (backbone + head: DeepLabV3PlusXception.load_weights)
+h5py is used when it is installed; otherwise the file is read by the dependency-free `dlv3p_b200.h5lite` (contiguous float datasets,
+the layout Keras writes).  `DeepLabHead.load_weights` / `DeepLabV3PlusXception.load_weights` read `.h5` files directly the same way.
 
 Both layouts Keras writes are handled: `model.save()` files keep the weights under `/model_weights`, `model.save_weights()` files at
 the root (model.py:102-103 loads either by topology, deeplabv3p_xception.py:237 by name).  Every dataset is visited and matched BY
@@ -43,7 +45,9 @@ def head_weights_from_h5(root) -> Dict[str, np.ndarray]:
         if len(parts) < 2:
             continue
         var = parts[-1].split(':')[0]
-        layer = parts[-2]
+        # Keras: /<layer>/<scope>/<variable>:0 — the top-level group is the layer name; the inner scope repeats it, with a '_1' suffix
+        # when the model was built twice in one session
+        layer = parts[0] if is_head_layer(parts[0]) else parts[-2]
         if var not in VARIABLES or not is_head_layer(layer):
             continue
         if layer == 'logits_semantic':
@@ -58,21 +62,44 @@ def head_weights_from_h5(root) -> Dict[str, np.ndarray]:
     return out
 
 
+def open_h5(path):
+    """h5py.File when h5py is importable, else the in-repo reader (same keys() / item interface)."""
+    try:
+        import h5py
+        return h5py.File(path, 'r')
+    except ImportError:
+        import os
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from dlv3p_b200 import h5lite
+        return h5lite.File(path)
+
+
 def main(argv) -> int:
+    every = '--all' in argv
+    argv = [a for a in argv if a != '--all']
     if len(argv) != 3:
         print(__doc__)
         return 2
-    try:
-        import h5py
-    except ImportError:
-        print('h5py is not installed here; run this where the reference (TensorFlow + h5py) is installed', file=sys.stderr)
-        return 1
-    with h5py.File(argv[1], 'r') as f:
+    with open_h5(argv[1]) as f:
         root = f['model_weights'] if 'model_weights' in f else f
-        W = head_weights_from_h5(root)
+        if every:
+            from dlv3p_b200 import h5lite
+            W = h5lite.keras_weights(f) if isinstance(f, h5lite.Group) else all_weights_from_h5(root)
+        else:
+            W = head_weights_from_h5(root)
     np.savez(argv[2], **W)
     print('wrote %d tensors to %s' % (len(W), argv[2]))
     return 0
+
+
+def all_weights_from_h5(root) -> Dict[str, np.ndarray]:
+    out: Dict[str, np.ndarray] = {}
+    for path, ds in walk_datasets(root):
+        parts = path.split('/')
+        var = parts[-1].split(':')[0]
+        if len(parts) >= 2 and var in VARIABLES:
+            out['%s/%s' % (parts[0], var)] = np.asarray(ds[()], np.float32)
+    return out
 
 
 if __name__ == '__main__':
