@@ -47,53 +47,79 @@ struct AsppGatherParams {
 // one (phase image, TS-column segment) on a half-warp.  img = this lane's view of the zero-bordered phase image
 // [na + 2][nseg * TS + 2][32 ch] bf16 in shared memory: no bounds checks, every load is base + immediate offset, and
 // everything past the map edge reads as zero (so the pooling sum needs no mask and only the store is predicated).
-template <int RC, int TS>   // RC > 0: the rate as a compile-time constant (divisions and store offsets fold), 0: runtime rate
-__device__ __forceinline__ void aspp_gather_item(const AsppGatherParams& P, const uint8_t* img, int ri, int pi, int pj, int seg,
-                                                 uint8_t* out_lane, const unsigned long long (&wt)[9], unsigned long long sh,
-                                                 unsigned long long& psum) {
-  const int r = RC ? RC : P.rates[ri];
-  const int NA = P.na[ri];
-  const int pitch = (P.nseg[ri] * TS + 2) * 64;          // bytes per padded row
-  const int t0 = seg * TS;
-  const int j0 = pj + r * t0;
-  int nvalid = j0 < P.w_ ? (P.w_ - j0 + r - 1) / r : 0;  // outputs of this segment that exist (uniform per half-warp)
-  if (P.debug & 1) nvalid = 0;
-  const uint8_t* base = img + t0 * 64;                   // padded row 0 (= row -1), padded column t0 (= column t0 - 1)
-  auto load_row = [&](int q, unsigned long long (&row)[TS + 2]) {   // q = -1 .. NA
-    const uint8_t* p = base + (q + 1) * pitch;
+// The loop is written for the instruction count (the kernel is issue bound: 43 instructions per output before this form, 9 of them
+// FFMA2): only the rows that exist are visited, the output pointer advances by one constant per row and every store of a row is
+// pointer + immediate; the column predicate is hoisted (kFull: all TS outputs of the segment exist).
+template <int RC, int TS, bool kPool, bool kFull>
+__device__ __forceinline__ void aspp_gather_rows(const uint8_t* base, int pitch, uint8_t* orow, size_t ostep, int rows, int nvalid, int r,
+                                                 const unsigned long long (&wt)[9], unsigned long long sh, unsigned long long& psum) {
+  auto load_row = [&](const uint8_t* p, unsigned long long (&row)[TS + 2]) {
 #pragma unroll
     for (int t = 0; t < TS + 2; ++t) row[t] = f32x2_from_bf16x2(*reinterpret_cast<const uint32_t*>(p + t * 64));
   };
-  auto emit = [&](int a, const unsigned long long (&top)[TS + 2], const unsigned long long (&mid)[TS + 2],
-                  const unsigned long long (&bot)[TS + 2]) {
-    const int i = pi + r * a;
-    const int nv = i < P.h ? nvalid : 0;                 // rows past the map: zero inputs, nothing stored
-    uint8_t* orow = out_lane + (static_cast<size_t>(i) * P.w_ + j0) * 128;
+  auto emit = [&](const unsigned long long (&top)[TS + 2], const unsigned long long (&mid)[TS + 2], const unsigned long long (&bot)[TS + 2]) {
 #pragma unroll
     for (int t = 0; t < TS; ++t) {
       unsigned long long acc = sh;
       ffma2_acc(acc, wt[0], top[t]); ffma2_acc(acc, wt[1], top[t + 1]); ffma2_acc(acc, wt[2], top[t + 2]);
       ffma2_acc(acc, wt[3], mid[t]); ffma2_acc(acc, wt[4], mid[t + 1]); ffma2_acc(acc, wt[5], mid[t + 2]);
       ffma2_acc(acc, wt[6], bot[t]); ffma2_acc(acc, wt[7], bot[t + 1]); ffma2_acc(acc, wt[8], bot[t + 2]);
-      psum = fadd2(psum, mid[t + 1]);
-      if (t < nv) *reinterpret_cast<uint32_t*>(orow + t * r * 128) = f32x2_to_bf16x2_relu(acc);
+      if (kPool) psum = fadd2(psum, mid[t + 1]);
+      const uint32_t v = f32x2_to_bf16x2_relu(acc);
+      if (RC) {
+        if (kFull || t < nvalid) *reinterpret_cast<uint32_t*>(orow + t * (RC * 128)) = v;
+      } else {
+        if (kFull || t < nvalid) *reinterpret_cast<uint32_t*>(orow + static_cast<size_t>(t) * r * 128) = v;
+      }
     }
+    orow += ostep;
   };
   unsigned long long ra[TS + 2], rb[TS + 2], rc[TS + 2];
-  load_row(-1, ra);
-  load_row(0, rb);
-  for (int a = 0; a < NA; a += 3) {
-    load_row(a + 1, rc);
-    emit(a, ra, rb, rc);
-    if (a + 1 < NA) {
-      load_row(a + 2, ra);
-      emit(a + 1, rb, rc, ra);
-    }
-    if (a + 2 < NA) {
-      load_row(a + 3, rb);
-      emit(a + 2, rc, ra, rb);
+  load_row(base, ra);                 // padded row 0 = map row -1 of the phase image
+  load_row(base + pitch, rb);
+  const uint8_t* p = base + 2 * pitch;
+  int a = 0;
+  for (; a + 3 <= rows; a += 3) {
+    load_row(p, rc);
+    emit(ra, rb, rc);
+    load_row(p + pitch, ra);
+    emit(rb, rc, ra);
+    load_row(p + 2 * pitch, rb);
+    emit(rc, ra, rb);
+    p += 3 * pitch;
+  }
+  if (a < rows) {
+    load_row(p, rc);
+    emit(ra, rb, rc);
+    if (a + 1 < rows) {
+      load_row(p + pitch, ra);
+      emit(rb, rc, ra);
     }
   }
+}
+
+template <int RC, int TS, bool kPool>
+__device__ __forceinline__ void aspp_gather_item(const AsppGatherParams& P, const uint8_t* img, int ri, int pi, int pj, int seg,
+                                                 uint8_t* out_lane, const unsigned long long (&wt)[9], unsigned long long sh,
+                                                 unsigned long long& psum) {
+  const int r = RC ? RC : P.rates[ri];
+  const int pitch = (P.nseg[ri] * TS + 2) * 64;          // bytes per padded row
+  const int t0 = seg * TS;
+  const int j0 = pj + r * t0;
+  int nvalid = j0 < P.w_ ? (P.w_ - j0 + r - 1) / r : 0;  // outputs of this segment that exist (uniform per half-warp)
+  if (nvalid > TS) nvalid = TS;
+  if (P.debug & 1) nvalid = 0;
+  // rows of this phase image that exist: i = pi + r a < h.  Rows past the map are zero inputs: nothing to store, nothing to pool
+  // (a padding segment entirely past the map edge has only zero inputs: skipped)
+  const int rows = pi < P.h ? (P.h - pi + r - 1) / r : 0;
+  const uint8_t* base = img + t0 * 64;                   // padded row 0 (= row -1), padded column t0 (= column t0 - 1)
+  uint8_t* orow = out_lane + (static_cast<size_t>(pi) * P.w_ + j0) * 128;
+  const size_t ostep = static_cast<size_t>(r) * P.w_ * 128;
+  // the two half-warps of a warp work on different items: pick the code path per WARP (a full and a partial segment side by side
+  // would otherwise run both instantiations one after the other)
+  const bool full = __all_sync(__activemask(), nvalid == TS);
+  if (full) aspp_gather_rows<RC, TS, kPool, true>(base, pitch, orow, ostep, rows, nvalid, r, wt, sh, psum);
+  else aspp_gather_rows<RC, TS, kPool, false>(base, pitch, orow, ostep, nvalid > 0 ? rows : 0, nvalid, r, wt, sh, psum);
 }
 
 template <int RC>
@@ -150,7 +176,8 @@ __device__ __forceinline__ void aspp_gather_body(const AsppGatherParams& P, uint
     const int ph = it / nseg, seg = it - ph * nseg;
     const int phase = ph0 + ph;
     const int pi = phase / r, pj = phase - pi * r;
-    aspp_gather_item<RC, 4>(P, s_img + ph * img_bytes + l16 * 4, ri, pi, pj, seg, out_lane, wt, sh, psum);
+    if (ri == 0) aspp_gather_item<RC, 4, true>(P, s_img + ph * img_bytes + l16 * 4, ri, pi, pj, seg, out_lane, wt, sh, psum);
+    else aspp_gather_item<RC, 4, false>(P, s_img + ph * img_bytes + l16 * 4, ri, pi, pj, seg, out_lane, wt, sh, psum);
   }
   // ---- image-pooling partial sums: the rate-0 batches cover every pixel exactly once
   if (ri == 0) {

@@ -1228,7 +1228,7 @@ static int forward_impl(dlv3p_ctx* c, const void* d_feat, const void* d_skip, vo
       } else if (c->aspp_gather) {
         AsppGatherParams G = c->gather_plan;
         G.x = feat; G.w = c->aspp_dw_w; G.shift = c->aspp_dw_shift; G.out = c->dw_out; G.pool_partial = c->pool_partial;
-        G.batches = c->gather_table_dev; G.B = g.B;
+        G.batches = c->gather_table_dev; G.B = g.B; G.debug = (g.flags >> 8) & 7;   // measurement aid (tools/kbench_gather.py)
         if (c->gather_maps_ptr != feat) {   // per-phase tensor maps follow the feature buffer (one-time for a fixed buffer)
           std::vector<CUtensorMap> maps;
           if (!encode_gather_maps(G, feat, g.B, &maps, &terr)) return fail(c, DLV3P_ERR_CUDA, terr);
