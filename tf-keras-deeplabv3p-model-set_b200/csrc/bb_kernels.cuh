@@ -25,74 +25,101 @@ struct StemParams {
   int B, H, W, Ho, Wo, pad_t, pad_l;
 };
 
-// thread = one output pixel x 32 output channels; weights in shared memory (warp-uniform broadcast reads).  fp32 arithmetic
-// on the exact normalised pixel values: the only rounding is the bf16 store.
+// CTA = one segment of kStemSeg output pixels of one output row; thread = two of them (t and t + 128) x all 32 output channels.
+// The three input rows of the segment are staged in shared memory as fp32 NORMALISED values (uint8 through a 256-entry table of the
+// correctly rounded x / 127.5 - 1, so the arithmetic is the reference's), split by column parity and channel so that a warp's reads
+// of a stride-2 convolution are consecutive words; zero padding of the normalised image = zeros in the staged rows.  Weights in
+// shared memory (warp-uniform 16-byte broadcast reads), every weight read feeds four packed-fp32 FMAs.  fp32 arithmetic in the tap
+// order (ky, kx, cin): the only rounding is the bf16 store.
+constexpr int kStemSeg = 256;
+constexpr int kStemIdx = kStemSeg + 8;      // even-parity entries 0..256 + pad
+
 __global__ void __launch_bounds__(128) stem_conv_kernel(const StemParams P) {
   __shared__ __align__(16) float s_w[27 * 32];
-  __shared__ float s_scale[32], s_shift[32];
+  __shared__ __align__(8) float s_scale[32], s_shift[32];
+  __shared__ float s_lut[256];
+  __shared__ float s_in[3][3][2][kStemIdx];     // [ky][cin][column parity][column / 2], columns relative to the segment's first tap
+  const int t = threadIdx.x;
   pdl_launch_dependents();
-  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) s_w[i] = P.w[i];
-  if (threadIdx.x < 32) {
-    s_scale[threadIdx.x] = P.scale[threadIdx.x];
-    s_shift[threadIdx.x] = P.shift[threadIdx.x];
+  for (int i = t; i < 27 * 32; i += 128) s_w[i] = P.w[i];
+  if (t < 32) {
+    s_scale[t] = P.scale[t];
+    s_shift[t] = P.shift[t];
+  }
+  s_lut[t] = __fsub_rn(__fdiv_rn(static_cast<float>(t), 127.5f), 1.0f);
+  s_lut[t + 128] = __fsub_rn(__fdiv_rn(static_cast<float>(t + 128), 127.5f), 1.0f);
+  const int segs = (P.Wo + kStemSeg - 1) / kStemSeg;
+  const int seg = static_cast<int>(blockIdx.x) % segs;
+  const int row = static_cast<int>(blockIdx.x) / segs;
+  const int oy = row % P.Ho, b = row / P.Ho;
+  const int x0 = seg * kStemSeg;
+  __syncthreads();
+  pdl_wait();          // the images may come from the previous kernel of the stream; the output buffer may still be read by it
+  // ---- stage: entry e of row ky is input column 2 * x0 + e - pad_l
+  const int ncols = 2 * min(kStemSeg, P.Wo - x0) + 1;
+  for (int i = t; i < 3 * ncols; i += 128) {
+    const int ky = i / ncols, e = i - ky * ncols;
+    const int iy = oy * 2 - P.pad_t + ky, ix = 2 * x0 + e - P.pad_l;
+    float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f;
+    if (iy >= 0 && iy < P.H && ix >= 0 && ix < P.W) {
+      const size_t off = ((static_cast<size_t>(b) * P.H + iy) * P.W + ix) * 3;
+      if (P.img_f32) {
+        const float* p = static_cast<const float*>(P.img) + off;
+        v0 = __ldg(p); v1 = __ldg(p + 1); v2 = __ldg(p + 2);
+      } else {
+        const uint8_t* p = static_cast<const uint8_t*>(P.img) + off;
+        v0 = s_lut[__ldg(p)]; v1 = s_lut[__ldg(p + 1)]; v2 = s_lut[__ldg(p + 2)];
+      }
+    }
+    s_in[ky][0][e & 1][e >> 1] = v0;
+    s_in[ky][1][e & 1][e >> 1] = v1;
+    s_in[ky][2][e & 1][e >> 1] = v2;
   }
   __syncthreads();
-  pdl_wait();          // the output buffer may still be read by the previous step's kernels
-  const long long total = static_cast<long long>(P.B) * P.Ho * P.Wo;
-  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (idx >= total) return;
-  const int ox = static_cast<int>(idx % P.Wo);
-  const int oy = static_cast<int>((idx / P.Wo) % P.Ho);
-  const int b = static_cast<int>(idx / (static_cast<long long>(P.Wo) * P.Ho));
-  float acc[32];
+  unsigned long long acc[2][16];
 #pragma unroll
-  for (int n = 0; n < 32; ++n) acc[n] = 0.0f;
+  for (int n = 0; n < 16; ++n) acc[0][n] = acc[1][n] = 0ull;
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
-    const int iy = oy * 2 - P.pad_t + ky;
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
-      const int ix = ox * 2 - P.pad_l + kx;
-      float v[3] = {0.0f, 0.0f, 0.0f};      // zero padding of the NORMALISED image
-      if (iy >= 0 && iy < P.H && ix >= 0 && ix < P.W) {
-        const size_t off = ((static_cast<size_t>(b) * P.H + iy) * P.W + ix) * 3;
-        if (P.img_f32) {
-          const float* p = static_cast<const float*>(P.img) + off;
-          v[0] = __ldg(p); v[1] = __ldg(p + 1); v[2] = __ldg(p + 2);
-        } else {
-          const uint8_t* p = static_cast<const uint8_t*>(P.img) + off;
-          v[0] = __fsub_rn(__fdiv_rn(static_cast<float>(__ldg(p)), 127.5f), 1.0f);
-          v[1] = __fsub_rn(__fdiv_rn(static_cast<float>(__ldg(p + 1)), 127.5f), 1.0f);
-          v[2] = __fsub_rn(__fdiv_rn(static_cast<float>(__ldg(p + 2)), 127.5f), 1.0f);
-        }
-      }
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const float4* wr = reinterpret_cast<const float4*>(s_w + ((ky * 3 + kx) * 3 + c) * 32);
+        const float* in = &s_in[ky][c][kx & 1][t + (kx >> 1)];
+        const float a0 = in[0], a1 = in[128];      // entries past the segment's columns are never stored (pixels >= Wo)
+        const unsigned long long v0 = pack_f32x2(a0, a0), v1 = pack_f32x2(a1, a1);
+        const ulonglong2* wr = reinterpret_cast<const ulonglong2*>(s_w + ((ky * 3 + kx) * 3 + c) * 32);
 #pragma unroll
         for (int n4 = 0; n4 < 8; ++n4) {
-          const float4 w4 = wr[n4];
-          acc[n4 * 4 + 0] = fmaf(v[c], w4.x, acc[n4 * 4 + 0]);
-          acc[n4 * 4 + 1] = fmaf(v[c], w4.y, acc[n4 * 4 + 1]);
-          acc[n4 * 4 + 2] = fmaf(v[c], w4.z, acc[n4 * 4 + 2]);
-          acc[n4 * 4 + 3] = fmaf(v[c], w4.w, acc[n4 * 4 + 3]);
+          const ulonglong2 w4 = wr[n4];
+          ffma2(acc[0][n4 * 2], v0, w4.x);
+          ffma2(acc[0][n4 * 2 + 1], v0, w4.y);
+          ffma2(acc[1][n4 * 2], v1, w4.x);
+          ffma2(acc[1][n4 * 2 + 1], v1, w4.y);
         }
       }
     }
   }
-  __nv_bfloat16* o = P.out + static_cast<size_t>(idx) * 32;
 #pragma unroll
-  for (int j = 0; j < 32; j += 8) {
-    uint32_t pk[4];
+  for (int h = 0; h < 2; ++h) {
+    const int ox = x0 + t + h * 128;
+    if (ox >= P.Wo) continue;
+    __nv_bfloat16* o = P.out + ((static_cast<size_t>(b) * P.Ho + oy) * P.Wo + ox) * 32;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float a = fmaxf(fmaf(acc[j + 2 * q], s_scale[j + 2 * q], s_shift[j + 2 * q]), 0.0f);
-      const float c = fmaxf(fmaf(acc[j + 2 * q + 1], s_scale[j + 2 * q + 1], s_shift[j + 2 * q + 1]), 0.0f);
-      pk[q] = pack_bf16x2(a, c);
+    for (int j = 0; j < 16; j += 4) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int n = 2 * (j + q);
+        const float x = fmaxf(fmaf(f32x2_lo(acc[h][j + q]), s_scale[n], s_shift[n]), 0.0f);
+        const float y = fmaxf(fmaf(f32x2_hi(acc[h][j + q]), s_scale[n + 1], s_shift[n + 1]), 0.0f);
+        pk[q] = pack_bf16x2(x, y);
+      }
+      stg_v4(o + j * 2, make_uint4(pk[0], pk[1], pk[2], pk[3]));
     }
-    stg_v4(o + j, make_uint4(pk[0], pk[1], pk[2], pk[3]));
   }
 }
+inline unsigned stem_grid(int B, int Ho, int Wo) { return static_cast<unsigned>(B) * Ho * ((Wo + kStemSeg - 1) / kStemSeg); }
 
 // ---------------------------------------------------------------------------------------------------------------- depthwise
 struct BbDwParams {
