@@ -25,101 +25,271 @@ struct StemParams {
   int B, H, W, Ho, Wo, pad_t, pad_l;
 };
 
-// CTA = one segment of kStemSeg output pixels of one output row; thread = two of them (t and t + 128) x all 32 output channels.
-// The three input rows of the segment are staged in shared memory as fp32 NORMALISED values (uint8 through a 256-entry table of the
+// Persistent CTAs over work items = a segment of kStemSeg output pixels on two consecutive output rows.  Warp = one of the rows x one
+// half of the output channels; lane = eight pixels of the segment (lane + 32 j) x 16 channels: every weight word read from shared
+// memory (warp-uniform 16-byte broadcast) feeds eight FMAs of the thread and every input word sixteen — broadcast reads deliver one
+// word per shared-memory wavefront, so at 2 pixels x 32 channels per thread the kernel was bound by wavefronts, not by the FP32 pipe.
+// The five input rows of an item are staged in shared memory as fp32 NORMALISED values (uint8 through a 256-entry table of the
 // correctly rounded x / 127.5 - 1, so the arithmetic is the reference's), split by column parity and channel so that a warp's reads
-// of a stride-2 convolution are consecutive words; zero padding of the normalised image = zeros in the staged rows.  Weights in
-// shared memory (warp-uniform 16-byte broadcast reads), every weight read feeds four packed-fp32 FMAs.  fp32 arithmetic in the tap
-// order (ky, kx, cin): the only rounding is the bf16 store.
+// of the stride-2 convolution are consecutive words; zero padding of the normalised image = zeros in the staged rows.  The raw
+// pixels of the NEXT item are on their way into shared memory (cp.async) while the current one is computed (uint8 images), so the
+// trip to HBM hides behind the arithmetic.  fp32 FMAs in the tap order (ky, kx, cin): the only rounding is the bf16 store.
 constexpr int kStemSeg = 256;
-constexpr int kStemIdx = kStemSeg + 8;      // even-parity entries 0..256 + pad
+constexpr int kStemIdx = kStemSeg + 8;                     // even-parity entries 0..256 + pad
+constexpr int kStemPer = (2 * kStemSeg + 1 + 127) / 128;   // staged entries per thread and input row
 
-__global__ void __launch_bounds__(128) stem_conv_kernel(const StemParams P) {
+struct StemItem { int b, oy0, x0; };
+__device__ __forceinline__ StemItem stem_item(const StemParams& P, int item) {
+  const int segs = (P.Wo + kStemSeg - 1) / kStemSeg, row_pairs = (P.Ho + 1) / 2;
+  const int seg = item % segs, rp = item / segs;
+  return StemItem{rp / row_pairs, (rp % row_pairs) * 2, seg * kStemSeg};
+}
+// The raw bytes of an item's five input rows travel global -> shared memory as asynchronous 4-byte copies (cp.async: no registers,
+// nothing waits until the bytes are converted): row r of the item is the byte stream that starts at pixel (2 oy0 - pad_t + r,
+// 2 x0 - pad_l), copied from the 4-byte boundary below it (shift s_sh[r]) in whole words.  Bytes outside the image (padding columns,
+// rows above / below, the neighbouring row's pixels inside the first / last word) are masked by geometry when the row is converted;
+// a word that straddles the ends of the image buffer is copied byte by byte.
+constexpr int kStemRawWords = (3 * (2 * kStemSeg + 1) + 3 + 3) / 4 + 3;      // + the words thread 127 reads past the stream
+__device__ __forceinline__ void stem_prefetch_u8(const StemParams& P, const StemItem& it, int t, uint32_t (*s_raw)[kStemRawWords], int* s_sh) {
+  const int ncols = 2 * min(kStemSeg, P.Wo - it.x0) + 1;
+  const long long total = static_cast<long long>(P.B) * P.H * P.W * 3;
+  const uint8_t* img = static_cast<const uint8_t*>(P.img);
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+    const int iy = it.oy0 * 2 - P.pad_t + r;
+    if (iy < 0 || iy >= P.H) continue;
+    const long long gs = ((static_cast<long long>(it.b) * P.H + iy) * P.W + (2 * it.x0 - P.pad_l)) * 3;     // stream start (may be -3)
+    const int sh = static_cast<int>((reinterpret_cast<uintptr_t>(img) + gs) & 3);
+    if (t == 0) s_sh[r] = sh;
+    const int words = (sh + 3 * ncols + 3) >> 2;
+    const long long first = gs - sh;                                   // byte offset of word 0 in the image buffer
+    const uint32_t dst0 = smem_u32(&s_raw[r][0]);
+    if (first >= 0 && first + 4ll * words <= total) {                  // all but the first / last row of the buffer
+      const uint8_t* src = img + first;
+      for (int w = t; w < words; w += 128)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst0 + 4 * w), "l"(src + 4 * w) : "memory");
+    } else {
+      for (int w = t; w < words; w += 128) {
+        const long long off = first + 4ll * w;
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (off + k >= 0 && off + k < total) v |= static_cast<uint32_t>(__ldg(img + off + k)) << (8 * k);
+        s_raw[r][w] = v;
+      }
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// Warp-specialised: warps 0-3 do nothing but the FMAs and the bf16 stores of an item (one FP32-pipe-bound warp per SM sub-partition),
+// warps 4-7 stage the NEXT item into the other half of a double-buffered s_in (copy -> table lookup -> parity-split store), handing
+// buffers over through two pairs of mbarriers.  With both jobs in the same warps (any number of CTAs per SM) the FMA pipe idled
+// through 70 % of the kernel: the register budget of the 8 x 16 accumulator block leaves two warps per sub-partition, too few to
+// cover the staging's dependent shared-memory chains.
+template <bool kU8>
+__global__ void __launch_bounds__(256, 1) stem_conv_kernel(const StemParams P) {
   __shared__ __align__(16) float s_w[27 * 32];
   __shared__ __align__(8) float s_scale[32], s_shift[32];
   __shared__ float s_lut[256];
-  __shared__ float s_in[3][3][2][kStemIdx];     // [ky][cin][column parity][column / 2], columns relative to the segment's first tap
-  const int t = threadIdx.x;
+  extern __shared__ __align__(16) float s_in_dyn[];
+  float (*s_in)[5][3][2][kStemIdx] = reinterpret_cast<float (*)[5][3][2][kStemIdx]>(s_in_dyn);   // [buffer][input row][cin][column parity][column / 2],
+                                                                                                 // columns relative to the item's first tap
+  __shared__ __align__(16) uint32_t s_raw[kU8 ? 2 : 1][kU8 ? 5 : 1][kStemRawWords];     // copies of item k and k + 1 in flight
+  __shared__ int s_sh[2][5];
+  __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+  const int t = threadIdx.x & 127, warp = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31;
+  const bool helper = threadIdx.x >= 128;
   pdl_launch_dependents();
-  for (int i = t; i < 27 * 32; i += 128) s_w[i] = P.w[i];
-  if (t < 32) {
-    s_scale[t] = P.scale[t];
-    s_shift[t] = P.shift[t];
+  for (int i = threadIdx.x; i < 27 * 32; i += 256) s_w[i] = P.w[i];
+  if (threadIdx.x < 32) {
+    s_scale[threadIdx.x] = P.scale[threadIdx.x];
+    s_shift[threadIdx.x] = P.shift[threadIdx.x];
   }
-  s_lut[t] = __fsub_rn(__fdiv_rn(static_cast<float>(t), 127.5f), 1.0f);
-  s_lut[t + 128] = __fsub_rn(__fdiv_rn(static_cast<float>(t + 128), 127.5f), 1.0f);
-  const int segs = (P.Wo + kStemSeg - 1) / kStemSeg;
-  const int seg = static_cast<int>(blockIdx.x) % segs;
-  const int row = static_cast<int>(blockIdx.x) / segs;
-  const int oy = row % P.Ho, b = row / P.Ho;
-  const int x0 = seg * kStemSeg;
+  s_lut[threadIdx.x] = __fsub_rn(__fdiv_rn(static_cast<float>(threadIdx.x), 127.5f), 1.0f);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 128);
+      mbar_init(&s_empty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  const int num_items = P.B * ((P.Ho + 1) / 2) * ((P.Wo + kStemSeg - 1) / kStemSeg);
+  const int step = static_cast<int>(gridDim.x);
   __syncthreads();
   pdl_wait();          // the images may come from the previous kernel of the stream; the output buffer may still be read by it
-  // ---- stage: entry e of row ky is input column 2 * x0 + e - pad_l
-  const int ncols = 2 * min(kStemSeg, P.Wo - x0) + 1;
-  for (int i = t; i < 3 * ncols; i += 128) {
-    const int ky = i / ncols, e = i - ky * ncols;
-    const int iy = oy * 2 - P.pad_t + ky, ix = 2 * x0 + e - P.pad_l;
-    float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f;
-    if (iy >= 0 && iy < P.H && ix >= 0 && ix < P.W) {
-      const size_t off = ((static_cast<size_t>(b) * P.H + iy) * P.W + ix) * 3;
-      if (P.img_f32) {
-        const float* p = static_cast<const float*>(P.img) + off;
-        v0 = __ldg(p); v1 = __ldg(p + 1); v2 = __ldg(p + 2);
-      } else {
-        const uint8_t* p = static_cast<const uint8_t*>(P.img) + off;
-        v0 = s_lut[__ldg(p)]; v1 = s_lut[__ldg(p + 1)]; v2 = s_lut[__ldg(p + 2)];
+  if (helper) {
+    // -------------------------------------------------------------------------------------------- staging warps
+    int item = static_cast<int>(blockIdx.x);
+    if (kU8) {
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        if (item + a * step < num_items) stem_prefetch_u8(P, stem_item(P, item + a * step), t, s_raw[a], s_sh[a]);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
       }
     }
-    s_in[ky][0][e & 1][e >> 1] = v0;
-    s_in[ky][1][e & 1][e >> 1] = v1;
-    s_in[ky][2][e & 1][e >> 1] = v2;
+    for (uint32_t k = 0; item < num_items; item += step, ++k) {
+      const StemItem it = stem_item(P, item);
+      const int ncols = 2 * min(kStemSeg, P.Wo - it.x0) + 1;
+      float (*in)[3][2][kStemIdx] = s_in[k & 1];
+      mbar_wait(&s_empty[k & 1], ((k >> 1) & 1) ^ 1);      // the FMA warps are done with this buffer (first two uses: free)
+      if (kU8) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");     // this item's copies (the next item's may still be in flight)
+        asm volatile("bar.sync 1, 128;" ::: "memory");      // ... of every staging thread have landed
+        uint32_t (*raw)[kStemRawWords] = s_raw[k & 1];
+        const int* shp = s_sh[k & 1];
+        // thread t converts entries 4t .. 4t+3 of every row (12 bytes = three words of the stream, funnel-shifted from four words of
+        // the copy: lanes read words 3 apart -> no bank conflicts), thread 0 also the last entry; twelve independent chains per row
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+          const int iy = it.oy0 * 2 - P.pad_t + r;
+          const bool row_ok = iy >= 0 && iy < P.H;
+          const int sh8 = row_ok ? shp[r] * 8 : 0;
+          const uint32_t* rw = &raw[r][3 * t];
+          const uint32_t q0 = rw[0], q1 = rw[1], q2 = rw[2], q3 = rw[3];
+          const uint32_t wv[3] = {__funnelshift_r(q0, q1, sh8), __funnelshift_r(q1, q2, sh8), __funnelshift_r(q2, q3, sh8)};
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const int e = 4 * t + kk, ix = 2 * it.x0 + e - P.pad_l;
+            const bool ok = row_ok && e < ncols && ix >= 0 && ix < P.W;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const int byte = 3 * kk + c;
+              const uint32_t u = (wv[byte >> 2] >> (8 * (byte & 3))) & 255u;
+              in[r][c][kk & 1][2 * t + (kk >> 1)] = ok ? s_lut[u] : 0.0f;
+            }
+          }
+          if (t == 0) {
+            const int e = 4 * 128, ix = 2 * it.x0 + e - P.pad_l;
+            const bool ok = row_ok && e < ncols && ix >= 0 && ix < P.W;
+            const uint8_t* rb = reinterpret_cast<const uint8_t*>(&raw[r][0]) + (sh8 >> 3) + 3 * e;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) in[r][c][0][e >> 1] = ok ? s_lut[rb[c]] : 0.0f;
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");      // this copy buffer is free: the bytes of the item after the next may land
+        if (item + 2 * step < num_items) stem_prefetch_u8(P, stem_item(P, item + 2 * step), t, raw, s_sh[k & 1]);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+      } else {
+#pragma unroll 1
+        for (int r = 0; r < 5; ++r) {
+          const int iy = it.oy0 * 2 - P.pad_t + r;
+          const bool row_ok = iy >= 0 && iy < P.H;
+          const float* rowp = static_cast<const float*>(P.img) + (static_cast<size_t>(it.b) * P.H + (row_ok ? iy : 0)) * P.W * 3;
+          float v[kStemPer][3];
+#pragma unroll
+          for (int i = 0; i < kStemPer; ++i) {
+            const int e = t + i * 128, ix = 2 * it.x0 + e - P.pad_l;
+            const bool ok = row_ok && e < ncols && ix >= 0 && ix < P.W;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[i][c] = ok ? __ldg(rowp + ix * 3 + c) : 0.0f;
+          }
+#pragma unroll
+          for (int i = 0; i < kStemPer; ++i) {
+            const int e = t + i * 128;
+            if (e < ncols) {
+#pragma unroll
+              for (int c = 0; c < 3; ++c) in[r][c][e & 1][e >> 1] = v[i][c];
+            }
+          }
+        }
+      }
+      mbar_arrive(&s_full[k & 1]);
+    }
+    return;
   }
-  __syncthreads();
-  unsigned long long acc[2][16];
+  // ---------------------------------------------------------------------------------------------- FMA warps
+  const int half = warp & 1, orow = warp >> 1;      // this warp: channels [16 half, 16 half + 16) of output row oy0 + orow
+  float sc[16], sf[16];
 #pragma unroll
-  for (int n = 0; n < 16; ++n) acc[0][n] = acc[1][n] = 0ull;
+  for (int n = 0; n < 16; ++n) {
+    sc[n] = s_scale[half * 16 + n];
+    sf[n] = s_shift[half * 16 + n];
+  }
+  uint32_t k = 0;
+  for (int item = static_cast<int>(blockIdx.x); item < num_items; item += step, ++k) {
+    const StemItem it = stem_item(P, item);
+    const int oy = it.oy0 + orow;
+    mbar_wait(&s_full[k & 1], (k >> 1) & 1);
+    float acc[8][16];
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky) {
+    for (int j = 0; j < 8; ++j)
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
+      for (int n = 0; n < 16; ++n) acc[j][n] = 0.0f;
+    if (oy < P.Ho) {
+#pragma unroll 1
+      for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float* in = &s_in[ky][c][kx & 1][t + (kx >> 1)];
-        const float a0 = in[0], a1 = in[128];      // entries past the segment's columns are never stored (pixels >= Wo)
-        const unsigned long long v0 = pack_f32x2(a0, a0), v1 = pack_f32x2(a1, a1);
-        const ulonglong2* wr = reinterpret_cast<const ulonglong2*>(s_w + ((ky * 3 + kx) * 3 + c) * 32);
+        for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
-        for (int n4 = 0; n4 < 8; ++n4) {
-          const ulonglong2 w4 = wr[n4];
-          ffma2(acc[0][n4 * 2], v0, w4.x);
-          ffma2(acc[0][n4 * 2 + 1], v0, w4.y);
-          ffma2(acc[1][n4 * 2], v1, w4.x);
-          ffma2(acc[1][n4 * 2 + 1], v1, w4.y);
+          for (int c = 0; c < 3; ++c) {
+            const float* in = &s_in[k & 1][orow * 2 + ky][c][kx & 1][lane + (kx >> 1)];
+            const float4* wr = reinterpret_cast<const float4*>(s_w + ((ky * 3 + kx) * 3 + c) * 32 + half * 16);
+            float w[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 w4 = wr[q];
+              w[4 * q] = w4.x; w[4 * q + 1] = w4.y; w[4 * q + 2] = w4.z; w[4 * q + 3] = w4.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float a = in[32 * j];      // entries past the item's columns belong to pixels >= Wo, which are never stored
+#pragma unroll
+              for (int n = 0; n < 16; ++n) acc[j][n] = fmaf(a, w[n], acc[j][n]);
+            }
+          }
+        }
+      }
+    }
+    mbar_arrive(&s_empty[k & 1]);      // the buffer may be refilled while the results are stored
+    if (oy < P.Ho) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int ox = it.x0 + lane + 32 * j;
+        if (ox >= P.Wo) continue;
+        __nv_bfloat16* o = P.out + ((static_cast<size_t>(it.b) * P.Ho + oy) * P.Wo + ox) * 32 + half * 16;
+#pragma unroll
+        for (int q4 = 0; q4 < 8; q4 += 4) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int n = 2 * (q4 + q);
+            const float x = fmaxf(fmaf(acc[j][n], sc[n], sf[n]), 0.0f);
+            const float y = fmaxf(fmaf(acc[j][n + 1], sc[n + 1], sf[n + 1]), 0.0f);
+            pk[q] = pack_bf16x2(x, y);
+          }
+          stg_v4(o + q4 * 2, make_uint4(pk[0], pk[1], pk[2], pk[3]));
         }
       }
     }
   }
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int ox = x0 + t + h * 128;
-    if (ox >= P.Wo) continue;
-    __nv_bfloat16* o = P.out + ((static_cast<size_t>(b) * P.Ho + oy) * P.Wo + ox) * 32;
-#pragma unroll
-    for (int j = 0; j < 16; j += 4) {
-      uint32_t pk[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int n = 2 * (j + q);
-        const float x = fmaxf(fmaf(f32x2_lo(acc[h][j + q]), s_scale[n], s_shift[n]), 0.0f);
-        const float y = fmaxf(fmaf(f32x2_hi(acc[h][j + q]), s_scale[n + 1], s_shift[n + 1]), 0.0f);
-        pk[q] = pack_bf16x2(x, y);
-      }
-      stg_v4(o + j * 2, make_uint4(pk[0], pk[1], pk[2], pk[3]));
-    }
-  }
 }
-inline unsigned stem_grid(int B, int Ho, int Wo) { return static_cast<unsigned>(B) * Ho * ((Wo + kStemSeg - 1) / kStemSeg); }
+// persistent: one CTA per SM (register bound), never more CTAs than items
+constexpr int kStemDynSmem = 2 * 5 * 3 * 2 * kStemIdx * 4;
+inline cudaError_t launch_stem(const StemParams& P, int num_sms, cudaStream_t st, bool pdl) {
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(stem_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemDynSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemDynSmem);
+    if (e != cudaSuccess) return e;
+    attr_done[dev & 63] = true;
+  }
+  const int items = P.B * ((P.Ho + 1) / 2) * ((P.Wo + kStemSeg - 1) / kStemSeg);
+  const int grid = items < num_sms ? items : num_sms;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = kStemDynSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return P.img_f32 ? cudaLaunchKernelEx(&cfg, stem_conv_kernel<false>, P) : cudaLaunchKernelEx(&cfg, stem_conv_kernel<true>, P);
+}
 
 // ---------------------------------------------------------------------------------------------------------------- depthwise
 struct BbDwParams {

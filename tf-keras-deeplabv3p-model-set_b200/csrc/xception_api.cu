@@ -1101,7 +1101,7 @@ static int run_backbone(dlv3p_model* m, const void* d_images, cudaStream_t st, i
       StemParams P{};
       P.img = d_images; P.img_f32 = g.img_dtype == DLV3P_IMG_F32; P.w = o.wf; P.scale = o.scale; P.shift = o.shift; P.out = to.p;
       P.B = g.B; P.H = g.H; P.W = g.W; P.Ho = to.H; P.Wo = to.W; P.pad_t = m->pad_t; P.pad_l = m->pad_l;
-      e = launch_pdl(g_pdl, stem_conv_kernel, dim3(stem_grid(to.B, to.H, to.W)), dim3(128), 0, st, P);
+      e = launch_stem(P, m->num_sms, st, g_pdl);
     } else if (o.kind == OP_CONV3) {
       const Tensor& to = m->tensors[o.out];
       Conv3x3Params P{};
@@ -1571,8 +1571,7 @@ int dlv3p_op_stem_conv(int device, const void* img, int img_dtype, int B, int H,
   P.B = B; P.H = H; P.W = W; P.Ho = cdiv(H, 2); P.Wo = cdiv(W, 2);
   P.pad_t = std::max((P.Ho - 1) * 2 + 3 - H, 0) / 2;
   P.pad_l = std::max((P.Wo - 1) * 2 + 3 - W, 0) / 2;
-  stem_conv_kernel<<<stem_grid(B, P.Ho, P.Wo), 128, 0, st>>>(P);
-  MCU(nullptr, cudaGetLastError());
+  MCU(nullptr, launch_stem(P, sms, st, false));
   MCU(nullptr, cudaStreamSynchronize(st));
   return DLV3P_OK;
 }
