@@ -227,6 +227,20 @@ int dlv3p_op_normalize_image(int device, const uint8_t* d_img_u8, int64_t n, voi
 int dlv3p_op_denormalize_image(int device, const float* d_img_f32, int64_t n, uint8_t* d_out_u8, void* cuda_stream);
 int dlv3p_op_mask_resize_nearest(int device, const uint8_t* d_mask, int B, int hi, int wi, int ho, int wo, uint8_t* d_out, void* cuda_stream);
 
+/* "Resize in" of the demo / evaluation loops: preprocess_image (common/data_utils.py:436-454) = PIL Image.resize((wo, ho), Image.BICUBIC)
+ * of B decoded uint8 images [H, W, C] -> [ho, wo, C] (device pointers).  Pillow's arithmetic (dependency of the reference, not vendored;
+ * algorithm of src/libImaging/Resample.c restated): Keys cubic a = -0.5 stretched by max(scale, 1) (antialiased down-scaling), double
+ * coefficients normalised and rounded to 22-bit fixed point on the host, horizontal pass first into a uint8 intermediate, each pass
+ * clip8((2^21 + sum) >> 22).  Integer work, bit exact against PIL (tests).  SYNCHRONOUS: coefficient tables and the intermediate
+ * image are allocated, used and freed inside the call (a pre-processing step, not part of the forward). */
+int dlv3p_op_resize_bicubic_u8(int device, const uint8_t* d_img, int B, int H, int W, int C, int ho, int wo, uint8_t* d_out, void* cuda_stream);
+
+/* Present-class set of the native post-process (inference/MNN/deeplabSegment.cpp:171-172: class_indexes, the non-background classes
+ * of the mask in order of first appearance).  d_first: device uint32 [B][256], d_first[b][c] = smallest raster index of a pixel of
+ * image b labelled c, 0xFFFFFFFF if absent (the call initialises it); sorting the present classes c != 0 by d_first reproduces the
+ * reference's order (dlv3p_b200.ffi.op_present_classes).  Asynchronous; integer work, bit exact. */
+int dlv3p_op_present_classes(int device, const uint8_t* d_labels, int B, int64_t n_per_image, unsigned int* d_first, void* cuda_stream);
+
 /* Training-mode batch statistics of CustomBatchNormalization / SyncBatchNormalization (layers.py:63-70) — the SyncBN half of
  * the cfg-5 exchange.  x: device bf16 [M, C] (NHWC as [pixels, channels]).  d_stats: device fp32 [2*C + 1] =
  * sum_x | sum_x2 | row count; with several replicas the caller all-reduces (SUM) d_stats over NCCL (sharding.py), then

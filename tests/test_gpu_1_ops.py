@@ -186,3 +186,44 @@ def test_mask_resize_is_cv2_inter_nearest(gpu, hi, wi, ho, wo):
     got = ffi.op_mask_resize(masks, (wo, ho))
     for b in range(3):
         assert np.array_equal(got[b], cv2.resize(masks[b], (wo, ho), interpolation=cv2.INTER_NEAREST))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('hw_in,hw_out,B', [((64, 48), (32, 32), 2), ((37, 51), (64, 80), 1), ((375, 500), (512, 512), 2), ((512, 512), (512, 300), 1),
+                                            ((96, 96), (96, 96), 1), ((9, 7), (40, 3), 3), ((300, 200), (31, 29), 1), ((33, 65), (16, 65), 2),
+                                            ((1024, 2048), (512, 512), 1)])
+def test_resize_in_is_pil_bicubic(gpu, hw_in, hw_out, B):
+    """The resize of preprocess_image (common/data_utils.py:449, PIL Image.resize(..., Image.BICUBIC)) on the device: bit exact against
+    the oracle's restatement of Pillow's resampler (itself pinned against Pillow) and against Pillow directly, batched."""
+    from PIL import Image
+    from dlv3p_b200 import ffi
+    rng = np.random.default_rng(hw_in[0] * 131 + hw_out[1])
+    img = rng.integers(0, 256, (B,) + hw_in + (3,)).astype(np.uint8)
+    img[:, : hw_in[0] // 2] = (img[:, : hw_in[0] // 2] // 128) * 255     # saturated blocks: the cubic's overshoot hits clip8
+    got = ffi.op_resize_bicubic(img, hw_out)
+    assert got.shape == (B,) + hw_out + (3,)
+    for b in range(B):
+        assert np.array_equal(got[b], R.pil_bicubic_resize(img[b], hw_out))
+        assert np.array_equal(got[b], np.asarray(Image.fromarray(img[b]).resize((hw_out[1], hw_out[0]), Image.BICUBIC)))
+    # single channel (a grey image) goes through the same passes
+    g = ffi.op_resize_bicubic(img[0, :, :, :1], hw_out)
+    assert np.array_equal(g[..., 0], np.asarray(Image.fromarray(img[0, :, :, 0]).resize((hw_out[1], hw_out[0]), Image.BICUBIC)))
+
+
+@pytest.mark.gpu
+def test_present_classes_of_the_native_postprocess(gpu):
+    """class_indexes (inference/MNN/deeplabSegment.cpp:171-172): classes != 0 in order of first appearance, per image."""
+    from dlv3p_b200 import ffi
+    rng = np.random.default_rng(11)
+    masks = rng.integers(0, 21, (3, 375, 500)).astype(np.uint8)
+    masks[0, :200] = 0
+    masks[0, 200, 17] = 20
+    masks[1] = 0
+    masks[2, 0, 0] = 255
+    got = ffi.op_present_classes(masks)
+    assert got == [R.present_classes(m) for m in masks]
+    assert got[0][0] == 20 and got[1] == [] and got[2][0] == 255
+    big = np.zeros((1, 1024, 2048), np.uint8)
+    big[0, -1, -1] = 3
+    big[0, 5, 5] = 9
+    assert ffi.op_present_classes(big) == [[9, 3]]

@@ -369,6 +369,24 @@ def test_example_images_whole_model_identical_miou(gpu, stem):
     m32.close(); m16.close()
 
 
+def test_segment_mask_is_the_reference_demo_pipeline(gpu):
+    """DeepLab.segment_image up to the mask (deeplab.py:81-109): PIL bicubic resize in -> normalize -> model -> argmax -> cv2 nearest resize
+    out.  The device pipeline (segment_mask) against the same steps done with Pillow / OpenCV around the same model: identical masks."""
+    import cv2
+    from PIL import Image
+    H, W = 96, 128
+    m, Wb, Wh, hcfg = _model_and_oracle(16, H, W, B=1, keep=False)
+    rng = np.random.default_rng(77)
+    for (H0, W0) in ((150, 200), (64, 300), (96, 128)):
+        img = rng.integers(0, 256, (H0, W0, 3)).astype(np.uint8)
+        got = m.segment_mask(Image.fromarray(img))
+        resized = np.asarray(Image.fromarray(img).resize((W, H), Image.BICUBIC))
+        lab = m(resized[None])[0]
+        want = cv2.resize(lab, (W0, H0), interpolation=cv2.INTER_NEAREST)
+        assert got.shape == (H0, W0) and np.array_equal(got, want)
+    m.close()
+
+
 def test_load_weights_from_a_keras_h5_file(gpu, tmp_path):
     """model.load_weights(weights_path) (model.py:102-103): the whole model loaded from a Keras-layout .h5 (read by h5lite, matched by
     layer / variable name) computes the same label maps, bit for bit, as the same weights given as a dict."""

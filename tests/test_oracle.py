@@ -141,3 +141,45 @@ def test_preprocessing_reproduces_the_reference_functions():
     jpg = '/root/reference/example/2007_000039.jpg'
     if os.path.exists(jpg):                      # the example image itself lives in the reference tree (build container only)
         assert np.array_equal(R.preprocess_image(Image.open(jpg), (48, 64)), z['preprocess_2007_000039_48x64'])
+
+
+PIL_CASES = [((64, 48), (32, 32)), ((37, 51), (64, 80)), ((375, 500), (512, 512)), ((512, 512), (512, 300)), ((96, 96), (96, 96)), ((9, 7), (40, 3)),
+             ((300, 200), (31, 29)), ((33, 65), (16, 65))]
+
+
+@pytest.mark.parametrize('hw_in,hw_out', PIL_CASES)
+def test_pil_bicubic_restatement_equals_pillow(hw_in, hw_out):
+    """preprocess_image's resize (common/data_utils.py:449) IS PIL's Image.resize(size, Image.BICUBIC): the integer restatement against
+    Pillow itself, bit for bit, up- and down-scaling (antialiased), one axis unchanged, identity."""
+    from PIL import Image
+    rng = np.random.default_rng(hw_in[0] * 131 + hw_out[1])
+    img = rng.integers(0, 256, hw_in + (3,)).astype(np.uint8)
+    img[: hw_in[0] // 2] = (img[: hw_in[0] // 2] // 128) * 255          # saturated blocks: the overshoot of the cubic hits clip8
+    ref = np.asarray(Image.fromarray(img).resize((hw_out[1], hw_out[0]), Image.BICUBIC))
+    assert np.array_equal(R.pil_bicubic_resize(img, hw_out), ref)
+
+
+def test_pil_bicubic_on_the_reference_example_image():
+    import os
+    from PIL import Image
+    path = '/root/reference/example/2007_000039.jpg'
+    if not os.path.exists(path):
+        pytest.skip('reference example images are not on this machine')
+    im = Image.open(path).convert('RGB')
+    ref = np.asarray(im.resize((512, 512), Image.BICUBIC))
+    assert np.array_equal(R.pil_bicubic_resize(np.asarray(im), (512, 512)), ref)
+    assert np.array_equal(R.preprocess_image(im, (512, 512))[0], R.normalize_image(ref.astype('float32')))
+
+
+def test_present_classes_follow_the_raster_order_of_the_native_postprocess():
+    """inference/MNN/deeplabSegment.cpp:160-173 restated literally (per pixel: append a non-zero class on first sight)."""
+    rng = np.random.default_rng(5)
+    mask = rng.integers(0, 21, (40, 50)).astype(np.uint8)
+    mask[:3] = 0
+    mask[3, :10] = 7
+    literal = []
+    for v in mask.reshape(-1):
+        if v != 0 and int(v) not in literal:
+            literal.append(int(v))
+    assert R.present_classes(mask) == literal and literal[0] == 7
+    assert R.present_classes(np.zeros((4, 4), np.uint8)) == []

@@ -1752,6 +1752,116 @@ int dlv3p_op_mask_resize_nearest(int device, const uint8_t* d_mask, int B, int h
   return DLV3P_OK;
 }
 
+// Pillow's precompute_coeffs + normalize_coeffs_8bpc for the bicubic filter (Resample.c), in double like the original
+namespace {
+double pil_bicubic(double x) {
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+  if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+  return 0.0;
+}
+int pil_coeffs(int in_size, int out_size, std::vector<int>* bounds, std::vector<int>* kk) {
+  const double scale = static_cast<double>(in_size) / out_size;
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = 2.0 * filterscale;
+  const int ksize = static_cast<int>(std::ceil(support)) * 2 + 1;
+  bounds->assign(static_cast<size_t>(out_size) * 2, 0);
+  kk->assign(static_cast<size_t>(out_size) * ksize, 0);
+  std::vector<double> k(ksize);
+  const double ss = 1.0 / filterscale;
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = (xx + 0.5) * scale;
+    double ww = 0.0;
+    int xmin = static_cast<int>(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = static_cast<int>(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    for (int x = 0; x < xmax; ++x) {
+      const double w = pil_bicubic((x + xmin - center + 0.5) * ss);
+      k[x] = w;
+      ww += w;
+    }
+    for (int x = 0; x < xmax; ++x) {
+      if (ww != 0.0) k[x] /= ww;
+      const double v = k[x] * (1 << 22);
+      (*kk)[static_cast<size_t>(xx) * ksize + x] = v < 0 ? static_cast<int>(-0.5 + v) : static_cast<int>(0.5 + v);
+    }
+    (*bounds)[2 * xx] = xmin;
+    (*bounds)[2 * xx + 1] = xmax;
+  }
+  return ksize;
+}
+}  // namespace
+
+int dlv3p_op_resize_bicubic_u8(int device, const uint8_t* d_img, int B, int H, int W, int C, int ho, int wo, uint8_t* d_out, void* cuda_stream) {
+  int sms = 0, r = op_prolog(device, &sms);
+  if (r) return r;
+  if (!d_img || !d_out || B < 1 || H < 1 || W < 1 || C < 1 || ho < 1 || wo < 1) return fail(nullptr, DLV3P_ERR_INVALID, "op_resize_bicubic_u8: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const bool horiz = wo != W, vert = ho != H;      // Pillow skips a pass whose size does not change
+  if (!horiz && !vert) {
+    CU_TRY(nullptr, cudaMemcpyAsync(d_out, d_img, static_cast<size_t>(B) * H * W * C, cudaMemcpyDeviceToDevice, st));
+    return DLV3P_OK;
+  }
+  std::vector<int> bx, kx, by, ky;
+  const int ksx = horiz ? pil_coeffs(W, wo, &bx, &kx) : 0, ksy = vert ? pil_coeffs(H, ho, &by, &ky) : 0;
+  const size_t tab_ints = bx.size() + kx.size() + by.size() + ky.size();
+  const size_t tmp_bytes = horiz && vert ? static_cast<size_t>(B) * H * wo * C : 0;
+  int* d_tab = nullptr;
+  uint8_t* d_tmp = nullptr;
+  CU_TRY(nullptr, cudaMalloc(&d_tab, tab_ints * sizeof(int)));
+  if (tmp_bytes && cudaMalloc(&d_tmp, tmp_bytes) != cudaSuccess) {
+    cudaFree(d_tab);
+    return fail(nullptr, DLV3P_ERR_NOMEM, "op_resize_bicubic_u8: cudaMalloc of the intermediate image failed");
+  }
+  std::vector<int> tab;
+  tab.reserve(tab_ints);
+  tab.insert(tab.end(), bx.begin(), bx.end());      // the {first, count} pairs first: both are read as int2 (even sizes keep them aligned)
+  tab.insert(tab.end(), by.begin(), by.end());
+  tab.insert(tab.end(), kx.begin(), kx.end());
+  tab.insert(tab.end(), ky.begin(), ky.end());
+  cudaError_t e = cudaMemcpyAsync(d_tab, tab.data(), tab_ints * sizeof(int), cudaMemcpyHostToDevice, st);
+  const int* d_bx = d_tab;
+  const int* d_by = d_bx + bx.size();
+  const int* d_kx = d_by + by.size();
+  const int* d_ky = d_kx + kx.size();
+  if (e == cudaSuccess && horiz) {      // rows are the outer axis, pixels the resampled one, channels inner
+    uint8_t* dst = vert ? d_tmp : d_out;
+    resample_pass_u8_kernel<<<grid_for(static_cast<size_t>(B) * H * wo * C, sms), 256, 0, st>>>(d_img, dst, static_cast<long long>(B) * H, W, wo, C,
+                                                                                                 reinterpret_cast<const int2*>(d_bx), d_kx, ksx);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess && vert) {       // images outer, rows resampled, a whole row of pixels x channels inner
+    const uint8_t* src = horiz ? d_tmp : d_img;
+    resample_pass_u8_kernel<<<grid_for(static_cast<size_t>(B) * ho * wo * C, sms), 256, 0, st>>>(src, d_out, B, H, ho, wo * C, reinterpret_cast<const int2*>(d_by),
+                                                                                                  d_ky, ksy);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // the tables and the intermediate live only for this call
+  cudaFree(d_tab);
+  if (d_tmp) cudaFree(d_tmp);
+  CU_TRY(nullptr, e);
+  return DLV3P_OK;
+}
+
+int dlv3p_op_present_classes(int device, const uint8_t* d_labels, int B, int64_t n_per_image, unsigned int* d_first, void* cuda_stream) {
+  int sms = 0, r = op_prolog(device, &sms);
+  if (r) return r;
+  if (!d_labels || !d_first || B < 1 || B > 65535 || n_per_image < 1 || n_per_image > 0xFFFFFFFEll)
+    return fail(nullptr, DLV3P_ERR_INVALID, "op_present_classes: bad arguments (n_per_image < 2^32 - 1)");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  CU_TRY(nullptr, cudaMemsetAsync(d_first, 0xFF, static_cast<size_t>(B) * 256 * sizeof(unsigned int), st));
+  int bpi = static_cast<int>((n_per_image + 256 * 16 - 1) / (256 * 16));
+  const int cap = (8 * sms + B - 1) / B;
+  if (bpi > cap) bpi = cap;
+  if (bpi < 1) bpi = 1;
+  present_classes_kernel<<<dim3(bpi, B), 256, 0, st>>>(d_labels, n_per_image, d_first);
+  CU_TRY(nullptr, cudaGetLastError());
+  return DLV3P_OK;   // asynchronous
+}
+
 size_t dlv3p_op_bn_scratch_bytes(int C) {
   const size_t a = static_cast<size_t>(kBnBands) * 2 * (C > 0 ? C : 0), b = col_scratch_floats(C, 2);
   return (a > b ? a : b) * sizeof(float);

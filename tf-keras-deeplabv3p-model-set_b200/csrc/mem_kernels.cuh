@@ -962,6 +962,48 @@ __global__ void __launch_bounds__(256) mask_resize_nearest_kernel(const uint8_t*
 }
 
 
+// "resize in" of the demo / evaluation loops: preprocess_image (common/data_utils.py:436-454) = PIL Image.resize(size, Image.BICUBIC)
+// on the decoded uint8 RGB image.  The arithmetic is Pillow's (third-party dependency of the reference, absent from /root/reference;
+// its published algorithm, src/libImaging/Resample.c, restated): a separable convolution with the Keys cubic (a = -0.5) stretched by
+// max(scale, 1) (so down-scaling is antialiased), coefficients normalised in DOUBLE on the host and rounded to 22-bit fixed point,
+// horizontal pass first into a uint8 intermediate, each pass  clip8((2^21 + sum(pixel * coeff)) >> 22).  Integer work, bit exact.
+// One pass over axis `axis_len_in` -> `n_out`: in [outer, n_in, inner] u8, out [outer, n_out, inner]; bounds[i] = {first, count}.
+__global__ void __launch_bounds__(256) resample_pass_u8_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, long long outer, int n_in, int n_out,
+                                                               int inner, const int2* __restrict__ bounds, const int* __restrict__ kk, int ksize) {
+  const long long total = outer * n_out * inner;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % inner);
+    long long r = idx / inner;
+    const int i = static_cast<int>(r % n_out);
+    const long long o = r / n_out;
+    const int2 bd = __ldg(bounds + i);
+    const int* k = kk + static_cast<size_t>(i) * ksize;
+    const uint8_t* src = in + (o * n_in + bd.x) * inner + c;
+    int ss = 1 << 21;
+    for (int t = 0; t < bd.y; ++t) ss += static_cast<int>(src[static_cast<size_t>(t) * inner]) * __ldg(k + t);
+    ss >>= 22;                                       // arithmetic shift, then Pillow's clip8 table = clamp to 0..255
+    out[idx] = static_cast<uint8_t>(ss < 0 ? 0 : (ss > 255 ? 255 : ss));
+  }
+}
+
+// Present-class set of the native post-process (inference/MNN/deeplabSegment.cpp:171-172): the non-background classes of a label map
+// in order of first appearance in raster order.  The device records, per image and class, the smallest pixel index holding the class
+// (0xFFFFFFFF = absent) — block-private minima in shared memory, one global atomicMin per class and block; sorting the present classes
+// by that index on the host reproduces the reference's emplace_back order exactly.  first: [B][256] uint32, pre-set to 0xFFFFFFFF.
+__global__ void __launch_bounds__(256) present_classes_kernel(const uint8_t* __restrict__ labels, long long n_per_image, unsigned int* __restrict__ first) {
+  __shared__ unsigned int s_first[256];
+  s_first[threadIdx.x] = 0xFFFFFFFFu;
+  __syncthreads();
+  const uint8_t* img = labels + static_cast<size_t>(blockIdx.y) * n_per_image;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_per_image; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const unsigned int cls = img[i];
+    if (s_first[cls] > static_cast<unsigned int>(i)) atomicMin(&s_first[cls], static_cast<unsigned int>(i));
+  }
+  __syncthreads();
+  const unsigned int v = s_first[threadIdx.x];
+  if (v != 0xFFFFFFFFu) atomicMin(first + static_cast<size_t>(blockIdx.y) * 256 + threadIdx.x, v);
+}
+
 // ------------------------------------------------------------------------------------------------ Jaccard metric counts (N3)
 // The training metric of the reference (deeplabv3p/metrics.py:30-45, compiled in at train.py:141): per image and per class i in
 // 0..NC the pixel counts  inter = #(gt == i & pred == i), true = #(gt == i), pred = #(pred == i)  (union = true + pred - inter; a

@@ -90,6 +90,8 @@ SYMBOLS = [
     ('dlv3p_op_normalize_image', _i, [_i, _vp, C.c_int64, _vp, _i, _vp]),
     ('dlv3p_op_denormalize_image', _i, [_i, _vp, C.c_int64, _vp, _vp]),
     ('dlv3p_op_mask_resize_nearest', _i, [_i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    ('dlv3p_op_resize_bicubic_u8', _i, [_i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    ('dlv3p_op_present_classes', _i, [_i, _vp, _i, C.c_int64, _vp, _vp]),
     ('dlv3p_op_bn_scratch_bytes', C.c_size_t, [_i]),
     ('dlv3p_op_bn_stats', _i, [_i, _vp, C.c_int64, _i, _vp, _vp, _vp]),
     ('dlv3p_op_bn_apply', _i, [_i, _vp, C.c_int64, _i, _vp, _vp, _vp, C.c_float, _i, _vp, _vp]),
@@ -607,6 +609,37 @@ def op_mask_resize(mask: np.ndarray, target_size: Tuple[int, int], device=0) -> 
     _check(load_library().dlv3p_op_mask_resize_nearest(device, din.ptr, B, hi, wi, ho, wo, dout.ptr, None))
     synchronize(device)
     return dout.download(a.shape[:-2] + (ho, wo), np.uint8)
+
+
+def op_resize_bicubic(image: np.ndarray, size_hw: Tuple[int, int], device=0) -> np.ndarray:
+    """The resize of preprocess_image (common/data_utils.py:449: image.resize(model_input_shape[::-1], Image.BICUBIC)) on the device:
+    uint8 images [..., H, W, C] -> [..., ho, wo, C], bit exact against Pillow."""
+    a = np.ascontiguousarray(image, np.uint8)
+    if a.ndim < 3:
+        raise ValueError('op_resize_bicubic: expected [..., H, W, C] uint8')
+    H, W, Cc = a.shape[-3:]
+    ho, wo = int(size_hw[0]), int(size_hw[1])
+    B = a.size // (H * W * Cc)
+    din = DeviceBuffer.from_numpy(a.reshape(-1), device)
+    dout = DeviceBuffer(B * ho * wo * Cc, device)
+    _check(load_library().dlv3p_op_resize_bicubic_u8(device, din.ptr, B, H, W, Cc, ho, wo, dout.ptr, None))
+    synchronize(device)
+    return dout.download(a.shape[:-3] + (ho, wo, Cc), np.uint8)
+
+
+def op_present_classes(labels: np.ndarray, device=0) -> List[List[int]]:
+    """class_indexes of the native post-process (inference/MNN/deeplabSegment.cpp:171-172) for uint8 label maps [B, H, W] (or [H, W]):
+    per image the classes != 0 that occur, in order of first appearance in raster order."""
+    a = np.ascontiguousarray(labels, np.uint8)
+    if a.ndim == 2:
+        a = a[None]
+    B, n = a.shape[0], int(a.shape[1] * a.shape[2])
+    din = DeviceBuffer.from_numpy(a.reshape(-1), device)
+    dfirst = DeviceBuffer(B * 256 * 4, device)
+    _check(load_library().dlv3p_op_present_classes(device, din.ptr, B, n, dfirst.ptr, None))
+    synchronize(device)
+    first = dfirst.download((B, 256), np.uint32)
+    return [[int(c) for c in np.argsort(first[b], kind='stable') if c != 0 and first[b, c] != 0xFFFFFFFF] for b in range(B)]
 
 
 def bn_stats(x_ptr: int, M: int, Cc: int, stats_ptr: int, scratch_ptr: int, stream=None, device=0) -> None:

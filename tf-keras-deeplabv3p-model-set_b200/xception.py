@@ -8,7 +8,7 @@
 Images go in as the reference's loaders produce them — uint8 RGB (normalize_image runs inside the first convolution) or the
 float32 [-1, 1] arrays of preprocess_image — and label maps / logits / probabilities come out.  Weights use the Keras layer and
 variable names of the reference in Keras creation order (backbone, then head), so `model.get_weights()` of the reference model
-or its `.h5` exported by tools/h5_to_npz.py load unchanged.
+or its `.h5` weight file (read by h5lite, no h5py needed) load unchanged.
 """
 from __future__ import annotations
 
@@ -124,6 +124,27 @@ class DeepLabV3PlusXception:
             raise ValueError('out must be a C-contiguous %s array of shape %s' % (np.dtype(dt).name, tuple(shape)))
         self.model.forward_host(a, out)
         return out
+
+    def segment_mask(self, image) -> np.ndarray:
+        """DeepLab.segment_image up to the mask (deeplab.py:81-109) with every array step on the device: preprocess_image's PIL bicubic
+        resize (common/data_utils.py:449, dlv3p_op_resize_bicubic_u8 — bit exact against Pillow), normalize_image (inside the first
+        convolution), the model, argmax, mask_resize back to the image's own size.  `image`: a PIL RGB image or a uint8 [H, W, 3] array;
+        batch-1 models with out_mode labels.  Returns the uint8 mask [H, W]."""
+        if self.B != 1 or self.out_mode != ffi.OUT_LABELS_U8 or self.image_dtype != np.uint8:
+            raise ValueError('segment_mask needs a batch-1 uint8-image model with label output')
+        a = np.ascontiguousarray(np.asarray(image), np.uint8)
+        if a.ndim != 3 or a.shape[2] != 3:
+            raise ValueError('segment_mask: expected an RGB image, got shape %s' % (a.shape,))
+        H0, W0 = a.shape[:2]
+        lib = ffi.load_library()
+        d_raw, d_img = self._dev('raw', a.nbytes), self._dev('img', self.H * self.W * 3)
+        d_lab, d_mask = self._dev('out', self.model.output_bytes()), self._dev('mask', H0 * W0)
+        d_raw.upload(a)
+        ffi._check(lib.dlv3p_op_resize_bicubic_u8(self.device, d_raw.ptr, 1, H0, W0, 3, self.H, self.W, d_img.ptr, None))
+        self.model.forward(d_img.ptr, d_lab.ptr)
+        ffi._check(lib.dlv3p_op_mask_resize_nearest(self.device, d_lab.ptr, 1, self.H, self.W, H0, W0, d_mask.ptr, None))
+        ffi.synchronize(self.device)
+        return d_mask.download((H0, W0), np.uint8)
 
     def tap(self, name: str) -> np.ndarray:
         """Backbone intermediates by Keras block name ('entry_flow_block1', 'feature', 'skip', ...) or head taps ('logits', ...)."""
