@@ -145,6 +145,8 @@ typedef struct dlv3p_trainer_config {
   float bn_momentum, eps;     /* 0.99, 1e-5 */
   float dropout;              /* 0.5 (layers.py:161) */
   float focal_gamma, focal_alpha;
+  int32_t lite;               /* 0: ASPP_block + Decoder_block (xception, resnet50, mobilenetv2 / v3 ...);  1: ASPP_Lite_block and no decoder,
+                                 the *_lite models (deeplabv3p_mobilenetv2.py:326-331): Cskip is ignored, d_skip may be NULL */
 } dlv3p_trainer_config;
 typedef struct dlv3p_trainer dlv3p_trainer;
 

@@ -53,8 +53,8 @@ def head_train_forward_backward(feat: np.ndarray, skip: np.ndarray, labels: np.n
     import torch
     import torch.nn.functional as F
     dt = dtype or torch.float32
-    if cfg.lite or not cfg.decoder:
-        raise ValueError('the training oracle covers the full head (ASPP_block + Decoder_block)')
+    if cfg.lite == cfg.decoder:
+        raise ValueError('the training oracle covers the reference\'s two heads: ASPP_block + Decoder_block, or ASPP_Lite_block without a decoder')
 
     class _RoundBF16(torch.autograd.Function):
         @staticmethod
@@ -73,7 +73,7 @@ def head_train_forward_backward(feat: np.ndarray, skip: np.ndarray, labels: np.n
         rw = lambda k: k
     P = {k: torch.tensor(np.asarray(v), dtype=dt, requires_grad=_trainable(k)) for k, v in W.items()}
     x_in = torch.tensor(feat, dtype=dt, requires_grad=True)
-    s_in = torch.tensor(skip, dtype=dt, requires_grad=True)
+    s_in = torch.tensor(skip if skip is not None else np.zeros((cfg.B, 1, 1, 8), np.float32), dtype=dt, requires_grad=True)
     x = x_in.permute(0, 3, 1, 2)
     s = s_in.permute(0, 3, 1, 2)
     stats = {}
@@ -102,20 +102,24 @@ def head_train_forward_backward(feat: np.ndarray, skip: np.ndarray, labels: np.n
         t = keep(prefix + '/p', conv(t, prefix + '_pointwise'))
         return keep(prefix + '/y', bn(t, prefix + '_pointwise_BN'))
 
-    # ASPP_block (layers.py:114-163)
     b4 = bn(conv(rb(rb(x).mean(dim=(2, 3), keepdim=True)), 'image_pooling'), 'image_pooling_BN')
     b4 = b4.expand(-1, -1, cfg.h, cfg.w)                          # bilinear resize of a 1x1 map = broadcast
     b0 = bn(conv(rb(x), 'aspp0'), 'aspp0_BN')
-    bs = [sep(x, 'aspp%d' % i, cfg.rates[i - 1]) for i in (1, 2, 3)]
+    if cfg.lite:                                                   # ASPP_Lite_block (layers.py:166-196): only the two branches
+        bs = []
+    else:                                                          # ASPP_block (layers.py:114-163)
+        bs = [sep(x, 'aspp%d' % i, cfg.rates[i - 1]) for i in (1, 2, 3)]
     y = bn(conv(rb(torch.cat([b4, b0] + bs, dim=1)), 'concat_projection'), 'concat_projection_BN')
     if keep_mask is not None:
         m = torch.tensor(np.asarray(keep_mask).reshape(cfg.B, cfg.h, cfg.w, 256), dtype=dt).permute(0, 3, 1, 2)
         y = rb(y * m * (1.0 / (1.0 - drop_rate)))
-    # Decoder_block (layers.py:199-219)
-    up = rb(F.interpolate(y, size=(cfg.hs, cfg.ws), mode='bilinear', align_corners=False))
-    sk = bn(conv(rb(s), 'feature_projection0'), 'feature_projection0_BN')
-    d = sep(torch.cat([up, sk], dim=1), 'decoder_conv0', 1)
-    d = sep(d, 'decoder_conv1', 1)
+    if cfg.decoder:                                                # Decoder_block (layers.py:199-219)
+        up = rb(F.interpolate(y, size=(cfg.hs, cfg.ws), mode='bilinear', align_corners=False))
+        sk = bn(conv(rb(s), 'feature_projection0'), 'feature_projection0_BN')
+        d = sep(torch.cat([up, sk], dim=1), 'decoder_conv0', 1)
+        d = sep(d, 'decoder_conv1', 1)
+    else:                                                          # the *_lite models: the classifier reads the ASPP output (deeplabv3p_mobilenetv2.py:326-331)
+        d = y
     # tail + loss
     logits = conv(d, 'conv_upsample', bias=True)
     logits = keep('logits', rb(logits) + (logits - rb(logits)).detach() if mode == 'bf16' else logits)   # fp32 value, bf16 gradient
@@ -135,7 +139,7 @@ def head_train_forward_backward(feat: np.ndarray, skip: np.ndarray, labels: np.n
     loss = px.sum() / float(cfg.B * cfg.H * cfg.W)
     loss.backward()
     grads = {k: v.grad.numpy().copy() for k, v in P.items() if v.requires_grad and v.grad is not None}
-    return {'loss': float(loss.item()), 'grads': grads, 'd_feat': x_in.grad.numpy().copy(), 'd_skip': s_in.grad.numpy().copy(),
+    return {'loss': float(loss.item()), 'grads': grads, 'd_feat': x_in.grad.numpy().copy(), 'd_skip': None if s_in.grad is None else s_in.grad.numpy().copy(),
             'act_grads': {k: v.grad.permute(0, 2, 3, 1).numpy().copy() for k, v in acts.items() if v.grad is not None},
             'batch_stats': stats, 'logits': logits.detach().permute(0, 2, 3, 1).numpy().copy(), 'valid_pixels': int(valid.sum().item())}
 

@@ -446,6 +446,64 @@ def test_head_training_step_matches_the_oracle(gpu):
     assert all(np.array_equal(grads[k], g2[k]) for k in grads)
 
 
+def test_lite_head_training_step_matches_the_oracle(gpu):
+    """The *_lite models' head (ASPP_Lite_block, no decoder: layers.py:166-196, deeplabv3p_mobilenetv2.py:326-331) through the same trainer
+    (dlv3p_trainer_config.lite): forward + loss + backward with Dropout against the oracle's bf16 and fp32 modes, then the update, the
+    CUDA-graph replay against the eager step, and a decreasing loss."""
+    torch = _t()
+    from dlv3p_b200 import train, train_ffi
+    cfg = R.HeadConfig(B=2, H=320, W=320, OS=16, Cin=320, Cskip=0, NC=21, lite=True, decoder=False)      # MobileNetV2's 320-channel feature map
+    W = R.make_weights(cfg, 41)
+    feat = R.bf16_round(R.make_inputs(cfg, 42)[0])
+    labels = TR.make_labels(cfg, 43)
+    tr = train.HeadTrainer(cfg.B, cfg.H, cfg.W, cfg.OS, cfg.Cin, 0, cfg.NC, W, device=0, seed=9, lite=True)
+    f, l = _bf(feat), torch.from_numpy(labels).cuda()
+    tr.forward_backward(f, None, l)
+    torch.cuda.synchronize()
+    keep = train_ffi.dropout_keep_mask(cfg.B * cfg.h * cfg.w * 256, train.dropout_seed(9, 0, 0), 0.5)
+    ref = TR.head_train_forward_backward(feat, None, labels, W, cfg, keep_mask=keep, mode='bf16')
+    ref32 = TR.head_train_forward_backward(feat, None, labels, W, cfg, keep_mask=keep, mode='fp32')
+    grads = tr.get_grads()
+    assert set(grads) == set(ref['grads'])
+    loss = tr.loss()
+    assert abs(loss - ref['loss']) <= 2e-3 * abs(ref['loss']) and abs(loss - ref32['loss']) <= 1e-2 * abs(ref32['loss'])
+    floor = 0.02 * float(np.median([np.linalg.norm(np.asarray(g, np.float64)) for g in ref['grads'].values()]))
+    worst = {}
+    for key, g in ref['grads'].items():
+        got = np.asarray(grads[key], np.float64)
+        g = np.asarray(g, np.float64).reshape(got.shape)
+        worst[key] = float(np.linalg.norm(got - g) / max(np.linalg.norm(g), floor))
+    worst['d_feat'] = rel_l2(tr.T['dfeat'].numpy(), ref['d_feat'].reshape(-1, cfg.Cin))
+    print('lite step: worst tensor rel-L2 vs the bf16-mode oracle %.4f (%s)' % max((v, str(k)) for k, v in worst.items()))
+    assert all(v < GRAD_TOL for v in worst.values()), worst
+    for key in [('conv_upsample', 'kernel'), ('conv_upsample', 'bias'), ('concat_projection_BN', 'gamma'), ('concat_projection_BN', 'beta')]:
+        assert worst[key] < 5e-3, (key, worst[key])
+    # update + moving statistics
+    tr.all_reduce_gradients()
+    tr.apply_gradients()
+    torch.cuda.synchronize()
+    Wn, _ = TR.sgd_momentum_update(W, {k: np.asarray(v).reshape(np.asarray(W[k]).shape) for k, v in ref['grads'].items()}, {})
+    Wn = TR.moving_update(Wn, ref['batch_stats'])
+    got = tr.get_weights()
+    assert set(got) == set(Wn)
+    for key, wref in Wn.items():
+        w0 = np.asarray(W[key], np.float32)
+        delta_ref, delta = np.asarray(wref, np.float32) - w0, got[key].reshape(w0.shape) - w0
+        ulp = 1.2e-7 * max(1.0, float(np.abs(w0).max())) * np.sqrt(delta.size)
+        assert np.linalg.norm((delta - delta_ref).astype(np.float64)) <= GRAD_TOL * np.linalg.norm(delta_ref.astype(np.float64)) + ulp, key
+    # graph replay == eager, bit for bit; the loss goes down
+    ta = train.HeadTrainer(cfg.B, cfg.H, cfg.W, cfg.OS, cfg.Cin, 0, cfg.NC, W, device=0, seed=3, lr=0.05, lite=True, graph=True)
+    tb = train.HeadTrainer(cfg.B, cfg.H, cfg.W, cfg.OS, cfg.Cin, 0, cfg.NC, W, device=0, seed=3, lr=0.05, lite=True, graph=False)
+    la, lb = [], []
+    for _ in range(6):
+        ta.train_step(f, None, l); la.append(ta.loss())
+        tb.train_step(f, None, l); lb.append(tb.loss())
+    assert ta.graph_captured and not tb.graph_captured and la == lb
+    wa, wb = ta.get_weights(), tb.get_weights()
+    assert all(np.array_equal(wa[k], wb[k]) for k in wa)
+    assert np.isfinite(la).all() and la[-1] < la[0] - 0.03, la
+
+
 def test_training_reduces_the_loss(gpu):
     torch = _t()
     from dlv3p_b200 import train

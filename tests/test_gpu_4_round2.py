@@ -213,3 +213,67 @@ def test_data_parallel_step_two_processes_one_gpu(gpu):
     for k in got[0][5]:
         assert np.array_equal(got[0][5][k], got[1][5][k]), 'replicas disagree on %s after the update' % (k,)
     _compare_step(got[0][1], d_feat, d_skip, got[0][4], ref, cfg)
+
+
+def _one_gpu_lite_worker(rank, world, port, q):
+    try:
+        import torch
+        import torch.distributed as dist
+        from dlv3p_b200 import train
+        os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+        torch.cuda.set_device(0)
+        dist.init_process_group('gloo', rank=rank, world_size=world)
+        cfg, W, feat, labels = _lite_case(B=2 * world)
+        Bl = cfg.B // world
+        sl = slice(rank * Bl, (rank + 1) * Bl)
+        tr = train.HeadTrainer(Bl, cfg.H, cfg.W, cfg.OS, cfg.Cin, 0, cfg.NC, W, device=0, seed=9, lite=True)
+        f = torch.from_numpy(feat[sl]).cuda().to(torch.bfloat16).contiguous()
+        l = torch.from_numpy(labels[sl]).cuda().contiguous()
+        losses = []
+        for _ in range(3):                      # eager, capture, replay: the exchanges inside the captured graph
+            tr.train_step(f, None, l)
+            losses.append(tr.loss())
+        q.put((rank, tr.get_grads(), tr.T['dfeat'].float().cpu().numpy(), losses, tr.get_weights(), tr.graph_captured))
+        dist.barrier()
+        tr.close()
+        dist.destroy_process_group()
+    except Exception as e:
+        import traceback
+        q.put((rank, 'ERROR', traceback.format_exc(), str(e), None, None))
+
+
+def _lite_case(B):
+    cfg = R.HeadConfig(B=B, H=320, W=320, OS=16, Cin=96, Cskip=0, NC=21, lite=True, decoder=False)
+    W = R.make_weights(cfg, 51)
+    feat = R.bf16_round(R.make_inputs(cfg, 52)[0])
+    return cfg, W, feat, TR.make_labels(cfg, 53)
+
+
+def test_lite_data_parallel_steps_two_processes_one_gpu(gpu):
+    """The *_lite head's training step with world size 2 (two processes on cuda:0, peer-memory exchanges through CUDA IPC): three steps
+    (eager, captured, replayed); the first step's loss equals the oracle's on the global batch, the replicas stay bit-identical."""
+    import torch.multiprocessing as mp
+    from dlv3p_b200 import train, train_ffi
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_one_gpu_lite_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = sorted([q.get(timeout=300) for _ in ps], key=lambda t: t[0])
+    for p in ps:
+        p.join(timeout=30)
+        if p.is_alive():
+            p.terminate()
+    for g in got:
+        assert not (isinstance(g[1], str) and g[1] == 'ERROR'), g[2]
+    cfg, W, feat, labels = _lite_case(B=4)
+    n_local = 2 * cfg.h * cfg.w * 256
+    keep = np.concatenate([train_ffi.dropout_keep_mask(n_local, train.dropout_seed(9, 0, r), 0.5) for r in range(2)])
+    ref = TR.head_train_forward_backward(feat, None, labels, W, cfg, keep_mask=keep, mode='bf16')
+    assert got[0][5] and got[1][5]
+    assert got[0][3] == got[1][3] and abs(got[0][3][0] - ref['loss']) <= 2e-3 * abs(ref['loss']), (got[0][3], ref['loss'])
+    for k in got[0][1]:
+        assert np.array_equal(got[0][1][k], got[1][1][k]), 'replicas disagree on the gradient of %s' % (k,)
+    for k in got[0][4]:
+        assert np.array_equal(got[0][4][k], got[1][4][k]), 'replicas disagree on %s after three steps' % (k,)

@@ -130,3 +130,37 @@ def test_oracle_loss_variants_match_finite_differences(kw):
     fd = (run(Wp)['loss'] - run(Wm)['loss']) / (2 * eps)
     assert abs(fd - out['grads'][key][idx]) <= 1e-7 + 1e-4 * abs(fd)
     assert out['loss'] != TR.head_train_forward_backward(feat.astype(np.float64), skip.astype(np.float64), labels, W64, cfg, dtype=torch.float64)['loss']
+
+
+def test_lite_oracle_gradients_match_finite_differences_and_the_layout_follows():
+    """The *_lite head (ASPP_Lite_block, no decoder; layers.py:166-196, deeplabv3p_mobilenetv2.py:326-331): autograd of the restated
+    graph against central differences in float64, and the host-side layout of the lite trainer (no depthwise region, two exchange
+    groups each way)."""
+    import torch
+    from dlv3p_b200 import train
+    cfg = R.HeadConfig(B=2, H=32, W=32, OS=16, Cin=8, Cskip=0, NC=5, lite=True, decoder=False, h=4, w=4)
+    W = R.make_weights(cfg, 17)
+    feat, _ = R.make_inputs(cfg, 18)
+    labels = TR.make_labels(cfg, 19)
+    assert not any(k[0].startswith(('aspp1', 'decoder', 'feature_projection')) for k in W)
+    W64 = {k: np.asarray(v, np.float64) for k, v in W.items()}
+    f64 = feat.astype(np.float64)
+    out = TR.head_train_forward_backward(f64, None, labels, W64, cfg, keep_mask=None, dtype=torch.float64)
+    assert out['logits'].shape == (2, 4, 4, 5) and out['d_skip'] is None
+    rng = np.random.default_rng(1)
+    for key in [('aspp0', 'kernel'), ('image_pooling', 'kernel'), ('concat_projection', 'kernel'), ('concat_projection_BN', 'gamma'), ('aspp0_BN', 'beta'),
+                ('conv_upsample', 'kernel'), ('conv_upsample', 'bias')]:
+        g = out['grads'][key]
+        for _ in range(3):
+            idx = tuple(int(rng.integers(0, n)) for n in g.shape)
+            Wp, Wm = dict(W64), dict(W64)
+            e = 1e-5
+            Wp[key] = W64[key].copy(); Wp[key][idx] += e
+            Wm[key] = W64[key].copy(); Wm[key][idx] -= e
+            fd = (TR.head_train_forward_backward(f64, None, labels, Wp, cfg, keep_mask=None, dtype=torch.float64)['loss'] -
+                  TR.head_train_forward_backward(f64, None, labels, Wm, cfg, keep_mask=None, dtype=torch.float64)['loss']) / (2 * e)
+            assert abs(fd - g[idx]) <= 1e-6 + 1e-4 * abs(fd), (key, idx, fd, g[idx])
+    lay = train.TrainLayout(Cin=320, Cskip=0, NC=21, lite=True)
+    assert lay.endA == lay.endB and [n for n, *_ in lay._conv_specs()] == ['image_pooling', 'aspp0', 'concat_projection', 'conv_upsample']
+    assert lay.off[('concat_projection', 'kernel')][1] == (512, 256) and lay.nbn == 768
+    assert len(lay.FWD_GROUPS) == 2 and len(lay.BWD_GROUPS) == 2 and len(train.TrainLayout.FWD_GROUPS) == 7

@@ -64,6 +64,14 @@ inline size_t rup(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 void tr_layout(dlv3p_trainer* t) {
   const int Cin = t->Cin, Cs = t->Cs, NCp = t->NCp;
+  if (t->cfg.lite) {
+    // ASPP_Lite_block (layers.py:166-196) + the tail straight on its output: the *_lite models (deeplabv3p_mobilenetv2.py:326-331)
+    t->conv_specs = {{"image_pooling", Cin, 256}, {"aspp0", Cin, 256}, {"concat_projection", 512, 256}, {"conv_upsample", 256, NCp}};
+    t->dw_specs = {};
+    t->bn_specs = {{"image_pooling_BN", 256}, {"aspp0_BN", 256}, {"concat_projection_BN", 256}};
+    t->fwd_groups = {{"image_pooling_BN", "aspp0_BN"}, {"concat_projection_BN"}};
+    t->bwd_groups = {{"concat_projection_BN"}, {"aspp0_BN", "image_pooling_BN"}};
+  } else {
   t->conv_specs = {{"image_pooling", Cin, 256}, {"aspp0", Cin, 256}, {"aspp1_pointwise", Cin, 256}, {"aspp2_pointwise", Cin, 256},
                    {"aspp3_pointwise", Cin, 256}, {"concat_projection", 1280, 256}, {"feature_projection0", Cs, 48},
                    {"decoder_conv0_pointwise", 304, 256}, {"decoder_conv1_pointwise", 256, 256}, {"conv_upsample", 256, NCp}};
@@ -80,6 +88,7 @@ void tr_layout(dlv3p_trainer* t) {
                    {"feature_projection0_BN", "concat_projection_BN"},
                    {"aspp0_BN", "aspp1_pointwise_BN", "aspp2_pointwise_BN", "aspp3_pointwise_BN", "image_pooling_BN"},
                    {"aspp1_depthwise_BN", "aspp2_depthwise_BN", "aspp3_depthwise_BN"}};
+  }
   size_t o = 0;
   for (auto& [name, K, N] : t->conv_specs) {
     t->off[name + "/kernel"] = {o, K, N};
@@ -259,6 +268,54 @@ struct Step {
     auto X = [&](const char* n, size_t elem_off = 0) { return static_cast<void*>(bf(n) + elem_off); };
     char nm[64];
     auto N3 = [&](const char* f, int i) { snprintf(nm, sizeof(nm), f, i); return std::string(nm); };
+    if (t->cfg.lite) {
+      // ================ ASPP_Lite_block (layers.py:166-196) -> Dropout -> classifier -> pred_resize -> loss; no decoder: hs = h, ws = w
+      call(dlv3p_train_rows_reduce(dev, feat, Cin, B, npix1, Cin, 1.0f / npix1, X("pool"), 0, st));
+      conv_fwd("image_pooling", X("pool"), Cin, Bp, X("r4"), 256);
+      bn_stats("image_pooling_BN", X("r4"), B);
+      conv_fwd("aspp0", feat, Cin, M1, X("r0"), 256);
+      bn_stats("aspp0_BN", X("r0"), M1);
+      sync_stats(0);
+      bn_apply("image_pooling_BN", X("r4"), B, X("b4"), 256);
+      call(dlv3p_train_bcast_rows(dev, X("b4"), B, npix1, 256, 1.0f, X("concat"), 512, 0, st));      // aspp_resize of a 1 x 1 map
+      bn_apply("aspp0_BN", X("r0"), M1, X("concat", 256), 512);
+      conv_fwd("concat_projection", X("concat"), 512, M1, X("rp"), 256);
+      bn_fwd("concat_projection_BN", X("rp"), M1, X("yproj"), 256);
+      const char* aspp_out = "yproj";
+      if (t->cfg.dropout > 0) {
+        call(dlv3p_train_dropout(dev, X("yproj"), X("aspp_out"), static_cast<int64_t>(M1) * 256, 0, t->seed_d, t->cfg.dropout, st));
+        aspp_out = "aspp_out";
+      }
+      conv_fwd("conv_upsample", X(aspp_out), 256, M1, f32("logits"), NCp, 1);
+      const float inv_norm = 1.0f / (static_cast<float>(t->cfg.global_batch) * t->H * t->W);
+      call(dlv3p_train_softmax_loss(dev, f32("logits"), NCp, P("conv_upsample/bias"), static_cast<const uint8_t*>(labels), B, NC, h, w, t->H, t->W,
+                                    t->cfg.ignore_index, inv_norm, t->cfg.loss_kind, f32("class_w"), t->cfg.focal_gamma, t->cfg.focal_alpha, f32("dfull"),
+                                    t->world > 1 ? t->loss_send : f32("loss"), t->T.at("loss_scratch"), st), 2);
+      // ================ backward
+      call(dlv3p_train_resize_bwd_planar(dev, f32("dfull"), B, NC, h, w, t->H, t->W, X("dlow"), NCp, t->T.at("adj_tmp"), st), 2);
+      call(dlv3p_op_bn_stats(dev, X("dlow"), M1, NCp, f32("bias_stats"), t->T.at("bn_scratch"), st), 2);
+      if (!rc && cudaMemcpyAsync(G("conv_upsample/bias"), f32("bias_stats"), NCp * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        rc = tfail(t, DLV3P_ERR_CUDA, "trainer: bias gradient copy failed");
+      conv_wgrad("conv_upsample", X(aspp_out), 256, X("dlow"), NCp, M1);
+      conv_dgrad("conv_upsample", X("dlow"), NCp, M1, X("da_out"), 256);
+      if (t->cfg.dropout > 0) call(dlv3p_train_dropout(dev, X("da_out"), X("da_out"), static_cast<int64_t>(M1) * 256, 0, t->seed_d, t->cfg.dropout, st));
+      bn_bwd("concat_projection_BN", X("da_out"), 256, X("yproj"), 256, X("rp"), M1, X("drp"));
+      conv_wgrad("concat_projection", X("concat"), 512, X("drp"), 256, M1);
+      conv_dgrad("concat_projection", X("drp"), 256, M1, X("dconcat"), 512);
+      call(dlv3p_train_rows_reduce(dev, X("dconcat"), 512, B, npix1, 256, 1.0f, X("db4"), 0, st));
+      bn_bwd_stats("aspp0_BN", X("dconcat", 256), 512, X("concat", 256), 512, X("r0"), M1);
+      bn_bwd_stats("image_pooling_BN", X("db4"), 256, X("b4"), 256, X("r4"), B);
+      sync_bn_grads(1);
+      bn_bwd_apply("aspp0_BN", X("dconcat", 256), 512, X("concat", 256), 512, X("r0"), M1, X("g1_256"));
+      bn_bwd_apply("image_pooling_BN", X("db4"), 256, X("b4"), 256, X("r4"), B, X("dr4"));
+      conv_wgrad("aspp0", feat, Cin, X("g1_256"), 256, M1);
+      conv_dgrad("aspp0", X("g1_256"), 256, M1, X("dfeat"), Cin);
+      conv_wgrad("image_pooling", X("pool"), Cin, X("dr4"), 256, Bp);
+      conv_dgrad("image_pooling", X("dr4"), 256, Bp, X("dpool"), Cin);
+      call(dlv3p_train_bcast_rows(dev, X("dpool"), B, npix1, Cin, 1.0f / npix1, X("dfeat"), Cin, 1, st));
+      (void)skip; (void)M2; (void)Cs; (void)hs; (void)ws;
+      return;
+    }
     // ---------------- ASPP_block (layers.py:114-163) + the decoder's skip projection (:209-213), phase by phase
     call(dlv3p_train_rows_reduce(dev, feat, Cin, B, npix1, Cin, 1.0f / npix1, X("pool"), 0, st));
     conv_fwd("image_pooling", X("pool"), Cin, Bp, X("r4"), 256);
@@ -420,9 +477,10 @@ int dlv3p_trainer_create(const dlv3p_trainer_config* cfg, int device, dlv3p_trai
   t->B = g.B; t->H = g.H; t->W = g.W; t->OS = g.OS; t->Cin = g.Cin; t->Cs = g.Cskip; t->NC = g.NC;
   t->NCp = static_cast<int>(rup(g.NC, 8)); t->Bp = static_cast<int>(rup(g.B, 8));
   t->h = ceil_div(g.H, g.OS); t->w = ceil_div(g.W, g.OS); t->hs = ceil_div(g.H, 4); t->ws = ceil_div(g.W, 4);
+  if (g.lite) { t->hs = t->h; t->ws = t->w; t->Cs = 0; }      // no decoder: the classifier works at the feature resolution, there is no skip input
   t->M1 = g.B * t->h * t->w; t->M2 = g.B * t->hs * t->ws;
   if (g.OS == 8) { t->rates[0] = 12; t->rates[1] = 24; t->rates[2] = 36; } else if (g.OS == 32) { t->rates[0] = 3; t->rates[1] = 6; t->rates[2] = 9; }
-  if (g.Cin % 8 || g.Cskip % 8 || g.Cin < 8 || g.Cskip < 8 || t->M1 % 8 || t->M2 % 8) {
+  if (g.Cin % 8 || g.Cin < 8 || (!g.lite && (g.Cskip % 8 || g.Cskip < 8)) || t->M1 % 8 || t->M2 % 8) {
     t->err = "trainer: Cin, Cskip and the pixel counts per replica must be multiples of 8";
     return bail(DLV3P_ERR_INVALID);
   }
@@ -467,8 +525,15 @@ int dlv3p_trainer_create(const dlv3p_trainer_config* cfg, int device, dlv3p_trai
       {"g1_256", M1 * 256, 2}, {"db4", Bp * 256, 2}, {"dr4", Bp * 256, 2}, {"dpool", Bp * Cin, 2}, {"partial", t->partial_floats, 4},
       {"scratch", dlv3p_train_scratch_bytes(static_cast<int>(maxC)) / 4 + 64, 4}, {"bn_scratch", dlv3p_op_bn_scratch_bytes(static_cast<int>(maxC)) / 4 + 64, 4},
       {"loss_scratch", dlv3p_train_loss_scratch_bytes() / 4 + 16, 4}};
-  for (const BS& b : bufs)
-    if ((r = tr_buf(t, b.n, b.e, b.sz))) return bail(r);
+  // buffers the lite variant (ASPP_Lite_block, no decoder) never touches stay one element long
+  static const char* const kFullOnly[] = {"d1", "a1", "p1", "d2", "a2", "p2", "d3", "a3", "p3", "dcat", "rs", "c0d", "c0a", "c0p", "y0", "c1d", "c1a", "c1p", "y1",
+                                          "g256a", "g256b", "g256c", "g304a", "g304b", "drs", "dskip", "gB", "gp1", "ga1", "gp2", "ga2", "gp3", "ga3", "dfeat_tmp"};
+  for (const BS& b : bufs) {
+    bool unused = false;
+    if (g.lite)
+      for (const char* n : kFullOnly) unused = unused || !strcmp(n, b.n);
+    if ((r = tr_buf(t, b.n, unused ? 1 : b.e, b.sz))) return bail(r);
+  }
   {
     std::vector<float> ones(std::max(t->NC, 1), 1.0f), var1(t->nbn, 1.0f);
     cudaMemcpy(t->T.at("class_w"), ones.data(), ones.size() * 4, cudaMemcpyHostToDevice);
@@ -589,7 +654,7 @@ static int trainer_inputs(dlv3p_trainer* t, const void* d_feat, const void* d_sk
   CU_TRY(nullptr, cudaEventRecord(t->ev_in, user));            // the caller's stream produced the inputs
   CU_TRY(nullptr, cudaStreamWaitEvent(t->stream, t->ev_in, 0));
   CU_TRY(nullptr, cudaMemcpyAsync(t->feat_s, d_feat, t->feat_bytes, cudaMemcpyDeviceToDevice, t->stream));
-  CU_TRY(nullptr, cudaMemcpyAsync(t->skip_s, d_skip, t->skip_bytes, cudaMemcpyDeviceToDevice, t->stream));
+  if (t->skip_bytes) CU_TRY(nullptr, cudaMemcpyAsync(t->skip_s, d_skip, t->skip_bytes, cudaMemcpyDeviceToDevice, t->stream));
   CU_TRY(nullptr, cudaMemcpyAsync(t->labels_s, d_labels, t->labels_bytes, cudaMemcpyDeviceToDevice, t->stream));
   return DLV3P_OK;
 }
@@ -601,7 +666,7 @@ static int trainer_done(dlv3p_trainer* t, cudaStream_t user) {
 
 // Piecewise entry points (parity tests): forward + loss + backward | gradient exchange | optimizer step.  Eager launches.
 int dlv3p_trainer_forward_backward(dlv3p_trainer* t, const void* d_feat, const void* d_skip, const void* d_labels, void* cuda_stream) {
-  if (!t || !d_feat || !d_skip || !d_labels) return tfail(t, DLV3P_ERR_INVALID, "null argument");
+  if (!t || !d_feat || (!d_skip && !t->cfg.lite) || !d_labels) return tfail(t, DLV3P_ERR_INVALID, "null argument");
   cudaStream_t user = static_cast<cudaStream_t>(cuda_stream);
   int r = trainer_inputs(t, d_feat, d_skip, d_labels, user);
   if (r) return tfail(t, r, g_tls_error);
@@ -630,7 +695,7 @@ int dlv3p_trainer_apply_gradients(dlv3p_trainer* t, void* cuda_stream) {
 // the whole step — kernels, the peer-memory exchanges, the seed / epoch increments — into ONE CUDA graph that later calls replay
 // (the step is launch bound otherwise).  Inputs are copied into static buffers the graph reads.  Asynchronous.
 int dlv3p_trainer_step(dlv3p_trainer* t, const void* d_feat, const void* d_skip, const void* d_labels, int use_graph, void* cuda_stream) {
-  if (!t || !d_feat || !d_skip || !d_labels) return tfail(t, DLV3P_ERR_INVALID, "null argument");
+  if (!t || !d_feat || (!d_skip && !t->cfg.lite) || !d_labels) return tfail(t, DLV3P_ERR_INVALID, "null argument");
   cudaStream_t user = static_cast<cudaStream_t>(cuda_stream);
   int r = trainer_inputs(t, d_feat, d_skip, d_labels, user);
   if (r) return tfail(t, r, g_tls_error);

@@ -15,7 +15,8 @@ all-reduce of the flat fp32 gradient bucket — run inside the library over NVLi
 only job is to hand the replicas' 64-byte CUDA-IPC handles around once (`exchange_handles`, any channel: torch.distributed if the
 program already runs it, MPI, a file).
 
-Scope: the full head (ASPP_block + Decoder_block + tail) — the Xception / ResNet50 / MobileNetV2 non-lite models.
+Scope: both head variants of the reference — ASPP_block + Decoder_block + tail (the Xception / ResNet50 / MobileNetV2 / V3 models) and,
+with lite=True, ASPP_Lite_block + tail without a decoder (the *_lite models, deeplabv3p_mobilenetv2.py:326-331; no skip input).
 """
 from __future__ import annotations
 
@@ -47,9 +48,12 @@ class TrainLayout:
     every BN layer's SyncBN vector lives, and which contiguous spans each collective of the step exchanges.  The world_size-2 gloo
     test on CPU (tests/test_dist_cpu.py) drives exactly these spans."""
 
-    def __init__(self, Cin: int, Cskip: int, NC: int):
-        self.Cin, self.Cs, self.NC = Cin, Cskip, NC
+    def __init__(self, Cin: int, Cskip: int, NC: int, lite: bool = False):
+        self.Cin, self.Cs, self.NC, self.lite = Cin, (0 if lite else Cskip), NC, bool(lite)
         self.NCp = _rup(NC, 8)
+        if self.lite:      # ASPP_Lite_block (layers.py:166-196): image pooling + one 1x1 branch, no depthwise convolutions, no decoder
+            self.FWD_GROUPS = [['image_pooling_BN', 'aspp0_BN'], ['concat_projection_BN']]
+            self.BWD_GROUPS = [['concat_projection_BN'], ['aspp0_BN', 'image_pooling_BN']]
         self._layout_params()
 
     def stats_span(self, group) -> Tuple[int, int]:
@@ -69,16 +73,22 @@ class TrainLayout:
     # ------------------------------------------------------------------------------------------------ parameters
     def _conv_specs(self):
         Cin, Cs, NCp = self.Cin, self.Cs, self.NCp
+        if self.lite:
+            return [('image_pooling', Cin, 256), ('aspp0', Cin, 256), ('concat_projection', 512, 256), ('conv_upsample', 256, NCp)]
         return [('image_pooling', Cin, 256), ('aspp0', Cin, 256), ('aspp1_pointwise', Cin, 256), ('aspp2_pointwise', Cin, 256),
                 ('aspp3_pointwise', Cin, 256), ('concat_projection', 1280, 256), ('feature_projection0', Cs, 48),
                 ('decoder_conv0_pointwise', 304, 256), ('decoder_conv1_pointwise', 256, 256), ('conv_upsample', 256, NCp)]
 
     def _dw_specs(self):
+        if self.lite:
+            return []
         return [('aspp1_depthwise', self.Cin), ('aspp2_depthwise', self.Cin), ('aspp3_depthwise', self.Cin),
                 ('decoder_conv0_depthwise', 304), ('decoder_conv1_depthwise', 256)]
 
     def _bn_specs(self):
         Cin = self.Cin
+        if self.lite:
+            return [('image_pooling_BN', 256), ('aspp0_BN', 256), ('concat_projection_BN', 256)]
         return [('image_pooling_BN', 256), ('aspp0_BN', 256),
                 ('aspp1_depthwise_BN', Cin), ('aspp1_pointwise_BN', 256), ('aspp2_depthwise_BN', Cin), ('aspp2_pointwise_BN', 256),
                 ('aspp3_depthwise_BN', Cin), ('aspp3_pointwise_BN', 256), ('concat_projection_BN', 256), ('feature_projection0_BN', 48),
@@ -185,18 +195,18 @@ class HeadTrainer(TrainLayout):
                  eps: float = 1e-5, dropout: float = 0.5, seed: int = 0, ignore_index: int = 255, global_batch: Optional[int] = None,
                  process_group=None, graph: bool = True, loss: str = 'crossentropy', class_weights=None,
                  focal_gamma: float = 2.0, focal_alpha: float = 0.25, world: Optional[int] = None, rank: Optional[int] = None,
-                 exchange_handles: Optional[Callable[[bytes], Sequence[bytes]]] = None, stream: int = 0, **_ignored):
+                 exchange_handles: Optional[Callable[[bytes], Sequence[bytes]]] = None, stream: int = 0, lite: bool = False, **_ignored):
         self.lib = tf_.lib()
         if ffi.device_count() == 0:
             raise ffi.Dlv3pError(-2, 'HeadTrainer needs a CUDA device: there is no CPU path')
         self.rates = atrous_rates(OS)
         self.B, self.H, self.W, self.OS, self.Cin, self.Cs, self.NC = B, H, W, OS, Cin, Cskip, NC
         self.h, self.w = -(-H // OS), -(-W // OS)
-        self.hs, self.ws = -(-H // 4), -(-W // 4)
+        self.hs, self.ws = (self.h, self.w) if lite else (-(-H // 4), -(-W // 4))      # lite: no decoder, logits at the feature resolution
         self.M1, self.M2 = B * self.h * self.w, B * self.hs * self.ws
-        if Cin % 8 or Cskip % 8 or self.M1 % 8 or self.M2 % 8:
+        if Cin % 8 or (not lite and Cskip % 8) or self.M1 % 8 or self.M2 % 8:
             raise ffi.Dlv3pError(-1, 'HeadTrainer: Cin, Cskip and the pixel counts per replica must be multiples of 8')
-        TrainLayout.__init__(self, Cin, Cskip, NC)
+        TrainLayout.__init__(self, Cin, Cskip, NC, lite)
         # train.py:114-138: --loss crossentropy (optionally class weighted, --weighted_type balanced) | focal (ignores the weights)
         if loss not in ('crossentropy', 'focal'):
             raise ValueError('invalid loss type {}'.format(loss))
@@ -224,7 +234,7 @@ class HeadTrainer(TrainLayout):
         cfg = tf_.TrainerConfig(B=B, H=H, W=W, OS=OS, Cin=Cin, Cskip=Cskip, NC=NC, world=self.world, rank=self.rank, global_batch=self.global_batch,
                                 ignore_index=ignore_index, loss_kind=2 if loss == 'focal' else (1 if cw is not None else 0), seed=seed & 0xFFFFFFFF,
                                 lr=lr, momentum=momentum, l2=l2, bn_momentum=bn_momentum, eps=eps, dropout=dropout, focal_gamma=focal_gamma,
-                                focal_alpha=focal_alpha)
+                                focal_alpha=focal_alpha, lite=int(bool(lite)))
         self._hyper = [lr, momentum, l2]
         h = C.c_void_p()
         buf = C.create_string_buffer(64)
@@ -315,7 +325,7 @@ class HeadTrainer(TrainLayout):
         """feat bf16 [B,h,w,Cin], skip bf16 [B,hs,ws,Cs], labels uint8 [B,H,W] (device memory).  Leaves this replica's share of the
         global mean loss, all weight gradients (BN gradients global, the rest per replica until all_reduce_gradients) and
         d(loss)/d(feat), d(loss)/d(skip) in the buffers 'dfeat' / 'dskip'."""
-        self._check(self.lib.dlv3p_trainer_forward_backward(self.handle, _ptr(feat), _ptr(skip), _ptr(labels), self.stream))
+        self._check(self.lib.dlv3p_trainer_forward_backward(self.handle, _ptr(feat), 0 if self.lite else _ptr(skip), _ptr(labels), self.stream))
 
     def all_reduce_gradients(self) -> None:
         """ONE exchange of the flat fp32 bucket holding every 1x1 kernel, the classifier bias and every depthwise kernel
@@ -330,7 +340,7 @@ class HeadTrainer(TrainLayout):
         """One optimizer step (fit's train_step): forward, loss, backward, gradient exchange, SGD update.  Asynchronous; read the
         loss with .loss() (synchronises).  The first call launches the ~190 kernels one by one; with graph=True the second call
         captures the whole step into ONE CUDA graph inside the library that later calls replay."""
-        self._check(self.lib.dlv3p_trainer_step(self.handle, _ptr(feat), _ptr(skip), _ptr(labels), int(self.use_graph), self.stream))
+        self._check(self.lib.dlv3p_trainer_step(self.handle, _ptr(feat), 0 if self.lite else _ptr(skip), _ptr(labels), int(self.use_graph), self.stream))
 
     def loss(self) -> float:
         """Global mean loss of the last step (synchronises)."""
@@ -341,7 +351,7 @@ class HeadTrainer(TrainLayout):
     def tensor(self, name: str) -> np.ndarray:
         """A named activation / gradient buffer as fp32 numpy ('dfeat' [B*h*w, Cin], 'dskip' [B*hs*ws, Cskip], 'logits' [B*hs*ws, NCp])."""
         shapes = {'dfeat': (self.M1, self.Cin), 'dskip': (self.M2, self.Cs), 'logits': (self.M2, self.NCp), 'yproj': (self.M1, 256),
-                  'y0': (self.M2, 256), 'y1': (self.M2, 256), 'dlow': (self.M2, self.NCp), 'concat': (self.M1, 1280)}
+                  'y0': (self.M2, 256), 'y1': (self.M2, 256), 'dlow': (self.M2, self.NCp), 'concat': (self.M1, 512 if self.lite else 1280)}
         a = np.empty(shapes[name], np.float32)
         self._check(self.lib.dlv3p_trainer_read(self.handle, name.encode(), a.ctypes.data_as(C.POINTER(C.c_float)), a.size))
         return a

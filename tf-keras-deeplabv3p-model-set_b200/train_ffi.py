@@ -65,7 +65,7 @@ SYMBOLS = [
 class TrainerConfig(C.Structure):
     """dlv3p_trainer_config (include/dlv3p_train.h)."""
     _fields_ = [(n, C.c_int32) for n in ('B', 'H', 'W', 'OS', 'Cin', 'Cskip', 'NC', 'world', 'rank', 'global_batch', 'ignore_index', 'loss_kind')] + \
-               [('seed', C.c_uint32)] + [(n, C.c_float) for n in ('lr', 'momentum', 'l2', 'bn_momentum', 'eps', 'dropout', 'focal_gamma', 'focal_alpha')]
+               [('seed', C.c_uint32)] + [(n, C.c_float) for n in ('lr', 'momentum', 'l2', 'bn_momentum', 'eps', 'dropout', 'focal_gamma', 'focal_alpha')] + [('lite', C.c_int32)]
 
 _typed = False
 
