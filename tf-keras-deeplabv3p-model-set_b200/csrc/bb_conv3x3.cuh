@@ -19,28 +19,31 @@
 namespace dlv3p {
 
 constexpr int kC3Threads = 192;
-constexpr int kC3Stages = 16;
-constexpr int kC3AStageBytes = 128 * 64;            // 128 pixels x 32 channels bf16
+constexpr int kC3TH = 16, kC3TW = 8;                // output tile: 16 rows of 8 pixels = the 16 eight-row atoms of the M = 128 operand
+constexpr int kC3HaloW = kC3TW + 2, kC3HaloH = kC3TH + 2;
+constexpr int kC3Stages = 8;
+constexpr int kC3HaloBytes = kC3HaloH * kC3HaloW * 64;             // 18 x 10 pixels x 32 channels bf16 = 11520
+constexpr int kC3AStageBytes = (kC3HaloBytes + 511) / 512 * 512;   // stages start on the 64-byte swizzle's 512-byte pattern
 constexpr int kC3WTapBytes = 64 * 64;               // 64 output channels x 32 input channels bf16
 constexpr int kC3WBytes = 9 * kC3WTapBytes;
 constexpr int kC3StoreBytes = 4 * 2 * 4096;         // 4 epilogue warps x 2 buffers x [32 pixels x 128 B]
 constexpr int kC3SmemBytes = 1024 + kC3WBytes + kC3Stages * kC3AStageBytes + kC3StoreBytes + 256;
 
 struct Conv3x3Params {
-  const CUtensorMap* tmap_x;    // 4D {32, W, H, B} bf16, box {32, 16, 8, 1}, SWIZZLE_64B, OOB -> 0
+  const CUtensorMap* tmap_x;    // 4D {32, W, H, B} bf16, box {32, 10, 18, 1} (tile + halo), SWIZZLE_64B, OOB -> 0
   const CUtensorMap* tmap_w;    // 2D [9 * 64 rows (tap, cout)][32 cin] bf16, box {32, 64}, SWIZZLE_64B
-  const CUtensorMap* tmap_out;  // 4D {64, W, H, B} bf16, box {64, 16, 2, 1}, SWIZZLE_128B
+  const CUtensorMap* tmap_out;  // 4D {64, W, H, B} bf16, box {64, 8, 4, 1}, SWIZZLE_128B
   float scale[64];              // folded BN, constant bank
   float shift[64];
   int tiles_x, tiles_y, num_tiles;
 };
 
-// K-major operand tile of 64-byte rows under the 64-byte swizzle: 8-row atoms 512 bytes apart
-__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr_bytes) {
+// K-major operand tile of 64-byte rows under the 64-byte swizzle: 8-row atoms `atom_stride` bytes apart (512: a dense tile)
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr_bytes, uint32_t atom_stride = 512) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr_bytes >> 4) & 0x3FFF);
   d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(atom_stride >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(4) << 61;                   // SWIZZLE_64B
   return d;
@@ -96,12 +99,10 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3x3_c32_kernel(const __grid
         const int b = tile / tiles_per_img;
         const int t2 = tile - b * tiles_per_img;
         const int ty = t2 / P.tiles_x, tx = t2 - ty * P.tiles_x;
-        for (int t = 0; t < 9; ++t) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], kC3AStageBytes);
-          tma_load_4d(smem_a + stage * kC3AStageBytes, P.tmap_x, &full_bar[stage], 0, tx * 16 + (t % 3) - 1, ty * 8 + (t / 3) - 1, b, kEvictNormal);
-          if (++stage == kC3Stages) { stage = 0; phase ^= 1; }
-        }
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], kC3HaloBytes);
+        tma_load_4d(smem_a + stage * kC3AStageBytes, P.tmap_x, &full_bar[stage], 0, tx * kC3TW - 1, ty * kC3TH - 1, b, kEvictNormal);
+        if (++stage == kC3Stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -114,21 +115,26 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3x3_c32_kernel(const __grid
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + acc * 64;
-      for (int t = 0; t < 9; ++t) {
-        mbar_wait(&full_bar[stage], phase);
-        tcgen05_fence_after();
-        if (elect_one()) {
-          const uint64_t da = make_smem_desc_sw64(smem_u32(smem_a + stage * kC3AStageBytes));
+      mbar_wait(&full_bar[stage], phase);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        // tap (ky, kx) reads the halo tile shifted by ky rows and kx pixels: atom y of the operand = the 8 pixels of halo row y + ky from
+        // pixel kx on, 512 contiguous bytes, atoms one halo row (640 bytes) apart.  TMA and UMMA apply the 64-byte swizzle to the same
+        // absolute shared-memory address bits, so a start address that is not a multiple of the pattern needs nothing else.
+        const uint32_t a0 = smem_u32(smem_a + stage * kC3AStageBytes);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const uint64_t da = make_smem_desc_sw64(a0 + ((t / 3) * kC3HaloW + (t % 3)) * 64, kC3HaloW * 64);
           const uint64_t db = make_smem_desc_sw64(smem_u32(smem_w + t * kC3WTapBytes));
 #pragma unroll
           for (int k = 0; k < 2; ++k)
             umma_bf16_ss(tmem_d, smem_desc_advance(da, k * 32), smem_desc_advance(db, k * 32), idesc, (t > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
-          if (t == 8) umma_commit(&tmem_full[acc]);
         }
-        __syncwarp();
-        if (++stage == kC3Stages) { stage = 0; phase ^= 1; }
+        umma_commit(&empty_bar[stage]);
+        umma_commit(&tmem_full[acc]);
       }
+      __syncwarp();
+      if (++stage == kC3Stages) { stage = 0; phase ^= 1; }
     }
   } else {
     const int q = warp & 3;
@@ -174,7 +180,7 @@ __global__ void __launch_bounds__(kC3Threads, 1) conv3x3_c32_kernel(const __grid
       if (lane == 0) {
         asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
                          reinterpret_cast<uint64_t>(P.tmap_out)),
-                     "r"(smem_u32(my_o + store_buf * 4096)), "r"(0), "r"(tx * 16), "r"(ty * 8 + 2 * q), "r"(b)
+                     "r"(smem_u32(my_o + store_buf * 4096)), "r"(0), "r"(tx * kC3TW), "r"(ty * kC3TH + 4 * q), "r"(b)
                      : "memory");
         tma_store_commit();
       }

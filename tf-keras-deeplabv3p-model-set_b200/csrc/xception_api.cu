@@ -981,9 +981,9 @@ int dlv3p_model_finalize_weights(dlv3p_model* m) {
       const Tensor& ti = m->tensors[o.in];
       const Tensor& to = m->tensors[o.out];
       o.tm0 = slot(); slot(); slot();
-      ok = ok && tm_nhwc(&m->h_tm[o.tm0], ti.p, ti.B, ti.H, ti.W, 32, 32, 16, 8, CU_TENSOR_MAP_SWIZZLE_64B, &terr);
+      ok = ok && tm_nhwc(&m->h_tm[o.tm0], ti.p, ti.B, ti.H, ti.W, 32, 32, kC3HaloW, kC3HaloH, CU_TENSOR_MAP_SWIZZLE_64B, &terr);
       ok = ok && tm_2d(&m->h_tm[o.tm0 + 1], o.w16, 9 * 64, 32, 32, 32, 64, CU_TENSOR_MAP_SWIZZLE_64B, &terr);
-      ok = ok && tm_nhwc(&m->h_tm[o.tm0 + 2], to.p, to.B, to.H, to.W, 64, 64, 16, 2, CU_TENSOR_MAP_SWIZZLE_128B, &terr);
+      ok = ok && tm_nhwc(&m->h_tm[o.tm0 + 2], to.p, to.B, to.H, to.W, 64, 64, kC3TW, 4, CU_TENSOR_MAP_SWIZZLE_128B, &terr);
     } else if (o.kind == OP_DW) {
       Fold f = mfold(m, o.bn, o.K);
       if ((r = m_upload(m, &o.wf, pack_taps(MW(m, o.name, "depthwise_kernel"), f.scale.data(), o.K, o.Cpad)))) return r;
@@ -1108,7 +1108,7 @@ static int run_backbone(dlv3p_model* m, const void* d_images, cudaStream_t st, i
       P.tmap_x = &m->d_tm[o.tm0]; P.tmap_w = &m->d_tm[o.tm0 + 1]; P.tmap_out = &m->d_tm[o.tm0 + 2];
       std::memcpy(P.scale, o.h_scale.data(), sizeof(P.scale));
       std::memcpy(P.shift, o.h_shift.data(), sizeof(P.shift));
-      P.tiles_x = cdiv(to.W, 16); P.tiles_y = cdiv(to.H, 8); P.num_tiles = to.B * P.tiles_x * P.tiles_y;
+      P.tiles_x = cdiv(to.W, kC3TW); P.tiles_y = cdiv(to.H, kC3TH); P.num_tiles = to.B * P.tiles_x * P.tiles_y;
       e = launch_conv3x3(P, m->num_sms, st);
     } else if (o.kind == OP_DW) {
       const Tensor& to = m->tensors[o.out];
@@ -1539,14 +1539,14 @@ int dlv3p_op_conv3x3_c32(int device, const void* x, int B, int H, int W, const f
   uint16_t* dw = tmp.put(pack_c3(w_hwio));
   std::string terr;
   std::vector<CUtensorMap> tm(3);
-  if (!tm_nhwc(&tm[0], x, B, H, W, 32, 32, 16, 8, CU_TENSOR_MAP_SWIZZLE_64B, &terr) || !tm_2d(&tm[1], dw, 9 * 64, 32, 32, 32, 64, CU_TENSOR_MAP_SWIZZLE_64B, &terr) ||
-      !tm_nhwc(&tm[2], out, B, H, W, 64, 64, 16, 2, CU_TENSOR_MAP_SWIZZLE_128B, &terr)) return mfail(nullptr, DLV3P_ERR_CUDA, terr);
+  if (!tm_nhwc(&tm[0], x, B, H, W, 32, 32, kC3HaloW, kC3HaloH, CU_TENSOR_MAP_SWIZZLE_64B, &terr) || !tm_2d(&tm[1], dw, 9 * 64, 32, 32, 32, 64, CU_TENSOR_MAP_SWIZZLE_64B, &terr) ||
+      !tm_nhwc(&tm[2], out, B, H, W, 64, 64, kC3TW, 4, CU_TENSOR_MAP_SWIZZLE_128B, &terr)) return mfail(nullptr, DLV3P_ERR_CUDA, terr);
   CUtensorMap* dtm = tmp.put(tm);
   if (!dw || !dtm) return mfail(nullptr, DLV3P_ERR_NOMEM, "op_conv3x3_c32: cudaMalloc failed");
   Conv3x3Params P{};
   P.tmap_x = &dtm[0]; P.tmap_w = &dtm[1]; P.tmap_out = &dtm[2];
   for (int i = 0; i < 64; ++i) { P.scale[i] = scale ? scale[i] : 1.0f; P.shift[i] = shift ? shift[i] : 0.0f; }
-  P.tiles_x = cdiv(W, 16); P.tiles_y = cdiv(H, 8); P.num_tiles = B * P.tiles_x * P.tiles_y;
+  P.tiles_x = cdiv(W, kC3TW); P.tiles_y = cdiv(H, kC3TH); P.num_tiles = B * P.tiles_x * P.tiles_y;
   MCU(nullptr, launch_conv3x3(P, sms, st));
   MCU(nullptr, cudaStreamSynchronize(st));
   return DLV3P_OK;
