@@ -49,6 +49,10 @@ struct BbGemmParams {
   int relu;
   int m_pairs, n_tiles;
   int debug;                     // benchmark aid: bit0 = skip the stores
+  // strided A (the 1x1 stride-2 shortcut convolutions, _conv2d_same with kernel_size 1: deeplabv3p_xception.py:44-52): tmap_a is a 4D map
+  // {K, Wo, Ho, B} over every second pixel of every second row of the block input, box {64, min(Wo, 128), 128 / min(Wo, 128), 1}: an M tile
+  // of 128 consecutive output pixels is whole rows (or a piece of one) of one image.  a_wo = Wo (0: plain [M, K] operand), a_hw = Ho * Wo.
+  int a_wo, a_hw;
 };
 
 template <int BN, bool kRes>
@@ -115,7 +119,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBbThreads, 1) bb_ge
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
           else mbar_arrive_cluster(&full_bar[stage], 0);
-          tma_load_2d_2sm(smem_a + stage * (kBbBM * 128), P.tmap_a, &full_bar[stage], kb * kBbBK, tile * kBbBM, kEvictNormal);
+          if (P.a_wo) {
+            const int pix = tile * kBbBM, img = pix / P.a_hw, rem = pix - img * P.a_hw, y0 = rem / P.a_wo;
+            tma_load_4d_2sm(smem_a + stage * (kBbBM * 128), P.tmap_a, &full_bar[stage], kb * kBbBK, rem - y0 * P.a_wo, y0, img, kEvictNormal);
+          } else {
+            tma_load_2d_2sm(smem_a + stage * (kBbBM * 128), P.tmap_a, &full_bar[stage], kb * kBbBK, tile * kBbBM, kEvictNormal);
+          }
           tma_load_2d_2sm(smem_b + stage * ((BN / 2) * 128), P.tmap_w, &full_bar[stage], kb * kBbBK, nt * BN + static_cast<int>(rank) * (BN / 2), kEvictLast);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }

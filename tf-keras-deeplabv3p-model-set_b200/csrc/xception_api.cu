@@ -326,6 +326,7 @@ struct Op {
   std::string prefix;    // OP_SEP: the SepConv_BN prefix (<prefix>_depthwise / _depthwise_BN / _pointwise / _pointwise_BN)
   int in = -1, out = -1, res = -1;   // tensor indices
   int stride = 1, rate = 1, relu_in = 0, relu_out = 0;
+  int a_stride = 1;      // OP_PW: 2 = the A operand is every second pixel of every second row of `in` (strided tensor map, no sampling kernel)
   int K = 0, N = 0, Kpad = 0, Npad = 0, Cpad = 0, BN = 256;
   DwVariant dv{1, 1, 8, 32};
   // device weights
@@ -493,7 +494,10 @@ int build_plan(dlv3p_model* m) {
     int res = b.shortcut == 1 ? x : -1;
     if (b.shortcut == 0) {
       int src = x;
-      if (b.stride == 2) {
+      // stride 2: the GEMM reads the sampled pixels itself through a strided tensor map when its 128-pixel M tiles are whole rows (or a
+      // piece of one row) of one image; otherwise a sampling kernel makes the dense operand first
+      const bool strided_a = b.stride == 2 && (ho * wo) % 128 == 0 && (wo % 128 == 0 || 128 % wo == 0) && !(g.flags & 1);
+      if (b.stride == 2 && !strided_a) {
         src = new_tensor(m, B, ho, wo, cin);
         Op s; s.kind = OP_SUB; s.name = b.prefix + "_shortcut_sample"; s.in = x; s.out = src;
         s.bytes = 2.0 * B * ho * wo * cin * 2;
@@ -501,6 +505,7 @@ int build_plan(dlv3p_model* m) {
       }
       res = new_tensor(m, B, ho, wo, b.depth[2]);
       Op q; q.kind = OP_PW; q.name = b.prefix + "_shortcut"; q.bn = b.prefix + "_shortcut_BN"; q.in = src; q.out = res; q.K = cin; q.N = b.depth[2];
+      q.a_stride = strided_a ? 2 : 1;
       q.flops = 2.0 * B * ho * wo * static_cast<double>(cin) * b.depth[2]; q.bytes = 2.0 * B * ho * wo * (cin + b.depth[2]);
       seq.push_back(q);
     }
@@ -1043,7 +1048,15 @@ int dlv3p_model_finalize_weights(dlv3p_model* m) {
       const Tensor& ti = m->tensors[o.in];
       const Tensor& to = m->tensors[o.out];
       o.tm0 = slot(); slot(); slot(); slot();
-      ok = ok && tm_2d(&m->h_tm[o.tm0], ti.p, ti.M(), o.K, o.K, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B, &terr);
+      if (o.a_stride == 2) {
+        const uint64_t C = ti.C, bw = to.W < 128 ? to.W : 128;
+        const uint64_t d[4] = {C, static_cast<uint64_t>(to.W), static_cast<uint64_t>(to.H), static_cast<uint64_t>(ti.B)};
+        const uint64_t sb[3] = {2 * C * 2, 2 * static_cast<uint64_t>(ti.W) * C * 2, static_cast<uint64_t>(ti.H) * ti.W * C * 2};
+        const uint32_t bx[4] = {64, static_cast<uint32_t>(bw), static_cast<uint32_t>(128 / bw), 1};
+        ok = ok && tm_encode(&m->h_tm[o.tm0], ti.p, 4, d, sb, bx, CU_TENSOR_MAP_SWIZZLE_128B, &terr);
+      } else {
+        ok = ok && tm_2d(&m->h_tm[o.tm0], ti.p, ti.M(), o.K, o.K, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B, &terr);
+      }
       ok = ok && tm_2d(&m->h_tm[o.tm0 + 1], o.w16, o.Npad, o.Kpad, o.Kpad, 64, o.BN / 2, CU_TENSOR_MAP_SWIZZLE_128B, &terr);
       ok = ok && tm_2d(&m->h_tm[o.tm0 + 2], to.p, to.M(), o.N, o.N, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B, &terr);
       if (o.res >= 0) ok = ok && tm_2d(&m->h_tm[o.tm0 + 3], m->tensors[o.res].p, to.M(), o.N, o.N, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B, &terr);
@@ -1141,6 +1154,7 @@ static int run_backbone(dlv3p_model* m, const void* d_images, cudaStream_t st, i
       P.tmap_a = &m->d_tm[o.tm0]; P.tmap_w = &m->d_tm[o.tm0 + 1]; P.tmap_out = &m->d_tm[o.tm0 + 2];
       P.scale = o.scale; P.shift = o.shift; P.tmap_res = o.res >= 0 ? &m->d_tm[o.tm0 + 3] : nullptr;
       P.M = to.M(); P.K = o.K; P.N = o.N; P.relu = o.relu_out; P.m_pairs = cdiv(cdiv(P.M, kBbBM), 2); P.n_tiles = o.Npad / o.BN;
+      if (o.a_stride == 2) { P.a_wo = to.W; P.a_hw = to.H * to.W; }
       e = launch_bb_gemm(o.BN, P, m->num_sms, st);
     } else {
       const Tensor& ti = m->tensors[o.in];
