@@ -72,14 +72,14 @@ NCU_DRAM_MB_PER_LAUNCH_B32 = {
 
 # DRAM traffic per step (dram__bytes_read.sum + dram__bytes_write.sum summed over a kernel function's launches, bytes) from one
 # `ncu --set full` capture of this command at batch 32; filled in from profiles/ once captured
-NCU_TRAFFIC = {   # profiles/r02l_ncu_per_kernel_dram_and_time.txt (every template variant of a function summed over one step)
-    'bb_gemm_kernel': (1807.2 + 1642.8 + 499.0 + 270.7 + 268.5 + 67.1 + 261.2 + 277.8 + 404.1 + 63.7 + 96.8 + 70.6) * 1e6,
-    'bb_depthwise_kernel': (2718.3 + 996.4 + 270.1 + 205.1 + 187.8 + 117.6) * 1e6,
-    'bb_sepconv_kernel': (537.0 + 268.5 + 268.6 + 134.3 + 488.8 + 480.3 + 218.2 + 210.7) * 1e6,
-    'conv3x3_c32_kernel': (134.3 + 209.3) * 1e6,
-    'stem_conv_kernel': (25.2 + 71.4) * 1e6,
+NCU_TRAFFIC = {   # profiles/r02w_ncu_per_kernel_dram_and_time.txt (every template variant of a function summed over one step, MB)
+    'bb_gemm_kernel': 5766.3 * 1e6,
+    'bb_depthwise_kernel': 4498.7 * 1e6,
+    'bb_sepconv_kernel': 2607.2 * 1e6,
+    'conv3x3_c32_kernel': 340.6 * 1e6,
+    'stem_conv_kernel': 97.7 * 1e6,
 }
-NCU_TRAFFIC_NOTE = 'bytes per step (dram__bytes_read.sum + dram__bytes_write.sum over the function\'s launches of one forward, ncu, cold caches: profiles/r02l_ncu_per_kernel_dram_and_time.txt)'
+NCU_TRAFFIC_NOTE = 'bytes per step (dram__bytes_read.sum + dram__bytes_write.sum over the function\'s launches of one forward, ncu, cold caches: profiles/r02w_ncu_per_kernel_dram_and_time.txt)'
 
 # algorithmic HBM bytes per image of the fused SepConv kernels (read the input once, write the 256-channel output once)
 ALGO_BYTES_PER_IMG = {
