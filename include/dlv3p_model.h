@@ -40,6 +40,8 @@ enum { /* flags */
   DLV3P_MODEL_FLAG_UNFUSED_ENTRY = 4, /* measurement aid: the entry flow's SepConv_BN layers as depthwise kernel + GEMM (like the rest of the backbone) */
   DLV3P_MODEL_FLAG_FUSED_MIDDLE = 16, /* experiment (slower): the middle flow's SepConv_BN layers through the fused two-SM cluster kernel
                                     (bb_sepwide.cuh) instead of depthwise kernel + GEMM */
+  DLV3P_MODEL_FLAG_FP32_STEM = 32, /* measurement aid: entry_flow_conv1_1 on uint8 images through the fp32 CUDA-core kernel (the path float images
+                                    take) instead of the tensor-core kernel (bb_stem_tc.cuh) */
   DLV3P_MODEL_FLAG_FP32 = 8      /* PRECISION MODE: the whole model in plain fp32 arithmetic (the reference's default numerics, train.py:37-46):
                                     weights as given, fp32 activations, CUDA-core kernels (csrc/f32_kernels.cuh).  Held to 1e-4 relative
                                     against the fp32 oracle; a mode to prove results, not the performance path.  out_mode: labels or

@@ -160,11 +160,12 @@ def test_backbone_sepwide_fused_middle_flow(gpu, B, H, W, C, N, relu_in, relu_ou
 
 
 # ---------------------------------------------------------------------------------------------------- blocks and the whole backbone
-def _model_and_oracle(OS, H, W, B=2, seed=4321, NC=21, keep=True, out_mode=ffi.OUT_LABELS_U8, image_dtype=np.uint8, precision='bf16'):
+def _model_and_oracle(OS, H, W, B=2, seed=4321, NC=21, keep=True, out_mode=ffi.OUT_LABELS_U8, image_dtype=np.uint8, precision='bf16', flags=0):
     Wb = X.make_calibrated_weights(OS, seed, size=64)
     hcfg = R.HeadConfig(B=B, H=H, W=W, OS=OS, Cin=2048, Cskip=256, NC=NC)
     Wh = R.make_weights(hcfg, seed + 5)
-    m = dlv3p_b200.DeepLabV3PlusXception((H, W, 3), NC, OS, batch=B, out_mode=out_mode, image_dtype=image_dtype, keep_intermediates=keep, precision=precision)
+    m = dlv3p_b200.DeepLabV3PlusXception((H, W, 3), NC, OS, batch=B, out_mode=out_mode, image_dtype=image_dtype, keep_intermediates=keep, precision=precision,
+                                         flags=flags)
     allw = dict(Wb)
     allw.update(Wh)
     m.set_weights(allw)
@@ -245,7 +246,8 @@ def test_whole_model_labels_and_logits(gpu):
     # the head alone on the backbone's OWN features: the head's usual tolerances
     own = R.head_forward_torch(m.tap('feature'), m.tap('skip'), Wh, hcfg, 'bf16')
     assert rel_err(logits, own['logits'].numpy()) < 8e-3
-    assert (labels == own['labels'].numpy()).mean() >= 0.999
+    ov, dec, _ = label_agreement(labels, own['labels'].numpy(), own['logits_full'].numpy(), 1e-2)
+    assert dec >= 0.999 and ov >= 0.997, (ov, dec)      # random weights: the pixels that differ are near-ties (margin < 1 % of the logit range)
     m.close()
 
 
@@ -261,8 +263,14 @@ def test_whole_model_host_path_dtypes_determinism_batch_independence(gpu):
     assert np.array_equal(a, b) and np.array_equal(a, c)
     assert np.array_equal(a[:2], a[2:])                                  # batch independence
     assert m.model.launch_count() >= 130
+    # float images (already normalised) take the fp32 CUDA-core stem; uint8 images the tensor-core stem (bb_stem_tc.cuh), whose fp32 accumulation
+    # order differs: the same kernel on both (A/B flag) gives identical label maps, the two kernels agree except at near-ties
     mf, _, _, _ = _model_and_oracle(16, H, W, B=4, keep=False, image_dtype=np.float32)
-    assert np.array_equal(mf(R.normalize_image(img)), a)                # fp32 normalised input == uint8 input normalised on the device
+    af = mf(R.normalize_image(img))
+    m32s, _, _, _ = _model_and_oracle(16, H, W, B=4, keep=False, flags=ffi.MODEL_FLAG_FP32_STEM)
+    assert np.array_equal(af, m32s(img))                                 # fp32 normalised input == uint8 input normalised on the device
+    assert (af == a).mean() >= 0.97
+    mf.close(); m32s.close()
     m2, _, _, _ = _model_and_oracle(16, H, W, B=2, keep=False)
     assert np.array_equal(m2(img[:2]), a[:2])
     with pytest.raises(ValueError):

@@ -24,6 +24,7 @@
 #include "bb_kernels.cuh"
 #include "bb_sepconv.cuh"
 #include "bb_sepwide.cuh"
+#include "bb_stem_tc.cuh"
 #include "f32_kernels.cuh"
 
 using namespace dlv3p;
@@ -291,6 +292,62 @@ std::vector<float> pack_taps(const float* w_hwc, const float* scale, int C, int 
   for (int t = 0; t < 9; ++t)
     for (int c = 0; c < C; ++c) out[static_cast<size_t>(t) * Cpad + c] = w_hwc[static_cast<size_t>(t) * C + c] * (scale ? scale[c] : 1.0f);
   return out;
+}
+// entry_flow_conv1_1 for the tensor-core stem (bb_stem_tc.cuh): Keras kernel [3][3][3][32] fp32 -> three bf16 pieces of every weight (w0 + w1 + w2 == w
+// exactly), laid out [piece][s2d tap (ty, tx)][k chunk][32 cout][8 k] with k = (dy, dx, cin), conv tap (2 ty + dy, 2 tx + dx); and the per-tap channel
+// sums [9][32] + their total [32] the epilogue subtracts (conv(x / 127.5 - 1) = conv(x) / 127.5 - sum of the weights of the taps inside the image)
+float bf16_to_f32_host(uint16_t b) {
+  const uint32_t u = static_cast<uint32_t>(b) << 16;
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+std::vector<uint16_t> pack_stem_tc(const float* w) {
+  std::vector<uint16_t> out(static_cast<size_t>(3) * 4 * 2 * 32 * 8, 0);
+  for (int t = 0; t < 4; ++t)
+    for (int dy = 0; dy < 2; ++dy)
+      for (int dx = 0; dx < 2; ++dx) {
+        const int ky = 2 * (t >> 1) + dy, kx = 2 * (t & 1) + dx;
+        if (ky > 2 || kx > 2) continue;
+        for (int c = 0; c < 3; ++c)
+          for (int n = 0; n < 32; ++n) {
+            const int k = (dy * 2 + dx) * 3 + c;
+            float rem = w[((ky * 3 + kx) * 3 + c) * 32 + n];
+            for (int piece = 0; piece < 3; ++piece) {
+              const uint16_t b = bf16_rne(rem);
+              out[((((static_cast<size_t>(piece) * 4 + t) * 2 + (k >> 3)) * 32 + n) * 8) + (k & 7)] = b;
+              rem -= bf16_to_f32_host(b);      // exact: the difference of a float and its bf16 rounding is a float
+            }
+          }
+      }
+  return out;
+}
+std::vector<float> stem_tap_sums(const float* w) {
+  std::vector<float> out(10 * 32, 0.0f);
+  for (int n = 0; n < 32; ++n) {
+    double tot = 0.0;
+    for (int t = 0; t < 9; ++t) {
+      double s = 0.0;
+      for (int c = 0; c < 3; ++c) s += w[(t * 3 + c) * 32 + n];
+      out[t * 32 + n] = static_cast<float>(s);
+      tot += s;
+    }
+    out[9 * 32 + n] = static_cast<float>(tot);
+  }
+  return out;
+}
+cudaError_t launch_stem_tc(StemTcParams P, int num_sms, cudaStream_t st, bool pdl) {
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStcSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_done[dev & 63] = true;
+  }
+  P.tiles_x = cdiv(P.Wo, kStcTW); P.tiles_y = cdiv(P.Ho, kStcTH); P.num_tiles = P.B * P.tiles_x * P.tiles_y;
+  const int grid = P.num_tiles < num_sms ? P.num_tiles : num_sms;
+  return launch_pdl(pdl, stem_tc_kernel, dim3(grid), dim3(kStcThreads), kStcSmemBytes, st, P);
 }
 // Keras 3x3 kernel [3][3][32][64] -> bf16 [9 taps][64 cout][32 cin]
 std::vector<uint16_t> pack_c3(const float* w) {
@@ -977,6 +1034,7 @@ int dlv3p_model_finalize_weights(dlv3p_model* m) {
       const float* k = MW(m, o.name, "kernel");
       std::vector<float> w(k, k + 27 * 32);
       if ((r = m_upload(m, &o.wf, w))) return r;
+      if ((r = m_upload(m, &o.w16, pack_stem_tc(k))) || (r = m_upload(m, &o.dshift, stem_tap_sums(k)))) return r;      // tensor-core stem (uint8 images)
       Fold f = mfold(m, o.bn, 32);
       if ((r = m_upload(m, &o.scale, f.scale)) || (r = m_upload(m, &o.shift, f.shift))) return r;
     } else if (o.kind == OP_CONV3) {
@@ -1114,7 +1172,14 @@ static int run_backbone(dlv3p_model* m, const void* d_images, cudaStream_t st, i
       StemParams P{};
       P.img = d_images; P.img_f32 = g.img_dtype == DLV3P_IMG_F32; P.w = o.wf; P.scale = o.scale; P.shift = o.shift; P.out = to.p;
       P.B = g.B; P.H = g.H; P.W = g.W; P.Ho = to.H; P.Wo = to.W; P.pad_t = m->pad_t; P.pad_l = m->pad_l;
-      e = launch_stem(P, m->num_sms, st, g_pdl);
+      if (g.img_dtype == DLV3P_IMG_F32 || (g.flags & DLV3P_MODEL_FLAG_FP32_STEM)) {
+        e = launch_stem(P, m->num_sms, st, g_pdl);      // fp32 FMAs on normalised pixels (float images; A/B flag)
+      } else {
+        StemTcParams Q{};
+        Q.img = static_cast<const uint8_t*>(d_images); Q.w16 = o.w16; Q.wk = o.dshift; Q.scale = o.scale; Q.shift = o.shift; Q.out = to.p;
+        Q.B = g.B; Q.H = g.H; Q.W = g.W; Q.Ho = to.H; Q.Wo = to.W; Q.pad_t = m->pad_t; Q.pad_l = m->pad_l;
+        e = launch_stem_tc(Q, m->num_sms, st, g_pdl);
+      }
     } else if (o.kind == OP_CONV3) {
       const Tensor& to = m->tensors[o.out];
       Conv3x3Params P{};
@@ -1585,7 +1650,17 @@ int dlv3p_op_stem_conv(int device, const void* img, int img_dtype, int B, int H,
   P.B = B; P.H = H; P.W = W; P.Ho = cdiv(H, 2); P.Wo = cdiv(W, 2);
   P.pad_t = std::max((P.Ho - 1) * 2 + 3 - H, 0) / 2;
   P.pad_l = std::max((P.Wo - 1) * 2 + 3 - W, 0) / 2;
-  MCU(nullptr, launch_stem(P, sms, st, false));
+  if (P.img_f32) {
+    MCU(nullptr, launch_stem(P, sms, st, false));
+  } else {
+    uint16_t* d16 = tmp.put(pack_stem_tc(w_hwio));
+    float* dwk = tmp.put(stem_tap_sums(w_hwio));
+    if (!d16 || !dwk) return mfail(nullptr, DLV3P_ERR_NOMEM, "op_stem_conv: cudaMalloc failed");
+    StemTcParams Q{};
+    Q.img = static_cast<const uint8_t*>(img); Q.w16 = d16; Q.wk = dwk; Q.scale = ds; Q.shift = dt; Q.out = static_cast<__nv_bfloat16*>(out);
+    Q.B = B; Q.H = H; Q.W = W; Q.Ho = P.Ho; Q.Wo = P.Wo; Q.pad_t = P.pad_t; Q.pad_l = P.pad_l;
+    MCU(nullptr, launch_stem_tc(Q, sms, st, false));
+  }
   MCU(nullptr, cudaStreamSynchronize(st));
   return DLV3P_OK;
 }

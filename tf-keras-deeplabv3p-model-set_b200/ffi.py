@@ -48,6 +48,7 @@ MODEL_FLAG_NO_PDL = 2
 MODEL_FLAG_UNFUSED_ENTRY = 4
 MODEL_FLAG_FP32 = 8
 MODEL_FLAG_FUSED_MIDDLE = 16
+MODEL_FLAG_FP32_STEM = 32
 
 # every symbol include/dlv3p.h declares: (name, restype, argtypes)
 _vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
