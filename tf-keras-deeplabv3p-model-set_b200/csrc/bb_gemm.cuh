@@ -198,6 +198,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBbThreads, 1) bb_ge
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      // the TMEM load of the next 32 columns is in flight while the current 32 are scaled, rounded and staged
+      uint32_t vbuf[2][32];
+      tmem_ld_32x32b_x32(taddr, vbuf[0]);
+      tmem_ld_wait();
 #pragma unroll 1
       for (int cb = 0; cb < nblk; ++cb) {
         if (lane == 0) tma_store_wait_read<1>();
@@ -208,9 +212,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBbThreads, 1) bb_ge
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int c0 = cb * 64 + half * 32;
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(taddr + c0, v);
-          tmem_ld_wait();
+          uint32_t (&v)[32] = vbuf[half];
+          if (half == 0) tmem_ld_32x32b_x32(taddr + c0 + 32, vbuf[1]);
+          else if (cb + 1 < nblk) tmem_ld_32x32b_x32(taddr + c0 + 32, vbuf[0]);
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             const ulonglong2 s0 = *reinterpret_cast<const ulonglong2*>(s_scale + c0 + j);
@@ -238,6 +242,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBbThreads, 1) bb_ge
             }
             sts_v4(cbuf + chunk * 16, make_uint4(f32x2_to_bf16x2(y0), f32x2_to_bf16x2(y1), f32x2_to_bf16x2(y2), f32x2_to_bf16x2(y3)));
           }
+          tmem_ld_wait();      // the load issued at the top of this half
         }
         fence_proxy_async_smem();
         __syncwarp();
