@@ -72,14 +72,14 @@ NCU_DRAM_MB_PER_LAUNCH_B32 = {
 
 # DRAM traffic per step (dram__bytes_read.sum + dram__bytes_write.sum summed over a kernel function's launches, bytes) from one
 # `ncu --set full` capture of this command at batch 32; filled in from profiles/ once captured
-NCU_TRAFFIC = {   # profiles/r02w_ncu_per_kernel_dram_and_time.txt (every template variant of a function summed over one step, MB)
-    'bb_gemm_kernel': 5766.3 * 1e6,
-    'bb_depthwise_kernel': 4498.7 * 1e6,
-    'bb_sepconv_kernel': 2607.2 * 1e6,
-    'conv3x3_c32_kernel': 340.6 * 1e6,
-    'stem_conv_kernel': 97.7 * 1e6,
+NCU_TRAFFIC = {   # profiles/r03g_ncu_per_kernel_dram_and_time.txt (every template variant of a function summed over one step, MB)
+    'bb_gemm_kernel': 5831.7 * 1e6,
+    'bb_depthwise_kernel': 4503.6 * 1e6,
+    'bb_sepconv_kernel': 2606.3 * 1e6,
+    'conv3x3_c32_kernel': 340.2 * 1e6,
+    'stem_tc_kernel': 98.7 * 1e6,
 }
-NCU_TRAFFIC_NOTE = 'bytes per step (dram__bytes_read.sum + dram__bytes_write.sum over the function\'s launches of one forward, ncu, cold caches: profiles/r02w_ncu_per_kernel_dram_and_time.txt)'
+NCU_TRAFFIC_NOTE = 'bytes per step (dram__bytes_read.sum + dram__bytes_write.sum over the function\'s launches of one forward, ncu, cold caches: profiles/r03g_ncu_per_kernel_dram_and_time.txt)'
 
 # algorithmic HBM bytes per image of the fused SepConv kernels (read the input once, write the 256-channel output once)
 ALGO_BYTES_PER_IMG = {
@@ -286,7 +286,7 @@ def time_train_step(rank, world, local_rank, steps=10, warmup=3, batch=8):
 
 
 KERNEL_OF = [('_shortcut_sample', 'subsample2_kernel'), ('_sepconv', 'bb_sepconv_kernel'), ('_depthwise', 'bb_depthwise_kernel'), ('_pointwise', 'bb_gemm_kernel'),
-             ('_shortcut', 'bb_gemm_kernel'), ('entry_flow_conv1_1', 'stem_conv_kernel'), ('entry_flow_conv1_2', 'conv3x3_c32_kernel')]
+             ('_shortcut', 'bb_gemm_kernel'), ('entry_flow_conv1_1', 'stem_tc_kernel'), ('entry_flow_conv1_2', 'conv3x3_c32_kernel')]
 HEAD_GEMMS = ('aspp_branches_gemm', 'concat_projection_gemm', 'feature_projection0_gemm', 'decoder_conv0_sepconv', 'decoder_conv1_sepconv', 'classifier_gemm')
 
 

@@ -15,7 +15,8 @@ HOT = [  # (file stem, substrings the demangled name must contain)
     ('bb_depthwise_kernel_s1_r1', ['bb_depthwise_kernel<(int)1, (int)1, (int)8, (int)32>']),
     ('bb_sepconv_kernel_kb2_n128', ['bb_sepconv_kernel<(int)2, (int)128']),
     ('conv3x3_c32_kernel', ['conv3x3_c32_kernel']),
-    ('stem_conv_kernel', ['stem_conv_kernel<(bool)1>']),
+    ('stem_tc_kernel', ['stem_tc_kernel']),
+    ('stem_conv_kernel', ['stem_conv_kernel<(bool)0>']),
     ('pw_gemm2_kernel', ['dlv3p::pw_gemm2_kernel']),
     ('dwpw_gemm2_kernel_kb5', ['dwpw_gemm2_kernel<(int)5>']),
     ('aspp_dw_fast3_kernel_32', ['aspp_dw_fast3_kernel<(int)32, (int)32, (int)6>']),
