@@ -29,9 +29,12 @@ def _one_rounding(got_bits, ref64, what):
 
 
 # ---------------------------------------------------------------------------------------------------- single operators
-@pytest.mark.parametrize('H,W,dtype', [(64, 64, np.uint8), (37, 51, np.uint8), (32, 48, np.float32)])
+@pytest.mark.parametrize('H,W,dtype', [(64, 64, np.uint8), (37, 51, np.uint8), (32, 48, np.float32), (16, 16, np.uint8), (18, 131, np.uint8), (7, 9, np.uint8),
+                                       (512, 512, np.uint8), (33, 40, np.float32)])
 def test_stem_conv(gpu, H, W, dtype):
-    """entry_flow_conv1_1: normalize_image + Conv2D(32, 3, strides 2, 'same') + BN + ReLU; TensorFlow 'same' pads (0,1) on even sizes."""
+    """entry_flow_conv1_1: normalize_image + Conv2D(32, 3, strides 2, 'same') + BN + ReLU; TensorFlow 'same' pads (0,1) on even sizes, (1,1) on odd
+    ones.  uint8 images: the tensor-core kernel (space-to-depth taps, three bf16 weight pieces, border-aware normalisation in the epilogue);
+    float images: the fp32 CUDA-core kernel.  Both against float64 to one bf16 rounding; partial tiles, images smaller than a tile."""
     import torch
     import torch.nn.functional as F
     rng = np.random.default_rng(H * W)
