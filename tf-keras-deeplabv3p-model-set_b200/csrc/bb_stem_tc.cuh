@@ -13,9 +13,9 @@
 // What differs from the fp32 kernel is the order of the fp32 accumulation (tensor core vs tap order): ~1e-6 relative before the bf16 rounding.
 //
 //   warp 0        MMA issuer: per tile 3 pieces x 4 taps = 12 tcgen05.mma 128 x 32 x 16; the four taps are descriptors shifted inside ONE
-//                 17 x 9 s2d halo tile (no-swizzle K-major core matrices: 8 pixels x 16 bytes, atoms one halo row = 144 bytes apart)
+//                 17 x 9 s2d halo tile (32-byte rows under the 32-byte swizzle, atoms one halo row = 288 bytes apart)
 //   warps 1..4    epilogue: tcgen05.ld -> normalise -> BN -> ReLU -> bf16 -> 64 bytes per pixel
-//   warps 5..12   builders, one pipeline stage each: image bytes -> bf16 s2d halo tile in the core-matrix layout (60 independent byte loads per lane)
+//   warps 5..12   builders, one pipeline stage each: image bytes -> bf16 s2d halo tile in the swizzled operand layout
 #pragma once
 
 #include <cuda.h>
@@ -29,12 +29,11 @@ constexpr int kStcSub = 1;                                   // M = 128 sub-tile
 constexpr int kStcTH = 16, kStcTW = 8 * kStcSub;
 constexpr int kStcHaloH = kStcTH + 1, kStcHaloW = kStcTW + 1;
 constexpr int kStcPix = kStcHaloH * kStcHaloW;               // 153 s2d pixels per tile
-constexpr int kStcPlaneBytes = kStcPix * 16;                 // k 0..7 | k 8..15 of every s2d pixel: two planes of 16-byte rows
-constexpr int kStcStageBytes = (2 * kStcPlaneBytes + 127) / 128 * 128;
+constexpr int kStcStageBytes = (kStcPix * 32 + 255) / 256 * 256;      // one 32-byte row (K = 16 bf16) per s2d pixel, 32-byte swizzle (256-byte pattern)
 constexpr int kStcStages = 8;
 constexpr int kStcBuilders = kStcStages;
 constexpr int kStcThreads = (1 + 4 + kStcBuilders) * 32;
-constexpr int kStcWBytes = 3 * 4 * 1024;                     // [piece][tap][k chunk][32 out][8 bf16]
+constexpr int kStcWBytes = 3 * 4 * 1024;                     // [piece][tap][32 out][16 k] bf16, 32-byte swizzle applied by the host
 constexpr int kStcRawRows = 2 * kStcHaloH;                   // image rows under a tile's s2d halo
 constexpr int kStcRawChunks = (2 * kStcHaloW * 3 + 15 + 15) / 16;     // 16-byte chunks that cover a row's 2 (TW + 1) pixels at any alignment
 constexpr int kStcRawRowBytes = kStcRawChunks * 16;
@@ -52,15 +51,18 @@ struct StemTcParams {
   int tiles_x, tiles_y, num_tiles;
 };
 
-// K-major operand without swizzle: core matrices of 8 rows x 16 bytes (128 contiguous bytes); `k_stride` bytes between the two core matrices of a
-// K = 16 step, `mn_stride` bytes between consecutive 8-row groups
-__device__ __forceinline__ uint64_t make_smem_desc_noswz(uint32_t smem_addr_bytes, uint32_t k_stride, uint32_t mn_stride) {
+// K-major operand of 32-byte rows (one K = 16 step) under the 32-byte swizzle: the two 16-byte halves of a row swap where address bit 7 is set;
+// eight-row atoms `atom_stride` bytes apart.  Like the 64-byte swizzle of bb_conv3x3.cuh the pattern is a function of the absolute shared-memory
+// address, so a descriptor may start at any row of a tile that was WRITTEN with the same rule.  (Without a swizzle — core matrices of 8 x 16
+// bytes, atoms 144 bytes apart — the kernel was correct but its operand fetches conflicted in shared memory: 58 % of all wavefronts.)
+__device__ __forceinline__ uint64_t make_smem_desc_sw32(uint32_t smem_addr_bytes, uint32_t atom_stride) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr_bytes >> 4) & 0x3FFF);
-  d |= static_cast<uint64_t>((k_stride >> 4) & 0x3FFF) << 16;      // leading-dimension byte offset
-  d |= static_cast<uint64_t>((mn_stride >> 4) & 0x3FFF) << 32;     // stride-dimension byte offset
+  d |= static_cast<uint64_t>(1) << 16;                             // leading-dimension byte offset: unused (one swizzle row per K step)
+  d |= static_cast<uint64_t>((atom_stride >> 4) & 0x3FFF) << 32;   // stride-dimension byte offset
   d |= static_cast<uint64_t>(1) << 46;                             // descriptor version
-  return d;                                                        // layout type 0: no swizzle
+  d |= static_cast<uint64_t>(6) << 61;                             // SWIZZLE_32B
+  return d;
 }
 
 __global__ void __launch_bounds__(kStcThreads, 1) stem_tc_kernel(const __grid_constant__ StemTcParams P) {
@@ -133,8 +135,8 @@ __global__ void __launch_bounds__(kStcThreads, 1) stem_tc_kernel(const __grid_co
           for (int piece = 0; piece < 3; ++piece)
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-              const uint64_t da = make_smem_desc_noswz(a0 + ((t >> 1) * kStcHaloW + 8 * sub + (t & 1)) * 16, kStcPlaneBytes, kStcHaloW * 16);
-              const uint64_t db = make_smem_desc_noswz(smem_u32(smem_w) + (piece * 4 + t) * 1024, 512, 128);
+              const uint64_t da = make_smem_desc_sw32(a0 + ((t >> 1) * kStcHaloW + 8 * sub + (t & 1)) * 32, kStcHaloW * 32);
+              const uint64_t db = make_smem_desc_sw32(smem_u32(smem_w) + (piece * 4 + t) * 1024, 256);
               umma_bf16_ss(tmem_d, da, db, idesc, (piece > 0 || t > 0) ? 1u : 0u);
             }
         }
@@ -273,8 +275,9 @@ __global__ void __launch_bounds__(kStcThreads, 1) stem_tc_kernel(const __grid_co
 #pragma unroll
           for (int j = 0; j < 6; ++j)                      // bf16 bits of an integer 0..255: the upper half of its fp32 pattern, exact
             wds[j] = (__float_as_uint(static_cast<float>(val[2 * j])) >> 16) | (__float_as_uint(static_cast<float>(val[2 * j + 1])) & 0xFFFF0000u);
-          sts_v4(st + p * 16, make_uint4(wds[0], wds[1], wds[2], wds[3]));
-          sts_v4(st + kStcPlaneBytes + p * 16, make_uint4(wds[4], wds[5], 0u, 0u));
+          const uint32_t row = st + p * 32, flip = (row >> 3) & 16u;      // 32-byte swizzle: halves swap where address bit 7 is set
+          sts_v4(row + flip, make_uint4(wds[0], wds[1], wds[2], wds[3]));
+          sts_v4(row + (flip ^ 16u), make_uint4(wds[4], wds[5], 0u, 0u));
         }
       }
       fence_proxy_async_smem();                          // generic-proxy stores -> visible to the tensor core's reads

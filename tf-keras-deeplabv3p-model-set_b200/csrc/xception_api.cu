@@ -294,7 +294,7 @@ std::vector<float> pack_taps(const float* w_hwc, const float* scale, int C, int 
   return out;
 }
 // entry_flow_conv1_1 for the tensor-core stem (bb_stem_tc.cuh): Keras kernel [3][3][3][32] fp32 -> three bf16 pieces of every weight (w0 + w1 + w2 == w
-// exactly), laid out [piece][s2d tap (ty, tx)][k chunk][32 cout][8 k] with k = (dy, dx, cin), conv tap (2 ty + dy, 2 tx + dx); and the per-tap channel
+// exactly), laid out [piece][s2d tap (ty, tx)][32 cout][16 k] (32-byte swizzle) with k = (dy, dx, cin), conv tap (2 ty + dy, 2 tx + dx); and the per-tap channel
 // sums [9][32] + their total [32] the epilogue subtracts (conv(x / 127.5 - 1) = conv(x) / 127.5 - sum of the weights of the taps inside the image)
 float bf16_to_f32_host(uint16_t b) {
   const uint32_t u = static_cast<uint32_t>(b) << 16;
@@ -315,7 +315,8 @@ std::vector<uint16_t> pack_stem_tc(const float* w) {
             float rem = w[((ky * 3 + kx) * 3 + c) * 32 + n];
             for (int piece = 0; piece < 3; ++piece) {
               const uint16_t b = bf16_rne(rem);
-              out[((((static_cast<size_t>(piece) * 4 + t) * 2 + (k >> 3)) * 32 + n) * 8) + (k & 7)] = b;
+              // [piece][tap][cout n][16 k], 32-byte rows with the two 16-byte halves swapped where bit 7 of the row's offset is set (n & 4)
+              out[((static_cast<size_t>(piece) * 4 + t) * 32 + n) * 16 + ((((k >> 3) ^ ((n >> 2) & 1)) << 3) | (k & 7))] = b;
               rem -= bf16_to_f32_host(b);      // exact: the difference of a float and its bf16 rounding is a float
             }
           }
