@@ -233,6 +233,9 @@ int dlv3p_op_mask_resize_nearest(int device, const uint8_t* d_mask, int B, int h
  * coefficients normalised and rounded to 22-bit fixed point on the host, horizontal pass first into a uint8 intermediate, each pass
  * clip8((2^21 + sum) >> 22).  Integer work, bit exact against PIL (tests).  SYNCHRONOUS: coefficient tables and the intermediate
  * image are allocated, used and freed inside the call (a pre-processing step, not part of the forward). */
+/* The coefficient tables dlv3p_op_resize_bicubic_u8 builds for one axis (host arithmetic only, no device needed; parity tests on a CPU box):
+ * bounds[2 * out_size] = {first input index, tap count} per output index, kk[out_size * *ksize] = 22-bit fixed-point taps, zero padded. */
+int dlv3p_pil_bicubic_coeffs(int in_size, int out_size, int* bounds, int* kk, int kk_capacity, int* ksize);
 int dlv3p_op_resize_bicubic_u8(int device, const uint8_t* d_img, int B, int H, int W, int C, int ho, int wo, uint8_t* d_out, void* cuda_stream);
 
 /* Present-class set of the native post-process (inference/MNN/deeplabSegment.cpp:171-172: class_indexes, the non-background classes

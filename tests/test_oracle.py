@@ -183,3 +183,14 @@ def test_present_classes_follow_the_raster_order_of_the_native_postprocess():
             literal.append(int(v))
     assert R.present_classes(mask) == literal and literal[0] == 7
     assert R.present_classes(np.zeros((4, 4), np.uint8)) == []
+
+
+@pytest.mark.parametrize('n_in,n_out', [(64, 32), (37, 64), (375, 512), (500, 512), (512, 300), (9, 40), (7, 3), (300, 31), (2048, 512), (1, 5), (5, 1)])
+def test_library_bicubic_coefficients_equal_the_restatement(n_in, n_out):
+    """The host half of dlv3p_op_resize_bicubic_u8 (double arithmetic, 22-bit fixed point) needs no GPU: its tables against the oracle's
+    restatement of Pillow's precompute_coeffs / normalize_coeffs_8bpc, integer for integer."""
+    from dlv3p_b200 import ffi
+    bounds, kk = ffi.pil_bicubic_coeffs(n_in, n_out)
+    rb, rk = R._pil_bicubic_coeffs(n_in, n_out)
+    assert np.array_equal(bounds, np.asarray(rb, np.int32))
+    assert kk.shape == rk.shape and np.array_equal(kk, rk.astype(np.int32))

@@ -1795,6 +1795,16 @@ int pil_coeffs(int in_size, int out_size, std::vector<int>* bounds, std::vector<
 }
 }  // namespace
 
+int dlv3p_pil_bicubic_coeffs(int in_size, int out_size, int* bounds, int* kk, int kk_capacity, int* ksize) {
+  if (in_size < 1 || out_size < 1 || !bounds || !kk || !ksize) return fail(nullptr, DLV3P_ERR_INVALID, "pil_bicubic_coeffs: bad arguments");
+  std::vector<int> b, k;
+  *ksize = pil_coeffs(in_size, out_size, &b, &k);
+  if (static_cast<size_t>(kk_capacity) < k.size()) return fail(nullptr, DLV3P_ERR_INVALID, "pil_bicubic_coeffs: kk_capacity < out_size * ksize");
+  std::memcpy(bounds, b.data(), b.size() * sizeof(int));
+  std::memcpy(kk, k.data(), k.size() * sizeof(int));
+  return DLV3P_OK;
+}
+
 int dlv3p_op_resize_bicubic_u8(int device, const uint8_t* d_img, int B, int H, int W, int C, int ho, int wo, uint8_t* d_out, void* cuda_stream) {
   int sms = 0, r = op_prolog(device, &sms);
   if (r) return r;

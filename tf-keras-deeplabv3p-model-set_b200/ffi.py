@@ -92,6 +92,7 @@ SYMBOLS = [
     ('dlv3p_op_denormalize_image', _i, [_i, _vp, C.c_int64, _vp, _vp]),
     ('dlv3p_op_mask_resize_nearest', _i, [_i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     ('dlv3p_op_resize_bicubic_u8', _i, [_i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    ('dlv3p_pil_bicubic_coeffs', _i, [_i, _i, _vp, _vp, _i, _vp]),
     ('dlv3p_op_present_classes', _i, [_i, _vp, _i, C.c_int64, _vp, _vp]),
     ('dlv3p_op_bn_scratch_bytes', C.c_size_t, [_i]),
     ('dlv3p_op_bn_stats', _i, [_i, _vp, C.c_int64, _i, _vp, _vp, _vp]),
@@ -626,6 +627,18 @@ def op_resize_bicubic(image: np.ndarray, size_hw: Tuple[int, int], device=0) -> 
     _check(load_library().dlv3p_op_resize_bicubic_u8(device, din.ptr, B, H, W, Cc, ho, wo, dout.ptr, None))
     synchronize(device)
     return dout.download(a.shape[:-3] + (ho, wo, Cc), np.uint8)
+
+
+def pil_bicubic_coeffs(in_size: int, out_size: int):
+    """(bounds [out_size, 2], kk [out_size, ksize]) of one resampling axis as the library computes them on the host (no GPU needed)."""
+    import math
+    ks = int(math.ceil(2.0 * max(in_size / out_size, 1.0))) * 2 + 1
+    bounds = np.zeros((out_size, 2), np.int32)
+    kk = np.zeros((out_size, ks), np.int32)
+    ksize = C.c_int()
+    _check(load_library().dlv3p_pil_bicubic_coeffs(in_size, out_size, bounds.ctypes.data_as(C.c_void_p), kk.ctypes.data_as(C.c_void_p), kk.size, C.byref(ksize)))
+    assert ksize.value == ks
+    return bounds, kk
 
 
 def op_present_classes(labels: np.ndarray, device=0) -> List[List[int]]:
